@@ -1,0 +1,167 @@
+/* kgeb200 -- C-ABI of the B200-native (sm_100a) LibKGE scoring/embedding hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (void* = cudaStream_t;
+ * NULL = legacy default stream) and returns an int status (KGEB_OK / KGEB_ERR_*); the text of the
+ * last failure on the calling thread is returned by kgeb_last_error().  No torch types appear in
+ * any signature.  All matrices are row-major, contiguous fp32; index arrays are int32 or int64
+ * (flag idx64), matching the reference (int64 in training, train.py:622,811,1022; int32 in
+ * evaluation, dataset.py:178 / entity_ranking.py:76).  A NULL index pointer means "row i".
+ *
+ * Each function cites the reference interface (file:line under Nzteb/kge-1) it replaces.
+ * The reference is pure Python/PyTorch, so the binding a maintainer adds is a ctypes stub; it is
+ * shown in INTEGRATION.md and implemented in kge-1_b200/lib.py.
+ */
+#ifndef KGEB200_H
+#define KGEB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGEB_OK 0
+#define KGEB_ERR_ARG 1         /* bad argument -> ValueError in the binding */
+#define KGEB_ERR_CUDA 2        /* CUDA runtime / driver error -> RuntimeError */
+#define KGEB_ERR_UNSUPPORTED 3 /* valid in the reference, not built here -> NotImplementedError */
+
+/* kge/model/{distmult,complex,cp,simple,rescal,transe,rotate}.py */
+enum { KGEB_DISTMULT = 0, KGEB_COMPLEX = 1, KGEB_CP = 2, KGEB_SIMPLE = 3, KGEB_RESCAL = 4,
+       KGEB_TRANSE = 5, KGEB_ROTATE = 6 };
+/* combine= of RelationalScorer.score_emb (kge_model.py:120-182) */
+enum { KGEB_SP_ = 0, KGEB__PO = 1 };
+/* score of one (query vector q, candidate row c) pair -- SURVEY.md Appendix D:
+ *   DOT    sum_k q_k c_k                 (DistMult, ComplEx, CP, SimplE, RESCAL)
+ *   NEG_L1 -sum_k |q_k - c_k|            (TransE l_norm=1, transe.py:19-21)
+ *   NEG_L2 -sqrt(sum_k (q_k - c_k)^2)    (TransE l_norm=2)
+ *   ROT_L1 +sum_{k<d/2} |q_k - c_k|_C    (RotatE l_norm=1, rotate.py:41-60; positive distance)
+ *   ROT_L2 +sqrt(sum_{k<d/2} |q_k - c_k|_C^2)                                              */
+enum { KGEB_DOT = 0, KGEB_NEG_L1 = 1, KGEB_NEG_L2 = 2, KGEB_ROT_L1 = 3, KGEB_ROT_L2 = 4 };
+/* kge/util/loss.py: KLDivWithSoftmaxKgeLoss (192-213), BCEWithLogitsKgeLoss bce_type=None (137-159) */
+enum { KGEB_LOSS_KL = 0, KGEB_LOSS_BCE = 1 };
+/* arithmetic of the all-entity DOT tiles */
+enum { KGEB_MATH_FP32 = 0,   /* CUDA-core FFMA, fp32 exact-order-free (1e-5 bar)              */
+       KGEB_MATH_TF32 = 1 }; /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (looser bound) */
+
+const char* kgeb_last_error(void);
+/* library build info: returns the compiled arch (100) and writes a version string */
+int kgeb_version(char* buf, int buflen);
+
+/* ---- a1/K1: LookupEmbedder.embed (embedder/lookup_embedder.py:91-92): out[i,:] = W[idx[i],:] ---- */
+int kgeb_gather_rows(const float* W, int64_t vocab, int dim, const void* idx, int idx64, int64_t n,
+                     float* out, void* stream);
+
+/* ---- a4/K5: score_emb(..., "spo") for the seven scorers, fused with the three gathers.
+ * x_src point at [vocab,d] tables (with x_idx) or at [n,d] embedding matrices (x_idx NULL).
+ * p rows have relation_dim(model,d) columns (d, d/2 for CP/RotatE, d*d for RESCAL).
+ * l_norm in {1,2} (TransE/RotatE).  TransE adds eps=1e-6 to the difference (pairwise_distance). */
+int kgeb_score_spo(int model, int l_norm, const float* s_src, const void* s_idx, const float* p_src,
+                   const void* p_idx, const float* o_src, const void* o_idx, int idx64, int64_t n, int d,
+                   float* out, void* stream);
+/* autograd of the above (reference: ATen backward of the expressions in <model>.py); writes per-row
+ * gradients ds[n,d], dp[n,dr], do[n,d] (not accumulated; scatter them with kgeb_scatter_add_rows). */
+int kgeb_score_spo_bwd(int model, int l_norm, const float* s_src, const void* s_idx, const float* p_src,
+                       const void* p_idx, const float* o_src, const void* o_idx, int idx64, int64_t n,
+                       int d, const float* gout, float* ds, float* dp, float* d_o, void* stream);
+
+/* ---- query transform of the sp_/_po forms (<model>.py score_emb "sp_"/"_po"):
+ * Q[i,:] = q(a_i, p_i), a = s for KGEB_SP_, a = o for KGEB__PO; Q is [n,d].  */
+int kgeb_query_build(int model, int combine, const float* a_src, const void* a_idx, const float* p_src,
+                     const void* p_idx, int idx64, int64_t n, int d, float* Q, void* stream);
+/* chain rule dQ -> da[n,d], dp[n,dr] */
+int kgeb_query_bwd(int model, int combine, const float* a_src, const void* a_idx, const float* p_src,
+                   const void* p_idx, int idx64, int64_t n, int d, const float* dQ, float* da, float* dp,
+                   void* stream);
+
+/* ---- negative-sampling pair scoring (train.py:872-893 "triple" implementation without the
+ * B*(1+N) expansion): out[i,j] = pair_score(kind, Q[i,:], table[cand[i,j],:]), cand is [B,M]. */
+int kgeb_pairs_score(int kind, const float* Q, const float* table, const void* cand, int idx64, int64_t B,
+                     int64_t M, int d, float* out, void* stream);
+/* backward: G[B,M] = dL/dout -> dQ[B,d] and per-pair candidate gradients dC[B*M,d] */
+int kgeb_pairs_bwd(int kind, const float* Q, const float* table, const void* cand, int idx64, int64_t B,
+                   int64_t M, int d, const float* G, const float* scores, float* dQ, float* dC, void* stream);
+
+/* ---- a5/a6/K4/K6/K7: score_emb(..., "sp_"|"_po") materialised:
+ * out[i*ld + col_off + j] = pair_score(kind, Q[i,:], table[cand_idx ? cand_idx[j] : j, :]), j < m.
+ * math = KGEB_MATH_FP32 | KGEB_MATH_TF32 (TF32 only for KGEB_DOT). */
+int kgeb_score_all(int kind, int math, const float* Q, int64_t B, int d, const float* table,
+                   const void* cand_idx, int idx64, int64_t m, float* out, int64_t ld, int64_t col_off,
+                   void* stream);
+/* backward of the materialised form: G is [B, ld] (columns col_off..col_off+m used), X the forward
+ * scores (needed by the L2 kinds).  dQ[B,d] is overwritten, dC[m,d] overwritten (row j = candidate j). */
+int kgeb_score_all_bwd(int kind, const float* Q, int64_t B, int d, const float* table, const void* cand_idx,
+                       int idx64, int64_t m, const float* G, const float* X, int64_t ld, int64_t col_off,
+                       float* dQ, float* dC, void* stream);
+
+/* ---- K4+K8+K9 fused all-entity training (DOT kinds): scores are never materialised.
+ * Labels are a CSR over the batch rows: lab_off[B+1] (int64), lab_col[nnz] (int64, ascending within a
+ * row, entity ids).  For 1vsAll each row has exactly one label.  Targets t_ij:
+ *   BCE: t = (1-ls)*y + ls_add           (train.py:715-721; ls_add = 1/E when ls>0 else 0)
+ *   KL : t = normalize_L1((1-ls)*y + ls_add) (loss.py:211-213), index labels = one-hot
+ * Entities [e_lo, e_hi) of `table` (row e of table = entity e_lo + e .. the table pointer is the shard's
+ * first row) are scored; num_entities is the global E (for ls_add and KL normalisation).
+ * fwd: per-row statistics of this shard, rowstat[i*4 + k]:
+ *   k=0  KL : max_j x_ij                         BCE: sum_j softplus(x_ij + offset)
+ *   k=1  KL : sum_j exp(x_ij - max)              BCE: unused
+ *   k=2  sum_j (x_ij [+ offset for BCE])         (dense part of the target, label smoothing)
+ *   k=3  sum over the row's label entries in this shard of (x_ij [+ offset for BCE])
+ *   from which the caller forms the loss (kge-1_b200/fused.py) and, across shards, the global
+ *   log-sum-exp.  KL with label_smoothing != 0 returns KGEB_ERR_UNSUPPORTED.
+ * bwd: G_ij = inv_batch * (softmax_ij * tsum_i - t_ij)  (KL, lse[i] = global log-sum-exp)
+ *      G_ij = inv_batch * (sigmoid(x_ij + offset) - t_ij) (BCE);
+ *   dQ[B,d] = G * table (overwritten with this shard's partial), dTable[e,:] += G^T Q.      */
+int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
+                   int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
+                   float label_smoothing, float offset, float* rowstat /*[B,4]*/, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
+                   int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
+                   float label_smoothing, float offset, const float* lse /*[B] (KL)*/, float inv_batch,
+                   const float* row_scale /*[B] per-row factor multiplied into G (upstream gradient), or NULL*/, float* dQ, float* dTable,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities);
+
+/* ---- a23-a26/K10: fused score-and-count for filtered entity ranking (entity_ranking.py:153-217,
+ * 469-529).  Q is [nq,d] (callers stack the B sp_ queries and the B _po queries).  For query i the
+ * candidate true_ent[i] takes the precomputed true_score[i] (entity_ranking.py:170-177); NaN -> -inf
+ * on both sides; filt CSR (offsets int64 [nq+1], cols int64 ascending per row) lists known answers of
+ * the filter splits, test CSR those of the test split (may be NULL); the row's own true entity is
+ * never filtered (entity_ranking.py:189-193); filters are cumulative (208-210).
+ * counts[i*6 + {0,1}] = (rank, ties) raw, {2,3} filtered, {4,5} filtered-with-test; int64, ADDED to
+ * the existing contents so that entity shards / chunks accumulate. */
+int kgeb_rank_count(int kind, int math, const float* Q, int64_t nq, int d, const float* table, int64_t e_lo,
+                    int64_t e_hi, const float* true_score, const void* true_ent, int idx64,
+                    const int64_t* filt_off, const int64_t* filt_col, const int64_t* test_off,
+                    const int64_t* test_col, int64_t* counts, void* stream);
+
+/* ---- a3/K3: deterministic sort-based segment scatter-add (autograd of nn.Embedding,
+ * lookup_embedder.py:39-41,91-92).  rows[n,d] are summed per distinct idx in ascending original
+ * position order and ADDED into dense[vocab,d].  workspace from kgeb_scatter_workspace_bytes(n). */
+int64_t kgeb_scatter_workspace_bytes(int64_t n);
+int kgeb_scatter_add_rows(const void* idx, int idx64, const float* rows, int64_t n, int d, float* dense,
+                          int64_t vocab, void* workspace, int64_t workspace_bytes, void* stream);
+/* sparse form (lookup_embedder.yaml sparse: True): returns distinct ids (ascending) + summed rows */
+int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int64_t n, int d,
+                             int64_t* uniq_ids /*[n]*/, float* uniq_rows /*[n,d]*/, int64_t* num_uniq /*dev*/,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- a21/K11: optimizer steps with torch.optim semantics (util/optimizer.py:10-17).
+ * Adagrad: g += wd*w; state += g*g; w -= clr * g / (sqrt(state) + eps), clr = lr/(1+(step-1)*lr_decay) */
+int kgeb_adagrad_dense(float* W, float* state, const float* grad, int64_t numel, float clr, float eps,
+                       float weight_decay, void* stream);
+/* touched-rows-only Adagrad (equals the dense step when untouched rows have zero gradient and wd=0) */
+int kgeb_adagrad_rows(float* W, float* state, const int64_t* row_ids, const float* row_grads,
+                      const int64_t* num_rows_dev, int64_t max_rows, int d, float clr, float eps, void* stream);
+/* Adam (torch.optim.Adam, amsgrad=False): bias corrections computed by the caller */
+int kgeb_adam_dense(float* W, float* exp_avg, float* exp_avg_sq, const float* grad, int64_t numel, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2,
+                    void* stream);
+
+/* ---- a28/8f-1: device-side CSR key lookup over KvsAllIndex arrays (indexing.py:36-55):
+ * keys[K,2] sorted lexicographically (int64); for each query pair finds its row or -1. */
+int kgeb_csr_lookup(const int64_t* keys, int64_t num_keys, const int64_t* query_pairs, int64_t n,
+                    int64_t* row_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGEB200_H */

@@ -1,0 +1,64 @@
+// Shared device/host helpers for the kgeb200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/kgeb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "kgeb200 is written for sm_100a (B200) only"
+#endif
+
+namespace kgeb {
+
+// thread-local last error text, returned by kgeb_last_error()
+void set_error(const char* fmt, ...);
+int cuda_status(cudaError_t e, const char* what);
+
+#define KGEB_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      kgeb::set_error(__VA_ARGS__);             \
+      return KGEB_ERR_ARG;                      \
+    }                                           \
+  } while (0)
+
+#define KGEB_LAUNCH_CHECK(what)                                  \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return kgeb::cuda_status(e__, what); \
+  } while (0)
+
+__device__ __forceinline__ int64_t load_index(const void* idx, int idx64, int64_t i) {
+  if (idx == nullptr) return i;
+  return idx64 ? reinterpret_cast<const int64_t*>(idx)[i]
+               : static_cast<int64_t>(reinterpret_cast<const int32_t*>(idx)[i]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// softplus(x) = max(x,0) + log1p(exp(-|x|)) ; sigmoid via the same exponential
+__device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoidf(float x) {
+  float e = __expf(-fabsf(x));
+  float r = 1.f / (1.f + e);
+  return x >= 0.f ? r : e * r;
+}
+
+constexpr int kNumSMs = 148;  // B200
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace kgeb

@@ -1,0 +1,728 @@
+// Row-wise (HBM/L2-bound) kernels: gather, "spo" scoring of the seven scorers and its backward,
+// query transforms of the sp_/_po forms, and negative-sampling pair scoring.
+// One warp per row; lanes stride the embedding dimension so every load is a coalesced 128 B line
+// (float4 per lane where the row is 16 B aligned).  Reference call sites are cited in kgeb200.h.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+namespace kgeb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_status(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return KGEB_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return KGEB_ERR_CUDA;
+}
+
+constexpr int kWarpsPerBlock = 8;
+constexpr float kPairwiseEps = 1e-6f;  // torch.nn.functional.pairwise_distance default eps
+
+__device__ __forceinline__ int relation_dim(int model, int d) {
+  return (model == KGEB_CP || model == KGEB_ROTATE) ? d / 2 : (model == KGEB_RESCAL ? d * d : d);
+}
+
+// ------------------------------------------------------------------------------------------
+// gather
+// ------------------------------------------------------------------------------------------
+__global__ void gather_rows_v4(const float4* __restrict__ W, int64_t vocab, int dim4, const void* idx,
+                               int idx64, int64_t n, float4* __restrict__ out) {
+  // one thread per float4; consecutive threads cover one row then the next -> coalesced stores
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t total = n * dim4;
+  for (; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = t / dim4;
+    int c = (int)(t - r * dim4);
+    int64_t src = load_index(idx, idx64, r);
+    out[t] = __ldg(&W[src * dim4 + c]);
+  }
+}
+__global__ void gather_rows_v1(const float* __restrict__ W, int64_t vocab, int dim, const void* idx,
+                               int idx64, int64_t n, float* __restrict__ out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t total = n * dim;
+  for (; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = t / dim;
+    int c = (int)(t - r * dim);
+    out[t] = __ldg(&W[load_index(idx, idx64, r) * dim + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// spo forward: warp per triple
+// ------------------------------------------------------------------------------------------
+struct RowSrc {
+  const float* base;
+  const void* idx;
+};
+__device__ __forceinline__ const float* row_ptr(const float* base, const void* idx, int idx64, int64_t i,
+                                                int width) {
+  return base + load_index(idx, idx64, i) * (int64_t)width;
+}
+
+template <int MODEL>
+__device__ __forceinline__ float spo_row(const float* __restrict__ s, const float* __restrict__ p,
+                                         const float* __restrict__ o, int d, int l_norm, int lane) {
+  const int h = d >> 1;
+  float acc = 0.f;
+  if (MODEL == KGEB_DISTMULT) {
+    for (int k = lane; k < d; k += 32) acc += s[k] * p[k] * o[k];
+  } else if (MODEL == KGEB_COMPLEX) {
+    for (int k = lane; k < h; k += 32) {
+      float sr = s[k], si = s[k + h], pr = p[k], pi = p[k + h], orr = o[k], oi = o[k + h];
+      acc += sr * pr * orr + si * pr * oi + sr * pi * oi - si * pi * orr;
+    }
+  } else if (MODEL == KGEB_CP) {
+    for (int k = lane; k < h; k += 32) acc += s[k] * p[k] * o[k + h];
+  } else if (MODEL == KGEB_SIMPLE) {
+    for (int k = lane; k < h; k += 32) acc += s[k] * p[k] * o[k + h] + s[k + h] * p[k + h] * o[k];
+    acc *= 0.5f;
+  } else if (MODEL == KGEB_RESCAL) {
+    for (int i = 0; i < d; ++i) {
+      float si = s[i];
+      const float* mrow = p + (int64_t)i * d;
+      for (int j = lane; j < d; j += 32) acc += si * mrow[j] * o[j];
+    }
+  } else if (MODEL == KGEB_TRANSE) {
+    for (int k = lane; k < d; k += 32) {
+      float df = s[k] + p[k] - o[k] + kPairwiseEps;
+      acc += (l_norm == 1) ? fabsf(df) : df * df;
+    }
+  } else if (MODEL == KGEB_ROTATE) {
+    for (int k = lane; k < h; k += 32) {
+      float pr, pi;
+      sincosf(p[k], &pi, &pr);
+      float sr = s[k], si = s[k + h];
+      float re = sr * pr - si * pi - o[k];
+      float im = sr * pi + si * pr - o[k + h];
+      float m2 = re * re + im * im;
+      acc += (l_norm == 1) ? sqrtf(m2) : m2;
+    }
+  }
+  acc = warp_sum(acc);
+  if (MODEL == KGEB_TRANSE) acc = (l_norm == 1) ? -acc : -sqrtf(acc);
+  if (MODEL == KGEB_ROTATE) acc = (l_norm == 1) ? acc : sqrtf(acc);
+  return acc;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+score_spo_kernel(int l_norm, const float* s_src, const void* s_idx, const float* p_src, const void* p_idx,
+                 const float* o_src, const void* o_idx, int idx64, int64_t n, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  const int dr = relation_dim(MODEL, d);
+  for (; row < n; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float* s = row_ptr(s_src, s_idx, idx64, row, d);
+    const float* p = row_ptr(p_src, p_idx, idx64, row, dr);
+    const float* o = row_ptr(o_src, o_idx, idx64, row, d);
+    float v = spo_row<MODEL>(s, p, o, d, l_norm, lane);
+    if (lane == 0) out[row] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// spo backward: warp per triple, per-row gradients (dense [n,*]); scattering is a separate step
+// ------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+score_spo_bwd_kernel(int l_norm, const float* s_src, const void* s_idx, const float* p_src, const void* p_idx,
+                     const float* o_src, const void* o_idx, int idx64, int64_t n, int d,
+                     const float* __restrict__ gout, float* __restrict__ ds, float* __restrict__ dp,
+                     float* __restrict__ d_o) {
+  const int lane = threadIdx.x & 31;
+  const int h = d >> 1;
+  const int dr = relation_dim(MODEL, d);
+  int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  for (; row < n; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float* s = row_ptr(s_src, s_idx, idx64, row, d);
+    const float* p = row_ptr(p_src, p_idx, idx64, row, dr);
+    const float* o = row_ptr(o_src, o_idx, idx64, row, d);
+    float* gs = ds + row * d;
+    float* gp = dp + row * (int64_t)dr;
+    float* go = d_o + row * d;
+    const float g = gout[row];
+    if (MODEL == KGEB_DISTMULT) {
+      for (int k = lane; k < d; k += 32) {
+        float a = s[k], b = p[k], c = o[k];
+        gs[k] = g * b * c;
+        gp[k] = g * a * c;
+        go[k] = g * a * b;
+      }
+    } else if (MODEL == KGEB_COMPLEX) {
+      for (int k = lane; k < h; k += 32) {
+        float sr = s[k], si = s[k + h], pr = p[k], pi = p[k + h], orr = o[k], oi = o[k + h];
+        gs[k] = g * (pr * orr + pi * oi);
+        gs[k + h] = g * (pr * oi - pi * orr);
+        gp[k] = g * (sr * orr + si * oi);
+        gp[k + h] = g * (sr * oi - si * orr);
+        go[k] = g * (sr * pr - si * pi);
+        go[k + h] = g * (si * pr + sr * pi);
+      }
+    } else if (MODEL == KGEB_CP) {
+      for (int k = lane; k < h; k += 32) {
+        float a = s[k], b = p[k], c = o[k + h];
+        gs[k] = g * b * c;
+        gs[k + h] = 0.f;
+        gp[k] = g * a * c;
+        go[k + h] = g * a * b;
+        go[k] = 0.f;
+      }
+    } else if (MODEL == KGEB_SIMPLE) {
+      const float gh = 0.5f * g;
+      for (int k = lane; k < h; k += 32) {
+        float sh = s[k], st = s[k + h], pf = p[k], pb = p[k + h], oh = o[k], ot = o[k + h];
+        gs[k] = gh * pf * ot;
+        gs[k + h] = gh * pb * oh;
+        gp[k] = gh * sh * ot;
+        gp[k + h] = gh * st * oh;
+        go[k + h] = gh * sh * pf;
+        go[k] = gh * st * pb;
+      }
+    } else if (MODEL == KGEB_RESCAL) {
+      // ds_i = g sum_j M_ij o_j ; do_j = g sum_i s_i M_ij ; dM_ij = g s_i o_j
+      for (int j = lane; j < d; j += 32) go[j] = 0.f;
+      __syncwarp();
+      for (int i = 0; i < d; ++i) {
+        const float* mrow = p + (int64_t)i * d;
+        float si = s[i];
+        float acc = 0.f;
+        for (int j = lane; j < d; j += 32) {
+          float m = mrow[j], oj = o[j];
+          acc += m * oj;
+          go[j] += g * si * m;  // lane-private columns j = lane (mod 32)
+          gp[(int64_t)i * d + j] = g * si * oj;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) gs[i] = g * acc;
+      }
+    } else if (MODEL == KGEB_TRANSE) {
+      float acc = 0.f;
+      if (l_norm != 1) {
+        for (int k = lane; k < d; k += 32) {
+          float df = s[k] + p[k] - o[k] + kPairwiseEps;
+          acc += df * df;
+        }
+        acc = sqrtf(warp_sum(acc));
+      }
+      const float inv = (l_norm == 1 || acc == 0.f) ? 0.f : 1.f / acc;
+      for (int k = lane; k < d; k += 32) {
+        float df = s[k] + p[k] - o[k] + kPairwiseEps;
+        float dd = (l_norm == 1) ? -sgnf(df) : -df * inv;  // d score / d diff
+        gs[k] = g * dd;
+        gp[k] = g * dd;
+        go[k] = -g * dd;
+      }
+    } else if (MODEL == KGEB_ROTATE) {
+      float acc = 0.f;
+      if (l_norm != 1) {
+        for (int k = lane; k < h; k += 32) {
+          float pr, pi;
+          sincosf(p[k], &pi, &pr);
+          float re = s[k] * pr - s[k + h] * pi - o[k];
+          float im = s[k] * pi + s[k + h] * pr - o[k + h];
+          acc += re * re + im * im;
+        }
+        acc = sqrtf(warp_sum(acc));
+      }
+      for (int k = lane; k < h; k += 32) {
+        float pr, pi;
+        sincosf(p[k], &pi, &pr);
+        float sr = s[k], si = s[k + h];
+        float re = sr * pr - si * pi - o[k];
+        float im = sr * pi + si * pr - o[k + h];
+        float den = (l_norm == 1) ? sqrtf(re * re + im * im) : acc;
+        float inv = den == 0.f ? 0.f : 1.f / den;
+        float dre = g * re * inv, dim_ = g * im * inv;
+        gs[k] = dre * pr + dim_ * pi;
+        gs[k + h] = -dre * pi + dim_ * pr;
+        go[k] = -dre;
+        go[k + h] = -dim_;
+        gp[k] = dre * (-sr * pi - si * pr) + dim_ * (sr * pr - si * pi);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// query transforms
+// ------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+query_build_kernel(int combine, const float* a_src, const void* a_idx, const float* p_src, const void* p_idx,
+                   int idx64, int64_t n, int d, float* __restrict__ Q) {
+  const int lane = threadIdx.x & 31;
+  const int h = d >> 1;
+  const int dr = relation_dim(MODEL, d);
+  const bool sp = (combine == KGEB_SP_);
+  int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  for (; row < n; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float* a = row_ptr(a_src, a_idx, idx64, row, d);
+    const float* p = row_ptr(p_src, p_idx, idx64, row, dr);
+    float* q = Q + row * d;
+    if (MODEL == KGEB_DISTMULT) {
+      for (int k = lane; k < d; k += 32) q[k] = a[k] * p[k];
+    } else if (MODEL == KGEB_COMPLEX) {
+      for (int k = lane; k < h; k += 32) {
+        float ar = a[k], ai = a[k + h], pr = p[k], pi = p[k + h];
+        if (sp) {
+          q[k] = ar * pr - ai * pi;
+          q[k + h] = ai * pr + ar * pi;
+        } else {
+          q[k] = pr * ar + pi * ai;
+          q[k + h] = pr * ai - pi * ar;
+        }
+      }
+    } else if (MODEL == KGEB_CP) {
+      for (int k = lane; k < h; k += 32) {
+        if (sp) {  // candidates contribute o[:, h:]
+          q[k] = 0.f;
+          q[k + h] = a[k] * p[k];
+        } else {  // candidates contribute s[:, :h]
+          q[k] = a[k + h] * p[k];
+          q[k + h] = 0.f;
+        }
+      }
+    } else if (MODEL == KGEB_SIMPLE) {
+      for (int k = lane; k < h; k += 32) {
+        float ah = a[k], at = a[k + h], pf = p[k], pb = p[k + h];
+        if (sp) {  // 1/2 [s_t*p_b | s_h*p_f]
+          q[k] = 0.5f * (at * pb);
+          q[k + h] = 0.5f * (ah * pf);
+        } else {  // 1/2 [o_t*p_f | o_h*p_b]
+          q[k] = 0.5f * (at * pf);
+          q[k + h] = 0.5f * (ah * pb);
+        }
+      }
+    } else if (MODEL == KGEB_RESCAL) {
+      if (sp) {  // q_j = sum_i s_i M_ij : lanes over j, coalesced rows of M
+        for (int j = lane; j < d; j += 32) {
+          float acc = 0.f;
+          for (int i = 0; i < d; ++i) acc += a[i] * p[(int64_t)i * d + j];
+          q[j] = acc;
+        }
+      } else {  // q_i = sum_j M_ij o_j
+        for (int i = 0; i < d; ++i) {
+          float acc = 0.f;
+          for (int j = lane; j < d; j += 32) acc += p[(int64_t)i * d + j] * a[j];
+          acc = warp_sum(acc);
+          if (lane == 0) q[i] = acc;
+        }
+      }
+    } else if (MODEL == KGEB_TRANSE) {
+      for (int k = lane; k < d; k += 32) q[k] = sp ? a[k] + p[k] : a[k] - p[k];
+    } else if (MODEL == KGEB_ROTATE) {
+      for (int k = lane; k < h; k += 32) {
+        float pr, pi;
+        sincosf(p[k], &pi, &pr);
+        float ar = a[k], ai = a[k + h];
+        if (sp) {  // s * r
+          q[k] = ar * pr - ai * pi;
+          q[k + h] = ar * pi + ai * pr;
+        } else {  // o * conj(r)
+          q[k] = ar * pr + ai * pi;
+          q[k + h] = ai * pr - ar * pi;
+        }
+      }
+    }
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+query_bwd_kernel(int combine, const float* a_src, const void* a_idx, const float* p_src, const void* p_idx,
+                 int idx64, int64_t n, int d, const float* __restrict__ dQ, float* __restrict__ da,
+                 float* __restrict__ dp) {
+  const int lane = threadIdx.x & 31;
+  const int h = d >> 1;
+  const int dr = relation_dim(MODEL, d);
+  const bool sp = (combine == KGEB_SP_);
+  int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  for (; row < n; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const float* a = row_ptr(a_src, a_idx, idx64, row, d);
+    const float* p = row_ptr(p_src, p_idx, idx64, row, dr);
+    const float* g = dQ + row * d;
+    float* ga = da + row * d;
+    float* gp = dp + row * (int64_t)dr;
+    if (MODEL == KGEB_DISTMULT) {
+      for (int k = lane; k < d; k += 32) {
+        ga[k] = g[k] * p[k];
+        gp[k] = g[k] * a[k];
+      }
+    } else if (MODEL == KGEB_COMPLEX) {
+      for (int k = lane; k < h; k += 32) {
+        float ar = a[k], ai = a[k + h], pr = p[k], pi = p[k + h], gr = g[k], gi = g[k + h];
+        if (sp) {
+          ga[k] = gr * pr + gi * pi;
+          ga[k + h] = -gr * pi + gi * pr;
+          gp[k] = gr * ar + gi * ai;
+          gp[k + h] = -gr * ai + gi * ar;
+        } else {
+          ga[k] = gr * pr - gi * pi;
+          ga[k + h] = gr * pi + gi * pr;
+          gp[k] = gr * ar + gi * ai;
+          gp[k + h] = gr * ai - gi * ar;
+        }
+      }
+    } else if (MODEL == KGEB_CP) {
+      for (int k = lane; k < h; k += 32) {
+        if (sp) {
+          ga[k] = g[k + h] * p[k];
+          ga[k + h] = 0.f;
+          gp[k] = g[k + h] * a[k];
+        } else {
+          ga[k + h] = g[k] * p[k];
+          ga[k] = 0.f;
+          gp[k] = g[k] * a[k + h];
+        }
+      }
+    } else if (MODEL == KGEB_SIMPLE) {
+      for (int k = lane; k < h; k += 32) {
+        float ah = a[k], at = a[k + h], pf = p[k], pb = p[k + h];
+        float g0 = 0.5f * g[k], g1 = 0.5f * g[k + h];
+        if (sp) {  // q0 = at*pb, q1 = ah*pf
+          ga[k + h] = g0 * pb;
+          gp[k + h] = g0 * at;
+          ga[k] = g1 * pf;
+          gp[k] = g1 * ah;
+        } else {  // q0 = at*pf, q1 = ah*pb
+          ga[k + h] = g0 * pf;
+          gp[k] = g0 * at;
+          ga[k] = g1 * pb;
+          gp[k + h] = g1 * ah;
+        }
+      }
+    } else if (MODEL == KGEB_RESCAL) {
+      if (sp) {  // q_j = sum_i s_i M_ij : ds_i = sum_j M_ij g_j ; dM_ij = s_i g_j
+        for (int i = 0; i < d; ++i) {
+          float acc = 0.f, ai = a[i];
+          for (int j = lane; j < d; j += 32) {
+            float gj = g[j];
+            acc += p[(int64_t)i * d + j] * gj;
+            gp[(int64_t)i * d + j] = ai * gj;
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) ga[i] = acc;
+        }
+      } else {  // q_i = sum_j M_ij o_j : do_j = sum_i M_ij g_i ; dM_ij = g_i o_j
+        for (int j = lane; j < d; j += 32) {
+          float acc = 0.f, oj = a[j];
+          for (int i = 0; i < d; ++i) {
+            float gi = g[i];
+            acc += p[(int64_t)i * d + j] * gi;
+            gp[(int64_t)i * d + j] = gi * oj;
+          }
+          ga[j] = acc;
+        }
+      }
+    } else if (MODEL == KGEB_TRANSE) {
+      for (int k = lane; k < d; k += 32) {
+        ga[k] = g[k];
+        gp[k] = sp ? g[k] : -g[k];
+      }
+    } else if (MODEL == KGEB_ROTATE) {
+      for (int k = lane; k < h; k += 32) {
+        float pr, pi;
+        sincosf(p[k], &pi, &pr);
+        float ar = a[k], ai = a[k + h], gr = g[k], gi = g[k + h];
+        if (sp) {  // q_re = ar pr - ai pi ; q_im = ar pi + ai pr
+          ga[k] = gr * pr + gi * pi;
+          ga[k + h] = -gr * pi + gi * pr;
+          gp[k] = gr * (-ar * pi - ai * pr) + gi * (ar * pr - ai * pi);
+        } else {  // q_re = ar pr + ai pi ; q_im = ai pr - ar pi
+          ga[k] = gr * pr - gi * pi;
+          ga[k + h] = gr * pi + gi * pr;
+          gp[k] = gr * (-ar * pi + ai * pr) + gi * (-ai * pi - ar * pr);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// negative-sampling pair scoring: warp per (row, candidate); the query row is read from L1/L2
+// ------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ float pair_accumulate(const float* __restrict__ q, const float* __restrict__ c,
+                                                 int d, int lane) {
+  float acc = 0.f;
+  if (KIND == KGEB_ROT_L1) {
+    const int h = d >> 1;
+    for (int k = lane; k < h; k += 32) {
+      float re = q[k] - c[k], im = q[k + h] - c[k + h];
+      acc += sqrtf(re * re + im * im);
+    }
+  } else if ((d & 3) == 0) {
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    const float4* c4 = reinterpret_cast<const float4*>(c);
+    for (int k = lane; k < (d >> 2); k += 32) {
+      float4 a = q4[k], b = __ldg(&c4[k]);
+      if (KIND == KGEB_DOT) {
+        acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      } else if (KIND == KGEB_NEG_L1) {
+        acc += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+      } else {
+        float x = a.x - b.x, y = a.y - b.y, z = a.z - b.z, w = a.w - b.w;
+        acc += x * x + y * y + z * z + w * w;
+      }
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) {
+      float x = q[k] - c[k];
+      acc += (KIND == KGEB_DOT) ? q[k] * c[k] : (KIND == KGEB_NEG_L1 ? fabsf(x) : x * x);
+    }
+  }
+  return warp_sum(acc);
+}
+template <int KIND>
+__device__ __forceinline__ float pair_finish(float acc) {
+  if (KIND == KGEB_NEG_L1) return -acc;
+  if (KIND == KGEB_NEG_L2) return -sqrtf(acc);
+  if (KIND == KGEB_ROT_L2) return sqrtf(acc);
+  return acc;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+pairs_score_kernel(const float* __restrict__ Q, const float* __restrict__ table, const void* cand, int idx64,
+                   int64_t B, int64_t M, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int64_t pair = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t total = B * M;
+  for (; pair < total; pair += (int64_t)gridDim.x * kWarpsPerBlock) {
+    int64_t row = pair / M;
+    const float* q = Q + row * d;
+    const float* c = table + load_index(cand, idx64, pair) * (int64_t)d;
+    float acc = pair_accumulate<KIND>(q, c, d, lane);
+    if (lane == 0) out[pair] = pair_finish<KIND>(acc);
+  }
+}
+
+// backward of pair scoring.  Block per query row: each warp walks candidates j = warp, warp+W, ...
+// writing dC[pair,:] and accumulating the row's dQ in registers; warps are then combined in a fixed
+// order through shared memory (deterministic, no float atomics).
+constexpr int kPairBwdWarps = 8;
+template <int KIND>
+__global__ void __launch_bounds__(kPairBwdWarps * 32)
+pairs_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ table, const void* cand, int idx64,
+                 int64_t B, int64_t M, int d, const float* __restrict__ G, const float* __restrict__ scores,
+                 float* __restrict__ dQ, float* __restrict__ dC) {
+  extern __shared__ float smem[];  // [kPairBwdWarps][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = d >> 1;
+  const int64_t row = blockIdx.x;
+  const float* q = Q + row * d;
+  float* acc = smem + warp * d;
+  for (int k = lane; k < d; k += 32) acc[k] = 0.f;
+  __syncwarp();
+  for (int64_t j = warp; j < M; j += kPairBwdWarps) {
+    const int64_t pair = row * M + j;
+    const float g = G[pair];
+    const float* c = table + load_index(cand, idx64, pair) * (int64_t)d;
+    float* gc = dC + pair * d;
+    if (KIND == KGEB_DOT) {
+      for (int k = lane; k < d; k += 32) {
+        gc[k] = g * q[k];
+        acc[k] += g * c[k];
+      }
+    } else if (KIND == KGEB_NEG_L1) {
+      for (int k = lane; k < d; k += 32) {
+        float t = -g * sgnf(q[k] - c[k]);
+        acc[k] += t;
+        gc[k] = -t;
+      }
+    } else if (KIND == KGEB_NEG_L2 || KIND == KGEB_ROT_L2) {
+      const float dist = fabsf(scores[pair]);
+      const float coef = dist == 0.f ? 0.f : ((KIND == KGEB_NEG_L2 ? -g : g) / dist);
+      for (int k = lane; k < d; k += 32) {
+        float t = coef * (q[k] - c[k]);
+        acc[k] += t;
+        gc[k] = -t;
+      }
+    } else {  // ROT_L1
+      for (int k = lane; k < h; k += 32) {
+        float re = q[k] - c[k], im = q[k + h] - c[k + h];
+        float m = sqrtf(re * re + im * im);
+        float inv = m == 0.f ? 0.f : g / m;
+        float tr = re * inv, ti = im * inv;
+        acc[k] += tr;
+        acc[k + h] += ti;
+        gc[k] = -tr;
+        gc[k + h] = -ti;
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPairBwdWarps; ++w) s += smem[w * d + k];
+    dQ[row * d + k] = s;
+  }
+}
+
+static int grid_for_rows(int64_t n) {
+  int64_t b = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+static int check_model(int model, int d, int l_norm) {
+  KGEB_REQUIRE(model >= KGEB_DISTMULT && model <= KGEB_ROTATE, "unknown model id %d", model);
+  KGEB_REQUIRE(d > 0, "embedding dim must be positive (got %d)", d);
+  if (model == KGEB_COMPLEX || model == KGEB_CP || model == KGEB_SIMPLE || model == KGEB_ROTATE)
+    KGEB_REQUIRE((d & 1) == 0, "model %d requires embeddings of even dimensionality (got %d)", model, d);
+  if (model == KGEB_TRANSE || model == KGEB_ROTATE) {
+    if (l_norm != 1 && l_norm != 2) {
+      set_error("l_norm=%d: only l_norm 1 and 2 are built", l_norm);
+      return KGEB_ERR_UNSUPPORTED;
+    }
+  }
+  return KGEB_OK;
+}
+
+}  // namespace kgeb
+
+using namespace kgeb;
+
+#define DISPATCH_MODEL(model, CALL)                         \
+  switch (model) {                                          \
+    case KGEB_DISTMULT: { constexpr int M_ = KGEB_DISTMULT; CALL; } break; \
+    case KGEB_COMPLEX: { constexpr int M_ = KGEB_COMPLEX; CALL; } break;   \
+    case KGEB_CP: { constexpr int M_ = KGEB_CP; CALL; } break;             \
+    case KGEB_SIMPLE: { constexpr int M_ = KGEB_SIMPLE; CALL; } break;     \
+    case KGEB_RESCAL: { constexpr int M_ = KGEB_RESCAL; CALL; } break;     \
+    case KGEB_TRANSE: { constexpr int M_ = KGEB_TRANSE; CALL; } break;     \
+    default: { constexpr int M_ = KGEB_ROTATE; CALL; } break;              \
+  }
+
+#define DISPATCH_KIND(kind, CALL)                                        \
+  switch (kind) {                                                        \
+    case KGEB_DOT: { constexpr int K_ = KGEB_DOT; CALL; } break;         \
+    case KGEB_NEG_L1: { constexpr int K_ = KGEB_NEG_L1; CALL; } break;   \
+    case KGEB_NEG_L2: { constexpr int K_ = KGEB_NEG_L2; CALL; } break;   \
+    case KGEB_ROT_L1: { constexpr int K_ = KGEB_ROT_L1; CALL; } break;   \
+    default: { constexpr int K_ = KGEB_ROT_L2; CALL; } break;            \
+  }
+
+extern "C" {
+
+const char* kgeb_last_error(void) { return g_err; }
+
+int kgeb_version(char* buf, int buflen) {
+  if (buf && buflen > 0) snprintf(buf, buflen, "kgeb200 0.1 (sm_100a, cuda %d)", CUDART_VERSION);
+  return 100;
+}
+
+int kgeb_gather_rows(const float* W, int64_t vocab, int dim, const void* idx, int idx64, int64_t n, float* out,
+                     void* stream) {
+  KGEB_REQUIRE(W && out && dim > 0 && n >= 0 && vocab >= 0, "gather_rows: bad arguments");
+  if (n == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  const int threads = 256;
+  bool v4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  int64_t work = v4 ? n * (dim / 4) : n * dim;
+  int64_t blocks = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)kNumSMs * 32;
+  int grid = (int)(blocks > cap ? cap : blocks);
+  if (v4)
+    gather_rows_v4<<<grid, threads, 0, st>>>(reinterpret_cast<const float4*>(W), vocab, dim / 4, idx, idx64, n,
+                                             reinterpret_cast<float4*>(out));
+  else
+    gather_rows_v1<<<grid, threads, 0, st>>>(W, vocab, dim, idx, idx64, n, out);
+  KGEB_LAUNCH_CHECK("gather_rows");
+  return KGEB_OK;
+}
+
+int kgeb_score_spo(int model, int l_norm, const float* s_src, const void* s_idx, const float* p_src,
+                   const void* p_idx, const float* o_src, const void* o_idx, int idx64, int64_t n, int d,
+                   float* out, void* stream) {
+  int rc = check_model(model, d, l_norm);
+  if (rc) return rc;
+  KGEB_REQUIRE(s_src && p_src && o_src && out && n >= 0, "score_spo: bad arguments");
+  if (n == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_MODEL(model, (score_spo_kernel<M_><<<grid_for_rows(n), kWarpsPerBlock * 32, 0, st>>>(
+                            l_norm, s_src, s_idx, p_src, p_idx, o_src, o_idx, idx64, n, d, out)));
+  KGEB_LAUNCH_CHECK("score_spo");
+  return KGEB_OK;
+}
+
+int kgeb_score_spo_bwd(int model, int l_norm, const float* s_src, const void* s_idx, const float* p_src,
+                       const void* p_idx, const float* o_src, const void* o_idx, int idx64, int64_t n, int d,
+                       const float* gout, float* ds, float* dp, float* d_o, void* stream) {
+  int rc = check_model(model, d, l_norm);
+  if (rc) return rc;
+  KGEB_REQUIRE(s_src && p_src && o_src && gout && ds && dp && d_o && n >= 0, "score_spo_bwd: bad arguments");
+  if (n == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_MODEL(model, (score_spo_bwd_kernel<M_><<<grid_for_rows(n), kWarpsPerBlock * 32, 0, st>>>(
+                            l_norm, s_src, s_idx, p_src, p_idx, o_src, o_idx, idx64, n, d, gout, ds, dp, d_o)));
+  KGEB_LAUNCH_CHECK("score_spo_bwd");
+  return KGEB_OK;
+}
+
+int kgeb_query_build(int model, int combine, const float* a_src, const void* a_idx, const float* p_src,
+                     const void* p_idx, int idx64, int64_t n, int d, float* Q, void* stream) {
+  int rc = check_model(model, d, 1);
+  if (rc) return rc;
+  KGEB_REQUIRE(combine == KGEB_SP_ || combine == KGEB__PO, "query_build: combine must be sp_ or _po");
+  KGEB_REQUIRE(a_src && p_src && Q && n >= 0, "query_build: bad arguments");
+  if (n == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_MODEL(model, (query_build_kernel<M_><<<grid_for_rows(n), kWarpsPerBlock * 32, 0, st>>>(
+                            combine, a_src, a_idx, p_src, p_idx, idx64, n, d, Q)));
+  KGEB_LAUNCH_CHECK("query_build");
+  return KGEB_OK;
+}
+
+int kgeb_query_bwd(int model, int combine, const float* a_src, const void* a_idx, const float* p_src,
+                   const void* p_idx, int idx64, int64_t n, int d, const float* dQ, float* da, float* dp,
+                   void* stream) {
+  int rc = check_model(model, d, 1);
+  if (rc) return rc;
+  KGEB_REQUIRE(combine == KGEB_SP_ || combine == KGEB__PO, "query_bwd: combine must be sp_ or _po");
+  KGEB_REQUIRE(a_src && p_src && dQ && da && dp && n >= 0, "query_bwd: bad arguments");
+  if (n == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_MODEL(model, (query_bwd_kernel<M_><<<grid_for_rows(n), kWarpsPerBlock * 32, 0, st>>>(
+                            combine, a_src, a_idx, p_src, p_idx, idx64, n, d, dQ, da, dp)));
+  KGEB_LAUNCH_CHECK("query_bwd");
+  return KGEB_OK;
+}
+
+int kgeb_pairs_score(int kind, const float* Q, const float* table, const void* cand, int idx64, int64_t B,
+                     int64_t M, int d, float* out, void* stream) {
+  KGEB_REQUIRE(kind >= KGEB_DOT && kind <= KGEB_ROT_L2, "pairs_score: unknown kind %d", kind);
+  KGEB_REQUIRE(Q && table && cand && out && B >= 0 && M >= 0 && d > 0, "pairs_score: bad arguments");
+  KGEB_REQUIRE(!(kind >= KGEB_ROT_L1) || (d % 2 == 0), "RotatE requires embeddings of even dimensionality");
+  if (B * M == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_KIND(kind, (pairs_score_kernel<K_><<<grid_for_rows(B * M), kWarpsPerBlock * 32, 0, st>>>(
+                          Q, table, cand, idx64, B, M, d, out)));
+  KGEB_LAUNCH_CHECK("pairs_score");
+  return KGEB_OK;
+}
+
+int kgeb_pairs_bwd(int kind, const float* Q, const float* table, const void* cand, int idx64, int64_t B,
+                   int64_t M, int d, const float* G, const float* scores, float* dQ, float* dC, void* stream) {
+  KGEB_REQUIRE(kind >= KGEB_DOT && kind <= KGEB_ROT_L2, "pairs_bwd: unknown kind %d", kind);
+  KGEB_REQUIRE(Q && table && cand && G && dQ && dC && B >= 0 && M >= 0 && d > 0, "pairs_bwd: bad arguments");
+  KGEB_REQUIRE(!(kind == KGEB_NEG_L2 || kind == KGEB_ROT_L2) || scores, "pairs_bwd: L2 kinds need the scores");
+  if (B == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  size_t smem = (size_t)kPairBwdWarps * d * sizeof(float);
+  KGEB_REQUIRE(smem <= 48 * 1024, "pairs_bwd: dim %d too large", d);
+  DISPATCH_KIND(kind, (pairs_bwd_kernel<K_><<<(unsigned)B, kPairBwdWarps * 32, smem, st>>>(
+                          Q, table, cand, idx64, B, M, d, G, scores, dQ, dC)));
+  KGEB_LAUNCH_CHECK("pairs_bwd");
+  return KGEB_OK;
+}
+
+}  // extern "C"

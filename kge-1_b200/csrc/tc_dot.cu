@@ -1,0 +1,673 @@
+// tcgen05 / TMEM / TMA tiles for the KGEB_DOT all-entity forms (DistMult, ComplEx, CP, SimplE, RESCAL):
+//   S[128 x 128] = A[128 x d] * B[128 x d]^T,  fp32 operands read in place as TF32 (kind::tf32), fp32
+//   accumulation in tensor memory.  Both operands are K-major 128-byte-swizzled slabs written by TMA
+//   straight from the row-major fp32 tables (no conversion pass, no re-layout of the table).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0    TMA producer   (query blocks -> resident smem, table slabs -> ring of stages)
+//   warp 1    MMA issuer     (one thread issues tcgen05.mma; tcgen05.commit frees smem / publishes TMEM)
+//   warp 2    TMEM allocator
+//   warps 4-7 epilogue       (tcgen05.ld -> registers -> fused epilogue; TMEM double-buffered)
+// A job = (group of NQB query blocks, contiguous chunk of entity tiles): the query blocks stay resident
+// in shared memory for the whole chunk, only table slabs stream.  Epilogue modes:
+//   MODE_SCORES  A = table tile, B = query block : lane = entity  -> coalesced stores of X[q, e]
+//   MODE_STATS   A = query block, B = table tile : lane = query   -> online max/sum-exp | softplus sums
+//   MODE_RANK    A = query block, B = table tile : lane = query   -> rank / tie counts with CSR filters
+#include "common.cuh"
+#include <cuda.h>
+
+namespace kgeb {
+namespace tc {
+
+constexpr int TILE = 128;                 // rows per operand tile (UMMA M = N = 128)
+constexpr int SLAB_K = 32;                // fp32 per 128-byte swizzle row
+constexpr int SLAB_BYTES = TILE * 128;    // 16 KiB: 128 rows x 128 B
+constexpr int UMMA_K = 8;                 // kind::tf32
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+enum { MODE_SCORES = 0, MODE_STATS = 1, MODE_RANK = 2 };
+
+struct Params {
+  int64_t B;          // query rows
+  int64_t n_ent;      // table rows of this shard
+  int64_t e_lo;       // global id of table row 0
+  int d;
+  int ks;             // K slabs = ceil(d / 32)
+  int stages;         // ring depth
+  int64_t n_qgroups;  // ceil(ceil(B/128) / NQB)
+  int64_t n_tiles;    // ceil(n_ent / 128)
+  int64_t chunks;     // entity chunks
+  int64_t tiles_per_chunk;
+  // MODE_SCORES
+  float* out; int64_t ld; int64_t col_off;
+  // MODE_STATS
+  int loss; float offset; float* partial;  // [chunks][B][4]
+  // MODE_RANK
+  const float* true_score; const void* true_ent; int idx64;
+  const int64_t* f_off; const int64_t* f_col; const int64_t* t_off; const int64_t* t_col;
+  unsigned long long* counts;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int32_t c_inner, int32_t c_row,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"((uint32_t)NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)NCOLS) : "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, mma_sm100_desc.hpp):
+//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
+// a_major @15, b_major @16 (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ int64_t lb_i64(const int64_t* a, int64_t lo, int64_t hi, int64_t v) {
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int NQB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_w, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KS = p.ks, STAGES = p.stages;
+  uint8_t* q_smem = smem;                                  // [NQB][KS] slabs, resident per job
+  uint8_t* ring = smem + (size_t)NQB * KS * SLAB_BYTES;    // [STAGES] slabs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * SLAB_BYTES);
+  uint64_t* full = bars;                 // [MAX_STAGES]
+  uint64_t* empty = bars + MAX_STAGES;   // [MAX_STAGES]
+  uint64_t* q_full = bars + 2 * MAX_STAGES;
+  uint64_t* q_empty = q_full + 1;
+  uint64_t* t_full = q_full + 2;         // [2]
+  uint64_t* t_empty = q_full + 4;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 6);
+  constexpr int TMEM_COLS = 2 * NQB * TILE;  // double-buffered accumulators (256 or 512 columns)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&t_full[b], 1);
+      mbar_init(&t_empty[b], 4 * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t n_qblocks = (p.B + TILE - 1) / TILE;
+  const int64_t n_jobs = p.n_qgroups * p.chunks;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, qphase = 0;
+      for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int64_t qg = job % p.n_qgroups, ch = job / p.n_qgroups;
+        const int nqb = (int)min((int64_t)NQB, n_qblocks - qg * NQB);
+        mbar_wait(q_empty, qphase ^ 1);
+        mbar_expect_tx(q_full, (uint32_t)(nqb * KS * SLAB_BYTES));
+        for (int qb = 0; qb < nqb; ++qb)
+          for (int k = 0; k < KS; ++k)
+            tma_load_2d(q_smem + (size_t)(qb * KS + k) * SLAB_BYTES, &tm_q, k * SLAB_K,
+                        (int32_t)((qg * NQB + qb) * TILE), q_full);
+        qphase ^= 1;
+        const int64_t t0 = ch * p.tiles_per_chunk, t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+        for (int64_t t = t0; t < t1; ++t)
+          for (int k = 0; k < KS; ++k) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], SLAB_BYTES);
+            tma_load_2d(ring + (size_t)stage * SLAB_BYTES, &tm_w, k * SLAB_K, (int32_t)(t * TILE), &full[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE, TILE, 0, 0);
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, qphase = 0, tphase[2] = {0, 0};
+      for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int64_t qg = job % p.n_qgroups, ch = job / p.n_qgroups;
+        const int nqb = (int)min((int64_t)NQB, n_qblocks - qg * NQB);
+        mbar_wait(q_full, qphase);
+        qphase ^= 1;
+        tc_fence_after();
+        const int64_t t0 = ch * p.tiles_per_chunk, t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+        for (int64_t t = t0; t < t1; ++t) {
+          mbar_wait(&t_empty[buf], tphase[buf] ^ 1);
+          tc_fence_after();
+          for (int k = 0; k < KS; ++k) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t w_addr = smem_u32(ring + (size_t)stage * SLAB_BYTES);
+            for (int qb = 0; qb < nqb; ++qb) {
+              const uint32_t q_addr = smem_u32(q_smem + (size_t)(qb * KS + k) * SLAB_BYTES);
+              const uint32_t acc = tmem_base + (uint32_t)((buf * NQB + qb) * TILE);
+#pragma unroll
+              for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk) {
+                const uint64_t qd = make_desc(q_addr + kk * UMMA_K * 4, 16, 1024);
+                const uint64_t wd = make_desc(w_addr + kk * UMMA_K * 4, 16, 1024);
+                if (MODE == MODE_SCORES) umma_tf32(acc, wd, qd, idesc, (k | kk) != 0);  // lanes = entities
+                else                     umma_tf32(acc, qd, wd, idesc, (k | kk) != 0);  // lanes = queries
+              }
+            }
+            umma_commit(&empty[stage]);  // frees the slab once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&t_full[buf]);     // accumulators of this tile are complete
+          tphase[buf] ^= 1;
+          buf ^= 1;
+        }
+        umma_commit(q_empty);            // resident query blocks may be overwritten
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ================================ epilogue ================================
+    const int ew = warp - EPI_WARP0;            // == warp % 4 : TMEM lane quadrant of this warp
+    const int trow = ew * 32 + lane;            // row of the A tile owned by this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(ew * 32) << 16);
+    int buf = 0;
+    uint32_t tphase[2] = {0, 0};
+    for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+      const int64_t qg = job % p.n_qgroups, ch = job / p.n_qgroups;
+      const int nqb = (int)min((int64_t)NQB, n_qblocks - qg * NQB);
+      const int64_t t0 = ch * p.tiles_per_chunk, t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
+
+      // per-job running state (MODE_STATS / MODE_RANK: thread = query row trow of block qb)
+      float s0[NQB], s1[NQB], s2[NQB];
+      int cnt[NQB][6];
+      float tsc[NQB];
+      int64_t tent[NQB], fcur[NQB], fend[NQB], ucur[NQB], uend[NQB];
+#pragma unroll
+      for (int qb = 0; qb < NQB; ++qb) {
+        s0[qb] = (MODE == MODE_STATS && p.loss == KGEB_LOSS_KL) ? -INFINITY : 0.f;
+        s1[qb] = s2[qb] = 0.f;
+        tsc[qb] = 0.f; tent[qb] = -1; fcur[qb] = fend[qb] = ucur[qb] = uend[qb] = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cnt[qb][k] = 0;
+        if (MODE == MODE_RANK) {
+          const int64_t r = (qg * NQB + qb) * TILE + trow;
+          if (qb < nqb && r < p.B) {
+            float t = p.true_score[r];
+            tsc[qb] = (t != t) ? -INFINITY : t;
+            tent[qb] = load_index(p.true_ent, p.idx64, r);
+            const int64_t first = p.e_lo + t0 * TILE;
+            if (p.f_off) { fend[qb] = p.f_off[r + 1]; fcur[qb] = lb_i64(p.f_col, p.f_off[r], fend[qb], first); }
+            if (p.t_off) { uend[qb] = p.t_off[r + 1]; ucur[qb] = lb_i64(p.t_col, p.t_off[r], uend[qb], first); }
+          }
+        }
+      }
+
+      for (int64_t t = t0; t < t1; ++t) {
+        mbar_wait(&t_full[buf], tphase[buf]);
+        tphase[buf] ^= 1;
+        tc_fence_after();
+        const int ncols = (int)min((int64_t)TILE, p.n_ent - t * TILE);  // valid B-tile rows (columns of S)
+#pragma unroll
+        for (int qb = 0; qb < NQB; ++qb) {
+          if (qb >= nqb) continue;
+          const uint32_t acc = lane_addr + (uint32_t)((buf * NQB + qb) * TILE);
+          const int64_t qrow0 = (qg * NQB + qb) * TILE;
+          if (MODE == MODE_SCORES) {
+            // lanes = entities of tile t, columns = query rows of block qb
+            const int64_t e = t * TILE + trow;
+            for (int c0 = 0; c0 < TILE; c0 += 32) {
+              if (qrow0 + c0 >= p.B) break;  // warp-uniform
+              float v[32];
+              tmem_ld32(acc + c0, v);
+              if (e < p.n_ent) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const int64_t q = qrow0 + c0 + c;
+                  if (q < p.B) p.out[q * p.ld + p.col_off + e] = v[c];
+                }
+              }
+            }
+          } else if (MODE == MODE_STATS) {
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+              float v[32];
+              tmem_ld32(acc + c0, v);
+              const int nv = min(32, ncols - c0);
+              if (p.loss == KGEB_LOSS_KL) {
+                float mx = s0[qb];
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c < nv) mx = fmaxf(mx, v[c]);
+                float l = (s0[qb] == -INFINITY) ? 0.f : s1[qb] * __expf(s0[qb] - mx);
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c < nv) {
+                    l += __expf(v[c] - mx);
+                    s2[qb] += v[c];
+                  }
+                s0[qb] = mx;
+                s1[qb] = l;
+              } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c < nv) {
+                    const float x = v[c] + p.offset;
+                    s0[qb] += softplusf(x);
+                    s2[qb] += x;
+                  }
+              }
+            }
+          } else {  // MODE_RANK
+            const float ts = tsc[qb];
+            const int64_t ent0 = p.e_lo + t * TILE;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+              float v[32];
+              tmem_ld32(acc + c0, v);
+              const int nv = min(32, ncols - c0);
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (c < nv) {
+                  float x = v[c];
+                  if (ent0 + c0 + c == tent[qb]) x = ts;  // entity_ranking.py:170-177
+                  if (x != x) x = -INFINITY;
+                  cnt[qb][0] += (x > ts);
+                  cnt[qb][1] += (x == ts);
+                }
+            }
+            // corrections for filtered candidates (their score becomes -inf): warp-cooperative, one
+            // filter entry per iteration; the value is re-read from the same TMEM accumulator so
+            // comparisons are bit-consistent with the raw pass.
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+              const int64_t* col = which ? p.t_col : p.f_col;
+              int64_t& cur = which ? ucur[qb] : fcur[qb];
+              const int64_t end = which ? uend[qb] : fend[qb];
+              int64_t prev = -1;
+              while (true) {
+                int loc = -1;
+                int64_t c = -1;
+                if (cur < end) {
+                  c = col[cur];
+                  if (c < ent0 + ncols) loc = (int)(c - ent0);
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, loc >= 0);
+                if (mask == 0) break;
+                const int src = __ffs(mask) - 1;
+                const int sloc = __shfl_sync(0xffffffffu, loc, src);
+                float x = tmem_ld1(acc + (uint32_t)sloc);
+                if (lane == src) {
+                  ++cur;
+                  if (c != prev && c != tent[qb]) {
+                    if (x != x) x = -INFINITY;
+                    cnt[qb][2 + 2 * which] -= (x > ts);
+                    cnt[qb][3 + 2 * which] += (ts == -INFINITY) - (x == ts);
+                  }
+                  prev = c;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&t_empty[buf]);
+        buf ^= 1;
+      }
+
+      // job results
+#pragma unroll
+      for (int qb = 0; qb < NQB; ++qb) {
+        const int64_t r = (qg * NQB + qb) * TILE + trow;
+        if (qb >= nqb || r >= p.B) continue;
+        if (MODE == MODE_STATS) {
+          float* o = p.partial + (ch * p.B + r) * 4;
+          o[0] = s0[qb]; o[1] = s1[qb]; o[2] = s2[qb]; o[3] = 0.f;
+        } else if (MODE == MODE_RANK) {
+          unsigned long long* c = p.counts + r * 6;
+          const long long rr = cnt[qb][0], rt = cnt[qb][1];
+          atomicAdd(c + 0, (unsigned long long)rr);
+          atomicAdd(c + 1, (unsigned long long)rt);
+          atomicAdd(c + 2, (unsigned long long)(rr + cnt[qb][2]));
+          atomicAdd(c + 3, (unsigned long long)(rt + cnt[qb][3]));
+          atomicAdd(c + 4, (unsigned long long)(rr + cnt[qb][4]));
+          atomicAdd(c + 5, (unsigned long long)(rt + cnt[qb][5]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, d]: box = 32 columns (128 B) x 128 rows, 128-byte swizzle, OOB -> zeros
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int d) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return KGEB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)SLAB_K, (cuuint32_t)TILE};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for [%lld x %d] at %p", (int)r, (long long)rows, d, base);
+    return KGEB_ERR_CUDA;
+  }
+  return KGEB_OK;
+}
+
+static int check_operands(const float* Q, const float* table, int d) {
+  KGEB_REQUIRE(d % 4 == 0, "TF32 tiles need an embedding dim that is a multiple of 4 (got %d)", d);
+  KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(table)) & 15) == 0,
+               "TF32 tiles need 16-byte aligned operands");
+  if (d > 256) {
+    set_error("TF32 tiles are built for entity dim <= 256 (got %d)", d);
+    return KGEB_ERR_UNSUPPORTED;
+  }
+  return KGEB_OK;
+}
+
+struct Plan {
+  int nqb;  // query blocks resident per job (1 or 2)
+  Params p;
+  size_t smem;
+};
+
+static Plan make_plan(int64_t B, int d, int64_t n_ent, int64_t e_lo) {
+  Plan pl;
+  const int ks = (d + SLAB_K - 1) / SLAB_K;
+  const int64_t n_qblocks = (B + TILE - 1) / TILE;
+  pl.nqb = (n_qblocks >= 2 && ks <= 4) ? 2 : 1;
+  const size_t q_bytes = (size_t)pl.nqb * ks * SLAB_BYTES;
+  const size_t fixed = 1024 /*align*/ + 512 /*barriers*/;
+  int stages = (int)((SMEM_BUDGET - fixed - q_bytes) / SLAB_BYTES);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  Params& p = pl.p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.n_ent = n_ent; p.e_lo = e_lo; p.d = d; p.ks = ks; p.stages = stages;
+  p.n_qgroups = (n_qblocks + pl.nqb - 1) / pl.nqb;
+  p.n_tiles = (n_ent + TILE - 1) / TILE;
+  int64_t chunks = kNumSMs / p.n_qgroups;
+  if (chunks < 1) chunks = 1;
+  if (chunks > p.n_tiles) chunks = p.n_tiles;
+  p.tiles_per_chunk = (p.n_tiles + chunks - 1) / chunks;
+  p.chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  pl.smem = q_bytes + (size_t)stages * SLAB_BYTES + fixed;
+  return pl;
+}
+
+template <int MODE>
+static int launch(const Plan& pl, const CUtensorMap& mq, const CUtensorMap& mw, cudaStream_t st) {
+  const int64_t jobs = pl.p.n_qgroups * pl.p.chunks;
+  const int grid = (int)(jobs < kNumSMs ? jobs : kNumSMs);
+  cudaError_t e;
+  if (pl.nqb == 2) {
+    e = cudaFuncSetAttribute(tc_tiles_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return cuda_status(e, "tc smem attribute");
+    tc_tiles_kernel<MODE, 2><<<grid, NUM_THREADS, pl.smem, st>>>(mq, mw, pl.p);
+  } else {
+    e = cudaFuncSetAttribute(tc_tiles_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return cuda_status(e, "tc smem attribute");
+    tc_tiles_kernel<MODE, 1><<<grid, NUM_THREADS, pl.smem, st>>>(mq, mw, pl.p);
+  }
+  KGEB_LAUNCH_CHECK("tc_tiles_kernel");
+  return KGEB_OK;
+}
+
+__global__ void stats_finalize_kernel(int loss, const float* __restrict__ partial, int64_t B, int64_t chunks,
+                                      const float* __restrict__ label_dot, float* __restrict__ rowstat) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  float s0 = (loss == KGEB_LOSS_KL) ? -INFINITY : 0.f, s1 = 0.f, s2 = 0.f;
+  for (int64_t c = 0; c < chunks; ++c) {
+    const float* q = partial + (c * B + r) * 4;
+    if (loss == KGEB_LOSS_KL) {
+      float mx = fmaxf(s0, q[0]);
+      float a = (s0 == -INFINITY) ? 0.f : s1 * __expf(s0 - mx);
+      float b = (q[0] == -INFINITY) ? 0.f : q[1] * __expf(q[0] - mx);
+      s0 = mx;
+      s1 = a + b;
+    } else {
+      s0 += q[0];
+    }
+    s2 += q[2];
+  }
+  float* o = rowstat + r * 4;
+  o[0] = s0; o[1] = s1; o[2] = s2; o[3] = label_dot[r];
+}
+
+// exact-fp32 sum over the label entries of each row that fall into this shard: warp per row
+__global__ void label_dot_kernel(const float* __restrict__ Q, int64_t B, int d, const float* __restrict__ table,
+                                 int64_t e_lo, int64_t n_ent, const int64_t* __restrict__ lab_off,
+                                 const int64_t* __restrict__ lab_col, float add_per_entry, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= B) return;
+  float total = 0.f;
+  if (lab_off) {
+    const float* q = Q + r * d;
+    for (int64_t i = lab_off[r]; i < lab_off[r + 1]; ++i) {
+      const int64_t c = lab_col[i] - e_lo;
+      if (c < 0 || c >= n_ent) continue;
+      const float* e = table + c * d;
+      float acc = 0.f;
+      for (int k = lane; k < d; k += 32) acc = fmaf(q[k], __ldg(e + k), acc);
+      total += warp_sum(acc) + add_per_entry;
+    }
+  }
+  if (lane == 0) out[r] = total;
+}
+
+}  // namespace tc
+
+int tc_score_all(const float* Q, int64_t B, int d, const float* table, int64_t m, float* out, int64_t ld,
+                 int64_t col_off, cudaStream_t st) {
+  int rc = tc::check_operands(Q, table, d);
+  if (rc) return rc;
+  tc::Plan pl = tc::make_plan(B, d, m, 0);
+  pl.p.out = out; pl.p.ld = ld; pl.p.col_off = col_off;
+  CUtensorMap mq, mw;
+  if ((rc = tc::make_map(&mq, Q, B, d)) || (rc = tc::make_map(&mw, table, m, d))) return rc;
+  return tc::launch<tc::MODE_SCORES>(pl, mq, mw, st);
+}
+
+int64_t tc_stats_partial_bytes(int64_t B) { return (int64_t)kNumSMs * B * 4 * (int64_t)sizeof(float) + B * 4 + 256; }
+
+int tc_fused_fwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
+                 const int64_t* lab_off, const int64_t* lab_col, float ls_keep, float ls_add, float offset,
+                 float* rowstat, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  int rc = tc::check_operands(Q, table, d);
+  if (rc) return rc;
+  KGEB_REQUIRE(ws_bytes >= tc_stats_partial_bytes(B), "fused_fwd(tf32): workspace too small");
+  float* partial = reinterpret_cast<float*>(ws);
+  tc::Plan pl = tc::make_plan(B, d, n_ent, e_lo);
+  float* label_dot = partial + pl.p.chunks * B * 4;
+  pl.p.loss = loss; pl.p.offset = offset; pl.p.partial = partial;
+  if (n_ent > 0) {
+    CUtensorMap mq, mw;
+    if ((rc = tc::make_map(&mq, Q, B, d)) || (rc = tc::make_map(&mw, table, n_ent, d))) return rc;
+    if ((rc = tc::launch<tc::MODE_STATS>(pl, mq, mw, st))) return rc;
+  }
+  tc::label_dot_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(Q, B, d, table, e_lo, n_ent, lab_off, lab_col,
+                                                                loss == KGEB_LOSS_BCE ? offset : 0.f, label_dot);
+  KGEB_LAUNCH_CHECK("label_dot");
+  tc::stats_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, partial, B, n_ent > 0 ? pl.p.chunks : 0,
+                                                                         label_dot, rowstat);
+  KGEB_LAUNCH_CHECK("stats_finalize");
+  return KGEB_OK;
+}
+
+int tc_rank_count(const float* Q, int64_t nq, int d, const float* table, int64_t e_lo, int64_t n_ent,
+                  const float* true_score, const void* true_ent, int idx64, const int64_t* f_off,
+                  const int64_t* f_col, const int64_t* t_off, const int64_t* t_col, int64_t* counts,
+                  cudaStream_t st) {
+  int rc = tc::check_operands(Q, table, d);
+  if (rc) return rc;
+  tc::Plan pl = tc::make_plan(nq, d, n_ent, e_lo);
+  pl.p.true_score = true_score; pl.p.true_ent = true_ent; pl.p.idx64 = idx64;
+  pl.p.f_off = f_off; pl.p.f_col = f_col; pl.p.t_off = t_off; pl.p.t_col = t_col;
+  pl.p.counts = reinterpret_cast<unsigned long long*>(counts);
+  CUtensorMap mq, mw;
+  if ((rc = tc::make_map(&mq, Q, nq, d)) || (rc = tc::make_map(&mw, table, n_ent, d))) return rc;
+  return tc::launch<tc::MODE_RANK>(pl, mq, mw, st);
+}
+
+int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent) { return 0; }
+
+int tc_fused_bwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
+                 const int64_t* lab_off, const int64_t* lab_col, const float* tscale, float ls_add, float offset,
+                 const float* lse, float inv_batch, const float* grad_scale, float* dQ, float* dTable, void* ws,
+                 int64_t ws_bytes, cudaStream_t st) {
+  set_error("fused_bwd: TF32 tensor-tile backward is not built yet");
+  return KGEB_ERR_UNSUPPORTED;
+}
+
+}  // namespace kgeb

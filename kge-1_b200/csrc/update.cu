@@ -1,0 +1,317 @@
+// Embedding gradient scatter and optimizer row updates.
+//  * sort-based, deterministic segment scatter-add (autograd of nn.Embedding in the reference,
+//    embedder/lookup_embedder.py:39-41,91-92): CUB radix sort of (row id, position) -- a stable sort, so
+//    equal ids keep ascending position order -- then one warp per distinct id sums its rows in that
+//    fixed order.  No float atomics anywhere.
+//  * Adagrad / Adam steps with torch.optim semantics (util/optimizer.py:10-17), dense and touched-rows.
+//  * device-side key lookup over KvsAllIndex arrays (indexing.py:36-55).
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace kgeb {
+
+struct ScatterWs {
+  int64_t* keys_in;
+  int64_t* keys_out;
+  int32_t* pos_in;
+  int32_t* pos_out;
+  int32_t* seg_id;     // inclusive scan of head flags (1-based segment number per sorted position)
+  int32_t* seg_start;  // [n+1]
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static size_t cub_temp_bytes(int64_t n) {
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const int64_t*)nullptr, (int64_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)n);
+  cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+  return a > b ? a : b;
+}
+
+static int64_t scatter_ws_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return (int64_t)(2 * align256(n * 8) + 3 * align256((n + 1) * 4) + align256(cub_temp_bytes(n)) + 256);
+}
+
+static bool carve(void* ws, int64_t bytes, int64_t n, ScatterWs& w) {
+  if (!ws || bytes < scatter_ws_bytes(n)) return false;
+  char* p = reinterpret_cast<char*>(ws);
+  p = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(p)));
+  w.keys_in = reinterpret_cast<int64_t*>(p); p += align256(n * 8);
+  w.keys_out = reinterpret_cast<int64_t*>(p); p += align256(n * 8);
+  w.pos_in = reinterpret_cast<int32_t*>(p); p += align256((n + 1) * 4);
+  w.pos_out = reinterpret_cast<int32_t*>(p); p += align256((n + 1) * 4);
+  w.seg_id = reinterpret_cast<int32_t*>(p); p += align256((n + 1) * 4);
+  w.cub_tmp = p;
+  w.cub_bytes = cub_temp_bytes(n);
+  w.seg_start = w.pos_in;  // pos_in is dead after the sort; reuse it for the segment starts
+  return true;
+}
+
+__global__ void iota_keys_kernel(const void* idx, int idx64, int64_t n, int64_t* keys, int32_t* pos) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = load_index(idx, idx64, i);
+    pos[i] = (int32_t)i;
+  }
+}
+__global__ void head_flags_kernel(const int64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ flags) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+__global__ void seg_starts_kernel(const int64_t* __restrict__ keys, const int32_t* __restrict__ seg_id, int64_t n,
+                                  int32_t* __restrict__ seg_start, int64_t* __restrict__ num_uniq) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    if (i == 0 || keys[i] != keys[i - 1]) seg_start[seg_id[i] - 1] = (int32_t)i;
+    if (i == n - 1) {
+      seg_start[seg_id[i]] = (int32_t)n;
+      if (num_uniq) *num_uniq = seg_id[i];
+    }
+  }
+}
+
+// one warp per segment; rows summed in ascending original position
+template <bool DENSE>
+__global__ void __launch_bounds__(256)
+segment_sum_kernel(const int64_t* __restrict__ keys, const int32_t* __restrict__ pos,
+                   const int32_t* __restrict__ seg_id, const int32_t* __restrict__ seg_start, int64_t n, int d,
+                   const float* __restrict__ rows, float* __restrict__ dense, int64_t vocab,
+                   int64_t* __restrict__ uniq_ids, float* __restrict__ uniq_rows) {
+  const int lane = threadIdx.x & 31;
+  const int nseg = seg_id[n - 1];
+  int64_t seg = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (; seg < nseg; seg += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int b = seg_start[seg], e = seg_start[seg + 1];
+    const int64_t key = keys[b];
+    if (DENSE && (key < 0 || key >= vocab)) continue;
+    for (int c0 = lane * 4; c0 < d; c0 += 128) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const bool full = (c0 + 3 < d) && ((d & 3) == 0);
+      int i = b;
+      for (; i < e; ++i) {
+        const float* r = rows + (int64_t)pos[i] * d + c0;
+        if (full) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(r));
+          a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+        } else {
+          a0 += r[0];
+          if (c0 + 1 < d) a1 += r[1];
+          if (c0 + 2 < d) a2 += r[2];
+          if (c0 + 3 < d) a3 += r[3];
+        }
+      }
+      float* dst = DENSE ? dense + key * d + c0 : uniq_rows + seg * (int64_t)d + c0;
+      if (DENSE) {
+        dst[0] += a0;
+        if (c0 + 1 < d) dst[1] += a1;
+        if (c0 + 2 < d) dst[2] += a2;
+        if (c0 + 3 < d) dst[3] += a3;
+      } else {
+        dst[0] = a0;
+        if (c0 + 1 < d) dst[1] = a1;
+        if (c0 + 2 < d) dst[2] = a2;
+        if (c0 + 3 < d) dst[3] = a3;
+      }
+    }
+    if (!DENSE && lane == 0) uniq_ids[seg] = key;
+  }
+}
+
+static int sort_and_segment(const void* idx, int idx64, int64_t n, int64_t vocab, ScatterWs& w, int64_t* num_uniq,
+                            cudaStream_t st) {
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  iota_keys_kernel<<<blocks, 256, 0, st>>>(idx, idx64, n, w.keys_in, w.pos_in);
+  int end_bit = 64;
+  if (vocab > 0) {
+    end_bit = 1;
+    while (end_bit < 63 && ((int64_t)1 << end_bit) < vocab) ++end_bit;
+  }
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, w.cub_bytes, w.keys_in, w.keys_out, w.pos_in, w.pos_out,
+                                                  (int)n, 0, end_bit, st);
+  if (e != cudaSuccess) return cuda_status(e, "radix sort");
+  head_flags_kernel<<<blocks, 256, 0, st>>>(w.keys_out, n, w.seg_id);
+  e = cub::DeviceScan::InclusiveSum(w.cub_tmp, w.cub_bytes, w.seg_id, w.seg_id, (int)n, st);
+  if (e != cudaSuccess) return cuda_status(e, "segment scan");
+  seg_starts_kernel<<<blocks, 256, 0, st>>>(w.keys_out, w.seg_id, n, w.seg_start, num_uniq);
+  KGEB_LAUNCH_CHECK("segment starts");
+  return KGEB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// optimizers
+// ------------------------------------------------------------------------------------------
+__global__ void adagrad_dense_kernel(float* __restrict__ W, float* __restrict__ state, const float* __restrict__ grad,
+                                     int64_t numel, float clr, float eps, float wd) {
+  int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < numel; i += stride) {
+    float4 w = *reinterpret_cast<float4*>(W + i);
+    float4 s = *reinterpret_cast<float4*>(state + i);
+    float4 g = *reinterpret_cast<const float4*>(grad + i);
+    g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
+    s.x = fmaf(g.x, g.x, s.x); s.y = fmaf(g.y, g.y, s.y); s.z = fmaf(g.z, g.z, s.z); s.w = fmaf(g.w, g.w, s.w);
+    w.x -= clr * g.x / (sqrtf(s.x) + eps);
+    w.y -= clr * g.y / (sqrtf(s.y) + eps);
+    w.z -= clr * g.z / (sqrtf(s.z) + eps);
+    w.w -= clr * g.w / (sqrtf(s.w) + eps);
+    *reinterpret_cast<float4*>(W + i) = w;
+    *reinterpret_cast<float4*>(state + i) = s;
+  }
+  // tail (numel % 4): handled by the thread whose i lands on it
+  if (i < numel && i + 3 >= numel) {
+    for (int64_t j = i; j < numel; ++j) {
+      float g = fmaf(wd, W[j], grad[j]);
+      float s = fmaf(g, g, state[j]);
+      state[j] = s;
+      W[j] -= clr * g / (sqrtf(s) + eps);
+    }
+  }
+}
+
+__global__ void adagrad_rows_kernel(float* __restrict__ W, float* __restrict__ state, const int64_t* __restrict__ ids,
+                                    const float* __restrict__ g, const int64_t* __restrict__ num_rows, int64_t max_rows,
+                                    int d, float clr, float eps) {
+  const int64_t nrows = min(*num_rows, max_rows);
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; t < nrows * d; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = t / d;
+    int c = (int)(t - r * d);
+    int64_t dst = ids[r] * d + c;
+    float gv = g[t];
+    float s = fmaf(gv, gv, state[dst]);
+    state[dst] = s;
+    W[dst] -= clr * gv / (sqrtf(s) + eps);
+  }
+}
+
+__global__ void adam_dense_kernel(float* __restrict__ W, float* __restrict__ m, float* __restrict__ v,
+                                  const float* __restrict__ grad, int64_t numel, float lr, float b1, float b2, float eps,
+                                  float wd, float bc1, float bc2) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  for (; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+    float w = W[i];
+    float g = fmaf(wd, w, grad[i]);
+    float mi = m[i] + (1.f - b1) * (g - m[i]);  // lerp, as torch's exp_avg.lerp_(grad, 1-beta1)
+    float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    W[i] = w - step_size * (mi / denom);
+  }
+}
+
+__global__ void csr_lookup_kernel(const int64_t* __restrict__ keys, int64_t nk, const int64_t* __restrict__ q,
+                                  int64_t n, int64_t* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t a = q[2 * i], b = q[2 * i + 1];
+  int64_t lo = 0, hi = nk;
+  while (lo < hi) {  // lexicographic lower bound over [K,2]
+    int64_t mid = (lo + hi) >> 1;
+    int64_t ka = keys[2 * mid], kb = keys[2 * mid + 1];
+    if (ka < a || (ka == a && kb < b)) lo = mid + 1; else hi = mid;
+  }
+  out[i] = (lo < nk && keys[2 * lo] == a && keys[2 * lo + 1] == b) ? lo : -1;
+}
+
+}  // namespace kgeb
+
+using namespace kgeb;
+
+extern "C" {
+
+int64_t kgeb_scatter_workspace_bytes(int64_t n) { return scatter_ws_bytes(n); }
+
+int kgeb_scatter_add_rows(const void* idx, int idx64, const float* rows, int64_t n, int d, float* dense,
+                          int64_t vocab, void* workspace, int64_t workspace_bytes, void* stream) {
+  KGEB_REQUIRE(idx && rows && dense && n >= 0 && d > 0 && vocab > 0, "scatter_add_rows: bad arguments");
+  KGEB_REQUIRE(n < ((int64_t)1 << 31), "scatter_add_rows: n too large");
+  if (n == 0) return KGEB_OK;
+  ScatterWs w;
+  KGEB_REQUIRE(carve(workspace, workspace_bytes, n, w), "scatter_add_rows: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  int rc = sort_and_segment(idx, idx64, n, vocab, w, nullptr, st);
+  if (rc) return rc;
+  int64_t blocks = (n + 7) / 8;
+  int grid = (int)(blocks > (int64_t)kNumSMs * 16 ? (int64_t)kNumSMs * 16 : blocks);
+  segment_sum_kernel<true><<<grid, 256, 0, st>>>(w.keys_out, w.pos_out, w.seg_id, w.seg_start, n, d, rows, dense, vocab,
+                                                 nullptr, nullptr);
+  KGEB_LAUNCH_CHECK("segment_sum(dense)");
+  return KGEB_OK;
+}
+
+int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int64_t n, int d, int64_t* uniq_ids,
+                             float* uniq_rows, int64_t* num_uniq, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  KGEB_REQUIRE(idx && rows && uniq_ids && uniq_rows && num_uniq && n >= 0 && d > 0, "segment_reduce_rows: bad arguments");
+  KGEB_REQUIRE(n < ((int64_t)1 << 31), "segment_reduce_rows: n too large");
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {
+    cudaMemsetAsync(num_uniq, 0, sizeof(int64_t), st);
+    return KGEB_OK;
+  }
+  ScatterWs w;
+  KGEB_REQUIRE(carve(workspace, workspace_bytes, n, w), "segment_reduce_rows: workspace too small");
+  int rc = sort_and_segment(idx, idx64, n, 0, w, num_uniq, st);
+  if (rc) return rc;
+  int64_t blocks = (n + 7) / 8;
+  int grid = (int)(blocks > (int64_t)kNumSMs * 16 ? (int64_t)kNumSMs * 16 : blocks);
+  segment_sum_kernel<false><<<grid, 256, 0, st>>>(w.keys_out, w.pos_out, w.seg_id, w.seg_start, n, d, rows, nullptr, 0,
+                                                  uniq_ids, uniq_rows);
+  KGEB_LAUNCH_CHECK("segment_sum(sparse)");
+  return KGEB_OK;
+}
+
+int kgeb_adagrad_dense(float* W, float* state, const float* grad, int64_t numel, float clr, float eps,
+                       float weight_decay, void* stream) {
+  KGEB_REQUIRE(W && state && grad && numel >= 0, "adagrad_dense: bad arguments");
+  KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(state) |
+                 reinterpret_cast<uintptr_t>(grad)) & 15) == 0, "adagrad_dense: pointers must be 16-byte aligned");
+  if (numel == 0) return KGEB_OK;
+  int64_t blocks = (numel / 4 + 255) / 256 + 1;
+  int grid = (int)(blocks > (int64_t)kNumSMs * 8 ? (int64_t)kNumSMs * 8 : blocks);
+  adagrad_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, state, grad, numel, clr, eps, weight_decay);
+  KGEB_LAUNCH_CHECK("adagrad_dense");
+  return KGEB_OK;
+}
+
+int kgeb_adagrad_rows(float* W, float* state, const int64_t* row_ids, const float* row_grads,
+                      const int64_t* num_rows_dev, int64_t max_rows, int d, float clr, float eps, void* stream) {
+  KGEB_REQUIRE(W && state && row_ids && row_grads && num_rows_dev && max_rows >= 0 && d > 0, "adagrad_rows: bad arguments");
+  if (max_rows == 0) return KGEB_OK;
+  int64_t blocks = (max_rows * d + 255) / 256;
+  int grid = (int)(blocks > (int64_t)kNumSMs * 8 ? (int64_t)kNumSMs * 8 : blocks);
+  adagrad_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, state, row_ids, row_grads, num_rows_dev, max_rows, d, clr, eps);
+  KGEB_LAUNCH_CHECK("adagrad_rows");
+  return KGEB_OK;
+}
+
+int kgeb_adam_dense(float* W, float* exp_avg, float* exp_avg_sq, const float* grad, int64_t numel, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2,
+                    void* stream) {
+  KGEB_REQUIRE(W && exp_avg && exp_avg_sq && grad && numel >= 0, "adam_dense: bad arguments");
+  if (numel == 0) return KGEB_OK;
+  int64_t blocks = (numel + 255) / 256;
+  int grid = (int)(blocks > (int64_t)kNumSMs * 8 ? (int64_t)kNumSMs * 8 : blocks);
+  adam_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, exp_avg, exp_avg_sq, grad, numel, lr, beta1, beta2, eps,
+                                                         weight_decay, bias_corr1, bias_corr2);
+  KGEB_LAUNCH_CHECK("adam_dense");
+  return KGEB_OK;
+}
+
+int kgeb_csr_lookup(const int64_t* keys, int64_t num_keys, const int64_t* query_pairs, int64_t n, int64_t* row_out,
+                    void* stream) {
+  KGEB_REQUIRE(keys && query_pairs && row_out && num_keys >= 0 && n >= 0, "csr_lookup: bad arguments");
+  if (n == 0) return KGEB_OK;
+  csr_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(keys, num_keys, query_pairs, n, row_out);
+  KGEB_LAUNCH_CHECK("csr_lookup");
+  return KGEB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,324 @@
+"""Batch bodies of the reference's training jobs and the entity-ranking evaluation, on top of the
+CUDA path.  Two forms of each:
+
+* the reference's own flow (`fused=False`): `model.score_sp/po/spo` -> `loss(scores, labels) / batch_size`
+  -> `.backward()`, line for line as kge/job/train.py:679-756, 823-999, 1032-1062 -- this is what the
+  unmodified reference jobs execute when the drop-in model classes are registered;
+* the fused flow (`fused=True`): query vectors -> fused score+loss kernels; the [B,E] matrix is never
+  materialised, both 1vsAll directions / both KvsAll query types go through one launch.
+Evaluation (`EntityRankingJob`) follows kge/job/entity_ranking.py:79-426 with the chunk loop and the
+three dense filter passes replaced by the fused score-and-count kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import fused, lib, ops
+from .index import KvsAllIndex, gather_csr_rows, merge_sorted_csr
+from .model import KgeModel, ReciprocalRelationsModel
+
+S, P, O = 0, 1, 2
+
+
+# ---------------------------------------------------------------------------------------------
+# losses on materialised scores (kge/util/loss.py:137-159, 192-213)
+# ---------------------------------------------------------------------------------------------
+class KgeLoss:
+    def __init__(self, name: str, offset: float = 0.0):
+        if name not in ("kl", "bce"):
+            raise ValueError(f"train.loss={name} is not on the hot path (built: kl, bce)")
+        self.name = name
+        self.offset = 0.0 if (offset is None or (isinstance(offset, float) and math.isnan(offset))) else float(offset)
+        self.kind = lib.LOSS_KL if name == "kl" else lib.LOSS_BCE
+
+    @staticmethod
+    def create(name: str, loss_arg: float = float("nan")) -> "KgeLoss":
+        return KgeLoss(name, loss_arg)
+
+    def __call__(self, scores, labels, **kwargs):
+        if self.name == "kl":
+            if labels.dim() == 1:
+                return F.cross_entropy(scores, labels.long(), reduction="sum")
+            return F.kl_div(F.log_softmax(scores, dim=1), F.normalize(labels.float(), p=1, dim=1), reduction="sum")
+        if labels.dim() == 1:
+            m = torch.zeros(scores.shape, device=scores.device, dtype=torch.float)
+            m[torch.arange(len(scores), device=scores.device), labels.long()] = 1.0
+            labels = m
+        if self.offset != 0.0:
+            scores = scores + self.offset
+        return F.binary_cross_entropy_with_logits(scores.reshape(-1), labels.reshape(-1), reduction="sum")
+
+
+class ProcessBatchResult:
+    def __init__(self, avg_loss, size, total_loss=None):
+        self.avg_loss, self.size = avg_loss, size
+        self.total_loss = avg_loss if total_loss is None else total_loss
+
+
+# ---------------------------------------------------------------------------------------------
+# training jobs
+# ---------------------------------------------------------------------------------------------
+class TrainingJob:
+    """run_epoch's step skeleton (train.py:309-376): zero_grad -> batch -> penalties -> optimizer.step."""
+
+    def __init__(self, model: KgeModel, optimizer, loss: KgeLoss, fused_path: bool = True,
+                 math_mode: int = lib.MATH_FP32, shard: Optional[fused.Shard] = None):
+        self.model, self.optimizer, self.loss = model, optimizer, loss
+        self.fused_path, self.math_mode, self.shard = fused_path, math_mode, shard
+        self.device = model.get_s_embedder().weight.device
+        self.pre_batch_hooks: List = []
+        model.prepare_job(self)
+
+    def step(self, batch_index: int, batch: dict) -> ProcessBatchResult:
+        for f in self.pre_batch_hooks:
+            f(self)
+        self.optimizer.zero_grad()
+        res = self._process_batch(batch_index, batch)
+        penalty = 0.0
+        for _, value in self.model.penalty(batch=batch):
+            value.backward()
+            penalty += value.item()
+        res.penalty = penalty
+        self.optimizer.step()
+        return res
+
+    def _use_fused(self) -> bool:
+        return self.fused_path and self.model.get_scorer().kind == lib.DOT and self.model.get_s_embedder().dim <= 256
+
+
+class TrainingJob1vsAll(TrainingJob):
+    def _process_batch(self, batch_index, batch) -> ProcessBatchResult:
+        triples = batch["triples"].to(self.device)
+        b = len(triples)
+        if self._use_fused():
+            # both directions as 2B queries in one launch (gradients accumulate before one step, train.py:375)
+            if isinstance(self.model, ReciprocalRelationsModel):
+                q_po = self.model.queries(lib.SP_, triples[:, 2], triples[:, 1] + self.model.num_relations)
+            else:
+                q_po = self.model.queries(lib._PO, triples[:, 2], triples[:, 1])
+            q = torch.cat((self.model.queries(lib.SP_, triples[:, 0], triples[:, 1]), q_po))
+            lab_off = torch.arange(2 * b + 1, dtype=torch.int64, device=self.device)
+            lab_col = torch.cat((triples[:, 2], triples[:, 0])).long().contiguous()
+            rows = fused.all_entity_loss(q, self.model.get_o_embedder().embed_all(), lab_off, lab_col,
+                                         self.loss.kind, b, 0.0, self.loss.offset, self.math_mode, self.shard)
+            loss_value = rows.sum()
+            loss_value.backward()
+            return ProcessBatchResult(loss_value.item(), b)
+        scores_sp = self.model.score_sp(triples[:, 0], triples[:, 1])
+        loss_value_sp = self.loss(scores_sp, triples[:, 2]) / b
+        loss_value = loss_value_sp.item()
+        loss_value_sp.backward()
+        scores_po = self.model.score_po(triples[:, 1], triples[:, 2])
+        loss_value_po = self.loss(scores_po, triples[:, 0]) / b
+        loss_value += loss_value_po.item()
+        loss_value_po.backward()
+        return ProcessBatchResult(loss_value, b)
+
+
+class TrainingJobKvsAll(TrainingJob):
+    """Query types sp_ and _po (config-default.yaml KvsAll.query_types; s_o stays on the reference's own path)."""
+
+    def __init__(self, model, optimizer, loss, num_entities: int, num_relations: int, label_smoothing: float = 0.0,
+                 **kw):
+        super().__init__(model, optimizer, loss, **kw)
+        self.num_entities, self.num_relations = num_entities, num_relations
+        self.label_smoothing = label_smoothing
+
+    def _process_batch(self, batch_index, batch) -> ProcessBatchResult:
+        queries = batch["queries"].to(self.device)
+        b = len(queries)
+        coords = batch["label_coords"].to(self.device)
+        qt = batch["query_type_indexes"]  # stays on the host, as in train.py:685
+        rows_of = [(qt == t).nonzero().view(-1) for t in (0, 1)]
+        if self._use_fused() and not (self.loss.kind == lib.LOSS_KL and self.label_smoothing > 0):
+            order = torch.cat(rows_of).to(self.device)                 # fused row order: sp_ rows then _po rows
+            n_sp = len(rows_of[0])
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(b, device=self.device)
+            lab_off, lab_col = fused.csr_from_coords(torch.stack((inv[coords[:, 0].long()], coords[:, 1].long()), 1), b)
+            qs = queries[order]
+            parts = []
+            if n_sp > 0:
+                parts.append(self.model.queries(lib.SP_, qs[:n_sp, 0], qs[:n_sp, 1]))
+            if n_sp < b:
+                if isinstance(self.model, ReciprocalRelationsModel):
+                    parts.append(self.model.queries(lib.SP_, qs[n_sp:, 1], qs[n_sp:, 0] + self.model.num_relations))
+                else:
+                    parts.append(self.model.queries(lib._PO, qs[n_sp:, 1], qs[n_sp:, 0]))
+            q = torch.cat(parts) if len(parts) > 1 else parts[0]
+            rows = fused.all_entity_loss(q, self.model.get_o_embedder().embed_all(), lab_off, lab_col, self.loss.kind,
+                                         b, self.label_smoothing, self.loss.offset, self.math_mode, self.shard)
+            total = rows.sum()
+            total.backward()
+            # train.py:747 reports the value of the last non-empty query type only
+            reported = rows[n_sp:].sum() if n_sp < b else rows.sum()
+            return ProcessBatchResult(reported.item(), b, total.item())
+
+        labels = torch.zeros(b, max(self.num_entities, self.num_relations), device=self.device)
+        labels.index_put_((coords[:, 0].long(), coords[:, 1].long()),
+                          torch.ones(len(coords), device=self.device), accumulate=True)
+        reported, total = 0.0, 0.0
+        for t, rows in enumerate(rows_of):
+            if len(rows) == 0:
+                continue
+            rows = rows.to(self.device)
+            lab = labels[rows, : self.num_entities]
+            if self.label_smoothing > 0.0:
+                lab = (1.0 - self.label_smoothing) * lab + 1.0 / lab.size(1)
+            if t == 0:
+                scores = self.model.score_sp(queries[rows, 0], queries[rows, 1])
+            else:
+                scores = self.model.score_po(queries[rows, 0], queries[rows, 1])
+            loss_value = self.loss(scores, lab) / b
+            reported = loss_value.item()
+            total += reported
+            loss_value.backward()
+        return ProcessBatchResult(reported, b, total)
+
+
+class TrainingJobNegativeSampling(TrainingJob):
+    """train.py:823-999.  fused: each positive's query vector is built once and scored against its
+    1+N candidates (no B*(1+N) triple expansion); otherwise implementation "triple" as in the reference."""
+
+    def _process_batch(self, batch_index, batch) -> ProcessBatchResult:
+        triples = batch["triples"].to(self.device)
+        negs = [ns.to(self.device) for ns in batch["negative_samples"]]
+        b = len(triples)
+        total = 0.0
+        for slot in (S, P, O):
+            n = negs[slot].shape[1] if negs[slot].dim() == 2 else 0
+            if n <= 0:
+                continue
+            labels = torch.zeros(b, 1 + n, device=self.device)
+            labels[:, 0] = 1
+            if self.fused_path and slot != P and not isinstance(self.model, ReciprocalRelationsModel):
+                if slot == O:
+                    q = self.model.queries(lib.SP_, triples[:, S], triples[:, P])
+                else:
+                    q = self.model.queries(lib._PO, triples[:, O], triples[:, P])
+                cand = torch.cat((triples[:, [slot]], negs[slot].long()), 1).contiguous()
+                emb = self.model.get_o_embedder()
+                scores = ops.pairs_score(self.model.get_scorer().kind, q, emb.embed_all(), cand, emb.sparse)
+            else:
+                rep = triples.repeat(1, 1 + n).view(-1, 3)
+                rep[:, slot] = torch.cat((triples[:, [slot]], negs[slot].long()), 1).view(-1)
+                scores = self.model.score_spo(rep[:, 0], rep[:, 1], rep[:, 2],
+                                              direction="s" if slot == S else ("o" if slot == O else "p")).view(b, -1)
+            loss_value = self.loss(scores, labels, num_negatives=n) / b
+            total += loss_value.item()
+            loss_value.backward()
+        return ProcessBatchResult(total, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# evaluation
+# ---------------------------------------------------------------------------------------------
+class EntityRankingJob:
+    """Filtered entity ranking (kge/job/entity_ranking.py), fused score-and-count form."""
+
+    def __init__(self, model: KgeModel, num_entities: int, filter_splits: Sequence, test_split=None,
+                 batch_size: int = 100, tie_handling: str = "rounded_mean_rank", hits_at_k_s=(1, 3, 10, 50, 100, 200, 300, 400, 500, 1000),
+                 math_mode: int = lib.MATH_FP32, shard: Optional[fused.Shard] = None):
+        if tie_handling not in ("rounded_mean_rank", "best_rank", "worst_rank"):
+            raise ValueError(f"entity_ranking.tie_handling={tie_handling}")
+        self.model, self.num_entities = model, num_entities
+        self.batch_size, self.tie_handling = batch_size, tie_handling
+        self.hits_at_k_s = [k for k in hits_at_k_s if k <= num_entities]  # eval.py:19-24
+        self.math_mode, self.shard = math_mode, shard
+        self.device = model.get_s_embedder().weight.device
+        # _prepare (entity_ranking.py:27-51): sp->o and po->s indexes per filter split (+ test)
+        self.filter_indexes = [(KvsAllIndex(t, "sp"), KvsAllIndex(t, "po")) for t in filter_splits]
+        self.test_indexes = (KvsAllIndex(test_split, "sp"), KvsAllIndex(test_split, "po")) if test_split is not None else None
+
+    def _filter_csr(self, indexes, s, p, o):
+        """Device-side replacement of _collate / get_sp_po_coords_from_spo_batch (job/util.py:5-38):
+        rows 0..B-1 = known objects of (s,p); rows B..2B-1 = known subjects of (p,o)."""
+        b = len(s)
+        parts = []
+        for sp_idx, po_idx in indexes:
+            _, off, val = sp_idx.device_arrays(self.device)
+            o_off, o_col = gather_csr_rows(off, val, sp_idx.lookup(torch.stack((s, p), 1)))
+            _, off, val = po_idx.device_arrays(self.device)
+            s_off, s_col = gather_csr_rows(off, val, po_idx.lookup(torch.stack((p, o), 1)))
+            parts.append((torch.cat((o_off, s_off[1:] + o_off[-1])), torch.cat((o_col, s_col))))
+        return parts
+
+    def _get_ranks(self, rank, ties):
+        if self.tie_handling == "rounded_mean_rank":
+            return rank + ties // 2
+        if self.tie_handling == "best_rank":
+            return rank
+        return rank + ties - 1
+
+    @torch.no_grad()
+    def rank_batch(self, batch: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """One batch [B,3] -> 0-based ranks per name s_raw, o_raw, s_filt, o_filt (, s_filt_test, o_filt_test)."""
+        model = self.model
+        t = batch.to(self.device).long()
+        s, p, o = t[:, 0].contiguous(), t[:, 1].contiguous(), t[:, 2].contiguous()
+        b = len(t)
+        o_true = model.score_spo(s, p, o, "o").view(-1)   # entity_ranking.py:139-140
+        s_true = model.score_spo(s, p, o, "s").view(-1)
+        if isinstance(model, ReciprocalRelationsModel):
+            q_po = model.queries(lib.SP_, o, p + model.num_relations)
+        else:
+            q_po = model.queries(lib._PO, o, p)
+        q = torch.cat((model.queries(lib.SP_, s, p), q_po)).contiguous()
+        true_ent = torch.cat((o, s)).contiguous()
+        true_score = torch.cat((o_true, s_true)).contiguous()
+        parts = self._filter_csr(self.filter_indexes, s, p, o)
+        filt = merge_sorted_csr(parts, 2 * b) if parts else None
+        filt_test = None
+        if self.test_indexes is not None:
+            filt_test = merge_sorted_csr(parts + self._filter_csr([self.test_indexes], s, p, o), 2 * b)
+        scorer = model.get_scorer()
+        table = model.get_o_embedder().embed_all()
+        counts = fused.rank_counts(scorer.kind, q, table, true_score, true_ent, filt, filt_test,
+                                   scorer._math(table) if self.math_mode == lib.MATH_TF32 else lib.MATH_FP32,
+                                   self.shard)
+        out = {}
+        for j, name in enumerate(("_raw", "_filt", "_filt_test")):
+            if name == "_filt_test" and filt_test is None:
+                continue
+            ranks = self._get_ranks(counts[:, 2 * j], counts[:, 2 * j + 1])
+            out["o" + name], out["s" + name] = ranks[:b], ranks[b:]
+        return out
+
+    def _compute_metrics(self, hist: torch.Tensor, suffix="") -> Dict[str, float]:
+        """entity_ranking.py:553-577."""
+        metrics = {}
+        n = torch.sum(hist).item()
+        ranks = torch.arange(1, self.num_entities + 1, device=hist.device).float()
+        metrics["mean_rank" + suffix] = (torch.sum(hist * ranks).item() / n) if n > 0.0 else 0.0
+        metrics["mean_reciprocal_rank" + suffix] = (torch.sum(hist * (1.0 / ranks)).item() / n) if n > 0.0 else 0.0
+        kmax = max(self.hits_at_k_s)
+        hits = (torch.cumsum(hist[:kmax], dim=0) / n).tolist() if n > 0.0 else [0.0] * kmax
+        for k in self.hits_at_k_s:
+            metrics["hits_at_{}{}".format(k, suffix)] = hits[k - 1]
+        return metrics
+
+    @torch.no_grad()
+    def run(self, triples) -> Dict[str, object]:
+        was_training = self.model.training
+        self.model.eval()
+        triples = torch.as_tensor(triples)
+        names = ["_raw", "_filt"] + (["_filt_test"] if self.test_indexes is not None else [])
+        hists = {n: torch.zeros(self.num_entities, device=self.device) for n in names}
+        all_ranks: Dict[str, List[torch.Tensor]] = {}
+        for lo in range(0, len(triples), self.batch_size):
+            res = self.rank_batch(triples[lo:lo + self.batch_size])
+            for k, v in res.items():
+                all_ranks.setdefault(k, []).append(v)
+                # hist_all (eval.py:138-171): a bincount instead of the Python loop over ranks
+                hists[k[1:]] += torch.bincount(v, minlength=self.num_entities).float()
+        suffix = {"_raw": "", "_filt": "_filtered", "_filt_test": "_filtered_with_test"}
+        metrics = {}
+        for n in names:
+            metrics.update(self._compute_metrics(hists[n], suffix[n]))
+        if was_training:
+            self.model.train()
+        return {"metrics": metrics, "ranks": {k: torch.cat(v) for k, v in all_ranks.items()}}

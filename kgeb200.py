@@ -1,0 +1,10 @@
+"""Alias: `import kgeb200` == the package in the directory `kge-1_b200/` (not a valid Python identifier)."""
+import importlib
+import os
+import sys
+
+_root = os.path.dirname(os.path.abspath(__file__))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+_pkg = importlib.import_module("kge-1_b200")
+sys.modules[__name__] = _pkg

@@ -226,10 +226,13 @@ def gen_eval(out):
         opts.update(extra)
         job = make_job(model, g, opts)
         with torch.no_grad():
-            # coarse weights => plenty of exact score ties
+            # coarse dyadic weights (multiples of 1/16, |w| <= 1/2) => plenty of exact score ties, and every
+            # product / sum is exact in fp32 (and in TF32) whatever the summation order, so tie counts are
+            # reproducible bit-for-bit by any implementation (rotate: sin/cos/sqrt make ties a matter of chance)
             for emb in (job.model.get_s_embedder(), job.model.get_p_embedder()):
                 w = emb._embeddings.weight
-                w.copy_(torch.round(w * 20) / 20 if model != "rotate" else torch.round(w * 4) / 4)
+                w.copy_(torch.clamp(torch.round(w * 16 * 2.5) / 16, -0.5, 0.5) if model != "rotate"
+                        else torch.round(w * 4) / 4)
         ev = job.valid_job
         ev._prepare()
         rec = []

@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C-ABI, kge-1_b200/) against golden vectors produced by the
+unmodified reference and against the oracle on seeded inputs.  Needs a B200: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): fp32 paths |a-b| <= 1e-5 * max|ref| ; TF32 tensor tiles
+|a-b| <= 2e-3 * max|ref| (documented in DESIGN.md) ; indices / rank counts bit-exact."""
+import ast
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import kge_oracle as ko  # noqa: E402
+
+T = torch.from_numpy
+TAGS = ["distmult", "complex", "cp", "simple", "rescal", "transe_l1", "transe_l2", "rotate_l1", "rotate_l2"]
+E, R = 53, 7
+
+
+@pytest.fixture(scope="module")
+def kb():
+    import kgeb200
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    kgeb200.lib.load()
+    return kgeb200
+
+
+def close(got, ref, rtol=1e-5, what=""):
+    got = got.detach().cpu().double().numpy() if isinstance(got, torch.Tensor) else np.asarray(got, dtype=np.float64)
+    ref = ref.detach().cpu().double().numpy() if isinstance(ref, torch.Tensor) else np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    scale = max(np.abs(ref).max(), 1e-30) if ref.size else 1.0
+    err = np.abs(got - ref).max() if ref.size else 0.0
+    assert err <= rtol * scale + 1e-30, f"{what}: max abs err {err:.3e} > {rtol:g} * {scale:.3e}"
+
+
+def split_tag(tag):
+    m = tag.split("_l")[0]
+    return m, (float(tag.split("_l")[1]) if "_l" in tag else 1.0)
+
+
+def make_model(kb, model, ent, rel, l_norm=1.0, **kw):
+    m = kb.KgeModel(model, ent.shape[0], rel.shape[0], ent.shape[1], l_norm=l_norm, relation_dim=rel.shape[1], **kw).cuda()
+    with torch.no_grad():
+        m.get_s_embedder().weight.copy_(torch.as_tensor(ent))
+        m.get_p_embedder().weight.copy_(torch.as_tensor(rel))
+    return m
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", TAGS)
+def test_scores_match_reference_golden(kb, golden, tag):
+    g = golden("scores")
+    model, ln = split_tag(tag)
+    m = make_model(kb, model, g[f"{tag}.ent"], g[f"{tag}.rel"], ln)
+    s, p, o, sub = (T(g[k]).cuda() for k in ("idx_s", "idx_p", "idx_o", "subset"))
+    with torch.no_grad():
+        close(m.score_spo(s, p, o), g[f"{tag}.spo"], what="spo")
+        close(m.score_spo(s.int(), p.int(), o.int()), g[f"{tag}.spo_i32"], what="spo int32")
+        close(m.score_sp(s, p), g[f"{tag}.sp"], what="sp_")
+        close(m.score_po(p, o), g[f"{tag}.po"], what="_po")
+        close(m.score_sp(s, p, sub), g[f"{tag}.sp_sub"], what="sp_ subset")
+        close(m.score_sp_po(s, p, o, sub), g[f"{tag}.sp_po_sub"], what="sp_po subset")
+        close(m.score_so(s, o), g[f"{tag}.so"], what="s_o")
+        # embedder API
+        close(m.get_s_embedder().embed(s.int()), g[f"{tag}.ent"][g["idx_s"]], rtol=0, what="embed")
+        assert m.get_s_embedder().embed_all().shape == (E, g[f"{tag}.ent"].shape[1])
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_score_gradients_match_oracle(kb, golden, tag):
+    g = golden("scores")
+    model, ln = split_tag(tag)
+    ent, rel = T(g[f"{tag}.ent"]), T(g[f"{tag}.rel"])
+    s, p, o = (T(g[k]) for k in ("idx_s", "idx_p", "idx_o"))
+    gen = torch.Generator().manual_seed(3)
+    for form in ("spo", "sp", "po"):
+        prm = ko.Params(ent, rel)
+        if form == "spo":
+            ref = ko.score_spo(model, prm.ent, prm.rel, s, p, o, ln)
+        elif form == "sp":
+            ref = ko.score_sp(model, prm.ent, prm.rel, s, p, l_norm=ln)
+        else:
+            ref = ko.score_po(model, prm.ent, prm.rel, p, o, l_norm=ln)
+        up = torch.randn(ref.shape, generator=gen)
+        (ref * up).sum().backward()
+        m = make_model(kb, model, ent, rel, ln)
+        sc, pc, oc = s.cuda(), p.cuda(), o.cuda()
+        got = m.score_spo(sc, pc, oc) if form == "spo" else (m.score_sp(sc, pc) if form == "sp" else m.score_po(pc, oc))
+        (got * up.cuda()).sum().backward()
+        ge, gr = prm.grads()
+        close(m.get_s_embedder().weight.grad, ge, rtol=2e-5, what=f"{tag} {form} d entity")
+        close(m.get_p_embedder().weight.grad, gr, rtol=2e-5, what=f"{tag} {form} d relation")
+
+
+def test_error_behaviour(kb):
+    with pytest.raises(ValueError):
+        kb.KgeModel("complex", 10, 3, 7)          # odd dim (complex.py / cp.py:45-49 style)
+    m = kb.KgeModel("distmult", 10, 3, 8).cuda()
+    x = torch.zeros(2, 8, device="cuda")
+    with pytest.raises(ValueError):
+        m.get_scorer().score_emb(x, x, x, "xyz")   # kge_model.py:180
+    with pytest.raises(ValueError):
+        kb.ops.score_all(kb.lib.DOT, torch.zeros(2, 8), x)  # CPU tensor: no CPU path
+    with pytest.raises(NotImplementedError):
+        kb.KgeModel("transe", 10, 3, 8, l_norm=3.0)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(300, 1000, 128), (128, 128, 32), (77, 333, 64), (513, 2049, 100)])
+def test_tf32_tensor_tiles_scores(kb, shape):
+    b, e, d = shape
+    gen = torch.Generator().manual_seed(b + e)
+    q = torch.randn(b, d, generator=gen).cuda() * 0.3
+    w = torch.randn(e, d, generator=gen).cuda() * 0.3
+    ref = (q.double() @ w.double().t()).float()
+    fp32 = kb.ops.score_all(kb.lib.DOT, q, w, kb.lib.MATH_FP32)
+    close(fp32, ref, rtol=1e-5, what="fp32 tiles")
+    tf32 = kb.ops.score_all(kb.lib.DOT, q, w, kb.lib.MATH_TF32)
+    close(tf32, ref, rtol=2e-3, what="tf32 tcgen05 tiles")
+    # dyadic inputs are exact in TF32: the tensor path must then be bit-identical to exact arithmetic
+    qd = torch.round(q * 16) / 16
+    wd = torch.round(w * 16) / 16
+    exact = (qd.double() @ wd.double().t()).float()
+    assert torch.equal(kb.ops.score_all(kb.lib.DOT, qd, wd, kb.lib.MATH_TF32), exact)
+
+
+# ---------------------------------------------------------------------------------------------
+def _run_case(kb, golden, tag, fused_path, math_mode=None):
+    g = golden("train")
+    _, ttype, model, loss = tag.split(".")
+    opts = dict(ast.literal_eval(str(g[tag + ".options"]))) if tag + ".options" in g else {}
+    ln = float(opts.get(model + ".l_norm", 1.0))
+    off = float(opts.get("train.loss_arg", 0.0))
+    ls = float(opts.get("KvsAll.label_smoothing", 0.0))
+    math_mode = kb.lib.MATH_FP32 if math_mode is None else math_mode
+    m = make_model(kb, model, g[tag + ".ent0"], g[tag + ".rel0"], ln)
+    opt = kb.optim.create("Adagrad", m.parameters(), lr=0.2)
+    lossf = kb.KgeLoss.create(loss, off)
+    kw = dict(fused_path=fused_path, math_mode=math_mode)
+    if ttype == "1vsAll":
+        job = kb.TrainingJob1vsAll(m, opt, lossf, **kw)
+    elif ttype == "KvsAll":
+        job = kb.TrainingJobKvsAll(m, opt, lossf, E, R, label_smoothing=ls, **kw)
+    else:
+        job = kb.TrainingJobNegativeSampling(m, opt, lossf, **kw)
+    rtol = 1e-5 if math_mode == kb.lib.MATH_FP32 else 2e-3
+    for step in range(2):
+        pre = f"{tag}.b{step}"
+        if ttype == "KvsAll":
+            batch = {"queries": T(g[pre + ".queries"]), "label_coords": T(g[pre + ".label_coords"]),
+                     "query_type_indexes": T(g[pre + ".query_type"])}
+        else:
+            batch = {"triples": T(g[pre + ".triples"])}
+            if ttype == "negative_sampling":
+                batch["negative_samples"] = [T(g[f"{pre}.neg{slot}"]) for slot in range(3)]
+        res = job.step(step, batch)
+        assert res.avg_loss == pytest.approx(float(g[pre + ".loss"]), rel=max(rtol, 2e-5)), f"{tag} loss step {step}"
+        close(m.get_s_embedder().weight.grad, g[pre + ".grad_ent"], rtol=2 * rtol, what=f"{tag} grad entity {step}")
+        close(m.get_p_embedder().weight.grad, g[pre + ".grad_rel"], rtol=2 * rtol, what=f"{tag} grad relation {step}")
+        # Adagrad divides by sqrt(sum g^2): where g ~ 0 the update direction is ill-conditioned, so the
+        # post-step parameters are compared with an absolute bound in units of the learning rate
+        for got, ref in ((m.get_s_embedder().weight, g[pre + ".ent"]), (m.get_p_embedder().weight, g[pre + ".rel"])):
+            err = (got.detach().cpu() - T(ref)).abs().max().item()
+            assert err <= 0.2 * (2e-3 if math_mode == kb.lib.MATH_FP32 else 5e-2), f"{tag} params step {step}: {err}"
+
+
+def _cases(golden):
+    return [str(x) for x in golden("train")["train.cases"]]
+
+
+def test_training_steps_reference_flow(kb, golden):
+    """The reference's own batch bodies (score_* -> loss -> backward -> Adagrad) on the CUDA path."""
+    for tag in _cases(golden):
+        _run_case(kb, golden, tag, fused_path=False)
+
+
+def test_training_steps_fused_flow(kb, golden):
+    """Fused score+loss kernels (scores never materialised), fp32 CUDA-core tiles."""
+    for tag in _cases(golden):
+        _run_case(kb, golden, tag, fused_path=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_fused_forward_stats_tf32_vs_fp32(kb):
+    gen = torch.Generator().manual_seed(5)
+    b, e, d = 200, 1500, 128
+    q = (torch.randn(b, d, generator=gen) * 0.2).cuda()
+    w = (torch.randn(e, d, generator=gen) * 0.2).cuda()
+    cols = torch.randint(0, e, (b, 3), generator=gen).sort(dim=1).values.cuda()
+    lab_off = torch.arange(0, 3 * b + 1, 3, dtype=torch.int64).cuda()
+    lab_col = cols.reshape(-1).contiguous()
+    x = (q.double() @ w.double().t())
+    for loss, name in ((kb.lib.LOSS_KL, "kl"), (kb.lib.LOSS_BCE, "bce")):
+        shard = kb.fused.Shard.full(e)
+        ref_rows = None
+        for math_mode, rtol in ((kb.lib.MATH_FP32, 2e-5), (kb.lib.MATH_TF32, 2e-3)):
+            st = kb.fused.fused_rowstats(q, w, lab_off, lab_col, loss, 0.0, 0.25 if loss else 0.0, math_mode, shard)
+            rows, lse = kb.fused.rows_loss(st, lab_off, loss, 0.0, e)
+            if loss == kb.lib.LOSS_KL:
+                want = torch.logsumexp(x, 1) - x.gather(1, cols).sum(1) / 3 - np.log(3.0)
+            else:
+                xo = x + 0.25
+                want = torch.nn.functional.softplus(xo).sum(1) - xo.gather(1, cols).sum(1)
+            close(rows, want.float(), rtol=rtol, what=f"{name} rows math={math_mode}")
+
+
+def test_entity_ranking_matches_reference_golden(kb, golden):
+    g = golden("eval")
+    graph = {k: g[f"eval.graph.{k}"] for k in ("train", "valid", "test")}
+    for tag in [str(x) for x in g["eval.cases"]]:
+        _, model, chunk, ties = tag.split(".")
+        for math_mode in (kb.lib.MATH_FP32, kb.lib.MATH_TF32):
+            m = make_model(kb, model, g[tag + ".ent"], g[tag + ".rel"], 1.0, math_mode=math_mode)
+            job = kb.EntityRankingJob(m, E, [graph["train"], graph["valid"]], graph["test"], batch_size=16,
+                                      tie_handling=ties, hits_at_k_s=(1, 3, 10, 50), math_mode=math_mode)
+            res = job.run(graph["valid"])
+            exact = model != "rotate"   # dyadic weights: every sum is exact, so ties must match bit-for-bit
+            for nm in ("raw", "filt", "filt_test"):
+                for d in "so":
+                    got = res["ranks"][f"{d}_{nm}"].cpu().numpy()
+                    want = g[f"{tag}.{d}_ranks_{nm}"]
+                    if exact:
+                        np.testing.assert_array_equal(got, want, err_msg=f"{tag} {d}_{nm} math={math_mode}")
+                    else:
+                        assert np.mean(got != want) < 0.1
+            mm = res["metrics"]
+            for key in ("mean_reciprocal_rank", "mean_reciprocal_rank_filtered",
+                        "mean_reciprocal_rank_filtered_with_test", "hits_at_10_filtered", "hits_at_1_filtered"):
+                assert mm[key] == pytest.approx(float(g[f"{tag}.metric.{key}"]), abs=1e-6 if exact else 1e-3), (tag, key)
+
+
+def test_scatter_and_segment_reduce_are_deterministic(kb):
+    gen = torch.Generator().manual_seed(0)
+    n, d, v = 5000, 48, 97
+    idx = torch.randint(0, v, (n,), generator=gen).cuda()
+    rows = torch.randn(n, d, generator=gen).cuda()
+    a = torch.zeros(v, d, device="cuda")
+    b = torch.zeros(v, d, device="cuda")
+    kb.ops.scatter_add_rows_(a, idx, rows)
+    kb.ops.scatter_add_rows_(b, idx.int(), rows)
+    assert torch.equal(a, b)
+    ref = torch.zeros(v, d, dtype=torch.float64).index_add_(0, idx.cpu(), rows.cpu().double())
+    close(a, ref.float(), rtol=1e-6, what="scatter")
+    ids, red, cnt = kb.ops.segment_reduce_rows(idx, rows)
+    k = int(cnt.item())
+    assert torch.equal(ids[:k].cpu(), torch.unique(idx.cpu()))
+    assert torch.equal(red[:k], a[ids[:k]])
+
+
+def test_kvsall_index_device_lookup_bit_exact(kb, golden):
+    g = golden("index")
+    tr = g["index.train.triples"]
+    for key in ("sp", "po"):
+        ix = kb.index.KvsAllIndex(tr, key)
+        np.testing.assert_array_equal(ix._keys.numpy(), g[f"index.train.{key}.keys"])
+        np.testing.assert_array_equal(ix._values_offset.numpy(), g[f"index.train.{key}.offsets"])
+        np.testing.assert_array_equal(ix._values.numpy(), g[f"index.train.{key}.values"])
+    # device-side filter coordinates == get_sp_po_coords_from_spo_batch (as a set per row)
+    batch = T(g["index.coords_batch"]).long().cuda()
+    sp, po = kb.index.KvsAllIndex(tr, "sp"), kb.index.KvsAllIndex(tr, "po")
+    _, off, val = sp.device_arrays("cuda")
+    o_off, o_col = kb.index.gather_csr_rows(off, val, sp.lookup(batch[:, [0, 1]].contiguous()))
+    _, off, val = po.device_arrays("cuda")
+    s_off, s_col = kb.index.gather_csr_rows(off, val, po.lookup(batch[:, [1, 2]].contiguous()), add=E)
+    got = set()
+    for r in range(len(batch)):
+        got |= {(r, int(c)) for c in o_col[o_off[r]:o_off[r + 1]].tolist()}
+        got |= {(r, int(c)) for c in s_col[s_off[r]:s_off[r + 1]].tolist()}
+    assert got == {(int(a), int(b)) for a, b in g["index.coords"]}
