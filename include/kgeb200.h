@@ -115,10 +115,10 @@ int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const f
                    int64_t workspace_bytes, void* stream);
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
-                   float label_smoothing, float offset, const float* lse /*[B] (KL)*/, float inv_batch,
+                   int64_t nnz /* = lab_off[B], known to the caller */, float label_smoothing, float offset, const float* lse /*[B] (KL)*/, float inv_batch,
                    const float* row_scale /*[B] per-row factor multiplied into G (upstream gradient), or NULL*/, float* dQ, float* dTable,
                    void* workspace, int64_t workspace_bytes, void* stream);
-int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities);
+int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities, int64_t nnz);
 
 /* ---- a23-a26/K10: fused score-and-count for filtered entity ranking (entity_ranking.py:153-217,
  * 469-529).  Q is [nq,d] (callers stack the B sp_ queries and the B _po queries).  For query i the

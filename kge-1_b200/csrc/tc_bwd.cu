@@ -1,0 +1,439 @@
+// tcgen05 backward of the fused all-entity loss for the KGEB_DOT scorers (TF32 operands, fp32 accumulate).
+//
+//   G = dL/dS (dense part) is recomputed tile by tile and never leaves the SM:
+//     MMA1  S[128 x 64]   = RES[128 x d] * STR[64 x d]^T          (both K-major, TMA 128B-swizzled slabs)
+//     epi   G = rs_q * (sigmoid(S+off) - ls_add | exp(S - lse_q))  TMEM -> registers -> swizzled smem
+//     MMA2  OUT[128 x d] += G[128 x 64] * STR[64 x d]              (A = G K-major, B = the same STR tile MN-major)
+//   with OUT accumulating in tensor memory across the streamed tiles of a job.
+//   RES_IS_Q = true : RES = one block of 128 query rows (resident), STR = 64-entity tiles of a chunk of the
+//                     table -> OUT = dQ block (partial per chunk, reduced in fixed order afterwards)
+//   RES_IS_Q = false: RES = one tile of 128 entities (resident), STR = 64-row tiles of Q (all of them)
+//                     -> OUT = G^T Q = dense gradient of those 128 table rows, added to dTable in place.
+//   The sparse label part of the target (t_ij at known answers) is linear in G and is applied exactly in
+//   fp32 by two small kernels (label_dq_kernel, label rows + sorted scatter), so these kernels carry no
+//   CSR logic.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue (one thread per TMEM lane).
+#include "tc_common.cuh"
+
+namespace kgeb {
+namespace tcb {
+
+using namespace kgeb::tc;
+
+constexpr int RES_ROWS = 128;                    // UMMA M
+constexpr int STR_ROWS = 64;                     // UMMA N of MMA1, K of MMA2
+constexpr int SLAB_K = 32;                       // fp32 per 128-byte swizzle row
+constexpr int RES_SLAB = RES_ROWS * 128;         // 16 KiB
+constexpr int STR_SLAB = STR_ROWS * 128;         // 8 KiB
+constexpr int G_BYTES = RES_ROWS * STR_ROWS * 4; // 32 KiB = two K-slabs of [128 rows x 128 B]
+constexpr int UMMA_K = 8;
+constexpr int MAX_STR = 8;                       // streamed-tile ring depth
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BUDGET = 227 * 1024;
+
+struct Params {
+  int64_t n_res;      // rows of the resident operand (B or shard entities)
+  int64_t n_str;      // rows of the streamed operand
+  int64_t B;
+  int d, ks, nstr;    // ks = ceil(d/32); nstr = ring depth
+  int64_t n_res_blocks, n_str_tiles, chunks, tiles_per_chunk;
+  int loss;
+  float offset, ls_add, inv_batch;
+  const float* lse;        // [B] (KL)
+  const float* row_scale;  // [B] or NULL
+  float* out;              // RES_IS_Q: partial [chunks][B][d] ; else dTable [n_res][d] (+=)
+};
+
+template <bool RES_IS_Q>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_str, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KS = p.ks, NSTR = p.nstr;
+  uint8_t* res_smem = smem;                                         // [KS] slabs of 16 KiB
+  uint8_t* g_smem = res_smem + (size_t)KS * RES_SLAB;               // [2] G buffers of 32 KiB
+  uint8_t* str_smem = g_smem + 2 * G_BYTES;                         // [NSTR][KS] slabs of 8 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(str_smem + (size_t)NSTR * KS * STR_SLAB);
+  uint64_t* str_full = bars;                    // [MAX_STR]  TMA -> MMA
+  uint64_t* str_empty = bars + MAX_STR;         // [MAX_STR]  MMA2 done -> TMA
+  uint64_t* res_full = bars + 2 * MAX_STR;      // TMA -> MMA
+  uint64_t* res_empty = res_full + 1;           // job's MMAs done -> TMA
+  uint64_t* s_full = res_full + 2;              // [2] MMA1 done -> epilogue
+  uint64_t* s_empty = res_full + 4;             // [2] epilogue read S -> MMA
+  uint64_t* g_full = res_full + 6;              // [2] epilogue wrote G -> MMA
+  uint64_t* g_empty = res_full + 8;             // [2] MMA2 read G -> epilogue
+  uint64_t* o_full = res_full + 10;             // job accumulator complete -> epilogue
+  uint64_t* o_empty = res_full + 11;            // epilogue flushed -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 12);
+  constexpr int TMEM_COLS = 512;
+  constexpr uint32_t S_COL = 0;                 // two S buffers of 64 columns: [0,64), [64,128)
+  constexpr uint32_t O_COL = 128;               // OUT accumulator: d <= 128 columns at [128, 256)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_res);
+    tma_prefetch_desc(&tm_str);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAX_STR; ++s) {
+      mbar_init(&str_full[s], 1);
+      mbar_init(&str_empty[s], 1);
+    }
+    mbar_init(res_full, 1);
+    mbar_init(res_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], 128);
+      mbar_init(&g_full[b], 128);
+      mbar_init(&g_empty[b], 1);
+    }
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t n_jobs = p.n_res_blocks * p.chunks;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0, rphase = 0;
+      for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int64_t rb = job % p.n_res_blocks, ch = job / p.n_res_blocks;
+        mbar_wait(res_empty, rphase ^ 1);
+        mbar_expect_tx(res_full, (uint32_t)(KS * RES_SLAB));
+        for (int k = 0; k < KS; ++k)
+          tma_load_2d(res_smem + (size_t)k * RES_SLAB, &tm_res, k * SLAB_K, (int32_t)(rb * RES_ROWS), res_full);
+        rphase ^= 1;
+        const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
+        for (int64_t u = u0; u < u1; ++u) {
+          mbar_wait(&str_empty[slot], phase ^ 1);
+          mbar_expect_tx(&str_full[slot], (uint32_t)(KS * STR_SLAB));
+          for (int k = 0; k < KS; ++k)
+            tma_load_2d(str_smem + ((size_t)slot * KS + k) * STR_SLAB, &tm_str, k * SLAB_K, (int32_t)(u * STR_ROWS),
+                        &str_full[slot]);
+          if (++slot == NSTR) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc(RES_ROWS, STR_ROWS, 0, 0);  // S = RES * STR^T   (K-major, K-major)
+      const uint32_t idesc2 = make_idesc(RES_ROWS, p.d, 0, 1);       // OUT += G * STR     (K-major, MN-major)
+      int slot1 = 0, slot2 = 0;          // ring slot of the next MMA1 / MMA2
+      uint32_t ph1 = 0;                  // parity for str_full at slot1
+      uint32_t sph[2] = {0, 0}, gph[2] = {0, 0}, rphase = 0, ophase = 0;
+      int sbuf = 0, gbuf = 0;
+
+      auto issue_mma1 = [&](int slot, int buf) {
+        const uint32_t acc = tmem_base + S_COL + (uint32_t)(buf * STR_ROWS);
+        for (int k = 0; k < KS; ++k) {
+          const uint32_t ra = smem_u32(res_smem + (size_t)k * RES_SLAB);
+          const uint32_t sa = smem_u32(str_smem + ((size_t)slot * KS + k) * STR_SLAB);
+#pragma unroll
+          for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk)
+            umma_tf32(acc, make_desc(ra + kk * UMMA_K * 4, 16, 1024), make_desc(sa + kk * UMMA_K * 4, 16, 1024), idesc1,
+                      (k | kk) != 0);
+        }
+      };
+      auto issue_mma2 = [&](int slot, int buf, bool first) {
+        const uint32_t acc = tmem_base + O_COL;
+        const uint32_t ga = smem_u32(g_smem + (size_t)buf * G_BYTES);
+        const uint32_t sa = smem_u32(str_smem + (size_t)slot * KS * STR_SLAB);
+#pragma unroll
+        for (int k8 = 0; k8 < STR_ROWS / UMMA_K; ++k8) {
+          // A: G K-major, 8 K-columns = 32 B inside the 128 B row of K-slab (k8/4); B: STR tile MN-major, 8 K-rows
+          // = one 1024 B group; N chunks of 32 columns are STR_SLAB apart (LBO), 8-row groups 1024 B apart (SBO)
+          const uint64_t ad = make_desc(ga + (k8 >> 2) * RES_SLAB + (k8 & 3) * UMMA_K * 4, 16, 1024);
+          const uint64_t bd = make_desc(sa + k8 * 1024, STR_SLAB, 1024);
+          umma_tf32(acc, ad, bd, idesc2, !(first && k8 == 0));
+        }
+      };
+
+      for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int64_t ch = job / p.n_res_blocks;
+        const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
+        const int64_t nu = u1 - u0;
+        mbar_wait(res_full, rphase);
+        rphase ^= 1;
+        mbar_wait(o_empty, ophase ^ 1);  // previous job's accumulator has been flushed
+        tc_fence_after();
+        // software pipeline: MMA1(u+1) is issued before MMA2(u) so the tensor pipe works while the epilogue of u runs
+        for (int64_t i = 0; i <= nu; ++i) {
+          if (i < nu) {
+            mbar_wait(&str_full[slot1], ph1);
+            mbar_wait(&s_empty[sbuf], sph[sbuf] ^ 1);
+            tc_fence_after();
+            issue_mma1(slot1, sbuf);
+            umma_commit(&s_full[sbuf]);
+            sph[sbuf] ^= 1;
+            sbuf ^= 1;
+            if (++slot1 == NSTR) { slot1 = 0; ph1 ^= 1; }
+          }
+          if (i > 0) {
+            mbar_wait(&g_full[gbuf], gph[gbuf]);
+            tc_fence_after();
+            issue_mma2(slot2, gbuf, i == 1);
+            umma_commit(&str_empty[slot2]);  // streamed tile free once MMA2 has read it
+            umma_commit(&g_empty[gbuf]);
+            gph[gbuf] ^= 1;
+            gbuf ^= 1;
+            if (++slot2 == NSTR) slot2 = 0;
+          }
+        }
+        umma_commit(o_full);      // accumulator complete
+        umma_commit(res_empty);   // resident block may be replaced
+        ophase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int ew = warp - 4;
+    const int trow = ew * 32 + lane;                       // resident row (TMEM lane) of this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(ew * 32) << 16);
+    uint32_t sph[2] = {0, 0}, gph[2] = {0, 0}, ophase = 0;
+    int sbuf = 0, gbuf = 0;
+    for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+      const int64_t rb = job % p.n_res_blocks, ch = job / p.n_res_blocks;
+      const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
+      const int64_t res_row = rb * RES_ROWS + trow;
+      float my_lse = 0.f, my_rs = 0.f;
+      if (RES_IS_Q && res_row < p.B) {
+        my_rs = p.inv_batch * (p.row_scale ? p.row_scale[res_row] : 1.f);
+        if (p.loss == KGEB_LOSS_KL) my_lse = p.lse[res_row];
+      }
+      for (int64_t u = u0; u < u1; ++u) {
+        mbar_wait(&s_full[sbuf], sph[sbuf]);
+        sph[sbuf] ^= 1;
+        tc_fence_after();
+        float v[2][32];
+        tmem_ld32(lane_addr + S_COL + (uint32_t)(sbuf * STR_ROWS), v[0]);
+        tmem_ld32(lane_addr + S_COL + (uint32_t)(sbuf * STR_ROWS + 32), v[1]);
+        tc_fence_before();
+        mbar_arrive(&s_empty[sbuf]);  // S buffer is in registers: MMA1 of the tile after next may overwrite it
+        sbuf ^= 1;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float lse = my_lse, rs = my_rs;
+            if (!RES_IS_Q) {  // columns are query rows: per-column parameters (warp-uniform loads)
+              const int64_t q = u * STR_ROWS + hlf * 32 + c;
+              rs = 0.f; lse = 0.f;
+              if (q < p.B) {
+                rs = p.inv_batch * (p.row_scale ? __ldg(p.row_scale + q) : 1.f);
+                if (p.loss == KGEB_LOSS_KL) lse = __ldg(p.lse + q);
+              }
+            }
+            const float x = v[hlf][c];
+            float gval;
+            if (p.loss == KGEB_LOSS_KL) gval = __expf(x - lse);
+            else gval = sigmoidf(x + p.offset) - p.ls_add;
+            v[hlf][c] = rs * gval;
+          }
+        mbar_wait(&g_empty[gbuf], gph[gbuf] ^ 1);  // MMA2 of two tiles ago has finished reading this buffer
+        uint8_t* gb = g_smem + (size_t)gbuf * G_BYTES;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint8_t* rowp = gb + (size_t)hlf * RES_SLAB + (size_t)trow * 128;
+#pragma unroll
+          for (int ck = 0; ck < 8; ++ck) {
+            float4 val = make_float4(v[hlf][ck * 4], v[hlf][ck * 4 + 1], v[hlf][ck * 4 + 2], v[hlf][ck * 4 + 3]);
+            *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) = val;  // 128-byte swizzle
+          }
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&g_full[gbuf]);
+        gph[gbuf] ^= 1;
+        gbuf ^= 1;
+      }
+      // flush the job's accumulator
+      mbar_wait(o_full, ophase);
+      ophase ^= 1;
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.d; c0 += 32) {
+        float o[32];
+        tmem_ld32(lane_addr + O_COL + (uint32_t)c0, o);
+        if (res_row < p.n_res) {
+          float* dst = RES_IS_Q ? p.out + ((size_t)ch * p.B + res_row) * p.d + c0 : p.out + (size_t)res_row * p.d + c0;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            if (c0 + c < p.d) {
+              float4* d4 = reinterpret_cast<float4*>(dst + c);
+              if (RES_IS_Q) {
+                *d4 = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+              } else {
+                float4 old = *d4;
+                *d4 = make_float4(old.x + o[c], old.y + o[c + 1], old.z + o[c + 2], old.w + o[c + 3]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(o_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact fp32 sparse label part and partial reduction
+// ---------------------------------------------------------------------------------------------
+// dQ[q,:] = sum_chunks partial[c][q,:] - w_q * sum_{e in labels(q) of this shard} table[e - e_lo,:]
+__global__ void reduce_dq_labels_kernel(const float* __restrict__ partial, int64_t chunks, int64_t B, int d,
+                                        const float* __restrict__ table, int64_t e_lo, int64_t n_ent,
+                                        const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
+                                        const float* __restrict__ tscale, const float* __restrict__ row_scale,
+                                        float inv_batch, float* __restrict__ dQ) {
+  const int64_t q = blockIdx.x;
+  const float w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float s = 0.f;
+    for (int64_t k = 0; k < chunks; ++k) s += partial[(k * B + q) * d + c];
+    float l = 0.f;
+    for (int64_t i = lab_off[q]; i < lab_off[q + 1]; ++i) {
+      const int64_t e = lab_col[i] - e_lo;
+      if (e >= 0 && e < n_ent) l += __ldg(table + e * d + c);
+    }
+    dQ[q * d + c] = s - w * l;
+  }
+}
+
+// rows[i,:] = -w_q * Q[q,:] and ent[i] = local entity id for label entry i (entries outside the shard get weight 0
+// and entity 0 so that the scatter stays in range)
+__global__ void label_rows_kernel(const float* __restrict__ Q, int64_t B, int d, int64_t e_lo, int64_t n_ent,
+                                  const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
+                                  const float* __restrict__ tscale, const float* __restrict__ row_scale, float inv_batch,
+                                  float* __restrict__ rows, int64_t* __restrict__ ent) {
+  const int64_t q = blockIdx.x;
+  const float w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
+  for (int64_t i = lab_off[q]; i < lab_off[q + 1]; ++i) {
+    const int64_t e = lab_col[i] - e_lo;
+    const bool in = (e >= 0 && e < n_ent);
+    for (int c = threadIdx.x; c < d; c += blockDim.x) rows[i * d + c] = in ? -w * Q[q * d + c] : 0.f;
+    if (threadIdx.x == 0) ent[i] = in ? e : 0;
+  }
+}
+
+struct Plan {
+  Params p;
+  size_t smem;
+};
+
+static Plan make_plan(bool res_is_q, int64_t B, int d, int64_t n_ent) {
+  Plan pl;
+  Params& p = pl.p;
+  memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.d = d;
+  p.ks = (d + SLAB_K - 1) / SLAB_K;
+  p.n_res = res_is_q ? B : n_ent;
+  p.n_str = res_is_q ? n_ent : B;
+  p.n_res_blocks = (p.n_res + RES_ROWS - 1) / RES_ROWS;
+  p.n_str_tiles = (p.n_str + STR_ROWS - 1) / STR_ROWS;
+  if (res_is_q) {
+    int64_t chunks = kNumSMs / (p.n_res_blocks > 0 ? p.n_res_blocks : 1);
+    if (chunks < 1) chunks = 1;
+    if (chunks > p.n_str_tiles) chunks = p.n_str_tiles > 0 ? p.n_str_tiles : 1;
+    p.tiles_per_chunk = (p.n_str_tiles + chunks - 1) / chunks;
+    if (p.tiles_per_chunk < 1) p.tiles_per_chunk = 1;
+    p.chunks = (p.n_str_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    if (p.chunks < 1) p.chunks = 1;
+  } else {
+    p.chunks = 1;
+    p.tiles_per_chunk = p.n_str_tiles > 0 ? p.n_str_tiles : 1;
+  }
+  const size_t fixed = 1024 + 512;
+  const size_t base = (size_t)p.ks * RES_SLAB + 2 * G_BYTES;
+  int nstr = (int)((SMEM_BUDGET - fixed - base) / ((size_t)p.ks * STR_SLAB));
+  if (nstr > MAX_STR) nstr = MAX_STR;
+  p.nstr = nstr;
+  pl.smem = base + (size_t)nstr * p.ks * STR_SLAB + fixed;
+  return pl;
+}
+
+}  // namespace tcb
+
+bool tc_bwd_supported(int d) { return d % 16 == 0 && d <= 128; }
+
+int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz) {
+  int64_t partial = (int64_t)kNumSMs * B * d * 4;
+  int64_t rows = nnz * (int64_t)d * 4 + nnz * 8 + 512;
+  return partial + rows + kgeb_scatter_workspace_bytes(nnz) + B * 4 + 2048;
+}
+
+int tc_fused_bwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
+                 const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const float* tscale, float ls_add,
+                 float offset, const float* lse, float inv_batch, const float* row_scale, float* dQ, float* dTable,
+                 void* ws, int64_t ws_bytes, cudaStream_t st) {
+  using namespace tcb;
+  KGEB_REQUIRE(tc_bwd_supported(d), "fused_bwd(tf32): entity dim must be a multiple of 16 and <= 128 (got %d)", d);
+  KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(table)) & 15) == 0,
+               "TF32 tiles need 16-byte aligned operands");
+  KGEB_REQUIRE(ws_bytes >= tc_bwd_workspace_bytes(B, d, n_ent, nnz), "fused_bwd(tf32): workspace too small");
+  char* wp = reinterpret_cast<char*>(ws);
+  float* partial = reinterpret_cast<float*>(wp);
+  wp += (((int64_t)kNumSMs * B * d * 4 + 255) / 256) * 256;
+  float* lab_rows = reinterpret_cast<float*>(wp);
+  wp += ((nnz * (int64_t)d * 4 + 255) / 256) * 256;
+  int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);
+  wp += ((nnz * 8 + 255) / 256) * 256;
+  void* scatter_ws = wp;
+  const int64_t scatter_bytes = ws_bytes - (wp - reinterpret_cast<char*>(ws)) - B * 4 - 512;  // tail holds tscale
+  int rc;
+  CUtensorMap m_q128, m_q64, m_w128, m_w64;
+  if (n_ent > 0 && B > 0) {
+    if (dQ) {
+      Plan pl = make_plan(true, B, d, n_ent);
+      if (pl.p.nstr < 2) { set_error("fused_bwd(tf32): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
+      pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
+      pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = partial;
+      if ((rc = make_map(&m_q128, Q, B, d, RES_ROWS)) || (rc = make_map(&m_w64, table, n_ent, d, STR_ROWS))) return rc;
+      const int64_t jobs = pl.p.n_res_blocks * pl.p.chunks;
+      cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
+      tc_bwd_kernel<true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_q128, m_w64, pl.p);
+      KGEB_LAUNCH_CHECK("tc_bwd_kernel<dQ>");
+      reduce_dq_labels_kernel<<<(unsigned)B, 128, 0, st>>>(partial, pl.p.chunks, B, d, table, e_lo, n_ent, lab_off,
+                                                          lab_col, tscale, row_scale, inv_batch, dQ);
+      KGEB_LAUNCH_CHECK("reduce_dq_labels");
+    }
+    if (dTable) {
+      Plan pl = make_plan(false, B, d, n_ent);
+      pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
+      pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = dTable;
+      if ((rc = make_map(&m_w128, table, n_ent, d, RES_ROWS)) || (rc = make_map(&m_q64, Q, B, d, STR_ROWS))) return rc;
+      const int64_t jobs = pl.p.n_res_blocks;
+      cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
+      tc_bwd_kernel<false><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_w128, m_q64, pl.p);
+      KGEB_LAUNCH_CHECK("tc_bwd_kernel<dTable>");
+      if (nnz > 0) {
+        label_rows_kernel<<<(unsigned)B, 128, 0, st>>>(Q, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale,
+                                                       inv_batch, lab_rows, lab_ent);
+        KGEB_LAUNCH_CHECK("label_rows");
+        if ((rc = kgeb_scatter_add_rows(lab_ent, 1, lab_rows, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st)))
+          return rc;
+      }
+    }
+  } else if (dQ && B > 0) {
+    cudaMemsetAsync(dQ, 0, (size_t)B * d * 4, st);
+  }
+  return KGEB_OK;
+}
+
+}  // namespace kgeb

@@ -14,14 +14,15 @@ constexpr int BM = 64, BN = 64, BK = 16, TT = 256;
 int tc_score_all(const float* Q, int64_t B, int d, const float* table, int64_t m, float* out, int64_t ld,
                  int64_t col_off, cudaStream_t st);  // tc_dot.cu
 int64_t tc_stats_partial_bytes(int64_t B);                       // tc_dot.cu
-int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent);  // tc_dot.cu
+int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz);  // tc_bwd.cu
+bool tc_bwd_supported(int d);                                                    // tc_bwd.cu
 int tc_fused_fwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
                  const int64_t* lab_off, const int64_t* lab_col, float ls_keep, float ls_add, float offset,
                  float* rowstat, void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_dot.cu
 int tc_fused_bwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
-                 const int64_t* lab_off, const int64_t* lab_col, const float* tscale, float ls_add, float offset,
-                 const float* lse, float inv_batch, const float* grad_scale, float* dQ, float* dTable, void* ws,
-                 int64_t ws_bytes, cudaStream_t st);  // tc_dot.cu
+                 const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const float* tscale, float ls_add,
+                 float offset, const float* lse, float inv_batch, const float* row_scale, float* dQ, float* dTable,
+                 void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
 int tc_rank_count(const float* Q, int64_t nq, int d, const float* table, int64_t e_lo, int64_t n_ent,
                   const float* true_score, const void* true_ent, int idx64, const int64_t* f_off,
                   const int64_t* f_col, const int64_t* t_off, const int64_t* t_col, int64_t* counts,
@@ -750,10 +751,10 @@ static int64_t fused_ws_cuda_core(int64_t B, int d, int64_t num_shard_entities) 
   return (a > b ? a : b) + c + 512;
 }
 
-int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities) {
+int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities, int64_t nnz) {
   int64_t a = fused_ws_cuda_core(B, d, num_shard_entities);
   int64_t b = tc_stats_partial_bytes(B);
-  int64_t c = tc_bwd_workspace_bytes(B, d, num_shard_entities);
+  int64_t c = tc_bwd_workspace_bytes(B, d, num_shard_entities, nnz);
   int64_t m = a > b ? a : b;
   return m > c ? m : c;
 }
@@ -807,7 +808,7 @@ __global__ void label_weight_kernel(int loss, const int64_t* __restrict__ lab_of
 }
 
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
-                   int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
+                   int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                    float label_smoothing, float offset, const float* lse, float inv_batch,
                    const float* grad_scale, float* dQ, float* dTable, void* workspace, int64_t workspace_bytes,
                    void* stream) {
@@ -828,11 +829,17 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
   int64_t part_bytes = chunks * B * (int64_t)d * 4, stat_bytes = chunks * B * 16;
   float* tscale = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
                                            (((part_bytes > stat_bytes ? part_bytes : stat_bytes) + 255) / 256) * 256);
+  if (math == KGEB_MATH_TF32 && tc_bwd_supported(d)) {
+    KGEB_REQUIRE(workspace_bytes >= tc_bwd_workspace_bytes(B, d, n_ent, nnz), "fused_bwd(tf32): workspace too small");
+    float* ts = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((workspace_bytes - B * 4) & ~(int64_t)255));
+    label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, ts);
+    KGEB_LAUNCH_CHECK("label_weight");
+    return tc_fused_bwd(loss, Q, B, d, table, e_lo, n_ent, lab_off, lab_col, nnz, ts, lp.ls_add, offset, lse, inv_batch,
+                        grad_scale, dQ, dTable, workspace, workspace_bytes, st);
+  }
+  // (TF32 requested but the dim is outside the tensor-tile build: the fp32 CUDA-core tiles below serve it)
   label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, tscale);
   KGEB_LAUNCH_CHECK("label_weight");
-  if (math == KGEB_MATH_TF32)
-    return tc_fused_bwd(loss, Q, B, d, table, e_lo, n_ent, lab_off, lab_col, tscale, lp.ls_add, offset, lse,
-                        inv_batch, grad_scale, dQ, dTable, workspace, workspace_bytes, st);
   const int nc = (d + 31) / 32;
 #define LAUNCH_BWD(NC)                                                                                              \
   {                                                                                                                 \

@@ -72,7 +72,7 @@ def fused_rowstats(q, table, lab_off, lab_col, loss, label_smoothing, offset, ma
     b, d = q.shape
     rowstat = torch.empty(b, 4, dtype=torch.float32, device=q.device)
     n_ent = shard.e_hi - shard.e_lo
-    ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent))
+    ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent, lab_col.numel()))
     lib.call("kgeb_fused_fwd", loss, math, lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo,
              shard.e_hi, shard.num_entities, lib.i64(lab_off, "label offsets"), lib.i64(lab_col, "label columns"),
              float(label_smoothing), float(offset), rowstat.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream_ptr(q))
@@ -102,10 +102,10 @@ def fused_backward(q, table, lab_off, lab_col, loss, label_smoothing, offset, ls
     b, d = q.shape
     n_ent = shard.e_hi - shard.e_lo
     dq = torch.empty(b, d, dtype=torch.float32, device=q.device) if want_dq else None
-    ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent))
+    ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent, lab_col.numel()))
     lib.call("kgeb_fused_bwd", loss, math, lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo,
-             shard.e_hi, shard.num_entities, lib.i64(lab_off), lib.i64(lab_col), float(label_smoothing), float(offset),
-             None if lse is None else lib.f32(lse, "lse"), float(inv_batch),
+             shard.e_hi, shard.num_entities, lib.i64(lab_off), lib.i64(lab_col), lab_col.numel(), float(label_smoothing),
+             float(offset), None if lse is None else lib.f32(lse, "lse"), float(inv_batch),
              None if grad_scale is None else lib.f32(grad_scale, "grad scale"),
              None if dq is None else dq.data_ptr(), None if d_table is None else lib.f32(d_table, "table gradient"),
              ws.data_ptr(), ws.numel(), lib.stream_ptr(q))

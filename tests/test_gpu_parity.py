@@ -269,3 +269,40 @@ def test_kvsall_index_device_lookup_bit_exact(kb, golden):
         got |= {(r, int(c)) for c in o_col[o_off[r]:o_off[r + 1]].tolist()}
         got |= {(r, int(c)) for c in s_col[s_off[r]:s_off[r + 1]].tolist()}
     assert got == {(int(a), int(b)) for a, b in g["index.coords"]}
+
+
+def test_training_steps_fused_tf32_tensor_tiles(kb, golden):
+    """Fused flow on the tcgen05 TF32 tiles (forward statistics and both backward GEMMs)."""
+    for tag in _cases(golden):
+        if tag.split(".")[2] in ("distmult", "complex", "cp", "simple", "rescal") and "negative_sampling" not in tag:
+            _run_case(kb, golden, tag, fused_path=True, math_mode=kb.lib.MATH_TF32)
+
+
+@pytest.mark.parametrize("shape", [(300, 1111, 128), (64, 4000, 64), (1000, 500, 32), (129, 257, 16)])
+def test_fused_backward_matches_float64(kb, shape):
+    b, e, d = shape
+    gen = torch.Generator().manual_seed(e)
+    q = (torch.randn(b, d, generator=gen) * 0.3).cuda()
+    w = (torch.randn(e, d, generator=gen) * 0.3).cuda()
+    nlab = 2
+    cols = torch.stack([torch.randperm(e, generator=gen)[:nlab].sort().values for _ in range(b)]).cuda()
+    lab_off = torch.arange(0, nlab * b + 1, nlab, dtype=torch.int64).cuda()
+    lab_col = cols.reshape(-1).contiguous()
+    rscale = (torch.rand(b, generator=gen) + 0.5).cuda()
+    shard = kb.fused.Shard.full(e)
+    for loss in (kb.lib.LOSS_KL, kb.lib.LOSS_BCE):
+        qd, wd = q.double().requires_grad_(True), w.double().requires_grad_(True)
+        x = qd @ wd.t()
+        if loss == kb.lib.LOSS_KL:
+            rows = torch.logsumexp(x, 1) - x.gather(1, cols).sum(1) / nlab
+        else:
+            rows = torch.nn.functional.softplus(x + 0.1).sum(1) - (x + 0.1).gather(1, cols).sum(1)
+        ((rows * rscale.double()).sum() / b).backward()
+        for math_mode, rtol in ((kb.lib.MATH_FP32, 2e-5), (kb.lib.MATH_TF32, 3e-3)):
+            st = kb.fused.fused_rowstats(q, w, lab_off, lab_col, loss, 0.0, 0.1 if loss else 0.0, math_mode, shard)
+            _, lse = kb.fused.rows_loss(st, lab_off, loss, 0.0, e)
+            dw = torch.zeros_like(w)
+            dq = kb.fused.fused_backward(q, w, lab_off, lab_col, loss, 0.0, 0.1 if loss else 0.0, lse, 1.0 / b, rscale,
+                                         math_mode, shard, dw)
+            close(dq, qd.grad.float(), rtol=rtol, what=f"dQ loss={loss} math={math_mode} {shape}")
+            close(dw, wd.grad.float(), rtol=rtol, what=f"dTable loss={loss} math={math_mode} {shape}")
