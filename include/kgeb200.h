@@ -39,8 +39,9 @@ enum { KGEB_DOT = 0, KGEB_NEG_L1 = 1, KGEB_NEG_L2 = 2, KGEB_ROT_L1 = 3, KGEB_ROT
 /* kge/util/loss.py: KLDivWithSoftmaxKgeLoss (192-213), BCEWithLogitsKgeLoss bce_type=None (137-159) */
 enum { KGEB_LOSS_KL = 0, KGEB_LOSS_BCE = 1 };
 /* arithmetic of the all-entity DOT tiles */
-enum { KGEB_MATH_FP32 = 0,   /* CUDA-core FFMA, fp32 exact-order-free (1e-5 bar)              */
-       KGEB_MATH_TF32 = 1 }; /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (looser bound) */
+enum { KGEB_MATH_FP32 = 0,   /* CUDA-core FFMA, fp32 (1e-5 bar)                                         */
+       KGEB_MATH_TF32 = 1,   /* tcgen05.mma kind::tf32 on the fp32 tables in place, fp32 accumulate in TMEM */
+       KGEB_MATH_BF16 = 2 }; /* tcgen05.mma kind::f16 on bf16 mirrors (kgeb_to_bf16), fp32 accumulate      */
 
 const char* kgeb_last_error(void);
 /* library build info: returns the compiled arch (100) and writes a version string */
@@ -111,13 +112,16 @@ int kgeb_score_all_bwd(int kind, const float* Q, int64_t B, int d, const float* 
  *   dQ[B,d] = G * table (overwritten with this shard's partial), dTable[e,:] += G^T Q.      */
 int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
-                   float label_smoothing, float offset, float* rowstat /*[B,4]*/, void* workspace,
-                   int64_t workspace_bytes, void* stream);
+                   float label_smoothing, float offset, const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */,
+                   float* rowstat /*[B,4]*/, void* workspace, int64_t workspace_bytes, void* stream);
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
                    int64_t nnz /* = lab_off[B], known to the caller */, float label_smoothing, float offset, const float* lse /*[B] (KL)*/, float inv_batch,
-                   const float* row_scale /*[B] per-row factor multiplied into G (upstream gradient), or NULL*/, float* dQ, float* dTable,
+                   const float* row_scale /*[B] per-row factor multiplied into G (upstream gradient), or NULL*/,
+                   const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */, float* dQ, float* dTable,
                    void* workspace, int64_t workspace_bytes, void* stream);
+/* fp32 -> bf16 (round to nearest even) mirror of a table / query matrix for KGEB_MATH_BF16 */
+int kgeb_to_bf16(const float* src, void* dst, int64_t numel, void* stream);
 int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities, int64_t nnz);
 
 /* ---- a23-a26/K10: fused score-and-count for filtered entity ranking (entity_ranking.py:153-217,

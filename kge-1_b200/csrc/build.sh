@@ -9,7 +9,7 @@ mkdir -p "$HERE/build"
 pids=()
 for f in rows tiles update tc_dot tc_bwd; do
   [ -f "$HERE/$f.cu" ] || continue
-  if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/../../include/kgeb200.h" -nt "$HERE/build/$f.o" ]; then
+  if [ ! -f "$HERE/build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/build/$f.o" ] || [ "$HERE/common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/tc_common.cuh" -nt "$HERE/build/$f.o" ] || [ "$HERE/../../include/kgeb200.h" -nt "$HERE/build/$f.o" ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
     pids+=($!)
   fi

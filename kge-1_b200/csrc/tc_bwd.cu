@@ -1,4 +1,7 @@
-// tcgen05 backward of the fused all-entity loss for the KGEB_DOT scorers (TF32 operands, fp32 accumulate).
+// tcgen05 backward of the fused all-entity loss for the KGEB_DOT scorers (BF16 operand mirrors, fp32 accumulate
+// in tensor memory).  The second GEMM consumes the streamed tile MN-major from the same shared-memory bytes the
+// first GEMM reads K-major; tcgen05 allows that for 16-bit operands with the plain 128-byte swizzle (for TF32 an
+// MN-major operand needs the SWIZZLE_128B_BASE32B layout, i.e. a second copy of the tile), hence BF16 here.
 //
 //   G = dL/dS (dense part) is recomputed tile by tile and never leaves the SM:
 //     MMA1  S[128 x 64]   = RES[128 x d] * STR[64 x d]^T          (both K-major, TMA 128B-swizzled slabs)
@@ -14,6 +17,7 @@
 //   CSR logic.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = epilogue (one thread per TMEM lane).
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 
 namespace kgeb {
 namespace tcb {
@@ -22,11 +26,8 @@ using namespace kgeb::tc;
 
 constexpr int RES_ROWS = 128;                    // UMMA M
 constexpr int STR_ROWS = 64;                     // UMMA N of MMA1, K of MMA2
-constexpr int SLAB_K = 32;                       // fp32 per 128-byte swizzle row
-constexpr int RES_SLAB = RES_ROWS * 128;         // 16 KiB
-constexpr int STR_SLAB = STR_ROWS * 128;         // 8 KiB
-constexpr int G_BYTES = RES_ROWS * STR_ROWS * 4; // 32 KiB = two K-slabs of [128 rows x 128 B]
-constexpr int UMMA_K = 8;
+constexpr int RES_SLAB = RES_ROWS * 128;         // 16 KiB: 128 rows x 128 B
+constexpr int STR_SLAB = STR_ROWS * 128;         // 8 KiB:  64 rows x 128 B
 constexpr int MAX_STR = 8;                       // streamed-tile ring depth
 constexpr int NUM_THREADS = 256;
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -44,15 +45,18 @@ struct Params {
   float* out;              // RES_IS_Q: partial [chunks][B][d] ; else dTable [n_res][d] (+=)
 };
 
-template <bool RES_IS_Q>
+template <bool RES_IS_Q, bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_str, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KS = p.ks, NSTR = p.nstr;
+  constexpr int SLAB_K = Elem<BF16>::kSlabK, UMMA_K = Elem<BF16>::kUmmaK;
+  constexpr int G_SLABS = STR_ROWS / SLAB_K;            // K-slabs of the G operand (2 for TF32, 1 for BF16)
+  constexpr int G_BYTES = G_SLABS * RES_SLAB;
   uint8_t* res_smem = smem;                                         // [KS] slabs of 16 KiB
-  uint8_t* g_smem = res_smem + (size_t)KS * RES_SLAB;               // [2] G buffers of 32 KiB
+  uint8_t* g_smem = res_smem + (size_t)KS * RES_SLAB;               // [2] G buffers
   uint8_t* str_smem = g_smem + 2 * G_BYTES;                         // [NSTR][KS] slabs of 8 KiB
   uint64_t* bars = reinterpret_cast<uint64_t*>(str_smem + (size_t)NSTR * KS * STR_SLAB);
   uint64_t* str_full = bars;                    // [MAX_STR]  TMA -> MMA
@@ -68,7 +72,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 12);
   constexpr int TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0;                 // two S buffers of 64 columns: [0,64), [64,128)
-  constexpr uint32_t O_COL = 128;               // OUT accumulator: d <= 128 columns at [128, 256)
+  constexpr uint32_t O_COL = 128;               // OUT accumulator: d <= 256 columns at [128, 384)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_res);
@@ -125,8 +129,8 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      const uint32_t idesc1 = make_idesc(RES_ROWS, STR_ROWS, 0, 0);  // S = RES * STR^T   (K-major, K-major)
-      const uint32_t idesc2 = make_idesc(RES_ROWS, p.d, 0, 1);       // OUT += G * STR     (K-major, MN-major)
+      const uint32_t idesc1 = make_idesc(RES_ROWS, STR_ROWS, 0, 0, Elem<BF16>::kFmt);  // S = RES * STR^T (K, K)
+      const uint32_t idesc2 = make_idesc(RES_ROWS, p.d, 0, 1, Elem<BF16>::kFmt);       // OUT += G * STR  (K, MN)
       int slot1 = 0, slot2 = 0;          // ring slot of the next MMA1 / MMA2
       uint32_t ph1 = 0;                  // parity for str_full at slot1
       uint32_t sph[2] = {0, 0}, gph[2] = {0, 0}, rphase = 0, ophase = 0;
@@ -139,8 +143,8 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           const uint32_t sa = smem_u32(str_smem + ((size_t)slot * KS + k) * STR_SLAB);
 #pragma unroll
           for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk)
-            umma_tf32(acc, make_desc(ra + kk * UMMA_K * 4, 16, 1024), make_desc(sa + kk * UMMA_K * 4, 16, 1024), idesc1,
-                      (k | kk) != 0);
+            umma<BF16>(acc, make_desc(ra + kk * 32, 16, 1024), make_desc(sa + kk * 32, 16, 1024), idesc1,
+                       (k | kk) != 0);
         }
       };
       auto issue_mma2 = [&](int slot, int buf, bool first) {
@@ -148,12 +152,14 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         const uint32_t ga = smem_u32(g_smem + (size_t)buf * G_BYTES);
         const uint32_t sa = smem_u32(str_smem + (size_t)slot * KS * STR_SLAB);
 #pragma unroll
-        for (int k8 = 0; k8 < STR_ROWS / UMMA_K; ++k8) {
-          // A: G K-major, 8 K-columns = 32 B inside the 128 B row of K-slab (k8/4); B: STR tile MN-major, 8 K-rows
-          // = one 1024 B group; N chunks of 32 columns are STR_SLAB apart (LBO), 8-row groups 1024 B apart (SBO)
-          const uint64_t ad = make_desc(ga + (k8 >> 2) * RES_SLAB + (k8 & 3) * UMMA_K * 4, 16, 1024);
-          const uint64_t bd = make_desc(sa + k8 * 1024, STR_SLAB, 1024);
-          umma_tf32(acc, ad, bd, idesc2, !(first && k8 == 0));
+        for (int km = 0; km < STR_ROWS / UMMA_K; ++km) {
+          // A: G K-major -- UMMA_K columns = 32 B inside the 128 B row of K-slab (km*UMMA_K / SLAB_K).
+          // B: the STR tile MN-major -- UMMA_K K-rows of 128 B (8-row groups 1024 B apart = SBO); N chunks of one
+          //    128 B row (SLAB_K columns) are one slab apart (LBO = STR_SLAB).
+          const int kcol = km * UMMA_K;
+          const uint64_t ad = make_desc(ga + (kcol / SLAB_K) * RES_SLAB + (kcol % SLAB_K) * Elem<BF16>::kBytes, 16, 1024);
+          const uint64_t bd = make_desc(sa + kcol * 128, STR_SLAB, 1024);
+          umma<BF16>(acc, ad, bd, idesc2, !(first && km == 0));
         }
       };
 
@@ -240,13 +246,29 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           }
         mbar_wait(&g_empty[gbuf], gph[gbuf] ^ 1);  // MMA2 of two tiles ago has finished reading this buffer
         uint8_t* gb = g_smem + (size_t)gbuf * G_BYTES;
-#pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint8_t* rowp = gb + (size_t)hlf * RES_SLAB + (size_t)trow * 128;
+        if (BF16) {
+          // row trow of the single K-slab: 64 bf16 = 8 chunks of 16 B, 128-byte swizzle
+          uint8_t* rowp = gb + (size_t)trow * 128;
 #pragma unroll
           for (int ck = 0; ck < 8; ++ck) {
-            float4 val = make_float4(v[hlf][ck * 4], v[hlf][ck * 4 + 1], v[hlf][ck * 4 + 2], v[hlf][ck * 4 + 3]);
-            *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) = val;  // 128-byte swizzle
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = ck * 8 + j * 2;
+              const float lo = v[c >> 5][c & 31], hi = v[(c + 1) >> 5][(c + 1) & 31];
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(hi), "f"(lo));
+            }
+            *reinterpret_cast<uint4*>(rowp + ((ck ^ (trow & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint8_t* rowp = gb + (size_t)hlf * RES_SLAB + (size_t)trow * 128;
+#pragma unroll
+            for (int ck = 0; ck < 8; ++ck) {
+              float4 val = make_float4(v[hlf][ck * 4], v[hlf][ck * 4 + 1], v[hlf][ck * 4 + 2], v[hlf][ck * 4 + 3]);
+              *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) = val;  // 128-byte swizzle
+            }
           }
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -334,13 +356,14 @@ struct Plan {
   size_t smem;
 };
 
-static Plan make_plan(bool res_is_q, int64_t B, int d, int64_t n_ent) {
+static Plan make_plan(bool res_is_q, bool bf16, int64_t B, int d, int64_t n_ent) {
   Plan pl;
   Params& p = pl.p;
   memset(&p, 0, sizeof(p));
+  const int slab_k = bf16 ? 64 : 32;
   p.B = B;
   p.d = d;
-  p.ks = (d + SLAB_K - 1) / SLAB_K;
+  p.ks = (d + slab_k - 1) / slab_k;
   p.n_res = res_is_q ? B : n_ent;
   p.n_str = res_is_q ? n_ent : B;
   p.n_res_blocks = (p.n_res + RES_ROWS - 1) / RES_ROWS;
@@ -358,7 +381,8 @@ static Plan make_plan(bool res_is_q, int64_t B, int d, int64_t n_ent) {
     p.tiles_per_chunk = p.n_str_tiles > 0 ? p.n_str_tiles : 1;
   }
   const size_t fixed = 1024 + 512;
-  const size_t base = (size_t)p.ks * RES_SLAB + 2 * G_BYTES;
+  const size_t g_bytes = (size_t)(STR_ROWS / slab_k) * RES_SLAB;
+  const size_t base = (size_t)p.ks * RES_SLAB + 2 * g_bytes;
   int nstr = (int)((SMEM_BUDGET - fixed - base) / ((size_t)p.ks * STR_SLAB));
   if (nstr > MAX_STR) nstr = MAX_STR;
   p.nstr = nstr;
@@ -366,25 +390,52 @@ static Plan make_plan(bool res_is_q, int64_t B, int d, int64_t n_ent) {
   return pl;
 }
 
+__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = *reinterpret_cast<const float4*>(src + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + i) = o;
+  }
+  if (i < n) for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+}
+
 }  // namespace tcb
 
-bool tc_bwd_supported(int d) { return d % 16 == 0 && d <= 128; }
+bool tc_bwd_supported(int math, int d) { return math == KGEB_MATH_BF16 && d % 16 == 0 && d <= 256; }
+
+int tc_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
+  if (n == 0) return KGEB_OK;
+  KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(src) & 15) | (reinterpret_cast<uintptr_t>(dst) & 7)) == 0,
+               "to_bf16: misaligned buffers");
+  int64_t blocks = (n / 4 + 255) / 256 + 1;
+  int grid = (int)(blocks > (int64_t)kNumSMs * 16 ? (int64_t)kNumSMs * 16 : blocks);
+  tcb::to_bf16_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  KGEB_LAUNCH_CHECK("to_bf16");
+  return KGEB_OK;
+}
 
 int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz) {
   int64_t partial = (int64_t)kNumSMs * B * d * 4;
   int64_t rows = nnz * (int64_t)d * 4 + nnz * 8 + 512;
-  return partial + rows + kgeb_scatter_workspace_bytes(nnz) + B * 4 + 2048;
+  return partial + rows + kgeb_scatter_workspace_bytes(nnz) + 2048;
 }
 
-int tc_fused_bwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
-                 const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const float* tscale, float ls_add,
-                 float offset, const float* lse, float inv_batch, const float* row_scale, float* dQ, float* dTable,
-                 void* ws, int64_t ws_bytes, cudaStream_t st) {
+// Qb / tableb: bf16 mirrors of Q [B,d] and of the table shard [n_ent,d]
+int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
+                 int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
+                 const float* tscale, float ls_add, float offset, const float* lse, float inv_batch,
+                 const float* row_scale, float* dQ, float* dTable, void* ws, int64_t ws_bytes, cudaStream_t st) {
   using namespace tcb;
-  KGEB_REQUIRE(tc_bwd_supported(d), "fused_bwd(tf32): entity dim must be a multiple of 16 and <= 128 (got %d)", d);
-  KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(table)) & 15) == 0,
-               "TF32 tiles need 16-byte aligned operands");
-  KGEB_REQUIRE(ws_bytes >= tc_bwd_workspace_bytes(B, d, n_ent, nnz), "fused_bwd(tf32): workspace too small");
+  KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_bwd(bf16): entity dim must be a multiple of 16 and <= 256 (got %d)", d);
+  KGEB_REQUIRE(Qb && tableb, "fused_bwd(bf16): the bf16 mirrors of Q and of the table are required");
+  KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(Qb) | reinterpret_cast<uintptr_t>(tableb)) & 15) == 0,
+               "tensor tiles need 16-byte aligned operands");
+  KGEB_REQUIRE(ws_bytes >= tc_bwd_workspace_bytes(B, d, n_ent, nnz), "fused_bwd(bf16): workspace too small");
   char* wp = reinterpret_cast<char*>(ws);
   float* partial = reinterpret_cast<float*>(wp);
   wp += (((int64_t)kNumSMs * B * d * 4 + 255) / 256) * 256;
@@ -393,34 +444,35 @@ int tc_fused_bwd(int loss, const float* Q, int64_t B, int d, const float* table,
   int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);
   wp += ((nnz * 8 + 255) / 256) * 256;
   void* scatter_ws = wp;
-  const int64_t scatter_bytes = ws_bytes - (wp - reinterpret_cast<char*>(ws)) - B * 4 - 512;  // tail holds tscale
+  const int64_t scatter_bytes = ws_bytes - (wp - reinterpret_cast<char*>(ws));
   int rc;
-  CUtensorMap m_q128, m_q64, m_w128, m_w64;
+  CUtensorMap m_res, m_str;
   if (n_ent > 0 && B > 0) {
     if (dQ) {
-      Plan pl = make_plan(true, B, d, n_ent);
-      if (pl.p.nstr < 2) { set_error("fused_bwd(tf32): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
+      Plan pl = make_plan(true, true, B, d, n_ent);
+      if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
       pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = partial;
-      if ((rc = make_map(&m_q128, Q, B, d, RES_ROWS)) || (rc = make_map(&m_w64, table, n_ent, d, STR_ROWS))) return rc;
+      if ((rc = make_map(&m_res, Qb, B, d, RES_ROWS, true)) || (rc = make_map(&m_str, tableb, n_ent, d, STR_ROWS, true))) return rc;
       const int64_t jobs = pl.p.n_res_blocks * pl.p.chunks;
-      cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
       if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
-      tc_bwd_kernel<true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_q128, m_w64, pl.p);
+      tc_bwd_kernel<true, true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);
       KGEB_LAUNCH_CHECK("tc_bwd_kernel<dQ>");
       reduce_dq_labels_kernel<<<(unsigned)B, 128, 0, st>>>(partial, pl.p.chunks, B, d, table, e_lo, n_ent, lab_off,
                                                           lab_col, tscale, row_scale, inv_batch, dQ);
       KGEB_LAUNCH_CHECK("reduce_dq_labels");
     }
     if (dTable) {
-      Plan pl = make_plan(false, B, d, n_ent);
+      Plan pl = make_plan(false, true, B, d, n_ent);
+      if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
       pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = dTable;
-      if ((rc = make_map(&m_w128, table, n_ent, d, RES_ROWS)) || (rc = make_map(&m_q64, Q, B, d, STR_ROWS))) return rc;
+      if ((rc = make_map(&m_res, tableb, n_ent, d, RES_ROWS, true)) || (rc = make_map(&m_str, Qb, B, d, STR_ROWS, true))) return rc;
       const int64_t jobs = pl.p.n_res_blocks;
-      cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
       if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
-      tc_bwd_kernel<false><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_w128, m_q64, pl.p);
+      tc_bwd_kernel<false, true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);
       KGEB_LAUNCH_CHECK("tc_bwd_kernel<dTable>");
       if (nnz > 0) {
         label_rows_kernel<<<(unsigned)B, 128, 0, st>>>(Q, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale,

@@ -80,10 +80,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
 // a_major @15, b_major @16 (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// fmt: 2 = TF32 (kind::tf32), 1 = BF16 (kind::f16)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int fmt = 2) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// element traits of the two tensor-core operand types: fp32 read as TF32, or BF16 mirrors
+template <bool BF16>
+struct Elem {
+  static constexpr int kBytes = BF16 ? 2 : 4;
+  static constexpr int kSlabK = 128 / kBytes;   // elements per 128-byte swizzle row (32 | 64)
+  static constexpr int kUmmaK = 32 / kBytes;    // K per tcgen05.mma (8 | 16): always 32 bytes of a row
+  static constexpr int kFmt = BF16 ? 1 : 2;
+};
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -94,6 +104,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if (BF16) umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -130,8 +157,9 @@ __device__ __forceinline__ int64_t lb_i64(const int64_t* a, int64_t lo, int64_t 
 }
 
 
-// 2-D fp32 row-major [rows, d] tensor map: box = 32 columns (128 B) x box_rows, 128-byte swizzle, OOB -> zeros
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int d, int box_rows);
+// 2-D row-major [rows, d] tensor map (fp32 or bf16): box = 128 bytes of a row x box_rows, 128-byte swizzle,
+// out-of-bounds elements read as zeros
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows, bool bf16 = false);
 
 }  // namespace tc
 }  // namespace kgeb

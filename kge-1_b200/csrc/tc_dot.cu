@@ -19,9 +19,7 @@ namespace kgeb {
 namespace tc {
 
 constexpr int TILE = 128;                 // rows per operand tile (UMMA M = N = 128)
-constexpr int SLAB_K = 32;                // fp32 per 128-byte swizzle row
 constexpr int SLAB_BYTES = TILE * 128;    // 16 KiB: 128 rows x 128 B
-constexpr int UMMA_K = 8;                 // kind::tf32
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int NUM_THREADS = 256;
@@ -53,13 +51,14 @@ struct Params {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODE, int NQB>
+template <int MODE, int NQB, bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_w, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KS = p.ks, STAGES = p.stages;
+  constexpr int SLAB_K = Elem<BF16>::kSlabK, UMMA_K = Elem<BF16>::kUmmaK;
   uint8_t* q_smem = smem;                                  // [NQB][KS] slabs, resident per job
   uint8_t* ring = smem + (size_t)NQB * KS * SLAB_BYTES;    // [STAGES] slabs
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * SLAB_BYTES);
@@ -126,7 +125,7 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE, TILE, 0, 0);
+      constexpr uint32_t idesc = make_idesc(TILE, TILE, 0, 0, Elem<BF16>::kFmt);
       int stage = 0, buf = 0;
       uint32_t phase = 0, qphase = 0, tphase[2] = {0, 0};
       for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -148,10 +147,10 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               const uint32_t acc = tmem_base + (uint32_t)((buf * NQB + qb) * TILE);
 #pragma unroll
               for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk) {
-                const uint64_t qd = make_desc(q_addr + kk * UMMA_K * 4, 16, 1024);
-                const uint64_t wd = make_desc(w_addr + kk * UMMA_K * 4, 16, 1024);
-                if (MODE == MODE_SCORES) umma_tf32(acc, wd, qd, idesc, (k | kk) != 0);  // lanes = entities
-                else                     umma_tf32(acc, qd, wd, idesc, (k | kk) != 0);  // lanes = queries
+                const uint64_t qd = make_desc(q_addr + kk * 32, 16, 1024);  // UMMA_K elements = 32 bytes
+                const uint64_t wd = make_desc(w_addr + kk * 32, 16, 1024);
+                if (MODE == MODE_SCORES) umma<BF16>(acc, wd, qd, idesc, (k | kk) != 0);  // lanes = entities
+                else                     umma<BF16>(acc, qd, wd, idesc, (k | kk) != 0);  // lanes = queries
               }
             }
             umma_commit(&empty[stage]);  // frees the slab once these MMAs have read it
@@ -360,19 +359,20 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int d, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows, bool bf16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return KGEB_ERR_CUDA;
   }
+  const int esize = bf16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)SLAB_K, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * esize};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d) for [%lld x %d] at %p", (int)r, (long long)rows, d, base);
     return KGEB_ERR_CUDA;
@@ -380,8 +380,9 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int d, int box_r
   return KGEB_OK;
 }
 
-static int check_operands(const float* Q, const float* table, int d) {
-  KGEB_REQUIRE(d % 4 == 0, "TF32 tiles need an embedding dim that is a multiple of 4 (got %d)", d);
+static int check_operands(const void* Q, const void* table, int d, bool bf16 = false) {
+  KGEB_REQUIRE(d % (bf16 ? 8 : 4) == 0, "tensor tiles need an embedding dim that is a multiple of %d (got %d)",
+               bf16 ? 8 : 4, d);
   KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(table)) & 15) == 0,
                "TF32 tiles need 16-byte aligned operands");
   if (d > 256) {
@@ -392,14 +393,17 @@ static int check_operands(const float* Q, const float* table, int d) {
 }
 
 struct Plan {
+  bool bf16;
   int nqb;  // query blocks resident per job (1 or 2)
   Params p;
   size_t smem;
 };
 
-static Plan make_plan(int64_t B, int d, int64_t n_ent, int64_t e_lo) {
+static Plan make_plan(int64_t B, int d, int64_t n_ent, int64_t e_lo, bool bf16 = false) {
   Plan pl;
-  const int ks = (d + SLAB_K - 1) / SLAB_K;
+  const int slab_k = bf16 ? 64 : 32;
+  const int ks = (d + slab_k - 1) / slab_k;
+  pl.bf16 = bf16;
   const int64_t n_qblocks = (B + TILE - 1) / TILE;
   pl.nqb = (n_qblocks >= 2 && ks <= 4) ? 2 : 1;
   const size_t q_bytes = (size_t)pl.nqb * ks * SLAB_BYTES;
@@ -425,15 +429,19 @@ static int launch(const Plan& pl, const CUtensorMap& mq, const CUtensorMap& mw, 
   const int64_t jobs = pl.p.n_qgroups * pl.p.chunks;
   const int grid = (int)(jobs < kNumSMs ? jobs : kNumSMs);
   cudaError_t e;
-  if (pl.nqb == 2) {
-    e = cudaFuncSetAttribute(tc_tiles_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return cuda_status(e, "tc smem attribute");
-    tc_tiles_kernel<MODE, 2><<<grid, NUM_THREADS, pl.smem, st>>>(mq, mw, pl.p);
-  } else {
-    e = cudaFuncSetAttribute(tc_tiles_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return cuda_status(e, "tc smem attribute");
-    tc_tiles_kernel<MODE, 1><<<grid, NUM_THREADS, pl.smem, st>>>(mq, mw, pl.p);
+#define KGEB_TC_LAUNCH(NQB_, BF_)                                                                                     \
+  {                                                                                                                   \
+    e = cudaFuncSetAttribute(tc_tiles_kernel<MODE, NQB_, BF_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                             (int)pl.smem);                                                                           \
+    if (e != cudaSuccess) return cuda_status(e, "tc smem attribute");                                                 \
+    tc_tiles_kernel<MODE, NQB_, BF_><<<grid, NUM_THREADS, pl.smem, st>>>(mq, mw, pl.p);                               \
   }
+  if (pl.nqb == 2) {
+    if (pl.bf16) KGEB_TC_LAUNCH(2, true) else KGEB_TC_LAUNCH(2, false)
+  } else {
+    if (pl.bf16) KGEB_TC_LAUNCH(1, true) else KGEB_TC_LAUNCH(1, false)
+  }
+#undef KGEB_TC_LAUNCH
   KGEB_LAUNCH_CHECK("tc_tiles_kernel");
   return KGEB_OK;
 }
@@ -497,19 +505,23 @@ int tc_score_all(const float* Q, int64_t B, int d, const float* table, int64_t m
 
 int64_t tc_stats_partial_bytes(int64_t B) { return (int64_t)kNumSMs * B * 4 * (int64_t)sizeof(float) + B * 4 + 256; }
 
-int tc_fused_fwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
-                 const int64_t* lab_off, const int64_t* lab_col, float ls_keep, float ls_add, float offset,
-                 float* rowstat, void* ws, int64_t ws_bytes, cudaStream_t st) {
-  int rc = tc::check_operands(Q, table, d);
+// math: KGEB_MATH_TF32 reads the fp32 Q / table in place; KGEB_MATH_BF16 reads the bf16 mirrors Qb / tableb
+int tc_fused_fwd(int loss, int math, const float* Q, const void* Qb, int64_t B, int d, const float* table,
+                 const void* tableb, int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col,
+                 float ls_keep, float ls_add, float offset, float* rowstat, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const bool bf16 = (math == KGEB_MATH_BF16);
+  int rc = tc::check_operands(bf16 ? Qb : (const void*)Q, bf16 ? tableb : (const void*)table, d, bf16);
   if (rc) return rc;
-  KGEB_REQUIRE(ws_bytes >= tc_stats_partial_bytes(B), "fused_fwd(tf32): workspace too small");
+  KGEB_REQUIRE(ws_bytes >= tc_stats_partial_bytes(B), "fused_fwd(tensor tiles): workspace too small");
   float* partial = reinterpret_cast<float*>(ws);
-  tc::Plan pl = tc::make_plan(B, d, n_ent, e_lo);
+  tc::Plan pl = tc::make_plan(B, d, n_ent, e_lo, bf16);
   float* label_dot = partial + pl.p.chunks * B * 4;
   pl.p.loss = loss; pl.p.offset = offset; pl.p.partial = partial;
   if (n_ent > 0) {
     CUtensorMap mq, mw;
-    if ((rc = tc::make_map(&mq, Q, B, d, tc::TILE)) || (rc = tc::make_map(&mw, table, n_ent, d, tc::TILE))) return rc;
+    if ((rc = tc::make_map(&mq, bf16 ? Qb : (const void*)Q, B, d, tc::TILE, bf16)) ||
+        (rc = tc::make_map(&mw, bf16 ? tableb : (const void*)table, n_ent, d, tc::TILE, bf16)))
+      return rc;
     if ((rc = tc::launch<tc::MODE_STATS>(pl, mq, mw, st))) return rc;
   }
   tc::label_dot_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(Q, B, d, table, e_lo, n_ent, lab_off, lab_col,

@@ -15,14 +15,17 @@ int tc_score_all(const float* Q, int64_t B, int d, const float* table, int64_t m
                  int64_t col_off, cudaStream_t st);  // tc_dot.cu
 int64_t tc_stats_partial_bytes(int64_t B);                       // tc_dot.cu
 int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz);  // tc_bwd.cu
-bool tc_bwd_supported(int d);                                                    // tc_bwd.cu
-int tc_fused_fwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
-                 const int64_t* lab_off, const int64_t* lab_col, float ls_keep, float ls_add, float offset,
-                 float* rowstat, void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_dot.cu
-int tc_fused_bwd(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent,
-                 const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const float* tscale, float ls_add,
-                 float offset, const float* lse, float inv_batch, const float* row_scale, float* dQ, float* dTable,
-                 void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
+bool tc_bwd_supported(int math, int d);                                                    // tc_bwd.cu
+int tc_fused_fwd(int loss, int math, const float* Q, const void* Qb, int64_t B, int d, const float* table,
+                 const void* tableb, int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col,
+                 float ls_keep, float ls_add, float offset, float* rowstat, void* ws, int64_t ws_bytes,
+                 cudaStream_t st);  // tc_dot.cu
+int tc_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);  // tc_bwd.cu
+int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
+                 int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
+                 const float* tscale, float ls_add, float offset, const float* lse, float inv_batch,
+                 const float* row_scale, float* dQ, float* dTable, void* ws, int64_t ws_bytes,
+                 cudaStream_t st);  // tc_bwd.cu
 int tc_rank_count(const float* Q, int64_t nq, int d, const float* table, int64_t e_lo, int64_t n_ent,
                   const float* true_score, const void* true_ent, int idx64, const int64_t* f_off,
                   const int64_t* f_col, const int64_t* t_off, const int64_t* t_col, int64_t* counts,
@@ -756,7 +759,21 @@ int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities,
   int64_t b = tc_stats_partial_bytes(B);
   int64_t c = tc_bwd_workspace_bytes(B, d, num_shard_entities, nnz);
   int64_t m = a > b ? a : b;
-  return m > c ? m : c;
+  m = m > c ? m : c;
+  return m + B * 4 + B * (int64_t)d * 2 + 1024;  // + tail: per-row label weights, bf16 mirror of Q
+}
+
+// tail of the workspace: [ ... usable ... | bf16 Q mirror | per-row label weights ]
+struct TailWs {
+  float* tscale;
+  void* qb;
+  int64_t usable;
+};
+static TailWs carve_tail(void* ws, int64_t ws_bytes, int64_t B, int d) {
+  char* base = reinterpret_cast<char*>(ws);
+  char* ts = reinterpret_cast<char*>(reinterpret_cast<uintptr_t>(base + ws_bytes - B * 4) & ~(uintptr_t)255);
+  char* qb = reinterpret_cast<char*>(reinterpret_cast<uintptr_t>(ts - B * (int64_t)d * 2) & ~(uintptr_t)255);
+  return TailWs{reinterpret_cast<float*>(ts), qb, (int64_t)(qb - base)};
 }
 
 
@@ -773,19 +790,25 @@ static int check_fused(int loss, int d, float ls, const void* Q, const void* tab
 
 int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
-                   float label_smoothing, float offset, float* rowstat, void* workspace, int64_t workspace_bytes,
-                   void* stream) {
+                   float label_smoothing, float offset, const void* table_bf16, float* rowstat, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
   int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
   if (rc) return rc;
   KGEB_REQUIRE(rowstat, "fused_fwd: rowstat is NULL");
   const int64_t n_ent = e_hi - e_lo;
   if (B == 0) return KGEB_OK;
   cudaStream_t st = as_stream(stream);
-  KGEB_REQUIRE(workspace && workspace_bytes >= fused_ws_cuda_core(B, d, n_ent), "fused_fwd: workspace too small");
+  KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, 0), "fused_fwd: workspace too small");
   LossParams lp{loss, 1.f - label_smoothing, label_smoothing > 0.f ? 1.f / (float)num_entities : 0.f, offset, 1.f};
-  if (math == KGEB_MATH_TF32)
-    return tc_fused_fwd(loss, Q, B, d, table, e_lo, n_ent, lab_off, lab_col, lp.ls_keep, lp.ls_add, offset, rowstat,
-                        workspace, workspace_bytes, st);
+  if (math == KGEB_MATH_TF32 || math == KGEB_MATH_BF16) {
+    TailWs tail = carve_tail(workspace, workspace_bytes, B, d);
+    if (math == KGEB_MATH_BF16) {
+      KGEB_REQUIRE(table_bf16, "fused_fwd(bf16): the bf16 mirror of the table is required (kgeb_to_bf16)");
+      if ((rc = tc_to_bf16(Q, tail.qb, B * (int64_t)d, st))) return rc;
+    }
+    return tc_fused_fwd(loss, math, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, lp.ls_keep,
+                        lp.ls_add, offset, rowstat, workspace, tail.usable, st);
+  }
   const int64_t ntc = (n_ent + BN - 1) / BN, ntr = (B + BM - 1) / BM;
   const int64_t chunks = pick_chunks(ntc < 1 ? 1 : ntc, ntr);
   const int64_t tpc = ntc == 0 ? 1 : (ntc + chunks - 1) / chunks;
@@ -810,8 +833,8 @@ __global__ void label_weight_kernel(int loss, const int64_t* __restrict__ lab_of
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                    float label_smoothing, float offset, const float* lse, float inv_batch,
-                   const float* grad_scale, float* dQ, float* dTable, void* workspace, int64_t workspace_bytes,
-                   void* stream) {
+                   const float* grad_scale, const void* table_bf16, float* dQ, float* dTable, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
   int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
   if (rc) return rc;
   KGEB_REQUIRE(loss != KGEB_LOSS_KL || lse, "fused_bwd: KL needs the per-row log-sum-exp");
@@ -819,7 +842,7 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
   const int64_t n_ent = e_hi - e_lo;
   if (B == 0) return KGEB_OK;
   cudaStream_t st = as_stream(stream);
-  KGEB_REQUIRE(workspace && workspace_bytes >= fused_ws_cuda_core(B, d, n_ent), "fused_bwd: workspace too small");
+  KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, nnz), "fused_bwd: workspace too small");
   LossParams lp{loss, 1.f - label_smoothing, label_smoothing > 0.f ? 1.f / (float)num_entities : 0.f, offset,
                 inv_batch};
   const int64_t ntc = (n_ent + BN - 1) / BN, ntr = (B + BM - 1) / BM;
@@ -829,15 +852,17 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
   int64_t part_bytes = chunks * B * (int64_t)d * 4, stat_bytes = chunks * B * 16;
   float* tscale = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) +
                                            (((part_bytes > stat_bytes ? part_bytes : stat_bytes) + 255) / 256) * 256);
-  if (math == KGEB_MATH_TF32 && tc_bwd_supported(d)) {
-    KGEB_REQUIRE(workspace_bytes >= tc_bwd_workspace_bytes(B, d, n_ent, nnz), "fused_bwd(tf32): workspace too small");
-    float* ts = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((workspace_bytes - B * 4) & ~(int64_t)255));
-    label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, ts);
+  if (tc_bwd_supported(math, d)) {
+    KGEB_REQUIRE(table_bf16, "fused_bwd(bf16): the bf16 mirror of the table is required (kgeb_to_bf16)");
+    TailWs tail = carve_tail(workspace, workspace_bytes, B, d);
+    label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, tail.tscale);
     KGEB_LAUNCH_CHECK("label_weight");
-    return tc_fused_bwd(loss, Q, B, d, table, e_lo, n_ent, lab_off, lab_col, nnz, ts, lp.ls_add, offset, lse, inv_batch,
-                        grad_scale, dQ, dTable, workspace, workspace_bytes, st);
+    if ((rc = tc_to_bf16(Q, tail.qb, B * (int64_t)d, st))) return rc;
+    return tc_fused_bwd(loss, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, tail.tscale,
+                        lp.ls_add, offset, lse, inv_batch, grad_scale, dQ, dTable, workspace, tail.usable, st);
   }
-  // (TF32 requested but the dim is outside the tensor-tile build: the fp32 CUDA-core tiles below serve it)
+  // KGEB_MATH_TF32 (an MN-major TF32 operand would need a second, differently swizzled copy of every tile) and
+  // dims outside the BF16 tile build use the fp32 CUDA-core tiles below
   label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, tscale);
   KGEB_LAUNCH_CHECK("label_weight");
   const int nc = (d + 31) / 32;
@@ -862,6 +887,11 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
   return KGEB_OK;
 }
 
+
+int kgeb_to_bf16(const float* src, void* dst, int64_t numel, void* stream) {
+  KGEB_REQUIRE(src && dst && numel >= 0, "to_bf16: bad arguments");
+  return tc_to_bf16(src, dst, numel, as_stream(stream));
+}
 
 int kgeb_rank_count(int kind, int math, const float* Q, int64_t nq, int d, const float* table, int64_t e_lo,
                     int64_t e_hi, const float* true_score, const void* true_ent, int idx64,

@@ -75,8 +75,16 @@ def fused_rowstats(q, table, lab_off, lab_col, loss, label_smoothing, offset, ma
     ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent, lab_col.numel()))
     lib.call("kgeb_fused_fwd", loss, math, lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo,
              shard.e_hi, shard.num_entities, lib.i64(lab_off, "label offsets"), lib.i64(lab_col, "label columns"),
-             float(label_smoothing), float(offset), rowstat.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream_ptr(q))
+             float(label_smoothing), float(offset), _mirror_ptr(table, math, b, d), rowstat.data_ptr(), ws.data_ptr(),
+             ws.numel(), lib.stream_ptr(q))
     return rowstat
+
+
+def _mirror_ptr(table, math, b, d):
+    """bf16 mirror of the table for KGEB_MATH_BF16 (None when the tensor tiles will not be used)."""
+    if math != lib.MATH_BF16 or d % 16 != 0 or d > 256:
+        return None
+    return ops.bf16_mirror(table).data_ptr()
 
 
 def rows_loss(rowstat: torch.Tensor, lab_off: torch.Tensor, loss: int, label_smoothing: float,
@@ -106,7 +114,7 @@ def fused_backward(q, table, lab_off, lab_col, loss, label_smoothing, offset, ls
     lib.call("kgeb_fused_bwd", loss, math, lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo,
              shard.e_hi, shard.num_entities, lib.i64(lab_off), lib.i64(lab_col), lab_col.numel(), float(label_smoothing),
              float(offset), None if lse is None else lib.f32(lse, "lse"), float(inv_batch),
-             None if grad_scale is None else lib.f32(grad_scale, "grad scale"),
+             None if grad_scale is None else lib.f32(grad_scale, "grad scale"), _mirror_ptr(table, math, b, d),
              None if dq is None else dq.data_ptr(), None if d_table is None else lib.f32(d_table, "table gradient"),
              ws.data_ptr(), ws.numel(), lib.stream_ptr(q))
     if dq is not None and n_ent == 0:

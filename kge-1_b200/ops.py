@@ -25,6 +25,25 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
     return buf
 
 
+_mirror_cache = {}
+
+
+def bf16_mirror(table: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of an fp32 table for KGEB_MATH_BF16, refreshed when the tensor's version counter moves
+    (optimizer steps, renormalisation hooks and checkpoint loads all bump it)."""
+    t = table.detach()
+    key = (t.data_ptr(), tuple(t.shape))
+    hit = _mirror_cache.get(key)
+    if hit is not None and hit[0] == table._version:
+        return hit[1]
+    buf = hit[1] if hit is not None else torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+    lib.call("kgeb_to_bf16", lib.f32(t.contiguous(), "table"), buf.data_ptr(), t.numel(), lib.stream_ptr(t))
+    if len(_mirror_cache) > 16:
+        _mirror_cache.clear()
+    _mirror_cache[key] = (table._version, buf)
+    return buf
+
+
 def pair_kind(model: str, l_norm: float = 1.0) -> int:
     """Pair-score family of a scorer for its all-entity forms (include/kgeb200.h)."""
     if model in ("distmult", "complex", "cp", "simple", "rescal"):

@@ -47,6 +47,7 @@ class Adagrad(torch.optim.Optimizer):
                     lib.call("kgeb_adagrad_dense", lib.f32(p.data, "param"), lib.f32(st["sum"], "state"),
                              lib.f32(g.contiguous(), "grad"), p.numel(), clr, group["eps"], group["weight_decay"],
                              lib.stream_ptr(p))
+                torch.autograd.graph.increment_version(p)  # the kernel wrote through the raw pointer
         return loss
 
 
@@ -76,6 +77,7 @@ class Adam(torch.optim.Optimizer):
                 lib.call("kgeb_adam_dense", lib.f32(p.data, "param"), lib.f32(st["exp_avg"]), lib.f32(st["exp_avg_sq"]),
                          lib.f32(p.grad.contiguous(), "grad"), p.numel(), group["lr"], b1, b2, group["eps"],
                          group["weight_decay"], 1 - b1 ** t, 1 - b2 ** t, lib.stream_ptr(p))
+                torch.autograd.graph.increment_version(p)
         return loss
 
 
