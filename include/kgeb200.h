@@ -66,12 +66,13 @@ int kgeb_score_spo_bwd(int model, int l_norm, const float* s_src, const void* s_
 
 /* ---- query transform of the sp_/_po forms (<model>.py score_emb "sp_"/"_po"):
  * Q[i,:] = q(a_i, p_i), a = s for KGEB_SP_, a = o for KGEB__PO; Q is [n,d].  */
-int kgeb_query_build(int model, int combine, const float* a_src, const void* a_idx, const float* p_src,
-                     const void* p_idx, int idx64, int64_t n, int d, float* Q, void* stream);
+int kgeb_query_build(int model, int combine, const int32_t* row_combine /* per-row KGEB_SP_/KGEB__PO, or NULL */,
+                     const float* a_src, const void* a_idx, const float* p_src, const void* p_idx, int idx64,
+                     int64_t n, int d, float* Q, void* stream);
 /* chain rule dQ -> da[n,d], dp[n,dr] */
-int kgeb_query_bwd(int model, int combine, const float* a_src, const void* a_idx, const float* p_src,
-                   const void* p_idx, int idx64, int64_t n, int d, const float* dQ, float* da, float* dp,
-                   void* stream);
+int kgeb_query_bwd(int model, int combine, const int32_t* row_combine, const float* a_src, const void* a_idx,
+                   const float* p_src, const void* p_idx, int idx64, int64_t n, int d, const float* dQ, float* da,
+                   float* dp, void* stream);
 
 /* ---- negative-sampling pair scoring (train.py:872-893 "triple" implementation without the
  * B*(1+N) expansion): out[i,j] = pair_score(kind, Q[i,:], table[cand[i,j],:]), cand is [B,M]. */
@@ -151,7 +152,7 @@ int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int6
 /* ---- a21/K11: optimizer steps with torch.optim semantics (util/optimizer.py:10-17).
  * Adagrad: g += wd*w; state += g*g; w -= clr * g / (sqrt(state) + eps), clr = lr/(1+(step-1)*lr_decay) */
 int kgeb_adagrad_dense(float* W, float* state, const float* grad, int64_t numel, float clr, float eps,
-                       float weight_decay, void* stream);
+                       float weight_decay, void* bf16_mirror /* updated alongside W, or NULL */, void* stream);
 /* touched-rows-only Adagrad (equals the dense step when untouched rows have zero gradient and wd=0) */
 int kgeb_adagrad_rows(float* W, float* state, const int64_t* row_ids, const float* row_grads,
                       const int64_t* num_rows_dev, int64_t max_rows, int d, float clr, float eps, void* stream);

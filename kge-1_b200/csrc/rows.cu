@@ -255,14 +255,14 @@ score_spo_bwd_kernel(int l_norm, const float* s_src, const void* s_idx, const fl
 // ------------------------------------------------------------------------------------------
 template <int MODEL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-query_build_kernel(int combine, const float* a_src, const void* a_idx, const float* p_src, const void* p_idx,
-                   int idx64, int64_t n, int d, float* __restrict__ Q) {
+query_build_kernel(int combine, const int32_t* __restrict__ row_combine, const float* a_src, const void* a_idx,
+                   const float* p_src, const void* p_idx, int idx64, int64_t n, int d, float* __restrict__ Q) {
   const int lane = threadIdx.x & 31;
   const int h = d >> 1;
   const int dr = relation_dim(MODEL, d);
-  const bool sp = (combine == KGEB_SP_);
   int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
   for (; row < n; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const bool sp = ((row_combine ? row_combine[row] : combine) == KGEB_SP_);
     const float* a = row_ptr(a_src, a_idx, idx64, row, d);
     const float* p = row_ptr(p_src, p_idx, idx64, row, dr);
     float* q = Q + row * d;
@@ -336,15 +336,15 @@ query_build_kernel(int combine, const float* a_src, const void* a_idx, const flo
 
 template <int MODEL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-query_bwd_kernel(int combine, const float* a_src, const void* a_idx, const float* p_src, const void* p_idx,
-                 int idx64, int64_t n, int d, const float* __restrict__ dQ, float* __restrict__ da,
-                 float* __restrict__ dp) {
+query_bwd_kernel(int combine, const int32_t* __restrict__ row_combine, const float* a_src, const void* a_idx,
+                 const float* p_src, const void* p_idx, int idx64, int64_t n, int d, const float* __restrict__ dQ,
+                 float* __restrict__ da, float* __restrict__ dp) {
   const int lane = threadIdx.x & 31;
   const int h = d >> 1;
   const int dr = relation_dim(MODEL, d);
-  const bool sp = (combine == KGEB_SP_);
   int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
   for (; row < n; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const bool sp = ((row_combine ? row_combine[row] : combine) == KGEB_SP_);
     const float* a = row_ptr(a_src, a_idx, idx64, row, d);
     const float* p = row_ptr(p_src, p_idx, idx64, row, dr);
     const float* g = dQ + row * d;
@@ -668,31 +668,31 @@ int kgeb_score_spo_bwd(int model, int l_norm, const float* s_src, const void* s_
   return KGEB_OK;
 }
 
-int kgeb_query_build(int model, int combine, const float* a_src, const void* a_idx, const float* p_src,
-                     const void* p_idx, int idx64, int64_t n, int d, float* Q, void* stream) {
+int kgeb_query_build(int model, int combine, const int32_t* row_combine, const float* a_src, const void* a_idx,
+                     const float* p_src, const void* p_idx, int idx64, int64_t n, int d, float* Q, void* stream) {
   int rc = check_model(model, d, 1);
   if (rc) return rc;
-  KGEB_REQUIRE(combine == KGEB_SP_ || combine == KGEB__PO, "query_build: combine must be sp_ or _po");
+  KGEB_REQUIRE(row_combine || combine == KGEB_SP_ || combine == KGEB__PO, "query_build: combine must be sp_ or _po");
   KGEB_REQUIRE(a_src && p_src && Q && n >= 0, "query_build: bad arguments");
   if (n == 0) return KGEB_OK;
   cudaStream_t st = as_stream(stream);
   DISPATCH_MODEL(model, (query_build_kernel<M_><<<grid_for_rows(n), kWarpsPerBlock * 32, 0, st>>>(
-                            combine, a_src, a_idx, p_src, p_idx, idx64, n, d, Q)));
+                            combine, row_combine, a_src, a_idx, p_src, p_idx, idx64, n, d, Q)));
   KGEB_LAUNCH_CHECK("query_build");
   return KGEB_OK;
 }
 
-int kgeb_query_bwd(int model, int combine, const float* a_src, const void* a_idx, const float* p_src,
-                   const void* p_idx, int idx64, int64_t n, int d, const float* dQ, float* da, float* dp,
-                   void* stream) {
+int kgeb_query_bwd(int model, int combine, const int32_t* row_combine, const float* a_src, const void* a_idx,
+                   const float* p_src, const void* p_idx, int idx64, int64_t n, int d, const float* dQ, float* da,
+                   float* dp, void* stream) {
   int rc = check_model(model, d, 1);
   if (rc) return rc;
-  KGEB_REQUIRE(combine == KGEB_SP_ || combine == KGEB__PO, "query_bwd: combine must be sp_ or _po");
+  KGEB_REQUIRE(row_combine || combine == KGEB_SP_ || combine == KGEB__PO, "query_bwd: combine must be sp_ or _po");
   KGEB_REQUIRE(a_src && p_src && dQ && da && dp && n >= 0, "query_bwd: bad arguments");
   if (n == 0) return KGEB_OK;
   cudaStream_t st = as_stream(stream);
   DISPATCH_MODEL(model, (query_bwd_kernel<M_><<<grid_for_rows(n), kWarpsPerBlock * 32, 0, st>>>(
-                            combine, a_src, a_idx, p_src, p_idx, idx64, n, d, dQ, da, dp)));
+                            combine, row_combine, a_src, a_idx, p_src, p_idx, idx64, n, d, dQ, da, dp)));
   KGEB_LAUNCH_CHECK("query_bwd");
   return KGEB_OK;
 }

@@ -340,8 +340,15 @@ __global__ void reduce_dq_labels_kernel(const float* __restrict__ partial, int64
 __global__ void label_rows_kernel(const float* __restrict__ Q, int64_t B, int d, int64_t e_lo, int64_t n_ent,
                                   const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
                                   const float* __restrict__ tscale, const float* __restrict__ row_scale, float inv_batch,
-                                  float* __restrict__ rows, int64_t* __restrict__ ent) {
+                                  int64_t nnz, float* __restrict__ rows, int64_t* __restrict__ ent) {
   const int64_t q = blockIdx.x;
+  if (q == B) {  // extra block: entries [lab_off[B], nnz) are padding of a fixed-size label buffer -> zero rows
+    for (int64_t i = lab_off[B]; i < nnz; ++i) {
+      for (int c = threadIdx.x; c < d; c += blockDim.x) rows[i * d + c] = 0.f;
+      if (threadIdx.x == 0) ent[i] = 0;
+    }
+    return;
+  }
   const float w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
   for (int64_t i = lab_off[q]; i < lab_off[q + 1]; ++i) {
     const int64_t e = lab_col[i] - e_lo;
@@ -475,8 +482,8 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       tc_bwd_kernel<false, true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);
       KGEB_LAUNCH_CHECK("tc_bwd_kernel<dTable>");
       if (nnz > 0) {
-        label_rows_kernel<<<(unsigned)B, 128, 0, st>>>(Q, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale,
-                                                       inv_batch, lab_rows, lab_ent);
+        label_rows_kernel<<<(unsigned)B + 1, 128, 0, st>>>(Q, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale,
+                                                           inv_batch, nnz, lab_rows, lab_ent);
         KGEB_LAUNCH_CHECK("label_rows");
         if ((rc = kgeb_scatter_add_rows(lab_ent, 1, lab_rows, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st)))
           return rc;

@@ -7,6 +7,7 @@
 //  * device-side key lookup over KvsAllIndex arrays (indexing.py:36-55).
 #include "common.cuh"
 #include <cub/cub.cuh>
+#include <cuda_bf16.h>
 
 namespace kgeb {
 
@@ -145,7 +146,7 @@ static int sort_and_segment(const void* idx, int idx64, int64_t n, int64_t vocab
 // optimizers
 // ------------------------------------------------------------------------------------------
 __global__ void adagrad_dense_kernel(float* __restrict__ W, float* __restrict__ state, const float* __restrict__ grad,
-                                     int64_t numel, float clr, float eps, float wd) {
+                                     int64_t numel, float clr, float eps, float wd, __nv_bfloat16* __restrict__ mirror) {
   int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (; i + 3 < numel; i += stride) {
@@ -160,6 +161,13 @@ __global__ void adagrad_dense_kernel(float* __restrict__ W, float* __restrict__ 
     w.w -= clr * g.w / (sqrtf(s.w) + eps);
     *reinterpret_cast<float4*>(W + i) = w;
     *reinterpret_cast<float4*>(state + i) = s;
+    if (mirror) {  // keep the bf16 mirror of the table in step with the fp32 master (KGEB_MATH_BF16)
+      __nv_bfloat162 a = __floats2bfloat162_rn(w.x, w.y), b = __floats2bfloat162_rn(w.z, w.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(mirror + i) = o;
+    }
   }
   // tail (numel % 4): handled by the thread whose i lands on it
   if (i < numel && i + 3 >= numel) {
@@ -168,6 +176,7 @@ __global__ void adagrad_dense_kernel(float* __restrict__ W, float* __restrict__ 
       float s = fmaf(g, g, state[j]);
       state[j] = s;
       W[j] -= clr * g / (sqrtf(s) + eps);
+      if (mirror) mirror[j] = __float2bfloat16_rn(W[j]);
     }
   }
 }
@@ -269,14 +278,15 @@ int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int6
 }
 
 int kgeb_adagrad_dense(float* W, float* state, const float* grad, int64_t numel, float clr, float eps,
-                       float weight_decay, void* stream) {
+                       float weight_decay, void* bf16_mirror, void* stream) {
   KGEB_REQUIRE(W && state && grad && numel >= 0, "adagrad_dense: bad arguments");
   KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(state) |
                  reinterpret_cast<uintptr_t>(grad)) & 15) == 0, "adagrad_dense: pointers must be 16-byte aligned");
   if (numel == 0) return KGEB_OK;
   int64_t blocks = (numel / 4 + 255) / 256 + 1;
   int grid = (int)(blocks > (int64_t)kNumSMs * 8 ? (int64_t)kNumSMs * 8 : blocks);
-  adagrad_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, state, grad, numel, clr, eps, weight_decay);
+  adagrad_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, state, grad, numel, clr, eps, weight_decay,
+                                                            reinterpret_cast<__nv_bfloat16*>(bf16_mirror));
   KGEB_LAUNCH_CHECK("adagrad_dense");
   return KGEB_OK;
 }

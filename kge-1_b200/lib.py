@@ -30,8 +30,8 @@ SIGNATURES = {
     "kgeb_gather_rows": [_p, _l, _i, _p, _i, _l, _p, _p],
     "kgeb_score_spo": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _l, _i, _p, _p],
     "kgeb_score_spo_bwd": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _l, _i, _p, _p, _p, _p, _p],
-    "kgeb_query_build": [_i, _i, _p, _p, _p, _p, _i, _l, _i, _p, _p],
-    "kgeb_query_bwd": [_i, _i, _p, _p, _p, _p, _i, _l, _i, _p, _p, _p, _p],
+    "kgeb_query_build": [_i, _i, _p, _p, _p, _p, _p, _i, _l, _i, _p, _p],
+    "kgeb_query_bwd": [_i, _i, _p, _p, _p, _p, _p, _i, _l, _i, _p, _p, _p, _p],
     "kgeb_pairs_score": [_i, _p, _p, _p, _i, _l, _l, _i, _p, _p],
     "kgeb_pairs_bwd": [_i, _p, _p, _p, _i, _l, _l, _i, _p, _p, _p, _p, _p],
     "kgeb_score_all": [_i, _i, _p, _l, _i, _p, _p, _i, _l, _p, _l, _l, _p],
@@ -42,7 +42,7 @@ SIGNATURES = {
     "kgeb_rank_count": [_i, _i, _p, _l, _i, _p, _l, _l, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "kgeb_scatter_add_rows": [_p, _i, _p, _l, _i, _p, _l, _p, _l, _p],
     "kgeb_segment_reduce_rows": [_p, _i, _p, _l, _i, _p, _p, _p, _p, _l, _p],
-    "kgeb_adagrad_dense": [_p, _p, _p, _l, _f, _f, _f, _p],
+    "kgeb_adagrad_dense": [_p, _p, _p, _l, _f, _f, _f, _p, _p],
     "kgeb_adagrad_rows": [_p, _p, _p, _p, _p, _l, _i, _f, _f, _p],
     "kgeb_adam_dense": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p],
     "kgeb_csr_lookup": [_p, _l, _p, _l, _p, _p],

@@ -216,7 +216,7 @@ class _QueryBuild(torch.autograd.Function):
         a, p = a_emb.detach().contiguous(), p_emb.detach().contiguous()
         n, d = a.shape
         q = torch.empty(n, d, dtype=torch.float32, device=a.device)
-        lib.call("kgeb_query_build", model_id, combine, lib.f32(a, "embeddings"), None, lib.f32(p, "p_emb"), None, 0,
+        lib.call("kgeb_query_build", model_id, combine, None, lib.f32(a, "embeddings"), None, lib.f32(p, "p_emb"), None, 0,
                  n, d, q.data_ptr(), lib.stream_ptr(a))
         ctx.save_for_backward(a, p)
         ctx.model_id, ctx.combine = model_id, combine
@@ -228,7 +228,7 @@ class _QueryBuild(torch.autograd.Function):
         n, d = a.shape
         da, dp = torch.empty_like(a), torch.empty_like(p)
         g = dq.contiguous().float()
-        lib.call("kgeb_query_bwd", ctx.model_id, ctx.combine, a.data_ptr(), None, p.data_ptr(), None, 0, n, d,
+        lib.call("kgeb_query_bwd", ctx.model_id, ctx.combine, None, a.data_ptr(), None, p.data_ptr(), None, 0, n, d,
                  lib.f32(g, "grad"), da.data_ptr(), dp.data_ptr(), lib.stream_ptr(a))
         return None, None, da, dp
 

@@ -46,7 +46,7 @@ class Adagrad(torch.optim.Optimizer):
                 else:
                     lib.call("kgeb_adagrad_dense", lib.f32(p.data, "param"), lib.f32(st["sum"], "state"),
                              lib.f32(g.contiguous(), "grad"), p.numel(), clr, group["eps"], group["weight_decay"],
-                             lib.stream_ptr(p))
+                             None, lib.stream_ptr(p))
                 torch.autograd.graph.increment_version(p)  # the kernel wrote through the raw pointer
         return loss
 

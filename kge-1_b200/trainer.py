@@ -1,0 +1,157 @@
+"""Static-shape fused training step for the all-entity jobs (1vsAll, KvsAll) of the DOT scorers.
+
+One step = the reference's run_epoch body for one batch (train.py:309-376 with _process_batch of
+train.py:679-756 / 1032-1062) without autograd and without host round trips:
+
+    gather + query transform -> fused score+loss statistics -> loss -> fused backward (dQ, dense table
+    gradient) -> query-transform backward -> sorted scatter of the query-side rows -> Adagrad on both tables
+
+Every buffer has a fixed address and size (rows, nnz_max), so the whole step can be replayed as one CUDA
+graph; the per-batch inputs are copied into the static input buffers before each replay.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import fused, lib, ops
+from .model import KgeModel
+
+
+class FusedAllEntityStepper:
+    def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
+                 offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
+                 use_graph: bool = True):
+        if model.get_scorer().kind != lib.DOT:
+            raise NotImplementedError("the fused all-entity step serves the DOT scorers")
+        self.model, self.opt = model, optimizer
+        self.rows, self.nnz_max, self.loss_kind, self.batch_size = rows, nnz_max, loss_kind, batch_size
+        self.offset, self.ls, self.math = float(offset), float(label_smoothing), math_mode
+        self.ent = model.get_s_embedder().weight
+        self.rel = model.get_p_embedder().weight
+        dev = self.ent.device
+        self.E, self.d = self.ent.shape
+        self.dr = self.rel.shape[1]
+        group = optimizer.param_groups[0]
+        if group.get("lr_decay", 0.0) != 0.0 or group.get("weight_decay", 0.0) != 0.0:
+            raise NotImplementedError("the graph-captured step bakes lr into the launch (lr_decay / weight_decay = 0)")
+        self.lr, self.eps = float(group["lr"]), float(group["eps"])
+        f32 = dict(dtype=torch.float32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        # static inputs
+        self.a_idx = torch.zeros(rows, **i64)
+        self.p_idx = torch.zeros(rows, **i64)
+        self.row_combine = torch.zeros(rows, dtype=torch.int32, device=dev)
+        self.lab_off = torch.zeros(rows + 1, **i64)
+        self.lab_col = torch.zeros(max(nnz_max, 1), **i64)
+        # static intermediates / outputs
+        self.Q = torch.empty(rows, self.d, **f32)
+        self.dQ = torch.empty(rows, self.d, **f32)
+        self.da = torch.empty(rows, self.d, **f32)
+        self.dp = torch.empty(rows, self.dr, **f32)
+        self.g_ent = torch.zeros(self.E, self.d, **f32)
+        self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
+        self.rowstat = torch.empty(rows, 4, **f32)
+        self.loss = torch.zeros((), **f32)
+        self.shard = fused.Shard.full(self.E)
+        self.ws = torch.empty(lib.load().kgeb_fused_workspace_bytes(rows, self.d, self.E, max(nnz_max, 1)),
+                              dtype=torch.uint8, device=dev)
+        self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(rows), dtype=torch.uint8, device=dev)
+        self.mirror = None
+        if math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256:
+            self.mirror = torch.empty(self.E, self.d, dtype=torch.bfloat16, device=dev)
+            lib.call("kgeb_to_bf16", lib.f32(self.ent.detach(), "table"), self.mirror.data_ptr(), self.ent.numel(),
+                     lib.stream_ptr(self.ent))
+        self.kernel_launches_per_step = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        if use_graph:
+            self._capture()
+
+    # -- one step on the current stream ---------------------------------------------------------
+    def _launch(self):
+        st = lib.stream_ptr(self.ent)
+        model_id = lib.MODELS[self.model.model]
+        ent, rel = self.ent.detach(), self.rel.detach()
+        mp = None if self.mirror is None else self.mirror.data_ptr()
+        n = 0
+        self.g_ent.zero_(); self.g_rel.zero_(); n += 2
+        lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
+                 rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st); n += 1
+        lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
+                 self.E, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.ls, self.offset, mp,
+                 self.rowstat.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 4
+        per_row, lse = fused.rows_loss(self.rowstat, self.lab_off, self.loss_kind, self.ls, self.E)
+        torch.sum(per_row, dim=0, out=self.loss); self.loss.div_(self.batch_size); n += 6
+        lib.call("kgeb_fused_bwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
+                 self.E, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
+                 None if lse is None else lse.data_ptr(), 1.0 / self.batch_size, None, mp, self.dQ.data_ptr(),
+                 self.g_ent.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 14
+        lib.call("kgeb_query_bwd", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
+                 rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.dQ.data_ptr(), self.da.data_ptr(),
+                 self.dp.data_ptr(), st); n += 1
+        lib.call("kgeb_scatter_add_rows", self.a_idx.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
+                 self.g_ent.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st); n += 8
+        lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
+                 self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st); n += 8
+        s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
+        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), ent.numel(), self.lr,
+                 self.eps, 0.0, mp, st); n += 1
+        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), rel.numel(), self.lr,
+                 self.eps, 0.0, None, st); n += 1
+        self.kernel_launches_per_step = n
+
+    def _capture(self):
+        # warm-up on a side stream (PyTorch's capture protocol), restoring the parameters afterwards
+        keep = [t.detach().clone() for t in (self.ent, self.rel, self.opt.state[self.ent]["sum"],
+                                             self.opt.state[self.rel]["sum"])]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._launch()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._launch()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for dst, src in zip((self.ent, self.rel, self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]),
+                                keep):
+                dst.copy_(src)
+        if self.mirror is not None:
+            lib.call("kgeb_to_bf16", lib.f32(self.ent.detach(), "table"), self.mirror.data_ptr(), self.ent.numel(),
+                     lib.stream_ptr(self.ent))
+        torch.cuda.synchronize()
+
+    # -- public -------------------------------------------------------------------------------------
+    def set_inputs(self, a_idx, p_idx, row_combine, lab_off, lab_col):
+        """Copies one batch into the static input buffers (host pinned or device tensors; non-blocking)."""
+        self.a_idx.copy_(a_idx, non_blocking=True)
+        self.p_idx.copy_(p_idx, non_blocking=True)
+        self.row_combine.copy_(row_combine, non_blocking=True)
+        self.lab_off.copy_(lab_off, non_blocking=True)
+        k = lab_col.numel()
+        if k > self.nnz_max:
+            raise ValueError(f"batch has {k} labels, stepper was built for at most {self.nnz_max}")
+        self.lab_col[:k].copy_(lab_col, non_blocking=True)
+
+    def step(self) -> torch.Tensor:
+        """Runs one training step; returns the (device) loss tensor of this batch."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+        for st in (self.opt.state[self.ent], self.opt.state[self.rel]):
+            st["step"] += 1
+        torch.autograd.graph.increment_version(self.ent)
+        torch.autograd.graph.increment_version(self.rel)
+        return self.loss
+
+
+def kvsall_rows(queries: torch.Tensor, query_type: torch.Tensor):
+    """KvsAll batch -> (a_idx, p_idx, row_combine): sp_ rows use (s,p) = (q0,q1); _po rows (p,o) = (q0,q1)."""
+    qt = query_type.to(torch.int32)
+    a = torch.where(qt == 0, queries[:, 0], queries[:, 1])
+    p = torch.where(qt == 0, queries[:, 1], queries[:, 0])
+    return a.contiguous(), p.contiguous(), qt.contiguous()
