@@ -127,6 +127,41 @@ class TrainingJobKvsAll(TrainingJob):
         super().__init__(model, optimizer, loss, **kw)
         self.num_entities, self.num_relations = num_entities, num_relations
         self.label_smoothing = label_smoothing
+        self.stepper = None
+
+    # -- static-shape, graph-captured step (trainer.py) ---------------------------------------------------
+    def enable_graph_step(self, batch_size: int, nnz_max: int, use_graph: bool = True):
+        """Routes step() through FusedAllEntityStepper for batches of exactly `batch_size` queries with at most
+        `nnz_max` labels (no autograd, one CUDA-graph replay per step).  Needs the DOT scorers, dense Adagrad
+        and no penalty terms."""
+        from .trainer import FusedAllEntityStepper
+        if any(e.regularize_weight != 0.0 and e.regularize != "" for e in
+               (self.model.get_s_embedder(), self.model.get_p_embedder())):
+            raise NotImplementedError("penalty terms are not part of the graph-captured step")
+        self.stepper = FusedAllEntityStepper(self.model, self.optimizer, batch_size, nnz_max, self.loss.kind,
+                                             batch_size, self.loss.offset, self.label_smoothing, self.math_mode,
+                                             use_graph)
+        return self.stepper
+
+    def device_inputs(self, batch):
+        """Host (pinned) KvsAll batch -> device tensors (a_idx, p_idx, row_combine, lab_off, lab_col)."""
+        from .trainer import kvsall_rows
+        q = batch["queries"].to(self.device, non_blocking=True)
+        qt = batch["query_type_indexes"].to(self.device, non_blocking=True)
+        coords = batch["label_coords"].to(self.device, non_blocking=True)
+        a, p, rc = kvsall_rows(q, qt)
+        lab_off, lab_col = fused.csr_from_coords(coords, len(q))
+        return a, p, rc, lab_off, lab_col
+
+    def step(self, batch_index: int, batch: dict) -> ProcessBatchResult:
+        if self.stepper is None or len(batch["queries"]) != self.stepper.rows:
+            return super().step(batch_index, batch)
+        for f in self.pre_batch_hooks:
+            f(self)
+        self.stepper.set_inputs(*self.device_inputs(batch))
+        loss = self.stepper.step()
+        value = loss.item()          # the reference reads the loss back every batch too (train.py:747)
+        return ProcessBatchResult(value, self.stepper.rows, value)
 
     def _process_batch(self, batch_index, batch) -> ProcessBatchResult:
         queries = batch["queries"].to(self.device)

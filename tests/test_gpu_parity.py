@@ -321,3 +321,30 @@ def test_fused_backward_matches_float64(kb, shape):
                                          math_mode, shard, dw)
             close(dq, qd.grad.float(), rtol=rtol, what=f"dQ loss={loss} math={math_mode} {shape}")
             close(dw, wd.grad.float(), rtol=rtol, what=f"dTable loss={loss} math={math_mode} {shape}")
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_graph_captured_stepper_matches_autograd_flow(kb, use_graph):
+    """FusedAllEntityStepper (no autograd, CUDA graph) == TrainingJobKvsAll's fused autograd flow, fp32 tiles."""
+    g = kb.graph.synthetic_graph("toy", seed=3)
+    e, r, d, b = g["num_entities"], g["num_relations"], 32, 64
+    idx = [ko.kvsall_index(g["train"], "sp"), ko.kvsall_index(g["train"], "po")]
+    rng = np.random.default_rng(1)
+    batches = []
+    for _ in range(3):
+        ids = rng.choice(len(idx[0][0]) + len(idx[1][0]), b, replace=False)
+        q, c, qt = ko.kvsall_collate(ids.tolist(), idx)
+        batches.append({"queries": T(q), "label_coords": T(c), "query_type_indexes": T(qt)})
+    nnz_max = max(len(x["label_coords"]) for x in batches)
+    torch.manual_seed(0)
+    ref = kb.KgeModel("complex", e, r, d).cuda()
+    new = kb.KgeModel("complex", e, r, d).cuda()
+    new.load_state_dict(ref.state_dict())
+    jr = kb.TrainingJobKvsAll(ref, kb.optim.create("Adagrad", ref.parameters(), lr=0.2), kb.KgeLoss.create("bce"), e, r)
+    jn = kb.TrainingJobKvsAll(new, kb.optim.create("Adagrad", new.parameters(), lr=0.2), kb.KgeLoss.create("bce"), e, r)
+    jn.enable_graph_step(b, nnz_max, use_graph=use_graph)
+    for i, batch in enumerate(batches):
+        a, c = jr.step(i, batch), jn.step(i, batch)
+        assert c.avg_loss == pytest.approx(a.total_loss, rel=1e-5)
+        close(new.get_s_embedder().weight, ref.get_s_embedder().weight, rtol=1e-5, what=f"entity table step {i}")
+        close(new.get_p_embedder().weight, ref.get_p_embedder().weight, rtol=1e-5, what=f"relation table step {i}")
