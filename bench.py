@@ -295,7 +295,7 @@ def kernel_roofline(kb, stepper, math_mode, B, E):
 
     def fwd():
         L.call("kgeb_fused_fwd", st.loss_kind, math_mode, st.Q.data_ptr(), B, d, ent.data_ptr(), 0, E, E,
-               st.lab_off.data_ptr(), st.lab_col.data_ptr(), st.ls, st.offset, mp, st.rowstat.data_ptr(),
+               st.lab_off.data_ptr(), st.lab_col.data_ptr(), st.nnz_max, st.ls, st.offset, mp, st.rowstat.data_ptr(),
                st.ws.data_ptr(), st.ws.numel(), L.stream_ptr(ent))
 
     def bwd(dq, dt):

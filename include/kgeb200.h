@@ -113,7 +113,7 @@ int kgeb_score_all_bwd(int kind, const float* Q, int64_t B, int d, const float* 
  *   dQ[B,d] = G * table (overwritten with this shard's partial), dTable[e,:] += G^T Q.      */
 int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
-                   float label_smoothing, float offset, const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */,
+                   int64_t nnz /* size of lab_col (>= lab_off[B]; the tail may be padding) */, float label_smoothing, float offset, const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */,
                    float* rowstat /*[B,4]*/, void* workspace, int64_t workspace_bytes, void* stream);
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
@@ -139,9 +139,10 @@ int kgeb_rank_count(int kind, int math, const float* Q, int64_t nq, int d, const
                     const int64_t* test_col, int64_t* counts, void* stream);
 
 /* ---- a3/K3: deterministic sort-based segment scatter-add (autograd of nn.Embedding,
- * lookup_embedder.py:39-41,91-92).  rows[n,d] are summed per distinct idx in ascending original
- * position order and ADDED into dense[vocab,d].  workspace from kgeb_scatter_workspace_bytes(n). */
-int64_t kgeb_scatter_workspace_bytes(int64_t n);
+ * lookup_embedder.py:39-41,91-92).  rows[n,d] are summed per distinct idx in a fixed order (stable sort
+ * by id, then chunked ordered partial sums) and ADDED into dense[vocab,d].
+ * workspace from kgeb_scatter_workspace_bytes(n, d). */
+int64_t kgeb_scatter_workspace_bytes(int64_t n, int d);
 int kgeb_scatter_add_rows(const void* idx, int idx64, const float* rows, int64_t n, int d, float* dense,
                           int64_t vocab, void* workspace, int64_t workspace_bytes, void* stream);
 /* sparse form (lookup_embedder.yaml sparse: True): returns distinct ids (ascending) + summed rows */

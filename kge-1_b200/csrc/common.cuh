@@ -49,13 +49,11 @@ __device__ __forceinline__ float warp_max(float v) {
 
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
-// softplus(x) = max(x,0) + log1p(exp(-|x|)) ; sigmoid via the same exponential
-__device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x))); }
-__device__ __forceinline__ float sigmoidf(float x) {
-  float e = __expf(-fabsf(x));
-  float r = 1.f / (1.f + e);
-  return x >= 0.f ? r : e * r;
-}
+// Branch-free transcendental forms (MUFU ex2 / lg2 / rcp; ~1e-6 relative error) so that the compiler can keep
+// many independent element chains in flight in the tile epilogues:
+//   softplus(x) = max(x,0) + log(1 + exp(-|x|)) ;  sigmoid(x) = 1 / (1 + exp(-x))  (exp overflow -> 1/inf = 0)
+__device__ __forceinline__ float softplusf(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 constexpr int kNumSMs = 148;  // B200
 

@@ -313,48 +313,56 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact fp32 sparse label part and partial reduction
+// exact fp32 sparse label part (entry-parallel: hot rows / hot entities cost no more than cold ones)
 // ---------------------------------------------------------------------------------------------
-// dQ[q,:] = sum_chunks partial[c][q,:] - w_q * sum_{e in labels(q) of this shard} table[e - e_lo,:]
-__global__ void reduce_dq_labels_kernel(const float* __restrict__ partial, int64_t chunks, int64_t B, int d,
-                                        const float* __restrict__ table, int64_t e_lo, int64_t n_ent,
-                                        const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
-                                        const float* __restrict__ tscale, const float* __restrict__ row_scale,
-                                        float inv_batch, float* __restrict__ dQ) {
-  const int64_t q = blockIdx.x;
-  const float w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+__global__ void reduce_dq_partials_kernel(const float* __restrict__ partial, int64_t chunks, int64_t numel,
+                                          float* __restrict__ dQ) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int64_t k = 0; k < chunks; ++k) s += partial[(k * B + q) * d + c];
-    float l = 0.f;
-    for (int64_t i = lab_off[q]; i < lab_off[q + 1]; ++i) {
-      const int64_t e = lab_col[i] - e_lo;
-      if (e >= 0 && e < n_ent) l += __ldg(table + e * d + c);
-    }
-    dQ[q * d + c] = s - w * l;
+    for (int64_t k = 0; k < chunks; ++k) s += partial[k * numel + i];  // fixed order
+    dQ[i] = s;
   }
 }
 
-// rows[i,:] = -w_q * Q[q,:] and ent[i] = local entity id for label entry i (entries outside the shard get weight 0
-// and entity 0 so that the scatter stays in range)
-__global__ void label_rows_kernel(const float* __restrict__ Q, int64_t B, int d, int64_t e_lo, int64_t n_ent,
-                                  const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
-                                  const float* __restrict__ tscale, const float* __restrict__ row_scale, float inv_batch,
-                                  int64_t nnz, float* __restrict__ rows, int64_t* __restrict__ ent) {
-  const int64_t q = blockIdx.x;
-  if (q == B) {  // extra block: entries [lab_off[B], nnz) are padding of a fixed-size label buffer -> zero rows
-    for (int64_t i = lab_off[B]; i < nnz; ++i) {
-      for (int c = threadIdx.x; c < d; c += blockDim.x) rows[i * d + c] = 0.f;
-      if (threadIdx.x == 0) ent[i] = 0;
+// one warp per label entry i (entries [lab_off[B], nnz) are padding of a fixed-size label buffer):
+//   rows_dq[i,:] = -w_q * table[e,:]   (scattered into dQ[q,:] ; keys erow[] are ascending)
+//   rows_dt[i,:] = -w_q * Q[q,:]       (scattered into dTable[e,:] ; keys ent[])
+// with w_q = tscale[q] * inv_batch * row_scale[q]; entries outside this shard get zero rows.
+__global__ void __launch_bounds__(256)
+label_entry_rows_kernel(const float* __restrict__ Q, const float* __restrict__ table, int64_t B, int d, int64_t e_lo,
+                        int64_t n_ent, const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
+                        const float* __restrict__ tscale, const float* __restrict__ row_scale, float inv_batch, int64_t nnz,
+                        float* __restrict__ rows_dq, float* __restrict__ rows_dt, int64_t* __restrict__ ent,
+                        int64_t* __restrict__ erow) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= nnz) return;
+  int64_t q = -1;
+  if (lane == 0 && i < lab_off[B]) {  // row of entry i: last q with lab_off[q] <= i
+    int64_t lo = 0, hi = B;
+    while (lo < hi) {
+      int64_t mid = (lo + hi + 1) >> 1;
+      if (lab_off[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    return;
+    q = lo;
   }
-  const float w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
-  for (int64_t i = lab_off[q]; i < lab_off[q + 1]; ++i) {
-    const int64_t e = lab_col[i] - e_lo;
-    const bool in = (e >= 0 && e < n_ent);
-    for (int c = threadIdx.x; c < d; c += blockDim.x) rows[i * d + c] = in ? -w * Q[q * d + c] : 0.f;
-    if (threadIdx.x == 0) ent[i] = in ? e : 0;
+  q = __shfl_sync(0xffffffffu, q, 0);
+  int64_t e = 0;
+  float w = 0.f;
+  if (q >= 0) {
+    e = lab_col[i] - e_lo;
+    if (e >= 0 && e < n_ent) w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
+    else e = 0;
+  }
+  const int64_t qq = q < 0 ? 0 : q;
+  for (int c = lane; c < d; c += 32) {
+    if (rows_dq) rows_dq[i * d + c] = -w * __ldg(table + e * d + c);
+    if (rows_dt) rows_dt[i * d + c] = -w * Q[qq * d + c];
+  }
+  if (lane == 0) {
+    ent[i] = e;
+    erow[i] = qq;
   }
 }
 
@@ -426,10 +434,19 @@ int tc_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
   return KGEB_OK;
 }
 
+}  // namespace kgeb
+
+extern "C" int scatter_add_rows_presorted(const int64_t* keys, const float* rows, int64_t n, int d, float* dense,
+                                          int64_t vocab, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+
+namespace kgeb {
+
+static int64_t a256(int64_t x) { return (x + 255) / 256 * 256; }
+
 int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz) {
-  int64_t partial = (int64_t)kNumSMs * B * d * 4;
-  int64_t rows = nnz * (int64_t)d * 4 + nnz * 8 + 512;
-  return partial + rows + kgeb_scatter_workspace_bytes(nnz) + 2048;
+  if (nnz < 1) nnz = 1;
+  return a256((int64_t)kNumSMs * B * d * 4) + 2 * a256(nnz * (int64_t)d * 4) + 2 * a256(nnz * 8) +
+         kgeb_scatter_workspace_bytes(nnz, d) + 2048;
 }
 
 // Qb / tableb: bf16 mirrors of Q [B,d] and of the table shard [n_ent,d]
@@ -443,18 +460,24 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
   KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(Qb) | reinterpret_cast<uintptr_t>(tableb)) & 15) == 0,
                "tensor tiles need 16-byte aligned operands");
   KGEB_REQUIRE(ws_bytes >= tc_bwd_workspace_bytes(B, d, n_ent, nnz), "fused_bwd(bf16): workspace too small");
+  const int64_t nz = nnz < 1 ? 1 : nnz;
   char* wp = reinterpret_cast<char*>(ws);
-  float* partial = reinterpret_cast<float*>(wp);
-  wp += (((int64_t)kNumSMs * B * d * 4 + 255) / 256) * 256;
-  float* lab_rows = reinterpret_cast<float*>(wp);
-  wp += ((nnz * (int64_t)d * 4 + 255) / 256) * 256;
-  int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);
-  wp += ((nnz * 8 + 255) / 256) * 256;
+  float* partial = reinterpret_cast<float*>(wp);      wp += a256((int64_t)kNumSMs * B * d * 4);
+  float* rows_dq = reinterpret_cast<float*>(wp);      wp += a256(nz * (int64_t)d * 4);
+  float* rows_dt = reinterpret_cast<float*>(wp);      wp += a256(nz * (int64_t)d * 4);
+  int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
+  int64_t* lab_row = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
   void* scatter_ws = wp;
   const int64_t scatter_bytes = ws_bytes - (wp - reinterpret_cast<char*>(ws));
   int rc;
   CUtensorMap m_res, m_str;
   if (n_ent > 0 && B > 0) {
+    if (nnz > 0) {
+      label_entry_rows_kernel<<<(unsigned)((nnz + 7) / 8), 256, 0, st>>>(
+          Q, table, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale, inv_batch, nnz, dQ ? rows_dq : nullptr,
+          dTable ? rows_dt : nullptr, lab_ent, lab_row);
+      KGEB_LAUNCH_CHECK("label_entry_rows");
+    }
     if (dQ) {
       Plan pl = make_plan(true, true, B, d, n_ent);
       if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
@@ -466,9 +489,12 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
       tc_bwd_kernel<true, true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);
       KGEB_LAUNCH_CHECK("tc_bwd_kernel<dQ>");
-      reduce_dq_labels_kernel<<<(unsigned)B, 128, 0, st>>>(partial, pl.p.chunks, B, d, table, e_lo, n_ent, lab_off,
-                                                          lab_col, tscale, row_scale, inv_batch, dQ);
-      KGEB_LAUNCH_CHECK("reduce_dq_labels");
+      const int64_t numel = B * (int64_t)d;
+      reduce_dq_partials_kernel<<<(unsigned)((numel + 255) / 256 > 4096 ? 4096 : (numel + 255) / 256), 256, 0, st>>>(
+          partial, pl.p.chunks, numel, dQ);
+      KGEB_LAUNCH_CHECK("reduce_dq_partials");
+      if (nnz > 0 && (rc = scatter_add_rows_presorted(lab_row, rows_dq, nnz, d, dQ, B, scatter_ws, scatter_bytes, st)))
+        return rc;
     }
     if (dTable) {
       Plan pl = make_plan(false, true, B, d, n_ent);
@@ -481,13 +507,8 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
       tc_bwd_kernel<false, true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);
       KGEB_LAUNCH_CHECK("tc_bwd_kernel<dTable>");
-      if (nnz > 0) {
-        label_rows_kernel<<<(unsigned)B + 1, 128, 0, st>>>(Q, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale,
-                                                           inv_batch, nnz, lab_rows, lab_ent);
-        KGEB_LAUNCH_CHECK("label_rows");
-        if ((rc = kgeb_scatter_add_rows(lab_ent, 1, lab_rows, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st)))
-          return rc;
-      }
+      if (nnz > 0 && (rc = kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st)))
+        return rc;
     }
   } else if (dQ && B > 0) {
     cudaMemsetAsync(dQ, 0, (size_t)B * d * 4, st);

@@ -468,26 +468,48 @@ __global__ void stats_finalize_kernel(int loss, const float* __restrict__ partia
   o[0] = s0; o[1] = s1; o[2] = s2; o[3] = label_dot[r];
 }
 
-// exact-fp32 sum over the label entries of each row that fall into this shard: warp per row
-__global__ void label_dot_kernel(const float* __restrict__ Q, int64_t B, int d, const float* __restrict__ table,
-                                 int64_t e_lo, int64_t n_ent, const int64_t* __restrict__ lab_off,
-                                 const int64_t* __restrict__ lab_col, float add_per_entry, float* __restrict__ out) {
+// exact-fp32 x_ij at the label entries of this shard, one warp per entry (+ add_per_entry), then ordered row sums
+__global__ void __launch_bounds__(256)
+label_entry_dot_kernel(const float* __restrict__ Q, int64_t B, int d, const float* __restrict__ table, int64_t e_lo,
+                       int64_t n_ent, const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
+                       float add_per_entry, int64_t nnz, float* __restrict__ entry_dot) {
   const int lane = threadIdx.x & 31;
-  int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= B) return;
-  float total = 0.f;
-  if (lab_off) {
-    const float* q = Q + r * d;
-    for (int64_t i = lab_off[r]; i < lab_off[r + 1]; ++i) {
-      const int64_t c = lab_col[i] - e_lo;
-      if (c < 0 || c >= n_ent) continue;
-      const float* e = table + c * d;
+  const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= nnz) return;
+  int64_t q = -1;
+  if (lane == 0 && i < lab_off[B]) {
+    int64_t lo = 0, hi = B;
+    while (lo < hi) {
+      int64_t mid = (lo + hi + 1) >> 1;
+      if (lab_off[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    q = lo;
+  }
+  q = __shfl_sync(0xffffffffu, q, 0);
+  float out = 0.f;
+  if (q >= 0) {
+    const int64_t c = lab_col[i] - e_lo;
+    if (c >= 0 && c < n_ent) {
+      const float* qr = Q + q * d;
+      const float* er = table + c * d;
       float acc = 0.f;
-      for (int k = lane; k < d; k += 32) acc = fmaf(q[k], __ldg(e + k), acc);
-      total += warp_sum(acc) + add_per_entry;
+      for (int k = lane; k < d; k += 32) acc = fmaf(qr[k], __ldg(er + k), acc);
+      out = warp_sum(acc) + add_per_entry;
     }
   }
-  if (lane == 0) out[r] = total;
+  if (lane == 0) entry_dot[i] = out;
+}
+__global__ void __launch_bounds__(256)
+label_row_sum_kernel(const float* __restrict__ entry_dot, const int64_t* __restrict__ lab_off, int64_t B,
+                     float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= B) return;
+  float acc = 0.f;
+  if (lab_off)
+    for (int64_t i = lab_off[r] + lane; i < lab_off[r + 1]; i += 32) acc += entry_dot[i];
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc;
 }
 
 }  // namespace tc
@@ -503,19 +525,23 @@ int tc_score_all(const float* Q, int64_t B, int d, const float* table, int64_t m
   return tc::launch<tc::MODE_SCORES>(pl, mq, mw, st);
 }
 
-int64_t tc_stats_partial_bytes(int64_t B) { return (int64_t)kNumSMs * B * 4 * (int64_t)sizeof(float) + B * 4 + 256; }
+int64_t tc_stats_partial_bytes(int64_t B, int64_t nnz) {
+  return (int64_t)kNumSMs * B * 4 * (int64_t)sizeof(float) + B * 4 + (nnz < 1 ? 1 : nnz) * 4 + 512;
+}
 
 // math: KGEB_MATH_TF32 reads the fp32 Q / table in place; KGEB_MATH_BF16 reads the bf16 mirrors Qb / tableb
 int tc_fused_fwd(int loss, int math, const float* Q, const void* Qb, int64_t B, int d, const float* table,
                  const void* tableb, int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col,
-                 float ls_keep, float ls_add, float offset, float* rowstat, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                 int64_t nnz, float ls_keep, float ls_add, float offset, float* rowstat, void* ws, int64_t ws_bytes,
+                 cudaStream_t st) {
   const bool bf16 = (math == KGEB_MATH_BF16);
   int rc = tc::check_operands(bf16 ? Qb : (const void*)Q, bf16 ? tableb : (const void*)table, d, bf16);
   if (rc) return rc;
-  KGEB_REQUIRE(ws_bytes >= tc_stats_partial_bytes(B), "fused_fwd(tensor tiles): workspace too small");
+  KGEB_REQUIRE(ws_bytes >= tc_stats_partial_bytes(B, nnz), "fused_fwd(tensor tiles): workspace too small");
   float* partial = reinterpret_cast<float*>(ws);
   tc::Plan pl = tc::make_plan(B, d, n_ent, e_lo, bf16);
-  float* label_dot = partial + pl.p.chunks * B * 4;
+  float* label_dot = partial + (int64_t)kNumSMs * B * 4;
+  float* entry_dot = label_dot + B;
   pl.p.loss = loss; pl.p.offset = offset; pl.p.partial = partial;
   if (n_ent > 0) {
     CUtensorMap mq, mw;
@@ -524,9 +550,13 @@ int tc_fused_fwd(int loss, int math, const float* Q, const void* Qb, int64_t B, 
       return rc;
     if ((rc = tc::launch<tc::MODE_STATS>(pl, mq, mw, st))) return rc;
   }
-  tc::label_dot_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(Q, B, d, table, e_lo, n_ent, lab_off, lab_col,
-                                                                loss == KGEB_LOSS_BCE ? offset : 0.f, label_dot);
-  KGEB_LAUNCH_CHECK("label_dot");
+  if (nnz > 0 && lab_off) {
+    tc::label_entry_dot_kernel<<<(unsigned)((nnz + 7) / 8), 256, 0, st>>>(
+        Q, B, d, table, e_lo, n_ent, lab_off, lab_col, loss == KGEB_LOSS_BCE ? offset : 0.f, nnz, entry_dot);
+    KGEB_LAUNCH_CHECK("label_entry_dot");
+  }
+  tc::label_row_sum_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(entry_dot, nnz > 0 ? lab_off : nullptr, B, label_dot);
+  KGEB_LAUNCH_CHECK("label_row_sum");
   tc::stats_finalize_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, partial, B, n_ent > 0 ? pl.p.chunks : 0,
                                                                          label_dot, rowstat);
   KGEB_LAUNCH_CHECK("stats_finalize");

@@ -13,12 +13,12 @@ constexpr int BM = 64, BN = 64, BK = 16, TT = 256;
 
 int tc_score_all(const float* Q, int64_t B, int d, const float* table, int64_t m, float* out, int64_t ld,
                  int64_t col_off, cudaStream_t st);  // tc_dot.cu
-int64_t tc_stats_partial_bytes(int64_t B);                       // tc_dot.cu
+int64_t tc_stats_partial_bytes(int64_t B, int64_t nnz);                       // tc_dot.cu
 int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz);  // tc_bwd.cu
 bool tc_bwd_supported(int math, int d);                                                    // tc_bwd.cu
 int tc_fused_fwd(int loss, int math, const float* Q, const void* Qb, int64_t B, int d, const float* table,
                  const void* tableb, int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col,
-                 float ls_keep, float ls_add, float offset, float* rowstat, void* ws, int64_t ws_bytes,
+                 int64_t nnz, float ls_keep, float ls_add, float offset, float* rowstat, void* ws, int64_t ws_bytes,
                  cudaStream_t st);  // tc_dot.cu
 int tc_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);  // tc_bwd.cu
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
@@ -756,7 +756,7 @@ static int64_t fused_ws_cuda_core(int64_t B, int d, int64_t num_shard_entities) 
 
 int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities, int64_t nnz) {
   int64_t a = fused_ws_cuda_core(B, d, num_shard_entities);
-  int64_t b = tc_stats_partial_bytes(B);
+  int64_t b = tc_stats_partial_bytes(B, nnz);
   int64_t c = tc_bwd_workspace_bytes(B, d, num_shard_entities, nnz);
   int64_t m = a > b ? a : b;
   m = m > c ? m : c;
@@ -789,7 +789,7 @@ static int check_fused(int loss, int d, float ls, const void* Q, const void* tab
 }
 
 int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
-                   int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
+                   int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                    float label_smoothing, float offset, const void* table_bf16, float* rowstat, void* workspace,
                    int64_t workspace_bytes, void* stream) {
   int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
@@ -798,7 +798,7 @@ int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const f
   const int64_t n_ent = e_hi - e_lo;
   if (B == 0) return KGEB_OK;
   cudaStream_t st = as_stream(stream);
-  KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, 0), "fused_fwd: workspace too small");
+  KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, nnz), "fused_fwd: workspace too small");
   LossParams lp{loss, 1.f - label_smoothing, label_smoothing > 0.f ? 1.f / (float)num_entities : 0.f, offset, 1.f};
   if (math == KGEB_MATH_TF32 || math == KGEB_MATH_BF16) {
     TailWs tail = carve_tail(workspace, workspace_bytes, B, d);
@@ -806,7 +806,7 @@ int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const f
       KGEB_REQUIRE(table_bf16, "fused_fwd(bf16): the bf16 mirror of the table is required (kgeb_to_bf16)");
       if ((rc = tc_to_bf16(Q, tail.qb, B * (int64_t)d, st))) return rc;
     }
-    return tc_fused_fwd(loss, math, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, lp.ls_keep,
+    return tc_fused_fwd(loss, math, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, lp.ls_keep,
                         lp.ls_add, offset, rowstat, workspace, tail.usable, st);
   }
   const int64_t ntc = (n_ent + BN - 1) / BN, ntr = (B + BM - 1) / BM;

@@ -12,6 +12,7 @@
 namespace kgeb {
 
 struct ScatterWs {
+  float* part;  // [ceil(n/32)][2][d] partial segment sums
   int64_t* keys_in;
   int64_t* keys_out;
   int32_t* pos_in;
@@ -32,15 +33,18 @@ static size_t cub_temp_bytes(int64_t n) {
   return a > b ? a : b;
 }
 
-static int64_t scatter_ws_bytes(int64_t n) {
+static size_t part_bytes(int64_t n, int d) { return align256((size_t)((n + 31) / 32) * 2 * (size_t)d * 4); }
+
+static int64_t scatter_ws_bytes(int64_t n, int d) {
   if (n < 1) n = 1;
-  return (int64_t)(2 * align256(n * 8) + 3 * align256((n + 1) * 4) + align256(cub_temp_bytes(n)) + 256);
+  return (int64_t)(2 * align256(n * 8) + 3 * align256((n + 1) * 4) + align256(cub_temp_bytes(n)) + part_bytes(n, d) + 512);
 }
 
-static bool carve(void* ws, int64_t bytes, int64_t n, ScatterWs& w) {
-  if (!ws || bytes < scatter_ws_bytes(n)) return false;
+static bool carve(void* ws, int64_t bytes, int64_t n, int d, ScatterWs& w) {
+  if (!ws || bytes < scatter_ws_bytes(n, d)) return false;
   char* p = reinterpret_cast<char*>(ws);
   p = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(p)));
+  w.part = reinterpret_cast<float*>(p); p += part_bytes(n, d);
   w.keys_in = reinterpret_cast<int64_t*>(p); p += align256(n * 8);
   w.keys_out = reinterpret_cast<int64_t*>(p); p += align256(n * 8);
   w.pos_in = reinterpret_cast<int32_t*>(p); p += align256((n + 1) * 4);
@@ -75,65 +79,140 @@ __global__ void seg_starts_kernel(const int64_t* __restrict__ keys, const int32_
   }
 }
 
-// one warp per segment; rows summed in ascending original position
+// Segment sums in two fixed-order phases (deterministic, no float atomics, no serial walk over hot keys):
+//  phase 1: one warp per chunk of CHUNK consecutive sorted positions walks its rows in order; runs that are whole
+//           segments are written out directly, the (at most two) runs that continue into a neighbouring chunk go
+//           to part[chunk][0] (run continuing from the previous chunk) / part[chunk][1] (run continuing into the next);
+//  phase 2: one warp per segment that spans several chunks adds its partials in chunk order.
+constexpr int CHUNK = 32;
+
+template <bool DENSE>
+__device__ __forceinline__ void seg_emit(float4 acc, int c0, int d, bool add, float* dst, bool vec) {
+  // dst points at column c0 of the destination row
+  if (vec && c0 + 3 < d) {
+    float4* p = reinterpret_cast<float4*>(dst);
+    if (add) { float4 o = *p; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    *p = acc;
+  } else {
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    for (int j = 0; j < 4 && c0 + j < d; ++j) dst[j] = add ? dst[j] + v[j] : v[j];
+  }
+}
+
 template <bool DENSE>
 __global__ void __launch_bounds__(256)
-segment_sum_kernel(const int64_t* __restrict__ keys, const int32_t* __restrict__ pos,
+segment_sum_phase1(const int64_t* __restrict__ keys, const int32_t* __restrict__ pos,
                    const int32_t* __restrict__ seg_id, const int32_t* __restrict__ seg_start, int64_t n, int d,
                    const float* __restrict__ rows, float* __restrict__ dense, int64_t vocab,
-                   int64_t* __restrict__ uniq_ids, float* __restrict__ uniq_rows) {
+                   int64_t* __restrict__ uniq_ids, float* __restrict__ uniq_rows, float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
-  const int nseg = seg_id[n - 1];
-  int64_t seg = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  for (; seg < nseg; seg += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-    const int b = seg_start[seg], e = seg_start[seg + 1];
-    const int64_t key = keys[b];
-    if (DENSE && (key < 0 || key >= vocab)) continue;
-    for (int c0 = lane * 4; c0 < d; c0 += 128) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const bool full = (c0 + 3 < d) && ((d & 3) == 0);
-      int i = b;
-      for (; i < e; ++i) {
-        const float* r = rows + (int64_t)pos[i] * d + c0;
-        if (full) {
-          float4 v = __ldg(reinterpret_cast<const float4*>(r));
-          a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+  const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
+  const bool vec = (d & 3) == 0;
+  for (int64_t ch = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks;
+       ch += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int cb = (int)(ch * CHUNK), ce = (int)min((int64_t)cb + CHUNK, n);
+    int i = cb;
+    while (i < ce) {
+      const int sid = seg_id[i];                 // 1-based
+      const int sb = seg_start[sid - 1], se = seg_start[sid];
+      const int re = min(se, ce);
+      const int64_t key = keys[i];
+      const bool complete = (i == sb) && (re == se);
+      const bool ok = !DENSE || (key >= 0 && key < vocab);
+      for (int c0 = lane * 4; c0 < d; c0 += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = i; r < re; ++r) {
+          const float* src = rows + (int64_t)pos[r] * d + c0;
+          if (vec) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(src));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          } else {
+            acc.x += src[0];
+            if (c0 + 1 < d) acc.y += src[1];
+            if (c0 + 2 < d) acc.z += src[2];
+            if (c0 + 3 < d) acc.w += src[3];
+          }
+        }
+        if (complete) {
+          if (ok) seg_emit<DENSE>(acc, c0, d, DENSE, DENSE ? dense + key * d + c0 : uniq_rows + (int64_t)(sid - 1) * d + c0, vec);
         } else {
-          a0 += r[0];
-          if (c0 + 1 < d) a1 += r[1];
-          if (c0 + 2 < d) a2 += r[2];
-          if (c0 + 3 < d) a3 += r[3];
+          const int slot = (i != sb) ? 0 : 1;    // continuation from the previous chunk | run continuing into the next
+          seg_emit<false>(acc, c0, d, false, part + ((ch * 2 + slot) * (int64_t)d) + c0, vec);
         }
       }
-      float* dst = DENSE ? dense + key * d + c0 : uniq_rows + seg * (int64_t)d + c0;
-      if (DENSE) {
-        dst[0] += a0;
-        if (c0 + 1 < d) dst[1] += a1;
-        if (c0 + 2 < d) dst[2] += a2;
-        if (c0 + 3 < d) dst[3] += a3;
-      } else {
-        dst[0] = a0;
-        if (c0 + 1 < d) dst[1] = a1;
-        if (c0 + 2 < d) dst[2] = a2;
-        if (c0 + 3 < d) dst[3] = a3;
+      if (!DENSE && complete && lane == 0) uniq_ids[sid - 1] = key;
+      i = re;
+    }
+  }
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(256)
+segment_sum_phase2(const int64_t* __restrict__ keys, const int32_t* __restrict__ seg_id,
+                   const int32_t* __restrict__ seg_start, int64_t n, int d, float* __restrict__ dense, int64_t vocab,
+                   int64_t* __restrict__ uniq_ids, float* __restrict__ uniq_rows, const float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int nseg = seg_id[n - 1];
+  const bool vec = (d & 3) == 0;
+  for (int64_t seg = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); seg < nseg;
+       seg += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const int sb = seg_start[seg], se = seg_start[seg + 1];
+    const int64_t c0ch = sb / CHUNK, c1ch = (se - 1) / CHUNK;
+    if (c0ch == c1ch) continue;  // finished in phase 1
+    const int64_t key = keys[sb];
+    if (DENSE && (key < 0 || key >= vocab)) continue;
+    for (int c0 = lane * 4; c0 < d; c0 += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t ch = c0ch; ch <= c1ch; ++ch) {
+        const int slot = (ch == c0ch) ? 1 : 0;
+        const float* src = part + ((ch * 2 + slot) * (int64_t)d) + c0;
+        if (vec && c0 + 3 < d) {
+          float4 v = *reinterpret_cast<const float4*>(src);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        } else {
+          acc.x += src[0];
+          if (c0 + 1 < d) acc.y += src[1];
+          if (c0 + 2 < d) acc.z += src[2];
+          if (c0 + 3 < d) acc.w += src[3];
+        }
       }
+      seg_emit<DENSE>(acc, c0, d, DENSE, DENSE ? dense + key * d + c0 : uniq_rows + seg * (int64_t)d + c0, vec);
     }
     if (!DENSE && lane == 0) uniq_ids[seg] = key;
   }
 }
 
+template <bool DENSE>
+static int segment_sums(ScatterWs& w, int64_t n, int d, const float* rows, float* dense, int64_t vocab,
+                        int64_t* uniq_ids, float* uniq_rows, cudaStream_t st) {
+  const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
+  int64_t b1 = (nchunks + 7) / 8, b2 = (n + 7) / 8;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  segment_sum_phase1<DENSE><<<(int)(b1 > cap ? cap : b1), 256, 0, st>>>(w.keys_out, w.pos_out, w.seg_id, w.seg_start, n,
+                                                                       d, rows, dense, vocab, uniq_ids, uniq_rows, w.part);
+  segment_sum_phase2<DENSE><<<(int)(b2 > cap ? cap : b2), 256, 0, st>>>(w.keys_out, w.seg_id, w.seg_start, n, d, dense,
+                                                                       vocab, uniq_ids, uniq_rows, w.part);
+  KGEB_LAUNCH_CHECK("segment_sum");
+  return KGEB_OK;
+}
+
 static int sort_and_segment(const void* idx, int idx64, int64_t n, int64_t vocab, ScatterWs& w, int64_t* num_uniq,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool presorted = false) {
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  iota_keys_kernel<<<blocks, 256, 0, st>>>(idx, idx64, n, w.keys_in, w.pos_in);
-  int end_bit = 64;
-  if (vocab > 0) {
-    end_bit = 1;
-    while (end_bit < 63 && ((int64_t)1 << end_bit) < vocab) ++end_bit;
+  cudaError_t e;
+  if (presorted) {  // keys already ascending: positions are the identity
+    iota_keys_kernel<<<blocks, 256, 0, st>>>(idx, idx64, n, w.keys_out, w.pos_out);
+  } else {
+    iota_keys_kernel<<<blocks, 256, 0, st>>>(idx, idx64, n, w.keys_in, w.pos_in);
+    int end_bit = 64;
+    if (vocab > 0) {
+      end_bit = 1;
+      while (end_bit < 63 && ((int64_t)1 << end_bit) < vocab) ++end_bit;
+    }
+    e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, w.cub_bytes, w.keys_in, w.keys_out, w.pos_in, w.pos_out, (int)n, 0,
+                                        end_bit, st);
+    if (e != cudaSuccess) return cuda_status(e, "radix sort");
   }
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, w.cub_bytes, w.keys_in, w.keys_out, w.pos_in, w.pos_out,
-                                                  (int)n, 0, end_bit, st);
-  if (e != cudaSuccess) return cuda_status(e, "radix sort");
   head_flags_kernel<<<blocks, 256, 0, st>>>(w.keys_out, n, w.seg_id);
   e = cub::DeviceScan::InclusiveSum(w.cub_tmp, w.cub_bytes, w.seg_id, w.seg_id, (int)n, st);
   if (e != cudaSuccess) return cuda_status(e, "segment scan");
@@ -235,7 +314,7 @@ using namespace kgeb;
 
 extern "C" {
 
-int64_t kgeb_scatter_workspace_bytes(int64_t n) { return scatter_ws_bytes(n); }
+int64_t kgeb_scatter_workspace_bytes(int64_t n, int d) { return scatter_ws_bytes(n, d); }
 
 int kgeb_scatter_add_rows(const void* idx, int idx64, const float* rows, int64_t n, int d, float* dense,
                           int64_t vocab, void* workspace, int64_t workspace_bytes, void* stream) {
@@ -243,16 +322,22 @@ int kgeb_scatter_add_rows(const void* idx, int idx64, const float* rows, int64_t
   KGEB_REQUIRE(n < ((int64_t)1 << 31), "scatter_add_rows: n too large");
   if (n == 0) return KGEB_OK;
   ScatterWs w;
-  KGEB_REQUIRE(carve(workspace, workspace_bytes, n, w), "scatter_add_rows: workspace too small");
+  KGEB_REQUIRE(carve(workspace, workspace_bytes, n, d, w), "scatter_add_rows: workspace too small");
   cudaStream_t st = as_stream(stream);
   int rc = sort_and_segment(idx, idx64, n, vocab, w, nullptr, st);
   if (rc) return rc;
-  int64_t blocks = (n + 7) / 8;
-  int grid = (int)(blocks > (int64_t)kNumSMs * 16 ? (int64_t)kNumSMs * 16 : blocks);
-  segment_sum_kernel<true><<<grid, 256, 0, st>>>(w.keys_out, w.pos_out, w.seg_id, w.seg_start, n, d, rows, dense, vocab,
-                                                 nullptr, nullptr);
-  KGEB_LAUNCH_CHECK("segment_sum(dense)");
-  return KGEB_OK;
+  return segment_sums<true>(w, n, d, rows, dense, vocab, nullptr, nullptr, st);
+}
+
+// internal: keys already ascending (e.g. label entries grouped by row)
+int scatter_add_rows_presorted(const int64_t* keys, const float* rows, int64_t n, int d, float* dense, int64_t vocab,
+                               void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (n == 0) return KGEB_OK;
+  kgeb::ScatterWs w;
+  KGEB_REQUIRE(kgeb::carve(workspace, workspace_bytes, n, d, w), "scatter_add_rows(presorted): workspace too small");
+  int rc = kgeb::sort_and_segment(keys, 1, n, vocab, w, nullptr, st, true);
+  if (rc) return rc;
+  return kgeb::segment_sums<true>(w, n, d, rows, dense, vocab, nullptr, nullptr, st);
 }
 
 int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int64_t n, int d, int64_t* uniq_ids,
@@ -266,15 +351,10 @@ int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int6
     return KGEB_OK;
   }
   ScatterWs w;
-  KGEB_REQUIRE(carve(workspace, workspace_bytes, n, w), "segment_reduce_rows: workspace too small");
+  KGEB_REQUIRE(carve(workspace, workspace_bytes, n, d, w), "segment_reduce_rows: workspace too small");
   int rc = sort_and_segment(idx, idx64, n, 0, w, num_uniq, st);
   if (rc) return rc;
-  int64_t blocks = (n + 7) / 8;
-  int grid = (int)(blocks > (int64_t)kNumSMs * 16 ? (int64_t)kNumSMs * 16 : blocks);
-  segment_sum_kernel<false><<<grid, 256, 0, st>>>(w.keys_out, w.pos_out, w.seg_id, w.seg_start, n, d, rows, nullptr, 0,
-                                                  uniq_ids, uniq_rows);
-  KGEB_LAUNCH_CHECK("segment_sum(sparse)");
-  return KGEB_OK;
+  return segment_sums<false>(w, n, d, rows, nullptr, 0, uniq_ids, uniq_rows, st);
 }
 
 int kgeb_adagrad_dense(float* W, float* state, const float* grad, int64_t numel, float clr, float eps,

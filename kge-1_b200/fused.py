@@ -75,7 +75,7 @@ def fused_rowstats(q, table, lab_off, lab_col, loss, label_smoothing, offset, ma
     ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent, lab_col.numel()))
     lib.call("kgeb_fused_fwd", loss, math, lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo,
              shard.e_hi, shard.num_entities, lib.i64(lab_off, "label offsets"), lib.i64(lab_col, "label columns"),
-             float(label_smoothing), float(offset), _mirror_ptr(table, math, b, d), rowstat.data_ptr(), ws.data_ptr(),
+             lab_col.numel(), float(label_smoothing), float(offset), _mirror_ptr(table, math, b, d), rowstat.data_ptr(), ws.data_ptr(),
              ws.numel(), lib.stream_ptr(q))
     return rowstat
 

@@ -75,7 +75,7 @@ def scatter_add_rows_(dense: torch.Tensor, indexes: torch.Tensor, rows: torch.Te
         return dense
     indexes = indexes.reshape(-1).contiguous()
     rows = rows.reshape(n, -1).contiguous()
-    nbytes = lib.load().kgeb_scatter_workspace_bytes(n)
+    nbytes = lib.load().kgeb_scatter_workspace_bytes(n, rows.shape[1])
     ws = _workspace(dense.device, nbytes)
     ip, i64 = lib.idx(indexes)
     lib.call("kgeb_scatter_add_rows", ip, i64, lib.f32(rows, "rows"), n, rows.shape[1], lib.f32(dense, "dense"),
@@ -92,7 +92,7 @@ def segment_reduce_rows(indexes: torch.Tensor, rows: torch.Tensor):
     ids = torch.empty(max(n, 1), dtype=torch.int64, device=rows.device)
     out = torch.empty(max(n, 1), d, dtype=torch.float32, device=rows.device)
     cnt = torch.zeros(1, dtype=torch.int64, device=rows.device)
-    ws = _workspace(rows.device, lib.load().kgeb_scatter_workspace_bytes(n))
+    ws = _workspace(rows.device, lib.load().kgeb_scatter_workspace_bytes(n, d))
     ip, i64 = lib.idx(indexes)
     lib.call("kgeb_segment_reduce_rows", ip, i64, lib.f32(rows, "rows"), n, d, ids.data_ptr(), out.data_ptr(),
              cnt.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream_ptr(rows))

@@ -57,7 +57,8 @@ class FusedAllEntityStepper:
         self.shard = fused.Shard.full(self.E)
         self.ws = torch.empty(lib.load().kgeb_fused_workspace_bytes(rows, self.d, self.E, max(nnz_max, 1)),
                               dtype=torch.uint8, device=dev)
-        self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(rows), dtype=torch.uint8, device=dev)
+        self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(rows, max(self.d, self.dr)), dtype=torch.uint8,
+                               device=dev)
         self.mirror = None
         if math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256:
             self.mirror = torch.empty(self.E, self.d, dtype=torch.bfloat16, device=dev)
@@ -79,7 +80,7 @@ class FusedAllEntityStepper:
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st); n += 1
         lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
-                 self.E, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.ls, self.offset, mp,
+                 self.E, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset, mp,
                  self.rowstat.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 4
         per_row, lse = fused.rows_loss(self.rowstat, self.lab_off, self.loss_kind, self.ls, self.E)
         torch.sum(per_row, dim=0, out=self.loss); self.loss.div_(self.batch_size); n += 6
