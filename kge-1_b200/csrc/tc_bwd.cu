@@ -29,7 +29,10 @@ constexpr int STR_ROWS = 64;                     // UMMA N of MMA1, K of MMA2
 constexpr int RES_SLAB = RES_ROWS * 128;         // 16 KiB: 128 rows x 128 B
 constexpr int STR_SLAB = STR_ROWS * 128;         // 8 KiB:  64 rows x 128 B
 constexpr int MAX_STR = 8;                       // streamed-tile ring depth
-constexpr int NUM_THREADS = 256;
+constexpr int EPQ = 4;                            // epilogue warps per TMEM lane quadrant (latency hiding)
+constexpr int NUM_EPI_THREADS = 4 * EPQ * 32;     // 512
+constexpr int NUM_THREADS = 128 + NUM_EPI_THREADS;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-19: epilogue
+constexpr int COLS_PER_WARP = STR_ROWS / EPQ;    // 16 S-columns per epilogue warp
 constexpr int SMEM_BUDGET = 227 * 1024;
 
 struct Params {
@@ -45,7 +48,7 @@ struct Params {
   float* out;              // RES_IS_Q: partial [chunks][B][d] ; else dTable [n_res][d] (+=)
 };
 
-template <bool RES_IS_Q, bool BF16>
+template <bool RES_IS_Q, bool BF16, int LOSS, bool HAS_RS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_str, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -87,12 +90,12 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
     mbar_init(res_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 128);
-      mbar_init(&g_full[b], 128);
+      mbar_init(&s_empty[b], NUM_EPI_THREADS);
+      mbar_init(&g_full[b], NUM_EPI_THREADS);
       mbar_init(&g_empty[b], 1);
     }
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 128);
+    mbar_init(o_empty, NUM_EPI_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -200,10 +203,12 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue ================================
+    // ================================ epilogue (16 warps: lane quadrant x column part) ================================
     const int ew = warp - 4;
-    const int trow = ew * 32 + lane;                       // resident row (TMEM lane) of this thread
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(ew * 32) << 16);
+    const int quad = ew & 3;                               // == warp % 4 : TMEM lane quadrant this warp may access
+    const int part = ew >> 2;                              // which 16 S-columns of the 64
+    const int trow = quad * 32 + lane;                     // resident row (TMEM lane) of this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     uint32_t sph[2] = {0, 0}, gph[2] = {0, 0}, ophase = 0;
     int sbuf = 0, gbuf = 0;
     for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -212,63 +217,55 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       const int64_t res_row = rb * RES_ROWS + trow;
       float my_lse = 0.f, my_rs = 0.f;
       if (RES_IS_Q && res_row < p.B) {
-        my_rs = p.inv_batch * (p.row_scale ? p.row_scale[res_row] : 1.f);
-        if (p.loss == KGEB_LOSS_KL) my_lse = p.lse[res_row];
+        my_rs = p.inv_batch * (HAS_RS ? p.row_scale[res_row] : 1.f);
+        if (LOSS == KGEB_LOSS_KL) my_lse = p.lse[res_row];
       }
       for (int64_t u = u0; u < u1; ++u) {
         mbar_wait(&s_full[sbuf], sph[sbuf]);
         sph[sbuf] ^= 1;
         tc_fence_after();
-        float v[2][32];
-        tmem_ld32(lane_addr + S_COL + (uint32_t)(sbuf * STR_ROWS), v[0]);
-        tmem_ld32(lane_addr + S_COL + (uint32_t)(sbuf * STR_ROWS + 32), v[1]);
+        float v[COLS_PER_WARP];
+        tmem_ld16(lane_addr + S_COL + (uint32_t)(sbuf * STR_ROWS + part * COLS_PER_WARP), v);
         tc_fence_before();
-        mbar_arrive(&s_empty[sbuf]);  // S buffer is in registers: MMA1 of the tile after next may overwrite it
+        mbar_arrive(&s_empty[sbuf]);  // S values are in registers: MMA1 of the tile after next may overwrite them
         sbuf ^= 1;
+        // Rows / columns beyond the matrices were zero-filled by TMA, so whatever finite G they get multiplies
+        // zeros in MMA2; only the parameter loads are clamped.
+        const int64_t qbase = u * STR_ROWS + part * COLS_PER_WARP;
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf)
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float lse = my_lse, rs = my_rs;
-            if (!RES_IS_Q) {  // columns are query rows: per-column parameters (warp-uniform loads)
-              const int64_t q = u * STR_ROWS + hlf * 32 + c;
-              rs = 0.f; lse = 0.f;
-              if (q < p.B) {
-                rs = p.inv_batch * (p.row_scale ? __ldg(p.row_scale + q) : 1.f);
-                if (p.loss == KGEB_LOSS_KL) lse = __ldg(p.lse + q);
-              }
-            }
-            const float x = v[hlf][c];
-            float gval;
-            if (p.loss == KGEB_LOSS_KL) gval = __expf(x - lse);
-            else gval = sigmoidf(x + p.offset) - p.ls_add;
-            v[hlf][c] = rs * gval;
+        for (int c = 0; c < COLS_PER_WARP; ++c) {
+          float lse = my_lse, rs = my_rs;
+          if (!RES_IS_Q) {  // columns are query rows: per-column parameters (warp-uniform, L1-resident loads)
+            const int64_t q = min(qbase + c, p.B - 1);
+            rs = HAS_RS ? p.inv_batch * __ldg(p.row_scale + q) : p.inv_batch;
+            if (LOSS == KGEB_LOSS_KL) lse = __ldg(p.lse + q);
           }
+          const float x = v[c];
+          const float gval = (LOSS == KGEB_LOSS_KL) ? __expf(x - lse) : sigmoidf(x + p.offset) - p.ls_add;
+          v[c] = rs * gval;
+        }
         mbar_wait(&g_empty[gbuf], gph[gbuf] ^ 1);  // MMA2 of two tiles ago has finished reading this buffer
         uint8_t* gb = g_smem + (size_t)gbuf * G_BYTES;
         if (BF16) {
-          // row trow of the single K-slab: 64 bf16 = 8 chunks of 16 B, 128-byte swizzle
+          // row trow of the single K-slab: this warp's 16 bf16 = chunks 2*part, 2*part+1 (16 B each), 128-byte swizzle
           uint8_t* rowp = gb + (size_t)trow * 128;
 #pragma unroll
-          for (int ck = 0; ck < 8; ++ck) {
+          for (int k = 0; k < 2; ++k) {
             uint32_t w[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int c = ck * 8 + j * 2;
-              const float lo = v[c >> 5][c & 31], hi = v[(c + 1) >> 5][(c + 1) & 31];
-              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(hi), "f"(lo));
-            }
+            for (int j = 0; j < 4; ++j)
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[k * 8 + j * 2 + 1]), "f"(v[k * 8 + j * 2]));
+            const int ck = part * 2 + k;
             *reinterpret_cast<uint4*>(rowp + ((ck ^ (trow & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         } else {
+          // TF32: 64 fp32 = two K-slabs of 32; this warp's 16 columns = chunks 4*(part&1).. of slab part>>1
+          uint8_t* rowp = gb + (size_t)(part >> 1) * RES_SLAB + (size_t)trow * 128;
 #pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            uint8_t* rowp = gb + (size_t)hlf * RES_SLAB + (size_t)trow * 128;
-#pragma unroll
-            for (int ck = 0; ck < 8; ++ck) {
-              float4 val = make_float4(v[hlf][ck * 4], v[hlf][ck * 4 + 1], v[hlf][ck * 4 + 2], v[hlf][ck * 4 + 3]);
-              *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) = val;  // 128-byte swizzle
-            }
+          for (int k = 0; k < 4; ++k) {
+            const int ck = (part & 1) * 4 + k;
+            *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) =
+                make_float4(v[k * 4], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
           }
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -276,25 +273,23 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         gph[gbuf] ^= 1;
         gbuf ^= 1;
       }
-      // flush the job's accumulator
+      // flush the job's accumulator: 16-column groups are dealt round-robin to the column parts
       mbar_wait(o_full, ophase);
       ophase ^= 1;
       tc_fence_after();
-      for (int c0 = 0; c0 < p.d; c0 += 32) {
-        float o[32];
-        tmem_ld32(lane_addr + O_COL + (uint32_t)c0, o);
+      for (int c0 = part * 16; c0 < p.d; c0 += 16 * EPQ) {
+        float o[16];
+        tmem_ld16(lane_addr + O_COL + (uint32_t)c0, o);
         if (res_row < p.n_res) {
           float* dst = RES_IS_Q ? p.out + ((size_t)ch * p.B + res_row) * p.d + c0 : p.out + (size_t)res_row * p.d + c0;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            if (c0 + c < p.d) {
-              float4* d4 = reinterpret_cast<float4*>(dst + c);
-              if (RES_IS_Q) {
-                *d4 = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-              } else {
-                float4 old = *d4;
-                *d4 = make_float4(old.x + o[c], old.y + o[c + 1], old.z + o[c + 2], old.w + o[c + 3]);
-              }
+          for (int c = 0; c < 16; c += 4) {
+            float4* d4 = reinterpret_cast<float4*>(dst + c);
+            if (RES_IS_Q) {
+              *d4 = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+            } else {
+              float4 old = *d4;
+              *d4 = make_float4(old.x + o[c], old.y + o[c + 1], old.z + o[c + 2], old.w + o[c + 3]);
             }
           }
         }
@@ -405,6 +400,28 @@ static Plan make_plan(bool res_is_q, bool bf16, int64_t B, int d, int64_t n_ent)
   return pl;
 }
 
+template <bool RES_IS_Q>
+static int launch_bwd(const Plan& pl, const CUtensorMap& m_res, const CUtensorMap& m_str, int64_t jobs, cudaStream_t st) {
+  const int grid = (int)(jobs < kNumSMs ? jobs : kNumSMs);
+  cudaError_t e = cudaSuccess;
+#define KGEB_BWD_LAUNCH(LOSS_, RS_)                                                                                   \
+  {                                                                                                                   \
+    e = cudaFuncSetAttribute(tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             (int)pl.smem);                                                                           \
+    if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");                                             \
+    tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_><<<grid, NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);                 \
+  }
+  const bool rs = pl.p.row_scale != nullptr;
+  if (pl.p.loss == KGEB_LOSS_KL) {
+    if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_KL, true) else KGEB_BWD_LAUNCH(KGEB_LOSS_KL, false)
+  } else {
+    if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, true) else KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, false)
+  }
+#undef KGEB_BWD_LAUNCH
+  KGEB_LAUNCH_CHECK("tc_bwd_kernel");
+  return KGEB_OK;
+}
+
 __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
@@ -485,10 +502,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = partial;
       if ((rc = make_map(&m_res, Qb, B, d, RES_ROWS, true)) || (rc = make_map(&m_str, tableb, n_ent, d, STR_ROWS, true))) return rc;
       const int64_t jobs = pl.p.n_res_blocks * pl.p.chunks;
-      cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-      if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
-      tc_bwd_kernel<true, true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);
-      KGEB_LAUNCH_CHECK("tc_bwd_kernel<dQ>");
+      if ((rc = launch_bwd<true>(pl, m_res, m_str, jobs, st))) return rc;
       const int64_t numel = B * (int64_t)d;
       reduce_dq_partials_kernel<<<(unsigned)((numel + 255) / 256 > 4096 ? 4096 : (numel + 255) / 256), 256, 0, st>>>(
           partial, pl.p.chunks, numel, dQ);
@@ -503,10 +517,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = dTable;
       if ((rc = make_map(&m_res, tableb, n_ent, d, RES_ROWS, true)) || (rc = make_map(&m_str, Qb, B, d, STR_ROWS, true))) return rc;
       const int64_t jobs = pl.p.n_res_blocks;
-      cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-      if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
-      tc_bwd_kernel<false, true><<<(int)(jobs < kNumSMs ? jobs : kNumSMs), NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);
-      KGEB_LAUNCH_CHECK("tc_bwd_kernel<dTable>");
+      if ((rc = launch_bwd<false>(pl, m_res, m_str, jobs, st))) return rc;
       if (nnz > 0 && (rc = kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st)))
         return rc;
     }

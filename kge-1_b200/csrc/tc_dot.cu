@@ -22,8 +22,12 @@ constexpr int TILE = 128;                 // rows per operand tile (UMMA M = N =
 constexpr int SLAB_BYTES = TILE * 128;    // 16 KiB: 128 rows x 128 B
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr int NUM_THREADS = 256;
+constexpr int EPQ = 4;                              // epilogue warps per TMEM lane quadrant (latency hiding)
+constexpr int NUM_EPI_THREADS = 4 * EPQ * 32;       // 512
+constexpr int NUM_THREADS = 128 + NUM_EPI_THREADS;  // warps 0-3: TMA / MMA / TMEM alloc / idle; 4-19: epilogue
 constexpr int EPI_WARP0 = 4;
+constexpr int COLS_PER_WARP = TILE / EPQ;           // 32 accumulator columns per epilogue warp
+constexpr int COMB_BYTES = EPQ * 2 * TILE * 3 * 4;  // per-job row-statistics exchange between column parts
 
 enum { MODE_SCORES = 0, MODE_STATS = 1, MODE_RANK = 2 };
 
@@ -69,6 +73,7 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* t_full = q_full + 2;         // [2]
   uint64_t* t_empty = q_full + 4;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 6);
+  float* comb = reinterpret_cast<float*>(q_full + 8);  // [EPQ][NQB][TILE][3]
   constexpr int TMEM_COLS = 2 * NQB * TILE;  // double-buffered accumulators (256 or 512 columns)
 
   if (warp == 0 && lane == 0) {
@@ -84,7 +89,7 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(q_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 4 * 32);
+      mbar_init(&t_empty[b], NUM_EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -164,10 +169,13 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
   } else if (warp >= EPI_WARP0) {
-    // ================================ epilogue ================================
-    const int ew = warp - EPI_WARP0;            // == warp % 4 : TMEM lane quadrant of this warp
-    const int trow = ew * 32 + lane;            // row of the A tile owned by this thread
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(ew * 32) << 16);
+    // ================================ epilogue (16 warps: lane quadrant x column part) ================================
+    const int ew = warp - EPI_WARP0;
+    const int quad = ew & 3;                    // == warp % 4 : TMEM lane quadrant this warp may access
+    const int part = ew >> 2;                   // which 32 accumulator columns of the 128
+    const int trow = quad * 32 + lane;          // row of the A tile owned by this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int cw0 = part * COLS_PER_WARP;       // first column of this warp
     int buf = 0;
     uint32_t tphase[2] = {0, 0};
     for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -175,7 +183,7 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int nqb = (int)min((int64_t)NQB, n_qblocks - qg * NQB);
       const int64_t t0 = ch * p.tiles_per_chunk, t1 = min(p.n_tiles, t0 + p.tiles_per_chunk);
 
-      // per-job running state (MODE_STATS / MODE_RANK: thread = query row trow of block qb)
+      // per-job running state (MODE_STATS / MODE_RANK: thread = query row trow of block qb, columns of its part)
       float s0[NQB], s1[NQB], s2[NQB];
       int cnt[NQB][6];
       float tsc[NQB];
@@ -205,6 +213,7 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tphase[buf] ^= 1;
         tc_fence_after();
         const int ncols = (int)min((int64_t)TILE, p.n_ent - t * TILE);  // valid B-tile rows (columns of S)
+        const int nv = min(COLS_PER_WARP, ncols - cw0);                  // valid columns of this warp (may be <= 0)
 #pragma unroll
         for (int qb = 0; qb < NQB; ++qb) {
           if (qb >= nqb) continue;
@@ -213,67 +222,69 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (MODE == MODE_SCORES) {
             // lanes = entities of tile t, columns = query rows of block qb
             const int64_t e = t * TILE + trow;
-            for (int c0 = 0; c0 < TILE; c0 += 32) {
-              if (qrow0 + c0 >= p.B) break;  // warp-uniform
+            if (qrow0 + cw0 < p.B) {  // warp-uniform
               float v[32];
-              tmem_ld32(acc + c0, v);
+              tmem_ld32(acc + cw0, v);
               if (e < p.n_ent) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                  const int64_t q = qrow0 + c0 + c;
+                  const int64_t q = qrow0 + cw0 + c;
                   if (q < p.B) p.out[q * p.ld + p.col_off + e] = v[c];
                 }
               }
             }
           } else if (MODE == MODE_STATS) {
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
+            if (nv > 0) {
               float v[32];
-              tmem_ld32(acc + c0, v);
-              const int nv = min(32, ncols - c0);
+              tmem_ld32(acc + cw0, v);
               if (p.loss == KGEB_LOSS_KL) {
                 float mx = s0[qb];
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                   if (c < nv) mx = fmaxf(mx, v[c]);
                 float l = (s0[qb] == -INFINITY) ? 0.f : s1[qb] * __expf(s0[qb] - mx);
+                float a2 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                   if (c < nv) {
                     l += __expf(v[c] - mx);
-                    s2[qb] += v[c];
+                    a2 += v[c];
                   }
                 s0[qb] = mx;
                 s1[qb] = l;
+                s2[qb] += a2;
               } else {
+                float a0 = 0.f, a2 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                  if (c < nv) {
-                    const float x = v[c] + p.offset;
-                    s0[qb] += softplusf(x);
-                    s2[qb] += x;
-                  }
+                for (int c = 0; c < 32; ++c) {
+                  const float x = v[c] + p.offset;
+                  const float sp = softplusf(x);
+                  a0 += (c < nv) ? sp : 0.f;
+                  a2 += (c < nv) ? x : 0.f;
+                }
+                s0[qb] += a0;
+                s2[qb] += a2;
               }
             }
           } else {  // MODE_RANK
             const float ts = tsc[qb];
             const int64_t ent0 = p.e_lo + t * TILE;
-            for (int c0 = 0; c0 < ncols; c0 += 32) {
+            if (nv > 0) {
               float v[32];
-              tmem_ld32(acc + c0, v);
-              const int nv = min(32, ncols - c0);
+              tmem_ld32(acc + cw0, v);
 #pragma unroll
               for (int c = 0; c < 32; ++c)
                 if (c < nv) {
                   float x = v[c];
-                  if (ent0 + c0 + c == tent[qb]) x = ts;  // entity_ranking.py:170-177
+                  if (ent0 + cw0 + c == tent[qb]) x = ts;  // entity_ranking.py:170-177
                   if (x != x) x = -INFINITY;
                   cnt[qb][0] += (x > ts);
                   cnt[qb][1] += (x == ts);
                 }
             }
-            // corrections for filtered candidates (their score becomes -inf): warp-cooperative, one
-            // filter entry per iteration; the value is re-read from the same TMEM accumulator so
-            // comparisons are bit-consistent with the raw pass.
+            // corrections for filtered candidates (their score becomes -inf): warp-cooperative, one filter entry per
+            // iteration; the value is re-read from the same TMEM accumulator so comparisons are bit-consistent with
+            // the raw pass.  Every column part walks the row's entries of this tile and handles those in its columns.
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
               const int64_t* col = which ? p.t_col : p.f_col;
@@ -283,9 +294,13 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               while (true) {
                 int loc = -1;
                 int64_t c = -1;
-                if (cur < end) {
+                while (cur < end) {
                   c = col[cur];
-                  if (c < ent0 + ncols) loc = (int)(c - ent0);
+                  if (c >= ent0 + ncols) break;
+                  const int l = (int)(c - ent0);
+                  if ((l / COLS_PER_WARP) == part && c != prev && c != tent[qb]) { loc = l; break; }
+                  prev = c;
+                  ++cur;
                 }
                 const unsigned mask = __ballot_sync(0xffffffffu, loc >= 0);
                 if (mask == 0) break;
@@ -294,12 +309,10 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 float x = tmem_ld1(acc + (uint32_t)sloc);
                 if (lane == src) {
                   ++cur;
-                  if (c != prev && c != tent[qb]) {
-                    if (x != x) x = -INFINITY;
-                    cnt[qb][2 + 2 * which] -= (x > ts);
-                    cnt[qb][3 + 2 * which] += (ts == -INFINITY) - (x == ts);
-                  }
                   prev = c;
+                  if (x != x) x = -INFINITY;
+                  cnt[qb][2 + 2 * which] -= (x > ts);
+                  cnt[qb][3 + 2 * which] += (ts == -INFINITY) - (x == ts);
                 }
               }
             }
@@ -311,14 +324,43 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
 
       // job results
+      if (MODE == MODE_STATS) {
+        // exchange the per-part statistics through shared memory; part 0 combines them in a fixed order
 #pragma unroll
-      for (int qb = 0; qb < NQB; ++qb) {
-        const int64_t r = (qg * NQB + qb) * TILE + trow;
-        if (qb >= nqb || r >= p.B) continue;
-        if (MODE == MODE_STATS) {
-          float* o = p.partial + (ch * p.B + r) * 4;
-          o[0] = s0[qb]; o[1] = s1[qb]; o[2] = s2[qb]; o[3] = 0.f;
-        } else if (MODE == MODE_RANK) {
+        for (int qb = 0; qb < NQB; ++qb) {
+          float* c = comb + (((size_t)part * 2 + qb) * TILE + trow) * 3;
+          c[0] = s0[qb]; c[1] = s1[qb]; c[2] = s2[qb];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+        if (part == 0) {
+#pragma unroll
+          for (int qb = 0; qb < NQB; ++qb) {
+            const int64_t r = (qg * NQB + qb) * TILE + trow;
+            if (qb >= nqb || r >= p.B) continue;
+            float a0 = s0[qb], a1 = s1[qb], a2 = s2[qb];
+            for (int pp = 1; pp < EPQ; ++pp) {
+              const float* c = comb + (((size_t)pp * 2 + qb) * TILE + trow) * 3;
+              if (p.loss == KGEB_LOSS_KL) {
+                const float mx = fmaxf(a0, c[0]);
+                const float x = (a0 == -INFINITY) ? 0.f : a1 * __expf(a0 - mx);
+                const float y = (c[0] == -INFINITY) ? 0.f : c[1] * __expf(c[0] - mx);
+                a0 = mx;
+                a1 = x + y;
+              } else {
+                a0 += c[0];
+              }
+              a2 += c[2];
+            }
+            float* o = p.partial + (ch * p.B + r) * 4;
+            o[0] = a0; o[1] = a1; o[2] = a2; o[3] = 0.f;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");  // comb[] may be rewritten by the next job
+      } else if (MODE == MODE_RANK) {
+#pragma unroll
+        for (int qb = 0; qb < NQB; ++qb) {
+          const int64_t r = (qg * NQB + qb) * TILE + trow;
+          if (qb >= nqb || r >= p.B) continue;
           unsigned long long* c = p.counts + r * 6;
           const long long rr = cnt[qb][0], rt = cnt[qb][1];
           atomicAdd(c + 0, (unsigned long long)rr);
@@ -407,7 +449,7 @@ static Plan make_plan(int64_t B, int d, int64_t n_ent, int64_t e_lo, bool bf16 =
   const int64_t n_qblocks = (B + TILE - 1) / TILE;
   pl.nqb = (n_qblocks >= 2 && ks <= 4) ? 2 : 1;
   const size_t q_bytes = (size_t)pl.nqb * ks * SLAB_BYTES;
-  const size_t fixed = 1024 /*align*/ + 512 /*barriers*/;
+  const size_t fixed = 1024 /*align*/ + 512 /*barriers*/ + COMB_BYTES;
   int stages = (int)((SMEM_BUDGET - fixed - q_bytes) / SLAB_BYTES);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   Params& p = pl.p;
