@@ -121,6 +121,12 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
                    const float* row_scale /*[B] per-row factor multiplied into G (upstream gradient), or NULL*/,
                    const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */, float* dQ, float* dTable,
                    void* workspace, int64_t workspace_bytes, void* stream);
+/* loss(scores, labels) / batch_size from the (shard-combined) forward statistics, as the reference's loss objects
+ * return it (loss.py:153-159, 198-213): rows_out[B] per-row values (may be NULL), lse_out[B] log-sum-exp per row for
+ * the KL backward (may be NULL), total[1] their sum in a fixed order. */
+int kgeb_loss_from_rowstat(int loss, const float* rowstat, const int64_t* lab_off, int64_t B, float label_smoothing,
+                           int64_t num_entities, float inv_batch, float* rows_out, float* lse_out, float* total,
+                           void* stream);
 /* fp32 -> bf16 (round to nearest even) mirror of a table / query matrix for KGEB_MATH_BF16 */
 int kgeb_to_bf16(const float* src, void* dst, int64_t numel, void* stream);
 int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities, int64_t nnz);

@@ -888,6 +888,49 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
 }
 
 
+// per-row loss values, log-sum-exp and the batch loss from the fused forward statistics: one block, fixed order
+__global__ void __launch_bounds__(1024)
+loss_rows_kernel(int loss, const float* __restrict__ rowstat, const int64_t* __restrict__ lab_off, int64_t B,
+                 float ls_keep, float ls_add, float inv_batch, float* __restrict__ rows_out,
+                 float* __restrict__ lse_out, float* __restrict__ total) {
+  __shared__ float red[1024];
+  float acc = 0.f;
+  for (int64_t r = threadIdx.x; r < B; r += blockDim.x) {
+    const float* s = rowstat + r * 4;
+    const float nnz = (float)(lab_off[r + 1] - lab_off[r]);
+    float v, lse = 0.f;
+    if (loss == KGEB_LOSS_KL) {
+      lse = s[0] + logf(s[1]);
+      v = nnz > 0.f ? lse - s[3] / nnz - logf(nnz) : 0.f;   // sum_j t (log t - log_softmax_j), t = y / nnz
+    } else {
+      v = s[0] - ls_keep * s[3] - ls_add * s[2];           // sum_j softplus(x) - t x, t = keep * y + add
+    }
+    v *= inv_batch;
+    if (rows_out) rows_out[r] = v;
+    if (lse_out) lse_out[r] = lse;
+    acc += v;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) total[0] = red[0];
+}
+
+int kgeb_loss_from_rowstat(int loss, const float* rowstat, const int64_t* lab_off, int64_t B, float label_smoothing,
+                           int64_t num_entities, float inv_batch, float* rows_out, float* lse_out, float* total,
+                           void* stream) {
+  KGEB_REQUIRE(loss == KGEB_LOSS_KL || loss == KGEB_LOSS_BCE, "loss_from_rowstat: unknown loss %d", loss);
+  KGEB_REQUIRE(rowstat && lab_off && B >= 0, "loss_from_rowstat: bad arguments");
+  const float add = label_smoothing > 0.f ? 1.f / (float)num_entities : 0.f;
+  loss_rows_kernel<<<1, 1024, 0, as_stream(stream)>>>(loss, rowstat, lab_off, B, 1.f - label_smoothing, add, inv_batch,
+                                                      rows_out, lse_out, total);
+  KGEB_LAUNCH_CHECK("loss_rows");
+  return KGEB_OK;
+}
+
 int kgeb_to_bf16(const float* src, void* dst, int64_t numel, void* stream) {
   KGEB_REQUIRE(src && dst && numel >= 0, "to_bf16: bad arguments");
   return tc_to_bf16(src, dst, numel, as_stream(stream));

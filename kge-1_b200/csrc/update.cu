@@ -12,7 +12,7 @@
 namespace kgeb {
 
 struct ScatterWs {
-  float* part;  // [ceil(n/32)][2][d] partial segment sums
+  float* part;  // [ceil(n/CHUNK)][2][d] partial segment sums
   int64_t* keys_in;
   int64_t* keys_out;
   int32_t* pos_in;
@@ -33,7 +33,7 @@ static size_t cub_temp_bytes(int64_t n) {
   return a > b ? a : b;
 }
 
-static size_t part_bytes(int64_t n, int d) { return align256((size_t)((n + 31) / 32) * 2 * (size_t)d * 4); }
+static size_t part_bytes(int64_t n, int d) { return align256((size_t)((n + 7) / 8) * 2 * (size_t)d * 4); }
 
 static int64_t scatter_ws_bytes(int64_t n, int d) {
   if (n < 1) n = 1;
@@ -79,69 +79,107 @@ __global__ void seg_starts_kernel(const int64_t* __restrict__ keys, const int32_
   }
 }
 
-// Segment sums in two fixed-order phases (deterministic, no float atomics, no serial walk over hot keys):
-//  phase 1: one warp per chunk of CHUNK consecutive sorted positions walks its rows in order; runs that are whole
-//           segments are written out directly, the (at most two) runs that continue into a neighbouring chunk go
-//           to part[chunk][0] (run continuing from the previous chunk) / part[chunk][1] (run continuing into the next);
+// Segment sums in two fixed-order phases (deterministic: every output element has exactly one writer per phase and
+// a fixed summation order; hot keys are not walked serially):
+//  phase 1: one warp per chunk of CHUNK consecutive sorted positions loads its rows in one batch and adds them in
+//           position order; runs that are whole segments go straight to the output, the (at most two) runs that
+//           continue into a neighbouring chunk go to part[chunk][0] (run continuing from the previous chunk) /
+//           part[chunk][1] (run continuing into the next);
 //  phase 2: one warp per segment that spans several chunks adds its partials in chunk order.
-constexpr int CHUNK = 32;
+constexpr int CHUNK = 8;
 
-template <bool DENSE>
-__device__ __forceinline__ void seg_emit(float4 acc, int c0, int d, bool add, float* dst, bool vec) {
-  // dst points at column c0 of the destination row
+__device__ __forceinline__ void seg_store(float4 acc, int c0, int d, float* dst, bool vec) {
   if (vec && c0 + 3 < d) {
-    float4* p = reinterpret_cast<float4*>(dst);
-    if (add) { float4 o = *p; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
-    *p = acc;
+    *reinterpret_cast<float4*>(dst) = acc;
   } else {
     float v[4] = {acc.x, acc.y, acc.z, acc.w};
-    for (int j = 0; j < 4 && c0 + j < d; ++j) dst[j] = add ? dst[j] + v[j] : v[j];
+    for (int j = 0; j < 4 && c0 + j < d; ++j) dst[j] = v[j];
   }
+}
+// dense[...] += acc.  Each address has a single writer in a kernel, so the fire-and-forget reduction is deterministic.
+__device__ __forceinline__ void seg_add(float4 acc, int c0, int d, float* dst) {
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (c0 + j < d) atomicAdd(dst + j, v[j]);
 }
 
 template <bool DENSE>
 __global__ void __launch_bounds__(256)
 segment_sum_phase1(const int64_t* __restrict__ keys, const int32_t* __restrict__ pos,
-                   const int32_t* __restrict__ seg_id, const int32_t* __restrict__ seg_start, int64_t n, int d,
-                   const float* __restrict__ rows, float* __restrict__ dense, int64_t vocab,
-                   int64_t* __restrict__ uniq_ids, float* __restrict__ uniq_rows, float* __restrict__ part) {
+                   const int32_t* __restrict__ seg_id, int64_t n, int d, const float* __restrict__ rows,
+                   float* __restrict__ dense, int64_t vocab, int64_t* __restrict__ uniq_ids,
+                   float* __restrict__ uniq_rows, float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
   const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
   const bool vec = (d & 3) == 0;
   for (int64_t ch = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks;
        ch += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-    const int cb = (int)(ch * CHUNK), ce = (int)min((int64_t)cb + CHUNK, n);
-    int i = cb;
-    while (i < ce) {
-      const int sid = seg_id[i];                 // 1-based
-      const int sb = seg_start[sid - 1], se = seg_start[sid];
-      const int re = min(se, ce);
-      const int64_t key = keys[i];
-      const bool complete = (i == sb) && (re == se);
-      const bool ok = !DENSE || (key >= 0 && key < vocab);
-      for (int c0 = lane * 4; c0 < d; c0 += 128) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = i; r < re; ++r) {
-          const float* src = rows + (int64_t)pos[r] * d + c0;
+    const int64_t cb = ch * CHUNK;
+    const int m = (int)min((int64_t)CHUNK, n - cb);
+    // chunk metadata, one position per lane (all loads issued together)
+    int my_pos = 0, my_sid = -1;
+    int64_t my_key = 0;
+    if (lane < m) {
+      my_pos = pos[cb + lane];
+      my_sid = seg_id[cb + lane];
+      my_key = keys[cb + lane];
+    }
+    const int prev_sid = cb > 0 ? seg_id[cb - 1] : -1;
+    const int next_sid = cb + m < n ? seg_id[cb + m] : -2;
+    int sid[CHUNK], prw[CHUNK];
+    int64_t key[CHUNK];
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      sid[j] = __shfl_sync(0xffffffffu, my_sid, j);
+      prw[j] = __shfl_sync(0xffffffffu, my_pos, j);
+      key[j] = __shfl_sync(0xffffffffu, my_key, j);
+    }
+    for (int cg = 0; cg < d; cg += 128) {
+      const int c0 = cg + lane * 4;
+      if (c0 >= d) continue;
+      float4 v[CHUNK];
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) {  // the whole chunk in flight at once
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < m) {
+          const float* src = rows + (int64_t)prw[j] * d + c0;
           if (vec) {
-            float4 v = __ldg(reinterpret_cast<const float4*>(src));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            v[j] = __ldg(reinterpret_cast<const float4*>(src));
           } else {
-            acc.x += src[0];
-            if (c0 + 1 < d) acc.y += src[1];
-            if (c0 + 2 < d) acc.z += src[2];
-            if (c0 + 3 < d) acc.w += src[3];
+            v[j].x = src[0];
+            if (c0 + 1 < d) v[j].y = src[1];
+            if (c0 + 2 < d) v[j].z = src[2];
+            if (c0 + 3 < d) v[j].w = src[3];
           }
         }
-        if (complete) {
-          if (ok) seg_emit<DENSE>(acc, c0, d, DENSE, DENSE ? dense + key * d + c0 : uniq_rows + (int64_t)(sid - 1) * d + c0, vec);
-        } else {
-          const int slot = (i != sb) ? 0 : 1;    // continuation from the previous chunk | run continuing into the next
-          seg_emit<false>(acc, c0, d, false, part + ((ch * 2 + slot) * (int64_t)d) + c0, vec);
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool from_prev = (prev_sid == sid[0]);   // the current run continues a segment of the previous chunk
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) {
+        if (j < m) {
+          acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+          const bool last_of_chunk = (j == m - 1);
+          const bool run_ends = last_of_chunk || (sid[j + 1 < CHUNK ? j + 1 : j] != sid[j]);
+          if (run_ends) {
+            const bool to_next = last_of_chunk && (next_sid == sid[j]);
+            if (!from_prev && !to_next) {          // a whole segment
+              const int64_t k = key[j];
+              if (DENSE) {
+                if (k >= 0 && k < vocab) seg_add(acc, c0, d, dense + k * d + c0);
+              } else {
+                seg_store(acc, c0, d, uniq_rows + (int64_t)(sid[j] - 1) * d + c0, vec);
+                if (cg == 0 && lane == 0) uniq_ids[sid[j] - 1] = k;
+              }
+            } else {
+              seg_store(acc, c0, d, part + ((ch * 2 + (from_prev ? 0 : 1)) * (int64_t)d) + c0, vec);
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            from_prev = false;
+          }
         }
       }
-      if (!DENSE && complete && lane == 0) uniq_ids[sid - 1] = key;
-      i = re;
     }
   }
 }
@@ -161,22 +199,32 @@ segment_sum_phase2(const int64_t* __restrict__ keys, const int32_t* __restrict__
     if (c0ch == c1ch) continue;  // finished in phase 1
     const int64_t key = keys[sb];
     if (DENSE && (key < 0 || key >= vocab)) continue;
-    for (int c0 = lane * 4; c0 < d; c0 += 128) {
+    for (int cg = 0; cg < d; cg += 128) {
+      const int c0 = cg + lane * 4;
+      if (c0 >= d) continue;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int64_t ch = c0ch; ch <= c1ch; ++ch) {
-        const int slot = (ch == c0ch) ? 1 : 0;
-        const float* src = part + ((ch * 2 + slot) * (int64_t)d) + c0;
-        if (vec && c0 + 3 < d) {
-          float4 v = *reinterpret_cast<const float4*>(src);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        } else {
-          acc.x += src[0];
-          if (c0 + 1 < d) acc.y += src[1];
-          if (c0 + 2 < d) acc.z += src[2];
-          if (c0 + 3 < d) acc.w += src[3];
+      for (int64_t ch = c0ch; ch <= c1ch; ch += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // eight partials in flight, added in chunk order
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ch + j <= c1ch) {
+            const float* src = part + (((ch + j) * 2 + ((ch + j) == c0ch ? 1 : 0)) * (int64_t)d) + c0;
+            if (vec && c0 + 3 < d) {
+              v[j] = *reinterpret_cast<const float4*>(src);
+            } else {
+              v[j].x = src[0];
+              if (c0 + 1 < d) v[j].y = src[1];
+              if (c0 + 2 < d) v[j].z = src[2];
+              if (c0 + 3 < d) v[j].w = src[3];
+            }
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
       }
-      seg_emit<DENSE>(acc, c0, d, DENSE, DENSE ? dense + key * d + c0 : uniq_rows + seg * (int64_t)d + c0, vec);
+      if (DENSE) seg_add(acc, c0, d, dense + key * d + c0);
+      else seg_store(acc, c0, d, uniq_rows + seg * (int64_t)d + c0, vec);
     }
     if (!DENSE && lane == 0) uniq_ids[seg] = key;
   }
@@ -188,8 +236,8 @@ static int segment_sums(ScatterWs& w, int64_t n, int d, const float* rows, float
   const int64_t nchunks = (n + CHUNK - 1) / CHUNK;
   int64_t b1 = (nchunks + 7) / 8, b2 = (n + 7) / 8;
   const int64_t cap = (int64_t)kNumSMs * 16;
-  segment_sum_phase1<DENSE><<<(int)(b1 > cap ? cap : b1), 256, 0, st>>>(w.keys_out, w.pos_out, w.seg_id, w.seg_start, n,
-                                                                       d, rows, dense, vocab, uniq_ids, uniq_rows, w.part);
+  segment_sum_phase1<DENSE><<<(int)(b1 > cap ? cap : b1), 256, 0, st>>>(w.keys_out, w.pos_out, w.seg_id, n, d, rows, dense,
+                                                                       vocab, uniq_ids, uniq_rows, w.part);
   segment_sum_phase2<DENSE><<<(int)(b2 > cap ? cap : b2), 256, 0, st>>>(w.keys_out, w.seg_id, w.seg_start, n, d, dense,
                                                                        vocab, uniq_ids, uniq_rows, w.part);
   KGEB_LAUNCH_CHECK("segment_sum");

@@ -54,6 +54,7 @@ class FusedAllEntityStepper:
         self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
         self.rowstat = torch.empty(rows, 4, **f32)
         self.loss = torch.zeros((), **f32)
+        self.lse = torch.zeros(rows, **f32)
         self.shard = fused.Shard.full(self.E)
         self.ws = torch.empty(lib.load().kgeb_fused_workspace_bytes(rows, self.d, self.E, max(nnz_max, 1)),
                               dtype=torch.uint8, device=dev)
@@ -82,8 +83,9 @@ class FusedAllEntityStepper:
         lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
                  self.E, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset, mp,
                  self.rowstat.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 4
-        per_row, lse = fused.rows_loss(self.rowstat, self.lab_off, self.loss_kind, self.ls, self.E)
-        torch.sum(per_row, dim=0, out=self.loss); self.loss.div_(self.batch_size); n += 6
+        lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
+                 self.ls, self.E, 1.0 / self.batch_size, None, self.lse.data_ptr(), self.loss.data_ptr(), st); n += 1
+        lse = self.lse if self.loss_kind == lib.LOSS_KL else None
         lib.call("kgeb_fused_bwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
                  self.E, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
                  None if lse is None else lse.data_ptr(), 1.0 / self.batch_size, None, mp, self.dQ.data_ptr(),
