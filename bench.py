@@ -179,12 +179,15 @@ def main():
     import kgeb200 as kb
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
     if world > 1:
-        import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     math_mode = {"bf16": kb.lib.MATH_BF16, "tf32": kb.lib.MATH_TF32, "fp32": kb.lib.MATH_FP32}[args.math]
     n_batches = args.steps + args.warmup
-    graph, batches = build_batches(n_batches, B, seed=7, rank=rank)
+    # entity-sharded scoring: every rank processes the whole global batch (world * B queries) against its own
+    # entity range, so all ranks build the same batches (weak scaling: per-GPU work B x E stays fixed)
+    GB = B * world
+    graph, batches = build_batches(n_batches, GB, seed=7, rank=0)
     E, R = graph["num_entities"], graph["num_relations"]
     nnz_max = max(int(b["label_coords"].shape[0]) for b in batches)
     for b in batches:
@@ -194,8 +197,10 @@ def main():
     torch.manual_seed(0)
     model = kb.KgeModel("complex", E, R, DIM).to(dev)
     opt = kb.optim.create("Adagrad", model.parameters(), lr=LR)
-    job = kb.TrainingJobKvsAll(model, opt, kb.KgeLoss.create("bce"), E, R, fused_path=True, math_mode=math_mode)
-    job.enable_graph_step(B, nnz_max, use_graph=not args.no_graph and world == 1)
+    shard = kb.fused.Shard.of_rank(E, rank, world, dist.group.WORLD) if world > 1 else None
+    job = kb.TrainingJobKvsAll(model, opt, kb.KgeLoss.create("bce"), E, R, fused_path=True, math_mode=math_mode,
+                               shard=shard)
+    job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph and world == 1)
     stepper = job.stepper
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -253,7 +258,7 @@ def main():
     h2d = int(np.mean([sum(v.numel() * v.element_size() for v in b.values()) for b in batches]))
 
     # ---------------- roofline of the dominant kernel (timed alone with CUDA events) ---------------------
-    roof = kernel_roofline(kb, stepper, math_mode, B, E)
+    roof = kernel_roofline(kb, stepper, math_mode, GB, E)
 
     if rank != 0:
         return

@@ -140,7 +140,7 @@ class TrainingJobKvsAll(TrainingJob):
             raise NotImplementedError("penalty terms are not part of the graph-captured step")
         self.stepper = FusedAllEntityStepper(self.model, self.optimizer, batch_size, nnz_max, self.loss.kind,
                                              batch_size, self.loss.offset, self.label_smoothing, self.math_mode,
-                                             use_graph)
+                                             use_graph, self.shard)
         return self.stepper
 
     def device_inputs(self, batch):

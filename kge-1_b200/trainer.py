@@ -22,7 +22,7 @@ from .model import KgeModel
 class FusedAllEntityStepper:
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
-                 use_graph: bool = True):
+                 use_graph: bool = True, shard: Optional[fused.Shard] = None):
         if model.get_scorer().kind != lib.DOT:
             raise NotImplementedError("the fused all-entity step serves the DOT scorers")
         self.model, self.opt = model, optimizer
@@ -55,7 +55,12 @@ class FusedAllEntityStepper:
         self.rowstat = torch.empty(rows, 4, **f32)
         self.loss = torch.zeros((), **f32)
         self.lse = torch.zeros(rows, **f32)
-        self.shard = fused.Shard.full(self.E)
+        # Multi-GPU: every rank sees the whole batch and scores it against its own entity range
+        # [e_lo, e_hi); row statistics, dQ and the dense table gradient are all-reduced over NVLink.  The (small)
+        # tables and the optimizer state are replicated, so every rank applies the identical update.
+        self.shard = shard or fused.Shard.full(self.E)
+        if self.shard.distributed and use_graph:
+            raise NotImplementedError("the sharded step issues NCCL collectives and is not graph-captured")
         self.ws = torch.empty(lib.load().kgeb_fused_workspace_bytes(rows, self.d, self.E, max(nnz_max, 1)),
                               dtype=torch.uint8, device=dev)
         self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(rows, max(self.d, self.dr)), dtype=torch.uint8,
@@ -75,21 +80,30 @@ class FusedAllEntityStepper:
         st = lib.stream_ptr(self.ent)
         model_id = lib.MODELS[self.model.model]
         ent, rel = self.ent.detach(), self.rel.detach()
-        mp = None if self.mirror is None else self.mirror.data_ptr()
         n = 0
         self.g_ent.zero_(); self.g_rel.zero_(); n += 2
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st); n += 1
-        lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
-                 self.E, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset, mp,
-                 self.rowstat.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 4
+        sh = self.shard
+        ent_sh = ent[sh.e_lo:sh.e_hi]                       # this rank's entity rows (a view: no copy)
+        g_sh = self.g_ent[sh.e_lo:sh.e_hi]
+        mp = None if self.mirror is None else self.mirror[sh.e_lo:sh.e_hi].data_ptr()
+        lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent_sh.data_ptr(),
+                 sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls,
+                 self.offset, mp, self.rowstat.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 4
+        if sh.distributed:
+            self.rowstat.copy_(fused.combine_rowstats(self.rowstat, self.loss_kind, sh))
         lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
                  self.ls, self.E, 1.0 / self.batch_size, None, self.lse.data_ptr(), self.loss.data_ptr(), st); n += 1
         lse = self.lse if self.loss_kind == lib.LOSS_KL else None
-        lib.call("kgeb_fused_bwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
-                 self.E, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
-                 None if lse is None else lse.data_ptr(), 1.0 / self.batch_size, None, mp, self.dQ.data_ptr(),
-                 self.g_ent.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 14
+        lib.call("kgeb_fused_bwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent_sh.data_ptr(),
+                 sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls,
+                 self.offset, None if lse is None else lse.data_ptr(), 1.0 / self.batch_size, None, mp,
+                 self.dQ.data_ptr(), g_sh.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 14
+        if sh.distributed:
+            import torch.distributed as dist
+            dist.all_reduce(self.dQ, group=sh.group)      # sum of the per-shard partial query gradients
+            dist.all_reduce(self.g_ent, group=sh.group)   # dense table gradient: each rank contributed its rows
         lib.call("kgeb_query_bwd", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.dQ.data_ptr(), self.da.data_ptr(),
                  self.dp.data_ptr(), st); n += 1
@@ -99,7 +113,7 @@ class FusedAllEntityStepper:
                  self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st); n += 8
         s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
         lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), ent.numel(), self.lr,
-                 self.eps, 0.0, mp, st); n += 1
+                 self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st); n += 1
         lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), rel.numel(), self.lr,
                  self.eps, 0.0, None, st); n += 1
         self.kernel_launches_per_step = n

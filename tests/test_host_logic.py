@@ -1,0 +1,154 @@
+"""CPU tests of the host-side logic: CSR / index construction against the reference's golden arrays, the synthetic
+graph generator, loss-from-statistics algebra, shard partitioning and -- with a world_size-2 gloo group -- the
+collective combination of per-shard row statistics (the multi-GPU path of SURVEY.md 8e).  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import kgeb200 as kb
+from oracle import kge_oracle as ko
+
+T = torch.from_numpy
+
+
+def test_kvsall_index_matches_reference_arrays(golden):
+    g = golden("index")
+    for split in ("train", "valid"):
+        for key in ("sp", "po"):
+            ix = kb.index.KvsAllIndex(g[f"index.{split}.triples"], key)
+            np.testing.assert_array_equal(ix._keys.numpy(), g[f"index.{split}.{key}.keys"])
+            np.testing.assert_array_equal(ix._values_offset.numpy(), g[f"index.{split}.{key}.offsets"])
+            np.testing.assert_array_equal(ix._values.numpy(), g[f"index.{split}.{key}.values"])
+    ix = kb.index.KvsAllIndex(g["index.train.triples"], "sp")
+    k = tuple(int(x) for x in g["index.train.sp.keys"][3])
+    off = g["index.train.sp.offsets"]
+    np.testing.assert_array_equal(ix.get(k).numpy(), g["index.train.sp.values"][off[3]:off[4]])
+    assert len(ix.get((10 ** 6, 0))) == 0     # default_factory list() in the reference (indexing.py:57-63)
+
+
+def test_csr_from_coords_and_gather_rows():
+    coords = torch.tensor([[2, 5], [0, 7], [2, 1], [0, 3], [3, 9]])
+    off, col = kb.fused.csr_from_coords(coords, 5)
+    assert off.tolist() == [0, 2, 2, 4, 5, 5]
+    assert col.tolist() == [3, 7, 1, 5, 9]
+    off, col = kb.fused.csr_from_coords(torch.zeros(0, 2, dtype=torch.long), 3)
+    assert off.tolist() == [0, 0, 0, 0] and col.numel() == 0
+    offsets = torch.tensor([0, 2, 2, 5])
+    values = torch.tensor([10, 11, 20, 21, 22])
+    o, v = kb.index.gather_csr_rows(offsets, values, torch.tensor([2, -1, 0, 1]), add=100)
+    assert o.tolist() == [0, 3, 3, 5, 5] and v.tolist() == [120, 121, 122, 110, 111]
+    mo, mc = kb.index.merge_sorted_csr([(o, v), (torch.tensor([0, 1, 1, 1, 2]), torch.tensor([5, 7]))], 4)
+    assert mo.tolist() == [0, 4, 4, 6, 7] and mc.tolist() == [5, 120, 121, 122, 110, 111, 7]
+
+
+def test_kvsall_rows_and_oracle_collate_agree(golden):
+    g = golden("train")
+    tag = "train.KvsAll.complex.bce.b0"
+    q, qt = T(g[tag + ".queries"]), T(g[tag + ".query_type"])
+    a, p, rc = kb.trainer.kvsall_rows(q, qt)
+    sp = qt == 0
+    assert torch.equal(a[sp], q[sp, 0]) and torch.equal(p[sp], q[sp, 1])      # sp_: (s, p)
+    assert torch.equal(a[~sp], q[~sp, 1]) and torch.equal(p[~sp], q[~sp, 0])  # _po: keys are (p, o)
+    assert rc.dtype == torch.int32 and set(rc.tolist()) <= {0, 1}
+    # the reference's collate emits coordinates grouped by row with ascending labels: CSR == plain counting
+    off, col = kb.fused.csr_from_coords(T(g[tag + ".label_coords"]), len(q))
+    assert torch.equal(col, T(g[tag + ".label_coords"])[:, 1].long())
+
+
+def test_synthetic_graph_generator():
+    g = kb.graph.synthetic_graph("toy", seed=5)
+    e, r = g["num_entities"], g["num_relations"]
+    allt = np.concatenate([g["train"], g["valid"], g["test"]])
+    assert g["train"].dtype == np.int32 and g["train"].shape == (4565, 3)
+    assert len(np.unique(allt, axis=0)) == len(allt)                     # no duplicates, disjoint splits
+    assert allt[:, [0, 2]].max() < e and allt[:, 1].max() < r and allt.min() >= 0
+    sp = kb.index.KvsAllIndex(g["train"], "sp")
+    assert len(sp) < len(g["train"])                                      # Zipf draws give multi-answer keys
+    g2 = kb.graph.synthetic_graph("toy", seed=5)
+    np.testing.assert_array_equal(g["train"], g2["train"])               # seeded
+
+
+def test_rows_loss_algebra_matches_oracle_losses():
+    gen = torch.Generator().manual_seed(0)
+    b, e = 7, 31
+    x = torch.randn(b, e, generator=gen) * 3
+    cols = torch.stack([torch.randperm(e, generator=gen)[:3].sort().values for _ in range(b)])
+    lab_off = torch.arange(0, 3 * b + 1, 3)
+    y = torch.zeros(b, e).scatter_(1, cols, 1.0)
+    # KL: statistics (max, sum exp, sum x, sum over labels)
+    st = torch.stack((x.max(1).values, torch.exp(x - x.max(1, keepdim=True).values).sum(1), x.sum(1),
+                      x.gather(1, cols).sum(1)), 1)
+    rows, lse = kb.fused.rows_loss(st, lab_off, kb.lib.LOSS_KL, 0.0, e)
+    assert rows.sum().item() == pytest.approx(ko.loss_kl(x, y).item(), rel=1e-5)
+    torch.testing.assert_close(lse, torch.logsumexp(x, 1))
+    # BCE with offset and label smoothing (train.py:715-721)
+    off, ls = 0.3, 0.1
+    xo = x + off
+    st = torch.stack((torch.nn.functional.softplus(xo).sum(1), torch.zeros(b), xo.sum(1), xo.gather(1, cols).sum(1)), 1)
+    rows, _ = kb.fused.rows_loss(st, lab_off, kb.lib.LOSS_BCE, ls, e)
+    assert rows.sum().item() == pytest.approx(ko.loss_bce(x, (1 - ls) * y + 1.0 / e, off).item(), rel=1e-5)
+
+
+def test_shard_partition_covers_entities():
+    for e, w in ((14541, 8), (10, 4), (7, 8), (4_600_000, 8)):
+        shards = [kb.fused.Shard.of_rank(e, r, w) for r in range(w)]
+        assert shards[0].e_lo == 0 and shards[-1].e_hi == e
+        for a, b in zip(shards, shards[1:]):
+            assert a.e_hi == b.e_lo and a.e_lo <= a.e_hi
+        assert not shards[0].distributed
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(1)
+        b, e = 9, 40
+        x = torch.randn(b, e, generator=gen) * 4
+        cols = torch.stack([torch.randperm(e, generator=gen)[:2].sort().values for _ in range(b)])
+        sh = kb.fused.Shard.of_rank(e, rank, world, dist.group.WORLD)
+        assert sh.distributed
+        xs = x[:, sh.e_lo:sh.e_hi]
+        in_sh = (cols >= sh.e_lo) & (cols < sh.e_hi)
+        labdot = torch.where(in_sh, x.gather(1, cols), torch.zeros(b, 2)).sum(1)
+        for loss in (kb.lib.LOSS_KL, kb.lib.LOSS_BCE):
+            if loss == kb.lib.LOSS_KL:
+                m = xs.max(1).values
+                st = torch.stack((m, torch.exp(xs - m[:, None]).sum(1), xs.sum(1), labdot), 1)
+            else:
+                st = torch.stack((torch.nn.functional.softplus(xs).sum(1), torch.zeros(b), xs.sum(1), labdot), 1)
+            full = kb.fused.combine_rowstats(st, loss, sh)
+            rows, lse = kb.fused.rows_loss(full, torch.arange(0, 2 * b + 1, 2), loss, 0.0, e)
+            if loss == kb.lib.LOSS_KL:
+                want = torch.logsumexp(x, 1) - x.gather(1, cols).sum(1) / 2 - np.log(2.0)
+                torch.testing.assert_close(lse, torch.logsumexp(x, 1), rtol=1e-5, atol=1e-5)
+            else:
+                want = torch.nn.functional.softplus(x).sum(1) - x.gather(1, cols).sum(1)
+            torch.testing.assert_close(rows, want, rtol=1e-5, atol=1e-4)
+        # integer rank counts add exactly across shards
+        t = x[:, 0:1]
+        cnt = torch.stack(((xs > t).sum(1), (xs == t).sum(1)), 1)
+        dist.all_reduce(cnt)
+        assert torch.equal(cnt, torch.stack(((x > t).sum(1), (x == t).sum(1)), 1))
+        out.put((rank, "ok"))
+    except Exception as ex:  # pragma: no cover
+        out.put((rank, repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_statistics_combine_over_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    res = dict(out.get() for _ in range(2))
+    assert res == {0: "ok", 1: "ok"}, res
