@@ -200,7 +200,7 @@ def main():
     shard = kb.fused.Shard.of_rank(E, rank, world, dist.group.WORLD) if world > 1 else None
     job = kb.TrainingJobKvsAll(model, opt, kb.KgeLoss.create("bce"), E, R, fused_path=True, math_mode=math_mode,
                                shard=shard)
-    job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph and world == 1)
+    job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph)  # NCCL all-reduces are captured too
     stepper = job.stepper
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -261,6 +261,8 @@ def main():
     roof = kernel_roofline(kb, stepper, math_mode, GB, E)
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---------------- cpu baseline: bounded sample of the same workload on the host cores -----------------
     cpu = cpu_reference(batches, graph, args.cpu_steps, 1, B)
@@ -282,6 +284,8 @@ def main():
                                    "of the reference's path (oracle/kge_oracle.py)"},
     }
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def kernel_roofline(kb, stepper, math_mode, B, E):

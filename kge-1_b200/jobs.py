@@ -312,6 +312,8 @@ class EntityRankingJob:
             filt_test = merge_sorted_csr(parts + self._filter_csr([self.test_indexes], s, p, o), 2 * b)
         scorer = model.get_scorer()
         table = model.get_o_embedder().embed_all()
+        if self.shard is not None:  # this rank scores its own entity rows; counts are all-reduced (exact integers)
+            table = table[self.shard.e_lo:self.shard.e_hi]
         counts = fused.rank_counts(scorer.kind, q, table, true_score, true_ent, filt, filt_test,
                                    scorer._math(table) if self.math_mode == lib.MATH_TF32 else lib.MATH_FP32,
                                    self.shard)

@@ -59,8 +59,6 @@ class FusedAllEntityStepper:
         # [e_lo, e_hi); row statistics, dQ and the dense table gradient are all-reduced over NVLink.  The (small)
         # tables and the optimizer state are replicated, so every rank applies the identical update.
         self.shard = shard or fused.Shard.full(self.E)
-        if self.shard.distributed and use_graph:
-            raise NotImplementedError("the sharded step issues NCCL collectives and is not graph-captured")
         self.ws = torch.empty(lib.load().kgeb_fused_workspace_bytes(rows, self.d, self.E, max(nnz_max, 1)),
                               dtype=torch.uint8, device=dev)
         self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(rows, max(self.d, self.dr)), dtype=torch.uint8,

@@ -1,0 +1,71 @@
+"""Run under torchrun on >= 2 GPUs (not collected by pytest):
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
+Checks that the entity-sharded training step and the sharded rank counts equal the single-GPU results."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import kgeb200 as kb  # noqa: E402
+from oracle import kge_oracle as ko  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    g = kb.graph.synthetic_graph("toy", seed=3)
+    e, r, d, b = g["num_entities"], g["num_relations"], 64, 128
+    idx = [ko.kvsall_index(g["train"], "sp"), ko.kvsall_index(g["train"], "po")]
+    rng = np.random.default_rng(1)
+    batches = []
+    for _ in range(3):
+        ids = rng.choice(len(idx[0][0]) + len(idx[1][0]), b, replace=False)
+        q, c, qt = ko.kvsall_collate(ids.tolist(), idx)
+        batches.append({"queries": torch.from_numpy(q), "label_coords": torch.from_numpy(c),
+                        "query_type_indexes": torch.from_numpy(qt)})
+    nnz_max = max(len(x["label_coords"]) for x in batches)
+    for math_mode, tol, use_graph in ((kb.lib.MATH_FP32, 1e-5, False), (kb.lib.MATH_BF16, 1e-5, False),
+                                      (kb.lib.MATH_BF16, 1e-5, True)):
+        torch.manual_seed(0)
+        ref = kb.KgeModel("complex", e, r, d).to(dev)
+        new = kb.KgeModel("complex", e, r, d).to(dev)
+        new.load_state_dict(ref.state_dict())
+        jr = kb.TrainingJobKvsAll(ref, kb.optim.create("Adagrad", ref.parameters(), lr=0.2), kb.KgeLoss.create("bce"),
+                                  e, r, math_mode=math_mode)
+        jr.enable_graph_step(b, nnz_max, use_graph=False)
+        sh = kb.fused.Shard.of_rank(e, rank, world, dist.group.WORLD)
+        jn = kb.TrainingJobKvsAll(new, kb.optim.create("Adagrad", new.parameters(), lr=0.2), kb.KgeLoss.create("bce"),
+                                  e, r, math_mode=math_mode, shard=sh)
+        jn.enable_graph_step(b, nnz_max, use_graph=use_graph)
+        for i, batch in enumerate(batches):
+            a, c = jr.step(i, batch), jn.step(i, batch)
+            assert abs(a.avg_loss - c.avg_loss) <= 1e-4 * abs(a.avg_loss), (a.avg_loss, c.avg_loss)
+            for x, y in ((ref.get_s_embedder().weight, new.get_s_embedder().weight),
+                         (ref.get_p_embedder().weight, new.get_p_embedder().weight)):
+                err = (x - y).abs().max().item()
+                # same tiles, different reduction grouping across shards: equal up to fp32 rounding of the sums
+                assert err <= 5e-3 if math_mode == kb.lib.MATH_BF16 else err <= 1e-4, (math_mode, use_graph, i, err)
+        if rank == 0:
+            print(f"sharded step == single-GPU step (math={math_mode}, graph={use_graph})")
+    # sharded filtered ranking: integer counts are exact under sharding
+    torch.manual_seed(0)
+    m = kb.KgeModel("transe", e, r, d).to(dev)
+    full = kb.EntityRankingJob(m, e, [g["train"], g["valid"]], g["test"], batch_size=64, hits_at_k_s=(1, 10))
+    shd = kb.EntityRankingJob(m, e, [g["train"], g["valid"]], g["test"], batch_size=64, hits_at_k_s=(1, 10),
+                              shard=kb.fused.Shard.of_rank(e, rank, world, dist.group.WORLD))
+    a, c = full.run(g["valid"]), shd.run(g["valid"])
+    for k in a["ranks"]:
+        assert torch.equal(a["ranks"][k], c["ranks"][k]), k
+    if rank == 0:
+        print("sharded filtered ranking == single-GPU ranking; MRR", a["metrics"]["mean_reciprocal_rank_filtered"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
