@@ -68,69 +68,100 @@ class FusedAllEntityStepper:
             self.mirror = torch.empty(self.E, self.d, dtype=torch.bfloat16, device=dev)
             lib.call("kgeb_to_bf16", lib.f32(self.ent.detach(), "table"), self.mirror.data_ptr(), self.ent.numel(),
                      lib.stream_ptr(self.ent))
-        self.kernel_launches_per_step = 0
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         if use_graph:
             self._capture()
 
-    # -- one step on the current stream ---------------------------------------------------------
-    def _launch(self):
+    # -- one step on the current stream, in three stages separated by the (optional) collectives ----------------
+    def _stage_forward(self):
         st = lib.stream_ptr(self.ent)
         model_id = lib.MODELS[self.model.model]
         ent, rel = self.ent.detach(), self.rel.detach()
-        n = 0
-        self.g_ent.zero_(); self.g_rel.zero_(); n += 2
-        lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
-                 rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st); n += 1
         sh = self.shard
-        ent_sh = ent[sh.e_lo:sh.e_hi]                       # this rank's entity rows (a view: no copy)
-        g_sh = self.g_ent[sh.e_lo:sh.e_hi]
-        mp = None if self.mirror is None else self.mirror[sh.e_lo:sh.e_hi].data_ptr()
-        lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent_sh.data_ptr(),
-                 sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls,
-                 self.offset, mp, self.rowstat.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 4
-        if sh.distributed:
-            self.rowstat.copy_(fused.combine_rowstats(self.rowstat, self.loss_kind, sh))
+        self.g_ent.zero_(); self.g_rel.zero_()
+        lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
+                 rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
+        lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
+                 ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
+                 self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset, self._mirror_ptr(), self.rowstat.data_ptr(),
+                 self.ws.data_ptr(), self.ws.numel(), st)
+
+    def _stage_backward(self):
+        st = lib.stream_ptr(self.ent)
+        ent = self.ent.detach()
+        sh = self.shard
         lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
-                 self.ls, self.E, 1.0 / self.batch_size, None, self.lse.data_ptr(), self.loss.data_ptr(), st); n += 1
-        lse = self.lse if self.loss_kind == lib.LOSS_KL else None
-        lib.call("kgeb_fused_bwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent_sh.data_ptr(),
-                 sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls,
-                 self.offset, None if lse is None else lse.data_ptr(), 1.0 / self.batch_size, None, mp,
-                 self.dQ.data_ptr(), g_sh.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st); n += 14
-        if sh.distributed:
-            import torch.distributed as dist
-            dist.all_reduce(self.dQ, group=sh.group)      # sum of the per-shard partial query gradients
-            dist.all_reduce(self.g_ent, group=sh.group)   # dense table gradient: each rank contributed its rows
+                 self.ls, self.E, 1.0 / self.batch_size, None, self.lse.data_ptr(), self.loss.data_ptr(), st)
+        lib.call("kgeb_fused_bwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
+                 ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
+                 self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
+                 self.lse.data_ptr() if self.loss_kind == lib.LOSS_KL else None, 1.0 / self.batch_size, None,
+                 self._mirror_ptr(), self.dQ.data_ptr(), self.g_ent[sh.e_lo:sh.e_hi].data_ptr(), self.ws.data_ptr(),
+                 self.ws.numel(), st)
+
+    def _stage_update(self):
+        st = lib.stream_ptr(self.ent)
+        model_id = lib.MODELS[self.model.model]
+        ent, rel = self.ent.detach(), self.rel.detach()
         lib.call("kgeb_query_bwd", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.dQ.data_ptr(), self.da.data_ptr(),
-                 self.dp.data_ptr(), st); n += 1
+                 self.dp.data_ptr(), st)
         lib.call("kgeb_scatter_add_rows", self.a_idx.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
-                 self.g_ent.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st); n += 8
+                 self.g_ent.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
         lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
-                 self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st); n += 8
+                 self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st)
         s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
         lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), ent.numel(), self.lr,
-                 self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st); n += 1
+                 self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st)
         lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), rel.numel(), self.lr,
-                 self.eps, 0.0, None, st); n += 1
-        self.kernel_launches_per_step = n
+                 self.eps, 0.0, None, st)
+
+    def _mirror_ptr(self):
+        return None if self.mirror is None else self.mirror[self.shard.e_lo:self.shard.e_hi].data_ptr()
+
+    def _exchange_stats(self):
+        if self.shard.distributed:   # per-row statistics of the shards -> global (max + rescaled sums for KL)
+            self.rowstat.copy_(fused.combine_rowstats(self.rowstat, self.loss_kind, self.shard))
+
+    def _exchange_grads(self):
+        if self.shard.distributed:
+            import torch.distributed as dist
+            dist.all_reduce(self.dQ, group=self.shard.group)      # sum of the per-shard partial query gradients
+            dist.all_reduce(self.g_ent, group=self.shard.group)   # dense table gradient: each rank filled its rows
+
+    def _launch(self):
+        self._stage_forward()
+        self._exchange_stats()
+        self._stage_backward()
+        self._exchange_grads()
+        self._stage_update()
+
+    # kernels of this library per step (bench.py gpu_launches): query build 1, fwd tiles + label dot + row sums +
+    # finalize + bf16(Q) 5, loss 1, bwd (label rows, bf16(Q), label weights, 2 tensor-tile kernels, partial reduce,
+    # presorted scatter 5, sorted scatter 8) 19, query bwd 1, two sorted scatters 16, two Adagrad 2
+    kernel_launches_per_step = 45
 
     def _capture(self):
-        # warm-up on a side stream (PyTorch's capture protocol), restoring the parameters afterwards
+        """CUDA graphs of the three stages; NCCL collectives (sharded mode) stay outside the graphs."""
         keep = [t.detach().clone() for t in (self.ent, self.rel, self.opt.state[self.ent]["sum"],
                                              self.opt.state[self.rel]["sum"])]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side):   # warm-up on a side stream (PyTorch's capture protocol)
             self._launch()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._launch()
+        self.graphs = []
+        stages = ([self._stage_forward, self._stage_backward, self._stage_update] if self.shard.distributed
+                  else [lambda: (self._stage_forward(), self._stage_backward(), self._stage_update())])
+        for fn in stages:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self.graphs.append(g)
+        self.graph = self.graphs[0]
         torch.cuda.synchronize()
-        with torch.no_grad():
+        with torch.no_grad():   # the warm-up / capture runs must not count as training steps
             for dst, src in zip((self.ent, self.rel, self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]),
                                 keep):
                 dst.copy_(src)
@@ -153,10 +184,16 @@ class FusedAllEntityStepper:
 
     def step(self) -> torch.Tensor:
         """Runs one training step; returns the (device) loss tensor of this batch."""
-        if self.graph is not None:
-            self.graph.replay()
-        else:
+        if self.graph is None:
             self._launch()
+        elif len(self.graphs) == 1:
+            self.graphs[0].replay()
+        else:
+            self.graphs[0].replay()
+            self._exchange_stats()
+            self.graphs[1].replay()
+            self._exchange_grads()
+            self.graphs[2].replay()
         for st in (self.opt.state[self.ent], self.opt.state[self.rel]):
             st["step"] += 1
         torch.autograd.graph.increment_version(self.ent)
