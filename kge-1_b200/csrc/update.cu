@@ -230,6 +230,182 @@ segment_sum_phase2(const int64_t* __restrict__ keys, const int32_t* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// small-n fast path of the dense scatter (n <= 32768 rows, the per-batch case): ids and positions packed into one
+// 32-bit word (id << PB | position), ONE single-block radix sort over the id bits only (stable, so positions stay
+// ascending within an id), then the two fixed-order phases working on the packed words -- 3 kernels instead of 11.
+// ------------------------------------------------------------------------------------------
+template <int ITEMS>
+__global__ void __launch_bounds__(1024)
+block_pack_sort_kernel(const void* idx, int idx64, int n, int pb, int kb, int presorted, uint32_t* __restrict__ packed) {
+  using Sort = cub::BlockRadixSort<uint32_t, 1024, ITEMS>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(smem_raw);
+  uint32_t keys[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int i = threadIdx.x * ITEMS + j;  // blocked arrangement: ascending positions
+    keys[j] = 0xFFFFFFFFu;                  // padding sorts last
+    if (i < n) keys[j] = ((uint32_t)load_index(idx, idx64, i) << pb) | (uint32_t)i;
+  }
+  if (!presorted) Sort(tmp).Sort(keys, pb, pb + kb);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int i = threadIdx.x * ITEMS + j;
+    if (i < n) packed[i] = keys[j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+packed_sum_phase1(const uint32_t* __restrict__ packed, int n, int pb, int d, const float* __restrict__ rows,
+                  float* __restrict__ dense, int64_t vocab, float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = (n + CHUNK - 1) / CHUNK;
+  const bool vec = (d & 3) == 0;
+  const uint32_t pmask = (1u << pb) - 1u;
+  for (int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks; ch += gridDim.x * (blockDim.x >> 5)) {
+    const int cb = ch * CHUNK;
+    const int m = min(CHUNK, n - cb);
+    uint32_t mine = 0xFFFFFFFFu;
+    if (lane < m) mine = packed[cb + lane];
+    const int64_t prev_key = cb > 0 ? (int64_t)(packed[cb - 1] >> pb) : -1;
+    const int64_t next_key = cb + m < n ? (int64_t)(packed[cb + m] >> pb) : -2;
+    int64_t key[CHUNK];
+    int prw[CHUNK];
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j) {
+      const uint32_t w = __shfl_sync(0xffffffffu, mine, j);
+      key[j] = (int64_t)(w >> pb);
+      prw[j] = (int)(w & pmask);
+    }
+    for (int cg = 0; cg < d; cg += 128) {
+      const int c0 = cg + lane * 4;
+      if (c0 >= d) continue;
+      float4 v[CHUNK];
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < m) {
+          const float* src = rows + (int64_t)prw[j] * d + c0;
+          if (vec) {
+            v[j] = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            v[j].x = src[0];
+            if (c0 + 1 < d) v[j].y = src[1];
+            if (c0 + 2 < d) v[j].z = src[2];
+            if (c0 + 3 < d) v[j].w = src[3];
+          }
+        }
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool from_prev = (prev_key == key[0]);
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j) {
+        if (j < m) {
+          acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+          const bool last_of_chunk = (j == m - 1);
+          const bool run_ends = last_of_chunk || (key[j + 1 < CHUNK ? j + 1 : j] != key[j]);
+          if (run_ends) {
+            const bool to_next = last_of_chunk && (next_key == key[j]);
+            if (!from_prev && !to_next) {
+              if (key[j] >= 0 && key[j] < vocab) seg_add(acc, c0, d, dense + key[j] * d + c0);
+            } else {
+              seg_store(acc, c0, d, part + (((int64_t)ch * 2 + (from_prev ? 0 : 1)) * d) + c0, vec);
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            from_prev = false;
+          }
+        }
+      }
+    }
+  }
+}
+
+// one warp per chunk whose last run STARTS a segment that continues into the following chunks: it finds the end of
+// the segment by binary search on the sorted ids and adds the partials in chunk order
+__global__ void __launch_bounds__(256)
+packed_sum_phase2(const uint32_t* __restrict__ packed, int n, int pb, int d, float* __restrict__ dense, int64_t vocab,
+                  const float* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = (n + CHUNK - 1) / CHUNK;
+  const bool vec = (d & 3) == 0;
+  for (int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks; ch += gridDim.x * (blockDim.x >> 5)) {
+    const int cb = ch * CHUNK;
+    const int m = min(CHUNK, n - cb);
+    if (cb + m >= n) continue;                                  // nothing follows the last chunk
+    const uint32_t kq = packed[cb + m - 1] >> pb;               // id of the chunk's last run
+    if ((packed[cb + m] >> pb) != kq) continue;                 // it does not continue
+    if ((packed[cb] >> pb) == kq && cb > 0 && (packed[cb - 1] >> pb) == kq) continue;  // not the segment's first chunk
+    int lo = cb + m, hi = n;                                    // first position with id > kq
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((packed[mid] >> pb) <= kq) lo = mid + 1; else hi = mid;
+    }
+    const int c1 = (lo - 1) / CHUNK;
+    if ((int64_t)kq >= vocab) continue;
+    for (int cg = 0; cg < d; cg += 128) {
+      const int c0 = cg + lane * 4;
+      if (c0 >= d) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = ch; c <= c1; c += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c + j <= c1) {
+            const float* src = part + (((int64_t)(c + j) * 2 + ((c + j) == ch ? 1 : 0)) * d) + c0;
+            if (vec && c0 + 3 < d) {
+              v[j] = *reinterpret_cast<const float4*>(src);
+            } else {
+              v[j].x = src[0];
+              if (c0 + 1 < d) v[j].y = src[1];
+              if (c0 + 2 < d) v[j].z = src[2];
+              if (c0 + 3 < d) v[j].w = src[3];
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+      }
+      seg_add(acc, c0, d, dense + (int64_t)kq * d + c0);
+    }
+  }
+}
+
+static int bits_for(int64_t x) {  // smallest b with 2^b >= x
+  int b = 1;
+  while (b < 62 && ((int64_t)1 << b) < x) ++b;
+  return b;
+}
+
+// returns -1 when the packed path does not apply
+static int scatter_small(const void* idx, int idx64, const float* rows, int64_t n, int d, float* dense, int64_t vocab,
+                         ScatterWs& w, cudaStream_t st, bool presorted) {
+  const int pb = bits_for(n), kb = bits_for(vocab);
+  if (n > 32768 || pb + kb > 32) return -1;
+  uint32_t* packed = reinterpret_cast<uint32_t*>(w.keys_in);
+  if (n <= 8192) {
+    using Sort = cub::BlockRadixSort<uint32_t, 1024, 8>;
+    const int smem = (int)sizeof(typename Sort::TempStorage);
+    cudaError_t e = cudaFuncSetAttribute(block_pack_sort_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e, "block sort smem attribute");
+    block_pack_sort_kernel<8><<<1, 1024, smem, st>>>(idx, idx64, (int)n, pb, kb, presorted, packed);
+  } else {
+    using Sort = cub::BlockRadixSort<uint32_t, 1024, 32>;
+    const int smem = (int)sizeof(typename Sort::TempStorage);
+    cudaError_t e = cudaFuncSetAttribute(block_pack_sort_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e, "block sort smem attribute");
+    block_pack_sort_kernel<32><<<1, 1024, smem, st>>>(idx, idx64, (int)n, pb, kb, presorted, packed);
+  }
+  const int nchunks = (int)((n + CHUNK - 1) / CHUNK);
+  int blocks = (nchunks + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  packed_sum_phase1<<<blocks, 256, 0, st>>>(packed, (int)n, pb, d, rows, dense, vocab, w.part);
+  packed_sum_phase2<<<blocks, 256, 0, st>>>(packed, (int)n, pb, d, dense, vocab, w.part);
+  KGEB_LAUNCH_CHECK("packed scatter");
+  return KGEB_OK;
+}
+
 template <bool DENSE>
 static int segment_sums(ScatterWs& w, int64_t n, int d, const float* rows, float* dense, int64_t vocab,
                         int64_t* uniq_ids, float* uniq_rows, cudaStream_t st) {
@@ -372,7 +548,9 @@ int kgeb_scatter_add_rows(const void* idx, int idx64, const float* rows, int64_t
   ScatterWs w;
   KGEB_REQUIRE(carve(workspace, workspace_bytes, n, d, w), "scatter_add_rows: workspace too small");
   cudaStream_t st = as_stream(stream);
-  int rc = sort_and_segment(idx, idx64, n, vocab, w, nullptr, st);
+  int rc = scatter_small(idx, idx64, rows, n, d, dense, vocab, w, st, false);
+  if (rc >= 0) return rc;
+  rc = sort_and_segment(idx, idx64, n, vocab, w, nullptr, st);
   if (rc) return rc;
   return segment_sums<true>(w, n, d, rows, dense, vocab, nullptr, nullptr, st);
 }
@@ -383,7 +561,9 @@ int scatter_add_rows_presorted(const int64_t* keys, const float* rows, int64_t n
   if (n == 0) return KGEB_OK;
   kgeb::ScatterWs w;
   KGEB_REQUIRE(kgeb::carve(workspace, workspace_bytes, n, d, w), "scatter_add_rows(presorted): workspace too small");
-  int rc = kgeb::sort_and_segment(keys, 1, n, vocab, w, nullptr, st, true);
+  int rc = kgeb::scatter_small(keys, 1, rows, n, d, dense, vocab, w, st, true);
+  if (rc >= 0) return rc;
+  rc = kgeb::sort_and_segment(keys, 1, n, vocab, w, nullptr, st, true);
   if (rc) return rc;
   return kgeb::segment_sums<true>(w, n, d, rows, dense, vocab, nullptr, nullptr, st);
 }
