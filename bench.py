@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--math", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--cpu-steps", type=int, default=8, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-calls", action="store_true", help="print GPU time per C-ABI call of one step and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -204,6 +205,9 @@ def main():
     stepper = job.stepper
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    if args.profile_calls:
+        profile_calls(kb, job, stepper, batches)
+        return
 
     def barrier():
         torch.cuda.synchronize()
@@ -286,6 +290,37 @@ def main():
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def profile_calls(kb, job, stepper, batches):
+    """GPU time of every C-ABI call of a step (sync + CUDA events around each call; eager mode)."""
+    import collections
+    acc = collections.OrderedDict()
+    orig = kb.lib.call
+
+    def timed(name, *a):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); orig(name, *a); e1.record()
+        torch.cuda.synchronize()
+        key = name + ("" if name != "kgeb_fused_bwd" else ("(dQ+dTable)"))
+        acc.setdefault(key, []).append(e0.elapsed_time(e1) * 1e3)
+
+    for m in (kb.lib, kb.trainer.lib):
+        m.call = timed
+    for i in range(6):
+        stepper.set_inputs(*job.device_inputs(batches[i]))
+        stepper._launch()
+        if i == 1:
+            acc.clear()
+    for m in (kb.lib, kb.trainer.lib):
+        m.call = orig
+    tot = 0.0
+    for k, v in acc.items():
+        per_step = float(np.sum(v)) / 4
+        tot += per_step
+        print(f"{per_step:9.1f} us/step  {len(v) // 4} call(s)  {k}")
+    print(f"{tot:9.1f} us/step  total of C-ABI calls")
 
 
 def kernel_roofline(kb, stepper, math_mode, B, E):

@@ -26,11 +26,13 @@ struct ScatterWs {
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 static size_t cub_temp_bytes(int64_t n) {
-  size_t a = 0, b = 0;
+  size_t a = 0, b = 0, c = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, c, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const int64_t*)nullptr, (int64_t*)nullptr, (const int32_t*)nullptr,
                                   (int32_t*)nullptr, (int)n);
   cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
-  return a > b ? a : b;
+  a = a > b ? a : b;
+  return a > c ? a : c;
 }
 
 static size_t part_bytes(int64_t n, int d) { return align256((size_t)((n + 7) / 8) * 2 * (size_t)d * 4); }
@@ -336,10 +338,20 @@ packed_sum_phase2(const uint32_t* __restrict__ packed, int n, int pb, int d, flo
     const uint32_t kq = packed[cb + m - 1] >> pb;               // id of the chunk's last run
     if ((packed[cb + m] >> pb) != kq) continue;                 // it does not continue
     if ((packed[cb] >> pb) == kq && cb > 0 && (packed[cb - 1] >> pb) == kq) continue;  // not the segment's first chunk
-    int lo = cb + m, hi = n;                                    // first position with id > kq
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if ((packed[mid] >> pb) <= kq) lo = mid + 1; else hi = mid;
+    // first position with id > kq: 32-ary search, one probe per lane and round
+    int lo = cb + m, hi = n;
+    while (hi - lo > 0) {
+      const int span = hi - lo;
+      const int step = (span + 31) / 32;
+      const int probe = min(lo + (lane + 1) * step - 1, hi - 1);   // last position of this lane's slice
+      const bool gt = (packed[probe] >> pb) > kq;
+      const unsigned mask = __ballot_sync(0xffffffffu, gt);
+      if (mask == 0) { lo = hi; break; }
+      const int first = __ffs(mask) - 1;                           // slice containing the boundary
+      const int nlo = lo + first * step;
+      hi = min(lo + (first + 1) * step - 1, hi - 1);                // its last position has id > kq
+      lo = nlo;
+      if (step == 1) { lo = hi; break; }
     }
     const int c1 = (lo - 1) / CHUNK;
     if ((int64_t)kq >= vocab) continue;
@@ -378,11 +390,16 @@ static int bits_for(int64_t x) {  // smallest b with 2^b >= x
   return b;
 }
 
+__global__ void pack_keys_kernel(const void* idx, int idx64, int n, int pb, uint32_t* __restrict__ packed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) packed[i] = ((uint32_t)load_index(idx, idx64, i) << pb) | (uint32_t)i;
+}
+
 // returns -1 when the packed path does not apply
 static int scatter_small(const void* idx, int idx64, const float* rows, int64_t n, int d, float* dense, int64_t vocab,
                          ScatterWs& w, cudaStream_t st, bool presorted) {
   const int pb = bits_for(n), kb = bits_for(vocab);
-  if (n > 32768 || pb + kb > 32) return -1;
+  if (n > (1 << 22) || pb + kb > 32) return -1;
   uint32_t* packed = reinterpret_cast<uint32_t*>(w.keys_in);
   if (n <= 8192) {
     using Sort = cub::BlockRadixSort<uint32_t, 1024, 8>;
@@ -391,11 +408,14 @@ static int scatter_small(const void* idx, int idx64, const float* rows, int64_t 
     if (e != cudaSuccess) return cuda_status(e, "block sort smem attribute");
     block_pack_sort_kernel<8><<<1, 1024, smem, st>>>(idx, idx64, (int)n, pb, kb, presorted, packed);
   } else {
-    using Sort = cub::BlockRadixSort<uint32_t, 1024, 32>;
-    const int smem = (int)sizeof(typename Sort::TempStorage);
-    cudaError_t e = cudaFuncSetAttribute(block_pack_sort_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_status(e, "block sort smem attribute");
-    block_pack_sort_kernel<32><<<1, 1024, smem, st>>>(idx, idx64, (int)n, pb, kb, presorted, packed);
+    // multi-block: coalesced pack, then a keys-only device radix sort over the id bits (stable -> positions ascending)
+    uint32_t* tmp = reinterpret_cast<uint32_t*>(w.keys_out);
+    pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, idx64, (int)n, pb, presorted ? packed : tmp);
+    if (!presorted) {
+      size_t bytes = w.cub_bytes;
+      cudaError_t e = cub::DeviceRadixSort::SortKeys(w.cub_tmp, bytes, tmp, packed, (int)n, pb, pb + kb, st);
+      if (e != cudaSuccess) return cuda_status(e, "radix sort (packed)");
+    }
   }
   const int nchunks = (int)((n + CHUNK - 1) / CHUNK);
   int blocks = (nchunks + 7) / 8;
