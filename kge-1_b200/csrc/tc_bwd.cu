@@ -32,7 +32,8 @@ constexpr int MAX_STR = 8;                       // streamed-tile ring depth
 constexpr int EPQ = 4;                            // epilogue warps per TMEM lane quadrant (latency hiding)
 constexpr int NUM_EPI_THREADS = 4 * EPQ * 32;     // 512
 constexpr int NUM_THREADS = 128 + NUM_EPI_THREADS;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-19: epilogue
-constexpr int COLS_PER_WARP = STR_ROWS / EPQ;    // 16 S-columns per epilogue warp
+constexpr int NUM_GROUP_THREADS = NUM_EPI_THREADS / 2;  // two epilogue groups ping-pong on alternate streamed tiles
+constexpr int COLS_PER_WARP = STR_ROWS / (EPQ / 2);     // 32 S-columns per warp of a group
 constexpr int SMEM_BUDGET = 227 * 1024;
 
 struct Params {
@@ -90,8 +91,8 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
     mbar_init(res_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], NUM_EPI_THREADS);
-      mbar_init(&g_full[b], NUM_EPI_THREADS);
+      mbar_init(&s_empty[b], NUM_GROUP_THREADS);
+      mbar_init(&g_full[b], NUM_GROUP_THREADS);
       mbar_init(&g_empty[b], 1);
     }
     mbar_init(o_full, 1);
@@ -130,87 +131,93 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+    // ================================ MMA1 issuer: S = RES * STR^T ================================
+    // One thread per GEMM: a single issuing thread (barrier probes + descriptor arithmetic + 12 tcgen05.mma per tile)
+    // was the critical path of the whole kernel; MMA1 and MMA2 only meet through mbarriers, so they are issued by two
+    // threads that run ahead of each other independently.
     if (lane == 0) {
-      const uint32_t idesc1 = make_idesc(RES_ROWS, STR_ROWS, 0, 0, Elem<BF16>::kFmt);  // S = RES * STR^T (K, K)
-      const uint32_t idesc2 = make_idesc(RES_ROWS, p.d, 0, 1, Elem<BF16>::kFmt);       // OUT += G * STR  (K, MN)
-      int slot1 = 0, slot2 = 0;          // ring slot of the next MMA1 / MMA2
-      uint32_t ph1 = 0;                  // parity for str_full at slot1
-      uint32_t sph[2] = {0, 0}, gph[2] = {0, 0}, rphase = 0, ophase = 0;
-      int sbuf = 0, gbuf = 0;
-
-      auto issue_mma1 = [&](int slot, int buf) {
-        const uint32_t acc = tmem_base + S_COL + (uint32_t)(buf * STR_ROWS);
-        for (int k = 0; k < KS; ++k) {
-          const uint32_t ra = smem_u32(res_smem + (size_t)k * RES_SLAB);
-          const uint32_t sa = smem_u32(str_smem + ((size_t)slot * KS + k) * STR_SLAB);
-#pragma unroll
-          for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk)
-            umma<BF16>(acc, make_desc(ra + kk * 32, 16, 1024), make_desc(sa + kk * 32, 16, 1024), idesc1,
-                       (k | kk) != 0);
-        }
-      };
-      auto issue_mma2 = [&](int slot, int buf, bool first) {
-        const uint32_t acc = tmem_base + O_COL;
-        const uint32_t ga = smem_u32(g_smem + (size_t)buf * G_BYTES);
-        const uint32_t sa = smem_u32(str_smem + (size_t)slot * KS * STR_SLAB);
-#pragma unroll
-        for (int km = 0; km < STR_ROWS / UMMA_K; ++km) {
-          // A: G K-major -- UMMA_K columns = 32 B inside the 128 B row of K-slab (km*UMMA_K / SLAB_K).
-          // B: the STR tile MN-major -- UMMA_K K-rows of 128 B (8-row groups 1024 B apart = SBO); N chunks of one
-          //    128 B row (SLAB_K columns) are one slab apart (LBO = STR_SLAB).
-          const int kcol = km * UMMA_K;
-          const uint64_t ad = make_desc(ga + (kcol / SLAB_K) * RES_SLAB + (kcol % SLAB_K) * Elem<BF16>::kBytes, 16, 1024);
-          const uint64_t bd = make_desc(sa + kcol * 128, STR_SLAB, 1024);
-          umma<BF16>(acc, ad, bd, idesc2, !(first && km == 0));
-        }
-      };
-
+      const uint32_t idesc1 = make_idesc(RES_ROWS, STR_ROWS, 0, 0, Elem<BF16>::kFmt);  // (K-major, K-major)
+      const uint64_t dbase = make_desc(0, 16, 1024);
+      int slot = 0, sbuf = 0;
+      uint32_t ph = 0, sph[2] = {0, 0}, rphase = 0;
+      const uint32_t res0 = smem_u32(res_smem), str0 = smem_u32(str_smem);
       for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         const int64_t ch = job / p.n_res_blocks;
         const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
-        const int64_t nu = u1 - u0;
         mbar_wait(res_full, rphase);
         rphase ^= 1;
+        for (int64_t u = u0; u < u1; ++u) {
+          mbar_wait(&str_full[slot], ph);
+          mbar_wait(&s_empty[sbuf], sph[sbuf] ^ 1);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + S_COL + (uint32_t)(sbuf * STR_ROWS);
+          for (int k = 0; k < KS; ++k) {
+            const uint64_t ra = dbase + (uint64_t)((res0 + (uint32_t)k * RES_SLAB) >> 4);
+            const uint64_t sa = dbase + (uint64_t)((str0 + (uint32_t)(slot * KS + k) * STR_SLAB) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk)   // +32 B (= 2 in descriptor units) per K step
+              umma<BF16>(acc, ra + 2 * kk, sa + 2 * kk, idesc1, (k | kk) != 0);
+          }
+          umma_commit(&s_full[sbuf]);
+          sph[sbuf] ^= 1;
+          sbuf ^= 1;
+          if (++slot == NSTR) { slot = 0; ph ^= 1; }
+        }
+        umma_commit(res_empty);   // all MMA1 of the job issued before this commit have read the resident block
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ MMA2 issuer: OUT += G * STR ================================
+    if (lane == 0) {
+      const uint32_t idesc2 = make_idesc(RES_ROWS, p.d, 0, 1, Elem<BF16>::kFmt);       // (K-major, MN-major)
+      const uint64_t abase = make_desc(0, 16, 1024);
+      const uint64_t bbase = make_desc(0, STR_SLAB, 1024);
+      int slot = 0, gbuf = 0;
+      uint32_t gph[2] = {0, 0}, ophase = 0;
+      const uint32_t g0 = smem_u32(g_smem), str0 = smem_u32(str_smem);
+      const uint32_t acc = tmem_base + O_COL;
+      for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const int64_t ch = job / p.n_res_blocks;
+        const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
         mbar_wait(o_empty, ophase ^ 1);  // previous job's accumulator has been flushed
-        tc_fence_after();
-        // software pipeline: MMA1(u+1) is issued before MMA2(u) so the tensor pipe works while the epilogue of u runs
-        for (int64_t i = 0; i <= nu; ++i) {
-          if (i < nu) {
-            mbar_wait(&str_full[slot1], ph1);
-            mbar_wait(&s_empty[sbuf], sph[sbuf] ^ 1);
-            tc_fence_after();
-            issue_mma1(slot1, sbuf);
-            umma_commit(&s_full[sbuf]);
-            sph[sbuf] ^= 1;
-            sbuf ^= 1;
-            if (++slot1 == NSTR) { slot1 = 0; ph1 ^= 1; }
+        for (int64_t u = u0; u < u1; ++u) {
+          mbar_wait(&g_full[gbuf], gph[gbuf]);
+          tc_fence_after();
+          const uint32_t ga = g0 + (uint32_t)gbuf * G_BYTES;
+          const uint32_t sa = str0 + (uint32_t)(slot * KS) * STR_SLAB;
+#pragma unroll
+          for (int km = 0; km < STR_ROWS / UMMA_K; ++km) {
+            // A: G K-major -- UMMA_K columns = 32 B inside the 128 B row of K-slab (km*UMMA_K / SLAB_K).
+            // B: the STR tile MN-major -- UMMA_K K-rows of 128 B (8-row groups 1024 B apart = SBO); N chunks of one
+            //    128 B row (SLAB_K columns) are one slab apart (LBO = STR_SLAB).
+            const int kcol = km * UMMA_K;
+            const uint64_t ad = abase + (uint64_t)((ga + (kcol / SLAB_K) * RES_SLAB + (kcol % SLAB_K) * Elem<BF16>::kBytes) >> 4);
+            const uint64_t bd = bbase + (uint64_t)((sa + kcol * 128) >> 4);
+            umma<BF16>(acc, ad, bd, idesc2, !(u == u0 && km == 0));
           }
-          if (i > 0) {
-            mbar_wait(&g_full[gbuf], gph[gbuf]);
-            tc_fence_after();
-            issue_mma2(slot2, gbuf, i == 1);
-            umma_commit(&str_empty[slot2]);  // streamed tile free once MMA2 has read it
-            umma_commit(&g_empty[gbuf]);
-            gph[gbuf] ^= 1;
-            gbuf ^= 1;
-            if (++slot2 == NSTR) slot2 = 0;
-          }
+          umma_commit(&str_empty[slot]);  // streamed tile free once MMA2 has read it (MMA1 of it finished long ago)
+          umma_commit(&g_empty[gbuf]);
+          gph[gbuf] ^= 1;
+          gbuf ^= 1;
+          if (++slot == NSTR) slot = 0;
         }
         umma_commit(o_full);      // accumulator complete
-        umma_commit(res_empty);   // resident block may be replaced
         ophase ^= 1;
       }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue (16 warps: lane quadrant x column part) ================================
+    // ================================ epilogue ================================
+    // 16 warps = 2 groups x (4 lane quadrants x 2 column halves).  Group g owns S/G buffer g, i.e. every other
+    // streamed tile: while one group waits on its barriers / TMEM loads the other keeps the MUFU and issue slots busy.
     const int ew = warp - 4;
     const int quad = ew & 3;                               // == warp % 4 : TMEM lane quadrant this warp may access
-    const int part = ew >> 2;                              // which 16 S-columns of the 64
+    const int part = ew >> 2;                              // 0..3
+    const int group = part >> 1;                           // buffer / tile parity served by this warp
+    const int sub = part & 1;                              // which 32 of the 64 S-columns
     const int trow = quad * 32 + lane;                     // resident row (TMEM lane) of this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t sph[2] = {0, 0}, gph[2] = {0, 0}, ophase = 0;
-    int sbuf = 0, gbuf = 0;
+    uint32_t sph = 0, gph = 0, ophase = 0;                 // phases of this group's buffers
+    int64_t gunit = 0;                                     // global tile counter (buffers alternate across jobs too)
     for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int64_t rb = job % p.n_res_blocks, ch = job / p.n_res_blocks;
       const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
@@ -220,18 +227,19 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         my_rs = p.inv_batch * (HAS_RS ? p.row_scale[res_row] : 1.f);
         if (LOSS == KGEB_LOSS_KL) my_lse = p.lse[res_row];
       }
-      for (int64_t u = u0; u < u1; ++u) {
-        mbar_wait(&s_full[sbuf], sph[sbuf]);
-        sph[sbuf] ^= 1;
+      for (int64_t u = u0; u < u1; ++u, ++gunit) {
+        if ((int)(gunit & 1) != group) continue;
+        const int bufi = group;
+        mbar_wait(&s_full[bufi], sph);
+        sph ^= 1;
         tc_fence_after();
         float v[COLS_PER_WARP];
-        tmem_ld16(lane_addr + S_COL + (uint32_t)(sbuf * STR_ROWS + part * COLS_PER_WARP), v);
+        tmem_ld32(lane_addr + S_COL + (uint32_t)(bufi * STR_ROWS + sub * COLS_PER_WARP), v);
         tc_fence_before();
-        mbar_arrive(&s_empty[sbuf]);  // S values are in registers: MMA1 of the tile after next may overwrite them
-        sbuf ^= 1;
+        mbar_arrive(&s_empty[bufi]);  // S values are in registers: MMA1 of the tile after next may overwrite them
         // Rows / columns beyond the matrices were zero-filled by TMA, so whatever finite G they get multiplies
         // zeros in MMA2; only the parameter loads are clamped.
-        const int64_t qbase = u * STR_ROWS + part * COLS_PER_WARP;
+        const int64_t qbase = u * STR_ROWS + sub * COLS_PER_WARP;
 #pragma unroll
         for (int c = 0; c < COLS_PER_WARP; ++c) {
           float lse = my_lse, rs = my_rs;
@@ -244,34 +252,31 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           const float gval = (LOSS == KGEB_LOSS_KL) ? __expf(x - lse) : sigmoidf(x + p.offset) - p.ls_add;
           v[c] = rs * gval;
         }
-        mbar_wait(&g_empty[gbuf], gph[gbuf] ^ 1);  // MMA2 of two tiles ago has finished reading this buffer
-        uint8_t* gb = g_smem + (size_t)gbuf * G_BYTES;
+        mbar_wait(&g_empty[bufi], gph ^ 1);  // MMA2 of this buffer's previous tile has finished reading it
+        uint8_t* gb = g_smem + (size_t)bufi * G_BYTES;
         if (BF16) {
-          // row trow of the single K-slab: this warp's 16 bf16 = chunks 2*part, 2*part+1 (16 B each), 128-byte swizzle
+          // row trow of the single K-slab: this warp's 32 bf16 = chunks 4*sub .. 4*sub+3 (16 B each), 128-byte swizzle
           uint8_t* rowp = gb + (size_t)trow * 128;
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
+          for (int k = 0; k < 4; ++k) {
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[k * 8 + j * 2 + 1]), "f"(v[k * 8 + j * 2]));
-            const int ck = part * 2 + k;
+            const int ck = sub * 4 + k;
             *reinterpret_cast<uint4*>(rowp + ((ck ^ (trow & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         } else {
-          // TF32: 64 fp32 = two K-slabs of 32; this warp's 16 columns = chunks 4*(part&1).. of slab part>>1
-          uint8_t* rowp = gb + (size_t)(part >> 1) * RES_SLAB + (size_t)trow * 128;
+          // TF32: 64 fp32 = two K-slabs of 32 columns; this warp's 32 columns are slab `sub`
+          uint8_t* rowp = gb + (size_t)sub * RES_SLAB + (size_t)trow * 128;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int ck = (part & 1) * 4 + k;
+          for (int ck = 0; ck < 8; ++ck)
             *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) =
-                make_float4(v[k * 4], v[k * 4 + 1], v[k * 4 + 2], v[k * 4 + 3]);
-          }
+                make_float4(v[ck * 4], v[ck * 4 + 1], v[ck * 4 + 2], v[ck * 4 + 3]);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(&g_full[gbuf]);
-        gph[gbuf] ^= 1;
-        gbuf ^= 1;
+        mbar_arrive(&g_full[bufi]);
+        gph ^= 1;
       }
       // flush the job's accumulator: 16-column groups are dealt round-robin to the column parts
       mbar_wait(o_full, ophase);
