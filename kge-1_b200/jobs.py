@@ -153,12 +153,25 @@ class TrainingJobKvsAll(TrainingJob):
         lab_off, lab_col = fused.csr_from_coords(coords, len(q))
         return a, p, rc, lab_off, lab_col
 
+    def collate_packed(self, batch: dict) -> dict:
+        """Host-side collate for the graph-captured step (what a DataLoader worker does instead of train.py:590-677's
+        tensors): query rows, per-row combine flags and the label CSR laid out in one pinned buffer."""
+        from .trainer import kvsall_rows
+        q, qt = batch["queries"], batch["query_type_indexes"]
+        a, p, rc = kvsall_rows(q, qt)
+        lab_off, lab_col = fused.csr_from_coords(batch["label_coords"], len(q))
+        return {"packed": self.stepper.pack_host_batch(a, p, rc, lab_off, lab_col), "size": len(q)}
+
     def step(self, batch_index: int, batch: dict) -> ProcessBatchResult:
-        if self.stepper is None or len(batch["queries"]) != self.stepper.rows:
+        size = batch["size"] if "packed" in batch else len(batch["queries"])
+        if self.stepper is None or size != self.stepper.rows:
             return super().step(batch_index, batch)
         for f in self.pre_batch_hooks:
             f(self)
-        self.stepper.set_inputs(*self.device_inputs(batch))
+        if "packed" in batch:
+            self.stepper.set_packed(batch["packed"])
+        else:
+            self.stepper.set_inputs(*self.device_inputs(batch))
         loss = self.stepper.step()
         value = loss.item()          # the reference reads the loss back every batch too (train.py:747)
         return ProcessBatchResult(value, self.stepper.rows, value)

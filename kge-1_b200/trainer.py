@@ -39,12 +39,15 @@ class FusedAllEntityStepper:
         self.lr, self.eps = float(group["lr"]), float(group["eps"])
         f32 = dict(dtype=torch.float32, device=dev)
         i64 = dict(dtype=torch.int64, device=dev)
-        # static inputs
-        self.a_idx = torch.zeros(rows, **i64)
-        self.p_idx = torch.zeros(rows, **i64)
-        self.row_combine = torch.zeros(rows, dtype=torch.int32, device=dev)
-        self.lab_off = torch.zeros(rows + 1, **i64)
-        self.lab_col = torch.zeros(max(nnz_max, 1), **i64)
+        # static inputs: ONE contiguous byte buffer so that a packed host batch arrives with a single H2D copy
+        #   int64 [a_idx (rows) | p_idx (rows) | lab_off (rows+1) | lab_col (nnz_max)]  then  int32 [row_combine (rows)]
+        nz = max(nnz_max, 1)
+        self.n_i64 = 3 * rows + 1 + nz
+        self.input_bytes = torch.zeros(self.n_i64 * 8 + rows * 4, dtype=torch.uint8, device=dev)
+        v64 = self.input_bytes[: self.n_i64 * 8].view(torch.int64)
+        self.a_idx, self.p_idx = v64[:rows], v64[rows:2 * rows]
+        self.lab_off, self.lab_col = v64[2 * rows:3 * rows + 1], v64[3 * rows + 1:]
+        self.row_combine = self.input_bytes[self.n_i64 * 8:].view(torch.int32)
         # static intermediates / outputs
         self.Q = torch.empty(rows, self.d, **f32)
         self.dQ = torch.empty(rows, self.d, **f32)
@@ -181,6 +184,25 @@ class FusedAllEntityStepper:
         if k > self.nnz_max:
             raise ValueError(f"batch has {k} labels, stepper was built for at most {self.nnz_max}")
         self.lab_col[:k].copy_(lab_col, non_blocking=True)
+
+    def pack_host_batch(self, a_idx, p_idx, row_combine, lab_off, lab_col) -> torch.Tensor:
+        """Collate-side helper: one pinned byte buffer in the layout of the static inputs (see __init__)."""
+        buf = torch.zeros(self.input_bytes.numel(), dtype=torch.uint8).pin_memory()
+        v64 = buf[: self.n_i64 * 8].view(torch.int64)
+        r = self.rows
+        v64[:r] = a_idx
+        v64[r:2 * r] = p_idx
+        v64[2 * r:3 * r + 1] = lab_off
+        k = lab_col.numel()
+        if k > self.nnz_max:
+            raise ValueError(f"batch has {k} labels, stepper was built for at most {self.nnz_max}")
+        v64[3 * r + 1:3 * r + 1 + k] = lab_col
+        buf[self.n_i64 * 8:].view(torch.int32)[:] = row_combine
+        return buf
+
+    def set_packed(self, packed: torch.Tensor):
+        """One H2D copy of a packed (pinned) host batch into the static inputs."""
+        self.input_bytes.copy_(packed, non_blocking=True)
 
     def step(self) -> torch.Tensor:
         """Runs one training step; returns the (device) loss tensor of this batch."""

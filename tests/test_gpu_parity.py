@@ -348,3 +348,21 @@ def test_graph_captured_stepper_matches_autograd_flow(kb, use_graph):
         assert c.avg_loss == pytest.approx(a.total_loss, rel=1e-5)
         close(new.get_s_embedder().weight, ref.get_s_embedder().weight, rtol=1e-5, what=f"entity table step {i}")
         close(new.get_p_embedder().weight, ref.get_p_embedder().weight, rtol=1e-5, what=f"relation table step {i}")
+
+
+def test_packed_host_batches_equal_dict_batches(kb):
+    g = kb.graph.synthetic_graph("toy", seed=3)
+    e, r, d, b = g["num_entities"], g["num_relations"], 32, 64
+    idx = [ko.kvsall_index(g["train"], "sp"), ko.kvsall_index(g["train"], "po")]
+    ids = np.random.default_rng(2).choice(len(idx[0][0]) + len(idx[1][0]), b, replace=False)
+    q, c, qt = ko.kvsall_collate(ids.tolist(), idx)
+    batch = {"queries": T(q), "label_coords": T(c), "query_type_indexes": T(qt)}
+    res = []
+    for packed in (False, True):
+        torch.manual_seed(0)
+        m = kb.KgeModel("distmult", e, r, d).cuda()
+        job = kb.TrainingJobKvsAll(m, kb.optim.create("Adagrad", m.parameters(), lr=0.2), kb.KgeLoss.create("kl"), e, r)
+        job.enable_graph_step(b, len(c) + 5)
+        out = job.step(0, job.collate_packed(batch) if packed else batch)
+        res.append((out.avg_loss, m.get_s_embedder().weight.detach().clone()))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
