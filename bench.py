@@ -326,7 +326,9 @@ def profile_calls(kb, job, stepper, batches):
 
 def kernel_roofline(kb, stepper, math_mode, B, E):
     """Times the three tensor-tile kernels of a step in isolation (CUDA events on the launching stream, L2 flushed
-    between launches) and reports the dominant one against the measured dense-bf16 peak."""
+    between launches; an empty label CSR so that only the tile kernel and its tiny pre/post kernels run) and reports the
+    dominant one against the measured dense-bf16 peak.  `traffic` = dram bytes of that kernel from the committed
+    ncu --set full capture (profiles/ncu_full_latest_summary.json)."""
     pk = peaks()
     st = stepper
     d = st.d
@@ -337,40 +339,49 @@ def kernel_roofline(kb, stepper, math_mode, B, E):
     L = kb.lib
     ent = st.ent.detach()
     gtmp = torch.zeros_like(ent)
+    off0 = torch.zeros(B + 1, dtype=torch.int64, device=dev)   # no labels: isolates the dense tile kernels
 
     def fwd():
         L.call("kgeb_fused_fwd", st.loss_kind, math_mode, st.Q.data_ptr(), B, d, ent.data_ptr(), 0, E, E,
-               st.lab_off.data_ptr(), st.lab_col.data_ptr(), st.nnz_max, st.ls, st.offset, mp, st.rowstat.data_ptr(),
+               off0.data_ptr(), st.lab_col.data_ptr(), 0, st.ls, st.offset, mp, st.rowstat.data_ptr(),
                st.ws.data_ptr(), st.ws.numel(), L.stream_ptr(ent))
 
     def bwd(dq, dt):
         L.call("kgeb_fused_bwd", st.loss_kind, math_mode, st.Q.data_ptr(), B, d, ent.data_ptr(), 0, E, E,
-               st.lab_off.data_ptr(), st.lab_col.data_ptr(), st.nnz_max, st.ls, st.offset, lse.data_ptr(), 1.0 / B, None,
+               off0.data_ptr(), st.lab_col.data_ptr(), 0, st.ls, st.offset, lse.data_ptr(), 1.0 / B, None,
                mp, st.dQ.data_ptr() if dq else None, gtmp.data_ptr() if dt else None, st.ws.data_ptr(), st.ws.numel(),
                L.stream_ptr(ent))
 
-    cases = {"fused_fwd(stats)": (fwd, 2.0), "fused_bwd(dQ)": (lambda: bwd(True, False), 4.0),
-             "fused_bwd(dTable)": (lambda: bwd(False, True), 4.0)}
+    cases = {"tc_tiles_kernel<stats> (fused_fwd)": (fwd, 1, "tc::tc_tiles_kernel<1, 2, 1>"),
+             "tc_bwd_kernel<dQ> (fused_bwd)": (lambda: bwd(True, False), 2, "tcb::tc_bwd_kernel<1, 1, 1, 0>"),
+             "tc_bwd_kernel<dTable> (fused_bwd)": (lambda: bwd(False, True), 2, "tcb::tc_bwd_kernel<0, 1, 1, 0>")}
     res = {}
-    for name, (fn, gemms) in cases.items():
+    for name, (fn, gemms, _) in cases.items():
         ts = []
-        for i in range(6):
+        for i in range(8):
             flush.fill_(i)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
             torch.cuda.synchronize()
-            if i >= 2:
+            if i >= 3:
                 ts.append(a.elapsed_time(b))
-        res[name] = (float(np.mean(ts)), gemms * B * E * d)
+        res[name] = (float(np.mean(ts)), gemms * 2.0 * B * E * d)
     name = max(res, key=lambda k: res[k][0])
     ms, flops = res[name]
     achieved = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    path = os.path.join(ROOT, "profiles", "ncu_full_latest_summary.json")
+    if os.path.exists(path):
+        k = json.load(open(path)).get(cases[name][2])
+        if k:
+            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     tensor = math_mode != kb.lib.MATH_FP32
     return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_burst"], "traffic": None,
-            "note": ("algorithmic FLOPs = %d GEMMs x 2*B*E*d per launch (the score tile is recomputed in each backward "
-                     "kernel); peak = %s dense bf16 burst; kernel timed alone, L2 flushed. " % (int(res[name][1] / (2 * B * E * d)), pk["source"]))
-                    + ("tcgen05 tiles" if tensor else "CUDA-core fp32 tiles"),
+            "frac": achieved / pk["bf16_burst"], "traffic": traffic,
+            "note": ("algorithmic FLOPs = %d GEMM(s) x 2*B*E*d per launch (backward kernels recompute the score tile); "
+                     "peak = %s dense bf16 burst; kernel timed alone incl. its bf16(Q) / reduce helpers, L2 flushed; "
+                     "these fused kernels are MUFU-bound (ex2+rcp per score), see DESIGN.md 4.1; "
+                     % (cases[name][1], pk["source"])) + ("tcgen05 tiles" if tensor else "CUDA-core fp32 tiles"),
             "all_ms": {k: v[0] for k, v in res.items()}}
 
 
