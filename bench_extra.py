@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""Measurements of the other BASELINE.json configurations (C3, C4, C5) on one B200.  These are
+parity-test shapes, not the bench line (bench.py is the contract's benchmark); results are appended as JSON lines to
+profiles/extra_workloads_r1.jsonl and summarised in DESIGN.md.
+
+    python bench_extra.py --workload wd5m-1vsall | wnrr-rotate-ns | wd5m-eval-transe | wd5m-eval-complex [--scale F]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import kgeb200 as kb  # noqa: E402
+
+
+def timed(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def peaks():
+    p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    return p.get("hbm_gbs", 6650.0), p.get("bf16_tflops_sustained", 1400.0)
+
+
+def wd5m_1vsall(args):
+    """C4: DistMult 1vsAll + KL, d=128, E=4.6M (scaled by --scale), B triples -> 2B query rows per step."""
+    E, R, d, B = int(4_600_000 * args.scale), 822, 128, args.batch
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    model = kb.KgeModel("distmult", E, R, d).to(dev)
+    opt = kb.optim.create("Adagrad", model.parameters(), lr=0.2)
+    math_mode = {"bf16": kb.lib.MATH_BF16, "tf32": kb.lib.MATH_TF32, "fp32": kb.lib.MATH_FP32}[args.math]
+    st = kb.trainer.FusedAllEntityStepper(model, opt, 2 * B, 2 * B, kb.lib.LOSS_KL, B, math_mode=math_mode, use_graph=True)
+    gen = torch.Generator(device=dev).manual_seed(1)
+
+    def new_batch():
+        s = torch.randint(0, E, (B,), device=dev, generator=gen)
+        o = torch.randint(0, E, (B,), device=dev, generator=gen)
+        p = torch.randint(0, R, (B,), device=dev, generator=gen)
+        st.set_inputs(torch.cat((s, o)), torch.cat((p, p)),
+                      torch.cat((torch.zeros(B, dtype=torch.int32, device=dev), torch.ones(B, dtype=torch.int32, device=dev))),
+                      torch.arange(2 * B + 1, device=dev), torch.cat((o, s)))
+
+    def step():
+        new_batch()
+        st.step()
+
+    ms = timed(step, args.steps, args.warmup)
+    hbm, tf = peaks()
+    flops = 5 * 2.0 * (2 * B) * E * d   # 1 forward + 2x2 backward GEMMs (S recomputed per output)
+    # bytes this implementation moves per step: 3 bf16 table reads (fwd, dQ, dTable), gradient zero + RMW,
+    # Adagrad read W/state/grad + write W/state/mirror
+    bytes_step = E * d * (3 * 2 + 4 + 8 + 12 + 10)
+    return {"workload": f"DistMult 1vsAll+KL d=128 E={E} B={B} triples ({2 * B} query rows) {args.math}",
+            "metric": "training triples/s", "value": B / (ms * 1e-3), "ms_per_step": ms,
+            "loss": st.loss.item(),
+            "roofline": {"tensor_tflops": flops / (ms * 1e-3) / 1e12, "tensor_frac_of_bf16_sustained": flops / (ms * 1e-3) / 1e12 / tf,
+                         "hbm_gbs": bytes_step / (ms * 1e-3) / 1e9, "hbm_frac": bytes_step / (ms * 1e-3) / 1e9 / hbm,
+                         "algorithmic_bytes_per_step": bytes_step, "algorithmic_flops_per_step": flops}}
+
+
+def wnrr_rotate_ns(args):
+    """C3: RotatE negative sampling, 256 negatives for s and o, E=40943, R=11, B=512."""
+    E, R, d, B, N = 40943, 11, 128, args.batch, 256
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    model = kb.KgeModel("rotate", E, R, d).to(dev)
+    opt = kb.optim.create("Adagrad", model.parameters(), lr=0.2)
+    job = kb.TrainingJobNegativeSampling(model, opt, kb.KgeLoss.create("kl"), fused_path=not args.reference_flow)
+    gen = torch.Generator().manual_seed(1)
+    batches = []
+    for _ in range(8):
+        t = torch.stack((torch.randint(0, E, (B,), generator=gen), torch.randint(0, R, (B,), generator=gen),
+                         torch.randint(0, E, (B,), generator=gen)), 1)
+        negs = [torch.randint(0, E, (B, N), generator=gen), torch.zeros(B, 0, dtype=torch.long),
+                torch.randint(0, E, (B, N), generator=gen)]
+        batches.append({"triples": t.to(dev), "negative_samples": [n.to(dev) for n in negs]})
+    i = [0]
+
+    def step():
+        job.step(i[0], batches[i[0] % len(batches)])
+        i[0] += 1
+
+    ms = timed(step, args.steps, args.warmup)
+    hbm, _ = peaks()
+    bytes_step = B * 2 * (1 + N) * d * 4 * 2   # gather of each candidate row + write of its gradient row
+    return {"workload": f"RotatE NS 2x{N} negatives d=128 E={E} B={B} ({'reference flow' if args.reference_flow else 'fused pairs'})",
+            "metric": "training triples/s", "value": B / (ms * 1e-3), "ms_per_step": ms,
+            "roofline": {"hbm_gbs": bytes_step / (ms * 1e-3) / 1e9, "hbm_frac": bytes_step / (ms * 1e-3) / 1e9 / hbm,
+                         "algorithmic_bytes_per_step": bytes_step}}
+
+
+def wd5m_eval(args, model_name):
+    """C5: filtered entity ranking on the Wikidata5M shape: B triples -> 2B queries per batch."""
+    E, R, d, B = int(4_600_000 * args.scale), 822, 128, args.batch
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    math_mode = kb.lib.MATH_TF32 if (model_name == "complex" and args.math != "fp32") else kb.lib.MATH_FP32
+    model = kb.KgeModel(model_name, E, R, d, math_mode=math_mode).to(dev)
+    rng = np.random.default_rng(0)
+    known = np.stack([rng.integers(0, E, 20000), rng.integers(0, R, 20000), rng.integers(0, E, 20000)], 1).astype(np.int32)
+    job = kb.EntityRankingJob(model, E, [known], None, batch_size=B, math_mode=math_mode, hits_at_k_s=(1, 3, 10))
+    batch = torch.from_numpy(known[:B].copy())
+
+    def step():
+        job.rank_batch(batch)
+
+    ms = timed(step, args.steps, args.warmup)
+    hbm, tf = peaks()
+    ops = 2.0 * (2 * B) * E * d
+    return {"workload": f"filtered ranking {model_name} d=128 E={E} B={B} triples ({2 * B} queries) "
+                        f"{'tf32 tcgen05 tiles' if math_mode == kb.lib.MATH_TF32 else 'fp32 CUDA-core tiles'}",
+            "metric": "eval queries/s", "value": 2 * B / (ms * 1e-3), "ms_per_batch": ms,
+            "roofline": {"ops_per_s_T": ops / (ms * 1e-3) / 1e12,
+                         "frac_of_fp32_alu_nominal_37T": ops / (ms * 1e-3) / 1e12 / 37.2 if math_mode == kb.lib.MATH_FP32 else None,
+                         "frac_of_bf16_sustained": ops / (ms * 1e-3) / 1e12 / tf if math_mode != kb.lib.MATH_FP32 else None,
+                         "table_read_gbs": E * d * 4 / (ms * 1e-3) / 1e9}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", required=True)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 4.6M entities (memory / time bound runs)")
+    ap.add_argument("--math", default="bf16")
+    ap.add_argument("--reference-flow", action="store_true")
+    args = ap.parse_args()
+    if args.workload == "wd5m-1vsall":
+        res = wd5m_1vsall(args)
+    elif args.workload == "wnrr-rotate-ns":
+        res = wnrr_rotate_ns(args)
+    elif args.workload == "wd5m-eval-transe":
+        res = wd5m_eval(args, "transe")
+    elif args.workload == "wd5m-eval-complex":
+        res = wd5m_eval(args, "complex")
+    else:
+        raise SystemExit(f"unknown workload {args.workload}")
+    res["n_gpus"] = 1
+    line = json.dumps(res)
+    print(line)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "extra_workloads.jsonl"), "a") as f:
+        f.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()
