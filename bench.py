@@ -349,7 +349,7 @@ def kernel_roofline(kb, stepper, math_mode, B, E):
     def bwd(dq, dt):
         L.call("kgeb_fused_bwd", st.loss_kind, math_mode, st.Q.data_ptr(), B, d, ent.data_ptr(), 0, E, E,
                off0.data_ptr(), st.lab_col.data_ptr(), 0, st.ls, st.offset, lse.data_ptr(), 1.0 / B, None,
-               mp, st.dQ.data_ptr() if dq else None, gtmp.data_ptr() if dt else None, st.ws.data_ptr(), st.ws.numel(),
+               mp, st.dQ.data_ptr() if dq else None, gtmp.data_ptr() if dt else None, None, st.ws.data_ptr(), st.ws.numel(),
                L.stream_ptr(ent))
 
     cases = {"tc_tiles_kernel<stats> (fused_fwd)": (fwd, 1, "tc::tc_tiles_kernel<1, 2, 1>"),

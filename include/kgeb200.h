@@ -120,6 +120,8 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
                    int64_t nnz /* = lab_off[B], known to the caller */, float label_smoothing, float offset, const float* lse /*[B] (KL)*/, float inv_batch,
                    const float* row_scale /*[B] per-row factor multiplied into G (upstream gradient), or NULL*/,
                    const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */, float* dQ, float* dTable,
+                   float* rowstat_out /* [B,4] or NULL: also produce the forward statistics of kgeb_fused_fwd (BCE on the
+                                         bf16 tiles gets them from the same pass; otherwise the forward kernels run) */,
                    void* workspace, int64_t workspace_bytes, void* stream);
 /* loss(scores, labels) / batch_size from the (shard-combined) forward statistics, as the reference's loss objects
  * return it (loss.py:153-159, 198-213): rows_out[B] per-row values (may be NULL), lse_out[B] log-sum-exp per row for

@@ -47,9 +47,10 @@ struct Params {
   const float* lse;        // [B] (KL)
   const float* row_scale;  // [B] or NULL
   float* out;              // RES_IS_Q: partial [chunks][B][d] ; else dTable [n_res][d] (+=)
+  float* stat_partial;     // STATS: [chunks][4 column parts][B][2] = (sum softplus(x+off), sum (x+off)) over valid entities
 };
 
-template <bool RES_IS_Q, bool BF16, int LOSS, bool HAS_RS>
+template <bool RES_IS_Q, bool BF16, int LOSS, bool HAS_RS, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_str, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -223,6 +224,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
       const int64_t res_row = rb * RES_ROWS + trow;
       float my_lse = 0.f, my_rs = 0.f;
+      float st_sp = 0.f, st_x = 0.f;   // STATS: BCE forward statistics of this (row, column part), summed over the job
       if (RES_IS_Q && res_row < p.B) {
         my_rs = p.inv_batch * (HAS_RS ? p.row_scale[res_row] : 1.f);
         if (LOSS == KGEB_LOSS_KL) my_lse = p.lse[res_row];
@@ -240,6 +242,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         // Rows / columns beyond the matrices were zero-filled by TMA, so whatever finite G they get multiplies
         // zeros in MMA2; only the parameter loads are clamped.
         const int64_t qbase = u * STR_ROWS + sub * COLS_PER_WARP;
+        const int nvalid = (int)min((int64_t)COLS_PER_WARP, p.n_str - qbase);  // STATS: valid entity columns here
 #pragma unroll
         for (int c = 0; c < COLS_PER_WARP; ++c) {
           float lse = my_lse, rs = my_rs;
@@ -249,7 +252,22 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
             if (LOSS == KGEB_LOSS_KL) lse = __ldg(p.lse + q);
           }
           const float x = v[c];
-          const float gval = (LOSS == KGEB_LOSS_KL) ? __expf(x - lse) : sigmoidf(x + p.offset) - p.ls_add;
+          float gval;
+          if (LOSS == KGEB_LOSS_KL) {
+            gval = __expf(x - lse);
+          } else if (STATS) {
+            // sigmoid and softplus from one exponential: e = exp(-|z|), r = 1/(1+e); sigma = z>=0 ? r : e r;
+            // softplus(z) = max(z,0) + log(1+e) = max(z,0) - log(r)          (3 MUFU: ex2, rcp, lg2)
+            const float z = x + p.offset;
+            const float e = __expf(-fabsf(z));
+            const float r = __fdividef(1.f, 1.f + e);
+            gval = (z >= 0.f ? r : e * r) - p.ls_add;
+            const bool valid = c < nvalid;          // entity columns beyond the table end (zero-filled) do not count
+            st_sp += valid ? fmaxf(z, 0.f) - __logf(r) : 0.f;
+            st_x += valid ? z : 0.f;
+          } else {
+            gval = sigmoidf(x + p.offset) - p.ls_add;
+          }
           v[c] = rs * gval;
         }
         mbar_wait(&g_empty[bufi], gph ^ 1);  // MMA2 of this buffer's previous tile has finished reading it
@@ -277,6 +295,11 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive(&g_full[bufi]);
         gph ^= 1;
+      }
+      if (STATS && res_row < p.B) {
+        float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
+        sp[0] = st_sp;
+        sp[1] = st_x;
       }
       // flush the job's accumulator: 16-column groups are dealt round-robin to the column parts
       mbar_wait(o_full, ophase);
@@ -334,7 +357,7 @@ label_entry_rows_kernel(const float* __restrict__ Q, const float* __restrict__ t
                         int64_t n_ent, const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
                         const float* __restrict__ tscale, const float* __restrict__ row_scale, float inv_batch, int64_t nnz,
                         float* __restrict__ rows_dq, float* __restrict__ rows_dt, int64_t* __restrict__ ent,
-                        int64_t* __restrict__ erow) {
+                        int64_t* __restrict__ erow, float* __restrict__ entry_dot, float add_per_entry) {
   const int lane = threadIdx.x & 31;
   const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= nnz) return;
@@ -350,19 +373,26 @@ label_entry_rows_kernel(const float* __restrict__ Q, const float* __restrict__ t
   q = __shfl_sync(0xffffffffu, q, 0);
   int64_t e = 0;
   float w = 0.f;
+  bool in_shard = false;
   if (q >= 0) {
     e = lab_col[i] - e_lo;
-    if (e >= 0 && e < n_ent) w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
+    in_shard = (e >= 0 && e < n_ent);
+    if (in_shard) w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
     else e = 0;
   }
   const int64_t qq = q < 0 ? 0 : q;
+  float dot = 0.f;
   for (int c = lane; c < d; c += 32) {
-    if (rows_dq) rows_dq[i * d + c] = -w * __ldg(table + e * d + c);
-    if (rows_dt) rows_dt[i * d + c] = -w * Q[qq * d + c];
+    const float tv = __ldg(table + e * d + c), qv = Q[qq * d + c];
+    dot = fmaf(qv, tv, dot);
+    if (rows_dq) rows_dq[i * d + c] = -w * tv;
+    if (rows_dt) rows_dt[i * d + c] = -w * qv;
   }
+  if (entry_dot) dot = warp_sum(dot);   // warp-uniform branch
   if (lane == 0) {
     ent[i] = e;
     erow[i] = qq;
+    if (entry_dot) entry_dot[i] = in_shard ? dot + add_per_entry : 0.f;   // x_ij (+offset) at the label, in-shard only
   }
 }
 
@@ -409,22 +439,51 @@ template <bool RES_IS_Q>
 static int launch_bwd(const Plan& pl, const CUtensorMap& m_res, const CUtensorMap& m_str, int64_t jobs, cudaStream_t st) {
   const int grid = (int)(jobs < kNumSMs ? jobs : kNumSMs);
   cudaError_t e = cudaSuccess;
-#define KGEB_BWD_LAUNCH(LOSS_, RS_)                                                                                   \
+#define KGEB_BWD_LAUNCH(LOSS_, RS_, ST_)                                                                              \
   {                                                                                                                   \
-    e = cudaFuncSetAttribute(tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             (int)pl.smem);                                                                           \
+    e = cudaFuncSetAttribute(tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_, ST_>,                                          \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);                              \
     if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");                                             \
-    tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_><<<grid, NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);                 \
+    tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_, ST_><<<grid, NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);            \
   }
   const bool rs = pl.p.row_scale != nullptr;
+  const bool stats = RES_IS_Q && pl.p.stat_partial != nullptr && pl.p.loss == KGEB_LOSS_BCE;
   if (pl.p.loss == KGEB_LOSS_KL) {
-    if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_KL, true) else KGEB_BWD_LAUNCH(KGEB_LOSS_KL, false)
+    if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_KL, true, false) else KGEB_BWD_LAUNCH(KGEB_LOSS_KL, false, false)
+  } else if (stats) {
+    if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, true, RES_IS_Q) else KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, false, RES_IS_Q)
   } else {
-    if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, true) else KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, false)
+    if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, true, false) else KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, false, false)
   }
 #undef KGEB_BWD_LAUNCH
   KGEB_LAUNCH_CHECK("tc_bwd_kernel");
   return KGEB_OK;
+}
+
+// rowstat[r] = (sum softplus, 0, sum (x+off), label_dot[r]) from the per-(chunk, column part) partials, fixed order
+__global__ void reduce_stat_partials_kernel(const float* __restrict__ sp, int64_t chunks, int64_t B,
+                                            const float* __restrict__ label_dot, float* __restrict__ rowstat) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  float a = 0.f, b = 0.f;
+  for (int64_t k = 0; k < chunks * 4; ++k) {
+    a += sp[(k * B + r) * 2];
+    b += sp[(k * B + r) * 2 + 1];
+  }
+  float* o = rowstat + r * 4;
+  o[0] = a; o[1] = 0.f; o[2] = b; o[3] = label_dot[r];
+}
+
+__global__ void __launch_bounds__(256)
+label_row_sum2_kernel(const float* __restrict__ entry_dot, const int64_t* __restrict__ lab_off, int64_t B,
+                      float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= B) return;
+  float acc = 0.f;
+  for (int64_t i = lab_off[r] + lane; i < lab_off[r + 1]; i += 32) acc += entry_dot[i];
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc;
 }
 
 __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
@@ -468,14 +527,15 @@ static int64_t a256(int64_t x) { return (x + 255) / 256 * 256; }
 int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz) {
   if (nnz < 1) nnz = 1;
   return a256((int64_t)kNumSMs * B * d * 4) + 2 * a256(nnz * (int64_t)d * 4) + 2 * a256(nnz * 8) +
-         kgeb_scatter_workspace_bytes(nnz, d) + 2048;
+         a256((int64_t)kNumSMs * 4 * B * 2 * 4) + a256(nnz * 4) + a256(B * 4) + kgeb_scatter_workspace_bytes(nnz, d) + 4096;
 }
 
 // Qb / tableb: bf16 mirrors of Q [B,d] and of the table shard [n_ent,d]
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                  const float* tscale, float ls_add, float offset, const float* lse, float inv_batch,
-                 const float* row_scale, float* dQ, float* dTable, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                 const float* row_scale, float* dQ, float* dTable, float* rowstat_out, void* ws, int64_t ws_bytes,
+                 cudaStream_t st) {
   using namespace tcb;
   KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_bwd(bf16): entity dim must be a multiple of 16 and <= 256 (got %d)", d);
   KGEB_REQUIRE(Qb && tableb, "fused_bwd(bf16): the bf16 mirrors of Q and of the table are required");
@@ -489,6 +549,10 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
   float* rows_dt = reinterpret_cast<float*>(wp);      wp += a256(nz * (int64_t)d * 4);
   int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
   int64_t* lab_row = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
+  float* stat_partial = reinterpret_cast<float*>(wp); wp += a256((int64_t)kNumSMs * 4 * B * 2 * 4);
+  float* entry_dot = reinterpret_cast<float*>(wp);    wp += a256(nz * 4);
+  float* label_dot = reinterpret_cast<float*>(wp);    wp += a256(B * 4);
+  const bool want_stats = rowstat_out != nullptr && dQ != nullptr && loss == KGEB_LOSS_BCE;
   void* scatter_ws = wp;
   const int64_t scatter_bytes = ws_bytes - (wp - reinterpret_cast<char*>(ws));
   int rc;
@@ -497,7 +561,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
     if (nnz > 0) {
       label_entry_rows_kernel<<<(unsigned)((nnz + 7) / 8), 256, 0, st>>>(
           Q, table, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale, inv_batch, nnz, dQ ? rows_dq : nullptr,
-          dTable ? rows_dt : nullptr, lab_ent, lab_row);
+          dTable ? rows_dt : nullptr, lab_ent, lab_row, want_stats ? entry_dot : nullptr, offset);
       KGEB_LAUNCH_CHECK("label_entry_rows");
     }
     if (dQ) {
@@ -505,6 +569,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
       pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = partial;
+      pl.p.stat_partial = want_stats ? stat_partial : nullptr;
       if ((rc = make_map(&m_res, Qb, B, d, RES_ROWS, true)) || (rc = make_map(&m_str, tableb, n_ent, d, STR_ROWS, true))) return rc;
       const int64_t jobs = pl.p.n_res_blocks * pl.p.chunks;
       if ((rc = launch_bwd<true>(pl, m_res, m_str, jobs, st))) return rc;
@@ -514,6 +579,13 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       KGEB_LAUNCH_CHECK("reduce_dq_partials");
       if (nnz > 0 && (rc = scatter_add_rows_presorted(lab_row, rows_dq, nnz, d, dQ, B, scatter_ws, scatter_bytes, st)))
         return rc;
+      if (want_stats) {   // BCE forward statistics came out of the same pass
+        if (nnz > 0) label_row_sum2_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(entry_dot, lab_off, B, label_dot);
+        else cudaMemsetAsync(label_dot, 0, (size_t)B * 4, st);
+        reduce_stat_partials_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(stat_partial, pl.p.chunks, B, label_dot,
+                                                                                rowstat_out);
+        KGEB_LAUNCH_CHECK("reduce_stat_partials");
+      }
     }
     if (dTable) {
       Plan pl = make_plan(false, true, B, d, n_ent);

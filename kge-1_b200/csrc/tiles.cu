@@ -24,7 +24,7 @@ int tc_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);  // tc_
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                  const float* tscale, float ls_add, float offset, const float* lse, float inv_batch,
-                 const float* row_scale, float* dQ, float* dTable, void* ws, int64_t ws_bytes,
+                 const float* row_scale, float* dQ, float* dTable, float* rowstat_out, void* ws, int64_t ws_bytes,
                  cudaStream_t st);  // tc_bwd.cu
 int tc_rank_count(const float* Q, int64_t nq, int d, const float* table, int64_t e_lo, int64_t n_ent,
                   const float* true_score, const void* true_ent, int idx64, const int64_t* f_off,
@@ -833,8 +833,8 @@ __global__ void label_weight_kernel(int loss, const int64_t* __restrict__ lab_of
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                    float label_smoothing, float offset, const float* lse, float inv_batch,
-                   const float* grad_scale, const void* table_bf16, float* dQ, float* dTable, void* workspace,
-                   int64_t workspace_bytes, void* stream) {
+                   const float* grad_scale, const void* table_bf16, float* dQ, float* dTable, float* rowstat_out,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
   if (rc) return rc;
   KGEB_REQUIRE(loss != KGEB_LOSS_KL || lse, "fused_bwd: KL needs the per-row log-sum-exp");
@@ -858,9 +858,19 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
     label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, tail.tscale);
     KGEB_LAUNCH_CHECK("label_weight");
     if ((rc = tc_to_bf16(Q, tail.qb, B * (int64_t)d, st))) return rc;
+    const bool fused_stats = rowstat_out && dQ && loss == KGEB_LOSS_BCE && n_ent > 0;
+    if (rowstat_out && !fused_stats &&
+        (rc = kgeb_fused_fwd(loss, math, Q, B, d, table, e_lo, e_hi, num_entities, lab_off, lab_col, nnz, label_smoothing,
+                             offset, table_bf16, rowstat_out, workspace, workspace_bytes, stream)))
+      return rc;
     return tc_fused_bwd(loss, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, tail.tscale,
-                        lp.ls_add, offset, lse, inv_batch, grad_scale, dQ, dTable, workspace, tail.usable, st);
+                        lp.ls_add, offset, lse, inv_batch, grad_scale, dQ, dTable, fused_stats ? rowstat_out : nullptr,
+                        workspace, tail.usable, st);
   }
+  if (rowstat_out && (rc = kgeb_fused_fwd(loss, math, Q, B, d, table, e_lo, e_hi, num_entities, lab_off, lab_col, nnz,
+                                          label_smoothing, offset, table_bf16, rowstat_out, workspace, workspace_bytes,
+                                          stream)))
+    return rc;
   // KGEB_MATH_TF32 (an MN-major TF32 operand would need a second, differently swizzled copy of every tile) and
   // dims outside the BF16 tile build use the fp32 CUDA-core tiles below
   label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, tscale);

@@ -116,7 +116,7 @@ def fused_backward(q, table, lab_off, lab_col, loss, label_smoothing, offset, ls
              float(offset), None if lse is None else lib.f32(lse, "lse"), float(inv_batch),
              None if grad_scale is None else lib.f32(grad_scale, "grad scale"), _mirror_ptr(table, math, b, d),
              None if dq is None else dq.data_ptr(), None if d_table is None else lib.f32(d_table, "table gradient"),
-             ws.data_ptr(), ws.numel(), lib.stream_ptr(q))
+             None, ws.data_ptr(), ws.numel(), lib.stream_ptr(q))
     if dq is not None and n_ent == 0:
         dq.zero_()
     if dq is not None and shard.distributed:

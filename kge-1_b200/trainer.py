@@ -76,6 +76,11 @@ class FusedAllEntityStepper:
             self._capture()
 
     # -- one step on the current stream, in three stages separated by the (optional) collectives ----------------
+    def _fused_stats_in_backward(self) -> bool:
+        """BCE on the bf16 tiles: the backward dQ kernel evaluates sigmoid and softplus from the same exponential, so the
+        forward statistics (only needed for the loss value) come out of the backward pass and the forward kernel is skipped."""
+        return self.loss_kind == lib.LOSS_BCE and self.mirror is not None
+
     def _stage_forward(self):
         st = lib.stream_ptr(self.ent)
         model_id = lib.MODELS[self.model.model]
@@ -84,25 +89,34 @@ class FusedAllEntityStepper:
         self.g_ent.zero_(); self.g_rel.zero_()
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
-        lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
-                 ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
-                 self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset, self._mirror_ptr(), self.rowstat.data_ptr(),
-                 self.ws.data_ptr(), self.ws.numel(), st)
+        if not self._fused_stats_in_backward():
+            lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
+                     ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
+                     self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset, self._mirror_ptr(),
+                     self.rowstat.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
+
+    def _loss_kernel(self):
+        lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
+                 self.ls, self.E, 1.0 / self.batch_size, None, self.lse.data_ptr(), self.loss.data_ptr(),
+                 lib.stream_ptr(self.ent))
 
     def _stage_backward(self):
         st = lib.stream_ptr(self.ent)
         ent = self.ent.detach()
         sh = self.shard
-        lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
-                 self.ls, self.E, 1.0 / self.batch_size, None, self.lse.data_ptr(), self.loss.data_ptr(), st)
+        late_stats = self._fused_stats_in_backward()
+        if not late_stats:
+            self._loss_kernel()   # KL needs the log-sum-exp before the backward
         lib.call("kgeb_fused_bwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
                  ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
                  self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
                  self.lse.data_ptr() if self.loss_kind == lib.LOSS_KL else None, 1.0 / self.batch_size, None,
-                 self._mirror_ptr(), self.dQ.data_ptr(), self.g_ent[sh.e_lo:sh.e_hi].data_ptr(), self.ws.data_ptr(),
-                 self.ws.numel(), st)
+                 self._mirror_ptr(), self.dQ.data_ptr(), self.g_ent[sh.e_lo:sh.e_hi].data_ptr(),
+                 self.rowstat.data_ptr() if late_stats else None, self.ws.data_ptr(), self.ws.numel(), st)
 
     def _stage_update(self):
+        if self._fused_stats_in_backward():
+            self._loss_kernel()
         st = lib.stream_ptr(self.ent)
         model_id = lib.MODELS[self.model.model]
         ent, rel = self.ent.detach(), self.rel.detach()
@@ -123,12 +137,15 @@ class FusedAllEntityStepper:
         return None if self.mirror is None else self.mirror[self.shard.e_lo:self.shard.e_hi].data_ptr()
 
     def _exchange_stats(self):
-        if self.shard.distributed:   # per-row statistics of the shards -> global (max + rescaled sums for KL)
+        # per-row statistics of the shards -> global (max + rescaled sums for KL)
+        if self.shard.distributed and not self._fused_stats_in_backward():
             self.rowstat.copy_(fused.combine_rowstats(self.rowstat, self.loss_kind, self.shard))
 
     def _exchange_grads(self):
         if self.shard.distributed:
             import torch.distributed as dist
+            if self._fused_stats_in_backward():
+                self.rowstat.copy_(fused.combine_rowstats(self.rowstat, self.loss_kind, self.shard))
             dist.all_reduce(self.dQ, group=self.shard.group)      # sum of the per-shard partial query gradients
             dist.all_reduce(self.g_ent, group=self.shard.group)   # dense table gradient: each rank filled its rows
 
