@@ -225,6 +225,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       const int64_t res_row = rb * RES_ROWS + trow;
       float my_lse = 0.f, my_rs = 0.f;
       float st_sp = 0.f, st_x = 0.f;   // STATS: BCE forward statistics of this (row, column part), summed over the job
+      int n_pad = 0;
       if (RES_IS_Q && res_row < p.B) {
         my_rs = p.inv_batch * (HAS_RS ? p.row_scale[res_row] : 1.f);
         if (LOSS == KGEB_LOSS_KL) my_lse = p.lse[res_row];
@@ -242,7 +243,9 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         // Rows / columns beyond the matrices were zero-filled by TMA, so whatever finite G they get multiplies
         // zeros in MMA2; only the parameter loads are clamped.
         const int64_t qbase = u * STR_ROWS + sub * COLS_PER_WARP;
-        const int nvalid = (int)min((int64_t)COLS_PER_WARP, p.n_str - qbase);  // STATS: valid entity columns here
+        // STATS: entity columns beyond the table end were zero-filled, their score is exactly 0: count them here
+        // and take their known contribution (softplus(off), off) out once per job instead of masking per element
+        if (STATS) n_pad += COLS_PER_WARP - (int)max((int64_t)0, min((int64_t)COLS_PER_WARP, p.n_str - qbase));
 #pragma unroll
         for (int c = 0; c < COLS_PER_WARP; ++c) {
           float lse = my_lse, rs = my_rs;
@@ -256,15 +259,13 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           if (LOSS == KGEB_LOSS_KL) {
             gval = __expf(x - lse);
           } else if (STATS) {
-            // sigmoid and softplus from one exponential: e = exp(-|z|), r = 1/(1+e); sigma = z>=0 ? r : e r;
-            // softplus(z) = max(z,0) + log(1+e) = max(z,0) - log(r)          (3 MUFU: ex2, rcp, lg2)
-            const float z = x + p.offset;
-            const float e = __expf(-fabsf(z));
-            const float r = __fdividef(1.f, 1.f + e);
-            gval = (z >= 0.f ? r : e * r) - p.ls_add;
-            const bool valid = c < nvalid;          // entity columns beyond the table end (zero-filled) do not count
-            st_sp += valid ? fmaxf(z, 0.f) - __logf(r) : 0.f;
-            st_x += valid ? z : 0.f;
+            // sigmoid and softplus from one exponential (3 MUFU: ex2, rcp, lg2):  a = 1 + exp(-z);  sigma = 1/a;
+            // softplus(z) = z + log(a).  z is clamped at -80 so that exp(-z) stays finite (softplus(-80) ~ 1e-35).
+            const float z = fmaxf(x + p.offset, -80.f);
+            const float a = 1.f + __expf(-z);
+            gval = __fdividef(1.f, a) - p.ls_add;
+            st_sp += fmaf(0.69314718f, __log2f(a), z);
+            st_x += z;
           } else {
             gval = sigmoidf(x + p.offset) - p.ls_add;
           }
@@ -298,8 +299,9 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       }
       if (STATS && res_row < p.B) {
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
-        sp[0] = st_sp;
-        sp[1] = st_x;
+        const float zp = fmaxf(p.offset, -80.f);
+        sp[0] = st_sp - (float)n_pad * fmaf(0.69314718f, __log2f(1.f + __expf(-zp)), zp);
+        sp[1] = st_x - (float)n_pad * zp;
       }
       // flush the job's accumulator: 16-column groups are dealt round-robin to the column parts
       mbar_wait(o_full, ophase);
