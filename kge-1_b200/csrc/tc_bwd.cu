@@ -259,12 +259,14 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           if (LOSS == KGEB_LOSS_KL) {
             gval = __expf(x - lse);
           } else if (STATS) {
-            // sigmoid and softplus from one exponential (3 MUFU: ex2, rcp, lg2):  a = 1 + exp(-z);  sigma = 1/a;
-            // softplus(z) = z + log(a).  z is clamped at -80 so that exp(-z) stays finite (softplus(-80) ~ 1e-35).
-            const float z = fmaxf(x + p.offset, -80.f);
-            const float a = 1.f + __expf(-z);
-            gval = __fdividef(1.f, a) - p.ls_add;
-            st_sp += fmaf(0.69314718f, __log2f(a), z);
+            // sigmoid and softplus from one exponential (3 MUFU: ex2, rcp, lg2), cancellation-free:
+            //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
+            const float z = x + p.offset;
+            const float e = __expf(-fabsf(z));
+            const float a = 1.f + e;
+            const float r = __fdividef(1.f, a);
+            gval = (z >= 0.f ? r : e * r) - p.ls_add;
+            st_sp += fmaf(0.69314718f, __log2f(a), fmaxf(z, 0.f));
             st_x += z;
           } else {
             gval = sigmoidf(x + p.offset) - p.ls_add;
@@ -299,8 +301,8 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       }
       if (STATS && res_row < p.B) {
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
-        const float zp = fmaxf(p.offset, -80.f);
-        sp[0] = st_sp - (float)n_pad * fmaf(0.69314718f, __log2f(1.f + __expf(-zp)), zp);
+        const float zp = p.offset;
+        sp[0] = st_sp - (float)n_pad * fmaf(0.69314718f, __log2f(1.f + __expf(-fabsf(zp))), fmaxf(zp, 0.f));
         sp[1] = st_x - (float)n_pad * zp;
       }
       // flush the job's accumulator: 16-column groups are dealt round-robin to the column parts
