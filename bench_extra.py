@@ -82,6 +82,8 @@ def wnrr_rotate_ns(args):
     model = kb.KgeModel("rotate", E, R, d).to(dev)
     opt = kb.optim.create("Adagrad", model.parameters(), lr=0.2)
     job = kb.TrainingJobNegativeSampling(model, opt, kb.KgeLoss.create("kl"), fused_path=not args.reference_flow)
+    if args.graph_step:
+        job.enable_graph_step(B, N, N)
     gen = torch.Generator().manual_seed(1)
     batches = []
     for _ in range(8):
@@ -99,7 +101,7 @@ def wnrr_rotate_ns(args):
     ms = timed(step, args.steps, args.warmup)
     hbm, _ = peaks()
     bytes_step = B * 2 * (1 + N) * d * 4 * 2   # gather of each candidate row + write of its gradient row
-    return {"workload": f"RotatE NS 2x{N} negatives d=128 E={E} B={B} ({'reference flow' if args.reference_flow else 'fused pairs'})",
+    return {"workload": f"RotatE NS 2x{N} negatives d=128 E={E} B={B} ({'reference flow' if args.reference_flow else ('graph-captured fused step' if args.graph_step else 'fused pairs, autograd')})",
             "metric": "training triples/s", "value": B / (ms * 1e-3), "ms_per_step": ms,
             "roofline": {"hbm_gbs": bytes_step / (ms * 1e-3) / 1e9, "hbm_frac": bytes_step / (ms * 1e-3) / 1e9 / hbm,
                          "algorithmic_bytes_per_step": bytes_step}}
@@ -141,6 +143,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 4.6M entities (memory / time bound runs)")
     ap.add_argument("--math", default="bf16")
     ap.add_argument("--reference-flow", action="store_true")
+    ap.add_argument("--graph-step", action="store_true")
     args = ap.parse_args()
     if args.workload == "wd5m-1vsall":
         res = wd5m_1vsall(args)

@@ -82,6 +82,15 @@ int kgeb_pairs_score(int kind, const float* Q, const float* table, const void* c
 int kgeb_pairs_bwd(int kind, const float* Q, const float* table, const void* cand, int idx64, int64_t B,
                    int64_t M, int d, const float* G, const float* scores, float* dQ, float* dC, void* stream);
 
+/* negative-sampling batch body without autograd (train.py:853-994, implementation "triple"):
+ * candidates [B,1+N] = (positive target | negatives); loss over the score rows with label column 0
+ * (KL = cross entropy, loss.py:195-208; BCE with offset, loss.py:153-159): writes G = dL/dscores [B,1+N] and
+ * the per-row loss, both already divided by the batch size (inv_batch). */
+int kgeb_ns_candidates(const int64_t* target, const int64_t* negatives, int64_t B, int64_t N, int64_t* cand,
+                       void* stream);
+int kgeb_ns_loss(int loss, const float* scores, int64_t B, int64_t M, float offset, float inv_batch, float* G,
+                 float* row_loss, void* stream);
+
 /* ---- a5/a6/K4/K6/K7: score_emb(..., "sp_"|"_po") materialised:
  * out[i*ld + col_off + j] = pair_score(kind, Q[i,:], table[cand_idx ? cand_idx[j] : j, :]), j < m.
  * math = KGEB_MATH_FP32 | KGEB_MATH_TF32 (TF32 only for KGEB_DOT). */

@@ -567,6 +567,52 @@ pairs_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ table, c
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// negative-sampling loss on the [B, 1+N] score rows (column 0 = the positive, train.py:860-868):
+//   KL : cross entropy with class 0 (loss.py:195-208)   G = softmax - onehot(0)
+//   BCE: sum_j softplus(x+off) - (x_0+off)              G = sigmoid(x+off) - [j == 0]
+// one warp per row; writes G (scaled by inv_batch) and the row loss (scaled by inv_batch)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+ns_loss_kernel(int loss, const float* __restrict__ scores, int64_t B, int64_t M, float offset, float inv_batch,
+               float* __restrict__ G, float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* x = scores + row * M;
+  float* g = G + row * M;
+  if (loss == KGEB_LOSS_KL) {
+    float mx = -INFINITY;
+    for (int64_t j = lane; j < M; j += 32) mx = fmaxf(mx, x[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int64_t j = lane; j < M; j += 32) sum += __expf(x[j] - mx);
+    sum = warp_sum(sum);
+    const float lse = mx + __logf(sum), inv = 1.f / sum;
+    for (int64_t j = lane; j < M; j += 32) g[j] = inv_batch * (__expf(x[j] - mx) * inv - (j == 0 ? 1.f : 0.f));
+    if (lane == 0) row_loss[row] = inv_batch * (lse - x[0]);
+  } else {
+    float acc = 0.f;
+    for (int64_t j = lane; j < M; j += 32) {
+      const float z = x[j] + offset;
+      acc += softplusf(z) - (j == 0 ? z : 0.f);
+      g[j] = inv_batch * (sigmoidf(z) - (j == 0 ? 1.f : 0.f));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) row_loss[row] = inv_batch * acc;
+  }
+}
+
+// cand[i,0] = target[i]; cand[i,1+j] = negatives[i,j]
+__global__ void ns_candidates_kernel(const int64_t* __restrict__ target, const int64_t* __restrict__ neg, int64_t B,
+                                     int64_t N, int64_t* __restrict__ cand) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t M = N + 1;
+  if (t >= B * M) return;
+  const int64_t i = t / M, j = t - i * M;
+  cand[t] = j == 0 ? target[i] : neg[i * N + (j - 1)];
+}
+
 static int grid_for_rows(int64_t n) {
   int64_t b = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
   int64_t cap = (int64_t)kNumSMs * 16;
@@ -707,6 +753,27 @@ int kgeb_pairs_score(int kind, const float* Q, const float* table, const void* c
   DISPATCH_KIND(kind, (pairs_score_kernel<K_><<<grid_for_rows(B * M), kWarpsPerBlock * 32, 0, st>>>(
                           Q, table, cand, idx64, B, M, d, out)));
   KGEB_LAUNCH_CHECK("pairs_score");
+  return KGEB_OK;
+}
+
+int kgeb_ns_loss(int loss, const float* scores, int64_t B, int64_t M, float offset, float inv_batch, float* G,
+                 float* row_loss, void* stream) {
+  KGEB_REQUIRE(loss == KGEB_LOSS_KL || loss == KGEB_LOSS_BCE, "ns_loss: unknown loss %d", loss);
+  KGEB_REQUIRE(scores && G && row_loss && B >= 0 && M >= 1, "ns_loss: bad arguments");
+  if (B == 0) return KGEB_OK;
+  ns_loss_kernel<<<(unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, 0, as_stream(stream)>>>(
+      loss, scores, B, M, offset, inv_batch, G, row_loss);
+  KGEB_LAUNCH_CHECK("ns_loss");
+  return KGEB_OK;
+}
+
+int kgeb_ns_candidates(const int64_t* target, const int64_t* negatives, int64_t B, int64_t N, int64_t* cand,
+                       void* stream) {
+  KGEB_REQUIRE(target && cand && (negatives || N == 0) && B >= 0 && N >= 0, "ns_candidates: bad arguments");
+  if (B == 0) return KGEB_OK;
+  const int64_t total = B * (N + 1);
+  ns_candidates_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(target, negatives, B, N, cand);
+  KGEB_LAUNCH_CHECK("ns_candidates");
   return KGEB_OK;
 }
 

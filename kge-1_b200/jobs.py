@@ -232,6 +232,28 @@ class TrainingJobNegativeSampling(TrainingJob):
     """train.py:823-999.  fused: each positive's query vector is built once and scored against its
     1+N candidates (no B*(1+N) triple expansion); otherwise implementation "triple" as in the reference."""
 
+    stepper = None
+
+    def enable_graph_step(self, batch_size: int, num_neg_s: int, num_neg_o: int, use_graph: bool = True):
+        """Routes step() through FusedNegSamplingStepper (no autograd, one CUDA-graph replay per step) for batches of
+        exactly `batch_size` triples with these negative counts for the S and O slots (no relation negatives)."""
+        from .trainer import FusedNegSamplingStepper
+        self.stepper = FusedNegSamplingStepper(self.model, self.optimizer, batch_size, num_neg_s, num_neg_o,
+                                               self.loss.kind, self.loss.offset, use_graph)
+        return self.stepper
+
+    def step(self, batch_index: int, batch: dict) -> ProcessBatchResult:
+        st = self.stepper
+        negs = batch["negative_samples"]
+        if (st is None or len(batch["triples"]) != st.B or (negs[1].dim() == 2 and negs[1].shape[1] > 0)
+                or any(negs[s].shape[1] != st.N[s] for s in (0, 2))):
+            return super().step(batch_index, batch)
+        for f in self.pre_batch_hooks:
+            f(self)
+        st.set_inputs(batch["triples"], negs)
+        value = st.step().item()
+        return ProcessBatchResult(value, st.B)
+
     def _process_batch(self, batch_index, batch) -> ProcessBatchResult:
         triples = batch["triples"].to(self.device)
         negs = [ns.to(self.device) for ns in batch["negative_samples"]]

@@ -34,6 +34,8 @@ SIGNATURES = {
     "kgeb_query_bwd": [_i, _i, _p, _p, _p, _p, _p, _i, _l, _i, _p, _p, _p, _p],
     "kgeb_pairs_score": [_i, _p, _p, _p, _i, _l, _l, _i, _p, _p],
     "kgeb_pairs_bwd": [_i, _p, _p, _p, _i, _l, _l, _i, _p, _p, _p, _p, _p],
+    "kgeb_ns_candidates": [_p, _p, _l, _l, _p, _p],
+    "kgeb_ns_loss": [_i, _p, _l, _l, _f, _f, _p, _p, _p],
     "kgeb_score_all": [_i, _i, _p, _l, _i, _p, _p, _i, _l, _p, _l, _l, _p],
     "kgeb_score_all_bwd": [_i, _p, _l, _i, _p, _p, _i, _l, _p, _p, _l, _l, _p, _p, _p],
     "kgeb_fused_fwd": [_i, _i, _p, _l, _i, _p, _l, _l, _l, _p, _p, _l, _f, _f, _p, _p, _p, _l, _p],

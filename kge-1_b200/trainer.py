@@ -246,3 +246,121 @@ def kvsall_rows(queries: torch.Tensor, query_type: torch.Tensor):
     a = torch.where(qt == 0, queries[:, 0], queries[:, 1])
     p = torch.where(qt == 0, queries[:, 1], queries[:, 0])
     return a.contiguous(), p.contiguous(), qt.contiguous()
+
+
+class FusedNegSamplingStepper:
+    """Static-shape negative-sampling step (train.py:823-999, implementation "triple", slots S and O) for all seven
+    scorers: per slot   query vector of the positive -> pair scores against its 1+N candidates -> loss + dL/dscores ->
+    pair backward (dQ, candidate gradient rows) -> query-transform backward;   then the sorted scatters of the candidate /
+    query-side rows and Adagrad on both tables.  No autograd, no B*(1+N) triple expansion; replayed as one CUDA graph.
+    """
+
+    def __init__(self, model: KgeModel, optimizer, batch_size: int, num_neg_s: int, num_neg_o: int, loss_kind: int,
+                 offset: float = 0.0, use_graph: bool = True):
+        self.model, self.opt = model, optimizer
+        self.B, self.N = batch_size, {0: int(num_neg_s), 2: int(num_neg_o)}
+        self.loss_kind, self.offset = loss_kind, float(offset)
+        self.kind = model.get_scorer().kind
+        self.ent, self.rel = model.get_s_embedder().weight, model.get_p_embedder().weight
+        dev = self.ent.device
+        self.E, self.d = self.ent.shape
+        self.dr = self.rel.shape[1]
+        group = optimizer.param_groups[0]
+        if group.get("lr_decay", 0.0) != 0.0 or group.get("weight_decay", 0.0) != 0.0:
+            raise NotImplementedError("the graph-captured step bakes lr into the launch (lr_decay / weight_decay = 0)")
+        self.lr, self.eps = float(group["lr"]), float(group["eps"])
+        f32 = dict(dtype=torch.float32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        B = batch_size
+        self.triples = torch.zeros(3, B, **i64)            # static inputs: rows s, p, o
+        self.neg = {slot: torch.zeros(B, n, **i64) for slot, n in self.N.items() if n > 0}
+        self.slots = [slot for slot in (0, 2) if self.N[slot] > 0]
+        self.buf = {}
+        for slot in self.slots:
+            m = 1 + self.N[slot]
+            self.buf[slot] = dict(cand=torch.zeros(B, m, **i64), scores=torch.empty(B, m, **f32), G=torch.empty(B, m, **f32),
+                                  rows=torch.empty(B, **f32), Q=torch.empty(B, self.d, **f32), dQ=torch.empty(B, self.d, **f32),
+                                  dC=torch.empty(B * m, self.d, **f32), da=torch.empty(B, self.d, **f32),
+                                  dp=torch.empty(B, self.dr, **f32))
+        self.g_ent = torch.zeros(self.E, self.d, **f32)
+        self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
+        self.loss = torch.zeros((), **f32)
+        nmax = B * (1 + max(self.N.values()))
+        self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(nmax, max(self.d, self.dr)), dtype=torch.uint8,
+                               device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        if use_graph:
+            self._capture()
+
+    def _launch(self):
+        st = lib.stream_ptr(self.ent)
+        model_id = lib.MODELS[self.model.model]
+        ent, rel = self.ent.detach(), self.rel.detach()
+        B, d = self.B, self.d
+        s_idx, p_idx, o_idx = self.triples[0], self.triples[1], self.triples[2]
+        self.g_ent.zero_(); self.g_rel.zero_()
+        for slot in self.slots:
+            b = self.buf[slot]
+            m = 1 + self.N[slot]
+            # slot O: query (s,p) against object candidates; slot S: query (p,o) against subject candidates
+            combine, a_idx, target = (lib.SP_, s_idx, o_idx) if slot == 2 else (lib._PO, o_idx, s_idx)
+            lib.call("kgeb_query_build", model_id, combine, None, ent.data_ptr(), a_idx.data_ptr(), rel.data_ptr(),
+                     p_idx.data_ptr(), 1, B, d, b["Q"].data_ptr(), st)
+            lib.call("kgeb_ns_candidates", target.data_ptr(), self.neg[slot].data_ptr(), B, self.N[slot],
+                     b["cand"].data_ptr(), st)
+            lib.call("kgeb_pairs_score", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), 1, B, m, d,
+                     b["scores"].data_ptr(), st)
+            lib.call("kgeb_ns_loss", self.loss_kind, b["scores"].data_ptr(), B, m, self.offset, 1.0 / B,
+                     b["G"].data_ptr(), b["rows"].data_ptr(), st)
+            lib.call("kgeb_pairs_bwd", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), 1, B, m, d,
+                     b["G"].data_ptr(), b["scores"].data_ptr(), b["dQ"].data_ptr(), b["dC"].data_ptr(), st)
+            lib.call("kgeb_query_bwd", model_id, combine, None, ent.data_ptr(), a_idx.data_ptr(), rel.data_ptr(),
+                     p_idx.data_ptr(), 1, B, d, b["dQ"].data_ptr(), b["da"].data_ptr(), b["dp"].data_ptr(), st)
+            lib.call("kgeb_scatter_add_rows", b["cand"].data_ptr(), 1, b["dC"].data_ptr(), B * m, d,
+                     self.g_ent.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
+            lib.call("kgeb_scatter_add_rows", a_idx.data_ptr(), 1, b["da"].data_ptr(), B, d, self.g_ent.data_ptr(),
+                     self.E, self.sws.data_ptr(), self.sws.numel(), st)
+            lib.call("kgeb_scatter_add_rows", p_idx.data_ptr(), 1, b["dp"].data_ptr(), B, self.dr,
+                     self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st)
+        torch.sum(torch.stack([self.buf[s]["rows"].sum() for s in self.slots]), dim=0, out=self.loss)
+        s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
+        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), ent.numel(), self.lr,
+                 self.eps, 0.0, None, st)
+        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), rel.numel(), self.lr,
+                 self.eps, 0.0, None, st)
+
+    def _capture(self):
+        keep = [t.detach().clone() for t in (self.ent, self.rel, self.opt.state[self.ent]["sum"],
+                                             self.opt.state[self.rel]["sum"])]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._launch()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._launch()
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for dst, src in zip((self.ent, self.rel, self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]),
+                                keep):
+                dst.copy_(src)
+        torch.cuda.synchronize()
+
+    def set_inputs(self, triples: torch.Tensor, negative_samples):
+        """triples [B,3]; negative_samples = list of [B,N_slot] for slots S, P, O (as the reference's collate emits)."""
+        self.triples.copy_(triples.t(), non_blocking=True)
+        for slot in self.slots:
+            self.neg[slot].copy_(negative_samples[slot], non_blocking=True)
+
+    def step(self) -> torch.Tensor:
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+        for st in (self.opt.state[self.ent], self.opt.state[self.rel]):
+            st["step"] += 1
+        torch.autograd.graph.increment_version(self.ent)
+        torch.autograd.graph.increment_version(self.rel)
+        return self.loss

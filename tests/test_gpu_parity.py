@@ -366,3 +366,25 @@ def test_packed_host_batches_equal_dict_batches(kb):
         out = job.step(0, job.collate_packed(batch) if packed else batch)
         res.append((out.avg_loss, m.get_s_embedder().weight.detach().clone()))
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("case", ["train.negative_sampling.rotate.kl", "train.negative_sampling.transe.bce",
+                                  "train.negative_sampling.complex.bce", "train.negative_sampling.distmult.kl"])
+def test_graph_captured_negative_sampling_step_matches_reference_golden(kb, golden, case):
+    g = golden("train")
+    _, _, model, loss = case.split(".")
+    opts = dict(ast.literal_eval(str(g[case + ".options"]))) if case + ".options" in g else {}
+    ln = float(opts.get(model + ".l_norm", 1.0))
+    m = make_model(kb, model, g[case + ".ent0"], g[case + ".rel0"], ln)
+    opt = kb.optim.create("Adagrad", m.parameters(), lr=0.2)
+    job = kb.TrainingJobNegativeSampling(m, opt, kb.KgeLoss.create(loss, float(opts.get("train.loss_arg", 0.0))))
+    negs0 = [T(g[f"{case}.b0.neg{slot}"]) for slot in range(3)]
+    job.enable_graph_step(len(g[case + ".b0.triples"]), negs0[0].shape[1], negs0[2].shape[1])
+    for step in range(2):
+        pre = f"{case}.b{step}"
+        batch = {"triples": T(g[pre + ".triples"]), "negative_samples": [T(g[f"{pre}.neg{slot}"]) for slot in range(3)]}
+        res = job.step(step, batch)
+        assert res.avg_loss == pytest.approx(float(g[pre + ".loss"]), rel=2e-5), f"{case} loss step {step}"
+        for got, ref in ((m.get_s_embedder().weight, g[pre + ".ent"]), (m.get_p_embedder().weight, g[pre + ".rel"])):
+            err = (got.detach().cpu() - T(ref)).abs().max().item()
+            assert err <= 0.2 * 2e-3, f"{case} params step {step}: {err}"
