@@ -26,8 +26,10 @@ struct ScatterWs {
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 static size_t cub_temp_bytes(int64_t n) {
-  size_t a = 0, b = 0, c = 0;
+  size_t a = 0, b = 0, c = 0, c2 = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, c, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+  cub::DeviceRadixSort::SortKeys(nullptr, c2, (const uint64_t*)nullptr, (uint64_t*)nullptr, (int)n);
+  if (c2 > c) c = c2;
   cub::DeviceRadixSort::SortPairs(nullptr, a, (const int64_t*)nullptr, (int64_t*)nullptr, (const int32_t*)nullptr,
                                   (int32_t*)nullptr, (int)n);
   cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
@@ -258,17 +260,18 @@ block_pack_sort_kernel(const void* idx, int idx64, int n, int pb, int kb, int pr
   }
 }
 
+template <typename W>
 __global__ void __launch_bounds__(256)
-packed_sum_phase1(const uint32_t* __restrict__ packed, int n, int pb, int d, const float* __restrict__ rows,
+packed_sum_phase1(const W* __restrict__ packed, int n, int pb, int d, const float* __restrict__ rows,
                   float* __restrict__ dense, int64_t vocab, float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
   const int nchunks = (n + CHUNK - 1) / CHUNK;
   const bool vec = (d & 3) == 0;
-  const uint32_t pmask = (1u << pb) - 1u;
+  const W pmask = ((W)1 << pb) - (W)1;
   for (int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks; ch += gridDim.x * (blockDim.x >> 5)) {
     const int cb = ch * CHUNK;
     const int m = min(CHUNK, n - cb);
-    uint32_t mine = 0xFFFFFFFFu;
+    W mine = ~(W)0;
     if (lane < m) mine = packed[cb + lane];
     const int64_t prev_key = cb > 0 ? (int64_t)(packed[cb - 1] >> pb) : -1;
     const int64_t next_key = cb + m < n ? (int64_t)(packed[cb + m] >> pb) : -2;
@@ -276,7 +279,7 @@ packed_sum_phase1(const uint32_t* __restrict__ packed, int n, int pb, int d, con
     int prw[CHUNK];
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j) {
-      const uint32_t w = __shfl_sync(0xffffffffu, mine, j);
+      const W w = __shfl_sync(0xffffffffu, mine, j);
       key[j] = (int64_t)(w >> pb);
       prw[j] = (int)(w & pmask);
     }
@@ -325,8 +328,9 @@ packed_sum_phase1(const uint32_t* __restrict__ packed, int n, int pb, int d, con
 
 // one warp per chunk whose last run STARTS a segment that continues into the following chunks: it finds the end of
 // the segment by binary search on the sorted ids and adds the partials in chunk order
+template <typename W>
 __global__ void __launch_bounds__(256)
-packed_sum_phase2(const uint32_t* __restrict__ packed, int n, int pb, int d, float* __restrict__ dense, int64_t vocab,
+packed_sum_phase2(const W* __restrict__ packed, int n, int pb, int d, float* __restrict__ dense, int64_t vocab,
                   const float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
   const int nchunks = (n + CHUNK - 1) / CHUNK;
@@ -335,7 +339,7 @@ packed_sum_phase2(const uint32_t* __restrict__ packed, int n, int pb, int d, flo
     const int cb = ch * CHUNK;
     const int m = min(CHUNK, n - cb);
     if (cb + m >= n) continue;                                  // nothing follows the last chunk
-    const uint32_t kq = packed[cb + m - 1] >> pb;               // id of the chunk's last run
+    const W kq = packed[cb + m - 1] >> pb;                      // id of the chunk's last run
     if ((packed[cb + m] >> pb) != kq) continue;                 // it does not continue
     if ((packed[cb] >> pb) == kq && cb > 0 && (packed[cb - 1] >> pb) == kq) continue;  // not the segment's first chunk
     // first position with id > kq: 32-ary search, one probe per lane and round
@@ -390,16 +394,41 @@ static int bits_for(int64_t x) {  // smallest b with 2^b >= x
   return b;
 }
 
-__global__ void pack_keys_kernel(const void* idx, int idx64, int n, int pb, uint32_t* __restrict__ packed) {
+template <typename W>
+__global__ void pack_keys_kernel(const void* idx, int idx64, int n, int pb, W* __restrict__ packed) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) packed[i] = ((uint32_t)load_index(idx, idx64, i) << pb) | (uint32_t)i;
+  if (i < n) packed[i] = ((W)load_index(idx, idx64, i) << pb) | (W)i;
+}
+
+template <typename W>
+static int packed_phases(const W* packed, int64_t n, int pb, int d, const float* rows, float* dense, int64_t vocab,
+                         float* part, cudaStream_t st) {
+  const int nchunks = (int)((n + CHUNK - 1) / CHUNK);
+  int blocks = (nchunks + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  packed_sum_phase1<W><<<blocks, 256, 0, st>>>(packed, (int)n, pb, d, rows, dense, vocab, part);
+  packed_sum_phase2<W><<<blocks, 256, 0, st>>>(packed, (int)n, pb, d, dense, vocab, part);
+  KGEB_LAUNCH_CHECK("packed scatter");
+  return KGEB_OK;
 }
 
 // returns -1 when the packed path does not apply
 static int scatter_small(const void* idx, int idx64, const float* rows, int64_t n, int d, float* dense, int64_t vocab,
                          ScatterWs& w, cudaStream_t st, bool presorted) {
   const int pb = bits_for(n), kb = bits_for(vocab);
-  if (n > (1 << 22) || pb + kb > 32) return -1;
+  if (n > (1 << 26) || pb + kb > 62) return -1;
+  if (pb + kb > 32) {
+    // 64-bit words: coalesced pack, keys-only device radix sort over the id bits (stable -> positions ascending)
+    uint64_t* packed = reinterpret_cast<uint64_t*>(w.keys_in);
+    uint64_t* tmp = reinterpret_cast<uint64_t*>(w.keys_out);
+    pack_keys_kernel<uint64_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, idx64, (int)n, pb, presorted ? packed : tmp);
+    if (!presorted) {
+      size_t bytes = w.cub_bytes;
+      cudaError_t e = cub::DeviceRadixSort::SortKeys(w.cub_tmp, bytes, tmp, packed, (int)n, pb, pb + kb, st);
+      if (e != cudaSuccess) return cuda_status(e, "radix sort (packed64)");
+    }
+    return packed_phases<uint64_t>(packed, n, pb, d, rows, dense, vocab, w.part, st);
+  }
   uint32_t* packed = reinterpret_cast<uint32_t*>(w.keys_in);
   if (n <= 8192) {
     using Sort = cub::BlockRadixSort<uint32_t, 1024, 8>;
@@ -410,20 +439,14 @@ static int scatter_small(const void* idx, int idx64, const float* rows, int64_t 
   } else {
     // multi-block: coalesced pack, then a keys-only device radix sort over the id bits (stable -> positions ascending)
     uint32_t* tmp = reinterpret_cast<uint32_t*>(w.keys_out);
-    pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, idx64, (int)n, pb, presorted ? packed : tmp);
+    pack_keys_kernel<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, idx64, (int)n, pb, presorted ? packed : tmp);
     if (!presorted) {
       size_t bytes = w.cub_bytes;
       cudaError_t e = cub::DeviceRadixSort::SortKeys(w.cub_tmp, bytes, tmp, packed, (int)n, pb, pb + kb, st);
       if (e != cudaSuccess) return cuda_status(e, "radix sort (packed)");
     }
   }
-  const int nchunks = (int)((n + CHUNK - 1) / CHUNK);
-  int blocks = (nchunks + 7) / 8;
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  packed_sum_phase1<<<blocks, 256, 0, st>>>(packed, (int)n, pb, d, rows, dense, vocab, w.part);
-  packed_sum_phase2<<<blocks, 256, 0, st>>>(packed, (int)n, pb, d, dense, vocab, w.part);
-  KGEB_LAUNCH_CHECK("packed scatter");
-  return KGEB_OK;
+  return packed_phases<uint32_t>(packed, n, pb, d, rows, dense, vocab, w.part, st);
 }
 
 template <bool DENSE>
