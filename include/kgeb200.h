@@ -169,8 +169,9 @@ int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int6
 
 /* ---- a21/K11: optimizer steps with torch.optim semantics (util/optimizer.py:10-17).
  * Adagrad: g += wd*w; state += g*g; w -= clr * g / (sqrt(state) + eps), clr = lr/(1+(step-1)*lr_decay) */
-int kgeb_adagrad_dense(float* W, float* state, const float* grad, int64_t numel, float clr, float eps,
-                       float weight_decay, void* bf16_mirror /* updated alongside W, or NULL */, void* stream);
+int kgeb_adagrad_dense(float* W, float* state, const float* grad, const float* grad2 /* added to grad, or NULL */,
+                       int64_t numel, float clr, float eps, float weight_decay,
+                       void* bf16_mirror /* updated alongside W, or NULL */, void* stream);
 /* touched-rows-only Adagrad (equals the dense step when untouched rows have zero gradient and wd=0) */
 int kgeb_adagrad_rows(float* W, float* state, const int64_t* row_ids, const float* row_grads,
                       const int64_t* num_rows_dev, int64_t max_rows, int d, float clr, float eps, void* stream);

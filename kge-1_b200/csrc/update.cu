@@ -492,13 +492,18 @@ static int sort_and_segment(const void* idx, int idx64, int64_t n, int64_t vocab
 // optimizers
 // ------------------------------------------------------------------------------------------
 __global__ void adagrad_dense_kernel(float* __restrict__ W, float* __restrict__ state, const float* __restrict__ grad,
-                                     int64_t numel, float clr, float eps, float wd, __nv_bfloat16* __restrict__ mirror) {
+                                     const float* __restrict__ grad2, int64_t numel, float clr, float eps, float wd,
+                                     __nv_bfloat16* __restrict__ mirror) {
   int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (; i + 3 < numel; i += stride) {
     float4 w = *reinterpret_cast<float4*>(W + i);
     float4 s = *reinterpret_cast<float4*>(state + i);
     float4 g = *reinterpret_cast<const float4*>(grad + i);
+    if (grad2) {  // gradient accumulated in two buffers (dense / query-side parts written on different streams)
+      const float4 h = *reinterpret_cast<const float4*>(grad2 + i);
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    }
     g.x = fmaf(wd, w.x, g.x); g.y = fmaf(wd, w.y, g.y); g.z = fmaf(wd, w.z, g.z); g.w = fmaf(wd, w.w, g.w);
     s.x = fmaf(g.x, g.x, s.x); s.y = fmaf(g.y, g.y, s.y); s.z = fmaf(g.z, g.z, s.z); s.w = fmaf(g.w, g.w, s.w);
     w.x -= clr * g.x / (sqrtf(s.x) + eps);
@@ -518,7 +523,7 @@ __global__ void adagrad_dense_kernel(float* __restrict__ W, float* __restrict__ 
   // tail (numel % 4): handled by the thread whose i lands on it
   if (i < numel && i + 3 >= numel) {
     for (int64_t j = i; j < numel; ++j) {
-      float g = fmaf(wd, W[j], grad[j]);
+      float g = fmaf(wd, W[j], grad[j] + (grad2 ? grad2[j] : 0.f));
       float s = fmaf(g, g, state[j]);
       state[j] = s;
       W[j] -= clr * g / (sqrtf(s) + eps);
@@ -628,15 +633,16 @@ int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int6
   return segment_sums<false>(w, n, d, rows, nullptr, 0, uniq_ids, uniq_rows, st);
 }
 
-int kgeb_adagrad_dense(float* W, float* state, const float* grad, int64_t numel, float clr, float eps,
-                       float weight_decay, void* bf16_mirror, void* stream) {
+int kgeb_adagrad_dense(float* W, float* state, const float* grad, const float* grad2, int64_t numel, float clr,
+                       float eps, float weight_decay, void* bf16_mirror, void* stream) {
   KGEB_REQUIRE(W && state && grad && numel >= 0, "adagrad_dense: bad arguments");
   KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(state) |
-                 reinterpret_cast<uintptr_t>(grad)) & 15) == 0, "adagrad_dense: pointers must be 16-byte aligned");
+                 reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(grad2)) & 15) == 0,
+               "adagrad_dense: pointers must be 16-byte aligned");
   if (numel == 0) return KGEB_OK;
   int64_t blocks = (numel / 4 + 255) / 256 + 1;
   int grid = (int)(blocks > (int64_t)kNumSMs * 8 ? (int64_t)kNumSMs * 8 : blocks);
-  adagrad_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, state, grad, numel, clr, eps, weight_decay,
+  adagrad_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, state, grad, grad2, numel, clr, eps, weight_decay,
                                                             reinterpret_cast<__nv_bfloat16*>(bf16_mirror));
   KGEB_LAUNCH_CHECK("adagrad_dense");
   return KGEB_OK;

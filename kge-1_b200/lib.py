@@ -45,7 +45,7 @@ SIGNATURES = {
     "kgeb_rank_count": [_i, _i, _p, _l, _i, _p, _l, _l, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "kgeb_scatter_add_rows": [_p, _i, _p, _l, _i, _p, _l, _p, _l, _p],
     "kgeb_segment_reduce_rows": [_p, _i, _p, _l, _i, _p, _p, _p, _p, _l, _p],
-    "kgeb_adagrad_dense": [_p, _p, _p, _l, _f, _f, _f, _p, _p],
+    "kgeb_adagrad_dense": [_p, _p, _p, _p, _l, _f, _f, _f, _p, _p],
     "kgeb_adagrad_rows": [_p, _p, _p, _p, _p, _l, _i, _f, _f, _p],
     "kgeb_adam_dense": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p],
     "kgeb_csr_lookup": [_p, _l, _p, _l, _p, _p],

@@ -45,8 +45,8 @@ class Adagrad(torch.optim.Optimizer):
                              lib.stream_ptr(p))
                 else:
                     lib.call("kgeb_adagrad_dense", lib.f32(p.data, "param"), lib.f32(st["sum"], "state"),
-                             lib.f32(g.contiguous(), "grad"), p.numel(), clr, group["eps"], group["weight_decay"],
-                             None, lib.stream_ptr(p))
+                             lib.f32(g.contiguous(), "grad"), None, p.numel(), clr, group["eps"],
+                             group["weight_decay"], None, lib.stream_ptr(p))
                 torch.autograd.graph.increment_version(p)  # the kernel wrote through the raw pointer
         return loss
 

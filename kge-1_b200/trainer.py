@@ -53,7 +53,8 @@ class FusedAllEntityStepper:
         self.dQ = torch.empty(rows, self.d, **f32)
         self.da = torch.empty(rows, self.d, **f32)
         self.dp = torch.empty(rows, self.dr, **f32)
-        self.g_ent = torch.zeros(self.E, self.d, **f32)
+        self.g_ent = torch.zeros(self.E, self.d, **f32)     # dense part (G^T Q) + label rows: written on the side stream
+        self.g_q = torch.zeros(self.E, self.d, **f32)       # query-side rows (da scattered by entity id)
         self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
         self.rowstat = torch.empty(rows, 4, **f32)
         self.loss = torch.zeros((), **f32)
@@ -66,6 +67,8 @@ class FusedAllEntityStepper:
                               dtype=torch.uint8, device=dev)
         self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(rows, max(self.d, self.dr)), dtype=torch.uint8,
                                device=dev)
+        self.ws2 = torch.empty_like(self.ws)   # workspace of the dTable half of the backward (runs on a second stream)
+        self.side = torch.cuda.Stream(device=dev)
         self.mirror = None
         if math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256:
             self.mirror = torch.empty(self.E, self.d, dtype=torch.bfloat16, device=dev)
@@ -86,7 +89,7 @@ class FusedAllEntityStepper:
         model_id = lib.MODELS[self.model.model]
         ent, rel = self.ent.detach(), self.rel.detach()
         sh = self.shard
-        self.g_ent.zero_(); self.g_rel.zero_()
+        self.g_ent.zero_(); self.g_q.zero_(); self.g_rel.zero_()
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
         if not self._fused_stats_in_backward():
@@ -107,12 +110,25 @@ class FusedAllEntityStepper:
         late_stats = self._fused_stats_in_backward()
         if not late_stats:
             self._loss_kernel()   # KL needs the log-sum-exp before the backward
-        lib.call("kgeb_fused_bwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
-                 ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
-                 self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
-                 self.lse.data_ptr() if self.loss_kind == lib.LOSS_KL else None, 1.0 / self.batch_size, None,
-                 self._mirror_ptr(), self.dQ.data_ptr(), self.g_ent[sh.e_lo:sh.e_hi].data_ptr(),
-                 self.rowstat.data_ptr() if late_stats else None, self.ws.data_ptr(), self.ws.numel(), st)
+        lse = self.lse.data_ptr() if self.loss_kind == lib.LOSS_KL else None
+        common = (self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent[sh.e_lo:sh.e_hi].data_ptr(),
+                  sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls,
+                  self.offset, lse, 1.0 / self.batch_size, None, self._mirror_ptr())
+        # The two halves of the backward are independent: the dense table gradient (+ its label rows) goes to a second
+        # stream, so that the chain of small latency-bound kernels that follows dQ on this stream (partial reduce, label
+        # scatter, query-transform backward, sorted scatters) runs underneath the dTable tile kernel.
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            lib.call("kgeb_fused_bwd", *common, None, self.g_ent[sh.e_lo:sh.e_hi].data_ptr(), None, self.ws2.data_ptr(),
+                     self.ws2.numel(), lib.stream_ptr(self.ent))
+        lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late_stats else None,
+                 self.ws.data_ptr(), self.ws.numel(), st)
+        if sh.distributed:
+            self._join_side()     # the collectives that follow need the complete dense gradient
+
+    def _join_side(self):
+        torch.cuda.current_stream().wait_stream(self.side)
 
     def _stage_update(self):
         if self._fused_stats_in_backward():
@@ -124,14 +140,16 @@ class FusedAllEntityStepper:
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.dQ.data_ptr(), self.da.data_ptr(),
                  self.dp.data_ptr(), st)
         lib.call("kgeb_scatter_add_rows", self.a_idx.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
-                 self.g_ent.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
+                 self.g_q.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
         lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
                  self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st)
         s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
-        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), ent.numel(), self.lr,
-                 self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st)
-        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), rel.numel(), self.lr,
-                 self.eps, 0.0, None, st)
+        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
+                 self.lr, self.eps, 0.0, None, st)
+        if not self.shard.distributed:
+            self._join_side()     # dense table gradient from the side stream
+        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
+                 ent.numel(), self.lr, self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st)
 
     def _mirror_ptr(self):
         return None if self.mirror is None else self.mirror[self.shard.e_lo:self.shard.e_hi].data_ptr()
@@ -156,10 +174,14 @@ class FusedAllEntityStepper:
         self._exchange_grads()
         self._stage_update()
 
-    # kernels of this library per step (bench.py gpu_launches): query build 1, fwd tiles + label dot + row sums +
-    # finalize + bf16(Q) 5, loss 1, bwd (label rows, bf16(Q), label weights, 2 tensor-tile kernels, partial reduce,
-    # presorted scatter 5, sorted scatter 8) 19, query bwd 1, two sorted scatters 16, two Adagrad 2
-    kernel_launches_per_step = 45
+    @property
+    def kernel_launches_per_step(self) -> int:
+        """Kernels of this library per step (bench.py gpu_launches), counted from the ncu launch lists under profiles/:
+        query build 1; dTable half 11 (label weights, bf16(Q), label rows, tile kernel, pack, 4 radix-sort kernels,
+        2 segment-sum phases); dQ half 10 (label weights, bf16(Q), label rows, tile kernel, partial reduce, pack,
+        2 segment-sum phases, label row sums, statistics reduce); loss 1; query backward 1; two sorted scatters 6;
+        Adagrad 2.  KL (or fp32 math) adds the 5 forward-statistics kernels."""
+        return 32 + (0 if self._fused_stats_in_backward() else 5)
 
     def _capture(self):
         """CUDA graphs of the three stages; NCCL collectives (sharded mode) stay outside the graphs."""
@@ -324,10 +346,10 @@ class FusedNegSamplingStepper:
                      self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st)
         torch.sum(torch.stack([self.buf[s]["rows"].sum() for s in self.slots]), dim=0, out=self.loss)
         s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
-        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), ent.numel(), self.lr,
-                 self.eps, 0.0, None, st)
-        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), rel.numel(), self.lr,
-                 self.eps, 0.0, None, st)
+        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), None, ent.numel(),
+                 self.lr, self.eps, 0.0, None, st)
+        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
+                 self.lr, self.eps, 0.0, None, st)
 
     def _capture(self):
         keep = [t.detach().clone() for t in (self.ent, self.rel, self.opt.state[self.ent]["sum"],
