@@ -68,7 +68,9 @@ class FusedAllEntityStepper:
         self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(rows, max(self.d, self.dr)), dtype=torch.uint8,
                                device=dev)
         self.ws2 = torch.empty_like(self.ws)   # workspace of the dTable half of the backward (runs on a second stream)
+        self.sws2 = torch.empty_like(self.sws)  # scatter workspace of the relation-side chain (third stream)
         self.side = torch.cuda.Stream(device=dev)
+        self.side2 = torch.cuda.Stream(device=dev)
         self.mirror = None
         if math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256:
             self.mirror = torch.empty(self.E, self.d, dtype=torch.bfloat16, device=dev)
@@ -131,25 +133,32 @@ class FusedAllEntityStepper:
         torch.cuda.current_stream().wait_stream(self.side)
 
     def _stage_update(self):
-        if self._fused_stats_in_backward():
-            self._loss_kernel()
         st = lib.stream_ptr(self.ent)
         model_id = lib.MODELS[self.model.model]
         ent, rel = self.ent.detach(), self.rel.detach()
         lib.call("kgeb_query_bwd", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.dQ.data_ptr(), self.da.data_ptr(),
                  self.dp.data_ptr(), st)
+        # relation-side chain (loss value, dp scatter, relation Adagrad) on a third stream, entity-side scatter here
+        cur = torch.cuda.current_stream()
+        self.side2.wait_stream(cur)
+        with torch.cuda.stream(self.side2):
+            st2 = lib.stream_ptr(self.ent)
+            if self._fused_stats_in_backward():
+                self._loss_kernel()
+            lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
+                     self.g_rel.data_ptr(), self.rel.shape[0], self.sws2.data_ptr(), self.sws2.numel(), st2)
+            s_rel = self.opt.state[self.rel]["sum"]
+            lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
+                     self.lr, self.eps, 0.0, None, st2)
         lib.call("kgeb_scatter_add_rows", self.a_idx.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
                  self.g_q.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
-        lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
-                 self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st)
-        s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
-        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
-                 self.lr, self.eps, 0.0, None, st)
         if not self.shard.distributed:
             self._join_side()     # dense table gradient from the side stream
+        s_ent = self.opt.state[self.ent]["sum"]
         lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
                  ent.numel(), self.lr, self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st)
+        cur.wait_stream(self.side2)
 
     def _mirror_ptr(self):
         return None if self.mirror is None else self.mirror[self.shard.e_lo:self.shard.e_hi].data_ptr()
