@@ -592,6 +592,10 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       }
     }
     if (dTable) {
+      // label rows first: the tile kernel below adds on top (it owns its rows; both orders are deterministic), and in
+      // the two-stream step this small sorted scatter then runs underneath the other stream's dQ tile kernel
+      if (nnz > 0 && (rc = kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st)))
+        return rc;
       Plan pl = make_plan(false, true, B, d, n_ent);
       if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
       pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
@@ -599,8 +603,6 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       if ((rc = make_map(&m_res, tableb, n_ent, d, RES_ROWS, true)) || (rc = make_map(&m_str, Qb, B, d, STR_ROWS, true))) return rc;
       const int64_t jobs = pl.p.n_res_blocks;
       if ((rc = launch_bwd<false>(pl, m_res, m_str, jobs, st))) return rc;
-      if (nnz > 0 && (rc = kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st)))
-        return rc;
     }
   } else if (dQ && B > 0) {
     cudaMemsetAsync(dQ, 0, (size_t)B * d * 4, st);
