@@ -151,6 +151,9 @@ def main():
     ap.add_argument("--math", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--cpu-steps", type=int, default=8, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--parallel", default="dp", choices=["dp", "shard"],
+                    help="N>1: dp = data-parallel replicas + one gradient all-reduce (graphs too small to shard); "
+                         "shard = entity-sharded scoring (SURVEY.md 8e)")
     ap.add_argument("--profile-calls", action="store_true", help="print GPU time per C-ABI call of one step and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -187,8 +190,9 @@ def main():
     n_batches = args.steps + args.warmup
     # entity-sharded scoring: every rank processes the whole global batch (world * B queries) against its own
     # entity range, so all ranks build the same batches (weak scaling: per-GPU work B x E stays fixed)
-    GB = B * world
-    graph, batches = build_batches(n_batches, GB, seed=7, rank=0)
+    sharded = world > 1 and args.parallel == "shard"
+    GB = B * world if sharded else B          # rows each rank processes per step
+    graph, batches = build_batches(n_batches, GB, seed=7, rank=0 if sharded else rank)
     E, R = graph["num_entities"], graph["num_relations"]
     nnz_max = max(int(b["label_coords"].shape[0]) for b in batches)
     for b in batches:
@@ -198,10 +202,11 @@ def main():
     torch.manual_seed(0)
     model = kb.KgeModel("complex", E, R, DIM).to(dev)
     opt = kb.optim.create("Adagrad", model.parameters(), lr=LR)
-    shard = kb.fused.Shard.of_rank(E, rank, world, dist.group.WORLD) if world > 1 else None
+    shard = kb.fused.Shard.of_rank(E, rank, world, dist.group.WORLD) if sharded else None
     job = kb.TrainingJobKvsAll(model, opt, kb.KgeLoss.create("bce"), E, R, fused_path=True, math_mode=math_mode,
                                shard=shard)
-    job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph)  # NCCL all-reduces are captured too
+    job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph,
+                          dp_group=dist.group.WORLD if (world > 1 and not sharded) else None)
     stepper = job.stepper
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -277,7 +282,10 @@ def main():
         "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.math], "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "optimizer": "Adagrad lr 0.2",
                    "math": args.math + " tensor tiles, fp32 accumulate, fp32 master tables and optimizer",
-                   "parallelism": "1 GPU" if world == 1 else f"entity-sharded scoring over {world} GPUs",
+                   "parallelism": "1 GPU" if world == 1 else (
+                       f"entity-sharded scoring over {world} GPUs (all-reduce of row statistics, dQ, dense gradient)"
+                       if sharded else f"dp{world}: replicas with one all-reduce of both tables' gradients + loss per "
+                                       "step (FB15k-237-sized tables are too small to shard, SURVEY.md 8e)"),
                    "l2": "flushed between timed steps (256 MiB write, untimed); table is 7.4 MB",
                    "cuda_graph": stepper.graph is not None, "final_loss": final_loss},
         "clocks": clocks.summary(),

@@ -130,7 +130,7 @@ class TrainingJobKvsAll(TrainingJob):
         self.stepper = None
 
     # -- static-shape, graph-captured step (trainer.py) ---------------------------------------------------
-    def enable_graph_step(self, batch_size: int, nnz_max: int, use_graph: bool = True):
+    def enable_graph_step(self, batch_size: int, nnz_max: int, use_graph: bool = True, dp_group=None):
         """Routes step() through FusedAllEntityStepper for batches of exactly `batch_size` queries with at most
         `nnz_max` labels (no autograd, one CUDA-graph replay per step).  Needs the DOT scorers, dense Adagrad
         and no penalty terms."""
@@ -140,7 +140,7 @@ class TrainingJobKvsAll(TrainingJob):
             raise NotImplementedError("penalty terms are not part of the graph-captured step")
         self.stepper = FusedAllEntityStepper(self.model, self.optimizer, batch_size, nnz_max, self.loss.kind,
                                              batch_size, self.loss.offset, self.label_smoothing, self.math_mode,
-                                             use_graph, self.shard)
+                                             use_graph, self.shard, dp_group)
         return self.stepper
 
     def device_inputs(self, batch):

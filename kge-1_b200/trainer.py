@@ -22,7 +22,7 @@ from .model import KgeModel
 class FusedAllEntityStepper:
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
-                 use_graph: bool = True, shard: Optional[fused.Shard] = None):
+                 use_graph: bool = True, shard: Optional[fused.Shard] = None, dp_group=None):
         if model.get_scorer().kind != lib.DOT:
             raise NotImplementedError("the fused all-entity step serves the DOT scorers")
         self.model, self.opt = model, optimizer
@@ -53,11 +53,23 @@ class FusedAllEntityStepper:
         self.dQ = torch.empty(rows, self.d, **f32)
         self.da = torch.empty(rows, self.d, **f32)
         self.dp = torch.empty(rows, self.dr, **f32)
-        self.g_ent = torch.zeros(self.E, self.d, **f32)     # dense part (G^T Q) + label rows: written on the side stream
-        self.g_q = torch.zeros(self.E, self.d, **f32)       # query-side rows (da scattered by entity id)
-        self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
+        # gradients and the loss live in ONE flat buffer so that data-parallel replicas need a single all-reduce
+        n_e, n_r = self.E * self.d, self.rel.shape[0] * self.dr
+        self.gflat = torch.zeros(2 * n_e + n_r + 1, **f32)
+        self.g_ent = self.gflat[:n_e].view(self.E, self.d)            # dense part (G^T Q) + label rows (side stream)
+        self.g_q = self.gflat[n_e:2 * n_e].view(self.E, self.d)       # query-side rows (da scattered by entity id)
+        self.g_rel = self.gflat[2 * n_e:2 * n_e + n_r].view(self.rel.shape[0], self.dr)
+        self.loss = self.gflat[2 * n_e + n_r:].view(())
         self.rowstat = torch.empty(rows, 4, **f32)
-        self.loss = torch.zeros((), **f32)
+        # Data parallelism for graphs too small to shard (SURVEY.md 8e "replicas" row): every rank trains on its own
+        # batch against its full replica; one all-reduce sums gradients and loss; loss terms are divided by the global
+        # batch size so all replicas apply the identical update.
+        self.dp_group = dp_group
+        self.dp_world = 1
+        if dp_group is not None:
+            import torch.distributed as dist
+            self.dp_world = dist.get_world_size(dp_group)
+        self.global_batch = batch_size * self.dp_world
         self.lse = torch.zeros(rows, **f32)
         # Multi-GPU: every rank sees the whole batch and scores it against its own entity range
         # [e_lo, e_hi); row statistics, dQ and the dense table gradient are all-reduced over NVLink.  The (small)
@@ -91,7 +103,7 @@ class FusedAllEntityStepper:
         model_id = lib.MODELS[self.model.model]
         ent, rel = self.ent.detach(), self.rel.detach()
         sh = self.shard
-        self.g_ent.zero_(); self.g_q.zero_(); self.g_rel.zero_()
+        self.gflat.zero_()
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
         if not self._fused_stats_in_backward():
@@ -102,7 +114,7 @@ class FusedAllEntityStepper:
 
     def _loss_kernel(self):
         lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
-                 self.ls, self.E, 1.0 / self.batch_size, None, self.lse.data_ptr(), self.loss.data_ptr(),
+                 self.ls, self.E, 1.0 / self.global_batch, None, self.lse.data_ptr(), self.loss.data_ptr(),
                  lib.stream_ptr(self.ent))
 
     def _stage_backward(self):
@@ -115,7 +127,7 @@ class FusedAllEntityStepper:
         lse = self.lse.data_ptr() if self.loss_kind == lib.LOSS_KL else None
         common = (self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent[sh.e_lo:sh.e_hi].data_ptr(),
                   sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls,
-                  self.offset, lse, 1.0 / self.batch_size, None, self._mirror_ptr())
+                  self.offset, lse, 1.0 / self.global_batch, None, self._mirror_ptr())
         # The two halves of the backward are independent: the dense table gradient (+ its label rows) goes to a second
         # stream, so that the chain of small latency-bound kernels that follows dQ on this stream (partial reduce, label
         # scatter, query-transform backward, sorted scatters) runs underneath the dTable tile kernel.
@@ -148,17 +160,36 @@ class FusedAllEntityStepper:
                 self._loss_kernel()
             lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
                      self.g_rel.data_ptr(), self.rel.shape[0], self.sws2.data_ptr(), self.sws2.numel(), st2)
-            s_rel = self.opt.state[self.rel]["sum"]
-            lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
-                     self.lr, self.eps, 0.0, None, st2)
+            if self.dp_world == 1:
+                s_rel = self.opt.state[self.rel]["sum"]
+                lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
+                         self.lr, self.eps, 0.0, None, st2)
         lib.call("kgeb_scatter_add_rows", self.a_idx.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
                  self.g_q.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
+        if self.dp_world > 1:
+            cur.wait_stream(self.side2)      # gradients complete on this stream before the all-reduce
+            self._join_side()
+            return
         if not self.shard.distributed:
             self._join_side()     # dense table gradient from the side stream
         s_ent = self.opt.state[self.ent]["sum"]
         lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
                  ent.numel(), self.lr, self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st)
         cur.wait_stream(self.side2)
+
+    def _stage_apply_dp(self):
+        """Data-parallel mode: both Adagrad steps after the gradient all-reduce."""
+        st = lib.stream_ptr(self.ent)
+        ent, rel = self.ent.detach(), self.rel.detach()
+        s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
+        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
+                 self.lr, self.eps, 0.0, None, st)
+        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
+                 ent.numel(), self.lr, self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st)
+
+    def _exchange_dp(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.gflat, group=self.dp_group)   # gradients of both tables and the loss in one collective
 
     def _mirror_ptr(self):
         return None if self.mirror is None else self.mirror[self.shard.e_lo:self.shard.e_hi].data_ptr()
@@ -182,6 +213,9 @@ class FusedAllEntityStepper:
         self._stage_backward()
         self._exchange_grads()
         self._stage_update()
+        if self.dp_world > 1:
+            self._exchange_dp()
+            self._stage_apply_dp()
 
     @property
     def kernel_launches_per_step(self) -> int:
@@ -203,8 +237,13 @@ class FusedAllEntityStepper:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graphs = []
-        stages = ([self._stage_forward, self._stage_backward, self._stage_update] if self.shard.distributed
-                  else [lambda: (self._stage_forward(), self._stage_backward(), self._stage_update())])
+        whole = lambda: (self._stage_forward(), self._stage_backward(), self._stage_update())
+        if self.shard.distributed:
+            stages = [self._stage_forward, self._stage_backward, self._stage_update]
+        elif self.dp_world > 1:
+            stages = [whole, self._stage_apply_dp]
+        else:
+            stages = [whole]
         for fn in stages:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -258,6 +297,10 @@ class FusedAllEntityStepper:
             self._launch()
         elif len(self.graphs) == 1:
             self.graphs[0].replay()
+        elif self.dp_world > 1:
+            self.graphs[0].replay()
+            self._exchange_dp()
+            self.graphs[1].replay()
         else:
             self.graphs[0].replay()
             self._exchange_stats()

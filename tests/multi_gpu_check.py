@@ -52,6 +52,36 @@ def main():
                 assert err <= 5e-3 if math_mode == kb.lib.MATH_BF16 else err <= 1e-4, (math_mode, use_graph, i, err)
         if rank == 0:
             print(f"sharded step == single-GPU step (math={math_mode}, graph={use_graph})")
+    # data-parallel replicas: rank r trains on batch r; one all-reduce of gradients + loss == single GPU on the
+    # concatenated (global) batch
+    def cat_batches(bs):
+        off, q, c, t = 0, [], [], []
+        for x in bs:
+            cc = x["label_coords"].clone()
+            cc[:, 0] += off
+            off += len(x["queries"])
+            q.append(x["queries"]); c.append(cc); t.append(x["query_type_indexes"])
+        return {"queries": torch.cat(q), "label_coords": torch.cat(c), "query_type_indexes": torch.cat(t)}
+
+    if world == 2:
+        torch.manual_seed(0)
+        ref = kb.KgeModel("complex", e, r, d).to(dev)
+        new = kb.KgeModel("complex", e, r, d).to(dev)
+        new.load_state_dict(ref.state_dict())
+        jr = kb.TrainingJobKvsAll(ref, kb.optim.create("Adagrad", ref.parameters(), lr=0.2), kb.KgeLoss.create("bce"),
+                                  e, r, math_mode=kb.lib.MATH_BF16)
+        glob = cat_batches(batches[:2])
+        jr.enable_graph_step(2 * b, len(glob["label_coords"]), use_graph=False)
+        jn = kb.TrainingJobKvsAll(new, kb.optim.create("Adagrad", new.parameters(), lr=0.2), kb.KgeLoss.create("bce"),
+                                  e, r, math_mode=kb.lib.MATH_BF16)
+        jn.enable_graph_step(b, nnz_max, use_graph=True, dp_group=dist.group.WORLD)
+        a, c = jr.step(0, glob), jn.step(0, batches[rank])
+        assert abs(a.avg_loss - c.avg_loss) <= 1e-4 * abs(a.avg_loss), (a.avg_loss, c.avg_loss)
+        err = (ref.get_s_embedder().weight - new.get_s_embedder().weight).abs().max().item()
+        assert err <= 5e-3, err
+        if rank == 0:
+            print("data-parallel step (one flat all-reduce) == single-GPU step on the global batch; loss", c.avg_loss)
+
     # sharded filtered ranking: integer counts are exact under sharding
     torch.manual_seed(0)
     m = kb.KgeModel("transe", e, r, d).to(dev)
