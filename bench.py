@@ -361,8 +361,8 @@ def kernel_roofline(kb, stepper, math_mode, B, E):
                L.stream_ptr(ent))
 
     cases = {"tc_tiles_kernel<stats> (fused_fwd)": (fwd, 1, "tc::tc_tiles_kernel<1, 2, 1>"),
-             "tc_bwd_kernel<dQ> (fused_bwd)": (lambda: bwd(True, False), 2, "tcb::tc_bwd_kernel<1, 1, 1, 0>"),
-             "tc_bwd_kernel<dTable> (fused_bwd)": (lambda: bwd(False, True), 2, "tcb::tc_bwd_kernel<0, 1, 1, 0>")}
+             "tc_bwd_kernel<dQ> (fused_bwd)": (lambda: bwd(True, False), 2, "tc_bwd_kernel<1, 1, 1, 0, 1>"),
+             "tc_bwd_kernel<dTable> (fused_bwd)": (lambda: bwd(False, True), 2, "tc_bwd_kernel<0, 1, 1, 0, 0>")}
     res = {}
     for name, (fn, gemms, _) in cases.items():
         ts = []
