@@ -155,6 +155,8 @@ def main():
                     help="N>1: dp = data-parallel replicas + one gradient all-reduce (graphs too small to shard); "
                          "shard = entity-sharded scoring (SURVEY.md 8e)")
     ap.add_argument("--profile-calls", action="store_true", help="print GPU time per C-ABI call of one step and exit")
+    ap.add_argument("--timeline", action="store_true",
+                    help="write the kernel timeline of one step (CUPTI) to gpurun_out/timeline_bench.txt and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +214,9 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     if args.profile_calls:
         profile_calls(kb, job, stepper, batches)
+        return
+    if args.timeline:
+        step_timeline(job, stepper, batches, flush)
         return
 
     def barrier():
@@ -332,6 +337,34 @@ def profile_calls(kb, job, stepper, batches):
     print(f"{tot:9.1f} us/step  total of C-ABI calls")
 
 
+def step_timeline(job, stepper, batches, flush):
+    """Start / duration / stream of every kernel of one step as CUPTI sees it (diagnostic; not a bench number)."""
+    from torch.profiler import profile, ProfilerActivity
+    for i in range(3):
+        stepper.set_inputs(*job.device_inputs(batches[i]))
+        stepper.step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(3, 6):
+            stepper.set_inputs(*job.device_inputs(batches[i]))
+            flush.fill_(i)
+            torch.cuda.synchronize()
+            stepper.step()
+            torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    # last step = everything after the last L2-flush fill
+    last = max(i for i, e in enumerate(evs) if "FillFunctor<unsigned char>" in e.name)
+    evs = evs[last + 1:]
+    t0 = evs[0].time_range.start
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "timeline_bench.txt"), "w") as f:
+        f.write("# start_us  dur_us  end_us  name   (one CUDA-graph replay of the training step)\n")
+        for e in evs:
+            st = e.time_range.start - t0
+            f.write(f"{st:9.1f} {e.device_time:8.1f} {st + e.device_time:9.1f}  {e.name[:110]}\n")
+
+
 def kernel_roofline(kb, stepper, math_mode, B, E):
     """Times the three tensor-tile kernels of a step in isolation (CUDA events on the launching stream, L2 flushed
     between launches; an empty label CSR so that only the tile kernel and its tiny pre/post kernels run) and reports the
@@ -356,7 +389,7 @@ def kernel_roofline(kb, stepper, math_mode, B, E):
 
     def bwd(dq, dt):
         L.call("kgeb_fused_bwd", st.loss_kind, math_mode, st.Q.data_ptr(), B, d, ent.data_ptr(), 0, E, E,
-               off0.data_ptr(), st.lab_col.data_ptr(), 0, st.ls, st.offset, lse.data_ptr(), 1.0 / B, None,
+               off0.data_ptr(), st.lab_col.data_ptr(), 0, None, st.ls, st.offset, lse.data_ptr(), 1.0 / B, None,
                mp, st.dQ.data_ptr() if dq else None, gtmp.data_ptr() if dt else None, None, st.ws.data_ptr(), st.ws.numel(),
                L.stream_ptr(ent))
 

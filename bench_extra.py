@@ -32,6 +32,29 @@ def timed(fn, steps, warmup):
     return a.elapsed_time(b) / steps
 
 
+def kernel_table(fn, steps, tag):
+    """Per-kernel device times of `steps` calls of fn through CUPTI activity tracing (torch.profiler); written to
+    gpurun_out/kernels_<tag>.txt.  Diagnostic only: the numbers reported as results are timed without it."""
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+    rows = {}
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            r = rows.setdefault(ev.name, [0, 0.0])
+            r[0] += 1
+            r[1] += ev.device_time
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    total = sum(r[1] for r in rows.values())
+    with open(os.path.join(ROOT, "gpurun_out", f"kernels_{tag}.txt"), "w") as f:
+        f.write(f"# {tag}: {steps} steps, {total / steps:.1f} us of kernel time per step\n")
+        for name, (cnt, us) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{us / steps:10.1f} us/step  {cnt / steps:6.1f} launches/step  {us / cnt:9.1f} us avg  {name[:150]}\n")
+
+
 def peaks():
     p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     return p.get("hbm_gbs", 6650.0), p.get("bf16_tflops_sustained", 1400.0)
@@ -61,6 +84,8 @@ def wd5m_1vsall(args):
         st.step()
 
     ms = timed(step, args.steps, args.warmup)
+    if args.kernels:
+        kernel_table(step, 3, f"wd5m_1vsall_B{B}")
     hbm, tf = peaks()
     flops = 5 * 2.0 * (2 * B) * E * d   # 1 forward + 2x2 backward GEMMs (S recomputed per output)
     # bytes this implementation moves per step: 3 bf16 table reads (fwd, dQ, dTable), gradient zero + RMW,
@@ -99,6 +124,8 @@ def wnrr_rotate_ns(args):
         i[0] += 1
 
     ms = timed(step, args.steps, args.warmup)
+    if args.kernels:
+        kernel_table(step, 3, "wnrr_rotate_ns" + ("_graph" if args.graph_step else ""))
     hbm, _ = peaks()
     bytes_step = B * 2 * (1 + N) * d * 4 * 2   # gather of each candidate row + write of its gradient row
     return {"workload": f"RotatE NS 2x{N} negatives d=128 E={E} B={B} ({'reference flow' if args.reference_flow else ('graph-captured fused step' if args.graph_step else 'fused pairs, autograd')})",
@@ -123,6 +150,8 @@ def wd5m_eval(args, model_name):
         job.rank_batch(batch)
 
     ms = timed(step, args.steps, args.warmup)
+    if args.kernels:
+        kernel_table(step, 3, f"wd5m_eval_{model_name}_B{B}")
     hbm, tf = peaks()
     ops = 2.0 * (2 * B) * E * d
     return {"workload": f"filtered ranking {model_name} d=128 E={E} B={B} triples ({2 * B} queries) "
@@ -144,6 +173,7 @@ def main():
     ap.add_argument("--math", default="bf16")
     ap.add_argument("--reference-flow", action="store_true")
     ap.add_argument("--graph-step", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="also write a per-kernel time table (CUPTI) to gpurun_out/")
     args = ap.parse_args()
     if args.workload == "wd5m-1vsall":
         res = wd5m_1vsall(args)

@@ -126,7 +126,11 @@ int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const f
                    float* rowstat /*[B,4]*/, void* workspace, int64_t workspace_bytes, void* stream);
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
-                   int64_t nnz /* = lab_off[B], known to the caller */, float label_smoothing, float offset, const float* lse /*[B] (KL)*/, float inv_batch,
+                   int64_t nnz /* size of lab_col (>= lab_off[B]; the tail may be padding) */,
+                   const int32_t* lab_perm /* [nnz] or NULL: stable argsort of lab_col[0..nnz) (entries grouped by
+                                              entity, positions ascending), as the batch collate can provide it; spares
+                                              the device sort of the label scatter into dTable (BF16 tiles) */,
+                   float label_smoothing, float offset, const float* lse /*[B] (KL)*/, float inv_batch,
                    const float* row_scale /*[B] per-row factor multiplied into G (upstream gradient), or NULL*/,
                    const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */, float* dQ, float* dTable,
                    float* rowstat_out /* [B,4] or NULL: also produce the forward statistics of kgeb_fused_fwd (BCE on the
@@ -162,6 +166,11 @@ int kgeb_rank_count(int kind, int math, const float* Q, int64_t nq, int d, const
 int64_t kgeb_scatter_workspace_bytes(int64_t n, int d);
 int kgeb_scatter_add_rows(const void* idx, int idx64, const float* rows, int64_t n, int d, float* dense,
                           int64_t vocab, void* workspace, int64_t workspace_bytes, void* stream);
+/* same, with the sort hoisted out: perm[n] (int32) = stable argsort of idx, e.g. computed once by the collate that
+ * built idx (the ids of a batch are known before the step).  The sums and their order are identical to
+ * kgeb_scatter_add_rows, so the results are bit-identical. */
+int kgeb_scatter_add_rows_perm(const void* idx, int idx64, const int32_t* perm, const float* rows, int64_t n, int d,
+                               float* dense, int64_t vocab, void* workspace, int64_t workspace_bytes, void* stream);
 /* sparse form (lookup_embedder.yaml sparse: True): returns distinct ids (ascending) + summed rows */
 int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int64_t n, int d,
                              int64_t* uniq_ids /*[n]*/, float* uniq_rows /*[n,d]*/, int64_t* num_uniq /*dev*/,

@@ -35,6 +35,7 @@ constexpr int NUM_THREADS = 128 + NUM_EPI_THREADS;  // warps 0-3: TMA / MMA / TM
 constexpr int NUM_GROUP_THREADS = NUM_EPI_THREADS / 2;  // two epilogue groups ping-pong on alternate streamed tiles
 constexpr int COLS_PER_WARP = STR_ROWS / (EPQ / 2);     // 32 S-columns per warp of a group
 constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int STAGE_BYTES = RES_ROWS * 128;      // flush staging box of one column part (dTable kernel)
 
 struct Params {
   int64_t n_res;      // rows of the resident operand (B or shard entities)
@@ -52,7 +53,8 @@ struct Params {
 
 template <bool RES_IS_Q, bool BF16, int LOSS, bool HAS_RS, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_str, const Params p) {
+tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_str,
+              const __grid_constant__ CUtensorMap tm_out, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -63,7 +65,10 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
   uint8_t* res_smem = smem;                                         // [KS] slabs of 16 KiB
   uint8_t* g_smem = res_smem + (size_t)KS * RES_SLAB;               // [2] G buffers
   uint8_t* str_smem = g_smem + 2 * G_BYTES;                         // [NSTR][KS] slabs of 8 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(str_smem + (size_t)NSTR * KS * STR_SLAB);
+  // !RES_IS_Q: one 16 KiB staging box (128 rows x 32 fp32, 128-byte swizzle) per epilogue column part for the
+  // TMA reduce-add flush of the accumulator into the dense table gradient
+  uint8_t* stage_smem = str_smem + (size_t)NSTR * KS * STR_SLAB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + (RES_IS_Q ? 0 : EPQ * STAGE_BYTES));
   uint64_t* str_full = bars;                    // [MAX_STR]  TMA -> MMA
   uint64_t* str_empty = bars + MAX_STR;         // [MAX_STR]  MMA2 done -> TMA
   uint64_t* res_full = bars + 2 * MAX_STR;      // TMA -> MMA
@@ -92,12 +97,12 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
     mbar_init(res_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], NUM_GROUP_THREADS);
-      mbar_init(&g_full[b], NUM_GROUP_THREADS);
+      mbar_init(&s_empty[b], NUM_GROUP_THREADS / 32);
+      mbar_init(&g_full[b], NUM_GROUP_THREADS / 32);
       mbar_init(&g_empty[b], 1);
     }
     mbar_init(o_full, 1);
-    mbar_init(o_empty, NUM_EPI_THREADS);
+    mbar_init(o_empty, NUM_EPI_THREADS / 32);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -224,12 +229,16 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
       const int64_t res_row = rb * RES_ROWS + trow;
       float my_lse = 0.f, my_rs = 0.f;
-      float st_sp = 0.f, st_x = 0.f;   // STATS: BCE forward statistics of this (row, column part), summed over the job
+      // STATS: BCE forward statistics of this (row, column part), summed over the job:
+      //   sum softplus(z) = ln2 * sum lg2(1 + e^-|z|) + sum max(z, 0)   (no cancellation between the sums)
+      float st_lg = 0.f, st_mx = 0.f, st_x = 0.f;
       int n_pad = 0;
       if (RES_IS_Q && res_row < p.B) {
         my_rs = p.inv_batch * (HAS_RS ? p.row_scale[res_row] : 1.f);
         if (LOSS == KGEB_LOSS_KL) my_lse = p.lse[res_row];
       }
+      constexpr float kLog2e = 1.4426950408889634f;
+      const float off2 = -p.offset * kLog2e;   // ex2(fma(x, -log2e, off2)) = exp(-(x + offset))
       for (int64_t u = u0; u < u1; ++u, ++gunit) {
         if ((int)(gunit & 1) != group) continue;
         const int bufi = group;
@@ -239,39 +248,48 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         float v[COLS_PER_WARP];
         tmem_ld32(lane_addr + S_COL + (uint32_t)(bufi * STR_ROWS + sub * COLS_PER_WARP), v);
         tc_fence_before();
-        mbar_arrive(&s_empty[bufi]);  // S values are in registers: MMA1 of the tile after next may overwrite them
+        mbar_arrive_warp(&s_empty[bufi]);  // S values are in registers: MMA1 of the tile after next may overwrite them
         // Rows / columns beyond the matrices were zero-filled by TMA, so whatever finite G they get multiplies
         // zeros in MMA2; only the parameter loads are clamped.
         const int64_t qbase = u * STR_ROWS + sub * COLS_PER_WARP;
         // STATS: entity columns beyond the table end were zero-filled, their score is exactly 0: count them here
         // and take their known contribution (softplus(off), off) out once per job instead of masking per element
         if (STATS) n_pad += COLS_PER_WARP - (int)max((int64_t)0, min((int64_t)COLS_PER_WARP, p.n_str - qbase));
+        // Per-column parameters (columns are query rows when RES is the entity tile): lane c of the warp loads
+        // those of column c once per tile, the element loop fetches them with one shuffle.  KL folds everything
+        // into one exponent offset:  rs * exp(x - lse) = ex2(x * log2e + kc),  kc = (log(rs) - lse) * log2e.
+        float col_k = 0.f, col_rs = my_rs;
+        if (!RES_IS_Q) {
+          const int64_t q = min(qbase + lane, p.B - 1);
+          col_rs = HAS_RS ? p.inv_batch * __ldg(p.row_scale + q) : p.inv_batch;
+          if (LOSS == KGEB_LOSS_KL) col_k = (__logf(col_rs) - __ldg(p.lse + q)) * kLog2e;
+        } else if (LOSS == KGEB_LOSS_KL) {
+          col_k = (__logf(my_rs) - my_lse) * kLog2e;   // rows beyond B: log(0) = -inf -> G = 0
+        }
 #pragma unroll
         for (int c = 0; c < COLS_PER_WARP; ++c) {
-          float lse = my_lse, rs = my_rs;
-          if (!RES_IS_Q) {  // columns are query rows: per-column parameters (warp-uniform, L1-resident loads)
-            const int64_t q = min(qbase + c, p.B - 1);
-            rs = HAS_RS ? p.inv_batch * __ldg(p.row_scale + q) : p.inv_batch;
-            if (LOSS == KGEB_LOSS_KL) lse = __ldg(p.lse + q);
-          }
           const float x = v[c];
-          float gval;
           if (LOSS == KGEB_LOSS_KL) {
-            gval = __expf(x - lse);
-          } else if (STATS) {
-            // sigmoid and softplus from one exponential (3 MUFU: ex2, rcp, lg2), cancellation-free:
-            //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
-            const float z = x + p.offset;
-            const float e = __expf(-fabsf(z));
-            const float a = 1.f + e;
-            const float r = __fdividef(1.f, a);
-            gval = (z >= 0.f ? r : e * r) - p.ls_add;
-            st_sp += fmaf(0.69314718f, __log2f(a), fmaxf(z, 0.f));
-            st_x += z;
+            const float kc = RES_IS_Q ? col_k : __shfl_sync(0xffffffffu, col_k, c);
+            v[c] = ex2_ftz(fmaf(x, kLog2e, kc));
           } else {
-            gval = sigmoidf(x + p.offset) - p.ls_add;
+            const float rs = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c) : col_rs;
+            if (STATS) {
+              // sigmoid and softplus from one exponential (3 MUFU: ex2, rcp, lg2), cancellation-free:
+              //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
+              const float z = x + p.offset;
+              const float e = ex2_ftz(fabsf(z) * -kLog2e);
+              const float a = 1.f + e;
+              const float r = rcp_ftz(a);
+              st_lg += lg2_ftz(a);
+              st_mx += fmaxf(z, 0.f);
+              st_x += z;
+              v[c] = fmaf(z >= 0.f ? r : e * r, rs, -p.ls_add * rs);
+            } else {
+              // rs * (sigmoid(x + offset) - ls_add): FFMA, EX2 (inf for very negative z -> rcp gives 0), FADD, RCP, FFMA
+              v[c] = fmaf(rcp_ftz(1.f + ex2_ftz(fmaf(x, -kLog2e, off2))), rs, -p.ls_add * rs);
+            }
           }
-          v[c] = rs * gval;
         }
         mbar_wait(&g_empty[bufi], gph ^ 1);  // MMA2 of this buffer's previous tile has finished reading it
         uint8_t* gb = g_smem + (size_t)bufi * G_BYTES;
@@ -296,41 +314,67 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
                 make_float4(v[ck * 4], v[ck * 4 + 1], v[ck * 4 + 2], v[ck * 4 + 3]);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(&g_full[bufi]);
+        mbar_arrive_warp(&g_full[bufi]);
         gph ^= 1;
       }
       if (STATS && res_row < p.B) {
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
         const float zp = p.offset;
+        const float st_sp = fmaf(0.69314718f, st_lg, st_mx);
         sp[0] = st_sp - (float)n_pad * fmaf(0.69314718f, __log2f(1.f + __expf(-fabsf(zp))), fmaxf(zp, 0.f));
         sp[1] = st_x - (float)n_pad * zp;
       }
-      // flush the job's accumulator: 16-column groups are dealt round-robin to the column parts
+      // flush the job's accumulator
       mbar_wait(o_full, ophase);
       ophase ^= 1;
       tc_fence_after();
-      for (int c0 = part * 16; c0 < p.d; c0 += 16 * EPQ) {
-        float o[16];
-        tmem_ld16(lane_addr + O_COL + (uint32_t)c0, o);
-        if (res_row < p.n_res) {
-          float* dst = RES_IS_Q ? p.out + ((size_t)ch * p.B + res_row) * p.d + c0 : p.out + (size_t)res_row * p.d + c0;
+      if (RES_IS_Q) {
+        // partial dQ of this chunk: plain stores, 16-column groups dealt round-robin to the column parts
+        for (int c0 = part * 16; c0 < p.d; c0 += 16 * EPQ) {
+          float o[16];
+          tmem_ld16(lane_addr + O_COL + (uint32_t)c0, o);
+          if (res_row < p.n_res) {
+            float* dst = p.out + ((size_t)ch * p.B + res_row) * p.d + c0;
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) {
-            float4* d4 = reinterpret_cast<float4*>(dst + c);
-            if (RES_IS_Q) {
-              *d4 = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-            } else {
-              float4 old = *d4;
-              *d4 = make_float4(old.x + o[c], old.y + o[c + 1], old.z + o[c + 2], old.w + o[c + 3]);
-            }
+            for (int c = 0; c < 16; c += 4)
+              *reinterpret_cast<float4*>(dst + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+          }
+        }
+      } else {
+        // dense table gradient += accumulator.  A thread-per-row read-modify-write of global memory is uncoalesced
+        // and keeps the whole pipeline waiting on HBM round trips once per job; instead each column part stages
+        // 32-column boxes in swizzled shared memory and one thread hands them to the TMA as reduce-adds (the add
+        // happens in L2, asynchronously; this CTA is the only writer of these rows, so the result is deterministic).
+        uint8_t* stage = stage_smem + (size_t)part * STAGE_BYTES;
+        const bool leader = (quad == 0 && lane == 0);
+        const int nbox = (p.d + 31) / 32;
+        for (int box = part; box < nbox; box += EPQ) {
+          if (leader) bulk_wait_read0();             // the previous store from this staging box has read it
+          named_bar_sync(1 + part, 128);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float o[16];
+            tmem_ld16(lane_addr + O_COL + (uint32_t)(box * 32 + h * 16), o);
+            uint8_t* rowp = stage + (size_t)trow * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(rowp + (((h * 4 + j) ^ (trow & 7)) << 4)) =
+                  make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + part, 128);
+          if (leader) {
+            tma_reduce_add_2d(&tm_out, stage, box * 32, (int32_t)(rb * RES_ROWS));  // rows / columns past the end are clipped
+            bulk_commit();
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(o_empty);
+      mbar_arrive_warp(o_empty);
     }
   }
 
+  if (!RES_IS_Q && warp >= 4 && ((warp - 4) & 3) == 0 && lane == 0) bulk_wait0();  // outstanding reduce-adds
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -343,19 +387,30 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
 // exact fp32 sparse label part (entry-parallel: hot rows / hot entities cost no more than cold ones)
 // ---------------------------------------------------------------------------------------------
 __global__ void reduce_dq_partials_kernel(const float* __restrict__ partial, int64_t chunks, int64_t numel,
-                                          float* __restrict__ dQ) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  for (; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int64_t k = 0; k < chunks; ++k) s += partial[k * numel + i];  // fixed order
-    dQ[i] = s;
+                                          const float* __restrict__ label_part, float* __restrict__ dQ) {
+  int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  for (; i < numel; i += (int64_t)gridDim.x * blockDim.x * 4) {   // numel = B*d with d % 16 == 0
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t k = 0; k < chunks; ++k) {  // fixed order
+      const float4 v = *reinterpret_cast<const float4*>(partial + k * numel + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    if (label_part) {   // exact fp32 label rows, summed per query row on the side stream
+      const float4 v = *reinterpret_cast<const float4*>(label_part + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dQ + i) = s;
   }
 }
 
-// one warp per label entry i (entries [lab_off[B], nnz) are padding of a fixed-size label buffer):
-//   rows_dq[i,:] = -w_q * table[e,:]   (scattered into dQ[q,:] ; keys erow[] are ascending)
+// Label entries i (entries [lab_off[B], nnz) are padding of a fixed-size label buffer); one warp handles
+// LABEL_EPW consecutive entries:
+//   rows_dq[i,:] = -w_q * table[e,:]   (summed per query row q ; keys erow[] are ascending)
 //   rows_dt[i,:] = -w_q * Q[q,:]       (scattered into dTable[e,:] ; keys ent[])
 // with w_q = tscale[q] * inv_batch * row_scale[q]; entries outside this shard get zero rows.
+// The row of the warp's first entry comes from a 32-ary search over lab_off (3 dependent loads for B = 4096 instead
+// of the 12 of a binary search -- this kernel is pure latency), the following entries walk forward from it.
+constexpr int LABEL_EPW = 4;
 __global__ void __launch_bounds__(256)
 label_entry_rows_kernel(const float* __restrict__ Q, const float* __restrict__ table, int64_t B, int d, int64_t e_lo,
                         int64_t n_ent, const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col,
@@ -363,40 +418,52 @@ label_entry_rows_kernel(const float* __restrict__ Q, const float* __restrict__ t
                         float* __restrict__ rows_dq, float* __restrict__ rows_dt, int64_t* __restrict__ ent,
                         int64_t* __restrict__ erow, float* __restrict__ entry_dot, float add_per_entry) {
   const int lane = threadIdx.x & 31;
-  const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= nnz) return;
-  int64_t q = -1;
-  if (lane == 0 && i < lab_off[B]) {  // row of entry i: last q with lab_off[q] <= i
-    int64_t lo = 0, hi = B;
-    while (lo < hi) {
-      int64_t mid = (lo + hi + 1) >> 1;
-      if (lab_off[mid] <= i) lo = mid; else hi = mid - 1;
+  const int64_t i0 = (blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5)) * LABEL_EPW;
+  if (i0 >= nnz) return;
+  const int64_t n_real = lab_off[B];
+  // last q in [0, B] with lab_off[q] <= i0 (lab_off[0] = 0 <= i0 always)
+  int64_t lo = 0, hi = B;
+  while (lo < hi) {
+    const int64_t step = (hi - lo + 32) / 32;          // ceil((hi - lo + 1) / 32)
+    const int64_t probe = lo + (int64_t)lane * step;
+    const bool ok = probe <= hi && lab_off[probe] <= i0;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);  // lane 0 always votes yes
+    const int top = 31 - __clz((int)m);
+    const int64_t nlo = lo + (int64_t)top * step;
+    hi = min(hi, nlo + step - 1);
+    lo = nlo;
+  }
+  int64_t q = lo;
+#pragma unroll 1
+  for (int k = 0; k < LABEL_EPW; ++k) {
+    const int64_t i = i0 + k;
+    if (i >= nnz) break;
+    const bool real = i < n_real;
+    if (real) while (q < B - 1 && lab_off[q + 1] <= i) ++q;   // skips empty rows
+    int64_t e = 0;
+    float w = 0.f;
+    bool in_shard = false;
+    if (real) {
+      e = lab_col[i] - e_lo;
+      in_shard = (e >= 0 && e < n_ent);
+      if (in_shard) w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
+      else e = e < 0 ? 0 : n_ent - 1;   // zero row; the monotone clamp keeps ent[] in the order of lab_col (lab_perm)
     }
-    q = lo;
-  }
-  q = __shfl_sync(0xffffffffu, q, 0);
-  int64_t e = 0;
-  float w = 0.f;
-  bool in_shard = false;
-  if (q >= 0) {
-    e = lab_col[i] - e_lo;
-    in_shard = (e >= 0 && e < n_ent);
-    if (in_shard) w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
-    else e = 0;
-  }
-  const int64_t qq = q < 0 ? 0 : q;
-  float dot = 0.f;
-  for (int c = lane; c < d; c += 32) {
-    const float tv = __ldg(table + e * d + c), qv = Q[qq * d + c];
-    dot = fmaf(qv, tv, dot);
-    if (rows_dq) rows_dq[i * d + c] = -w * tv;
-    if (rows_dt) rows_dt[i * d + c] = -w * qv;
-  }
-  if (entry_dot) dot = warp_sum(dot);   // warp-uniform branch
-  if (lane == 0) {
-    ent[i] = e;
-    erow[i] = qq;
-    if (entry_dot) entry_dot[i] = in_shard ? dot + add_per_entry : 0.f;   // x_ij (+offset) at the label, in-shard only
+    const int64_t qq = real ? q : 0;
+    float dot = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {   // d % 4 == 0
+      const float4 tv = __ldg(reinterpret_cast<const float4*>(table + e * d + c));
+      const float4 qv = *reinterpret_cast<const float4*>(Q + qq * d + c);
+      dot = fmaf(qv.x, tv.x, fmaf(qv.y, tv.y, fmaf(qv.z, tv.z, fmaf(qv.w, tv.w, dot))));
+      if (rows_dq) *reinterpret_cast<float4*>(rows_dq + i * d + c) = make_float4(-w * tv.x, -w * tv.y, -w * tv.z, -w * tv.w);
+      if (rows_dt) *reinterpret_cast<float4*>(rows_dt + i * d + c) = make_float4(-w * qv.x, -w * qv.y, -w * qv.z, -w * qv.w);
+    }
+    if (entry_dot) dot = warp_sum(dot);   // warp-uniform branch
+    if (lane == 0) {
+      ent[i] = e;
+      erow[i] = qq;
+      if (entry_dot) entry_dot[i] = in_shard ? dot + add_per_entry : 0.f;   // x_ij (+offset) at the label, in-shard only
+    }
   }
 }
 
@@ -431,7 +498,7 @@ static Plan make_plan(bool res_is_q, bool bf16, int64_t B, int d, int64_t n_ent)
   }
   const size_t fixed = 1024 + 512;
   const size_t g_bytes = (size_t)(STR_ROWS / slab_k) * RES_SLAB;
-  const size_t base = (size_t)p.ks * RES_SLAB + 2 * g_bytes;
+  const size_t base = (size_t)p.ks * RES_SLAB + 2 * g_bytes + (res_is_q ? 0 : (size_t)EPQ * STAGE_BYTES);
   int nstr = (int)((SMEM_BUDGET - fixed - base) / ((size_t)p.ks * STR_SLAB));
   if (nstr > MAX_STR) nstr = MAX_STR;
   p.nstr = nstr;
@@ -440,15 +507,27 @@ static Plan make_plan(bool res_is_q, bool bf16, int64_t B, int d, int64_t n_ent)
 }
 
 template <bool RES_IS_Q>
-static int launch_bwd(const Plan& pl, const CUtensorMap& m_res, const CUtensorMap& m_str, int64_t jobs, cudaStream_t st) {
+static int launch_bwd(const Plan& pl, const CUtensorMap& m_res, const CUtensorMap& m_str, const CUtensorMap& m_out,
+                      int64_t jobs, cudaStream_t st) {
   const int grid = (int)(jobs < kNumSMs ? jobs : kNumSMs);
   cudaError_t e = cudaSuccess;
+  // (A raised launch priority for this kernel was tried and measured worse: it starts a few microseconds earlier but
+  // then starves the label kernels of the other stream, which the second tile kernel waits for.)
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
 #define KGEB_BWD_LAUNCH(LOSS_, RS_, ST_)                                                                              \
   {                                                                                                                   \
     e = cudaFuncSetAttribute(tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_, ST_>,                                          \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);                              \
     if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");                                             \
-    tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_, ST_><<<grid, NUM_THREADS, pl.smem, st>>>(m_res, m_str, pl.p);            \
+    e = cudaLaunchKernelEx(&cfg, tc_bwd_kernel<RES_IS_Q, true, LOSS_, RS_, ST_>, m_res, m_str, m_out, pl.p);           \
+    if (e != cudaSuccess) return cuda_status(e, "tc_bwd launch");                                                     \
   }
   const bool rs = pl.p.row_scale != nullptr;
   const bool stats = RES_IS_Q && pl.p.stat_partial != nullptr && pl.p.loss == KGEB_LOSS_BCE;
@@ -530,16 +609,39 @@ static int64_t a256(int64_t x) { return (x + 255) / 256 * 256; }
 
 int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz) {
   if (nnz < 1) nnz = 1;
-  return a256((int64_t)kNumSMs * B * d * 4) + 2 * a256(nnz * (int64_t)d * 4) + 2 * a256(nnz * 8) +
+  return a256((int64_t)kNumSMs * B * d * 4) + a256(B * (int64_t)d * 4) + 2 * a256(nnz * (int64_t)d * 4) + 2 * a256(nnz * 8) +
          a256((int64_t)kNumSMs * 4 * B * 2 * 4) + a256(nnz * 4) + a256(B * 4) + kgeb_scatter_workspace_bytes(nnz, d) + 4096;
+}
+
+// A library-owned side stream per device: the sparse label part of a call is independent of its tile kernel, so it
+// is forked onto the side stream and joined where its result is consumed (plain event fork / join: works in eager
+// mode and inside a CUDA-graph capture, where the side stream joins the capture).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+// which: 0 for calls that produce dQ, 1 for dTable-only calls -- the two halves of a step are issued as two calls on
+// two streams (trainer.py) and must not queue behind each other's label chains
+static SideStream* side_stream(int which) {
+  static thread_local SideStream per_dev[64][2];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_dev[dev][which];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess)
+      return nullptr;
+  }
+  return &s;
 }
 
 // Qb / tableb: bf16 mirrors of Q [B,d] and of the table shard [n_ent,d]
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
-                 const float* tscale, float ls_add, float offset, const float* lse, float inv_batch,
-                 const float* row_scale, float* dQ, float* dTable, float* rowstat_out, void* ws, int64_t ws_bytes,
-                 cudaStream_t st) {
+                 const int32_t* lab_perm, const float* tscale, float ls_add, float offset, const float* lse,
+                 float inv_batch, const float* row_scale, float* dQ, float* dTable, float* rowstat_out, void* ws,
+                 int64_t ws_bytes, cudaStream_t st) {
   using namespace tcb;
   KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_bwd(bf16): entity dim must be a multiple of 16 and <= 256 (got %d)", d);
   KGEB_REQUIRE(Qb && tableb, "fused_bwd(bf16): the bf16 mirrors of Q and of the table are required");
@@ -549,6 +651,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
   const int64_t nz = nnz < 1 ? 1 : nnz;
   char* wp = reinterpret_cast<char*>(ws);
   float* partial = reinterpret_cast<float*>(wp);      wp += a256((int64_t)kNumSMs * B * d * 4);
+  float* dq_lab = reinterpret_cast<float*>(wp);       wp += a256(B * (int64_t)d * 4);
   float* rows_dq = reinterpret_cast<float*>(wp);      wp += a256(nz * (int64_t)d * 4);
   float* rows_dt = reinterpret_cast<float*>(wp);      wp += a256(nz * (int64_t)d * 4);
   int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
@@ -562,12 +665,38 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
   int rc;
   CUtensorMap m_res, m_str;
   if (n_ent > 0 && B > 0) {
+    // ---- sparse label part, forked onto the side stream --------------------------------------------------
+    SideStream* ss = nullptr;
     if (nnz > 0) {
-      label_entry_rows_kernel<<<(unsigned)((nnz + 7) / 8), 256, 0, st>>>(
+      ss = side_stream(dQ ? 0 : 1);
+      KGEB_REQUIRE(ss, "fused_bwd(bf16): cannot create the side stream");
+      cudaError_t e = cudaEventRecord(ss->fork, st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ss->stream, ss->fork, 0);
+      if (e != cudaSuccess) return cuda_status(e, "fused_bwd fork");
+      cudaStream_t sd = ss->stream;
+      label_entry_rows_kernel<<<(unsigned)((nnz + 8 * LABEL_EPW - 1) / (8 * LABEL_EPW)), 256, 0, sd>>>(
           Q, table, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale, inv_batch, nnz, dQ ? rows_dq : nullptr,
           dTable ? rows_dt : nullptr, lab_ent, lab_row, want_stats ? entry_dot : nullptr, offset);
       KGEB_LAUNCH_CHECK("label_entry_rows");
+      if (dTable) {
+        // label rows into the dense gradient before the tile kernel adds on top (it owns its rows; the order is fixed)
+        rc = lab_perm ? kgeb_scatter_add_rows_perm(lab_ent, 1, lab_perm, rows_dt, nnz, d, dTable, n_ent, scatter_ws,
+                                                   scatter_bytes, sd)
+                      : kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, sd);
+        if (rc) return rc;
+      }
+      if (dQ) {
+        // label rows summed per query row (entries are grouped by row already) into a zeroed buffer that the partial
+        // reduce adds in: the whole label part runs underneath the tile kernel
+        e = cudaMemsetAsync(dq_lab, 0, (size_t)B * d * 4, sd);
+        if (e != cudaSuccess) return cuda_status(e, "fused_bwd memset");
+        if ((rc = scatter_add_rows_presorted(lab_row, rows_dq, nnz, d, dq_lab, B, scatter_ws, scatter_bytes, sd))) return rc;
+      }
+      if (want_stats) label_row_sum2_kernel<<<(unsigned)((B + 7) / 8), 256, 0, sd>>>(entry_dot, lab_off, B, label_dot);
+      e = cudaEventRecord(ss->join, sd);
+      if (e != cudaSuccess) return cuda_status(e, "fused_bwd join");
     }
+    bool joined = (ss == nullptr);
     if (dQ) {
       Plan pl = make_plan(true, true, B, d, n_ent);
       if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
@@ -576,33 +705,39 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       pl.p.stat_partial = want_stats ? stat_partial : nullptr;
       if ((rc = make_map(&m_res, Qb, B, d, RES_ROWS, true)) || (rc = make_map(&m_str, tableb, n_ent, d, STR_ROWS, true))) return rc;
       const int64_t jobs = pl.p.n_res_blocks * pl.p.chunks;
-      if ((rc = launch_bwd<true>(pl, m_res, m_str, jobs, st))) return rc;
+      if ((rc = launch_bwd<true>(pl, m_res, m_str, m_res, jobs, st))) return rc;
+      if (!joined) {
+        cudaError_t e = cudaStreamWaitEvent(st, ss->join, 0);
+        if (e != cudaSuccess) return cuda_status(e, "fused_bwd join wait");
+        joined = true;
+      }
       const int64_t numel = B * (int64_t)d;
-      reduce_dq_partials_kernel<<<(unsigned)((numel + 255) / 256 > 4096 ? 4096 : (numel + 255) / 256), 256, 0, st>>>(
-          partial, pl.p.chunks, numel, dQ);
+      const int64_t rblocks = (numel / 4 + 255) / 256;
+      reduce_dq_partials_kernel<<<(unsigned)(rblocks > 4096 ? 4096 : rblocks), 256, 0, st>>>(
+          partial, pl.p.chunks, numel, nnz > 0 ? dq_lab : nullptr, dQ);
       KGEB_LAUNCH_CHECK("reduce_dq_partials");
-      if (nnz > 0 && (rc = scatter_add_rows_presorted(lab_row, rows_dq, nnz, d, dQ, B, scatter_ws, scatter_bytes, st)))
-        return rc;
       if (want_stats) {   // BCE forward statistics came out of the same pass
-        if (nnz > 0) label_row_sum2_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(entry_dot, lab_off, B, label_dot);
-        else cudaMemsetAsync(label_dot, 0, (size_t)B * 4, st);
+        if (nnz == 0) cudaMemsetAsync(label_dot, 0, (size_t)B * 4, st);
         reduce_stat_partials_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(stat_partial, pl.p.chunks, B, label_dot,
                                                                                 rowstat_out);
         KGEB_LAUNCH_CHECK("reduce_stat_partials");
       }
     }
+    if (!joined) {
+      cudaError_t e = cudaStreamWaitEvent(st, ss->join, 0);
+      if (e != cudaSuccess) return cuda_status(e, "fused_bwd join wait");
+    }
     if (dTable) {
-      // label rows first: the tile kernel below adds on top (it owns its rows; both orders are deterministic), and in
-      // the two-stream step this small sorted scatter then runs underneath the other stream's dQ tile kernel
-      if (nnz > 0 && (rc = kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st)))
-        return rc;
       Plan pl = make_plan(false, true, B, d, n_ent);
       if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
       pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = dTable;
-      if ((rc = make_map(&m_res, tableb, n_ent, d, RES_ROWS, true)) || (rc = make_map(&m_str, Qb, B, d, STR_ROWS, true))) return rc;
+      CUtensorMap m_out;   // fp32 [n_ent, d], boxes of 32 columns x 128 rows for the reduce-add flush
+      if ((rc = make_map(&m_res, tableb, n_ent, d, RES_ROWS, true)) || (rc = make_map(&m_str, Qb, B, d, STR_ROWS, true)) ||
+          (rc = make_map(&m_out, dTable, n_ent, d, RES_ROWS, false)))
+        return rc;
       const int64_t jobs = pl.p.n_res_blocks;
-      if ((rc = launch_bwd<false>(pl, m_res, m_str, jobs, st))) return rc;
+      if ((rc = launch_bwd<false>(pl, m_res, m_str, m_out, jobs, st))) return rc;
     }
   } else if (dQ && B > 0) {
     cudaMemsetAsync(dQ, 0, (size_t)B * d * 4, st);

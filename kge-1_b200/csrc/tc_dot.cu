@@ -13,6 +13,7 @@
 //   MODE_SCORES  A = table tile, B = query block : lane = entity  -> coalesced stores of X[q, e]
 //   MODE_STATS   A = query block, B = table tile : lane = query   -> online max/sum-exp | softplus sums
 //   MODE_RANK    A = query block, B = table tile : lane = query   -> rank / tie counts with CSR filters
+#include <climits>
 #include "tc_common.cuh"
 
 namespace kgeb {
@@ -89,7 +90,7 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(q_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], NUM_EPI_THREADS);
+      mbar_init(&t_empty[b], NUM_EPI_THREADS / 32);
     }
     fence_barrier_init();
   }
@@ -187,12 +188,20 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float s0[NQB], s1[NQB], s2[NQB];
       int cnt[NQB][6];
       float tsc[NQB];
-      int64_t tent[NQB], fcur[NQB], fend[NQB], ucur[NQB], uend[NQB];
+      // MODE_RANK: entity columns are tracked relative to the first entity of the chunk (32-bit); the next unconsumed
+      // filter column of each row sits in a register so that the per-tile "any filter entry here?" test costs no load
+      int trel[NQB], fcur[NQB], fend[NQB], fnxt[NQB], ucur[NQB], uend[NQB], unxt[NQB];
+      const int64_t chunk_ent0 = p.e_lo + t0 * TILE;
+      auto rel_of = [&](const int64_t* col, int cur, int end) -> int {
+        if (cur >= end) return INT_MAX;
+        const int64_t r = col[cur] - chunk_ent0;
+        return r >= (int64_t)INT_MAX ? INT_MAX : (int)r;
+      };
 #pragma unroll
       for (int qb = 0; qb < NQB; ++qb) {
         s0[qb] = (MODE == MODE_STATS && p.loss == KGEB_LOSS_KL) ? -INFINITY : 0.f;
         s1[qb] = s2[qb] = 0.f;
-        tsc[qb] = 0.f; tent[qb] = -1; fcur[qb] = fend[qb] = ucur[qb] = uend[qb] = 0;
+        tsc[qb] = 0.f; trel[qb] = -1; fcur[qb] = fend[qb] = ucur[qb] = uend[qb] = 0; fnxt[qb] = unxt[qb] = INT_MAX;
 #pragma unroll
         for (int k = 0; k < 6; ++k) cnt[qb][k] = 0;
         if (MODE == MODE_RANK) {
@@ -200,10 +209,18 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (qb < nqb && r < p.B) {
             float t = p.true_score[r];
             tsc[qb] = (t != t) ? -INFINITY : t;
-            tent[qb] = load_index(p.true_ent, p.idx64, r);
-            const int64_t first = p.e_lo + t0 * TILE;
-            if (p.f_off) { fend[qb] = p.f_off[r + 1]; fcur[qb] = lb_i64(p.f_col, p.f_off[r], fend[qb], first); }
-            if (p.t_off) { uend[qb] = p.t_off[r + 1]; ucur[qb] = lb_i64(p.t_col, p.t_off[r], uend[qb], first); }
+            const int64_t te = load_index(p.true_ent, p.idx64, r) - chunk_ent0;
+            trel[qb] = (te < 0 || te >= (int64_t)INT_MAX) ? -1 : (int)te;
+            if (p.f_off) {
+              fend[qb] = (int)p.f_off[r + 1];
+              fcur[qb] = (int)lb_i64(p.f_col, p.f_off[r], p.f_off[r + 1], chunk_ent0);
+              fnxt[qb] = rel_of(p.f_col, fcur[qb], fend[qb]);
+            }
+            if (p.t_off) {
+              uend[qb] = (int)p.t_off[r + 1];
+              ucur[qb] = (int)lb_i64(p.t_col, p.t_off[r], p.t_off[r + 1], chunk_ent0);
+              unxt[qb] = rel_of(p.t_col, ucur[qb], uend[qb]);
+            }
           }
         }
       }
@@ -235,72 +252,105 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
           } else if (MODE == MODE_STATS) {
             if (nv > 0) {
+              constexpr float kLog2e = 1.4426950408889634f;
               float v[32];
               tmem_ld32(acc + cw0, v);
+              // sum of the raw scores first: columns beyond the table were zero-filled by TMA (score exactly 0), so no
+              // masking is needed; afterwards the last tile (warp-uniform test) turns them into -inf, the neutral
+              // element of everything below
+              float a2 = 0.f;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) a2 += v[c];
+              if (nv < 32) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c >= nv) v[c] = -INFINITY;
+              }
               if (p.loss == KGEB_LOSS_KL) {
+                // online max / sum-exp, 5 instructions per element: FADD | FMNMX | FFMA, EX2, FADD
                 float mx = s0[qb];
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                  if (c < nv) mx = fmaxf(mx, v[c]);
-                float l = (s0[qb] == -INFINITY) ? 0.f : s1[qb] * __expf(s0[qb] - mx);
-                float a2 = 0.f;
+                for (int c = 0; c < 32; ++c) mx = fmaxf(mx, v[c]);
+                const float mxl = mx * kLog2e;
+                float l = (s0[qb] == -INFINITY) ? 0.f : s1[qb] * ex2_ftz(fmaf(s0[qb], kLog2e, -mxl));
 #pragma unroll
-                for (int c = 0; c < 32; ++c)
-                  if (c < nv) {
-                    l += __expf(v[c] - mx);
-                    a2 += v[c];
-                  }
+                for (int c = 0; c < 32; ++c) l += ex2_ftz(fmaf(v[c], kLog2e, -mxl));   // ex2(-inf) = 0
                 s0[qb] = mx;
                 s1[qb] = l;
                 s2[qb] += a2;
               } else {
-                float a0 = 0.f, a2 = 0.f;
+                // softplus(z) = max(z,0) + ln2 * lg2(1 + 2^(-|z| log2e)); padded columns (z = -inf) contribute 0
+                float a_lg = 0.f, a_mx = 0.f;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                  const float x = v[c] + p.offset;
-                  const float sp = softplusf(x);
-                  a0 += (c < nv) ? sp : 0.f;
-                  a2 += (c < nv) ? x : 0.f;
+                  const float z = v[c] + p.offset;
+                  a_lg += lg2_ftz(1.f + ex2_ftz(fabsf(z) * -kLog2e));
+                  a_mx += fmaxf(z, 0.f);
                 }
-                s0[qb] += a0;
-                s2[qb] += a2;
+                s0[qb] += fmaf(0.69314718f, a_lg, a_mx);
+                s2[qb] += fmaf((float)nv, p.offset, a2);
               }
             }
           } else {  // MODE_RANK
             const float ts = tsc[qb];
-            const int64_t ent0 = p.e_lo + t * TILE;
+            const int rel0 = (int)((t - t0) * TILE);        // first column of this tile, relative to the chunk
             if (nv > 0) {
               float v[32];
               tmem_ld32(acc + cw0, v);
+              // fast pass (3 instructions per element): rank count and an "anything unusual" flag
+              // x > ts  <=>  sign bit of (ts - x), added with one LEA.HI; `plain` stays true while every x is
+              // ordered and different from ts (a NaN or an infinite ts - x = inf - inf also sends the row to the
+              // exact pass)
+              unsigned g0 = 0, g1 = 0;
+              bool plain = true;
 #pragma unroll
-              for (int c = 0; c < 32; ++c)
-                if (c < nv) {
-                  float x = v[c];
-                  if (ent0 + cw0 + c == tent[qb]) x = ts;  // entity_ranking.py:170-177
-                  if (x != x) x = -INFINITY;
-                  cnt[qb][0] += (x > ts);
-                  cnt[qb][1] += (x == ts);
-                }
+              for (int c = 0; c < 32; c += 2) {
+                g0 += __float_as_uint(ts - v[c]) >> 31;
+                g1 += __float_as_uint(ts - v[c + 1]) >> 31;
+                plain = plain & ((v[c] < ts) | (v[c] > ts)) & ((v[c + 1] < ts) | (v[c + 1] > ts));
+              }
+              int gt = (int)(g0 + g1);
+              const bool eq = !plain;
+              // exact pass for the rare rows that need it: a tie, a -inf true score (NaN / filtered candidates tie
+              // with it), the true entity's own column (overwritten with the true score, entity_ranking.py:170-177),
+              // or the ragged last tile
+              const bool own = (unsigned)(trel[qb] - (rel0 + cw0)) < 32u;
+              int ties = 0;
+              if (eq || own || nv < 32 || ts == -INFINITY) {
+                gt = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c < nv) {
+                    float x = v[c];
+                    if (rel0 + cw0 + c == trel[qb]) x = ts;
+                    if (x != x) x = -INFINITY;
+                    gt += (x > ts);
+                    ties += (x == ts);
+                  }
+              }
+              cnt[qb][0] += gt;
+              cnt[qb][1] += ties;
             }
             // corrections for filtered candidates (their score becomes -inf): warp-cooperative, one filter entry per
             // iteration; the value is re-read from the same TMEM accumulator so comparisons are bit-consistent with
             // the raw pass.  Every column part walks the row's entries of this tile and handles those in its columns.
+            const int rel_end = rel0 + ncols;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
               const int64_t* col = which ? p.t_col : p.f_col;
-              int64_t& cur = which ? ucur[qb] : fcur[qb];
-              const int64_t end = which ? uend[qb] : fend[qb];
-              int64_t prev = -1;
+              int& cur = which ? ucur[qb] : fcur[qb];
+              int& nxt = which ? unxt[qb] : fnxt[qb];
+              const int end = which ? uend[qb] : fend[qb];
+              if (!__any_sync(0xffffffffu, nxt < rel_end)) continue;
+              int prev = -1;
               while (true) {
                 int loc = -1;
-                int64_t c = -1;
-                while (cur < end) {
-                  c = col[cur];
-                  if (c >= ent0 + ncols) break;
-                  const int l = (int)(c - ent0);
-                  if ((l / COLS_PER_WARP) == part && c != prev && c != tent[qb]) { loc = l; break; }
-                  prev = c;
+                while (nxt < rel_end) {
+                  const int l = nxt - rel0;
+                  if ((l / COLS_PER_WARP) == part && nxt != prev && nxt != trel[qb]) { loc = l; break; }
+                  prev = nxt;
                   ++cur;
+                  nxt = rel_of(col, cur, end);
                 }
                 const unsigned mask = __ballot_sync(0xffffffffu, loc >= 0);
                 if (mask == 0) break;
@@ -308,8 +358,9 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const int sloc = __shfl_sync(0xffffffffu, loc, src);
                 float x = tmem_ld1(acc + (uint32_t)sloc);
                 if (lane == src) {
+                  prev = nxt;
                   ++cur;
-                  prev = c;
+                  nxt = rel_of(col, cur, end);
                   if (x != x) x = -INFINITY;
                   cnt[qb][2 + 2 * which] -= (x > ts);
                   cnt[qb][3 + 2 * which] += (ts == -INFINITY) - (x == ts);
@@ -319,7 +370,7 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
         tc_fence_before();
-        mbar_arrive(&t_empty[buf]);
+        mbar_arrive_warp(&t_empty[buf]);
         buf ^= 1;
       }
 

@@ -23,9 +23,9 @@ int tc_fused_fwd(int loss, int math, const float* Q, const void* Qb, int64_t B, 
 int tc_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);  // tc_bwd.cu
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
-                 const float* tscale, float ls_add, float offset, const float* lse, float inv_batch,
-                 const float* row_scale, float* dQ, float* dTable, float* rowstat_out, void* ws, int64_t ws_bytes,
-                 cudaStream_t st);  // tc_bwd.cu
+                 const int32_t* lab_perm, const float* tscale, float ls_add, float offset, const float* lse,
+                 float inv_batch, const float* row_scale, float* dQ, float* dTable, float* rowstat_out, void* ws,
+                 int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
 int tc_rank_count(const float* Q, int64_t nq, int d, const float* table, int64_t e_lo, int64_t n_ent,
                   const float* true_score, const void* true_ent, int idx64, const int64_t* f_off,
                   const int64_t* f_col, const int64_t* t_off, const int64_t* t_col, int64_t* counts,
@@ -832,7 +832,7 @@ __global__ void label_weight_kernel(int loss, const int64_t* __restrict__ lab_of
 
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
-                   float label_smoothing, float offset, const float* lse, float inv_batch,
+                   const int32_t* lab_perm, float label_smoothing, float offset, const float* lse, float inv_batch,
                    const float* grad_scale, const void* table_bf16, float* dQ, float* dTable, float* rowstat_out,
                    void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
@@ -863,7 +863,7 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
         (rc = kgeb_fused_fwd(loss, math, Q, B, d, table, e_lo, e_hi, num_entities, lab_off, lab_col, nnz, label_smoothing,
                              offset, table_bf16, rowstat_out, workspace, workspace_bytes, stream)))
       return rc;
-    return tc_fused_bwd(loss, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, tail.tscale,
+    return tc_fused_bwd(loss, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, lab_perm, tail.tscale,
                         lp.ls_add, offset, lse, inv_batch, grad_scale, dQ, dTable, fused_stats ? rowstat_out : nullptr,
                         workspace, tail.usable, st);
   }

@@ -400,6 +400,17 @@ __global__ void pack_keys_kernel(const void* idx, int idx64, int n, int pb, W* _
   if (i < n) packed[i] = ((W)load_index(idx, idx64, i) << pb) | (W)i;
 }
 
+// packed words straight from a precomputed stable argsort of the ids (no device sort)
+template <typename W>
+__global__ void pack_perm_kernel(const void* idx, int idx64, const int32_t* __restrict__ perm, int n, int pb,
+                                 W* __restrict__ packed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int src = perm[i];
+    packed[i] = ((W)load_index(idx, idx64, src) << pb) | (W)src;
+  }
+}
+
 template <typename W>
 static int packed_phases(const W* packed, int64_t n, int pb, int d, const float* rows, float* dense, int64_t vocab,
                          float* part, cudaStream_t st) {
@@ -601,6 +612,26 @@ int kgeb_scatter_add_rows(const void* idx, int idx64, const float* rows, int64_t
   rc = sort_and_segment(idx, idx64, n, vocab, w, nullptr, st);
   if (rc) return rc;
   return segment_sums<true>(w, n, d, rows, dense, vocab, nullptr, nullptr, st);
+}
+
+int kgeb_scatter_add_rows_perm(const void* idx, int idx64, const int32_t* perm, const float* rows, int64_t n, int d,
+                               float* dense, int64_t vocab, void* workspace, int64_t workspace_bytes, void* stream) {
+  KGEB_REQUIRE(idx && perm && rows && dense && n >= 0 && d > 0 && vocab > 0, "scatter_add_rows_perm: bad arguments");
+  if (n == 0) return KGEB_OK;
+  const int pb = kgeb::bits_for(n), kb = kgeb::bits_for(vocab);
+  KGEB_REQUIRE(n <= (1 << 26) && pb + kb <= 62, "scatter_add_rows_perm: n / vocab out of range");
+  kgeb::ScatterWs w;
+  KGEB_REQUIRE(kgeb::carve(workspace, workspace_bytes, n, d, w), "scatter_add_rows_perm: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (pb + kb > 32) {
+    uint64_t* packed = reinterpret_cast<uint64_t*>(w.keys_in);
+    kgeb::pack_perm_kernel<uint64_t><<<blocks, 256, 0, st>>>(idx, idx64, perm, (int)n, pb, packed);
+    return kgeb::packed_phases<uint64_t>(packed, n, pb, d, rows, dense, vocab, w.part, st);
+  }
+  uint32_t* packed = reinterpret_cast<uint32_t*>(w.keys_in);
+  kgeb::pack_perm_kernel<uint32_t><<<blocks, 256, 0, st>>>(idx, idx64, perm, (int)n, pb, packed);
+  return kgeb::packed_phases<uint32_t>(packed, n, pb, d, rows, dense, vocab, w.part, st);
 }
 
 // internal: keys already ascending (e.g. label entries grouped by row)

@@ -105,15 +105,17 @@ def rows_loss(rowstat: torch.Tensor, lab_off: torch.Tensor, loss: int, label_smo
 
 
 def fused_backward(q, table, lab_off, lab_col, loss, label_smoothing, offset, lse, inv_batch, grad_scale, math,
-                   shard: Shard, d_table: Optional[torch.Tensor], want_dq: bool = True) -> Optional[torch.Tensor]:
-    """dQ (returned, all-reduced over shards) and d_table += G^T Q for the rows of this shard."""
+                   shard: Shard, d_table: Optional[torch.Tensor], want_dq: bool = True,
+                   lab_perm: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """dQ (returned, all-reduced over shards) and d_table += G^T Q for the rows of this shard.  lab_perm (int32,
+    optional): stable argsort of lab_col from the collate (spares the device sort of the label scatter)."""
     b, d = q.shape
     n_ent = shard.e_hi - shard.e_lo
     dq = torch.empty(b, d, dtype=torch.float32, device=q.device) if want_dq else None
     ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent, lab_col.numel()))
     lib.call("kgeb_fused_bwd", loss, math, lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo,
-             shard.e_hi, shard.num_entities, lib.i64(lab_off), lib.i64(lab_col), lab_col.numel(), float(label_smoothing),
-             float(offset), None if lse is None else lib.f32(lse, "lse"), float(inv_batch),
+             shard.e_hi, shard.num_entities, lib.i64(lab_off), lib.i64(lab_col), lab_col.numel(),
+             None if lab_perm is None else lab_perm.data_ptr(), float(label_smoothing), float(offset), None if lse is None else lib.f32(lse, "lse"), float(inv_batch),
              None if grad_scale is None else lib.f32(grad_scale, "grad scale"), _mirror_ptr(table, math, b, d),
              None if dq is None else dq.data_ptr(), None if d_table is None else lib.f32(d_table, "table gradient"),
              None, ws.data_ptr(), ws.numel(), lib.stream_ptr(q))

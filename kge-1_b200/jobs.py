@@ -144,14 +144,14 @@ class TrainingJobKvsAll(TrainingJob):
         return self.stepper
 
     def device_inputs(self, batch):
-        """Host (pinned) KvsAll batch -> device tensors (a_idx, p_idx, row_combine, lab_off, lab_col)."""
+        """Host (pinned) KvsAll batch -> device tensors (a_idx, p_idx, row_combine, lab_off, lab_col, perms)."""
         from .trainer import kvsall_rows
         q = batch["queries"].to(self.device, non_blocking=True)
         qt = batch["query_type_indexes"].to(self.device, non_blocking=True)
         coords = batch["label_coords"].to(self.device, non_blocking=True)
         a, p, rc = kvsall_rows(q, qt)
         lab_off, lab_col = fused.csr_from_coords(coords, len(q))
-        return a, p, rc, lab_off, lab_col
+        return a, p, rc, lab_off, lab_col, self.stepper.batch_perms(a, p, lab_col)
 
     def collate_packed(self, batch: dict) -> dict:
         """Host-side collate for the graph-captured step (what a DataLoader worker does instead of train.py:590-677's

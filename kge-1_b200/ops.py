@@ -68,8 +68,10 @@ def relation_dim(model: str, d: int) -> int:
 # ---------------------------------------------------------------------------------------------
 # scatter (autograd of the gathers)
 # ---------------------------------------------------------------------------------------------
-def scatter_add_rows_(dense: torch.Tensor, indexes: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
-    """dense[indexes[i], :] += rows[i, :] (sorted, deterministic)."""
+def scatter_add_rows_(dense: torch.Tensor, indexes: torch.Tensor, rows: torch.Tensor,
+                      perm: torch.Tensor = None) -> torch.Tensor:
+    """dense[indexes[i], :] += rows[i, :] (sorted, deterministic).  perm (int32, optional) = stable argsort of indexes,
+    e.g. from the batch collate: spares the device sort, same sums in the same order."""
     n = indexes.numel()
     if n == 0:
         return dense
@@ -78,6 +80,12 @@ def scatter_add_rows_(dense: torch.Tensor, indexes: torch.Tensor, rows: torch.Te
     nbytes = lib.load().kgeb_scatter_workspace_bytes(n, rows.shape[1])
     ws = _workspace(dense.device, nbytes)
     ip, i64 = lib.idx(indexes)
+    if perm is not None:
+        if perm.dtype != torch.int32 or perm.numel() != n or not perm.is_cuda:
+            raise ValueError("perm must be an int32 CUDA tensor with one entry per index")
+        lib.call("kgeb_scatter_add_rows_perm", ip, i64, perm.contiguous().data_ptr(), lib.f32(rows, "rows"), n,
+                 rows.shape[1], lib.f32(dense, "dense"), dense.shape[0], ws.data_ptr(), ws.numel(), lib.stream_ptr(dense))
+        return dense
     lib.call("kgeb_scatter_add_rows", ip, i64, lib.f32(rows, "rows"), n, rows.shape[1], lib.f32(dense, "dense"),
              dense.shape[0], ws.data_ptr(), ws.numel(), lib.stream_ptr(dense))
     return dense

@@ -40,14 +40,20 @@ class FusedAllEntityStepper:
         f32 = dict(dtype=torch.float32, device=dev)
         i64 = dict(dtype=torch.int64, device=dev)
         # static inputs: ONE contiguous byte buffer so that a packed host batch arrives with a single H2D copy
-        #   int64 [a_idx (rows) | p_idx (rows) | lab_off (rows+1) | lab_col (nnz_max)]  then  int32 [row_combine (rows)]
+        #   int64 [a_idx (rows) | p_idx (rows) | lab_off (rows+1) | lab_col (nnz_max)]
+        #   int32 [row_combine (rows) | a_perm (rows) | p_perm (rows) | lab_perm (nnz_max)]
+        # The three permutations are stable argsorts of a_idx, p_idx and the label entities (padding counts as entity
+        # 0): the collate knows all ids of the batch, so the sorts of the three deterministic scatters are done there,
+        # once per batch, off the step's critical path (kgeb_scatter_add_rows_perm)
         nz = max(nnz_max, 1)
         self.n_i64 = 3 * rows + 1 + nz
-        self.input_bytes = torch.zeros(self.n_i64 * 8 + rows * 4, dtype=torch.uint8, device=dev)
+        self.input_bytes = torch.zeros(self.n_i64 * 8 + (3 * rows + nz) * 4, dtype=torch.uint8, device=dev)
         v64 = self.input_bytes[: self.n_i64 * 8].view(torch.int64)
         self.a_idx, self.p_idx = v64[:rows], v64[rows:2 * rows]
         self.lab_off, self.lab_col = v64[2 * rows:3 * rows + 1], v64[3 * rows + 1:]
-        self.row_combine = self.input_bytes[self.n_i64 * 8:].view(torch.int32)
+        v32 = self.input_bytes[self.n_i64 * 8:].view(torch.int32)
+        self.row_combine, self.a_perm, self.p_perm = v32[:rows], v32[rows:2 * rows], v32[2 * rows:3 * rows]
+        self.lab_perm = v32[3 * rows:]
         # static intermediates / outputs
         self.Q = torch.empty(rows, self.d, **f32)
         self.dQ = torch.empty(rows, self.d, **f32)
@@ -103,7 +109,11 @@ class FusedAllEntityStepper:
         model_id = lib.MODELS[self.model.model]
         ent, rel = self.ent.detach(), self.rel.detach()
         sh = self.shard
-        self.gflat.zero_()
+        # the gradient buffers are cleared on the third stream, beside the query build (joined where they are first used)
+        cur = torch.cuda.current_stream()
+        self.side2.wait_stream(cur)
+        with torch.cuda.stream(self.side2):
+            self.gflat.zero_()
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
         if not self._fused_stats_in_backward():
@@ -111,6 +121,8 @@ class FusedAllEntityStepper:
                      ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
                      self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset, self._mirror_ptr(),
                      self.rowstat.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
+        if sh.distributed:
+            cur.wait_stream(self.side2)       # the stages are separate graphs there: nothing may stay forked
 
     def _loss_kernel(self):
         lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
@@ -126,13 +138,16 @@ class FusedAllEntityStepper:
             self._loss_kernel()   # KL needs the log-sum-exp before the backward
         lse = self.lse.data_ptr() if self.loss_kind == lib.LOSS_KL else None
         common = (self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, ent[sh.e_lo:sh.e_hi].data_ptr(),
-                  sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.ls,
-                  self.offset, lse, 1.0 / self.global_batch, None, self._mirror_ptr())
+                  sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
+                  self.lab_perm.data_ptr() if self.nnz_max > 0 else None, self.ls, self.offset, lse,
+                  1.0 / self.global_batch, None, self._mirror_ptr())
         # The two halves of the backward are independent: the dense table gradient (+ its label rows) goes to a second
         # stream, so that the chain of small latency-bound kernels that follows dQ on this stream (partial reduce, label
         # scatter, query-transform backward, sorted scatters) runs underneath the dTable tile kernel.
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)
+        if not sh.distributed:
+            self.side.wait_stream(self.side2)     # cleared gradient buffers
         with torch.cuda.stream(self.side):
             lib.call("kgeb_fused_bwd", *common, None, self.g_ent[sh.e_lo:sh.e_hi].data_ptr(), None, self.ws2.data_ptr(),
                      self.ws2.numel(), lib.stream_ptr(self.ent))
@@ -153,19 +168,22 @@ class FusedAllEntityStepper:
                  self.dp.data_ptr(), st)
         # relation-side chain (loss value, dp scatter, relation Adagrad) on a third stream, entity-side scatter here
         cur = torch.cuda.current_stream()
+        if not self.shard.distributed:
+            cur.wait_stream(self.side2)       # cleared gradient buffers
         self.side2.wait_stream(cur)
         with torch.cuda.stream(self.side2):
             st2 = lib.stream_ptr(self.ent)
             if self._fused_stats_in_backward():
                 self._loss_kernel()
-            lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
-                     self.g_rel.data_ptr(), self.rel.shape[0], self.sws2.data_ptr(), self.sws2.numel(), st2)
+            lib.call("kgeb_scatter_add_rows_perm", self.p_idx.data_ptr(), 1, self.p_perm.data_ptr(), self.dp.data_ptr(),
+                     self.rows, self.dr, self.g_rel.data_ptr(), self.rel.shape[0], self.sws2.data_ptr(),
+                     self.sws2.numel(), st2)
             if self.dp_world == 1:
                 s_rel = self.opt.state[self.rel]["sum"]
                 lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
                          self.lr, self.eps, 0.0, None, st2)
-        lib.call("kgeb_scatter_add_rows", self.a_idx.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
-                 self.g_q.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
+        lib.call("kgeb_scatter_add_rows_perm", self.a_idx.data_ptr(), 1, self.a_perm.data_ptr(), self.da.data_ptr(),
+                 self.rows, self.d, self.g_q.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
         if self.dp_world > 1:
             cur.wait_stream(self.side2)      # gradients complete on this stream before the all-reduce
             self._join_side()
@@ -219,12 +237,12 @@ class FusedAllEntityStepper:
 
     @property
     def kernel_launches_per_step(self) -> int:
-        """Kernels of this library per step (bench.py gpu_launches), counted from the ncu launch lists under profiles/:
-        query build 1; dTable half 11 (label weights, bf16(Q), label rows, tile kernel, pack, 4 radix-sort kernels,
-        2 segment-sum phases); dQ half 10 (label weights, bf16(Q), label rows, tile kernel, partial reduce, pack,
-        2 segment-sum phases, label row sums, statistics reduce); loss 1; query backward 1; two sorted scatters 6;
-        Adagrad 2.  KL (or fp32 math) adds the 5 forward-statistics kernels."""
-        return 32 + (0 if self._fused_stats_in_backward() else 5)
+        """Kernels of this library per step (bench.py gpu_launches), counted from the step timeline under profiles/:
+        query build 1; dTable half 7 (label weights, bf16(Q), label rows, permutation pack, 2 segment-sum phases, tile
+        kernel); dQ half 10 (label weights, bf16(Q), label rows, key pack, 2 segment-sum phases, label row sums, tile
+        kernel, partial reduce, statistics reduce); loss 1; query backward 1; two scatters 6 (permutation pack + 2 phases
+        each); Adagrad 2.  KL (or fp32 math) adds the 5 forward-statistics kernels."""
+        return 28 + (0 if self._fused_stats_in_backward() else 5)
 
     def _capture(self):
         """CUDA graphs of the three stages; NCCL collectives (sharded mode) stay outside the graphs."""
@@ -261,8 +279,28 @@ class FusedAllEntityStepper:
         torch.cuda.synchronize()
 
     # -- public -------------------------------------------------------------------------------------
-    def set_inputs(self, a_idx, p_idx, row_combine, lab_off, lab_col):
+    @staticmethod
+    def sort_perm(ids: torch.Tensor, size: int = 0) -> torch.Tensor:
+        """Stable argsort (int32) of ids, zero-padded to `size` entries -- the order in which a deterministic scatter
+        sums its rows.  Works on host or device tensors; part of the batch collate."""
+        n = max(size, ids.numel(), 1)
+        padded = torch.zeros(n, dtype=torch.int64, device=ids.device)
+        padded[: ids.numel()] = ids
+        return torch.sort(padded, stable=True).indices.to(torch.int32)
+
+    def batch_perms(self, a_idx, p_idx, lab_col):
+        """(a_perm, p_perm, lab_perm) of a batch, see __init__."""
+        if lab_col.numel() > self.nnz_max:
+            raise ValueError(f"batch has {lab_col.numel()} labels, stepper was built for at most {self.nnz_max}")
+        return self.sort_perm(a_idx), self.sort_perm(p_idx), self.sort_perm(lab_col, self.nnz_max)
+
+    def set_inputs(self, a_idx, p_idx, row_combine, lab_off, lab_col, perms=None):
         """Copies one batch into the static input buffers (host pinned or device tensors; non-blocking)."""
+        if perms is None:
+            perms = self.batch_perms(a_idx, p_idx, lab_col)
+        self.a_perm.copy_(perms[0], non_blocking=True)
+        self.p_perm.copy_(perms[1], non_blocking=True)
+        self.lab_perm.copy_(perms[2], non_blocking=True)
         self.a_idx.copy_(a_idx, non_blocking=True)
         self.p_idx.copy_(p_idx, non_blocking=True)
         self.row_combine.copy_(row_combine, non_blocking=True)
@@ -284,7 +322,10 @@ class FusedAllEntityStepper:
         if k > self.nnz_max:
             raise ValueError(f"batch has {k} labels, stepper was built for at most {self.nnz_max}")
         v64[3 * r + 1:3 * r + 1 + k] = lab_col
-        buf[self.n_i64 * 8:].view(torch.int32)[:] = row_combine
+        v32 = buf[self.n_i64 * 8:].view(torch.int32)
+        v32[:r] = row_combine
+        v32[r:2 * r], v32[2 * r:3 * r], v32[3 * r:] = self.batch_perms(torch.as_tensor(a_idx), torch.as_tensor(p_idx),
+                                                                      torch.as_tensor(lab_col))
         return buf
 
     def set_packed(self, packed: torch.Tensor):

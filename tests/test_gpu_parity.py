@@ -261,6 +261,71 @@ def test_scatter_and_segment_reduce_are_deterministic(kb):
     assert torch.equal(red[:k], a[ids[:k]])
 
 
+@pytest.mark.parametrize("n,v", [(5000, 97), (20000, 14541), (300, 3)])
+def test_scatter_with_collate_permutation_is_bit_identical(kb, n, v):
+    """kgeb_scatter_add_rows_perm (sort hoisted into the collate) == kgeb_scatter_add_rows (device sort)."""
+    gen = torch.Generator().manual_seed(n)
+    idx = torch.randint(0, v, (n,), generator=gen)
+    rows = torch.randn(n, 40, generator=gen).cuda()
+    perm = torch.sort(idx, stable=True).indices.to(torch.int32).cuda()
+    a = torch.zeros(v, 40, device="cuda")
+    b = torch.zeros(v, 40, device="cuda")
+    kb.ops.scatter_add_rows_(a, idx.cuda(), rows)
+    kb.ops.scatter_add_rows_(b, idx.cuda(), rows, perm=perm)
+    assert torch.equal(a, b)
+
+
+def test_fused_backward_label_permutation_is_bit_identical(kb):
+    b, e, d = 300, 1000, 64
+    gen = torch.Generator().manual_seed(5)
+    q = (torch.randn(b, d, generator=gen) * 0.3).cuda()
+    w = (torch.randn(e, d, generator=gen) * 0.3).cuda()
+    cols = torch.stack([torch.randperm(e, generator=gen)[:3].sort().values for _ in range(b)])
+    lab_off = torch.arange(0, 3 * b + 1, 3, dtype=torch.int64).cuda()
+    lab_col = cols.reshape(-1).contiguous().cuda()
+    perm = torch.sort(lab_col, stable=True).indices.to(torch.int32)
+    shard = kb.fused.Shard.full(e)
+    out = []
+    for lp in (None, perm):
+        dw = torch.zeros_like(w)
+        dq = kb.fused.fused_backward(q, w, lab_off, lab_col, kb.lib.LOSS_BCE, 0.0, 0.0, None, 1.0 / b, None,
+                                     kb.lib.MATH_BF16, shard, dw, lab_perm=lp)
+        out.append((dq, dw))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
+def test_graph_stepper_bf16_tiles_match_autograd_bf16_flow(kb):
+    """The graph-captured step on the BF16 tensor tiles (statistics from the dQ kernel, label permutation from the
+    collate, forked label part) against the autograd flow on the same tiles."""
+    g = kb.graph.synthetic_graph("toy", seed=3)
+    e, r, d, b = g["num_entities"], g["num_relations"], 32, 64
+    idx = [ko.kvsall_index(g["train"], "sp"), ko.kvsall_index(g["train"], "po")]
+    rng = np.random.default_rng(4)
+    batches = []
+    for _ in range(3):
+        ids = rng.choice(len(idx[0][0]) + len(idx[1][0]), b, replace=False)
+        q, c, qt = ko.kvsall_collate(ids.tolist(), idx)
+        batches.append({"queries": T(q), "label_coords": T(c), "query_type_indexes": T(qt)})
+    nnz_max = max(len(x["label_coords"]) for x in batches) + 7
+    torch.manual_seed(0)
+    ref = kb.KgeModel("complex", e, r, d).cuda()
+    with torch.no_grad():
+        for p_ in ref.parameters():
+            p_.mul_(0.2)
+    new = kb.KgeModel("complex", e, r, d).cuda()
+    new.load_state_dict(ref.state_dict())
+    mk = lambda m: kb.TrainingJobKvsAll(m, kb.optim.create("Adagrad", m.parameters(), lr=0.05), kb.KgeLoss.create("bce"),
+                                        e, r, math_mode=kb.lib.MATH_BF16)
+    jr, jn = mk(ref), mk(new)
+    jn.enable_graph_step(b, nnz_max)
+    for i, batch in enumerate(batches):
+        a = jr.step(i, batch)
+        c = jn.step(i, jn.collate_packed(batch) if i % 2 else batch)
+        assert c.avg_loss == pytest.approx(a.total_loss, rel=1e-3)
+        close(new.get_s_embedder().weight, ref.get_s_embedder().weight, rtol=2e-3, what=f"entity table step {i}")
+        close(new.get_p_embedder().weight, ref.get_p_embedder().weight, rtol=2e-3, what=f"relation table step {i}")
+
+
 def test_kvsall_index_device_lookup_bit_exact(kb, golden):
     g = golden("index")
     tr = g["index.train.triples"]
