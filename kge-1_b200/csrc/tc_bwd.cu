@@ -271,14 +271,16 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           const float x = v[c];
           if (LOSS == KGEB_LOSS_KL) {
             const float kc = RES_IS_Q ? col_k : __shfl_sync(0xffffffffu, col_k, c);
-            v[c] = ex2_ftz(fmaf(x, kLog2e, kc));
+            const float a = fmaf(x, kLog2e, kc);
+            v[c] = ((c & 7) < KGEB_POLY8_KL) ? ex2_poly<3, false>(a) : ex2_ftz(a);
           } else {
             const float rs = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c) : col_rs;
             if (STATS) {
               // sigmoid and softplus from one exponential (3 MUFU: ex2, rcp, lg2), cancellation-free:
               //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
               const float z = x + p.offset;
-              const float e = ex2_ftz(fabsf(z) * -kLog2e);
+              const float t = fabsf(z) * -kLog2e;
+              const float e = ((c & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t) : ex2_ftz(t);
               const float a = 1.f + e;
               const float r = rcp_ftz(a);
               st_lg += lg2_ftz(a);
@@ -287,7 +289,9 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
               v[c] = fmaf(z >= 0.f ? r : e * r, rs, -p.ls_add * rs);
             } else {
               // rs * (sigmoid(x + offset) - ls_add): FFMA, EX2 (inf for very negative z -> rcp gives 0), FADD, RCP, FFMA
-              v[c] = fmaf(rcp_ftz(1.f + ex2_ftz(fmaf(x, -kLog2e, off2))), rs, -p.ls_add * rs);
+              const float t = fmaf(x, -kLog2e, off2);
+              const float e = ((c & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t) : ex2_ftz(t);
+              v[c] = fmaf(rcp_ftz(1.f + e), rs, -p.ls_add * rs);
             }
           }
         }

@@ -167,6 +167,37 @@ __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite split with the round-to-nearest magic constant, minimax polynomial on
+// [-0.5, 0.5], exponent inserted with one integer multiply-add).  The tile epilogues are bound by the 16-lane MUFU
+// pipe; evaluating a compile-time fraction of the exponentials here (FlashAttention-4's trick) moves that work to
+// pipes with spare issue slots.  Relative error: degree 3 -> 7.5e-5 (results that are rounded to bf16 anyway),
+// degree 4 -> 2.7e-6 (loss statistics).  x is clamped to the normal exponent range; CLAMP_HI = false when x <= ~0.
+template <int DEG, bool CLAMP_HI>
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  if (CLAMP_HI) x = fminf(x, 126.f);
+  const float xf = x + 12582912.f;                  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (xf - 12582912.f);            // x - round(x)
+  float p;
+  if (DEG == 3) {
+    p = fmaf(fmaf(fmaf(0.0551716685f, f, 0.2426111251f), f, 0.6932609677f), f, 0.9999280572f);
+  } else {
+    p = fmaf(fmaf(fmaf(fmaf(0.009570102207f, f, 0.05591785908f), f, 0.2402474433f), f, 0.6931217909f), f,
+             0.9999992847f);
+  }
+  return __int_as_float(__float_as_int(xf) * (1 << 23) + __float_as_int(p));   // p * 2^round(x)
+}
+// exponentials of columns (c & 7) < N8 of an unrolled epilogue loop go to the polynomial, the others to the MUFU
+#ifndef KGEB_POLY8_BCE
+#define KGEB_POLY8_BCE 5
+#endif
+#ifndef KGEB_POLY8_KL
+#define KGEB_POLY8_KL 3
+#endif
+#ifndef KGEB_POLY8_STATS
+#define KGEB_POLY8_STATS 5
+#endif
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(

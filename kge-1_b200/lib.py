@@ -61,11 +61,12 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("KGEB200_LIB", LIB_PATH)   # tuning builds (tools/build_variant.sh); default = in-tree library
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} not found: the CUDA extension is not built (run `python -c 'import __graft_entry__ as g; "
+            f"{path} not found: the CUDA extension is not built (run `python -c 'import __graft_entry__ as g; "
             "g.build()'` or kge-1_b200/csrc/build.sh).  There is no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
