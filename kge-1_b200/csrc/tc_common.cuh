@@ -187,15 +187,19 @@ __device__ __forceinline__ float ex2_poly(float x) {
   }
   return __int_as_float(__float_as_int(xf) * (1 << 23) + __float_as_int(p));   // p * 2^round(x)
 }
-// exponentials of columns (c & 7) < N8 of an unrolled epilogue loop go to the polynomial, the others to the MUFU
+// exponentials of columns (c & 7) < N8 of an unrolled epilogue loop go to the polynomial, the others to the MUFU.
+// Measured on B200 (tools/build_variant.sh, bench.py + bench_extra.py wd5m-1vsall): every N8 > 0 was slower than
+// MUFU-only (BCE dQ 62.9 -> 67.3 / 72.4 us at N8 = 3 / 6, dTable 63.5 -> 64.4 / 67.2 us; KL step 16.4 -> 17.2 /
+// 17.6 ms): these epilogues are bound by dependent-issue latency, not by MUFU throughput alone, so the extra
+// FMA-pipe instructions cost more than the MUFU slots they free.  Default 0; kept for re-tuning.
 #ifndef KGEB_POLY8_BCE
-#define KGEB_POLY8_BCE 5
+#define KGEB_POLY8_BCE 0
 #endif
 #ifndef KGEB_POLY8_KL
-#define KGEB_POLY8_KL 3
+#define KGEB_POLY8_KL 0
 #endif
 #ifndef KGEB_POLY8_STATS
-#define KGEB_POLY8_STATS 5
+#define KGEB_POLY8_STATS 0
 #endif
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
