@@ -194,6 +194,40 @@ int kgeb_adam_dense(float* W, float* exp_avg, float* exp_avg_sq, const float* gr
 int kgeb_csr_lookup(const int64_t* keys, int64_t num_keys, const int64_t* query_pairs, int64_t n,
                     int64_t* row_out, void* stream);
 
+/* ---- 8f-1: on-device batch construction from device-resident KvsAllIndex arrays.
+ * kgeb_index_t = one index of the reference (indexing.py:8-98) on the device: keys [num_keys,2] sorted
+ * lexicographically, offsets [num_keys+1], values; all int64. */
+typedef struct {
+  const int64_t* keys;
+  int64_t num_keys;
+  const int64_t* offsets;
+  const int64_t* values;
+} kgeb_index_t;
+
+/* Filter CSR of an evaluation batch (EntityRankingJob._collate, entity_ranking.py:53-77; job/util.py:5-38): for the
+ * triples (s,p,o)[B] and num_splits filter splits (host arrays of index descriptors, <= 4), source list
+ * j = row * num_splits + k holds, for row < B, the known objects of (s,p) in split k and, for row >= B, the known
+ * subjects of (p,o) of triple row-B.  count: src_row[j] = key row in that index or -1, len[j] = list length.
+ * The caller turns len into positions pos[] (exclusive scan); fill copies the lists to col[pos[j]...] and/or writes
+ * sort_keys = (row << 32) | value, whose ascending order is the per-row merged order the ranking kernel needs. */
+int kgeb_filter_csr_count(const kgeb_index_t* sp_indexes, const kgeb_index_t* po_indexes, int num_splits, const void* s,
+                          const void* p, const void* o, int idx64, int64_t B, int64_t* src_row /*[2B*num_splits]*/,
+                          int64_t* len /*[2B*num_splits]*/, void* stream);
+int kgeb_filter_csr_fill(const kgeb_index_t* sp_indexes, const kgeb_index_t* po_indexes, int num_splits, int64_t B,
+                         const int64_t* src_row, const int64_t* pos, int64_t* col /* or NULL */,
+                         int64_t* sort_keys /* or NULL */, void* stream);
+
+/* KvsAll training batch (TrainingJobKvsAll collate, train.py:590-677) from example ids: id < sp.num_keys is the
+ * sp-query of that key row of the sp index, the others are po-queries of row id - sp.num_keys.  count writes the
+ * query rows in the layout of kgeb_query_build (a_idx = the entity of the key, p_idx = its relation, row_combine) and
+ * the label counts; the caller scans them into lab_off[B+1]; fill writes the label entities to lab_col (capacity
+ * entries; *overflow is set to 1 on the device when a batch does not fit). */
+int kgeb_kvsall_batch_count(const kgeb_index_t* sp_index, const kgeb_index_t* po_index, const int64_t* example_ids,
+                            int64_t B, int64_t* a_idx, int64_t* p_idx, int32_t* row_combine, int64_t* len, void* stream);
+int kgeb_kvsall_batch_fill(const kgeb_index_t* sp_index, const kgeb_index_t* po_index, const int64_t* example_ids,
+                           int64_t B, const int64_t* lab_off, int64_t capacity, int64_t* lab_col, int32_t* overflow,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

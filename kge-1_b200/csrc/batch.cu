@@ -1,0 +1,179 @@
+// On-device batch construction from device-resident KvsAllIndex arrays: the steps *before* the hot
+// path that the reference does with Python dict lookups per triple.
+//   * filter CSR of an evaluation batch   -- EntityRankingJob._collate + get_sp_po_coords_from_spo_batch
+//     (kge/job/entity_ranking.py:53-77, kge/job/util.py:5-38)
+//   * query rows + label CSR of a KvsAll training batch -- TrainingJobKvsAll collate (kge/job/train.py:590-677)
+// Both are "gather CSR rows": a count pass (one thread per source list: key binary search, length), an exclusive
+// scan by the caller, and a fill pass (one warp per source list, coalesced copies).  Integer work only; results are
+// bit-exact by construction and compared against the reference's coordinates in the tests.
+#include <cstdint>
+
+#include "../../include/kgeb200.h"
+#include "common.cuh"
+
+namespace kgeb {
+
+constexpr int MAX_SPLITS = 4;
+
+struct IndexSet {            // K splits x (sp index, po index), passed by value to the kernels
+  kgeb_index_t sp[MAX_SPLITS];
+  kgeb_index_t po[MAX_SPLITS];
+  int k;
+};
+
+// row of the key pair (a, b) in the lexicographically sorted keys [num_keys, 2], or -1
+__device__ __forceinline__ int64_t find_key(const kgeb_index_t& ix, int64_t a, int64_t b) {
+  int64_t lo = 0, hi = ix.num_keys;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int64_t ka = ix.keys[2 * mid], kb = ix.keys[2 * mid + 1];
+    if (ka < a || (ka == a && kb < b)) lo = mid + 1; else hi = mid;
+  }
+  return (lo < ix.num_keys && ix.keys[2 * lo] == a && ix.keys[2 * lo + 1] == b) ? lo : -1;
+}
+
+// Source list j = row * K + k of an evaluation batch: rows [0,B) = known objects of (s,p) in split k, rows [B,2B) =
+// known subjects of (p,o) in split k.
+__global__ void filter_count_kernel(IndexSet set, const void* __restrict__ s, const void* __restrict__ p,
+                                    const void* __restrict__ o, int idx64, int64_t B, int64_t* __restrict__ src_row,
+                                    int64_t* __restrict__ len) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= 2 * B * set.k) return;
+  const int64_t row = j / set.k;
+  const int k = (int)(j % set.k);
+  const bool sp = row < B;
+  const int64_t t = sp ? row : row - B;
+  const kgeb_index_t& ix = sp ? set.sp[k] : set.po[k];
+  const int64_t a = sp ? load_index(s, idx64, t) : load_index(p, idx64, t);
+  const int64_t b = sp ? load_index(p, idx64, t) : load_index(o, idx64, t);
+  const int64_t r = find_key(ix, a, b);
+  src_row[j] = r;
+  len[j] = r < 0 ? 0 : ix.offsets[r + 1] - ix.offsets[r];
+}
+
+// one warp per source list: values -> col[pos[j] ...]; key_out (optional) = (row << 32) | value for the per-row sort
+__global__ void __launch_bounds__(256)
+filter_fill_kernel(IndexSet set, int64_t B, const int64_t* __restrict__ src_row, const int64_t* __restrict__ pos,
+                   int64_t* __restrict__ col, int64_t* __restrict__ key_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= 2 * B * set.k) return;
+  const int64_t r = src_row[j];
+  if (r < 0) return;
+  const int64_t row = j / set.k;
+  const int k = (int)(j % set.k);
+  const kgeb_index_t& ix = row < B ? set.sp[k] : set.po[k];
+  const int64_t b0 = ix.offsets[r], n = ix.offsets[r + 1] - b0, dst = pos[j];
+  for (int64_t i = lane; i < n; i += 32) {
+    const int64_t v = ix.values[b0 + i];
+    if (col) col[dst + i] = v;
+    if (key_out) key_out[dst + i] = (row << 32) | v;
+  }
+}
+
+// KvsAll training batch: example id < n_sp is the sp-query with key row id of the sp index, the others are po-queries
+// (train.py:611-640: queries = the key pair, labels = the values of that key).
+__global__ void kvsall_count_kernel(kgeb_index_t sp, kgeb_index_t po, const int64_t* __restrict__ ids, int64_t B,
+                                    int64_t* __restrict__ a_idx, int64_t* __restrict__ p_idx,
+                                    int32_t* __restrict__ row_combine, int64_t* __restrict__ len) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const int64_t id = ids[i];
+  const bool is_sp = id < sp.num_keys;
+  const kgeb_index_t& ix = is_sp ? sp : po;
+  const int64_t r = is_sp ? id : id - sp.num_keys;
+  // sp key = (s, p): entity first; po key = (p, o): entity second
+  a_idx[i] = is_sp ? ix.keys[2 * r] : ix.keys[2 * r + 1];
+  p_idx[i] = is_sp ? ix.keys[2 * r + 1] : ix.keys[2 * r];
+  row_combine[i] = is_sp ? KGEB_SP_ : KGEB__PO;
+  len[i] = ix.offsets[r + 1] - ix.offsets[r];
+}
+
+__global__ void __launch_bounds__(256)
+kvsall_fill_kernel(kgeb_index_t sp, kgeb_index_t po, const int64_t* __restrict__ ids, int64_t B,
+                   const int64_t* __restrict__ lab_off, int64_t capacity, int64_t* __restrict__ lab_col,
+                   int32_t* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= B) return;
+  const int64_t id = ids[i];
+  const bool is_sp = id < sp.num_keys;
+  const kgeb_index_t& ix = is_sp ? sp : po;
+  const int64_t r = is_sp ? id : id - sp.num_keys;
+  const int64_t b0 = ix.offsets[r], n = ix.offsets[r + 1] - b0, dst = lab_off[i];
+  if (dst + n > capacity) {          // the static label buffer of the graph-captured step is too small for this batch
+    if (lane == 0) *overflow = 1;
+    return;
+  }
+  for (int64_t k = lane; k < n; k += 32) lab_col[dst + k] = ix.values[b0 + k];
+}
+
+static bool index_ok(const kgeb_index_t& ix) { return ix.num_keys >= 0 && (ix.num_keys == 0 || (ix.keys && ix.offsets && ix.values)); }
+
+}  // namespace kgeb
+
+using namespace kgeb;
+
+extern "C" {
+
+int kgeb_filter_csr_count(const kgeb_index_t* sp_indexes, const kgeb_index_t* po_indexes, int num_splits, const void* s,
+                          const void* p, const void* o, int idx64, int64_t B, int64_t* src_row, int64_t* len,
+                          void* stream) {
+  KGEB_REQUIRE(num_splits >= 1 && num_splits <= MAX_SPLITS, "filter_csr: 1..%d splits (got %d)", MAX_SPLITS, num_splits);
+  KGEB_REQUIRE(sp_indexes && po_indexes && s && p && o && src_row && len && B >= 0, "filter_csr_count: bad arguments");
+  if (B == 0) return KGEB_OK;
+  IndexSet set;
+  set.k = num_splits;
+  for (int k = 0; k < num_splits; ++k) {
+    KGEB_REQUIRE(index_ok(sp_indexes[k]) && index_ok(po_indexes[k]), "filter_csr_count: index %d has NULL arrays", k);
+    set.sp[k] = sp_indexes[k];
+    set.po[k] = po_indexes[k];
+  }
+  const int64_t n = 2 * B * num_splits;
+  filter_count_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(set, s, p, o, idx64, B, src_row, len);
+  KGEB_LAUNCH_CHECK("filter_count");
+  return KGEB_OK;
+}
+
+int kgeb_filter_csr_fill(const kgeb_index_t* sp_indexes, const kgeb_index_t* po_indexes, int num_splits, int64_t B,
+                         const int64_t* src_row, const int64_t* pos, int64_t* col, int64_t* sort_keys, void* stream) {
+  KGEB_REQUIRE(num_splits >= 1 && num_splits <= MAX_SPLITS, "filter_csr: 1..%d splits (got %d)", MAX_SPLITS, num_splits);
+  KGEB_REQUIRE(sp_indexes && po_indexes && src_row && pos && (col || sort_keys) && B >= 0, "filter_csr_fill: bad arguments");
+  if (B == 0) return KGEB_OK;
+  IndexSet set;
+  set.k = num_splits;
+  for (int k = 0; k < num_splits; ++k) {
+    set.sp[k] = sp_indexes[k];
+    set.po[k] = po_indexes[k];
+  }
+  const int64_t n = 2 * B * num_splits;
+  filter_fill_kernel<<<(unsigned)((n + 7) / 8), 256, 0, as_stream(stream)>>>(set, B, src_row, pos, col, sort_keys);
+  KGEB_LAUNCH_CHECK("filter_fill");
+  return KGEB_OK;
+}
+
+int kgeb_kvsall_batch_count(const kgeb_index_t* sp_index, const kgeb_index_t* po_index, const int64_t* example_ids,
+                            int64_t B, int64_t* a_idx, int64_t* p_idx, int32_t* row_combine, int64_t* len, void* stream) {
+  KGEB_REQUIRE(sp_index && po_index && example_ids && a_idx && p_idx && row_combine && len && B >= 0,
+               "kvsall_batch_count: bad arguments");
+  KGEB_REQUIRE(index_ok(*sp_index) && index_ok(*po_index), "kvsall_batch_count: index has NULL arrays");
+  if (B == 0) return KGEB_OK;
+  kvsall_count_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(*sp_index, *po_index, example_ids, B,
+                                                                                 a_idx, p_idx, row_combine, len);
+  KGEB_LAUNCH_CHECK("kvsall_count");
+  return KGEB_OK;
+}
+
+int kgeb_kvsall_batch_fill(const kgeb_index_t* sp_index, const kgeb_index_t* po_index, const int64_t* example_ids,
+                           int64_t B, const int64_t* lab_off, int64_t capacity, int64_t* lab_col, int32_t* overflow,
+                           void* stream) {
+  KGEB_REQUIRE(sp_index && po_index && example_ids && lab_off && lab_col && overflow && B >= 0 && capacity >= 0,
+               "kvsall_batch_fill: bad arguments");
+  if (B == 0) return KGEB_OK;
+  kvsall_fill_kernel<<<(unsigned)((B + 7) / 8), 256, 0, as_stream(stream)>>>(*sp_index, *po_index, example_ids, B,
+                                                                             lab_off, capacity, lab_col, overflow);
+  KGEB_LAUNCH_CHECK("kvsall_fill");
+  return KGEB_OK;
+}
+
+}  // extern "C"

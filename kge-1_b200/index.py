@@ -61,6 +61,68 @@ class KvsAllIndex:
         return out
 
 
+def filter_csr(sp_indexes: Sequence["KvsAllIndex"], po_indexes: Sequence["KvsAllIndex"], s, p, o):
+    """Filter CSR of an evaluation batch, built on the device (kgeb_filter_csr_count / _fill): rows 0..B-1 = known
+    objects of (s,p), rows B..2B-1 = known subjects of (p,o), over all given splits, ascending per row (duplicates
+    kept; the ranking kernels skip repeated columns).  Replaces EntityRankingJob._collate's dict lookups
+    (entity_ranking.py:53-77, job/util.py:5-38).  One host sync (the total size of the result)."""
+    dev = s.device
+    k, b = len(sp_indexes), s.numel()
+    sp = lib.index_descs([ix.device_arrays(dev) for ix in sp_indexes])
+    po = lib.index_descs([ix.device_arrays(dev) for ix in po_indexes])
+    sp_ptr, s64 = lib.idx(s.contiguous())
+    if p.dtype != s.dtype or o.dtype != s.dtype:
+        raise ValueError("s, p, o must have the same index dtype")
+    st = lib.stream_ptr(s)
+    n = 2 * b * k
+    src_row = torch.empty(n, dtype=torch.int64, device=dev)
+    pos = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    lib.call("kgeb_filter_csr_count", sp, po, k, sp_ptr, p.contiguous().data_ptr(), o.contiguous().data_ptr(), s64, b,
+             src_row.data_ptr(), pos[1:].data_ptr(), st)
+    torch.cumsum(pos[1:], 0, out=pos[1:])
+    off = pos[::k].contiguous()
+    total = int(pos[-1].item())
+    col = torch.empty(total, dtype=torch.int64, device=dev)
+    if total == 0:
+        return off, col
+    if k == 1:     # a single sorted list per row
+        lib.call("kgeb_filter_csr_fill", sp, po, k, b, src_row.data_ptr(), pos.data_ptr(), col.data_ptr(), None, st)
+        return off, col
+    lib.call("kgeb_filter_csr_fill", sp, po, k, b, src_row.data_ptr(), pos.data_ptr(), None, col.data_ptr(), st)
+    col = torch.sort(col).values          # keys (row << 32 | entity): merges the per-split lists of every row
+    return off, col.bitwise_and_(0xFFFFFFFF)
+
+
+def kvsall_batch(sp_index: "KvsAllIndex", po_index: "KvsAllIndex", example_ids: torch.Tensor, out=None, capacity=None):
+    """KvsAll training batch on the device from example ids (kgeb_kvsall_batch_count / _fill; train.py:590-677):
+    returns (a_idx, p_idx, row_combine, lab_off, lab_col, overflow).  With `out` = (a_idx, p_idx, row_combine, lab_off,
+    lab_col) preallocated static buffers nothing is allocated and nothing syncs; lab_col then has `capacity` entries and
+    the int32 device flag `overflow` reports a batch that did not fit."""
+    dev = example_ids.device
+    b = example_ids.numel()
+    sp = lib.index_descs([sp_index.device_arrays(dev)])
+    po = lib.index_descs([po_index.device_arrays(dev)])
+    st = lib.stream_ptr(example_ids)
+    ids = lib.i64(example_ids.contiguous(), "example ids")
+    if out is None:
+        a = torch.empty(b, dtype=torch.int64, device=dev)
+        p = torch.empty(b, dtype=torch.int64, device=dev)
+        rc = torch.empty(b, dtype=torch.int32, device=dev)
+        lab_off = torch.zeros(b + 1, dtype=torch.int64, device=dev)
+    else:
+        a, p, rc, lab_off, lab_col = out
+        lab_off[:1].zero_()
+    lib.call("kgeb_kvsall_batch_count", sp, po, ids, b, a.data_ptr(), p.data_ptr(), rc.data_ptr(), lab_off[1:].data_ptr(), st)
+    torch.cumsum(lab_off[1:], 0, out=lab_off[1:])
+    if out is None:
+        capacity = int(lab_off[-1].item())
+        lab_col = torch.empty(capacity, dtype=torch.int64, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib.call("kgeb_kvsall_batch_fill", sp, po, ids, b, lab_off.data_ptr(), int(capacity), lab_col.data_ptr(),
+             overflow.data_ptr(), st)
+    return a, p, rc, lab_off, lab_col, overflow
+
+
 def gather_csr_rows(offsets: torch.Tensor, values: torch.Tensor, rows: torch.Tensor, add: int = 0):
     """CSR slice for the given index rows (-1 = empty): returns (row_offsets [n+1], concatenated values + add)."""
     valid = rows >= 0

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import fused, lib, ops
-from .index import KvsAllIndex, gather_csr_rows, merge_sorted_csr
+from .index import KvsAllIndex, filter_csr, gather_csr_rows, merge_sorted_csr
 from .model import KgeModel, ReciprocalRelationsModel
 
 S, P, O = 0, 1, 2
@@ -305,17 +305,9 @@ class EntityRankingJob:
         self.test_indexes = (KvsAllIndex(test_split, "sp"), KvsAllIndex(test_split, "po")) if test_split is not None else None
 
     def _filter_csr(self, indexes, s, p, o):
-        """Device-side replacement of _collate / get_sp_po_coords_from_spo_batch (job/util.py:5-38):
-        rows 0..B-1 = known objects of (s,p); rows B..2B-1 = known subjects of (p,o)."""
-        b = len(s)
-        parts = []
-        for sp_idx, po_idx in indexes:
-            _, off, val = sp_idx.device_arrays(self.device)
-            o_off, o_col = gather_csr_rows(off, val, sp_idx.lookup(torch.stack((s, p), 1)))
-            _, off, val = po_idx.device_arrays(self.device)
-            s_off, s_col = gather_csr_rows(off, val, po_idx.lookup(torch.stack((p, o), 1)))
-            parts.append((torch.cat((o_off, s_off[1:] + o_off[-1])), torch.cat((o_col, s_col))))
-        return parts
+        """Device-side replacement of _collate / get_sp_po_coords_from_spo_batch (job/util.py:5-38): one merged CSR
+        over the given (sp, po) index pairs; rows 0..B-1 = known objects of (s,p); rows B..2B-1 = known subjects of (p,o)."""
+        return filter_csr([sp for sp, _ in indexes], [po for _, po in indexes], s, p, o)
 
     def _get_ranks(self, rank, ties):
         if self.tie_handling == "rounded_mean_rank":
@@ -340,11 +332,10 @@ class EntityRankingJob:
         q = torch.cat((model.queries(lib.SP_, s, p), q_po)).contiguous()
         true_ent = torch.cat((o, s)).contiguous()
         true_score = torch.cat((o_true, s_true)).contiguous()
-        parts = self._filter_csr(self.filter_indexes, s, p, o)
-        filt = merge_sorted_csr(parts, 2 * b) if parts else None
+        filt = self._filter_csr(self.filter_indexes, s, p, o) if self.filter_indexes else None
         filt_test = None
         if self.test_indexes is not None:
-            filt_test = merge_sorted_csr(parts + self._filter_csr([self.test_indexes], s, p, o), 2 * b)
+            filt_test = self._filter_csr(list(self.filter_indexes) + [self.test_indexes], s, p, o)
         scorer = model.get_scorer()
         table = model.get_o_embedder().embed_all()
         if self.shard is not None:  # this rank scores its own entity rows; counts are all-reduced (exact integers)

@@ -50,7 +50,27 @@ SIGNATURES = {
     "kgeb_adagrad_rows": [_p, _p, _p, _p, _p, _l, _i, _f, _f, _p],
     "kgeb_adam_dense": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _f, _p],
     "kgeb_csr_lookup": [_p, _l, _p, _l, _p, _p],
+    "kgeb_filter_csr_count": [_p, _p, _i, _p, _p, _p, _i, _l, _p, _p, _p],
+    "kgeb_filter_csr_fill": [_p, _p, _i, _l, _p, _p, _p, _p, _p],
+    "kgeb_kvsall_batch_count": [_p, _p, _p, _l, _p, _p, _p, _p, _p],
+    "kgeb_kvsall_batch_fill": [_p, _p, _p, _l, _p, _l, _p, _p, _p],
 }
+
+
+class IndexDesc(ctypes.Structure):
+    """kgeb_index_t of include/kgeb200.h: one KvsAllIndex resident on the device."""
+    _fields_ = [("keys", _c.c_void_p), ("num_keys", _c.c_int64), ("offsets", _c.c_void_p), ("values", _c.c_void_p)]
+
+
+def index_descs(arrays) -> "ctypes.Array":
+    """Host array of kgeb_index_t from [(keys [K,2], offsets [K+1], values)] int64 CUDA tensors."""
+    out = (IndexDesc * len(arrays))()
+    for d, (keys, offsets, values) in zip(out, arrays):
+        for t in (keys, offsets, values):
+            if not t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous():
+                raise ValueError("index arrays must be contiguous int64 CUDA tensors")
+        d.keys, d.num_keys, d.offsets, d.values = keys.data_ptr(), keys.shape[0], offsets.data_ptr(), values.data_ptr()
+    return out
 _INT64_RESULT = {"kgeb_fused_workspace_bytes": [_l, _i, _l, _l], "kgeb_scatter_workspace_bytes": [_l, _i]}
 
 _lib: Optional[ctypes.CDLL] = None

@@ -326,6 +326,52 @@ def test_graph_stepper_bf16_tiles_match_autograd_bf16_flow(kb):
         close(new.get_p_embedder().weight, ref.get_p_embedder().weight, rtol=2e-3, what=f"relation table step {i}")
 
 
+def test_device_filter_csr_matches_reference_coordinates(kb, golden):
+    """kgeb_filter_csr_* against get_sp_po_coords_from_spo_batch (job/util.py:5-38) restated in the oracle, for one
+    split and for the union of two splits: per row the same multiset of (column) coordinates, ascending."""
+    g = kb.graph.synthetic_graph("toy", seed=5)
+    e = g["num_entities"]
+    splits = [g["train"], g["valid"]]
+    batch = np.concatenate([g["valid"][:40], g["train"][:25], np.array([[0, 0, 0], [e - 1, 0, e - 1]])]).astype(np.int64)
+    s, p, o = (torch.from_numpy(batch[:, i].copy()).cuda() for i in range(3))
+    for use in ([0], [0, 1]):
+        sp = [kb.index.KvsAllIndex(splits[i], "sp") for i in use]
+        po = [kb.index.KvsAllIndex(splits[i], "po") for i in use]
+        off, col = kb.index.filter_csr(sp, po, s, p, o)
+        off, col = off.cpu().numpy(), col.cpu().numpy()
+        b = len(batch)
+        want = [[] for _ in range(2 * b)]
+        for i in use:
+            coords = ko.sp_po_coords(batch, e, ko.CsrIndex(splits[i], "sp"), ko.CsrIndex(splits[i], "po"))
+            for r, c in coords.tolist():
+                want[r if c < e else b + r].append(c if c < e else c - e)
+        assert off[0] == 0 and off[-1] == len(col) == sum(len(w) for w in want)
+        for r in range(2 * b):
+            assert col[off[r]:off[r + 1]].tolist() == sorted(want[r]), f"row {r} splits {use}"
+    # int32 triples (the evaluation dtype of the reference, dataset.py:178) give the same CSR
+    off32, col32 = kb.index.filter_csr(sp, po, s.int(), p.int(), o.int())
+    assert torch.equal(off32.cpu(), torch.from_numpy(off)) and torch.equal(col32.cpu(), torch.from_numpy(col))
+
+
+def test_device_kvsall_batch_matches_reference_collate(kb):
+    """kgeb_kvsall_batch_* against TrainingJobKvsAll's collate (train.py:590-677) restated in the oracle."""
+    g = kb.graph.synthetic_graph("toy", seed=3)
+    idx = [ko.kvsall_index(g["train"], "sp"), ko.kvsall_index(g["train"], "po")]
+    sp, po = kb.index.KvsAllIndex(g["train"], "sp"), kb.index.KvsAllIndex(g["train"], "po")
+    ids = np.random.default_rng(0).choice(len(idx[0][0]) + len(idx[1][0]), 97, replace=False)
+    q, coords, qt = ko.kvsall_collate(ids.tolist(), idx)
+    a, p_, rc, lab_off, lab_col, ovf = kb.index.kvsall_batch(sp, po, torch.from_numpy(ids).cuda())
+    wa, wp, wrc = kb.trainer.kvsall_rows(T(q), T(qt))
+    assert torch.equal(a.cpu(), wa) and torch.equal(p_.cpu(), wp) and torch.equal(rc.cpu(), wrc) and ovf.item() == 0
+    w_off, w_col = kb.fused.csr_from_coords(T(coords), len(ids))
+    assert torch.equal(lab_off.cpu(), w_off) and torch.equal(lab_col.cpu(), w_col)
+    # static buffers: no allocation, overflow flag when the label buffer is too small
+    out = (torch.empty_like(a), torch.empty_like(p_), torch.empty_like(rc), torch.empty_like(lab_off),
+           torch.zeros(len(w_col) - 1, dtype=torch.int64, device="cuda"))
+    *_, ovf = kb.index.kvsall_batch(sp, po, torch.from_numpy(ids).cuda(), out=out, capacity=len(w_col) - 1)
+    assert ovf.item() == 1 and torch.equal(out[3].cpu(), w_off)
+
+
 def test_kvsall_index_device_lookup_bit_exact(kb, golden):
     g = golden("index")
     tr = g["index.train.triples"]
