@@ -228,6 +228,16 @@ int kgeb_kvsall_batch_fill(const kgeb_index_t* sp_index, const kgeb_index_t* po_
                            int64_t B, const int64_t* lab_off, int64_t capacity, int64_t* lab_col, int32_t* overflow,
                            void* stream);
 
+/* The whole KvsAll batch in one call, straight into the static input buffers of the graph-captured step: count,
+ * scan, fill (lab_col zero-padded to `capacity`) and the three stable argsorts a_perm[B], p_perm[B], lab_perm[capacity]
+ * (int32) that kgeb_fused_bwd / kgeb_scatter_add_rows_perm take.  No host synchronisation, no allocation. */
+int64_t kgeb_kvsall_build_workspace_bytes(int64_t B, int64_t capacity);
+int kgeb_kvsall_batch_build(const kgeb_index_t* sp_index, const kgeb_index_t* po_index, const int64_t* example_ids,
+                            int64_t B, int64_t capacity, int64_t num_entities, int64_t num_relations, int64_t* a_idx,
+                            int64_t* p_idx, int32_t* row_combine, int64_t* lab_off, int64_t* lab_col, int32_t* a_perm,
+                            int32_t* p_perm, int32_t* lab_perm, int32_t* overflow, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,8 @@
 // bit-exact by construction and compared against the reference's coordinates in the tests.
 #include <cstdint>
 
-#include "../../include/kgeb200.h"
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 
 namespace kgeb {
@@ -108,6 +109,33 @@ kvsall_fill_kernel(kgeb_index_t sp, kgeb_index_t po, const int64_t* __restrict__
   for (int64_t k = lane; k < n; k += 32) lab_col[dst + k] = ix.values[b0 + k];
 }
 
+__global__ void iota_kernel(int32_t* __restrict__ out, int64_t n, int64_t* __restrict__ first_off) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)i;
+  if (i == 0 && first_off) *first_off = 0;
+}
+
+static int bits_needed(int64_t x) {  // smallest b with 2^b >= x
+  int b = 1;
+  while (b < 62 && ((int64_t)1 << b) < x) ++b;
+  return b;
+}
+static size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct BuildWs {
+  int64_t* keys_tmp;   // [n] sorted keys (discarded)
+  int32_t* iota;       // [n]
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+static size_t build_cub_bytes(int64_t n) {
+  size_t a = 0, b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const int64_t*)nullptr, (int64_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)n, 0, 40);
+  cub::DeviceScan::InclusiveSum(nullptr, b, (const int64_t*)nullptr, (int64_t*)nullptr, (int)n);
+  return a > b ? a : b;
+}
+
 static bool index_ok(const kgeb_index_t& ix) { return ix.num_keys >= 0 && (ix.num_keys == 0 || (ix.keys && ix.offsets && ix.values)); }
 
 }  // namespace kgeb
@@ -173,6 +201,62 @@ int kgeb_kvsall_batch_fill(const kgeb_index_t* sp_index, const kgeb_index_t* po_
   kvsall_fill_kernel<<<(unsigned)((B + 7) / 8), 256, 0, as_stream(stream)>>>(*sp_index, *po_index, example_ids, B,
                                                                              lab_off, capacity, lab_col, overflow);
   KGEB_LAUNCH_CHECK("kvsall_fill");
+  return KGEB_OK;
+}
+
+int64_t kgeb_kvsall_build_workspace_bytes(int64_t B, int64_t capacity) {
+  const int64_t n = (B > capacity ? B : capacity) + 1;
+  return (int64_t)(up256((size_t)n * 8) + up256((size_t)n * 4) + up256(build_cub_bytes(n)) + 1024);
+}
+
+int kgeb_kvsall_batch_build(const kgeb_index_t* sp_index, const kgeb_index_t* po_index, const int64_t* example_ids,
+                            int64_t B, int64_t capacity, int64_t num_entities, int64_t num_relations, int64_t* a_idx,
+                            int64_t* p_idx, int32_t* row_combine, int64_t* lab_off, int64_t* lab_col, int32_t* a_perm,
+                            int32_t* p_perm, int32_t* lab_perm, int32_t* overflow, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  KGEB_REQUIRE(sp_index && po_index && example_ids && a_idx && p_idx && row_combine && lab_off && lab_col && a_perm &&
+                   p_perm && lab_perm && overflow && workspace,
+               "kvsall_batch_build: NULL argument");
+  KGEB_REQUIRE(B > 0 && capacity > 0 && B < ((int64_t)1 << 30) && capacity < ((int64_t)1 << 30),
+               "kvsall_batch_build: batch size / label capacity out of range");
+  KGEB_REQUIRE(index_ok(*sp_index) && index_ok(*po_index), "kvsall_batch_build: index has NULL arrays");
+  KGEB_REQUIRE(workspace_bytes >= kgeb_kvsall_build_workspace_bytes(B, capacity), "kvsall_batch_build: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int64_t n = (B > capacity ? B : capacity) + 1;
+  char* wp = reinterpret_cast<char*>(workspace);
+  BuildWs w;
+  w.keys_tmp = reinterpret_cast<int64_t*>(wp);  wp += up256((size_t)n * 8);
+  w.iota = reinterpret_cast<int32_t*>(wp);      wp += up256((size_t)n * 4);
+  w.cub_tmp = wp;
+  w.cub_bytes = build_cub_bytes(n);
+  cudaError_t e;
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.iota, n, lab_off);
+  kvsall_count_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(*sp_index, *po_index, example_ids, B, a_idx, p_idx,
+                                                                  row_combine, lab_off + 1);
+  KGEB_LAUNCH_CHECK("kvsall_count");
+  size_t bytes = w.cub_bytes;
+  e = cub::DeviceScan::InclusiveSum(w.cub_tmp, bytes, lab_off + 1, lab_off + 1, (int)B, st);
+  if (e != cudaSuccess) return cuda_status(e, "kvsall_batch_build scan");
+  e = cudaMemsetAsync(lab_col, 0, (size_t)capacity * 8, st);   // padding counts as entity 0 in lab_perm
+  if (e == cudaSuccess) e = cudaMemsetAsync(overflow, 0, 4, st);
+  if (e != cudaSuccess) return cuda_status(e, "kvsall_batch_build memset");
+  kvsall_fill_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(*sp_index, *po_index, example_ids, B, lab_off, capacity,
+                                                             lab_col, overflow);
+  KGEB_LAUNCH_CHECK("kvsall_fill");
+  // the three stable argsorts (ids of the batch are known here, so the step's scatters need no sort)
+  const int eb = bits_needed(num_entities), rb = bits_needed(num_relations);
+  bytes = w.cub_bytes;
+  e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, (const int64_t*)a_idx, w.keys_tmp, (const int32_t*)w.iota, a_perm,
+                                      (int)B, 0, eb, st);
+  bytes = w.cub_bytes;
+  if (e == cudaSuccess)
+    e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, (const int64_t*)p_idx, w.keys_tmp, (const int32_t*)w.iota, p_perm,
+                                        (int)B, 0, rb, st);
+  bytes = w.cub_bytes;
+  if (e == cudaSuccess)
+    e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, (const int64_t*)lab_col, w.keys_tmp, (const int32_t*)w.iota,
+                                        lab_perm, (int)capacity, 0, eb, st);
+  if (e != cudaSuccess) return cuda_status(e, "kvsall_batch_build sort");
   return KGEB_OK;
 }
 

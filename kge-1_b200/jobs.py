@@ -143,6 +143,84 @@ class TrainingJobKvsAll(TrainingJob):
                                              use_graph, self.shard, dp_group)
         return self.stepper
 
+    # -- on-device batch construction: the host sends example ids only ----------------------------
+    def enable_device_collate(self, sp_index: KvsAllIndex, po_index: KvsAllIndex):
+        """KvsAll batches are built on the device from the device-resident indexes (kgeb_kvsall_batch_*, three stable
+        sorts for the scatter permutations) on a collate stream, double-buffered so that batch i+1 is built while step
+        i runs; step_ids() then costs one 8*B-byte H2D copy and one small D2D copy on top of the graph replay."""
+        st = self.stepper
+        if st is None:
+            raise RuntimeError("enable_graph_step() first")
+        dev = self.device
+        self._dc = {"sp": sp_index, "po": po_index, "stream": torch.cuda.Stream(device=dev), "slot": 0, "pending": [],
+                    "staging": [torch.zeros_like(st.input_bytes) for _ in range(2)],
+                    "ids": [torch.zeros(st.rows, dtype=torch.int64, device=dev) for _ in range(2)],
+                    "overflow": [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(2)],
+                    "built": [torch.cuda.Event() for _ in range(2)], "consumed": [torch.cuda.Event() for _ in range(2)],
+                    "descs": (lib.index_descs([sp_index.device_arrays(dev)]), lib.index_descs([po_index.device_arrays(dev)])),
+                    "ws": torch.empty(lib.load().kgeb_kvsall_build_workspace_bytes(st.rows, max(st.nnz_max, 1)),
+                                      dtype=torch.uint8, device=dev)}
+        for ev in self._dc["consumed"]:
+            ev.record()
+        # one CUDA graph per staging slot: the build is ~25 small launches (CUB scan / radix sorts), far more host time
+        # than device time when issued one by one
+        dc = self._dc
+        dc["graphs"] = []
+        cs = dc["stream"]
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            for slot in range(2):
+                self._build_batch(slot)          # warm-up outside capture
+        cs.synchronize()
+        for slot in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cs):
+                self._build_batch(slot)
+            dc["graphs"].append(g)
+        torch.cuda.synchronize()
+
+    def _build_batch(self, slot: int):
+        dc, st = self._dc, self.stepper
+        v = st.input_views(dc["staging"][slot])
+        lib.call("kgeb_kvsall_batch_build", dc["descs"][0], dc["descs"][1], dc["ids"][slot].data_ptr(), st.rows,
+                 max(st.nnz_max, 1), self.num_entities, self.num_relations, v["a_idx"].data_ptr(), v["p_idx"].data_ptr(),
+                 v["row_combine"].data_ptr(), v["lab_off"].data_ptr(), v["lab_col"].data_ptr(), v["a_perm"].data_ptr(),
+                 v["p_perm"].data_ptr(), v["lab_perm"].data_ptr(), dc["overflow"][slot].data_ptr(),
+                 dc["ws"].data_ptr(), dc["ws"].numel(), torch.cuda.current_stream().cuda_stream)
+
+    def prefetch_ids(self, example_ids: torch.Tensor):
+        """Enqueues the construction of the batch with these example ids (host pinned or device int64 [batch_size])."""
+        dc = self._dc
+        if len(dc["pending"]) >= 2:
+            raise RuntimeError("two batches are already in flight")
+        slot = dc["slot"]
+        dc["slot"] ^= 1
+        cs = dc["stream"]
+        with torch.cuda.stream(cs):
+            cs.wait_event(dc["consumed"][slot])          # the step that used this staging buffer has copied it
+            dc["ids"][slot].copy_(example_ids, non_blocking=True)
+            dc["graphs"][slot].replay()
+            dc["built"][slot].record(cs)
+        dc["pending"].append(slot)
+
+    def step_ids(self, example_ids: Optional[torch.Tensor] = None) -> ProcessBatchResult:
+        """One training step on the oldest prefetched batch (or on `example_ids`, built now)."""
+        dc, st = self._dc, self.stepper
+        if example_ids is not None:
+            self.prefetch_ids(example_ids)
+        slot = dc["pending"].pop(0)
+        for f in self.pre_batch_hooks:
+            f(self)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(dc["built"][slot])
+        st.input_bytes.copy_(dc["staging"][slot], non_blocking=True)
+        dc["consumed"][slot].record(cur)
+        loss = st.step()
+        value, overflow = torch.stack((loss, dc["overflow"][slot][0].float())).tolist()   # one D2H read, as train.py:747
+        if overflow:
+            raise ValueError(f"batch has more than {st.nnz_max} labels (enable_graph_step(nnz_max=...))")
+        return ProcessBatchResult(value, st.rows, value)
+
     def device_inputs(self, batch):
         """Host (pinned) KvsAll batch -> device tensors (a_idx, p_idx, row_combine, lab_off, lab_col, perms)."""
         from .trainer import kvsall_rows

@@ -54,6 +54,7 @@ SIGNATURES = {
     "kgeb_filter_csr_fill": [_p, _p, _i, _l, _p, _p, _p, _p, _p],
     "kgeb_kvsall_batch_count": [_p, _p, _p, _l, _p, _p, _p, _p, _p],
     "kgeb_kvsall_batch_fill": [_p, _p, _p, _l, _p, _l, _p, _p, _p],
+    "kgeb_kvsall_batch_build": [_p, _p, _p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p],
 }
 
 
@@ -71,7 +72,8 @@ def index_descs(arrays) -> "ctypes.Array":
                 raise ValueError("index arrays must be contiguous int64 CUDA tensors")
         d.keys, d.num_keys, d.offsets, d.values = keys.data_ptr(), keys.shape[0], offsets.data_ptr(), values.data_ptr()
     return out
-_INT64_RESULT = {"kgeb_fused_workspace_bytes": [_l, _i, _l, _l], "kgeb_scatter_workspace_bytes": [_l, _i]}
+_INT64_RESULT = {"kgeb_fused_workspace_bytes": [_l, _i, _l, _l], "kgeb_scatter_workspace_bytes": [_l, _i],
+                 "kgeb_kvsall_build_workspace_bytes": [_l, _l]}
 
 _lib: Optional[ctypes.CDLL] = None
 

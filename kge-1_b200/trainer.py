@@ -48,12 +48,10 @@ class FusedAllEntityStepper:
         nz = max(nnz_max, 1)
         self.n_i64 = 3 * rows + 1 + nz
         self.input_bytes = torch.zeros(self.n_i64 * 8 + (3 * rows + nz) * 4, dtype=torch.uint8, device=dev)
-        v64 = self.input_bytes[: self.n_i64 * 8].view(torch.int64)
-        self.a_idx, self.p_idx = v64[:rows], v64[rows:2 * rows]
-        self.lab_off, self.lab_col = v64[2 * rows:3 * rows + 1], v64[3 * rows + 1:]
-        v32 = self.input_bytes[self.n_i64 * 8:].view(torch.int32)
-        self.row_combine, self.a_perm, self.p_perm = v32[:rows], v32[rows:2 * rows], v32[2 * rows:3 * rows]
-        self.lab_perm = v32[3 * rows:]
+        iv = self.input_views(self.input_bytes)
+        self.a_idx, self.p_idx, self.lab_off, self.lab_col = iv["a_idx"], iv["p_idx"], iv["lab_off"], iv["lab_col"]
+        self.row_combine, self.a_perm, self.p_perm, self.lab_perm = (iv["row_combine"], iv["a_perm"], iv["p_perm"],
+                                                                     iv["lab_perm"])
         # static intermediates / outputs
         self.Q = torch.empty(rows, self.d, **f32)
         self.dQ = torch.empty(rows, self.d, **f32)
@@ -97,6 +95,15 @@ class FusedAllEntityStepper:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         if use_graph:
             self._capture()
+
+    def input_views(self, buf: torch.Tensor) -> dict:
+        """Typed views into a byte buffer with the layout of the static inputs (see __init__)."""
+        rows, nz = self.rows, max(self.nnz_max, 1)
+        v64 = buf[: self.n_i64 * 8].view(torch.int64)
+        v32 = buf[self.n_i64 * 8:].view(torch.int32)
+        return {"a_idx": v64[:rows], "p_idx": v64[rows:2 * rows], "lab_off": v64[2 * rows:3 * rows + 1],
+                "lab_col": v64[3 * rows + 1:], "row_combine": v32[:rows], "a_perm": v32[rows:2 * rows],
+                "p_perm": v32[2 * rows:3 * rows], "lab_perm": v32[3 * rows:3 * rows + nz]}
 
     # -- one step on the current stream, in three stages separated by the (optional) collectives ----------------
     def _fused_stats_in_backward(self) -> bool:

@@ -372,6 +372,44 @@ def test_device_kvsall_batch_matches_reference_collate(kb):
     assert ovf.item() == 1 and torch.equal(out[3].cpu(), w_off)
 
 
+def test_device_collated_steps_equal_host_collated_steps(kb):
+    """TrainingJobKvsAll.step_ids (batches built on the device from example ids, double-buffered) is bit-identical
+    to step() on the host-collated batches of the same ids."""
+    g = kb.graph.synthetic_graph("toy", seed=3)
+    e, r, d, b = g["num_entities"], g["num_relations"], 32, 64
+    oidx = [ko.kvsall_index(g["train"], "sp"), ko.kvsall_index(g["train"], "po")]
+    sp, po = kb.index.KvsAllIndex(g["train"], "sp"), kb.index.KvsAllIndex(g["train"], "po")
+    rng = np.random.default_rng(9)
+    ids = [rng.choice(len(oidx[0][0]) + len(oidx[1][0]), b, replace=False) for _ in range(4)]
+    host = []
+    for x in ids:
+        q, c, qt = ko.kvsall_collate(x.tolist(), oidx)
+        host.append({"queries": T(q), "label_coords": T(c), "query_type_indexes": T(qt)})
+    nnz_max = max(len(x["label_coords"]) for x in host) + 3
+    res = []
+    for device_collate in (False, True):
+        torch.manual_seed(0)
+        m = kb.KgeModel("complex", e, r, d).cuda()
+        job = kb.TrainingJobKvsAll(m, kb.optim.create("Adagrad", m.parameters(), lr=0.2), kb.KgeLoss.create("bce"), e, r,
+                                   math_mode=kb.lib.MATH_BF16)
+        job.enable_graph_step(b, nnz_max)
+        losses = []
+        if device_collate:
+            job.enable_device_collate(sp, po)
+            pinned = [torch.from_numpy(x.astype(np.int64)).pin_memory() for x in ids]
+            job.prefetch_ids(pinned[0])
+            for i in range(len(ids)):
+                if i + 1 < len(ids):
+                    job.prefetch_ids(pinned[i + 1])
+                losses.append(job.step_ids().avg_loss)
+        else:
+            for i, batch in enumerate(host):
+                losses.append(job.step(i, job.collate_packed(batch)).avg_loss)
+        res.append((losses, m.get_s_embedder().weight.detach().clone(), m.get_p_embedder().weight.detach().clone()))
+    assert res[0][0] == res[1][0]
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
 def test_kvsall_index_device_lookup_bit_exact(kb, golden):
     g = golden("index")
     tr = g["index.train.triples"]
