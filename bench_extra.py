@@ -68,7 +68,13 @@ def wd5m_1vsall(args):
     model = kb.KgeModel("distmult", E, R, d).to(dev)
     opt = kb.optim.create("Adagrad", model.parameters(), lr=0.2)
     math_mode = {"bf16": kb.lib.MATH_BF16, "tf32": kb.lib.MATH_TF32, "fp32": kb.lib.MATH_FP32}[args.math]
-    st = kb.trainer.FusedAllEntityStepper(model, opt, 2 * B, 2 * B, kb.lib.LOSS_KL, B, math_mode=math_mode, use_graph=True)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:   # entity table sharded by row over the ranks; every rank sees the whole batch
+        import torch.distributed as dist
+        sh = kb.fused.Shard.of_rank(E, int(os.environ["RANK"]), world, dist.group.WORLD)
+        st = kb.trainer.RowShardedAllEntityStepper(model, opt, 2 * B, 2 * B, kb.lib.LOSS_KL, B, sh, math_mode=math_mode)
+    else:
+        st = kb.trainer.FusedAllEntityStepper(model, opt, 2 * B, 2 * B, kb.lib.LOSS_KL, B, math_mode=math_mode, use_graph=True)
     gen = torch.Generator(device=dev).manual_seed(1)
 
     def new_batch():
@@ -91,8 +97,9 @@ def wd5m_1vsall(args):
     # bytes this implementation moves per step: 3 bf16 table reads (fwd, dQ, dTable), gradient zero + RMW,
     # Adagrad read W/state/grad + write W/state/mirror
     bytes_step = E * d * (3 * 2 + 4 + 8 + 12 + 10)
-    return {"workload": f"DistMult 1vsAll+KL d=128 E={E} B={B} triples ({2 * B} query rows) {args.math}",
-            "metric": "training triples/s", "value": B / (ms * 1e-3), "ms_per_step": ms,
+    return {"workload": f"DistMult 1vsAll+KL d=128 E={E} B={B} triples ({2 * B} query rows) {args.math}"
+                        + (f", entity table row-sharded over {world} GPUs (same batch on every rank)" if world > 1 else ""),
+            "metric": "training triples/s", "value": B / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world,
             "loss": st.loss.item(),
             "roofline": {"tensor_tflops": flops / (ms * 1e-3) / 1e12, "tensor_frac_of_bf16_sustained": flops / (ms * 1e-3) / 1e12 / tf,
                          "hbm_gbs": bytes_step / (ms * 1e-3) / 1e9, "hbm_frac": bytes_step / (ms * 1e-3) / 1e9 / hbm,
@@ -143,7 +150,13 @@ def wd5m_eval(args, model_name):
     model = kb.KgeModel(model_name, E, R, d, math_mode=math_mode).to(dev)
     rng = np.random.default_rng(0)
     known = np.stack([rng.integers(0, E, 20000), rng.integers(0, R, 20000), rng.integers(0, E, 20000)], 1).astype(np.int32)
-    job = kb.EntityRankingJob(model, E, [known], None, batch_size=B, math_mode=math_mode, hits_at_k_s=(1, 3, 10))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    shard = None
+    if world > 1:   # every rank scores the whole batch against its own entity rows; int64 counts are all-reduced
+        import torch.distributed as dist
+        shard = kb.fused.Shard.of_rank(E, int(os.environ["RANK"]), world, dist.group.WORLD)
+    job = kb.EntityRankingJob(model, E, [known], None, batch_size=B, math_mode=math_mode, hits_at_k_s=(1, 3, 10),
+                              shard=shard)
     batch = torch.from_numpy(known[:B].copy())
 
     def step():
@@ -155,8 +168,9 @@ def wd5m_eval(args, model_name):
     hbm, tf = peaks()
     ops = 2.0 * (2 * B) * E * d
     return {"workload": f"filtered ranking {model_name} d=128 E={E} B={B} triples ({2 * B} queries) "
-                        f"{'tf32 tcgen05 tiles' if math_mode == kb.lib.MATH_TF32 else 'fp32 CUDA-core tiles'}",
-            "metric": "eval queries/s", "value": 2 * B / (ms * 1e-3), "ms_per_batch": ms,
+                        f"{'tf32 tcgen05 tiles' if math_mode == kb.lib.MATH_TF32 else 'fp32 CUDA-core tiles'}"
+                        + (f", scoring sharded by entity over {world} GPUs" if world > 1 else ""),
+            "metric": "eval queries/s", "value": 2 * B / (ms * 1e-3), "ms_per_batch": ms, "n_gpus": world,
             "roofline": {"ops_per_s_T": ops / (ms * 1e-3) / 1e12,
                          "frac_of_fp32_alu_nominal_37T": ops / (ms * 1e-3) / 1e12 / 37.2 if math_mode == kb.lib.MATH_FP32 else None,
                          "frac_of_bf16_sustained": ops / (ms * 1e-3) / 1e12 / tf if math_mode != kb.lib.MATH_FP32 else None,
@@ -175,6 +189,10 @@ def main():
     ap.add_argument("--graph-step", action="store_true")
     ap.add_argument("--kernels", action="store_true", help="also write a per-kernel time table (CUPTI) to gpurun_out/")
     args = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
     if args.workload == "wd5m-1vsall":
         res = wd5m_1vsall(args)
     elif args.workload == "wnrr-rotate-ns":
@@ -185,7 +203,9 @@ def main():
         res = wd5m_eval(args, "complex")
     else:
         raise SystemExit(f"unknown workload {args.workload}")
-    res["n_gpus"] = 1
+    res.setdefault("n_gpus", 1)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
     line = json.dumps(res)
     print(line)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

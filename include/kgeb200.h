@@ -51,6 +51,12 @@ int kgeb_version(char* buf, int buflen);
 int kgeb_gather_rows(const float* W, int64_t vocab, int dim, const void* idx, int idx64, int64_t n,
                      float* out, void* stream);
 
+/* Entity-sharded tables: W_shard holds the rows [e_lo, e_hi) of the global table.  out[i,:] = the row of
+ * idx[i] if this shard owns it, zeros otherwise (an all-reduce over the shards assembles the rows); local_ids[i]
+ * (optional) = idx[i] - e_lo, or e_hi - e_lo ("not mine": the dummy row a sharded scatter adds such gradients to). */
+int kgeb_gather_rows_shard(const float* W_shard, int64_t e_lo, int64_t e_hi, int dim, const void* idx, int idx64,
+                           int64_t n, float* out, int64_t* local_ids, void* stream);
+
 /* ---- a4/K5: score_emb(..., "spo") for the seven scorers, fused with the three gathers.
  * x_src point at [vocab,d] tables (with x_idx) or at [n,d] embedding matrices (x_idx NULL).
  * p rows have relation_dim(model,d) columns (d, d/2 for CP/RotatE, d*d for RESCAL).

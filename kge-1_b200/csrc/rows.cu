@@ -43,6 +43,22 @@ __global__ void gather_rows_v4(const float4* __restrict__ W, int64_t vocab, int 
     out[t] = __ldg(&W[src * dim4 + c]);
   }
 }
+// rows of an entity-sharded table: W holds the rows [e_lo, e_hi) of the global table; ids outside give zero rows (the
+// owners' partial results are summed by an all-reduce).  local_ids (optional) = id - e_lo, or e_hi - e_lo for "not mine".
+__global__ void gather_rows_shard_kernel(const float* __restrict__ W, int64_t e_lo, int64_t e_hi, int dim,
+                                         const void* idx, int idx64, int64_t n, float* __restrict__ out,
+                                         int64_t* __restrict__ local_ids) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t total = n * dim;
+  for (; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / dim;
+    const int c = (int)(t - r * dim);
+    const int64_t e = load_index(idx, idx64, r);
+    const bool mine = e >= e_lo && e < e_hi;
+    out[t] = mine ? __ldg(&W[(e - e_lo) * dim + c]) : 0.f;
+    if (c == 0 && local_ids) local_ids[r] = mine ? e - e_lo : e_hi - e_lo;
+  }
+}
 __global__ void gather_rows_v1(const float* __restrict__ W, int64_t vocab, int dim, const void* idx,
                                int idx64, int64_t n, float* __restrict__ out) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -683,6 +699,17 @@ int kgeb_gather_rows(const float* W, int64_t vocab, int dim, const void* idx, in
   else
     gather_rows_v1<<<grid, threads, 0, st>>>(W, vocab, dim, idx, idx64, n, out);
   KGEB_LAUNCH_CHECK("gather_rows");
+  return KGEB_OK;
+}
+
+int kgeb_gather_rows_shard(const float* W_shard, int64_t e_lo, int64_t e_hi, int dim, const void* idx, int idx64,
+                           int64_t n, float* out, int64_t* local_ids, void* stream) {
+  KGEB_REQUIRE(W_shard && idx && out && dim > 0 && n >= 0 && e_lo >= 0 && e_hi >= e_lo, "gather_rows_shard: bad arguments");
+  if (n == 0) return KGEB_OK;
+  const int64_t blocks = (n * dim + 255) / 256, cap = (int64_t)kNumSMs * 32;
+  gather_rows_shard_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(W_shard, e_lo, e_hi, dim, idx,
+                                                                                             idx64, n, out, local_ids);
+  KGEB_LAUNCH_CHECK("gather_rows_shard");
   return KGEB_OK;
 }
 

@@ -28,6 +28,7 @@ _p, _i, _l, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
 # name -> argtypes, exactly the declarations of include/kgeb200.h (checked by tests/test_abi.py)
 SIGNATURES = {
     "kgeb_gather_rows": [_p, _l, _i, _p, _i, _l, _p, _p],
+    "kgeb_gather_rows_shard": [_p, _l, _l, _i, _p, _i, _l, _p, _p, _p],
     "kgeb_score_spo": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _l, _i, _p, _p],
     "kgeb_score_spo_bwd": [_i, _i, _p, _p, _p, _p, _p, _p, _i, _l, _i, _p, _p, _p, _p, _p],
     "kgeb_query_build": [_i, _i, _p, _p, _p, _p, _p, _i, _l, _i, _p, _p],

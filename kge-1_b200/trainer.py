@@ -362,6 +362,234 @@ class FusedAllEntityStepper:
         return self.loss
 
 
+class RowShardedAllEntityStepper:
+    """All-entity training step (1vsAll / KvsAll, DOT scorers) with the entity table sharded BY ROW over the ranks of
+    `shard.group` (first row): rank g owns the rows [e_lo, e_hi) -- parameters, Adagrad state, bf16
+    mirror and gradient -- and every rank sees the whole batch.  Per step the ranks exchange only
+
+        all-reduce  [rows, d]   query-side entity rows (owners contribute theirs, zeros elsewhere)
+        all-reduce  [rows, 4]   row statistics (max + rescaled sums for KL; plain sums for BCE)
+        all-reduce  [rows, d]   partial dQ of the shards
+
+    i.e. O(batch * d) bytes, independent of the table size; the dense table gradient, the label scatter and the Adagrad
+    update stay local to the owner, the (small) relation table is replicated and updated identically everywhere.
+    The model object keeps its full-size table: rows outside the shard go stale during training and are refreshed by
+    sync_tables() (broadcast of every owner's rows) before evaluation or checkpointing.  The compute stages between
+    the collectives are CUDA graphs; the collectives are plain NCCL calls."""
+
+    def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
+                 shard: fused.Shard, offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
+                 use_graph: bool = True):
+        if model.get_scorer().kind != lib.DOT:
+            raise NotImplementedError("the fused all-entity step serves the DOT scorers")
+        if not shard.distributed:
+            raise ValueError("RowShardedAllEntityStepper needs a distributed Shard (fused.Shard.of_rank)")
+        self.model, self.opt, self.shard = model, optimizer, shard
+        self.rows, self.nnz_max, self.loss_kind, self.batch_size = rows, nnz_max, loss_kind, batch_size
+        self.offset, self.ls, self.math = float(offset), float(label_smoothing), math_mode
+        self.ent = model.get_s_embedder().weight
+        self.rel = model.get_p_embedder().weight
+        dev = self.ent.device
+        self.E, self.d = self.ent.shape
+        self.dr = self.rel.shape[1]
+        group = optimizer.param_groups[0]
+        if group.get("lr_decay", 0.0) != 0.0 or group.get("weight_decay", 0.0) != 0.0:
+            raise NotImplementedError("the graph-captured step bakes lr into the launch (lr_decay / weight_decay = 0)")
+        self.lr, self.eps = float(group["lr"]), float(group["eps"])
+        self.e_lo, self.e_hi = shard.e_lo, shard.e_hi
+        self.n_loc = self.e_hi - self.e_lo
+        f32 = dict(dtype=torch.float32, device=dev)
+        i64 = dict(dtype=torch.int64, device=dev)
+        nz = max(nnz_max, 1)
+        self.a_idx, self.p_idx = torch.zeros(rows, **i64), torch.zeros(rows, **i64)
+        self.row_combine = torch.zeros(rows, dtype=torch.int32, device=dev)
+        self.lab_off, self.lab_col = torch.zeros(rows + 1, **i64), torch.zeros(nz, **i64)
+        self.iota = torch.arange(rows, **i64)
+        self.loc_ids = torch.zeros(rows, **i64)
+        self.A = torch.zeros(rows, self.d, **f32)          # query-side entity rows, assembled by all-reduce
+        self.Q, self.dQ = torch.empty(rows, self.d, **f32), torch.empty(rows, self.d, **f32)
+        self.da, self.dp = torch.empty(rows, self.d, **f32), torch.empty(rows, self.dr, **f32)
+        self.g_ent = torch.zeros(max(self.n_loc, 1), self.d, **f32)       # dense part + label rows, local rows only
+        self.g_q = torch.zeros(self.n_loc + 1, self.d, **f32)             # query-side rows; last row = "not mine"
+        self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
+        self.loss = torch.zeros((), **f32)
+        self.rowstat = torch.empty(rows, 4, **f32)
+        self.lse = torch.zeros(rows, **f32)
+        L = lib.load()
+        self.ws = torch.empty(L.kgeb_fused_workspace_bytes(rows, self.d, max(self.n_loc, 1), nz), dtype=torch.uint8, device=dev)
+        self.ws2 = torch.empty_like(self.ws)
+        self.sws = torch.empty(L.kgeb_scatter_workspace_bytes(rows, max(self.d, self.dr)), dtype=torch.uint8, device=dev)
+        self.sws2 = torch.empty_like(self.sws)
+        self.side = torch.cuda.Stream(device=dev)
+        self.mirror = None
+        if math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256:
+            self.mirror = torch.empty(max(self.n_loc, 1), self.d, dtype=torch.bfloat16, device=dev)
+            self._refresh_mirror()
+        self.graphs = None
+        if use_graph:
+            self._capture()
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def _ent_loc(self):
+        return self.ent.detach()[self.e_lo:self.e_hi]
+
+    def _refresh_mirror(self):
+        if self.mirror is not None and self.n_loc > 0:
+            lib.call("kgeb_to_bf16", self._ent_loc().data_ptr(), self.mirror.data_ptr(), self.n_loc * self.d,
+                     lib.stream_ptr(self.ent))
+
+    def _late_stats(self) -> bool:
+        return self.loss_kind == lib.LOSS_BCE and self.mirror is not None
+
+    def _loss_kernel(self):
+        lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
+                 self.ls, self.E, 1.0 / self.batch_size, None, self.lse.data_ptr(), self.loss.data_ptr(),
+                 lib.stream_ptr(self.ent))
+
+    # -- compute stages (each one CUDA graph) and the collectives between them ----------------------------------
+    def _stage_gather(self):
+        st = lib.stream_ptr(self.ent)
+        self.g_ent.zero_(); self.g_q.zero_(); self.g_rel.zero_()
+        lib.call("kgeb_gather_rows_shard", self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.d, self.a_idx.data_ptr(),
+                 1, self.rows, self.A.data_ptr(), self.loc_ids.data_ptr(), st)
+
+    def _stage_forward(self):
+        st = lib.stream_ptr(self.ent)
+        model_id = lib.MODELS[self.model.model]
+        rel = self.rel.detach()
+        lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), self.A.data_ptr(), self.iota.data_ptr(),
+                 rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
+        if not self._late_stats():
+            lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
+                     self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.E, self.lab_off.data_ptr(),
+                     self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
+                     None if self.mirror is None else self.mirror.data_ptr(), self.rowstat.data_ptr(),
+                     self.ws.data_ptr(), self.ws.numel(), st)
+
+    def _stage_backward(self):
+        st = lib.stream_ptr(self.ent)
+        late = self._late_stats()
+        if not late:
+            self._loss_kernel()          # KL needs the global log-sum-exp before the backward
+        lse = self.lse.data_ptr() if self.loss_kind == lib.LOSS_KL else None
+        common = (self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d, self._ent_loc().data_ptr(), self.e_lo,
+                  self.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, None, self.ls,
+                  self.offset, lse, 1.0 / self.batch_size, None, None if self.mirror is None else self.mirror.data_ptr())
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            lib.call("kgeb_fused_bwd", *common, None, self.g_ent.data_ptr(), None, self.ws2.data_ptr(), self.ws2.numel(),
+                     lib.stream_ptr(self.ent))
+        lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late else None,
+                 self.ws.data_ptr(), self.ws.numel(), st)
+        cur.wait_stream(self.side)
+
+    def _stage_update(self):
+        st = lib.stream_ptr(self.ent)
+        model_id = lib.MODELS[self.model.model]
+        rel = self.rel.detach()
+        if self._late_stats():
+            self._loss_kernel()
+        lib.call("kgeb_query_bwd", model_id, 0, self.row_combine.data_ptr(), self.A.data_ptr(), self.iota.data_ptr(),
+                 rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.dQ.data_ptr(), self.da.data_ptr(),
+                 self.dp.data_ptr(), st)
+        lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
+                 self.g_rel.data_ptr(), self.rel.shape[0], self.sws2.data_ptr(), self.sws2.numel(), st)
+        lib.call("kgeb_adagrad_dense", rel.data_ptr(), self.opt.state[self.rel]["sum"].data_ptr(), self.g_rel.data_ptr(),
+                 None, rel.numel(), self.lr, self.eps, 0.0, None, st)
+        # query-side rows: every rank has the same da (dQ was all-reduced); each adds the rows it owns, the others go
+        # to the dummy row n_loc
+        lib.call("kgeb_scatter_add_rows", self.loc_ids.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
+                 self.g_q.data_ptr(), self.n_loc + 1, self.sws.data_ptr(), self.sws.numel(), st)
+        if self.n_loc > 0:
+            s_loc = self.opt.state[self.ent]["sum"][self.e_lo:self.e_hi]
+            lib.call("kgeb_adagrad_dense", self._ent_loc().data_ptr(), s_loc.data_ptr(), self.g_ent.data_ptr(),
+                     self.g_q.data_ptr(), self.n_loc * self.d, self.lr, self.eps, 0.0,
+                     None if self.mirror is None else self.mirror.data_ptr(), st)
+
+    def _exchange(self, which: int):
+        import torch.distributed as dist
+        grp = self.shard.group
+        if which == 0:
+            dist.all_reduce(self.A, group=grp)
+        elif which == 1:
+            if not self._late_stats():
+                self.rowstat.copy_(fused.combine_rowstats(self.rowstat, self.loss_kind, self.shard))
+        else:
+            dist.all_reduce(self.dQ, group=grp)
+            if self._late_stats():
+                self.rowstat.copy_(fused.combine_rowstats(self.rowstat, self.loss_kind, self.shard))
+
+    def _stages(self):
+        return [self._stage_gather, self._stage_forward, self._stage_backward, self._stage_update]
+
+    def _launch(self):
+        for i, fn in enumerate(self._stages()):
+            fn()
+            if i < 3:
+                self._exchange(i)
+
+    def _capture(self):
+        keep = [t.detach().clone() for t in (self.ent, self.rel, self.opt.state[self.ent]["sum"],
+                                             self.opt.state[self.rel]["sum"])]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._launch()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graphs = []
+        for fn in self._stages():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self.graphs.append(g)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for dst, src in zip((self.ent, self.rel, self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]), keep):
+                dst.copy_(src)
+        self._refresh_mirror()
+        torch.cuda.synchronize()
+
+    # -- public -------------------------------------------------------------------------------------
+    def set_inputs(self, a_idx, p_idx, row_combine, lab_off, lab_col, perms=None):
+        if lab_col.numel() > self.nnz_max:
+            raise ValueError(f"batch has {lab_col.numel()} labels, stepper was built for at most {self.nnz_max}")
+        self.a_idx.copy_(a_idx, non_blocking=True)
+        self.p_idx.copy_(p_idx, non_blocking=True)
+        self.row_combine.copy_(row_combine, non_blocking=True)
+        self.lab_off.copy_(lab_off, non_blocking=True)
+        self.lab_col[: lab_col.numel()].copy_(lab_col, non_blocking=True)
+
+    def step(self) -> torch.Tensor:
+        if self.graphs is None:
+            self._launch()
+        else:
+            for i, g in enumerate(self.graphs):
+                g.replay()
+                if i < 3:
+                    self._exchange(i)
+        for st in (self.opt.state[self.ent], self.opt.state[self.rel]):
+            st["step"] += 1
+        torch.autograd.graph.increment_version(self.ent)
+        torch.autograd.graph.increment_version(self.rel)
+        return self.loss
+
+    def sync_tables(self):
+        """Every owner broadcasts its rows of the entity table and of the Adagrad state: afterwards all ranks hold the
+        complete, current table (evaluation, checkpoints)."""
+        import torch.distributed as dist
+        world = dist.get_world_size(self.shard.group)
+        ranks = dist.get_process_group_ranks(self.shard.group)
+        with torch.no_grad():
+            for r in range(world):
+                sh = fused.Shard.of_rank(self.E, r, world, self.shard.group)
+                if sh.e_hi > sh.e_lo:
+                    dist.broadcast(self.ent.data[sh.e_lo:sh.e_hi], src=ranks[r], group=self.shard.group)
+                    dist.broadcast(self.opt.state[self.ent]["sum"][sh.e_lo:sh.e_hi], src=ranks[r], group=self.shard.group)
+        torch.autograd.graph.increment_version(self.ent)
+
+
 def kvsall_rows(queries: torch.Tensor, query_type: torch.Tensor):
     """KvsAll batch -> (a_idx, p_idx, row_combine): sp_ rows use (s,p) = (q0,q1); _po rows (p,o) = (q0,q1)."""
     qt = query_type.to(torch.int32)

@@ -82,6 +82,45 @@ def main():
         if rank == 0:
             print("data-parallel step (one flat all-reduce) == single-GPU step on the global batch; loss", c.avg_loss)
 
+    # row-sharded tables: each rank owns (and updates) its rows only; per step three all-reduces of O(batch * d)
+    for loss_name, loss_kind, math_mode, use_graph in (("bce", kb.lib.LOSS_BCE, kb.lib.MATH_BF16, True),
+                                                       ("kl", kb.lib.LOSS_KL, kb.lib.MATH_BF16, True),
+                                                       ("kl", kb.lib.LOSS_KL, kb.lib.MATH_FP32, False)):
+        torch.manual_seed(0)
+        ref = kb.KgeModel("complex", e, r, d).to(dev)
+        new = kb.KgeModel("complex", e, r, d).to(dev)
+        new.load_state_dict(ref.state_dict())
+        jr = kb.TrainingJobKvsAll(ref, kb.optim.create("Adagrad", ref.parameters(), lr=0.2), kb.KgeLoss.create(loss_name),
+                                  e, r, math_mode=math_mode)
+        jr.enable_graph_step(b, nnz_max, use_graph=False)
+        sh = kb.fused.Shard.of_rank(e, rank, world, dist.group.WORLD)
+        opt_new = kb.optim.create("Adagrad", new.parameters(), lr=0.2)
+        st = kb.trainer.RowShardedAllEntityStepper(new, opt_new, b, nnz_max, loss_kind, b, sh, math_mode=math_mode,
+                                                   use_graph=use_graph)
+        # KL on the bf16 tiles: one step only -- a flipped sign (see below) moves a weight by 2 * lr, after which the
+        # two runs are different trajectories
+        for i, batch in enumerate(batches[:1] if (loss_name == "kl" and math_mode == kb.lib.MATH_BF16) else batches):
+            st.set_inputs(*jr.device_inputs(batch)[:5])
+            loss = st.step().item()
+            a = jr.step(i, batch)
+            # bf16 tiles: after the first update the tables differ by rounding (different partial-sum grouping)
+            ltol = 1e-3 if math_mode == kb.lib.MATH_BF16 else 1e-4
+            assert abs(a.avg_loss - loss) <= ltol * abs(a.avg_loss), (loss_name, math_mode, i, a.avg_loss, loss)
+        st.sync_tables()
+        for x, y in ((ref.get_s_embedder().weight, new.get_s_embedder().weight),
+                     (ref.get_p_embedder().weight, new.get_p_embedder().weight),
+                     (jr.optimizer.state[ref.get_s_embedder().weight]["sum"], opt_new.state[new.get_s_embedder().weight]["sum"])):
+            diff = (x - y).abs()
+            if loss_name == "bce":
+                assert diff.max().item() <= 5e-3, (loss_name, math_mode, diff.max().item())
+            else:
+                # softmax gradients of far-away entities are ~1e-9 and Adagrad's first steps move every touched weight
+                # by ~lr * sign(g): rounding-level differences flip a few signs, so compare all but a 0.5 % tail
+                frac = (diff > 5e-3).float().mean().item()
+                assert frac <= 5e-3, (loss_name, math_mode, frac, diff.max().item())
+        if rank == 0:
+            print(f"row-sharded step == single-GPU step ({loss_name}, math={math_mode}, graph={use_graph})")
+
     # sharded filtered ranking: integer counts are exact under sharding
     torch.manual_seed(0)
     m = kb.KgeModel("transe", e, r, d).to(dev)
