@@ -59,11 +59,13 @@ class FusedAllEntityStepper:
         self.dp = torch.empty(rows, self.dr, **f32)
         # gradients and the loss live in ONE flat buffer so that data-parallel replicas need a single all-reduce
         n_e, n_r = self.E * self.d, self.rel.shape[0] * self.dr
+        # layout [g_q | g_ent | g_rel | loss]: data-parallel replicas fold g_q into g_ent and all-reduce the tail only
         self.gflat = torch.zeros(2 * n_e + n_r + 1, **f32)
-        self.g_ent = self.gflat[:n_e].view(self.E, self.d)            # dense part (G^T Q) + label rows (side stream)
-        self.g_q = self.gflat[n_e:2 * n_e].view(self.E, self.d)       # query-side rows (da scattered by entity id)
+        self.g_q = self.gflat[:n_e].view(self.E, self.d)              # query-side rows (da scattered by entity id)
+        self.g_ent = self.gflat[n_e:2 * n_e].view(self.E, self.d)     # dense part (G^T Q) + label rows (side stream)
         self.g_rel = self.gflat[2 * n_e:2 * n_e + n_r].view(self.rel.shape[0], self.dr)
         self.loss = self.gflat[2 * n_e + n_r:].view(())
+        self.dp_flat = self.gflat[n_e:]                               # what the replicas exchange
         self.rowstat = torch.empty(rows, 4, **f32)
         # Data parallelism for graphs too small to shard (SURVEY.md 8e "replicas" row): every rank trains on its own
         # batch against its full replica; one all-reduce sums gradients and loss; loss terms are divided by the global
@@ -194,6 +196,7 @@ class FusedAllEntityStepper:
         if self.dp_world > 1:
             cur.wait_stream(self.side2)      # gradients complete on this stream before the all-reduce
             self._join_side()
+            self.g_ent.add_(self.g_q)        # one table-sized buffer on the wire instead of two
             return
         if not self.shard.distributed:
             self._join_side()     # dense table gradient from the side stream
@@ -209,12 +212,12 @@ class FusedAllEntityStepper:
         s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
         lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
                  self.lr, self.eps, 0.0, None, st)
-        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
+        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), None,
                  ent.numel(), self.lr, self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st)
 
     def _exchange_dp(self):
         import torch.distributed as dist
-        dist.all_reduce(self.gflat, group=self.dp_group)   # gradients of both tables and the loss in one collective
+        dist.all_reduce(self.dp_flat, group=self.dp_group)   # gradients of both tables and the loss in one collective
 
     def _mirror_ptr(self):
         return None if self.mirror is None else self.mirror[self.shard.e_lo:self.shard.e_hi].data_ptr()
