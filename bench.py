@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--math", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--cpu-steps", type=int, default=8, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="tuning runs: device-resident value + kernel roofline only")
     ap.add_argument("--parallel", default="dp", choices=["dp", "shard"],
                     help="N>1: dp = data-parallel replicas + one gradient all-reduce (graphs too small to shard); "
                          "shard = entity-sharded scoring (SURVEY.md 8e)")
@@ -257,7 +258,7 @@ def main():
     # ---------------- e2e: public API, pinned host batches, H2D + loss D2H inside the timed region -------
     e2e_s = 0.0
     packed = [job.collate_packed(b) for b in batches]   # host collate output (pinned), as a DataLoader worker emits it
-    for i in range(args.warmup + args.steps):
+    for i in range(0 if args.skip_e2e else args.warmup + args.steps):
         b = packed[i]
         flush.fill_(i & 0xFF)
         torch.cuda.synchronize()
@@ -271,14 +272,14 @@ def main():
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
-    e2e_value = world * B * args.steps / e2e_s
+    e2e_value = None if args.skip_e2e else world * B * args.steps / e2e_s
     h2d = int(packed[0]["packed"].numel())
 
     # ---------------- e2e with on-device batch construction: the host sends example ids only ------------------
     #  batch i+1 is built on the collate stream while step i runs; every timed step contains one
     # H2D copy of 8*B bytes of ids, one batch construction, one step and the loss read-back
     e2e_dc = None
-    if world == 1:
+    if world == 1 and not args.skip_e2e:
         job.enable_device_collate(*graph["_indexes"])
         ids = [b["example_ids"].pin_memory() for b in batches]
         dc_s = 0.0
@@ -305,7 +306,7 @@ def main():
             dist.destroy_process_group()
         return
     # ---------------- cpu baseline: bounded sample of the same workload on the host cores -----------------
-    cpu = cpu_reference(batches, graph, args.cpu_steps, 1, B)
+    cpu = cpu_reference(batches, graph, args.cpu_steps, 1, B) if args.cpu_steps > 0 else {"value": None, "cores": 0}
     out = {
         "metric": "training queries/s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -266,32 +266,79 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         } else if (LOSS == KGEB_LOSS_KL) {
           col_k = (__logf(my_rs) - my_lse) * kLog2e;   // rows beyond B: log(0) = -inf -> G = 0
         }
+        if (LOSS == KGEB_LOSS_KL) {
 #pragma unroll
-        for (int c = 0; c < COLS_PER_WARP; ++c) {
-          const float x = v[c];
-          if (LOSS == KGEB_LOSS_KL) {
+          for (int c = 0; c < COLS_PER_WARP; ++c) {
             const float kc = RES_IS_Q ? col_k : __shfl_sync(0xffffffffu, col_k, c);
-            const float a = fmaf(x, kLog2e, kc);
+            const float a = fmaf(v[c], kLog2e, kc);
             v[c] = ((c & 7) < KGEB_POLY8_KL) ? ex2_poly<3, false>(a) : ex2_ftz(a);
-          } else {
-            const float rs = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c) : col_rs;
+          }
+        } else {
+          // BCE, two columns per iteration.  MUFU diet (the pipe has 16 lanes/clk/SM, every other pipe 128):
+          //  * KGEB_RCP_PAIR: the two reciprocals of a pair come from ONE rcp of the product (batch inversion:
+          //    1/a0 = a1 / (a0 a1), 1/a1 = a0 / (a0 a1)) -- 1 MUFU + 3 FMUL instead of 2 MUFU;
+          //  * KGEB_LG2_GROUP: sum lg2(a_i) = lg2(prod a_i); a_i in [1, 2], so a product of <= 32 factors stays far
+          //    inside the fp32 range and costs one FMUL per factor instead of one MUFU.
+          float prod = 1.f;
+          const float nls = -p.ls_add;
+#pragma unroll
+          for (int c = 0; c < COLS_PER_WARP; c += 2) {
+            const float rs0 = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c) : col_rs;
+            const float rs1 = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c + 1) : col_rs;
             if (STATS) {
-              // sigmoid and softplus from one exponential (3 MUFU: ex2, rcp, lg2), cancellation-free:
+              // sigmoid and softplus from one exponential, cancellation-free:
               //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
-              const float z = x + p.offset;
-              const float t = fabsf(z) * -kLog2e;
-              const float e = ((c & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t) : ex2_ftz(t);
-              const float a = 1.f + e;
-              const float r = rcp_ftz(a);
-              st_lg += lg2_ftz(a);
-              st_mx += fmaxf(z, 0.f);
-              st_x += z;
-              v[c] = fmaf(z >= 0.f ? r : e * r, rs, -p.ls_add * rs);
+              const float z0 = v[c] + p.offset, z1 = v[c + 1] + p.offset;
+              const float t0 = fabsf(z0) * -kLog2e, t1 = fabsf(z1) * -kLog2e;
+              const float e0 = ((c & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t0) : ex2_ftz(t0);
+              const float e1 = (((c + 1) & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t1) : ex2_ftz(t1);
+              const float a0 = 1.f + e0, a1 = 1.f + e1;
+              float r0, r1;
+              if (KGEB_RCP_PAIR) {
+                const float pr = a0 * a1, ri = rcp_ftz(pr);
+                r0 = ri * a1;
+                r1 = ri * a0;
+                if (KGEB_LG2_GROUP > 1) prod *= pr;
+              } else {
+                r0 = rcp_ftz(a0);
+                r1 = rcp_ftz(a1);
+                if (KGEB_LG2_GROUP > 1) prod *= a0 * a1;
+              }
+              if (KGEB_LG2_GROUP > 1) {
+                if (((c + 2) % KGEB_LG2_GROUP) == 0) {
+                  st_lg += lg2_ftz(prod);
+                  prod = 1.f;
+                }
+              } else {
+                st_lg += lg2_ftz(a0) + lg2_ftz(a1);
+              }
+              st_mx += fmaxf(z0, 0.f) + fmaxf(z1, 0.f);
+              st_x += z0 + z1;
+              v[c] = fmaf(z0 >= 0.f ? r0 : e0 * r0, rs0, nls * rs0);
+              v[c + 1] = fmaf(z1 >= 0.f ? r1 : e1 * r1, rs1, nls * rs1);
             } else {
-              // rs * (sigmoid(x + offset) - ls_add): FFMA, EX2 (inf for very negative z -> rcp gives 0), FADD, RCP, FFMA
-              const float t = fmaf(x, -kLog2e, off2);
-              const float e = ((c & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t) : ex2_ftz(t);
-              v[c] = fmaf(rcp_ftz(1.f + e), rs, -p.ls_add * rs);
+              // rs * (sigmoid(x + offset) - ls_add) = rs / (1 + exp(-(x + offset))) - rs ls_add
+              float t0 = fmaf(v[c], -kLog2e, off2), t1 = fmaf(v[c + 1], -kLog2e, off2);
+              if (KGEB_RCP_PAIR) {
+                // exponent clamp: the product of the pair must stay finite (sigmoid(z < -41.6) reads 8.7e-19, far
+                // below the bf16 resolution of G next to any other entry)
+                t0 = fminf(t0, 60.f);
+                t1 = fminf(t1, 60.f);
+              }
+              const float e0 = ((c & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t0) : ex2_ftz(t0);
+              const float e1 = (((c + 1) & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t1) : ex2_ftz(t1);
+              const float a0 = 1.f + e0, a1 = 1.f + e1;
+              float r0, r1;
+              if (KGEB_RCP_PAIR) {
+                const float ri = rcp_ftz(a0 * a1);
+                r0 = ri * a1;
+                r1 = ri * a0;
+              } else {
+                r0 = rcp_ftz(a0);   // e = inf for very negative z -> rcp gives 0
+                r1 = rcp_ftz(a1);
+              }
+              v[c] = fmaf(r0, rs0, nls * rs0);
+              v[c + 1] = fmaf(r1, rs1, nls * rs1);
             }
           }
         }

@@ -201,6 +201,14 @@ __device__ __forceinline__ float ex2_poly(float x) {
 #ifndef KGEB_POLY8_STATS
 #define KGEB_POLY8_STATS 0
 #endif
+// MUFU diet of the BCE epilogues (tc_bwd.cu, tc_dot.cu): reciprocals of two columns from one rcp of their product;
+// one lg2 per KGEB_LG2_GROUP columns (of the product of the 1 + e^-|z| factors) instead of one per column.
+#ifndef KGEB_RCP_PAIR
+#define KGEB_RCP_PAIR 0
+#endif
+#ifndef KGEB_LG2_GROUP
+#define KGEB_LG2_GROUP 1
+#endif
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];

@@ -280,11 +280,21 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 s2[qb] += a2;
               } else {
                 // softplus(z) = max(z,0) + ln2 * lg2(1 + 2^(-|z| log2e)); padded columns (z = -inf) contribute 0
-                float a_lg = 0.f, a_mx = 0.f;
+                // (KGEB_LG2_GROUP > 1: one lg2 per group of columns, of the product of their 1 + e^-|z| factors in [1, 2])
+                float a_lg = 0.f, a_mx = 0.f, prod = 1.f;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                   const float z = v[c] + p.offset;
-                  a_lg += lg2_ftz(1.f + ex2_ftz(fabsf(z) * -kLog2e));
+                  const float a = 1.f + ex2_ftz(fabsf(z) * -kLog2e);
+                  if (KGEB_LG2_GROUP > 1) {
+                    prod *= a;
+                    if (((c + 1) % KGEB_LG2_GROUP) == 0) {
+                      a_lg += lg2_ftz(prod);
+                      prod = 1.f;
+                    }
+                  } else {
+                    a_lg += lg2_ftz(a);
+                  }
                   a_mx += fmaxf(z, 0.f);
                 }
                 s0[qb] += fmaf(0.69314718f, a_lg, a_mx);
