@@ -244,6 +244,57 @@ int kgeb_kvsall_batch_build(const kgeb_index_t* sp_index, const kgeb_index_t* po
                             int32_t* p_perm, int32_t* lab_perm, int32_t* overflow, void* workspace,
                             int64_t workspace_bytes, void* stream);
 
+/* ---- 8f-2: on-device negative sampling (kge/util/sampler.py).  Philox4x32-10, counter-based: results depend only on
+ * state = {seed, offset} (device memory, so CUDA-graph replays draw fresh numbers; kgeb_philox_advance bumps the offset
+ * on the stream), never on launch shape.  The reference's torch / numpy / `random` streams cannot be reproduced on a
+ * device; oracle/sampler_oracle.py restates THIS generator in numpy and the tests compare bit for bit. */
+int kgeb_philox_words(uint64_t seed, uint64_t offset, uint64_t elem0, int64_t n, uint32_t* out /*[4n]*/, void* stream);
+int kgeb_philox_advance(uint64_t* state, uint64_t inc, void* stream);
+/* KgeUniformSampler._sample (sampler.py:195-198): out[i] uniform in [0, vocab), i < n = batch * num_samples */
+int kgeb_sample_uniform(const uint64_t* state, int64_t vocab, int64_t n, int64_t* out, void* stream);
+/* _filter_and_resample (sampler.py:148-176 / 257-315): row i's samples that occur among the known positives of its key
+ * pair (key_a[i], key_b[i]) in `index` (the "<split>_<pair>_to_<slot>" index) are redrawn until they are true negatives.
+ * *status is set to 1 when a row cannot be satisfied within 65536 redraws (the reference would loop forever). */
+int kgeb_sample_filter(const uint64_t* state, int64_t vocab, const kgeb_index_t* index, const int64_t* key_a,
+                       const int64_t* key_b, int64_t B, int64_t N, int64_t* negatives /*[B,N] in/out*/, int32_t* status,
+                       void* stream);
+/* KgeUniformSampler._sample_shared (sampler.py:200-255): one set of num_distinct+1 distinct samples shared by the batch;
+ * each row drops its own positive if sampled, else a random position; WR upsamples to N columns.
+ * meta[0] = num_distinct, meta[1] = 1 if the draw did not converge. */
+int64_t kgeb_sample_shared_workspace_bytes(int64_t N);
+int kgeb_sample_shared(const uint64_t* state, int64_t vocab, const int64_t* positives /*[B] slot column*/, int64_t B,
+                       int64_t N, int with_replacement, int64_t* out /*[B,N]*/, int32_t* meta /*[2]*/, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/* ---- a22 / 8f-3: Lp penalties of LookupEmbedder (lookup_embedder.py:112-158) with their gradient, deterministic.
+ * dense (unweighted):  value_out[0] = weight/p * sum |W|^p ;  grad += weight * |W|^(p-1) sign(W)  (grad may be NULL)
+ * rows (weighted):     over the distinct indexes u (multiplicity c_u) of indexes[n]:
+ *                      value_out[0] = weight/p * sum_u c_u sum_k |W[u,k]|^p / n ;  grad[u,:] += weight c_u/n |W|^(p-1) sign(W)
+ * adagrad_dense_lp:    kgeb_adagrad_dense with the dense penalty gradient formed from the parameter it reads anyway
+ *                      and value_out[0] = the penalty of the pre-update parameters (train.py:320-338 then :375). */
+int64_t kgeb_penalty_workspace_bytes(int64_t n_indexes, int64_t numel);
+int kgeb_lp_penalty_dense(const float* W, int64_t numel, int p, float weight, float* grad, float* value_out,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int kgeb_lp_penalty_rows(const float* W, int64_t vocab, int dim, const void* indexes, int idx64, int64_t n, int p,
+                         float weight, float* grad, float* value_out, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+int kgeb_adagrad_dense_lp(float* W, float* state, const float* grad, const float* grad2, int64_t numel, float clr,
+                          float eps, float weight_decay, int p, float pen_weight, void* bf16_mirror, float* value_out,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- 8f-4: rank histograms and metrics on the device (eval.py:138-224, entity_ranking.py:553-577).
+ * rank_hist:    hist[ranks[i]] += 1 for every i with mask[i] != 0 (mask NULL = all); *status = 1 on a rank outside
+ *               [0, num_entities).  isin_sorted builds the drill-down masks (`id in set`, eval.py:187,205-221).
+ * rank_metrics: out = {count, mean_rank, mean_reciprocal_rank, hits@k[0..num_k)} (double, device); hits_at_k is a
+ *               HOST array of at most 16 values; all metrics 0 for an empty histogram. */
+int kgeb_rank_hist(const int64_t* ranks, const uint8_t* mask, int64_t n, int64_t num_entities, float* hist,
+                   int32_t* status, void* stream);
+int kgeb_isin_sorted(const void* values, int idx64, int64_t n, const int64_t* sorted_set, int64_t m, uint8_t* mask,
+                     void* stream);
+int64_t kgeb_rank_metrics_workspace_bytes(void);
+int kgeb_rank_metrics(const float* hist, int64_t num_entities, const int32_t* hits_at_k, int num_k, double* out,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

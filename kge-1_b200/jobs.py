@@ -132,12 +132,9 @@ class TrainingJobKvsAll(TrainingJob):
     # -- static-shape, graph-captured step (trainer.py) ---------------------------------------------------
     def enable_graph_step(self, batch_size: int, nnz_max: int, use_graph: bool = True, dp_group=None):
         """Routes step() through FusedAllEntityStepper for batches of exactly `batch_size` queries with at most
-        `nnz_max` labels (no autograd, one CUDA-graph replay per step).  Needs the DOT scorers, dense Adagrad
-        and no penalty terms."""
+        `nnz_max` labels (no autograd, one CUDA-graph replay per step).  Needs the DOT scorers and dense Adagrad;
+        unweighted Lp penalties are folded into the Adagrad kernels (the toy config's regularize_weight)."""
         from .trainer import FusedAllEntityStepper
-        if any(e.regularize_weight != 0.0 and e.regularize != "" for e in
-               (self.model.get_s_embedder(), self.model.get_p_embedder())):
-            raise NotImplementedError("penalty terms are not part of the graph-captured step")
         self.stepper = FusedAllEntityStepper(self.model, self.optimizer, batch_size, nnz_max, self.loss.kind,
                                              batch_size, self.loss.offset, self.label_smoothing, self.math_mode,
                                              use_graph, self.shard, dp_group)
@@ -252,7 +249,10 @@ class TrainingJobKvsAll(TrainingJob):
             self.stepper.set_inputs(*self.device_inputs(batch))
         loss = self.stepper.step()
         value = loss.item()          # the reference reads the loss back every batch too (train.py:747)
-        return ProcessBatchResult(value, self.stepper.rows, value)
+        res = ProcessBatchResult(value, self.stepper.rows, value)
+        if self.stepper.pen is not None:
+            res.penalty = float(self.stepper.penalty_values.sum().item())   # train.py:320-338 (sum of the terms)
+        return res
 
     def _process_batch(self, batch_index, batch) -> ProcessBatchResult:
         queries = batch["queries"].to(self.device)
@@ -319,6 +319,29 @@ class TrainingJobNegativeSampling(TrainingJob):
         self.stepper = FusedNegSamplingStepper(self.model, self.optimizer, batch_size, num_neg_s, num_neg_o,
                                                self.loss.kind, self.loss.offset, use_graph)
         return self.stepper
+
+    def enable_device_sampling(self, sampler):
+        """Negatives are drawn on the device (sampler.KgeSampler) straight into the static inputs of
+        the captured step: the host then ships only the positive triples (24 B each) -- see step_triples()."""
+        if self.stepper is None:
+            raise ValueError("enable_graph_step() first")
+        self.sampler = sampler
+        return sampler
+
+    def step_triples(self, triples: torch.Tensor) -> ProcessBatchResult:
+        """One step from positive triples alone ([B,3] int64, host or device): H2D copy, on-device sampling of the S
+        and O negatives (train.py:801-821 does this on the CPU in the collate), graph replay."""
+        st = self.stepper
+        if len(triples) != st.B:
+            raise ValueError(f"the captured step serves batches of exactly {st.B} triples")
+        for f in self.pre_batch_hooks:
+            f(self)
+        t = triples.to(self.device, non_blocking=True).long()
+        st.triples.copy_(t.t(), non_blocking=True)
+        for slot in st.slots:
+            self.sampler.sample(t, slot, out=st.neg[slot])
+        value = st.step().item()
+        return ProcessBatchResult(value, st.B)
 
     def step(self, batch_index: int, batch: dict) -> ProcessBatchResult:
         st = self.stepper
@@ -430,36 +453,54 @@ class EntityRankingJob:
         return out
 
     def _compute_metrics(self, hist: torch.Tensor, suffix="") -> Dict[str, float]:
-        """entity_ranking.py:553-577."""
-        metrics = {}
-        n = torch.sum(hist).item()
-        ranks = torch.arange(1, self.num_entities + 1, device=hist.device).float()
-        metrics["mean_rank" + suffix] = (torch.sum(hist * ranks).item() / n) if n > 0.0 else 0.0
-        metrics["mean_reciprocal_rank" + suffix] = (torch.sum(hist * (1.0 / ranks)).item() / n) if n > 0.0 else 0.0
-        kmax = max(self.hits_at_k_s)
-        hits = (torch.cumsum(hist[:kmax], dim=0) / n).tolist() if n > 0.0 else [0.0] * kmax
-        for k in self.hits_at_k_s:
-            metrics["hits_at_{}{}".format(k, suffix)] = hits[k - 1]
-        return metrics
+        """entity_ranking.py:553-577, reduced on the device (csrc/metrics.cu)."""
+        from . import metrics as dm
+        return dm.rank_metrics(hist, self.hits_at_k_s, suffix)
 
     @torch.no_grad()
-    def run(self, triples) -> Dict[str, object]:
+    def run(self, triples, head_and_tail: bool = False,
+            relations_per_type: Optional[Dict[str, Sequence[int]]] = None) -> Dict[str, object]:
+        """Ranks every triple and reduces the ranks to histograms + metrics on the device.  `head_and_tail` adds the
+        "head" / "tail" histograms of eval.py:151-171, `relations_per_type` ({type: relation ids}) the drill-down of
+        hist_per_relation_type (eval.py:173-198); metric names follow entity_ranking.py:370-381
+        ("mean_rank_filtered_head", "hits_at_10_1-N_tail", ...)."""
+        from . import metrics as dm
         was_training = self.model.training
         self.model.eval()
         triples = torch.as_tensor(triples)
         names = ["_raw", "_filt"] + (["_filt_test"] if self.test_indexes is not None else [])
-        hists = {n: torch.zeros(self.num_entities, device=self.device) for n in names}
+        E = self.num_entities
+        zeros = lambda: torch.zeros(E, dtype=torch.float32, device=self.device)  # noqa: E731
+        hists = {n: {"all": zeros()} for n in names}
+        rel_sets = {t: torch.as_tensor(sorted(set(int(r) for r in rels)), dtype=torch.int64, device=self.device)
+                    for t, rels in (relations_per_type or {}).items()}
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
         all_ranks: Dict[str, List[torch.Tensor]] = {}
         for lo in range(0, len(triples), self.batch_size):
-            res = self.rank_batch(triples[lo:lo + self.batch_size])
+            batch = triples[lo:lo + self.batch_size]
+            res = self.rank_batch(batch)
+            masks = {t: dm.isin_sorted(batch[:, P].to(self.device), rs) for t, rs in rel_sets.items()}
             for k, v in res.items():
                 all_ranks.setdefault(k, []).append(v)
-                # hist_all (eval.py:138-171): a bincount instead of the Python loop over ranks
-                hists[k[1:]] += torch.bincount(v, minlength=self.num_entities).float()
+                side, name = k[0], k[1:]               # "o_raw" -> tail ranks of the raw setting
+                h = hists[name]
+                # hist_all (eval.py:138-171): one kernel per histogram instead of the Python loop over ranks
+                dm.rank_hist(v, E, h["all"], status=status)
+                if head_and_tail:
+                    dm.rank_hist(v, E, h.setdefault("tail" if side == "o" else "head", zeros()), status=status)
+                for t, m in masks.items():
+                    dm.rank_hist(v, E, h.setdefault(t, zeros()), mask=m, status=status)
+                    if head_and_tail:
+                        dm.rank_hist(v, E, h.setdefault(f"{t}_{'tail' if side == 'o' else 'head'}", zeros()), mask=m,
+                                     status=status)
+        if int(status.item()) != 0:
+            raise RuntimeError("a rank outside [0, num_entities) reached the histogram")
         suffix = {"_raw": "", "_filt": "_filtered", "_filt_test": "_filtered_with_test"}
         metrics = {}
         for n in names:
-            metrics.update(self._compute_metrics(hists[n], suffix[n]))
+            for key, h in hists[n].items():      # entity_ranking.py:370-381: "<metric><suffix>[_<group>]"
+                metrics.update(self._compute_metrics(h, suffix[n] + ("" if key == "all" else "_" + key)))
         if was_training:
             self.model.train()
+        self.hists = hists
         return {"metrics": metrics, "ranks": {k: torch.cat(v) for k, v in all_ranks.items()}}

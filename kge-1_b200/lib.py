@@ -23,7 +23,7 @@ LOSS_KL, LOSS_BCE = 0, 1
 MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
 
 _c = ctypes
-_p, _i, _l, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+_p, _i, _l, _f, _u = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_uint64
 
 # name -> argtypes, exactly the declarations of include/kgeb200.h (checked by tests/test_abi.py)
 SIGNATURES = {
@@ -56,6 +56,17 @@ SIGNATURES = {
     "kgeb_kvsall_batch_count": [_p, _p, _p, _l, _p, _p, _p, _p, _p],
     "kgeb_kvsall_batch_fill": [_p, _p, _p, _l, _p, _l, _p, _p, _p],
     "kgeb_kvsall_batch_build": [_p, _p, _p, _l, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p],
+    "kgeb_philox_words": [_u, _u, _u, _l, _p, _p],
+    "kgeb_philox_advance": [_p, _u, _p],
+    "kgeb_sample_uniform": [_p, _l, _l, _p, _p],
+    "kgeb_sample_filter": [_p, _l, _p, _p, _p, _l, _l, _p, _p, _p],
+    "kgeb_sample_shared": [_p, _l, _p, _l, _l, _i, _p, _p, _p, _l, _p],
+    "kgeb_lp_penalty_dense": [_p, _l, _i, _f, _p, _p, _p, _l, _p],
+    "kgeb_lp_penalty_rows": [_p, _l, _i, _p, _i, _l, _i, _f, _p, _p, _p, _l, _p],
+    "kgeb_adagrad_dense_lp": [_p, _p, _p, _p, _l, _f, _f, _f, _i, _f, _p, _p, _p, _l, _p],
+    "kgeb_rank_hist": [_p, _p, _l, _l, _p, _p, _p],
+    "kgeb_isin_sorted": [_p, _i, _l, _p, _l, _p, _p],
+    "kgeb_rank_metrics": [_p, _l, _p, _i, _p, _p, _l, _p],
 }
 
 
@@ -74,7 +85,8 @@ def index_descs(arrays) -> "ctypes.Array":
         d.keys, d.num_keys, d.offsets, d.values = keys.data_ptr(), keys.shape[0], offsets.data_ptr(), values.data_ptr()
     return out
 _INT64_RESULT = {"kgeb_fused_workspace_bytes": [_l, _i, _l, _l], "kgeb_scatter_workspace_bytes": [_l, _i],
-                 "kgeb_kvsall_build_workspace_bytes": [_l, _l]}
+                 "kgeb_kvsall_build_workspace_bytes": [_l, _l], "kgeb_sample_shared_workspace_bytes": [_l],
+                 "kgeb_penalty_workspace_bytes": [_l, _l], "kgeb_rank_metrics_workspace_bytes": []}
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -76,13 +76,9 @@ class LookupEmbedder(torch.nn.Module):
             return []
         p, w = self.regularize_p, self.regularize_weight
         if not self.regularize_weighted:
-            value = (w / p * self._embeddings.weight.norm(p=p) ** p).sum()
+            value = ops.lp_penalty(self._embeddings.weight, p, w)
         else:
-            unique, counts = torch.unique(kwargs["indexes"], return_counts=True)
-            prm = self.embed(unique) if self.dropout.p == 0 else ops.gather_rows(self._embeddings.weight, unique)
-            if p % 2 == 1:
-                prm = torch.abs(prm)
-            value = (w / p * (prm ** p * counts.float().view(-1, 1))).sum() / len(kwargs["indexes"])
+            value = ops.lp_penalty(self._embeddings.weight, p, w, kwargs["indexes"])
         return [(f"{self.configuration_key}.L{p}_penalty", value)]
 
 

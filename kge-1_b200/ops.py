@@ -338,3 +338,74 @@ class _PairsScore(torch.autograd.Function):
 
 def pairs_score(kind: int, q: torch.Tensor, table: torch.Tensor, cand: torch.Tensor, sparse: bool = False):
     return _PairsScore.apply(kind, q, table, cand, sparse)
+
+
+# ---------------------------------------------------------------------------------------------
+# Lp penalties (lookup_embedder.py:112-158) -- csrc/penalty.cu
+# ---------------------------------------------------------------------------------------------
+def _penalty_ws(device, n_indexes: int, numel: int) -> torch.Tensor:
+    return _workspace(device, lib.load().kgeb_penalty_workspace_bytes(int(n_indexes), int(numel)))
+
+
+class _LpPenaltyDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, p, reg_weight):
+        w = weight.detach()
+        value = torch.empty(1, dtype=torch.float32, device=w.device)
+        ws = _penalty_ws(w.device, 0, w.numel())
+        lib.call("kgeb_lp_penalty_dense", lib.f32(w, "weight"), w.numel(), int(p), float(reg_weight), None,
+                 value.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream_ptr(w))
+        ctx.save_for_backward(weight)
+        ctx.p, ctx.reg_weight = int(p), float(reg_weight)
+        return value.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        (weight,) = ctx.saved_tensors
+        w = weight.detach()
+        grad = torch.zeros_like(w)
+        value = torch.empty(1, dtype=torch.float32, device=w.device)
+        ws = _penalty_ws(w.device, 0, w.numel())
+        lib.call("kgeb_lp_penalty_dense", lib.f32(w, "weight"), w.numel(), ctx.p, ctx.reg_weight, grad.data_ptr(),
+                 value.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream_ptr(w))
+        return grad * gout, None, None
+
+
+class _LpPenaltyRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, indexes, p, reg_weight):
+        w = weight.detach()
+        iptr, i64 = lib.idx(indexes.contiguous(), "indexes")
+        value = torch.empty(1, dtype=torch.float32, device=w.device)
+        ws = _penalty_ws(w.device, indexes.numel(), 0)
+        lib.call("kgeb_lp_penalty_rows", lib.f32(w, "weight"), w.shape[0], w.shape[1], iptr, i64, indexes.numel(), int(p),
+                 float(reg_weight), None, value.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream_ptr(w))
+        ctx.save_for_backward(weight, indexes)
+        ctx.p, ctx.reg_weight = int(p), float(reg_weight)
+        return value.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        weight, indexes = ctx.saved_tensors
+        w = weight.detach()
+        iptr, i64 = lib.idx(indexes.contiguous(), "indexes")
+        grad = torch.zeros_like(w)
+        value = torch.empty(1, dtype=torch.float32, device=w.device)
+        ws = _penalty_ws(w.device, indexes.numel(), 0)
+        lib.call("kgeb_lp_penalty_rows", lib.f32(w, "weight"), w.shape[0], w.shape[1], iptr, i64, indexes.numel(), ctx.p,
+                 ctx.reg_weight, grad.data_ptr(), value.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream_ptr(w))
+        return grad * gout, None, None, None
+
+
+def lp_penalty(weight: torch.Tensor, p: int, reg_weight: float, indexes: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """reg_weight/p * ||W||_p^p (indexes None: unweighted, whole table) or the weighted per-distinct-index form divided
+    by len(indexes) (lookup_embedder.py:126-155); differentiable w.r.t. `weight`."""
+    if not weight.is_cuda:
+        raise ValueError("weight must be a CUDA tensor (no CPU path exists)")
+    if int(p) != p or p < 1:
+        raise NotImplementedError(f"regularize_args.p={p}: integer p >= 1 only")
+    if indexes is None:
+        return _LpPenaltyDense.apply(weight, int(p), float(reg_weight))
+    if indexes.numel() == 0:
+        return weight.new_zeros(())
+    return _LpPenaltyRows.apply(weight, indexes, int(p), float(reg_weight))

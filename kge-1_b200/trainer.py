@@ -39,6 +39,21 @@ class FusedAllEntityStepper:
         self.lr, self.eps = float(group["lr"]), float(group["eps"])
         f32 = dict(dtype=torch.float32, device=dev)
         i64 = dict(dtype=torch.int64, device=dev)
+        # Unweighted Lp penalties (lookup_embedder.py:126-134) are folded into the Adagrad kernels:
+        # the entity table is penalised by the s- and the o-embedder (kge_model.py:588-606), i.e. twice.
+        self.pen = None
+        e_emb, r_emb = model.get_s_embedder(), model.get_p_embedder()
+        active = [e for e in (e_emb, r_emb) if e.regularize != "" and e.regularize_weight != 0.0]
+        if active:
+            if any(e.regularize_weighted for e in active):
+                raise NotImplementedError("weighted penalties need the triples of the batch; not part of this step")
+            if dp_group is not None or (shard is not None and shard.distributed):
+                raise NotImplementedError("penalty terms are built for the single-GPU captured step")
+            self.pen = dict(ent=(int(e_emb.regularize_p), 2.0 * e_emb.regularize_weight if e_emb in active else 0.0),
+                            rel=(int(r_emb.regularize_p), r_emb.regularize_weight if r_emb in active else 0.0))
+            self.penalty_values = torch.zeros(2, **f32)          # [entity terms (s + o), relation term]
+            nb = lib.load().kgeb_penalty_workspace_bytes(0, max(self.ent.numel(), self.rel.numel()))
+            self.pen_ws = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2)]
         # static inputs: ONE contiguous byte buffer so that a packed host batch arrives with a single H2D copy
         #   int64 [a_idx (rows) | p_idx (rows) | lab_off (rows+1) | lab_col (nnz_max)]
         #   int32 [row_combine (rows) | a_perm (rows) | p_perm (rows) | lab_perm (nnz_max)]
@@ -189,8 +204,13 @@ class FusedAllEntityStepper:
                      self.sws2.numel(), st2)
             if self.dp_world == 1:
                 s_rel = self.opt.state[self.rel]["sum"]
-                lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
-                         self.lr, self.eps, 0.0, None, st2)
+                if self.pen is not None:
+                    lib.call("kgeb_adagrad_dense_lp", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None,
+                             rel.numel(), self.lr, self.eps, 0.0, self.pen["rel"][0], self.pen["rel"][1], None,
+                             self.penalty_values[1:].data_ptr(), self.pen_ws[1].data_ptr(), self.pen_ws[1].numel(), st2)
+                else:
+                    lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None,
+                             rel.numel(), self.lr, self.eps, 0.0, None, st2)
         lib.call("kgeb_scatter_add_rows_perm", self.a_idx.data_ptr(), 1, self.a_perm.data_ptr(), self.da.data_ptr(),
                  self.rows, self.d, self.g_q.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
         if self.dp_world > 1:
@@ -201,8 +221,14 @@ class FusedAllEntityStepper:
         if not self.shard.distributed:
             self._join_side()     # dense table gradient from the side stream
         s_ent = self.opt.state[self.ent]["sum"]
-        lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
-                 ent.numel(), self.lr, self.eps, 0.0, None if self.mirror is None else self.mirror.data_ptr(), st)
+        mirror = None if self.mirror is None else self.mirror.data_ptr()
+        if self.pen is not None:
+            lib.call("kgeb_adagrad_dense_lp", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
+                     ent.numel(), self.lr, self.eps, 0.0, self.pen["ent"][0], self.pen["ent"][1], mirror,
+                     self.penalty_values.data_ptr(), self.pen_ws[0].data_ptr(), self.pen_ws[0].numel(), st)
+        else:
+            lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
+                     ent.numel(), self.lr, self.eps, 0.0, mirror, st)
         cur.wait_stream(self.side2)
 
     def _stage_apply_dp(self):

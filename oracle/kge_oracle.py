@@ -542,3 +542,52 @@ def entity_ranking(model, ent_w, rel_w, triples, filter_triples: Sequence[np.nda
                 hists[n] += rank_histogram(r, e)
     metrics = {n: metrics_from_hist(h, hits_at_k) for n, h in hists.items()}
     return metrics, {k: torch.cat(v) if v else torch.zeros(0, dtype=torch.long) for k, v in all_ranks.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# rows around the path
+# ---------------------------------------------------------------------------------------------
+def lp_penalty(weight: torch.Tensor, p: int, reg_weight: float, indexes: Optional[torch.Tensor] = None,
+               weighted: bool = False) -> torch.Tensor:
+    """lookup_embedder.py:112-158: unweighted `w/p * ||W||_p^p` over the whole table (:126-134), or the weighted
+    per-distinct-index form divided by len(indexes) (:135-155).  Differentiable w.r.t. `weight`."""
+    if not weighted:
+        return (reg_weight / p * weight.norm(p=p) ** p).sum()
+    unique, counts = torch.unique(indexes, return_counts=True)
+    prm = F.embedding(unique.long(), weight)
+    if p % 2 == 1:
+        prm = torch.abs(prm)
+    return (reg_weight / p * (prm ** p * counts.float().view(-1, 1))).sum() / len(indexes)
+
+
+def model_penalties(ent_w: torch.Tensor, rel_w: torch.Tensor, triples: torch.Tensor, p: int, w_ent: float, w_rel: float,
+                    weighted: bool) -> List[torch.Tensor]:
+    """kge_model.py:588-606: s-embedder, p-embedder, o-embedder terms in that order (the shared entity table is
+    penalised once per slot)."""
+    return [lp_penalty(ent_w, p, w_ent, triples[:, S], weighted), lp_penalty(rel_w, p, w_rel, triples[:, P], weighted),
+            lp_penalty(ent_w, p, w_ent, triples[:, O], weighted)]
+
+
+def grouped_rank_histograms(ranks: Dict[str, torch.Tensor], relations: torch.Tensor, num_entities: int,
+                            relations_per_type: Optional[Dict[str, Sequence[int]]] = None,
+                            head_and_tail: bool = False) -> Dict[str, torch.Tensor]:
+    """eval.py:138-198 for one filter setting: ranks = {"s": subject ranks, "o": object ranks} of the same triples;
+    returns histograms keyed "all", "head", "tail", "<type>", "<type>_head", "<type>_tail"."""
+    h: Dict[str, torch.Tensor] = {"all": torch.zeros(num_entities)}
+
+    def add(key, r):
+        h.setdefault(key, torch.zeros(num_entities))
+        h[key][r] += 1
+
+    p = relations.tolist()
+    for side, name in (("o", "tail"), ("s", "head")):
+        for i, r in enumerate(ranks[side].tolist()):
+            add("all", r)
+            if head_and_tail:
+                add(name, r)
+            for t, rels in (relations_per_type or {}).items():
+                if p[i] in set(int(x) for x in rels):
+                    add(t, r)
+                    if head_and_tail:
+                        add(f"{t}_{name}", r)
+    return h

@@ -21,6 +21,8 @@ def _header_decls():
                 kinds.append("p")
             elif a.startswith("int64_t"):
                 kinds.append("l")
+            elif a.startswith("uint64_t"):
+                kinds.append("u")
             elif a.startswith("float"):
                 kinds.append("f")
             elif a.startswith("int"):
@@ -52,7 +54,8 @@ def test_library_loads_and_exports_every_declared_symbol(kb):
 def test_ctypes_signatures_agree_with_header(kb):
     import ctypes
     decls = _header_decls()
-    code = {ctypes.c_void_p: "p", ctypes.c_int: "i", ctypes.c_int64: "l", ctypes.c_float: "f", ctypes.c_char_p: "p"}
+    code = {ctypes.c_void_p: "p", ctypes.c_int: "i", ctypes.c_int64: "l", ctypes.c_float: "f", ctypes.c_char_p: "p",
+            ctypes.c_uint64: "u"}
     for name, argtypes in {**kb.lib.SIGNATURES, **kb.lib._INT64_RESULT}.items():
         assert name in decls, f"{name} bound in lib.py but not declared in the header"
         assert [code[a] for a in argtypes] == decls[name][1], name

@@ -1,0 +1,104 @@
+"""CPU checks of the oracles for the rows around the hot path: the Philox restatement against the
+Random123 known-answer vectors, the penalty / metric restatements against golden vectors from the unmodified
+reference (tests/golden/make_golden_aux.py -> aux.npz), and the reference's sampling contract on the oracle sampler."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kge_oracle as ko
+from oracle import sampler_oracle as so
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def aux():
+    return np.load(os.path.join(GOLD, "aux.npz"), allow_pickle=False)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = so.philox4x32_10(np.array([ctr], dtype=np.uint32), np.array(key, dtype=np.uint32))[0]
+        assert tuple(int(x) for x in got) == want
+
+
+def test_penalty_oracle_matches_reference(aux):
+    triples = torch.from_numpy(aux["penalty.triples"])
+    for tag in aux["penalty.cases"]:
+        tag = str(tag)
+        p = int(tag.split(".")[1][1:])
+        weighted = tag.endswith(".weighted")
+        ent = torch.from_numpy(aux[tag + ".ent"]).requires_grad_()
+        rel = torch.from_numpy(aux[tag + ".rel"]).requires_grad_()
+        vals = []
+        for v in ko.model_penalties(ent, rel, triples, p, 0.05, 0.02, weighted):
+            v.backward()
+            vals.append(v.item())
+        np.testing.assert_allclose(vals, aux[tag + ".values"], rtol=1e-6)
+        np.testing.assert_allclose(ent.grad.numpy(), aux[tag + ".grad_ent"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(rel.grad.numpy(), aux[tag + ".grad_rel"], rtol=1e-6, atol=1e-9)
+
+
+def _oracle_grouped_metrics(aux):
+    g = {k: aux[f"metrics.graph.{k}"] for k in ("train", "valid", "test")}
+    ent, rel = torch.from_numpy(aux["metrics.ent"]), torch.from_numpy(aux["metrics.rel"])
+    rpt = {str(t): aux[f"metrics.relations_of.{t}"].tolist() for t in aux["metrics.relation_types"]}
+    _, ranks = ko.entity_ranking("complex", ent, rel, g["valid"], [g["train"], g["valid"]], g["test"], batch_size=16,
+                                 hits_at_k=(1, 3, 10))
+    out = {}
+    suffix = {"_raw": "", "_filt": "_filtered", "_filt_test": "_filtered_with_test"}
+    rels = torch.from_numpy(g["valid"][:, 1].astype(np.int64))
+    for n, sfx in suffix.items():
+        hs = ko.grouped_rank_histograms({"s": ranks["s" + n], "o": ranks["o" + n]}, rels, len(ent), rpt, True)
+        for key, h in hs.items():
+            for k, v in ko.metrics_from_hist(h, (1, 3, 10)).items():
+                out[k + sfx + ("" if key == "all" else "_" + key)] = v
+    return out
+
+
+def test_grouped_metrics_oracle_matches_reference(aux):
+    got = _oracle_grouped_metrics(aux)
+    keys = [str(k) for k in aux["metrics.keys"]]
+    assert len(keys) >= 60
+    for k in keys:
+        assert k in got, k
+        assert abs(got[k] - float(aux[f"metrics.value.{k}"])) <= 1e-6, (k, got[k], float(aux[f"metrics.value.{k}"]))
+
+
+def test_sampler_oracle_contract():
+    vocab, b, n = 97, 40, 12
+    rng = np.random.default_rng(0)
+    pos = rng.integers(0, vocab, b)
+    # uniform: range and rough uniformity (sampler.py:195-198)
+    u = so.sample_uniform(7, 0, vocab, 20000)
+    assert u.min() >= 0 and u.max() < vocab
+    cnt = np.bincount(u, minlength=vocab)
+    assert cnt.min() > 120 and cnt.max() < 300
+    assert not np.array_equal(u[:100], so.sample_uniform(7, 1 << 20, vocab, 100))
+    # shared WOR (sampler.py:200-255): n distinct values per row, own positive never present, rows differ from the
+    # shared set in at most one position
+    out, nd, shared = so.sample_shared(3, 0, vocab, pos, n, with_replacement=False)
+    assert nd == n and len(set(shared.tolist())) == n + 1
+    for i in range(b):
+        assert len(set(out[i].tolist())) == n and pos[i] not in out[i]
+        assert (out[i] != shared[:n]).sum() <= 1
+    # shared WR: num_distinct <= n distinct values per row, the remaining columns are copies
+    out, nd, shared = so.sample_shared(5, 0, 9, rng.integers(0, 9, b), 7, with_replacement=True)
+    assert 1 <= nd <= 7
+    for i in range(b):
+        assert len(set(out[i, :nd].tolist())) == nd and set(out[i, nd:].tolist()) <= set(out[i, :nd].tolist())
+    # filtering (sampler.py:148-176): no known positive survives
+    index = {(int(a), int(c)): np.sort(rng.choice(vocab, 30, replace=False)) for a, c in zip(range(b), range(b))}
+    neg = so.sample_uniform(11, 0, vocab, b * n).reshape(b, n)
+    f = so.sample_filter(11, 0, vocab, index, np.arange(b), np.arange(b), neg)
+    for i in range(b):
+        assert not set(f[i].tolist()) & set(index[(i, i)].tolist())
+        keep = ~np.isin(neg[i], index[(i, i)])
+        assert np.array_equal(f[i][keep], neg[i][keep])
