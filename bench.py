@@ -154,9 +154,10 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="tuning runs: device-resident value + kernel roofline only")
-    ap.add_argument("--parallel", default="dp", choices=["dp", "shard"],
-                    help="N>1: dp = data-parallel replicas + one gradient all-reduce (graphs too small to shard); "
-                         "shard = entity-sharded scoring (SURVEY.md 8e)")
+    ap.add_argument("--parallel", default="dp", choices=["dp", "p2p", "shard"],
+                    help="N>1: dp = data-parallel replicas + one NCCL all-reduce of the gradients (graphs too small to "
+                         "shard); p2p = the same replicas with the exchange fused into the Adagrad update over NVLink "
+                         "peer memory, whole step in one CUDA graph; shard = entity-sharded scoring (SURVEY.md 8e)")
     ap.add_argument("--profile-calls", action="store_true", help="print GPU time per C-ABI call of one step and exit")
     ap.add_argument("--timeline", action="store_true",
                     help="write the kernel timeline of one step (CUPTI) to gpurun_out/timeline_bench.txt and exit")
@@ -211,7 +212,8 @@ def main():
     job = kb.TrainingJobKvsAll(model, opt, kb.KgeLoss.create("bce"), E, R, fused_path=True, math_mode=math_mode,
                                shard=shard)
     job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph,
-                          dp_group=dist.group.WORLD if (world > 1 and not sharded) else None)
+                          dp_group=dist.group.WORLD if (world > 1 and not sharded) else None,
+                          dp_p2p=args.parallel == "p2p")
     stepper = job.stepper
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -253,7 +255,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = t.item()
     value = world * B * args.steps / (total_ms / 1e3)
-    final_loss = stepper.loss.item()
+    final_loss = (stepper.loss if getattr(stepper, "p2p", None) is None else stepper.loss_global).item()
+    if getattr(stepper, "p2p", None) is not None:
+        stepper.check_p2p()
 
     # ---------------- e2e: public API, pinned host batches, H2D + loss D2H inside the timed region -------
     e2e_s = 0.0
@@ -315,8 +319,12 @@ def main():
                    "math": args.math + " tensor tiles, fp32 accumulate, fp32 master tables and optimizer",
                    "parallelism": "1 GPU" if world == 1 else (
                        f"entity-sharded scoring over {world} GPUs (all-reduce of row statistics, dQ, dense gradient)"
-                       if sharded else f"dp{world}: replicas with one all-reduce of both tables' gradients + loss per "
-                                       "step (FB15k-237-sized tables are too small to shard, SURVEY.md 8e)"),
+                       if sharded else (f"dp{world}: replicas; gradient exchange fused with the Adagrad update over "
+                                        "NVLink peer memory (reduce-scatter of gradients, all-gather of updated "
+                                        "weights, sharded optimizer state), one CUDA graph per step"
+                                        if args.parallel == "p2p" else
+                                        f"dp{world}: replicas with one all-reduce of both tables' gradients + loss per "
+                                        "step (FB15k-237-sized tables are too small to shard, SURVEY.md 8e)")),
                    "l2": "flushed between timed steps (256 MiB write, untimed); table is 7.4 MB",
                    "cuda_graph": stepper.graph is not None, "final_loss": final_loss},
         "clocks": clocks.summary(),

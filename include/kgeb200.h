@@ -295,6 +295,23 @@ int64_t kgeb_rank_metrics_workspace_bytes(void);
 int kgeb_rank_metrics(const float* hist, int64_t num_entities, const int32_t* hits_at_k, int num_k, double* out,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- 8e (replicas row): data-parallel gradient exchange fused with the Adagrad update over NVLink peer memory.
+ * All pointer arrays are HOST arrays of `world` device pointers, entry k = rank k's buffer mapped into this process
+ * (torch symmetric memory / cuMem VMM + IPC).  Replaces  all-reduce(grad) ; torch.optim.Adagrad.step  (train.py:375)
+ * of replicated training.  Sequence per step and table:  barrier ; p2p_adagrad ; barrier ; p2p_apply.
+ * p2p_barrier: signal pad of rank k = uint32[world]; *epoch (local device counter) is advanced by one; *timeout_flag is
+ *   set if a peer does not arrive within ~10 s (a dead peer must not hang the GPU).
+ * p2p_adagrad: rank r reduces its slice of the gradient over all ranks in rank order, updates its slice of W / state /
+ *   bf16 mirror and stores the new values into every peer's staging buffer.
+ * p2p_apply:   copies the other owners' slices from the local staging buffer into W (+ mirror).
+ * p2p_sum_scalar: out[0] = sum_k peer_values[k][0] in rank order (the loss of the global batch). */
+int kgeb_p2p_barrier(const void* const* peer_signal_pads, int rank, int world, uint32_t* epoch, uint32_t* timeout_flag,
+                     void* stream);
+int kgeb_p2p_adagrad(const void* const* peer_grads, const void* const* peer_stage, int rank, int world, float* W,
+                     float* state, void* bf16_mirror, int64_t numel, float clr, float eps, void* stream);
+int kgeb_p2p_apply(const float* stage, int rank, int world, float* W, void* bf16_mirror, int64_t numel, void* stream);
+int kgeb_p2p_sum_scalar(const void* const* peer_values, int world, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,25 @@ constexpr int COLS_PER_WARP = STR_ROWS / (EPQ / 2);     // 32 S-columns per warp
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int STAGE_BYTES = RES_ROWS * 128;      // flush staging box of one column part (dTable kernel)
 
+// KGEB_TRACE (tuning builds only): block 0 records (warp, event, tile, clock64) of the pipeline's hand-offs into a global
+// buffer read back with kgeb_debug_trace(); tools/trace_bwd.py turns it into a per-tile timeline.
+#ifdef KGEB_TRACE
+// per-warp slots and a register counter: one fire-and-forget store per event (an atomic slot counter costs an L2 round
+// trip of ~850 clk per event and swamps the timeline)
+__device__ unsigned long long g_trace[32 << 11];
+#define KGEB_TR(ev, u)                                                                                          \
+  do {                                                                                                          \
+    if (blockIdx.x == 0 && tr_n__ < 2048u)                                                                      \
+      g_trace[((threadIdx.x >> 5) << 11) + tr_n__++] =                                                          \
+          ((unsigned long long)(ev) << 52) | ((unsigned long long)((u) & 0xfff) << 40) |                         \
+          ((unsigned long long)clock64() & 0xffffffffffULL);                                                    \
+  } while (0)
+#define KGEB_TRW(ev, u) do { if ((threadIdx.x & 31) == 0) KGEB_TR(ev, u); } while (0)
+#else
+#define KGEB_TR(ev, u)
+#define KGEB_TRW(ev, u)
+#endif
+
 struct Params {
   int64_t n_res;      // rows of the resident operand (B or shard entities)
   int64_t n_str;      // rows of the streamed operand
@@ -57,7 +76,13 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
               const __grid_constant__ CUtensorMap tm_out, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // the same base as a shared-window offset: derived from the symbol's shared address (a link-time constant), so the
+  // MMA issuers' descriptor arithmetic stays on the uniform datapath (the generic pointer goes through S2R)
+  const uint32_t smem_s = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef KGEB_TRACE
+  unsigned tr_n__ = 0;
+#endif
   const int KS = p.ks, NSTR = p.nstr;
   constexpr int SLAB_K = Elem<BF16>::kSlabK, UMMA_K = Elem<BF16>::kUmmaK;
   constexpr int G_SLABS = STR_ROWS / SLAB_K;            // K-slabs of the G operand (2 for TF32, 1 for BF16)
@@ -115,7 +140,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (elect_one()) {   // (single elected thread, see the MMA issuers below)
       int slot = 0;
       uint32_t phase = 0, rphase = 0;
       for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -138,15 +163,22 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================ MMA1 issuer: S = RES * STR^T ================================
-    // One thread per GEMM: a single issuing thread (barrier probes + descriptor arithmetic + 12 tcgen05.mma per tile)
+    // One warp per GEMM: a single issuing thread (barrier probes + descriptor arithmetic + 12 tcgen05.mma per tile)
     // was the critical path of the whole kernel; MMA1 and MMA2 only meet through mbarriers, so they are issued by two
-    // threads that run ahead of each other independently.
-    if (lane == 0) {
+    // warps that run ahead of each other independently.
+    // The loop runs under ONE elect.sync predicate: the compiler then knows a single thread executes it and keeps the
+    // descriptors in uniform registers (UTCHMMA back to back with one UIADD3.64 between them).  Under `if (lane == 0)`
+    // -- or with elect.sync around each instruction -- every tcgen05.mma operand is re-broadcast from vector registers
+    // (ELECT / 5x R2UR.BROADCAST / BRA.U.ANY waterfall, 18-19 instructions per MMA): ~150 dependent instructions of a
+    // single warp per tile, which the ncu source view showed to be the critical path (epilogue warps spent 26 % of their
+    // time waiting for S while the issuer never waited; profiles/README.md).
+    if (elect_one()) {
       const uint32_t idesc1 = make_idesc(RES_ROWS, STR_ROWS, 0, 0, Elem<BF16>::kFmt);  // (K-major, K-major)
       const uint64_t dbase = make_desc(0, 16, 1024);
+      const uint32_t tbase = tmem_base;
       int slot = 0, sbuf = 0;
       uint32_t ph = 0, sph[2] = {0, 0}, rphase = 0;
-      const uint32_t res0 = smem_u32(res_smem), str0 = smem_u32(str_smem);
+      const uint32_t res0 = smem_s, str0 = smem_s + (uint32_t)(KS * RES_SLAB + 2 * G_BYTES);
       for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         const int64_t ch = job / p.n_res_blocks;
         const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
@@ -154,9 +186,11 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         rphase ^= 1;
         for (int64_t u = u0; u < u1; ++u) {
           mbar_wait(&str_full[slot], ph);
+          KGEB_TR(1, u);
           mbar_wait(&s_empty[sbuf], sph[sbuf] ^ 1);
+          KGEB_TR(2, u);
           tc_fence_after();
-          const uint32_t acc = tmem_base + S_COL + (uint32_t)(sbuf * STR_ROWS);
+          const uint32_t acc = tbase + S_COL + (uint32_t)(sbuf * STR_ROWS);
           for (int k = 0; k < KS; ++k) {
             const uint64_t ra = dbase + (uint64_t)((res0 + (uint32_t)k * RES_SLAB) >> 4);
             const uint64_t sa = dbase + (uint64_t)((str0 + (uint32_t)(slot * KS + k) * STR_SLAB) >> 4);
@@ -165,6 +199,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
               umma<BF16>(acc, ra + 2 * kk, sa + 2 * kk, idesc1, (k | kk) != 0);
           }
           umma_commit(&s_full[sbuf]);
+          KGEB_TR(3, u);
           sph[sbuf] ^= 1;
           sbuf ^= 1;
           if (++slot == NSTR) { slot = 0; ph ^= 1; }
@@ -174,20 +209,22 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
     }
   } else if (warp == 3) {
     // ================================ MMA2 issuer: OUT += G * STR ================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc2 = make_idesc(RES_ROWS, p.d, 0, 1, Elem<BF16>::kFmt);       // (K-major, MN-major)
       const uint64_t abase = make_desc(0, 16, 1024);
       const uint64_t bbase = make_desc(0, STR_SLAB, 1024);
+      const uint32_t tbase = tmem_base;
       int slot = 0, gbuf = 0;
       uint32_t gph[2] = {0, 0}, ophase = 0;
-      const uint32_t g0 = smem_u32(g_smem), str0 = smem_u32(str_smem);
-      const uint32_t acc = tmem_base + O_COL;
+      const uint32_t g0 = smem_s + (uint32_t)(KS * RES_SLAB), str0 = g0 + (uint32_t)(2 * G_BYTES);
+      const uint32_t acc = tbase + O_COL;
       for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         const int64_t ch = job / p.n_res_blocks;
         const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
         mbar_wait(o_empty, ophase ^ 1);  // previous job's accumulator has been flushed
         for (int64_t u = u0; u < u1; ++u) {
           mbar_wait(&g_full[gbuf], gph[gbuf]);
+          KGEB_TR(4, u);
           tc_fence_after();
           const uint32_t ga = g0 + (uint32_t)gbuf * G_BYTES;
           const uint32_t sa = str0 + (uint32_t)(slot * KS) * STR_SLAB;
@@ -203,6 +240,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           }
           umma_commit(&str_empty[slot]);  // streamed tile free once MMA2 has read it (MMA1 of it finished long ago)
           umma_commit(&g_empty[gbuf]);
+          KGEB_TR(5, u);
           gph[gbuf] ^= 1;
           gbuf ^= 1;
           if (++slot == NSTR) slot = 0;
@@ -242,13 +280,16 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       for (int64_t u = u0; u < u1; ++u, ++gunit) {
         if ((int)(gunit & 1) != group) continue;
         const int bufi = group;
+        KGEB_TRW(8, u);
         mbar_wait(&s_full[bufi], sph);
+        KGEB_TRW(9, u);
         sph ^= 1;
         tc_fence_after();
         float v[COLS_PER_WARP];
         tmem_ld32(lane_addr + S_COL + (uint32_t)(bufi * STR_ROWS + sub * COLS_PER_WARP), v);
         tc_fence_before();
-        mbar_arrive_warp(&s_empty[bufi]);  // S values are in registers: MMA1 of the tile after next may overwrite them
+        mbar_arrive_warp(&s_empty[bufi]);
+        KGEB_TRW(10, u);  // S values are in registers: MMA1 of the tile after next may overwrite them
         // Rows / columns beyond the matrices were zero-filled by TMA, so whatever finite G they get multiplies
         // zeros in MMA2; only the parameter loads are clamped.
         const int64_t qbase = u * STR_ROWS + sub * COLS_PER_WARP;
@@ -274,75 +315,79 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
             v[c] = ((c & 7) < KGEB_POLY8_KL) ? ex2_poly<3, false>(a) : ex2_ftz(a);
           }
         } else {
-          // BCE, two columns per iteration.  MUFU diet (the pipe has 16 lanes/clk/SM, every other pipe 128):
-          //  * KGEB_RCP_PAIR: the two reciprocals of a pair come from ONE rcp of the product (batch inversion:
-          //    1/a0 = a1 / (a0 a1), 1/a1 = a0 / (a0 a1)) -- 1 MUFU + 3 FMUL instead of 2 MUFU;
-          //  * KGEB_LG2_GROUP: sum lg2(a_i) = lg2(prod a_i); a_i in [1, 2], so a product of <= 32 factors stays far
-          //    inside the fp32 range and costs one FMUL per factor instead of one MUFU.
+          // BCE, four columns per iteration.  MUFU diet (the XU pipe has 16 lanes/clk/SM, the FMA pipe 128; the pipeline
+          // trace (tools/trace_bwd.py) shows the epilogue warps spending 55-75 % of a tile in this loop with the XU pipe
+          // ~80 % busy, i.e. these kernels are bound by MUFU throughput):
+          //  * KGEB_RCP_GROUP = 2 | 4: the reciprocals of a group come from ONE rcp of the product of the group (batch
+          //    inversion, 1/a0 = a1 / (a0 a1) ...): 1 MUFU + 3 | 9 FMUL instead of 2 | 4 MUFU; relative error ~4 ulp;
+          //  * KGEB_LG2_GROUP = 4..32: sum lg2(a_i) = lg2(prod a_i); a_i in [1, 2], so a product of <= 32 factors stays
+          //    far inside the fp32 range and costs one FMUL per factor instead of one MUFU.
+          constexpr int RG = KGEB_RCP_GROUP, LG = KGEB_LG2_GROUP;
+          static_assert(RG == 1 || RG == 2 || RG == 4, "KGEB_RCP_GROUP must be 1, 2 or 4");
+          static_assert(LG == 1 || (LG % 4 == 0 && COLS_PER_WARP % LG == 0), "KGEB_LG2_GROUP must be 1 or a multiple of 4");
           float prod = 1.f;
           const float nls = -p.ls_add;
+          // exponent clamp of the non-STATS form: the product of a group must stay finite (the sigmoid of z < -20.8
+          // (-41.6) then reads 9e-10 (9e-19), far below the bf16 resolution of G next to any other entry)
+          const float tmax = RG == 4 ? 30.f : 60.f;
 #pragma unroll
-          for (int c = 0; c < COLS_PER_WARP; c += 2) {
-            const float rs0 = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c) : col_rs;
-            const float rs1 = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c + 1) : col_rs;
-            if (STATS) {
-              // sigmoid and softplus from one exponential, cancellation-free:
-              //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
-              const float z0 = v[c] + p.offset, z1 = v[c + 1] + p.offset;
-              const float t0 = fabsf(z0) * -kLog2e, t1 = fabsf(z1) * -kLog2e;
-              const float e0 = ((c & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t0) : ex2_ftz(t0);
-              const float e1 = (((c + 1) & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t1) : ex2_ftz(t1);
-              const float a0 = 1.f + e0, a1 = 1.f + e1;
-              float r0, r1;
-              if (KGEB_RCP_PAIR) {
-                const float pr = a0 * a1, ri = rcp_ftz(pr);
-                r0 = ri * a1;
-                r1 = ri * a0;
-                if (KGEB_LG2_GROUP > 1) prod *= pr;
+          for (int c = 0; c < COLS_PER_WARP; c += 4) {
+            float z[4], e[4], a[4], r[4], rs[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rs[j] = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c + j) : col_rs;
+              float t;
+              if (STATS) {
+                // sigmoid and softplus from one exponential, cancellation-free:
+                //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
+                z[j] = v[c + j] + p.offset;
+                t = fabsf(z[j]) * -kLog2e;
+                e[j] = (((c + j) & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t) : ex2_ftz(t);
               } else {
-                r0 = rcp_ftz(a0);
-                r1 = rcp_ftz(a1);
-                if (KGEB_LG2_GROUP > 1) prod *= a0 * a1;
+                // rs * (sigmoid(x + offset) - ls_add) = rs / (1 + exp(-(x + offset))) - rs ls_add
+                t = fmaf(v[c + j], -kLog2e, off2);
+                if (RG > 1) t = fminf(t, tmax);
+                e[j] = (((c + j) & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t) : ex2_ftz(t);
               }
-              if (KGEB_LG2_GROUP > 1) {
-                if (((c + 2) % KGEB_LG2_GROUP) == 0) {
+              a[j] = 1.f + e[j];
+            }
+            const float p01 = a[0] * a[1], p23 = a[2] * a[3];
+            if (RG == 1) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) r[j] = rcp_ftz(a[j]);   // e = inf for very negative z -> rcp gives 0
+            } else if (RG == 2) {
+              const float i01 = rcp_ftz(p01), i23 = rcp_ftz(p23);
+              r[0] = i01 * a[1]; r[1] = i01 * a[0]; r[2] = i23 * a[3]; r[3] = i23 * a[2];
+            } else {
+              const float ri = rcp_ftz(p01 * p23);
+              const float i01 = ri * p23, i23 = ri * p01;
+              r[0] = i01 * a[1]; r[1] = i01 * a[0]; r[2] = i23 * a[3]; r[3] = i23 * a[2];
+            }
+            if (STATS) {
+              if (LG > 1) {
+                prod *= p01 * p23;
+                if (((c + 4) % LG) == 0) {
                   st_lg += lg2_ftz(prod);
                   prod = 1.f;
                 }
               } else {
-                st_lg += lg2_ftz(a0) + lg2_ftz(a1);
+                st_lg += (lg2_ftz(a[0]) + lg2_ftz(a[1])) + (lg2_ftz(a[2]) + lg2_ftz(a[3]));
               }
-              st_mx += fmaxf(z0, 0.f) + fmaxf(z1, 0.f);
-              st_x += z0 + z1;
-              v[c] = fmaf(z0 >= 0.f ? r0 : e0 * r0, rs0, nls * rs0);
-              v[c + 1] = fmaf(z1 >= 0.f ? r1 : e1 * r1, rs1, nls * rs1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                st_mx += fmaxf(z[j], 0.f);
+                st_x += z[j];
+                v[c + j] = fmaf(z[j] >= 0.f ? r[j] : e[j] * r[j], rs[j], nls * rs[j]);
+              }
             } else {
-              // rs * (sigmoid(x + offset) - ls_add) = rs / (1 + exp(-(x + offset))) - rs ls_add
-              float t0 = fmaf(v[c], -kLog2e, off2), t1 = fmaf(v[c + 1], -kLog2e, off2);
-              if (KGEB_RCP_PAIR) {
-                // exponent clamp: the product of the pair must stay finite (sigmoid(z < -41.6) reads 8.7e-19, far
-                // below the bf16 resolution of G next to any other entry)
-                t0 = fminf(t0, 60.f);
-                t1 = fminf(t1, 60.f);
-              }
-              const float e0 = ((c & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t0) : ex2_ftz(t0);
-              const float e1 = (((c + 1) & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t1) : ex2_ftz(t1);
-              const float a0 = 1.f + e0, a1 = 1.f + e1;
-              float r0, r1;
-              if (KGEB_RCP_PAIR) {
-                const float ri = rcp_ftz(a0 * a1);
-                r0 = ri * a1;
-                r1 = ri * a0;
-              } else {
-                r0 = rcp_ftz(a0);   // e = inf for very negative z -> rcp gives 0
-                r1 = rcp_ftz(a1);
-              }
-              v[c] = fmaf(r0, rs0, nls * rs0);
-              v[c + 1] = fmaf(r1, rs1, nls * rs1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[c + j] = fmaf(r[j], rs[j], nls * rs[j]);
             }
           }
         }
+        KGEB_TRW(11, u);
         mbar_wait(&g_empty[bufi], gph ^ 1);  // MMA2 of this buffer's previous tile has finished reading it
+        KGEB_TRW(12, u);
         uint8_t* gb = g_smem + (size_t)bufi * G_BYTES;
         if (BF16) {
           // row trow of the single K-slab: this warp's 32 bf16 = chunks 4*sub .. 4*sub+3 (16 B each), 128-byte swizzle
@@ -366,6 +411,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         }
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive_warp(&g_full[bufi]);
+        KGEB_TRW(13, u);
         gph ^= 1;
       }
       if (STATS && res_row < p.B) {
@@ -797,3 +843,18 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
 }
 
 }  // namespace kgeb
+
+#ifdef KGEB_TRACE
+// tuning builds: copies the trace of block 0 to the host and resets it; returns the number of events
+extern "C" int kgeb_debug_trace(unsigned long long* host_dst, int max_n) {
+  // all 32 x 2048 slots (zero = unused); cleared for the next launch
+  const int n = 32 << 11;
+  if (max_n < n) return -1;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_dst, kgeb::tcb::g_trace, sizeof(unsigned long long) * n);
+  void* p = nullptr;
+  cudaGetSymbolAddress(&p, kgeb::tcb::g_trace);
+  cudaMemset(p, 0, sizeof(unsigned long long) * n);
+  return n;
+}
+#endif

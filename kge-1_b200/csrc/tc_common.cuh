@@ -54,9 +54,43 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The retry loop lives INSIDE the asm statement: to the compiler the wait is straight-line code, so a warp that only
+// waits and issues (the MMA issuers) stays in provably uniform control flow and its descriptor arithmetic runs on the
+// uniform datapath.  A C++ `while (!try_wait)` loop has a per-thread exit condition, after which the compiler treats
+// every value as potentially divergent (R2UR.BROADCAST of each tcgen05.mma operand, ~18 instructions per MMA).
+// KGEB_TRYWAIT_HINT_NS > 0: try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware until the phase
+// completes instead of returning (and re-issuing the probe) after the short default limit.  Every probe is a SYNCS
+// instruction in the MIO queue, the same queue the epilogues' MUFU / shared-memory instructions go through: the ncu source
+// view counted 2.0 M probes against 3.7 M MUFU instructions in one dTable launch (profiles/README.md).
+#ifndef KGEB_TRYWAIT_HINT_NS
+#define KGEB_TRYWAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+#if KGEB_TRYWAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"((uint32_t)KGEB_TRYWAIT_HINT_NS)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -156,6 +190,21 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
   if (BF16) umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
   else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
+// One lane of a converged warp (elect.sync; the same lane every time for the full mask).  Code predicated on it is
+// single-threaded *as far as the compiler knows*, so operands of the uniform-datapath instructions (tcgen05.mma
+// descriptors, commit addresses) are moved to uniform registers directly; under a plain `lane == 0` test every such
+// instruction is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -201,13 +250,15 @@ __device__ __forceinline__ float ex2_poly(float x) {
 #ifndef KGEB_POLY8_STATS
 #define KGEB_POLY8_STATS 0
 #endif
-// MUFU diet of the BCE epilogues (tc_bwd.cu, tc_dot.cu): reciprocals of two columns from one rcp of their product;
+// MUFU diet of the BCE epilogues (tc_bwd.cu, tc_dot.cu): reciprocals of 2 | 4 columns from one rcp of their product;
 // one lg2 per KGEB_LG2_GROUP columns (of the product of the 1 + e^-|z| factors) instead of one per column.
-#ifndef KGEB_RCP_PAIR
-#define KGEB_RCP_PAIR 0
+// Measured (bench.py, B=4096, tools/build_variant.sh): RCP_GROUP / LG2_GROUP = 1/1 158.7 us per step, 4/1 152.2,
+// 2/8 151.3, 4/16 148.9, 4/8 144.8 (dTable kernel alone 64.8 -> 58.4 us, dQ 62.4 -> 58.4 us).
+#ifndef KGEB_RCP_GROUP
+#define KGEB_RCP_GROUP 4
 #endif
 #ifndef KGEB_LG2_GROUP
-#define KGEB_LG2_GROUP 1
+#define KGEB_LG2_GROUP 8
 #endif
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {

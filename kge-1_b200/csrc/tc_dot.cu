@@ -105,7 +105,7 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (elect_one()) {   // single elected thread: see the MMA issuer
       int stage = 0;
       uint32_t phase = 0, qphase = 0;
       for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -130,7 +130,8 @@ tc_tiles_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // under one elect.sync predicate the compiler keeps the descriptors in uniform registers (tc_bwd.cu, MMA1 issuer)
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(TILE, TILE, 0, 0, Elem<BF16>::kFmt);
       int stage = 0, buf = 0;
       uint32_t phase = 0, qphase = 0, tphase[2] = {0, 0};

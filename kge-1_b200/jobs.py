@@ -130,14 +130,15 @@ class TrainingJobKvsAll(TrainingJob):
         self.stepper = None
 
     # -- static-shape, graph-captured step (trainer.py) ---------------------------------------------------
-    def enable_graph_step(self, batch_size: int, nnz_max: int, use_graph: bool = True, dp_group=None):
+    def enable_graph_step(self, batch_size: int, nnz_max: int, use_graph: bool = True, dp_group=None,
+                          dp_p2p: bool = False):
         """Routes step() through FusedAllEntityStepper for batches of exactly `batch_size` queries with at most
         `nnz_max` labels (no autograd, one CUDA-graph replay per step).  Needs the DOT scorers and dense Adagrad;
         unweighted Lp penalties are folded into the Adagrad kernels (the toy config's regularize_weight)."""
         from .trainer import FusedAllEntityStepper
         self.stepper = FusedAllEntityStepper(self.model, self.optimizer, batch_size, nnz_max, self.loss.kind,
                                              batch_size, self.loss.offset, self.label_smoothing, self.math_mode,
-                                             use_graph, self.shard, dp_group)
+                                             use_graph, self.shard, dp_group, dp_p2p)
         return self.stepper
 
     # -- on-device batch construction (SURVEY.md 8f-1): the host sends example ids only ----------------------------

@@ -67,12 +67,21 @@ SIGNATURES = {
     "kgeb_rank_hist": [_p, _p, _l, _l, _p, _p, _p],
     "kgeb_isin_sorted": [_p, _i, _l, _p, _l, _p, _p],
     "kgeb_rank_metrics": [_p, _l, _p, _i, _p, _p, _l, _p],
+    "kgeb_p2p_barrier": [_p, _i, _i, _p, _p, _p],
+    "kgeb_p2p_adagrad": [_p, _p, _i, _i, _p, _p, _p, _l, _f, _f, _p],
+    "kgeb_p2p_apply": [_p, _i, _i, _p, _p, _l, _p],
+    "kgeb_p2p_sum_scalar": [_p, _i, _p, _p],
 }
 
 
 class IndexDesc(ctypes.Structure):
     """kgeb_index_t of include/kgeb200.h: one KvsAllIndex resident on the device."""
     _fields_ = [("keys", _c.c_void_p), ("num_keys", _c.c_int64), ("offsets", _c.c_void_p), ("values", _c.c_void_p)]
+
+
+def ptr_array(ptrs) -> "ctypes.Array":
+    """Host array of device pointers (the `const void* const*` arguments of the kgeb_p2p_* entry points)."""
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
 
 
 def index_descs(arrays) -> "ctypes.Array":

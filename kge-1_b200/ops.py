@@ -375,7 +375,8 @@ class _LpPenaltyRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, weight, indexes, p, reg_weight):
         w = weight.detach()
-        iptr, i64 = lib.idx(indexes.contiguous(), "indexes")
+        indexes = indexes.contiguous()          # (a column view of the triples: keep the copy alive across the call)
+        iptr, i64 = lib.idx(indexes, "indexes")
         value = torch.empty(1, dtype=torch.float32, device=w.device)
         ws = _penalty_ws(w.device, indexes.numel(), 0)
         lib.call("kgeb_lp_penalty_rows", lib.f32(w, "weight"), w.shape[0], w.shape[1], iptr, i64, indexes.numel(), int(p),
@@ -388,7 +389,7 @@ class _LpPenaltyRows(torch.autograd.Function):
     def backward(ctx, gout):
         weight, indexes = ctx.saved_tensors
         w = weight.detach()
-        iptr, i64 = lib.idx(indexes.contiguous(), "indexes")
+        iptr, i64 = lib.idx(indexes, "indexes")     # made contiguous in forward
         grad = torch.zeros_like(w)
         value = torch.empty(1, dtype=torch.float32, device=w.device)
         ws = _penalty_ws(w.device, indexes.numel(), 0)

@@ -22,7 +22,7 @@ from .model import KgeModel
 class FusedAllEntityStepper:
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
-                 use_graph: bool = True, shard: Optional[fused.Shard] = None, dp_group=None):
+                 use_graph: bool = True, shard: Optional[fused.Shard] = None, dp_group=None, dp_p2p: bool = False):
         if model.get_scorer().kind != lib.DOT:
             raise NotImplementedError("the fused all-entity step serves the DOT scorers")
         self.model, self.opt = model, optimizer
@@ -75,7 +75,11 @@ class FusedAllEntityStepper:
         # gradients and the loss live in ONE flat buffer so that data-parallel replicas need a single all-reduce
         n_e, n_r = self.E * self.d, self.rel.shape[0] * self.dr
         # layout [g_q | g_ent | g_rel | loss]: data-parallel replicas fold g_q into g_ent and all-reduce the tail only
-        self.gflat = torch.zeros(2 * n_e + n_r + 1, **f32)
+        self.p2p = None
+        if dp_group is not None and dp_p2p:
+            self._setup_p2p(dp_group, n_e, n_r, dev)      # gradients live in peer-mapped (symmetric) memory
+        else:
+            self.gflat = torch.zeros(2 * n_e + n_r + 1, **f32)
         self.g_q = self.gflat[:n_e].view(self.E, self.d)              # query-side rows (da scattered by entity id)
         self.g_ent = self.gflat[n_e:2 * n_e].view(self.E, self.d)     # dense part (G^T Q) + label rows (side stream)
         self.g_rel = self.gflat[2 * n_e:2 * n_e + n_r].view(self.rel.shape[0], self.dr)
@@ -231,6 +235,77 @@ class FusedAllEntityStepper:
                      ent.numel(), self.lr, self.eps, 0.0, mirror, st)
         cur.wait_stream(self.side2)
 
+    # -- data-parallel exchange fused with the update over NVLink peer memory (csrc/p2p.cu) ---------------------------
+    def _setup_p2p(self, group, n_e: int, n_r: int, dev):
+        """Gradient buffer, staging buffer (updated weights pushed by the slice owners) and signal pads in torch symmetric
+        memory: cuMem allocations that every process of the node maps, so kernels address the peers' copies directly."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if n_e % 4 or n_r % 4:
+            raise NotImplementedError("peer-memory exchange needs table sizes that are multiples of 4 elements")
+        self.gflat = symm.empty(2 * n_e + n_r + 1, dtype=torch.float32, device=dev)
+        hg = symm.rendezvous(self.gflat, group)
+        self.p2p_stage = symm.empty(n_e + n_r, dtype=torch.float32, device=dev)
+        hs = symm.rendezvous(self.p2p_stage, group)
+        self.p2p_pad = symm.empty(64, dtype=torch.int32, device=dev)
+        hp = symm.rendezvous(self.p2p_pad, group)
+        self.gflat.zero_(); self.p2p_stage.zero_(); self.p2p_pad.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group)                 # nobody signals before every pad is zero
+        world = hg.world_size
+        gp, sp = [int(x) for x in hg.buffer_ptrs], [int(x) for x in hs.buffer_ptrs]
+        self.p2p = dict(rank=hg.rank, world=world, handles=(hg, hs, hp),
+                        g_ent=lib.ptr_array([x + 4 * n_e for x in gp]), g_rel=lib.ptr_array([x + 8 * n_e for x in gp]),
+                        loss=lib.ptr_array([x + 4 * (2 * n_e + n_r) for x in gp]),
+                        st_ent=lib.ptr_array(sp), st_rel=lib.ptr_array([x + 4 * n_e for x in sp]),
+                        pads=lib.ptr_array([int(x) for x in hp.buffer_ptrs]))
+        self.p2p_epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.p2p_timeout = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_global = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def _stage_exchange_p2p(self):
+        """barrier ; reduce + Adagrad on the owned slice + push of the new weights ; barrier ; apply the peers' slices.
+        Plain kernels on peer pointers: captured in the same CUDA graph as the compute stages."""
+        st = lib.stream_ptr(self.ent)
+        x = self.p2p
+        ent, rel = self.ent.detach(), self.rel.detach()
+        s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
+        mirror = None if self.mirror is None else self.mirror.data_ptr()
+        n_e = ent.numel()
+        bar = lambda: lib.call("kgeb_p2p_barrier", x["pads"], x["rank"], x["world"], self.p2p_epoch.data_ptr(),  # noqa: E731
+                               self.p2p_timeout.data_ptr(), st)
+        bar()
+        lib.call("kgeb_p2p_adagrad", x["g_rel"], x["st_rel"], x["rank"], x["world"], rel.data_ptr(), s_rel.data_ptr(), None,
+                 rel.numel(), self.lr, self.eps, st)
+        lib.call("kgeb_p2p_adagrad", x["g_ent"], x["st_ent"], x["rank"], x["world"], ent.data_ptr(), s_ent.data_ptr(), mirror,
+                 n_e, self.lr, self.eps, st)
+        lib.call("kgeb_p2p_sum_scalar", x["loss"], x["world"], self.loss_global.data_ptr(), st)
+        bar()
+        lib.call("kgeb_p2p_apply", self.p2p_stage.data_ptr(), x["rank"], x["world"], ent.data_ptr(), mirror, n_e, st)
+        lib.call("kgeb_p2p_apply", self.p2p_stage[n_e:].data_ptr(), x["rank"], x["world"], rel.data_ptr(), None, rel.numel(), st)
+
+    def check_p2p(self):
+        """Host check (one sync): no peer-memory barrier ran into its timeout."""
+        if self.p2p is not None and int(self.p2p_timeout.item()) != 0:
+            raise RuntimeError("a peer did not arrive at a peer-memory barrier")
+
+    def sync_optimizer_state(self):
+        """Peer-memory mode shards the Adagrad state by slice owner: gather the slices so that every rank holds the
+        complete accumulators again (checkpoints; switching modes)."""
+        if self.p2p is None:
+            return
+        import torch.distributed as dist
+        x = self.p2p
+        for t in (self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]):
+            flat = t.view(-1)
+            n = flat.numel()
+            per = ((n + 4 * x["world"] - 1) // (4 * x["world"])) * 4
+            ranks = dist.get_process_group_ranks(self.dp_group)
+            for r in range(x["world"]):
+                lo, hi = min(n, per * r), min(n, per * r + per)
+                if hi > lo:
+                    dist.broadcast(flat[lo:hi], src=ranks[r], group=self.dp_group)
+
     def _stage_apply_dp(self):
         """Data-parallel mode: both Adagrad steps after the gradient all-reduce."""
         st = lib.stream_ptr(self.ent)
@@ -267,7 +342,9 @@ class FusedAllEntityStepper:
         self._stage_backward()
         self._exchange_grads()
         self._stage_update()
-        if self.dp_world > 1:
+        if self.p2p is not None:
+            self._stage_exchange_p2p()
+        elif self.dp_world > 1:
             self._exchange_dp()
             self._stage_apply_dp()
 
@@ -292,7 +369,9 @@ class FusedAllEntityStepper:
         torch.cuda.synchronize()
         self.graphs = []
         whole = lambda: (self._stage_forward(), self._stage_backward(), self._stage_update())
-        if self.shard.distributed:
+        if self.p2p is not None:
+            stages = [lambda: (whole(), self._stage_exchange_p2p())]     # compute + exchange + update: ONE graph
+        elif self.shard.distributed:
             stages = [self._stage_forward, self._stage_backward, self._stage_update]
         elif self.dp_world > 1:
             stages = [whole, self._stage_apply_dp]
@@ -388,7 +467,7 @@ class FusedAllEntityStepper:
             st["step"] += 1
         torch.autograd.graph.increment_version(self.ent)
         torch.autograd.graph.increment_version(self.rel)
-        return self.loss
+        return self.loss if self.p2p is None else self.loss_global
 
 
 class RowShardedAllEntityStepper:

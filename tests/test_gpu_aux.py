@@ -207,7 +207,7 @@ def test_adagrad_with_fused_penalty_equals_penalty_then_adagrad(kb, p):
     ws = torch.empty(L.kgeb_penalty_workspace_bytes(0, n * d), dtype=torch.uint8, device="cuda")
     kb.lib.call("kgeb_adagrad_dense_lp", w.data_ptr(), state.data_ptr(), grad.cuda().data_ptr(), None, n * d, 0.1, 1e-10, 0.0,
                 p, lam, mirror.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), kb.lib.stream_ptr(w))
-    assert out.item() == pytest.approx(value.item(), rel=2e-6)
+    assert out.item() == pytest.approx(value.item(), rel=1e-5)
     np.testing.assert_allclose(state.cpu().numpy(), opt.state[wref]["sum"].numpy(), rtol=1e-5, atol=1e-12)
     np.testing.assert_allclose(w.cpu().numpy(), wref.detach().numpy(), rtol=0, atol=2e-6)
     assert torch.equal(mirror, w.bfloat16())
@@ -295,13 +295,16 @@ def test_captured_kvsall_step_with_fused_penalty_matches_autograd_flow(kb, p):
     ref = kb.KgeModel("complex", e, r, d, **reg).cuda()
     new = kb.KgeModel("complex", e, r, d, **reg).cuda()
     new.load_state_dict(ref.state_dict())
-    jr = kb.TrainingJobKvsAll(ref, kb.optim.create("Adagrad", ref.parameters(), lr=0.2), kb.KgeLoss.create("kl"), e, r)
-    jn = kb.TrainingJobKvsAll(new, kb.optim.create("Adagrad", new.parameters(), lr=0.2), kb.KgeLoss.create("kl"), e, r)
+    # a non-zero initial accumulator: with sum = 0 the first Adagrad step is lr * g / (|g| + 1e-10), which turns the
+    # ~1e-8 summation-order differences between the two loss-gradient paths into O(lr) differences wherever g ~ 0
+    mk = lambda m: kb.optim.create("Adagrad", m.parameters(), lr=0.2, initial_accumulator_value=0.1)  # noqa: E731
+    jr = kb.TrainingJobKvsAll(ref, mk(ref), kb.KgeLoss.create("kl"), e, r)
+    jn = kb.TrainingJobKvsAll(new, mk(new), kb.KgeLoss.create("kl"), e, r)
     jn.enable_graph_step(b, nnz_max, use_graph=True)
     for i, batch in enumerate(batches):
         a, c = jr.step(i, batch), jn.step(i, batch)
         assert c.avg_loss == pytest.approx(a.total_loss, rel=1e-5)
-        assert c.penalty == pytest.approx(a.penalty, rel=1e-5) and a.penalty > 0
+        assert c.penalty == pytest.approx(a.penalty, rel=2e-5) and a.penalty > 0
         for got, want in ((new.get_s_embedder().weight, ref.get_s_embedder().weight),
                           (new.get_p_embedder().weight, ref.get_p_embedder().weight)):
             err = (got - want).abs().max().item()
