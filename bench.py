@@ -393,7 +393,8 @@ def step_timeline(job, stepper, batches, flush):
     evs = evs[last + 1:]
     t0 = evs[0].time_range.start
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "timeline_bench.txt"), "w") as f:
+    rank = int(os.environ.get("RANK", "0"))
+    with open(os.path.join(ROOT, "gpurun_out", "timeline_bench.txt" if rank == 0 else f"timeline_bench_rank{rank}.txt"), "w") as f:
         f.write("# start_us  dur_us  end_us  name   (one CUDA-graph replay of the training step)\n")
         for e in evs:
             st = e.time_range.start - t0

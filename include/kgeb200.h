@@ -109,6 +109,20 @@ int kgeb_score_all_bwd(int kind, const float* Q, int64_t B, int d, const float* 
                        int idx64, int64_t m, const float* G, const float* X, int64_t ld, int64_t col_off,
                        float* dQ, float* dC, void* stream);
 
+/* The sparse label part of kgeb_fused_bwd's dense table gradient on its own: for every label entry (row q, entity e)
+ * dTable_out[e - e_lo, :] += -inv_batch * grad_scale[q] * t_q * Q[q, :]  (t_q as in kgeb_fused_bwd; fixed-order segment
+ * sums, lab_perm as there).  A caller that sends these rows to a second gradient buffer and calls kgeb_fused_bwd with
+ * nnz = 0 for the dense part removes the label chain from the tile kernel's critical path (the optimizer adds the two
+ * buffers anyway, kgeb_adagrad_dense grad / grad2).  Workspace: kgeb_fused_workspace_bytes(B, d, e_hi - e_lo, nnz). */
+/* Makes `stream` wait for the dQ tile kernel of the calling thread's most recent kgeb_fused_bwd(dQ != NULL, bf16 tiles)
+ * on this device -- not for the small reduction kernels that follow it: a second persistent tile kernel (the dense
+ * dTable half) queued on `stream` starts the moment the first one releases the SMs.  Event wait: capturable. */
+int kgeb_fused_bwd_wait_tiles(void* stream);
+int kgeb_fused_label_rows(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
+                          const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const int32_t* lab_perm,
+                          float label_smoothing, float inv_batch, const float* grad_scale, float* dTable_out,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- K4+K8+K9 fused all-entity training (DOT kinds): scores are never materialised.
  * Labels are a CSR over the batch rows: lab_off[B+1] (int64), lab_col[nnz] (int64, ascending within a
  * row, entity ids).  For 1vsAll each row has exactly one label.  Targets t_ij:
@@ -298,19 +312,23 @@ int kgeb_rank_metrics(const float* hist, int64_t num_entities, const int32_t* hi
 /* ---- 8e (replicas row): data-parallel gradient exchange fused with the Adagrad update over NVLink peer memory.
  * All pointer arrays are HOST arrays of `world` device pointers, entry k = rank k's buffer mapped into this process
  * (torch symmetric memory / cuMem VMM + IPC).  Replaces  all-reduce(grad) ; torch.optim.Adagrad.step  (train.py:375)
- * of replicated training.  Sequence per step and table:  barrier ; p2p_adagrad ; barrier ; p2p_apply.
- * p2p_barrier: signal pad of rank k = uint32[world]; *epoch (local device counter) is advanced by one; *timeout_flag is
- *   set if a peer does not arrive within ~10 s (a dead peer must not hang the GPU).
- * p2p_adagrad: rank r reduces its slice of the gradient over all ranks in rank order, updates its slice of W / state /
- *   bf16 mirror and stores the new values into every peer's staging buffer.
- * p2p_apply:   copies the other owners' slices from the local staging buffer into W (+ mirror).
- * p2p_sum_scalar: out[0] = sum_k peer_values[k][0] in rank order (the loss of the global batch). */
-int kgeb_p2p_barrier(const void* const* peer_signal_pads, int rank, int world, uint32_t* epoch, uint32_t* timeout_flag,
-                     void* stream);
-int kgeb_p2p_adagrad(const void* const* peer_grads, const void* const* peer_stage, int rank, int world, float* W,
-                     float* state, void* bf16_mirror, int64_t numel, float clr, float eps, void* stream);
-int kgeb_p2p_apply(const float* stage, int rank, int world, float* W, void* bf16_mirror, int64_t numel, void* stream);
-int kgeb_p2p_sum_scalar(const void* const* peer_values, int world, float* out, void* stream);
+ * of replicated training with two kernels per step, capturable in the step's CUDA graph:
+ * p2p_exchange: [barrier: every rank's gradients are complete]  rank r reduces its slice of each table's gradient over
+ *   all ranks in rank order, updates its slice of W / state / bf16 mirror and stores the new values into every peer's
+ *   staging buffer; loss_out[0] = sum of the ranks' losses.  peer_flat[k] = rank k's [g_table0 | g_table1 | loss],
+ *   peer_stage[k] = rank k's [W_table0 | W_table1] staging buffer.
+ * p2p_apply:    [barrier: all pushes have landed]  copies the other owners' slices from the local staging buffer into
+ *   the tables (+ mirror) and advances *ctr.
+ * Signal pad of rank k = uint32[world] (zero-initialised); *ctr = completed steps (device, zero-initialised), the two
+ * barriers of step s use the values 2s+1 and 2s+2; *ticket = 0; *timeout_flag is set if a peer does not arrive within
+ * ~10 s (a dead peer must not hang the GPU). */
+int kgeb_p2p_exchange(const void* const* peer_pads, const void* const* peer_flat, const void* const* peer_stage, int rank,
+                      int world, const uint32_t* ctr, uint32_t* timeout_flag, float* W0, float* state0, void* mirror0,
+                      int64_t numel0, float* W1, float* state1, int64_t numel1, float* loss_out, float clr, float eps,
+                      void* stream);
+int kgeb_p2p_apply(const void* const* peer_pads, const float* stage, int rank, int world, uint32_t* ctr, uint32_t* ticket,
+                   uint32_t* timeout_flag, float* W0, void* mirror0, int64_t numel0, float* W1, int64_t numel1,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,18 +47,19 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr) {
   return v;
 }
 
-// <<<1, world>>>: thread t talks to peer t.  *epoch (local) is the last completed barrier number.
-__global__ void p2p_barrier_kernel(PeerPtrs pads, int rank, int world, uint32_t* epoch, uint32_t* timeout_flag) {
+// Barrier inside a kernel: block 0 signals (this GPU has finished everything that precedes this kernel on its stream),
+// every block waits until all peers signalled epoch e.  Bounded spin (~10 s): a dead peer must not hang the GPU.
+__device__ __forceinline__ void grid_peer_barrier(const PeerPtrs& pads, int rank, int world, uint32_t e, uint32_t* timeout_flag) {
   const int t = threadIdx.x;
-  const uint32_t e = *epoch + 1;
-  __threadfence_system();   // everything this GPU wrote before the barrier (incl. peer stores) is visible system-wide
-  if (t < world) {
+  if (blockIdx.x == 0 && t < world) {
+    __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(pads.p[t]) + rank, e);
+  }
+  if (t < world) {
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(pads.p[rank]) + t;
-    // bounded spin (~10 s): a peer that died must not hang this GPU until the watchdog of the job runner fires
     long long spins = 0;
     while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
-      __nanosleep(64);
+      __nanosleep(32);
       if (++spins > (1ll << 23)) {
         *timeout_flag = 1;
         break;
@@ -66,7 +67,6 @@ __global__ void p2p_barrier_kernel(PeerPtrs pads, int rank, int world, uint32_t*
     }
   }
   __syncthreads();
-  if (t == 0) *epoch = e;
 }
 
 __host__ __device__ inline void slice_of(int64_t numel, int world, int r, int64_t& lo, int64_t& hi) {
@@ -75,90 +75,113 @@ __host__ __device__ inline void slice_of(int64_t numel, int world, int r, int64_
   hi = lo + per < numel ? lo + per : numel;
 }
 
-// reduce + Adagrad on the owner's slice, push of the new values to every peer's staging buffer.
-// grads.p[k] / stage.p[k]: rank k's buffers of this table (float, numel each, 16-byte aligned).
+struct Table {
+  float* W;
+  float* state;
+  __nv_bfloat16* mirror;   // or NULL
+  int64_t numel;           // multiple of 4
+  int64_t flat_off;        // offset of this table's gradient in the exchanged flat buffer / of its weights in staging
+};
+
+__device__ __forceinline__ void adagrad4(float4& w, float4& s, const float4& g, float clr, float eps) {
+  s.x = fmaf(g.x, g.x, s.x); s.y = fmaf(g.y, g.y, s.y); s.z = fmaf(g.z, g.z, s.z); s.w = fmaf(g.w, g.w, s.w);
+  w.x -= clr * g.x / (sqrtf(s.x) + eps);
+  w.y -= clr * g.y / (sqrtf(s.y) + eps);
+  w.z -= clr * g.z / (sqrtf(s.z) + eps);
+  w.w -= clr * g.w / (sqrtf(s.w) + eps);
+}
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* dst, const float4& w) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(w.x, w.y), b = __floats2bfloat162_rn(w.z, w.w);
+  uint2 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a);
+  o.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(dst) = o;
+}
+
+constexpr int kUnroll = 4;   // independent float4 groups per thread: remote loads are ~2 us away, keep many in flight
+
+// Exchange kernel.  epoch counter *ctr = number of completed steps; this kernel's barrier uses 2*ctr + 1.
+//   flat.p[k]  : rank k's [g_table0 | g_table1 | ... | loss] buffer;  stage.p[k] : rank k's [W_table0 | W_table1 ...]
 __global__ void __launch_bounds__(256)
-p2p_adagrad_kernel(PeerPtrs grads, PeerPtrs stage, int rank, int world, float* __restrict__ W, float* __restrict__ state,
-                   __nv_bfloat16* __restrict__ mirror, int64_t numel, float clr, float eps) {
-  int64_t lo, hi;
-  slice_of(numel, world, rank, lo, hi);
-  const int64_t n4 = (hi - lo) / 4;           // full float4 groups; the slice start is a multiple of 4
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = lo + q * 4;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < world; ++k) {         // fixed order: the same sum on whichever rank owns the slice
-      const float4 h = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[k]) + i);
-      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
-    }
-    float4 w = *reinterpret_cast<float4*>(W + i);
-    float4 s = *reinterpret_cast<float4*>(state + i);
-    s.x = fmaf(g.x, g.x, s.x); s.y = fmaf(g.y, g.y, s.y); s.z = fmaf(g.z, g.z, s.z); s.w = fmaf(g.w, g.w, s.w);
-    w.x -= clr * g.x / (sqrtf(s.x) + eps);
-    w.y -= clr * g.y / (sqrtf(s.y) + eps);
-    w.z -= clr * g.z / (sqrtf(s.z) + eps);
-    w.w -= clr * g.w / (sqrtf(s.w) + eps);
-    *reinterpret_cast<float4*>(W + i) = w;
-    *reinterpret_cast<float4*>(state + i) = s;
-    if (mirror) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(w.x, w.y), b = __floats2bfloat162_rn(w.z, w.w);
-      uint2 o;
-      o.x = *reinterpret_cast<uint32_t*>(&a);
-      o.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(mirror + i) = o;
-    }
-    for (int k = 0; k < world; ++k)
-      if (k != rank) *reinterpret_cast<float4*>(reinterpret_cast<float*>(stage.p[k]) + i) = w;
+p2p_exchange_kernel(PeerPtrs pads, PeerPtrs flat, PeerPtrs stage, int rank, int world, const uint32_t* __restrict__ ctr,
+                    uint32_t* timeout_flag, Table t0, Table t1, int64_t loss_off, float* __restrict__ loss_out, float clr,
+                    float eps) {
+  grid_peer_barrier(pads, rank, world, 2u * *ctr + 1u, timeout_flag);     // every rank's gradients are complete
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) {
+    float a = 0.f;
+    for (int k = 0; k < world; ++k) a += reinterpret_cast<const float*>(flat.p[k])[loss_off];
+    *loss_out = a;
   }
-  // tail of the LAST slice only (numel % 4 elements), by one thread
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int64_t i = lo + n4 * 4; i < hi; ++i) {
-      float g = 0.f;
-      for (int k = 0; k < world; ++k) g += reinterpret_cast<const float*>(grads.p[k])[i];
-      const float s = fmaf(g, g, state[i]);
-      state[i] = s;
-      const float w = W[i] - clr * g / (sqrtf(s) + eps);
-      W[i] = w;
-      if (mirror) mirror[i] = __float2bfloat16_rn(w);
-      for (int k = 0; k < world; ++k)
-        if (k != rank) reinterpret_cast<float*>(stage.p[k])[i] = w;
+#pragma unroll 1
+  for (int ti = 0; ti < 2; ++ti) {
+    const Table& tb = ti == 0 ? t0 : t1;
+    if (tb.numel == 0) continue;
+    int64_t lo, hi;
+    slice_of(tb.numel, world, rank, lo, hi);
+    const int64_t n4 = (hi - lo) / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q0 < n4; q0 += stride * kUnroll) {
+      float4 g[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < world; ++k) {         // rank order: the same sum whichever rank owns the slice
+        const float* src = reinterpret_cast<const float*>(flat.p[k]) + tb.flat_off + lo;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int64_t q = q0 + u * stride;
+          if (q < n4) {
+            const float4 h = *reinterpret_cast<const float4*>(src + q * 4);
+            g[u].x += h.x; g[u].y += h.y; g[u].z += h.z; g[u].w += h.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t q = q0 + u * stride;
+        if (q >= n4) continue;
+        const int64_t i = lo + q * 4;
+        float4 w = *reinterpret_cast<float4*>(tb.W + i);
+        float4 s = *reinterpret_cast<float4*>(tb.state + i);
+        adagrad4(w, s, g[u], clr, eps);
+        *reinterpret_cast<float4*>(tb.W + i) = w;
+        *reinterpret_cast<float4*>(tb.state + i) = s;
+        if (tb.mirror) store_bf16x4(tb.mirror + i, w);
+        for (int k = 0; k < world; ++k)
+          if (k != rank) *reinterpret_cast<float4*>(reinterpret_cast<float*>(stage.p[k]) + tb.flat_off + i) = w;
+      }
     }
   }
 }
 
-// after barrier B: the slices owned by the other ranks, from the local staging buffer into the table (+ mirror)
+// Apply kernel: barrier 2*ctr + 2 (all pushes have landed), then the other owners' slices from the local staging
+// buffer into the tables (+ mirror); the last block to finish advances *ctr (every block has read it by then).
 __global__ void __launch_bounds__(256)
-p2p_apply_kernel(const float* __restrict__ stage, int rank, int world, float* __restrict__ W,
-                 __nv_bfloat16* __restrict__ mirror, int64_t numel) {
-  int64_t lo, hi;
-  slice_of(numel, world, rank, lo, hi);
-  const int64_t n4 = numel / 4;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = q * 4;
-    if (i >= lo && i < hi) continue;            // own slice: already updated in place (slice bounds are multiples of 4)
-    const float4 w = *reinterpret_cast<const float4*>(stage + i);
-    *reinterpret_cast<float4*>(W + i) = w;
-    if (mirror) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(w.x, w.y), b = __floats2bfloat162_rn(w.z, w.w);
-      uint2 o;
-      o.x = *reinterpret_cast<uint32_t*>(&a);
-      o.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(mirror + i) = o;
+p2p_apply_kernel(PeerPtrs pads, const float* __restrict__ stage, int rank, int world, uint32_t* ctr, uint32_t* ticket,
+                 uint32_t* timeout_flag, Table t0, Table t1) {
+  grid_peer_barrier(pads, rank, world, 2u * *ctr + 2u, timeout_flag);
+#pragma unroll 1
+  for (int ti = 0; ti < 2; ++ti) {
+    const Table& tb = ti == 0 ? t0 : t1;
+    if (tb.numel == 0) continue;
+    int64_t lo, hi;
+    slice_of(tb.numel, world, rank, lo, hi);
+    const int64_t n4 = tb.numel / 4;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = q * 4;
+      if (i >= lo && i < hi) continue;          // own slice: updated in place by the exchange kernel
+      const float4 w = *reinterpret_cast<const float4*>(stage + tb.flat_off + i);
+      *reinterpret_cast<float4*>(tb.W + i) = w;
+      if (tb.mirror) store_bf16x4(tb.mirror + i, w);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int64_t i = n4 * 4; i < numel; ++i) {
-      if (i >= lo && i < hi) continue;
-      W[i] = stage[i];
-      if (mirror) mirror[i] = __float2bfloat16_rn(stage[i]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0;
+      *ctr = *ctr + 1;
     }
   }
-}
-
-// out[0] = sum over ranks of values.p[k][0], in rank order (the loss of the global batch)
-__global__ void p2p_sum_scalar_kernel(PeerPtrs values, int world, float* out) {
-  float a = 0.f;
-  for (int k = 0; k < world; ++k) a += *reinterpret_cast<const float*>(values.p[k]);
-  *out = a;
 }
 
 static int fill_ptrs(PeerPtrs& pp, const void* const* host_ptrs, int world) {
@@ -172,57 +195,49 @@ using namespace kgeb;
 
 extern "C" {
 
-int kgeb_p2p_barrier(const void* const* peer_signal_pads, int rank, int world, uint32_t* epoch, uint32_t* timeout_flag,
-                     void* stream) {
-  KGEB_REQUIRE(peer_signal_pads && epoch && timeout_flag && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
-               "p2p_barrier: bad arguments");
-  PeerPtrs pads;
-  fill_ptrs(pads, peer_signal_pads, world);
-  p2p_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pads, rank, world, epoch, timeout_flag);
-  KGEB_LAUNCH_CHECK("p2p_barrier");
-  return KGEB_OK;
-}
-
-int kgeb_p2p_adagrad(const void* const* peer_grads, const void* const* peer_stage, int rank, int world, float* W,
-                     float* state, void* bf16_mirror, int64_t numel, float clr, float eps, void* stream) {
-  KGEB_REQUIRE(peer_grads && peer_stage && W && state && numel >= 0 && world >= 1 && world <= kMaxWorld && rank >= 0 &&
-                   rank < world,
-               "p2p_adagrad: bad arguments");
-  PeerPtrs g, s;
-  fill_ptrs(g, peer_grads, world);
-  fill_ptrs(s, peer_stage, world);
-  uintptr_t bits = reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(bf16_mirror);
-  for (int k = 0; k < world; ++k) bits |= reinterpret_cast<uintptr_t>(g.p[k]) | reinterpret_cast<uintptr_t>(s.p[k]);
-  KGEB_REQUIRE((bits & 15) == 0, "p2p_adagrad: pointers must be 16-byte aligned");
-  if (numel == 0) return KGEB_OK;
+int kgeb_p2p_exchange(const void* const* peer_pads, const void* const* peer_flat, const void* const* peer_stage, int rank,
+                      int world, const uint32_t* ctr, uint32_t* timeout_flag, float* W0, float* state0, void* mirror0,
+                      int64_t numel0, float* W1, float* state1, int64_t numel1, float* loss_out, float clr, float eps,
+                      void* stream) {
+  KGEB_REQUIRE(peer_pads && peer_flat && peer_stage && ctr && timeout_flag && W0 && state0 && numel0 >= 0 && numel1 >= 0 &&
+                   (numel1 == 0 || (W1 && state1)) && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
+               "p2p_exchange: bad arguments");
+  KGEB_REQUIRE(numel0 % 4 == 0 && numel1 % 4 == 0, "p2p_exchange: table sizes must be multiples of 4 elements");
+  PeerPtrs pads, flat, stage;
+  fill_ptrs(pads, peer_pads, world);
+  fill_ptrs(flat, peer_flat, world);
+  fill_ptrs(stage, peer_stage, world);
+  uintptr_t bits = reinterpret_cast<uintptr_t>(W0) | reinterpret_cast<uintptr_t>(state0) | reinterpret_cast<uintptr_t>(mirror0) |
+                   reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(state1);
+  for (int k = 0; k < world; ++k) bits |= reinterpret_cast<uintptr_t>(flat.p[k]) | reinterpret_cast<uintptr_t>(stage.p[k]);
+  KGEB_REQUIRE((bits & 15) == 0, "p2p_exchange: pointers must be 16-byte aligned");
+  Table t0{W0, state0, reinterpret_cast<__nv_bfloat16*>(mirror0), numel0, 0};
+  Table t1{W1, state1, nullptr, numel1, numel0};
   int64_t lo, hi;
-  slice_of(numel, world, rank, lo, hi);
-  int64_t blocks = ((hi - lo) / 4 + 255) / 256 + 1;
-  const int grid = (int)(blocks > (int64_t)kNumSMs * 4 ? (int64_t)kNumSMs * 4 : blocks);
-  p2p_adagrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, s, rank, world, W, state,
-                                                         reinterpret_cast<__nv_bfloat16*>(bf16_mirror), numel, clr, eps);
-  KGEB_LAUNCH_CHECK("p2p_adagrad");
+  slice_of(numel0, world, rank, lo, hi);
+  int64_t blocks = ((hi - lo) / 4 + 256 * kUnroll - 1) / (256 * kUnroll) + 1;
+  const int grid = (int)(blocks > (int64_t)kNumSMs * 4 ? (int64_t)kNumSMs * 4 : blocks);   // all blocks co-resident
+  p2p_exchange_kernel<<<grid, 256, 0, as_stream(stream)>>>(pads, flat, stage, rank, world, ctr, timeout_flag, t0, t1,
+                                                          numel0 + numel1, loss_out, clr, eps);
+  KGEB_LAUNCH_CHECK("p2p_exchange");
   return KGEB_OK;
 }
 
-int kgeb_p2p_apply(const float* stage, int rank, int world, float* W, void* bf16_mirror, int64_t numel, void* stream) {
-  KGEB_REQUIRE(stage && W && numel >= 0 && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
+int kgeb_p2p_apply(const void* const* peer_pads, const float* stage, int rank, int world, uint32_t* ctr, uint32_t* ticket,
+                   uint32_t* timeout_flag, float* W0, void* mirror0, int64_t numel0, float* W1, int64_t numel1,
+                   void* stream) {
+  KGEB_REQUIRE(peer_pads && stage && ctr && ticket && timeout_flag && W0 && numel0 >= 0 && numel1 >= 0 &&
+                   (numel1 == 0 || W1) && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
                "p2p_apply: bad arguments");
-  if (numel == 0 || world == 1) return KGEB_OK;
-  int64_t blocks = (numel / 4 + 255) / 256 + 1;
+  KGEB_REQUIRE(numel0 % 4 == 0 && numel1 % 4 == 0, "p2p_apply: table sizes must be multiples of 4 elements");
+  PeerPtrs pads;
+  fill_ptrs(pads, peer_pads, world);
+  Table t0{W0, nullptr, reinterpret_cast<__nv_bfloat16*>(mirror0), numel0, 0};
+  Table t1{W1, nullptr, nullptr, numel1, numel0};
+  int64_t blocks = (numel0 / 4 + 255) / 256 + 1;
   const int grid = (int)(blocks > (int64_t)kNumSMs * 4 ? (int64_t)kNumSMs * 4 : blocks);
-  p2p_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(stage, rank, world, W, reinterpret_cast<__nv_bfloat16*>(bf16_mirror),
-                                                       numel);
+  p2p_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(pads, stage, rank, world, ctr, ticket, timeout_flag, t0, t1);
   KGEB_LAUNCH_CHECK("p2p_apply");
-  return KGEB_OK;
-}
-
-int kgeb_p2p_sum_scalar(const void* const* peer_values, int world, float* out, void* stream) {
-  KGEB_REQUIRE(peer_values && out && world >= 1 && world <= kMaxWorld, "p2p_sum_scalar: bad arguments");
-  PeerPtrs v;
-  fill_ptrs(v, peer_values, world);
-  p2p_sum_scalar_kernel<<<1, 1, 0, as_stream(stream)>>>(v, world, out);
-  KGEB_LAUNCH_CHECK("p2p_sum_scalar");
   return KGEB_OK;
 }
 

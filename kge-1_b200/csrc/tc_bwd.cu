@@ -716,6 +716,7 @@ int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz) {
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t tiles = nullptr;   // recorded right after the dQ tile kernel (kgeb_fused_bwd_wait_tiles)
 };
 // which: 0 for calls that produce dQ, 1 for dTable-only calls -- the two halves of a step are issued as two calls on
 // two streams (trainer.py) and must not queue behind each other's label chains
@@ -727,7 +728,8 @@ static SideStream* side_stream(int which) {
   if (!s.stream) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.tiles, cudaEventDisableTiming) != cudaSuccess)
       return nullptr;
   }
   return &s;
@@ -803,6 +805,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       if ((rc = make_map(&m_res, Qb, B, d, RES_ROWS, true)) || (rc = make_map(&m_str, tableb, n_ent, d, STR_ROWS, true))) return rc;
       const int64_t jobs = pl.p.n_res_blocks * pl.p.chunks;
       if ((rc = launch_bwd<true>(pl, m_res, m_str, m_res, jobs, st))) return rc;
+      if (SideStream* s0 = side_stream(0)) cudaEventRecord(s0->tiles, st);   // the SMs are free again from here on
       if (!joined) {
         cudaError_t e = cudaStreamWaitEvent(st, ss->join, 0);
         if (e != cudaSuccess) return cuda_status(e, "fused_bwd join wait");
@@ -839,6 +842,35 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
   } else if (dQ && B > 0) {
     cudaMemsetAsync(dQ, 0, (size_t)B * d * 4, st);
   }
+  return KGEB_OK;
+}
+
+// The sparse label part of the dense table gradient on its own (kgeb_fused_label_rows): lets a caller route the label
+// rows into a different buffer than the tile kernel's output, so that the tile kernel does not have to wait for them.
+int tc_label_rows(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent, const int64_t* lab_off,
+                  const int64_t* lab_col, int64_t nnz, const int32_t* lab_perm, const float* tscale, const float* row_scale,
+                  float inv_batch, float* dense_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  using namespace tcb;
+  if (nnz <= 0 || n_ent <= 0 || B <= 0) return KGEB_OK;
+  char* wp = reinterpret_cast<char*>(ws);
+  float* rows_dt = reinterpret_cast<float*>(wp);      wp += a256(nnz * (int64_t)d * 4);
+  int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);  wp += a256(nnz * 8);
+  int64_t* lab_row = reinterpret_cast<int64_t*>(wp);  wp += a256(nnz * 8);
+  const int64_t scatter_bytes = ws_bytes - (wp - reinterpret_cast<char*>(ws));
+  KGEB_REQUIRE(scatter_bytes >= kgeb_scatter_workspace_bytes(nnz, d), "fused_label_rows: workspace too small");
+  label_entry_rows_kernel<<<(unsigned)((nnz + 8 * LABEL_EPW - 1) / (8 * LABEL_EPW)), 256, 0, st>>>(
+      Q, table, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale, inv_batch, nnz, nullptr, rows_dt, lab_ent, lab_row,
+      nullptr, 0.f);
+  KGEB_LAUNCH_CHECK("label_entry_rows");
+  return lab_perm ? kgeb_scatter_add_rows_perm(lab_ent, 1, lab_perm, rows_dt, nnz, d, dense_out, n_ent, wp, scatter_bytes, st)
+                  : kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dense_out, n_ent, wp, scatter_bytes, st);
+}
+
+int tc_wait_tiles(cudaStream_t st) {
+  SideStream* s0 = side_stream(0);
+  KGEB_REQUIRE(s0, "fused_bwd_wait_tiles: cannot create the event");
+  cudaError_t e = cudaStreamWaitEvent(st, s0->tiles, 0);
+  if (e != cudaSuccess) return cuda_status(e, "fused_bwd_wait_tiles");
   return KGEB_OK;
 }
 

@@ -21,6 +21,10 @@ int tc_fused_fwd(int loss, int math, const float* Q, const void* Qb, int64_t B, 
                  int64_t nnz, float ls_keep, float ls_add, float offset, float* rowstat, void* ws, int64_t ws_bytes,
                  cudaStream_t st);  // tc_dot.cu
 int tc_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);  // tc_bwd.cu
+int tc_wait_tiles(cudaStream_t st);  // tc_bwd.cu
+int tc_label_rows(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent, const int64_t* lab_off,
+                  const int64_t* lab_col, int64_t nnz, const int32_t* lab_perm, const float* tscale, const float* row_scale,
+                  float inv_batch, float* dense_out, void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                  const int32_t* lab_perm, const float* tscale, float ls_add, float offset, const float* lse,
@@ -828,6 +832,27 @@ __global__ void label_weight_kernel(int loss, const int64_t* __restrict__ lab_of
   if (loss == KGEB_LOSS_BCE) { tscale[r] = ls_keep; return; }
   int64_t n = lab_off[r + 1] - lab_off[r];  // KL: t = y / ||y||_1  (loss.py:211-213); one-hot for index labels
   tscale[r] = n > 0 ? 1.f / (float)n : 0.f;
+}
+
+int kgeb_fused_bwd_wait_tiles(void* stream) { return tc_wait_tiles(as_stream(stream)); }
+
+int kgeb_fused_label_rows(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
+                          const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const int32_t* lab_perm,
+                          float label_smoothing, float inv_batch, const float* grad_scale, float* dTable_out,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
+  if (rc) return rc;
+  KGEB_REQUIRE(lab_off && lab_col && dTable_out && workspace, "fused_label_rows: bad arguments");
+  KGEB_REQUIRE(d % 4 == 0, "fused_label_rows: entity dim must be a multiple of 4 (got %d)", d);
+  if (B == 0 || nnz == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  const int64_t head = ((B * 4 + 255) / 256) * 256;
+  KGEB_REQUIRE(workspace_bytes > head, "fused_label_rows: workspace too small");
+  float* tscale = reinterpret_cast<float*>(workspace);
+  label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, 1.f - label_smoothing, tscale);
+  KGEB_LAUNCH_CHECK("label_weight");
+  return tc_label_rows(Q, B, d, table, e_lo, e_hi - e_lo, lab_off, lab_col, nnz, lab_perm, tscale, grad_scale, inv_batch,
+                       dTable_out, reinterpret_cast<char*>(workspace) + head, workspace_bytes - head, st);
 }
 
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,

@@ -41,6 +41,8 @@ SIGNATURES = {
     "kgeb_score_all_bwd": [_i, _p, _l, _i, _p, _p, _i, _l, _p, _p, _l, _l, _p, _p, _p],
     "kgeb_fused_fwd": [_i, _i, _p, _l, _i, _p, _l, _l, _l, _p, _p, _l, _f, _f, _p, _p, _p, _l, _p],
     "kgeb_fused_bwd": [_i, _i, _p, _l, _i, _p, _l, _l, _l, _p, _p, _l, _p, _f, _f, _p, _f, _p, _p, _p, _p, _p, _p, _l, _p],
+    "kgeb_fused_label_rows": [_i, _p, _l, _i, _p, _l, _l, _p, _p, _l, _p, _f, _f, _p, _p, _p, _l, _p],
+    "kgeb_fused_bwd_wait_tiles": [_p],
     "kgeb_to_bf16": [_p, _p, _l, _p],
     "kgeb_loss_from_rowstat": [_i, _p, _p, _l, _f, _l, _f, _p, _p, _p, _p],
     "kgeb_rank_count": [_i, _i, _p, _l, _i, _p, _l, _l, _p, _p, _i, _p, _p, _p, _p, _p, _p],
@@ -67,10 +69,8 @@ SIGNATURES = {
     "kgeb_rank_hist": [_p, _p, _l, _l, _p, _p, _p],
     "kgeb_isin_sorted": [_p, _i, _l, _p, _l, _p, _p],
     "kgeb_rank_metrics": [_p, _l, _p, _i, _p, _p, _l, _p],
-    "kgeb_p2p_barrier": [_p, _i, _i, _p, _p, _p],
-    "kgeb_p2p_adagrad": [_p, _p, _i, _i, _p, _p, _p, _l, _f, _f, _p],
-    "kgeb_p2p_apply": [_p, _i, _i, _p, _p, _l, _p],
-    "kgeb_p2p_sum_scalar": [_p, _i, _p, _p],
+    "kgeb_p2p_exchange": [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _l, _p, _f, _f, _p],
+    "kgeb_p2p_apply": [_p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p, _l, _p],
 }
 
 

@@ -106,8 +106,10 @@ class FusedAllEntityStepper:
                                device=dev)
         self.ws2 = torch.empty_like(self.ws)   # workspace of the dTable half of the backward (runs on a second stream)
         self.sws2 = torch.empty_like(self.sws)  # scatter workspace of the relation-side chain (third stream)
+        self.ws3 = torch.empty_like(self.ws)   # workspace of the dense-only dTable kernel when the label rows go to g_q
         self.side = torch.cuda.Stream(device=dev)
         self.side2 = torch.cuda.Stream(device=dev)
+        self.ev_clear, self.ev_q = torch.cuda.Event(), torch.cuda.Event()
         self.mirror = None
         if math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256:
             self.mirror = torch.empty(self.E, self.d, dtype=torch.bfloat16, device=dev)
@@ -142,8 +144,22 @@ class FusedAllEntityStepper:
         self.side2.wait_stream(cur)
         with torch.cuda.stream(self.side2):
             self.gflat.zero_()
+            self.ev_clear.record()
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
+        if self._split_label_rows():
+            # Label rows of the dense table gradient go to g_q (the optimizer adds g_ent + g_q), on the third stream
+            # and underneath the dQ tile kernel: the dTable tile kernel then depends on nothing but the cleared g_ent
+            # and starts the moment dQ releases the SMs.  (Scattered into g_ent in front of the tile kernel, as
+            # kgeb_fused_bwd does on its own, this chain -- starved of SMs by the persistent dQ CTAs -- ended ~14 us after
+            # dQ and delayed dTable by as much: profiles/README.md, step timeline.)
+            self.ev_q.record()
+            with torch.cuda.stream(self.side2):
+                self.side2.wait_event(self.ev_q)
+                lib.call("kgeb_fused_label_rows", self.loss_kind, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
+                         self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.lab_perm.data_ptr(),
+                         self.ls, 1.0 / self.global_batch, None, self.g_q.data_ptr(), self.ws2.data_ptr(),
+                         self.ws2.numel(), lib.stream_ptr(self.ent))
         if not self._fused_stats_in_backward():
             lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
                      ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
@@ -173,6 +189,18 @@ class FusedAllEntityStepper:
         # stream, so that the chain of small latency-bound kernels that follows dQ on this stream (partial reduce, label
         # scatter, query-transform backward, sorted scatters) runs underneath the dTable tile kernel.
         cur = torch.cuda.current_stream()
+        if self._split_label_rows():
+            # dQ first; the dense-only dTable kernel (nnz = 0: no label part) queues behind it on the second stream
+            lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late_stats else None,
+                     self.ws.data_ptr(), self.ws.numel(), st)
+            dense = list(common)
+            dense[11], dense[12] = 0, None          # nnz, lab_perm
+            with torch.cuda.stream(self.side):
+                lib.call("kgeb_fused_bwd_wait_tiles", lib.stream_ptr(self.ent))   # the dQ tile kernel, not its reductions
+                self.side.wait_event(self.ev_clear)
+                lib.call("kgeb_fused_bwd", *dense, None, self.g_ent.data_ptr(), None, self.ws3.data_ptr(), self.ws3.numel(),
+                         lib.stream_ptr(self.ent))
+            return
         self.side.wait_stream(cur)
         if not sh.distributed:
             self.side.wait_stream(self.side2)     # cleared gradient buffers
@@ -186,6 +214,10 @@ class FusedAllEntityStepper:
 
     def _join_side(self):
         torch.cuda.current_stream().wait_stream(self.side)
+
+    def _split_label_rows(self) -> bool:
+        """bf16 tile path on an unsharded table with labels: see _stage_forward."""
+        return self.mirror is not None and not self.shard.distributed and self.nnz_max > 0
 
     def _stage_update(self):
         st = lib.stream_ptr(self.ent)
@@ -253,36 +285,29 @@ class FusedAllEntityStepper:
         torch.cuda.synchronize()
         dist.barrier(group)                 # nobody signals before every pad is zero
         world = hg.world_size
-        gp, sp = [int(x) for x in hg.buffer_ptrs], [int(x) for x in hs.buffer_ptrs]
         self.p2p = dict(rank=hg.rank, world=world, handles=(hg, hs, hp),
-                        g_ent=lib.ptr_array([x + 4 * n_e for x in gp]), g_rel=lib.ptr_array([x + 8 * n_e for x in gp]),
-                        loss=lib.ptr_array([x + 4 * (2 * n_e + n_r) for x in gp]),
-                        st_ent=lib.ptr_array(sp), st_rel=lib.ptr_array([x + 4 * n_e for x in sp]),
+                        flat=lib.ptr_array([int(x) + 4 * n_e for x in hg.buffer_ptrs]),     # [g_ent | g_rel | loss]
+                        stage=lib.ptr_array([int(x) for x in hs.buffer_ptrs]),              # [W_ent | W_rel]
                         pads=lib.ptr_array([int(x) for x in hp.buffer_ptrs]))
-        self.p2p_epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.p2p_ctr = torch.zeros(2, dtype=torch.int32, device=dev)        # [completed steps, block ticket]
         self.p2p_timeout = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_global = torch.zeros((), dtype=torch.float32, device=dev)
 
     def _stage_exchange_p2p(self):
-        """barrier ; reduce + Adagrad on the owned slice + push of the new weights ; barrier ; apply the peers' slices.
-        Plain kernels on peer pointers: captured in the same CUDA graph as the compute stages."""
+        """Two kernels on peer pointers, captured in the same CUDA graph as the compute stages:
+        exchange = barrier ; reduce the owned slice over all ranks ; Adagrad ; push the new weights to the peers' staging
+        apply    = barrier ; copy the other owners' slices into the tables (+ bf16 mirror)."""
         st = lib.stream_ptr(self.ent)
         x = self.p2p
         ent, rel = self.ent.detach(), self.rel.detach()
         s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
         mirror = None if self.mirror is None else self.mirror.data_ptr()
-        n_e = ent.numel()
-        bar = lambda: lib.call("kgeb_p2p_barrier", x["pads"], x["rank"], x["world"], self.p2p_epoch.data_ptr(),  # noqa: E731
-                               self.p2p_timeout.data_ptr(), st)
-        bar()
-        lib.call("kgeb_p2p_adagrad", x["g_rel"], x["st_rel"], x["rank"], x["world"], rel.data_ptr(), s_rel.data_ptr(), None,
-                 rel.numel(), self.lr, self.eps, st)
-        lib.call("kgeb_p2p_adagrad", x["g_ent"], x["st_ent"], x["rank"], x["world"], ent.data_ptr(), s_ent.data_ptr(), mirror,
-                 n_e, self.lr, self.eps, st)
-        lib.call("kgeb_p2p_sum_scalar", x["loss"], x["world"], self.loss_global.data_ptr(), st)
-        bar()
-        lib.call("kgeb_p2p_apply", self.p2p_stage.data_ptr(), x["rank"], x["world"], ent.data_ptr(), mirror, n_e, st)
-        lib.call("kgeb_p2p_apply", self.p2p_stage[n_e:].data_ptr(), x["rank"], x["world"], rel.data_ptr(), None, rel.numel(), st)
+        lib.call("kgeb_p2p_exchange", x["pads"], x["flat"], x["stage"], x["rank"], x["world"], self.p2p_ctr.data_ptr(),
+                 self.p2p_timeout.data_ptr(), ent.data_ptr(), s_ent.data_ptr(), mirror, ent.numel(), rel.data_ptr(),
+                 s_rel.data_ptr(), rel.numel(), self.loss_global.data_ptr(), self.lr, self.eps, st)
+        lib.call("kgeb_p2p_apply", x["pads"], self.p2p_stage.data_ptr(), x["rank"], x["world"], self.p2p_ctr.data_ptr(),
+                 self.p2p_ctr[1:].data_ptr(), self.p2p_timeout.data_ptr(), ent.data_ptr(), mirror, ent.numel(),
+                 rel.data_ptr(), rel.numel(), st)
 
     def check_p2p(self):
         """Host check (one sync): no peer-memory barrier ran into its timeout."""
