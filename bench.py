@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8, help="steps of the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="tuning runs: device-resident value + kernel roofline only")
-    ap.add_argument("--parallel", default="dp", choices=["dp", "p2p", "shard"],
+    ap.add_argument("--parallel", default="p2p", choices=["dp", "p2p", "shard"],
                     help="N>1: dp = data-parallel replicas + one NCCL all-reduce of the gradients (graphs too small to "
                          "shard); p2p = the same replicas with the exchange fused into the Adagrad update over NVLink "
                          "peer memory, whole step in one CUDA graph; shard = entity-sharded scoring (SURVEY.md 8e)")

@@ -391,7 +391,8 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         uint8_t* gb = g_smem + (size_t)bufi * G_BYTES;
         if (BF16) {
           // row trow of the single K-slab: this warp's 32 bf16 = chunks 4*sub .. 4*sub+3 (16 B each), 128-byte swizzle
-          uint8_t* rowp = gb + (size_t)trow * 128;
+          // (shared-window address + st.shared: through the generic pointer these are ST.E, resolved in the LSU)
+          const uint32_t rowa = smem_s + (uint32_t)(KS * RES_SLAB + bufi * G_BYTES + trow * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint32_t w[4];
@@ -399,7 +400,9 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
             for (int j = 0; j < 4; ++j)
               asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[k * 8 + j * 2 + 1]), "f"(v[k * 8 + j * 2]));
             const int ck = sub * 4 + k;
-            *reinterpret_cast<uint4*>(rowp + ((ck ^ (trow & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (uint32_t)((ck ^ (trow & 7)) << 4)),
+                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                         : "memory");
           }
         } else {
           // TF32: 64 fp32 = two K-slabs of 32 columns; this warp's 32 columns are slab `sub`

@@ -375,12 +375,14 @@ class FusedAllEntityStepper:
 
     @property
     def kernel_launches_per_step(self) -> int:
-        """Kernels of this library per step (bench.py gpu_launches), counted from the step timeline under profiles/:
-        query build 1; dTable half 7 (label weights, bf16(Q), label rows, permutation pack, 2 segment-sum phases, tile
-        kernel); dQ half 10 (label weights, bf16(Q), label rows, key pack, 2 segment-sum phases, label row sums, tile
-        kernel, partial reduce, statistics reduce); loss 1; query backward 1; two scatters 6 (permutation pack + 2 phases
-        each); Adagrad 2.  KL (or fp32 math) adds the 5 forward-statistics kernels."""
-        return 28 + (0 if self._fused_stats_in_backward() else 5)
+        """Kernels of this library per step (bench.py gpu_launches), counted from the step timeline under profiles/
+        (timeline_bench_r1s2.txt: 31 launches, 29 of them this library's -- the other two are the gradient clear and a
+        memset): query build 1; label rows of the table gradient 5 (label weights, label rows, permutation pack, 2
+        segment-sum phases); dQ half 10 (label weights, bf16(Q), label rows, key pack, 2 segment-sum phases, label row
+        sums, tile kernel, partial reduce, statistics reduce); dense dTable half 3 (label weights, bf16(Q), tile kernel);
+        loss 1; query backward 1; two scatters 6 (permutation pack + 2 phases each); Adagrad 2 (or the exchange and
+        apply kernels of the peer-memory mode).  KL (or fp32 math) adds the 5 forward-statistics kernels."""
+        return 29 + (0 if self._fused_stats_in_backward() else 5)
 
     def _capture(self):
         """CUDA graphs of the three stages; NCCL collectives (sharded mode) stay outside the graphs."""
