@@ -136,6 +136,10 @@ class TrainingJobKvsAll(TrainingJob):
         `nnz_max` labels (no autograd, one CUDA-graph replay per step).  Needs the DOT scorers and dense Adagrad;
         unweighted Lp penalties are folded into the Adagrad kernels (the toy config's regularize_weight)."""
         from .trainer import FusedAllEntityStepper
+        if any(e.normalize_p > 0 for e in (self.model.get_s_embedder(), self.model.get_p_embedder())):
+            # the hook of lookup_embedder.py:58-75 REPLACES the weight tensor every batch; the captured step reads fixed
+            # addresses
+            raise NotImplementedError("per-batch renormalisation (normalize_p) is served by the autograd path only")
         self.stepper = FusedAllEntityStepper(self.model, self.optimizer, batch_size, nnz_max, self.loss.kind,
                                              batch_size, self.loss.offset, self.label_smoothing, self.math_mode,
                                              use_graph, self.shard, dp_group, dp_p2p)
