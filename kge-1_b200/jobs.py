@@ -242,13 +242,44 @@ class TrainingJobKvsAll(TrainingJob):
         lab_off, lab_col = fused.csr_from_coords(batch["label_coords"], len(q))
         return {"packed": self.stepper.pack_host_batch(a, p, rc, lab_off, lab_col), "size": len(q)}
 
+    def prefetch_packed(self, batch: dict):
+        """Starts the H2D copy of a packed (pinned) batch on a copy stream into one of two device staging buffers, so
+        that it runs underneath the step in flight -- what pinned DataLoader batches with non_blocking copies give the
+        reference's loop.  step() recognises the batch and takes it from the staging buffer (one D2D copy)."""
+        st = self.stepper
+        pf = getattr(self, "_pf", None)
+        if pf is None:
+            dev = st.input_bytes.device
+            pf = self._pf = dict(stream=torch.cuda.Stream(device=dev), staging=[torch.empty_like(st.input_bytes) for _ in range(2)],
+                                 ready=[torch.cuda.Event(), torch.cuda.Event()],
+                                 consumed=[torch.cuda.Event(), torch.cuda.Event()], slot=0, pending=[])
+            for ev in pf["consumed"]:
+                ev.record()
+        if len(pf["pending"]) >= 2:
+            raise RuntimeError("two batches are already in flight")
+        slot = pf["slot"]
+        pf["slot"] ^= 1
+        cs = pf["stream"]
+        with torch.cuda.stream(cs):
+            cs.wait_event(pf["consumed"][slot])          # the step that used this staging buffer has copied it
+            pf["staging"][slot].copy_(batch["packed"], non_blocking=True)
+            pf["ready"][slot].record(cs)
+        pf["pending"].append((batch["packed"].data_ptr(), slot))
+
     def step(self, batch_index: int, batch: dict) -> ProcessBatchResult:
         size = batch["size"] if "packed" in batch else len(batch["queries"])
         if self.stepper is None or size != self.stepper.rows:
             return super().step(batch_index, batch)
         for f in self.pre_batch_hooks:
             f(self)
-        if "packed" in batch:
+        pf = getattr(self, "_pf", None)
+        if "packed" in batch and pf is not None and pf["pending"] and pf["pending"][0][0] == batch["packed"].data_ptr():
+            _, slot = pf["pending"].pop(0)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(pf["ready"][slot])
+            self.stepper.input_bytes.copy_(pf["staging"][slot], non_blocking=True)
+            pf["consumed"][slot].record(cur)
+        elif "packed" in batch:
             self.stepper.set_packed(batch["packed"])
         else:
             self.stepper.set_inputs(*self.device_inputs(batch))

@@ -51,7 +51,9 @@ def main():
         for i, batch in enumerate(batches):
             a, c = jobs[0].step(i, batch), jobs[1].step(i, batch)
             jobs[1].stepper.check_p2p()
-            tol = 0.0 if world == 2 else 1e-6 * abs(a.avg_loss)
+            # world > 2: NCCL's ring / tree order differs from the rank order, and the difference compounds over the steps
+            # (8 GPUs, step 3: 1.9e-6 relative)
+            tol = 0.0 if world == 2 else 2e-5 * abs(a.avg_loss)
             assert abs(a.avg_loss - c.avg_loss) <= tol, (math_mode, i, a.avg_loss, c.avg_loss)
             for x, y in ((models[0].get_s_embedder().weight, models[1].get_s_embedder().weight),
                          (models[0].get_p_embedder().weight, models[1].get_p_embedder().weight)):

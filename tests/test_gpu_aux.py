@@ -309,3 +309,32 @@ def test_captured_kvsall_step_with_fused_penalty_matches_autograd_flow(kb, p):
                           (new.get_p_embedder().weight, ref.get_p_embedder().weight)):
             err = (got - want).abs().max().item()
             assert err <= 1e-5 * want.abs().max().item() + 1e-6, (i, err)
+
+
+def test_prefetched_packed_batches_equal_direct_copies(kb):
+    """prefetch_packed(): the double-buffered H2D staging feeds step() the same bytes as the direct copy."""
+    g = kb.graph.synthetic_graph("toy", seed=3)
+    e, r, d, b = g["num_entities"], g["num_relations"], 32, 64
+    idx = [ko.kvsall_index(g["train"], "sp"), ko.kvsall_index(g["train"], "po")]
+    rng = np.random.default_rng(4)
+    batches = []
+    for _ in range(5):
+        ids = rng.choice(len(idx[0][0]) + len(idx[1][0]), b, replace=False)
+        q, c, qt = ko.kvsall_collate(ids.tolist(), idx)
+        batches.append({"queries": T(q), "label_coords": T(c), "query_type_indexes": T(qt)})
+    nnz_max = max(len(x["label_coords"]) for x in batches)
+    res = []
+    for prefetch in (False, True):
+        torch.manual_seed(0)
+        m = kb.KgeModel("complex", e, r, d).cuda()
+        job = kb.TrainingJobKvsAll(m, kb.optim.create("Adagrad", m.parameters(), lr=0.2), kb.KgeLoss.create("bce"), e, r,
+                                   math_mode=kb.lib.MATH_BF16)
+        job.enable_graph_step(b, nnz_max)
+        packed = [job.collate_packed(x) for x in batches]
+        losses = []
+        for i, pb in enumerate(packed):
+            if prefetch and i + 1 < len(packed):
+                job.prefetch_packed(packed[i + 1])
+            losses.append(job.step(i, pb).avg_loss)
+        res.append((losses, m.get_s_embedder().weight.detach().clone()))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
