@@ -19,6 +19,14 @@ from . import fused, lib, ops
 from .model import KgeModel
 
 
+def p2p_slice(numel: int, world: int, rank: int):
+    """[lo, hi) of a table's elements that `rank` owns in the peer-memory exchange (csrc/p2p.cu, slice_of): equal
+    slices whose bounds are multiples of 4 elements (float4 accesses), the last ones possibly short or empty."""
+    per = ((numel + 4 * world - 1) // (4 * world)) * 4
+    lo = min(numel, per * rank)
+    return lo, min(numel, lo + per)
+
+
 class FusedAllEntityStepper:
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
@@ -324,10 +332,9 @@ class FusedAllEntityStepper:
         for t in (self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]):
             flat = t.view(-1)
             n = flat.numel()
-            per = ((n + 4 * x["world"] - 1) // (4 * x["world"])) * 4
             ranks = dist.get_process_group_ranks(self.dp_group)
             for r in range(x["world"]):
-                lo, hi = min(n, per * r), min(n, per * r + per)
+                lo, hi = p2p_slice(n, x["world"], r)
                 if hi > lo:
                     dist.broadcast(flat[lo:hi], src=ranks[r], group=self.dp_group)
 

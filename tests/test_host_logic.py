@@ -152,3 +152,33 @@ def test_sharded_statistics_combine_over_gloo_world2():
         p.join(120)
     res = dict(out.get() for _ in range(2))
     assert res == {0: "ok", 1: "ok"}, res
+
+
+def test_p2p_slices_partition_the_table():
+    """Owner slices of the peer-memory exchange (trainer.p2p_slice == slice_of in csrc/p2p.cu)."""
+    from importlib import import_module
+    tr = import_module("kge-1_b200.trainer")
+    for numel in (0, 4, 12, 128 * 237, 14541 * 128, 1000):
+        for world in (1, 2, 3, 4, 8, 16):
+            cover = 0
+            for r in range(world):
+                lo, hi = tr.p2p_slice(numel, world, r)
+                assert lo == cover and lo <= hi <= numel and lo % 4 == 0
+                assert hi == numel or (hi - lo) % 4 == 0
+                cover = hi
+            assert cover == numel
+
+
+def test_sampler_option_errors_match_reference():
+    """kge/util/sampler.py:27-31, 46-50, 67-77: option validation happens before anything touches a device."""
+    from importlib import import_module
+    sm = import_module("kge-1_b200.sampler")
+    import pytest as _pt
+    with _pt.raises(ValueError, match="Without replacement"):
+        sm.KgeUniformSampler(10, 3, shared=False, with_replacement=False, device="cpu")
+    with _pt.raises(ValueError, match="Filtering is not supported"):
+        sm.KgeUniformSampler(10, 3, shared=True, filter_positives=(True, False, False), device="cpu")
+    with _pt.raises(ValueError):
+        sm.KgeSampler.create("frequency", 10, 3)
+    with _pt.raises(ValueError, match="no CPU path"):
+        sm.KgeUniformSampler(10, 3, device="cpu")
