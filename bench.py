@@ -211,9 +211,18 @@ def main():
     shard = kb.fused.Shard.of_rank(E, rank, world, dist.group.WORLD) if sharded else None
     job = kb.TrainingJobKvsAll(model, opt, kb.KgeLoss.create("bce"), E, R, fused_path=True, math_mode=math_mode,
                                shard=shard)
-    job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph,
-                          dp_group=dist.group.WORLD if (world > 1 and not sharded) else None,
-                          dp_p2p=args.parallel == "p2p")
+    try:
+        job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph,
+                              dp_group=dist.group.WORLD if (world > 1 and not sharded) else None,
+                              dp_p2p=args.parallel == "p2p")
+    except (RuntimeError, ImportError) as exc:
+        # peer-mapped (symmetric) memory is a property of the box (NVLink / NVSwitch + fabric handles): where it cannot be
+        # set up -- on every rank alike -- the replicas exchange gradients through NCCL instead, and the line says so
+        if not (world > 1 and args.parallel == "p2p"):
+            raise
+        print(f"[bench] peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using the NCCL mode", file=sys.stderr)
+        args.parallel = "dp"
+        job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph, dp_group=dist.group.WORLD, dp_p2p=False)
     stepper = job.stepper
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
