@@ -74,6 +74,10 @@ class KgeSampler:
         elif (not out.is_cuda or out.dtype != torch.int64 or not out.is_contiguous()
               or tuple(out.shape) != (pt.shape[0], num_samples)):
             raise ValueError("out must be a contiguous [batch, num_samples] int64 CUDA tensor")
+        if self.shared and num_samples + 1 > self.vocabulary_size[slot]:
+            raise ValueError(f"{num_samples + 1} distinct shared samples from a vocabulary of {self.vocabulary_size[slot]}")
+        if out.numel() == 0:                   # empty batch / no samples for this slot: nothing to draw
+            return out
         if self.shared:
             neg = self._sample_shared(pt, slot, num_samples, out)
         else:

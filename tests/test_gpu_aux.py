@@ -338,3 +338,56 @@ def test_prefetched_packed_batches_equal_direct_copies(kb):
             losses.append(job.step(i, pb).avg_loss)
         res.append((losses, m.get_s_embedder().weight.detach().clone()))
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("model", ["complex", "transe"])
+@pytest.mark.parametrize("ties", ["rounded_mean_rank", "best_rank", "worst_rank"])
+def test_ranking_edge_cases_all_ties_and_nan_scores(kb, model, ties):
+    """Edge cases of _filter_and_rank / _get_ranks_and_num_ties (entity_ranking.py:469-551): every candidate tied with
+    the true triple (all-zero tables), and NaN scores, which count as -inf (:500-507) -- also for the true triple."""
+    g = kb.graph.synthetic_graph("toy", seed=5)
+    e, r, d = g["num_entities"], g["num_relations"], 16
+    gen = torch.Generator().manual_seed(7)
+    valid = g["valid"][:40]
+    for case in ("zeros", "nan"):
+        if case == "zeros":
+            ent, rel = torch.zeros(e, d), torch.zeros(r, d)
+        else:
+            if model == "complex":
+                ent = torch.round(torch.randn(e, d, generator=gen) * 4) / 4    # dyadic: sums are exact in fp32 and TF32
+                rel = torch.round(torch.randn(r, d, generator=gen) * 4) / 4
+            else:
+                # TransE's true score carries pairwise_distance's eps (transe.py:17, +1e-6 per coordinate) while the
+                # candidates' scores do not: on dyadic tables a candidate at exactly the true distance is ordered by the
+                # rounding of sum |diff + 1e-6|, i.e. by the summation order.  Generic weights keep that boundary empty.
+                ent = torch.randn(e, d, generator=gen) * 0.5
+                rel = torch.randn(r, d, generator=gen) * 0.5
+            bad = torch.randperm(e, generator=gen)[:9]
+            ent[bad] = float("nan")
+            ent[int(valid[0, 2])] = float("nan")                               # a true object with a NaN score
+        want, wranks = ko.entity_ranking(model, ent, rel, valid, [g["train"], g["valid"]], g["test"], batch_size=16,
+                                         tie_handling=ties, hits_at_k=(1, 3, 10))
+        for math_mode in ((kb.lib.MATH_FP32, kb.lib.MATH_TF32) if model == "complex" else (kb.lib.MATH_FP32,)):
+            m = kb.KgeModel(model, e, r, d, math_mode=math_mode).cuda()
+            with torch.no_grad():
+                m.get_s_embedder().weight.copy_(ent)
+                m.get_p_embedder().weight.copy_(rel)
+            job = kb.EntityRankingJob(m, e, [g["train"], g["valid"]], g["test"], batch_size=16, tie_handling=ties,
+                                      hits_at_k_s=(1, 3, 10), math_mode=math_mode)
+            res = job.run(valid)
+            for key, ref in wranks.items():
+                np.testing.assert_array_equal(res["ranks"][key].cpu().numpy(), ref.numpy(),
+                                              err_msg=f"{model} {ties} {case} {key} math={math_mode}")
+            assert res["metrics"]["mean_reciprocal_rank_filtered"] == pytest.approx(
+                want["_filt"]["mean_reciprocal_rank"], abs=1e-6)
+
+
+def test_sampler_edge_cases_empty_batch(kb):
+    smp = kb.KgeUniformSampler(50, 5, num_samples=(4, 0, 4), seed=1)
+    empty = torch.zeros(0, 3, dtype=torch.long, device="cuda")
+    assert smp.sample(empty, 0).shape == (0, 4)
+    shared = kb.KgeUniformSampler(50, 5, num_samples=(4, 0, 4), shared=True, with_replacement=False, seed=1)
+    assert shared.sample(empty, 2).shape == (0, 4)
+    shared.check_status()
+    with pytest.raises(ValueError):
+        shared.sample(torch.zeros(3, 3, dtype=torch.long, device="cuda"), 0, num_samples=50)   # 51 distinct of 50
