@@ -216,6 +216,34 @@ def reciprocal_score_sp_po(model, ent_w, rel_w, num_rel, s, p, o, entity_subset=
     return torch.cat((sp, po), dim=1)
 
 
+def reciprocal_score_spo(model, ent_w, rel_w, num_rel, s, p, o, direction, l_norm=1.0):
+    """reciprocal_relations_model.py:56-63: "o" scores (s, p, o); "s" scores (o, p + R, s); no undirected form."""
+    if direction == "o":
+        return score_spo(model, ent_w, rel_w, s, p, o, l_norm)
+    if direction == "s":
+        return score_spo(model, ent_w, rel_w, o, p + num_rel, s, l_norm)
+    raise Exception("The reciprocal relations model cannot compute undirected spo scores.")
+
+
+def reciprocal_score_po(model, ent_w, rel_w, num_rel, p, o, s=None, l_norm=1.0):
+    """reciprocal_relations_model.py:65-74: subjects ranked with the inverse relation, combine "sp_"."""
+    cand = embed_all(ent_w) if s is None else embed(ent_w, s)
+    return score_emb(model, embed(ent_w, o), embed(rel_w, p + num_rel), cand, "sp_", l_norm)
+
+
+def batch_1vsall_reciprocal(model, prm: "Params", num_rel: int, triples: torch.Tensor, loss_name="kl", offset=0.0,
+                            l_norm=1.0):
+    """train.py:1032-1062 on a ReciprocalRelationsModel: the _po pass goes through reciprocal_score_po."""
+    loss = make_loss(loss_name, offset)
+    t = triples.long()
+    b = len(t)
+    l_sp = loss(score_sp(model, prm.ent, prm.rel, t[:, 0], t[:, 1], l_norm=l_norm), t[:, 2]) / b
+    l_sp.backward()
+    l_po = loss(reciprocal_score_po(model, prm.ent, prm.rel, num_rel, t[:, 1], t[:, 2], l_norm=l_norm), t[:, 0]) / b
+    l_po.backward()
+    return l_sp.item() + l_po.item()
+
+
 # --------------------------------------------------------------------------------------
 # a16/a17: losses (util/loss.py:137-159, 192-213).  Un-normalised sums; callers divide by B.
 # --------------------------------------------------------------------------------------

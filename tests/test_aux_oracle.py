@@ -102,3 +102,87 @@ def test_sampler_oracle_contract():
         assert not set(f[i].tolist()) & set(index[(i, i)].tolist())
         keep = ~np.isin(neg[i], index[(i, i)])
         assert np.array_equal(f[i][keep], neg[i][keep])
+
+
+@pytest.fixture(scope="module")
+def aux2():
+    return np.load(os.path.join(GOLD, "aux2.npz"), allow_pickle=False)
+
+
+def test_reciprocal_relations_oracle_matches_reference(aux2):
+    """a15: ReciprocalRelationsModel (reciprocal_relations_model.py:56-106) over distmult / complex."""
+    T = torch.from_numpy
+    s, p, o, sub = (T(aux2[k]).long() for k in ("recip.idx_s", "recip.idx_p", "recip.idx_o", "recip.subset"))
+    num_rel = 7
+    for tag in aux2["recip.cases"]:
+        tag = str(tag)
+        base = tag.split(".")[1]
+        ent, rel = T(aux2[tag + ".ent"]), T(aux2[tag + ".rel"])
+        assert rel.shape[0] == 2 * num_rel
+        eq = lambda got, key: np.testing.assert_array_equal(got.numpy(), aux2[f"{tag}.{key}"], err_msg=f"{tag} {key}")  # noqa: E731
+        eq(ko.reciprocal_score_spo(base, ent, rel, num_rel, s, p, o, "o").view(-1), "spo_o")
+        eq(ko.reciprocal_score_spo(base, ent, rel, num_rel, s, p, o, "s").view(-1), "spo_s")
+        eq(ko.score_sp(base, ent, rel, s, p), "sp")
+        eq(ko.reciprocal_score_po(base, ent, rel, num_rel, p, o), "po")
+        eq(ko.reciprocal_score_sp_po(base, ent, rel, num_rel, s, p, o), "sp_po")
+        eq(ko.reciprocal_score_sp_po(base, ent, rel, num_rel, s, p, o, sub), "sp_po_sub")
+        with pytest.raises(Exception, match="undirected"):
+            ko.reciprocal_score_spo(base, ent, rel, num_rel, s, p, o, None)
+        prm = ko.Params(ent, rel)
+        opt = ko.make_optimizer("Adagrad", prm, lr=0.2)
+        lv = ko.batch_1vsall_reciprocal(base, prm, num_rel, T(aux2[tag + ".b0.triples"]), "kl")
+        assert lv == pytest.approx(float(aux2[tag + ".b0.loss"]), rel=1e-6)
+        ge, gr = prm.grads()
+        np.testing.assert_allclose(ge.numpy(), aux2[tag + ".b0.grad_ent"], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(gr.numpy(), aux2[tag + ".b0.grad_rel"], rtol=0, atol=1e-7)
+        opt.step()
+        np.testing.assert_allclose(prm.ent.detach().numpy(), aux2[tag + ".b0.ent"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(prm.rel.detach().numpy(), aux2[tag + ".b0.rel"], rtol=0, atol=1e-6)
+
+
+def test_adam_steps_oracle_matches_reference(aux2):
+    """util/optimizer.py:10-17 with train.optimizer: Adam."""
+    T = torch.from_numpy
+    prm = ko.Params(T(aux2["adam.ent0"]), T(aux2["adam.rel0"]))
+    opt = ko.make_optimizer("Adam", prm, lr=0.01)
+    for step in range(2):
+        opt.zero_grad()
+        lv = ko.batch_1vsall("distmult", prm, T(aux2[f"adam.b{step}.triples"]), "kl")
+        assert lv == pytest.approx(float(aux2[f"adam.b{step}.loss"]), rel=1e-6)
+        ge, _ = prm.grads()
+        np.testing.assert_allclose(ge.numpy(), aux2[f"adam.b{step}.grad_ent"], rtol=0, atol=1e-7)
+        opt.step()
+        np.testing.assert_allclose(prm.ent.detach().numpy(), aux2[f"adam.b{step}.ent"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(prm.rel.detach().numpy(), aux2[f"adam.b{step}.rel"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(opt.state[prm.ent]["exp_avg"].numpy(), aux2["adam.exp_avg_ent"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(opt.state[prm.ent]["exp_avg_sq"].numpy(), aux2["adam.exp_avg_sq_ent"], rtol=0, atol=1e-9)
+
+
+def test_toy_config_steps_with_penalty_oracle_matches_reference(aux2):
+    """examples/toy-complex-train.yaml as written (ComplEx, KvsAll + KL, Lp penalty): run_epoch's body (train.py:309-376)."""
+    T = torch.from_numpy
+    e, r = 53, 7
+    prm = ko.Params(T(aux2["toy.ent0"]), T(aux2["toy.rel0"]))
+    opt = ko.make_optimizer("Adagrad", prm, lr=0.2)
+    assert [str(k) for k in aux2["toy.penalty_keys"]] == ["complex.entity_embedder.L2_penalty",
+                                                          "complex.relation_embedder.L2_penalty",
+                                                          "complex.entity_embedder.L2_penalty"]
+    for step in range(2):
+        pre = f"toy.b{step}"
+        opt.zero_grad()
+        lv, _ = ko.batch_kvsall("complex", prm, aux2[pre + ".queries"], aux2[pre + ".label_coords"], aux2[pre + ".query_type"],
+                                e, r, "kl")
+        # KvsAll batches carry no "triples": the unweighted penalty of the s-, p- and o-embedder (kge_model.py:598-606)
+        vals = []
+        for w, lam in ((prm.ent, 1e-2), (prm.rel, 1e-2), (prm.ent, 1e-2)):
+            v = ko.lp_penalty(w, 2, lam)
+            v.backward()
+            vals.append(v.item())
+        assert lv == pytest.approx(float(aux2[pre + ".loss"]), rel=1e-6)
+        np.testing.assert_allclose(vals, aux2[pre + ".penalties"], rtol=1e-6)
+        ge, gr = prm.grads()
+        np.testing.assert_allclose(ge.numpy(), aux2[pre + ".grad_ent"], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(gr.numpy(), aux2[pre + ".grad_rel"], rtol=0, atol=1e-7)
+        opt.step()
+        np.testing.assert_allclose(prm.ent.detach().numpy(), aux2[pre + ".ent"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(prm.rel.detach().numpy(), aux2[pre + ".rel"], rtol=0, atol=1e-6)

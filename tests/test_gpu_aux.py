@@ -391,3 +391,94 @@ def test_sampler_edge_cases_empty_batch(kb):
     shared.check_status()
     with pytest.raises(ValueError):
         shared.sample(torch.zeros(3, 3, dtype=torch.long, device="cuda"), 0, num_samples=50)   # 51 distinct of 50
+
+
+# ---------------------------------------------------------------------------------------------
+# Written after the round's GPU budget was spent: the golden vectors (tests/golden/aux2.npz, from the unmodified
+# reference) and the oracle side are verified on the CPU (tests/test_aux_oracle.py); the CUDA side of these three has not
+# run on hardware yet.  Non-strict xfail keeps the suite's verdict independent of them until the first GPU call of the
+# next round (an XPASS means: remove the marker).
+# ---------------------------------------------------------------------------------------------
+_unconfirmed = pytest.mark.xfail(strict=False, reason="CUDA side not yet run on hardware (GPU budget of round 1 exhausted)")
+
+
+def _close(got, ref, rtol, what):
+    got = got.detach().cpu().double().numpy()
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, what
+    assert np.abs(got - ref).max() <= rtol * max(np.abs(ref).max(), 1e-30), what
+
+
+@_unconfirmed
+def test_reciprocal_relations_model_matches_reference_golden(kb, golden):
+    """a15: ReciprocalRelationsModel (reciprocal_relations_model.py:56-106); fp32 tolerance 1e-5."""
+    g = golden("aux2")
+    s, p, o, sub = (T(g[k]).cuda() for k in ("recip.idx_s", "recip.idx_p", "recip.idx_o", "recip.subset"))
+    for tag in g["recip.cases"]:
+        tag = str(tag)
+        base = tag.split(".")[1]
+        ent, rel = g[tag + ".ent"], g[tag + ".rel"]
+        m = kb.ReciprocalRelationsModel(base, ent.shape[0], rel.shape[0] // 2, ent.shape[1]).cuda()
+        with torch.no_grad():
+            m.get_s_embedder().weight.copy_(T(ent))
+            m.get_p_embedder().weight.copy_(T(rel))
+            _close(m.score_spo(s, p, o, "o").view(-1), g[tag + ".spo_o"], 1e-5, "spo o")
+            _close(m.score_spo(s, p, o, "s").view(-1), g[tag + ".spo_s"], 1e-5, "spo s")
+            _close(m.score_sp(s, p), g[tag + ".sp"], 1e-5, "sp")
+            _close(m.score_po(p, o), g[tag + ".po"], 1e-5, "po")
+            _close(m.score_sp_po(s, p, o), g[tag + ".sp_po"], 1e-5, "sp_po")
+            _close(m.score_sp_po(s, p, o, sub), g[tag + ".sp_po_sub"], 1e-5, "sp_po subset")
+        with pytest.raises(Exception):
+            m.score_spo(s, p, o, None)
+        job = kb.TrainingJob1vsAll(m, kb.optim.create("Adagrad", m.parameters(), lr=0.2), kb.KgeLoss.create("kl"),
+                                   fused_path=False)
+        res = job.step(0, {"triples": T(g[tag + ".b0.triples"])})
+        assert res.avg_loss == pytest.approx(float(g[tag + ".b0.loss"]), rel=2e-5)
+        _close(m.get_s_embedder().weight.grad, g[tag + ".b0.grad_ent"], 2e-5, "grad entity")
+        _close(m.get_p_embedder().weight.grad, g[tag + ".b0.grad_rel"], 2e-5, "grad relation")
+
+
+@_unconfirmed
+def test_adam_steps_match_reference_golden(kb, golden):
+    """train.optimizer: Adam (util/optimizer.py:10-17) through kgeb_adam_dense."""
+    g = golden("aux2")
+    ent, rel = g["adam.ent0"], g["adam.rel0"]
+    m = kb.KgeModel("distmult", ent.shape[0], rel.shape[0], ent.shape[1]).cuda()
+    with torch.no_grad():
+        m.get_s_embedder().weight.copy_(T(ent))
+        m.get_p_embedder().weight.copy_(T(rel))
+    job = kb.TrainingJob1vsAll(m, kb.optim.create("Adam", m.parameters(), lr=0.01), kb.KgeLoss.create("kl"), fused_path=False)
+    for step in range(2):
+        res = job.step(step, {"triples": T(g[f"adam.b{step}.triples"])})
+        assert res.avg_loss == pytest.approx(float(g[f"adam.b{step}.loss"]), rel=2e-5)
+        # Adam's first steps move every weight by ~lr * sign(g): compare in units of the learning rate
+        for got, ref in ((m.get_s_embedder().weight, g[f"adam.b{step}.ent"]), (m.get_p_embedder().weight, g[f"adam.b{step}.rel"])):
+            assert (got.detach().cpu() - T(ref)).abs().max().item() <= 0.01 * 2e-2
+
+
+@_unconfirmed
+def test_toy_config_steps_with_penalty_match_reference_golden(kb, golden):
+    """examples/toy-complex-train.yaml as written: ComplEx, KvsAll + KL, Lp penalty; run_epoch's body (train.py:309-376)
+    on the autograd path (fp32) and on the captured step with the penalty folded into the Adagrad kernels."""
+    g = golden("aux2")
+    e, r = 53, 7
+    reg = dict(entity_embedder=dict(regularize_weight=1e-2, regularize_p=2), relation_embedder=dict(regularize_weight=1e-2, regularize_p=2))
+    nnz_max = max(len(g[f"toy.b{step}.label_coords"]) for step in range(2))
+    for captured in (False, True):
+        m = kb.KgeModel("complex", e, r, g["toy.ent0"].shape[1], **reg).cuda()
+        with torch.no_grad():
+            m.get_s_embedder().weight.copy_(T(g["toy.ent0"]))
+            m.get_p_embedder().weight.copy_(T(g["toy.rel0"]))
+        job = kb.TrainingJobKvsAll(m, kb.optim.create("Adagrad", m.parameters(), lr=0.2), kb.KgeLoss.create("kl"), e, r)
+        for step in range(2):
+            pre = f"toy.b{step}"
+            batch = {"queries": T(g[pre + ".queries"]), "label_coords": T(g[pre + ".label_coords"]),
+                     "query_type_indexes": T(g[pre + ".query_type"])}
+            if captured:
+                job.enable_graph_step(len(batch["queries"]), nnz_max)
+            res = job.step(step, batch)
+            assert res.total_loss == pytest.approx(float(g[pre + ".loss"]), rel=2e-5)
+            assert res.penalty == pytest.approx(float(g[pre + ".penalties"].sum()), rel=2e-5)
+            # Adagrad's first steps: compare in units of the learning rate (see tests/test_gpu_parity.py)
+            for got, ref in ((m.get_s_embedder().weight, g[pre + ".ent"]), (m.get_p_embedder().weight, g[pre + ".rel"])):
+                assert (got.detach().cpu() - T(ref)).abs().max().item() <= 0.2 * 2e-3, (captured, step)
