@@ -470,12 +470,12 @@ def test_toy_config_steps_with_penalty_match_reference_golden(kb, golden):
             m.get_s_embedder().weight.copy_(T(g["toy.ent0"]))
             m.get_p_embedder().weight.copy_(T(g["toy.rel0"]))
         job = kb.TrainingJobKvsAll(m, kb.optim.create("Adagrad", m.parameters(), lr=0.2), kb.KgeLoss.create("kl"), e, r)
+        if captured:
+            job.enable_graph_step(len(g["toy.b0.queries"]), nnz_max)
         for step in range(2):
             pre = f"toy.b{step}"
             batch = {"queries": T(g[pre + ".queries"]), "label_coords": T(g[pre + ".label_coords"]),
                      "query_type_indexes": T(g[pre + ".query_type"])}
-            if captured:
-                job.enable_graph_step(len(batch["queries"]), nnz_max)
             res = job.step(step, batch)
             assert res.total_loss == pytest.approx(float(g[pre + ".loss"]), rel=2e-5)
             assert res.penalty == pytest.approx(float(g[pre + ".penalties"].sum()), rel=2e-5)
