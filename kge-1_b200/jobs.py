@@ -71,7 +71,16 @@ class TrainingJob:
         self.fused_path, self.math_mode, self.shard = fused_path, math_mode, shard
         self.device = model.get_s_embedder().weight.device
         self.pre_batch_hooks: List = []
+        self.abort_on_nan = True          # train.abort_on_nan (config-default.yaml:211)
         model.prepare_job(self)
+
+    def _check_cost(self, res: "ProcessBatchResult") -> "ProcessBatchResult":
+        """train.py:341-345: cost = batch loss + penalties; a NaN cost aborts the job (before optimizer.step() on the
+        autograd path; the captured steps have applied their update by the time the loss is read back)."""
+        cost = res.avg_loss + getattr(res, "penalty", 0.0)
+        if self.abort_on_nan and math.isnan(cost):
+            raise FloatingPointError("Cost became nan, aborting training job")
+        return res
 
     def step(self, batch_index: int, batch: dict) -> ProcessBatchResult:
         for f in self.pre_batch_hooks:
@@ -83,6 +92,7 @@ class TrainingJob:
             value.backward()
             penalty += value.item()
         res.penalty = penalty
+        self._check_cost(res)
         self.optimizer.step()
         return res
 
@@ -221,7 +231,7 @@ class TrainingJobKvsAll(TrainingJob):
         value, overflow = torch.stack((loss, dc["overflow"][slot][0].float())).tolist()   # one D2H read, as train.py:747
         if overflow:
             raise ValueError(f"batch has more than {st.nnz_max} labels (enable_graph_step(nnz_max=...))")
-        return ProcessBatchResult(value, st.rows, value)
+        return self._check_cost(ProcessBatchResult(value, st.rows, value))
 
     def device_inputs(self, batch):
         """Host (pinned) KvsAll batch -> device tensors (a_idx, p_idx, row_combine, lab_off, lab_col, perms)."""
@@ -288,7 +298,7 @@ class TrainingJobKvsAll(TrainingJob):
         res = ProcessBatchResult(value, self.stepper.rows, value)
         if self.stepper.pen is not None:
             res.penalty = float(self.stepper.penalty_values.sum().item())   # train.py:320-338 (sum of the terms)
-        return res
+        return self._check_cost(res)
 
     def _process_batch(self, batch_index, batch) -> ProcessBatchResult:
         queries = batch["queries"].to(self.device)
@@ -377,7 +387,7 @@ class TrainingJobNegativeSampling(TrainingJob):
         for slot in st.slots:
             self.sampler.sample(t, slot, out=st.neg[slot])
         value = st.step().item()
-        return ProcessBatchResult(value, st.B)
+        return self._check_cost(ProcessBatchResult(value, st.B))
 
     def step(self, batch_index: int, batch: dict) -> ProcessBatchResult:
         st = self.stepper
@@ -389,7 +399,7 @@ class TrainingJobNegativeSampling(TrainingJob):
             f(self)
         st.set_inputs(batch["triples"], negs)
         value = st.step().item()
-        return ProcessBatchResult(value, st.B)
+        return self._check_cost(ProcessBatchResult(value, st.B))
 
     def _process_batch(self, batch_index, batch) -> ProcessBatchResult:
         triples = batch["triples"].to(self.device)

@@ -182,3 +182,24 @@ def test_sampler_option_errors_match_reference():
         sm.KgeSampler.create("frequency", 10, 3)
     with _pt.raises(ValueError, match="no CPU path"):
         sm.KgeUniformSampler(10, 3, device="cpu")
+
+
+def test_nan_cost_aborts_like_the_reference():
+    """train.py:341-345: cost = avg_loss + penalty; NaN raises FloatingPointError when train.abort_on_nan."""
+    from importlib import import_module
+    import pytest as _pt
+    jobs = import_module("kge-1_b200.jobs")
+    job = object.__new__(jobs.TrainingJob)
+    job.abort_on_nan = True
+    ok = jobs.ProcessBatchResult(1.5, 4)
+    ok.penalty = 0.25
+    assert job._check_cost(ok) is ok
+    bad = jobs.ProcessBatchResult(float("nan"), 4)
+    with _pt.raises(FloatingPointError, match="Cost became nan"):
+        job._check_cost(bad)
+    pen = jobs.ProcessBatchResult(1.0, 4)
+    pen.penalty = float("nan")
+    with _pt.raises(FloatingPointError):
+        job._check_cost(pen)
+    job.abort_on_nan = False
+    assert job._check_cost(bad) is bad
