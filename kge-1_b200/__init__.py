@@ -4,7 +4,7 @@ The directory name follows the build contract; import it as `importlib.import_mo
 through the `kgeb200` alias module at the repository root.
 """
 from . import lib  # noqa: F401  (ctypes binding; loading the .so is deferred to first use)
-from . import ops, fused, index, graph, optim, jobs, model, trainer, sampler, metrics  # noqa: F401
+from . import ops, fused, index, graph, optim, jobs, model, trainer, sampler, metrics, libkge_plugin  # noqa: F401
 from .model import KgeModel, LookupEmbedder, RelationalScorer, ReciprocalRelationsModel  # noqa: F401
 from .jobs import (KgeLoss, TrainingJob1vsAll, TrainingJobKvsAll, TrainingJobNegativeSampling,  # noqa: F401
                    EntityRankingJob)
