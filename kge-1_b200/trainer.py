@@ -27,6 +27,20 @@ def p2p_slice(numel: int, world: int, rank: int):
     return lo, min(numel, lo + per)
 
 
+def gather_owner_slices(flat: torch.Tensor, group) -> torch.Tensor:
+    """Every rank broadcasts the slice of `flat` it owns in the peer-memory exchange (p2p_slice): afterwards all ranks hold
+    the owners' values everywhere.  Used for the optimizer state, which that mode updates on the owner only."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    ranks = dist.get_process_group_ranks(group)
+    n = flat.numel()
+    for r in range(world):
+        lo, hi = p2p_slice(n, world, r)
+        if hi > lo:
+            dist.broadcast(flat[lo:hi], src=ranks[r], group=group)
+    return flat
+
+
 class FusedAllEntityStepper:
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
@@ -327,16 +341,8 @@ class FusedAllEntityStepper:
         complete accumulators again (checkpoints; switching modes)."""
         if self.p2p is None:
             return
-        import torch.distributed as dist
-        x = self.p2p
         for t in (self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]):
-            flat = t.view(-1)
-            n = flat.numel()
-            ranks = dist.get_process_group_ranks(self.dp_group)
-            for r in range(x["world"]):
-                lo, hi = p2p_slice(n, x["world"], r)
-                if hi > lo:
-                    dist.broadcast(flat[lo:hi], src=ranks[r], group=self.dp_group)
+            gather_owner_slices(t.view(-1), self.dp_group)
 
     def _stage_apply_dp(self):
         """Data-parallel mode: both Adagrad steps after the gradient all-reduce."""

@@ -203,3 +203,63 @@ def test_nan_cost_aborts_like_the_reference():
         job._check_cost(pen)
     job.abort_on_nan = False
     assert job._check_cost(bad) is bad
+
+
+def _p2p_protocol_worker(rank, world, port, out):
+    """The peer-memory exchange (csrc/p2p.cu) restated with gloo collectives on host tensors: every rank contributes a
+    gradient, the slice owner sums the contributions in rank order, applies Adagrad to its slice of weights and state
+    and the new weights are gathered -- the result must equal all-reduce(sum) + a full Adagrad step on every rank, and
+    gather_owner_slices must restore the sharded state."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from importlib import import_module
+        tr = import_module("kge-1_b200.trainer")
+        n, lr, eps = 1003 * 4, 0.2, 1e-10
+        gen = torch.Generator().manual_seed(5)
+        w0 = torch.randn(n, generator=gen)
+        grads = [torch.randn(n, generator=gen) * 0.1 for _ in range(world)]     # every rank can rebuild all of them
+        # reference: all-reduce in rank order + full update everywhere
+        g_sum = torch.zeros(n)
+        for g in grads:
+            g_sum = g_sum + g
+        s_ref = g_sum * g_sum
+        w_ref = w0 - lr * g_sum / (s_ref.sqrt() + eps)
+        # protocol: owner slices
+        w, state = w0.clone(), torch.zeros(n)
+        gathered = [torch.empty(n) for _ in range(world)]
+        dist.all_gather(gathered, grads[rank])                                   # "peer-mapped" gradient buffers
+        lo, hi = tr.p2p_slice(n, world, rank)
+        g = torch.zeros(hi - lo)
+        for k in range(world):
+            g = g + gathered[k][lo:hi]
+        state[lo:hi] += g * g
+        w[lo:hi] -= lr * g / (state[lo:hi].sqrt() + eps)
+        staged = [torch.empty(n) for _ in range(world)]
+        dist.all_gather(staged, w)                                               # owners push their slices
+        for k in range(world):
+            klo, khi = tr.p2p_slice(n, world, k)
+            if k != rank:
+                w[klo:khi] = staged[k][klo:khi]
+        assert torch.equal(w, w_ref), "weights differ from all-reduce + full update"
+        assert not torch.equal(state, s_ref) and torch.equal(state[lo:hi], s_ref[lo:hi])
+        tr.gather_owner_slices(state, dist.group.WORLD)
+        assert torch.equal(state, s_ref), "state shards not restored"
+        out.put((rank, "ok"))
+    except Exception as ex:  # pragma: no cover
+        out.put((rank, repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_exchange_protocol_over_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_p2p_protocol_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    res = dict(out.get() for _ in range(2))
+    assert res == {0: "ok", 1: "ok"}, res
