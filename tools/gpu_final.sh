@@ -1,4 +1,5 @@
 #!/bin/bash
+# usage (from the repo root): gpurun --timeout 2400 -- bash tools/gpu_final.sh
 # Round-end style validation on one B200: parity tests, smoke, both bench arms, ncu launch list + full capture, other workloads
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log

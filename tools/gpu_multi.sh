@@ -1,4 +1,5 @@
 #!/bin/bash
+# usage: gpurun --gpus N --timeout 800 -- bash tools/gpu_multi.sh N   (peer-memory mode against NCCL: check + bench in both modes)
 N=${1:-4}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
