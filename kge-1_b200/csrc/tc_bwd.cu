@@ -25,7 +25,16 @@ namespace tcb {
 using namespace kgeb::tc;
 
 constexpr int RES_ROWS = 128;                    // UMMA M
-constexpr int STR_ROWS = 64;                     // UMMA N of MMA1, K of MMA2
+// Rows of a streamed tile = UMMA N of MMA1 = K of MMA2.  64 is the measured default.  KGEB_STR_ROWS=128 (tuning build,
+// NOT yet run on hardware) halves the per-score cost of everything that is paid per tile -- barrier probes, fences,
+// TMEM-load latency -- and issues MMA1 with N = 128 (8 KB of shared-memory operands per 262 k MAC instead of 6 KB per
+// 131 k); each epilogue warp then walks its 64 columns in two passes of 32 so that the register budget is unchanged.
+#ifndef KGEB_STR_ROWS
+#define KGEB_STR_ROWS 64
+#endif
+constexpr int STR_ROWS = KGEB_STR_ROWS;          // UMMA N of MMA1, K of MMA2
+static_assert(STR_ROWS == 64 || STR_ROWS == 128, "KGEB_STR_ROWS must be 64 or 128");
+constexpr int PASSES = STR_ROWS / 64;            // epilogue passes of 32 columns per warp and tile
 constexpr int RES_SLAB = RES_ROWS * 128;         // 16 KiB: 128 rows x 128 B
 constexpr int STR_SLAB = STR_ROWS * 128;         // 8 KiB:  64 rows x 128 B
 constexpr int MAX_STR = 8;                       // streamed-tile ring depth
@@ -33,7 +42,7 @@ constexpr int EPQ = 4;                            // epilogue warps per TMEM lan
 constexpr int NUM_EPI_THREADS = 4 * EPQ * 32;     // 512
 constexpr int NUM_THREADS = 128 + NUM_EPI_THREADS;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-19: epilogue
 constexpr int NUM_GROUP_THREADS = NUM_EPI_THREADS / 2;  // two epilogue groups ping-pong on alternate streamed tiles
-constexpr int COLS_PER_WARP = STR_ROWS / (EPQ / 2);     // 32 S-columns per warp of a group
+constexpr int COLS_PER_WARP = 32;                       // S-columns per warp, pass and tile
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int STAGE_BYTES = RES_ROWS * 128;      // flush staging box of one column part (dTable kernel)
 
@@ -107,7 +116,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 12);
   constexpr int TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0;                 // two S buffers of 64 columns: [0,64), [64,128)
-  constexpr uint32_t O_COL = 128;               // OUT accumulator: d <= 256 columns at [128, 384)
+  constexpr uint32_t O_COL = 2 * STR_ROWS;      // OUT accumulator: d <= 256 columns behind the two S buffers
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_res);
@@ -285,6 +294,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         KGEB_TRW(9, u);
         sph ^= 1;
         tc_fence_after();
+#if KGEB_STR_ROWS == 64   // the measured kernel, kept textually as it ran on hardware
         float v[COLS_PER_WARP];
         tmem_ld32(lane_addr + S_COL + (uint32_t)(bufi * STR_ROWS + sub * COLS_PER_WARP), v);
         tc_fence_before();
@@ -417,6 +427,148 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         KGEB_TRW(13, u);
         gph ^= 1;
       }
+#else                     // two passes of 32 columns per warp (tuning build, see KGEB_STR_ROWS above)
+        float v[COLS_PER_WARP];
+#pragma unroll 1
+        for (int pass = 0; pass < PASSES; ++pass) {
+        const int cw0 = sub * (COLS_PER_WARP * PASSES) + pass * COLS_PER_WARP;   // first tile column of this warp and pass
+        tmem_ld32(lane_addr + S_COL + (uint32_t)(bufi * STR_ROWS + cw0), v);
+        if (pass == PASSES - 1) {
+          tc_fence_before();
+          mbar_arrive_warp(&s_empty[bufi]);
+          KGEB_TRW(10, u);  // S values are in registers: MMA1 of the tile after next may overwrite them
+        }
+        // Rows / columns beyond the matrices were zero-filled by TMA, so whatever finite G they get multiplies
+        // zeros in MMA2; only the parameter loads are clamped.
+        const int64_t qbase = u * STR_ROWS + cw0;
+        // STATS: entity columns beyond the table end were zero-filled, their score is exactly 0: count them here
+        // and take their known contribution (softplus(off), off) out once per job instead of masking per element
+        if (STATS) n_pad += COLS_PER_WARP - (int)max((int64_t)0, min((int64_t)COLS_PER_WARP, p.n_str - qbase));
+        // Per-column parameters (columns are query rows when RES is the entity tile): lane c of the warp loads
+        // those of column c once per tile, the element loop fetches them with one shuffle.  KL folds everything
+        // into one exponent offset:  rs * exp(x - lse) = ex2(x * log2e + kc),  kc = (log(rs) - lse) * log2e.
+        float col_k = 0.f, col_rs = my_rs;
+        if (!RES_IS_Q) {
+          const int64_t q = min(qbase + lane, p.B - 1);
+          col_rs = HAS_RS ? p.inv_batch * __ldg(p.row_scale + q) : p.inv_batch;
+          if (LOSS == KGEB_LOSS_KL) col_k = (__logf(col_rs) - __ldg(p.lse + q)) * kLog2e;
+        } else if (LOSS == KGEB_LOSS_KL) {
+          col_k = (__logf(my_rs) - my_lse) * kLog2e;   // rows beyond B: log(0) = -inf -> G = 0
+        }
+        if (LOSS == KGEB_LOSS_KL) {
+#pragma unroll
+          for (int c = 0; c < COLS_PER_WARP; ++c) {
+            const float kc = RES_IS_Q ? col_k : __shfl_sync(0xffffffffu, col_k, c);
+            const float a = fmaf(v[c], kLog2e, kc);
+            v[c] = ((c & 7) < KGEB_POLY8_KL) ? ex2_poly<3, false>(a) : ex2_ftz(a);
+          }
+        } else {
+          // BCE, four columns per iteration.  MUFU diet (the XU pipe has 16 lanes/clk/SM, the FMA pipe 128; the pipeline
+          // trace (tools/trace_bwd.py) shows the epilogue warps spending 55-75 % of a tile in this loop with the XU pipe
+          // ~80 % busy, i.e. these kernels are bound by MUFU throughput):
+          //  * KGEB_RCP_GROUP = 2 | 4: the reciprocals of a group come from ONE rcp of the product of the group (batch
+          //    inversion, 1/a0 = a1 / (a0 a1) ...): 1 MUFU + 3 | 9 FMUL instead of 2 | 4 MUFU; relative error ~4 ulp;
+          //  * KGEB_LG2_GROUP = 4..32: sum lg2(a_i) = lg2(prod a_i); a_i in [1, 2], so a product of <= 32 factors stays
+          //    far inside the fp32 range and costs one FMUL per factor instead of one MUFU.
+          constexpr int RG = KGEB_RCP_GROUP, LG = KGEB_LG2_GROUP;
+          static_assert(RG == 1 || RG == 2 || RG == 4, "KGEB_RCP_GROUP must be 1, 2 or 4");
+          static_assert(LG == 1 || (LG % 4 == 0 && COLS_PER_WARP % LG == 0), "KGEB_LG2_GROUP must be 1 or a multiple of 4");
+          float prod = 1.f;
+          const float nls = -p.ls_add;
+          // exponent clamp of the non-STATS form: the product of a group must stay finite (the sigmoid of z < -20.8
+          // (-41.6) then reads 9e-10 (9e-19), far below the bf16 resolution of G next to any other entry)
+          const float tmax = RG == 4 ? 30.f : 60.f;
+#pragma unroll
+          for (int c = 0; c < COLS_PER_WARP; c += 4) {
+            float z[4], e[4], a[4], r[4], rs[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              rs[j] = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c + j) : col_rs;
+              float t;
+              if (STATS) {
+                // sigmoid and softplus from one exponential, cancellation-free:
+                //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
+                z[j] = v[c + j] + p.offset;
+                t = fabsf(z[j]) * -kLog2e;
+                e[j] = (((c + j) & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t) : ex2_ftz(t);
+              } else {
+                // rs * (sigmoid(x + offset) - ls_add) = rs / (1 + exp(-(x + offset))) - rs ls_add
+                t = fmaf(v[c + j], -kLog2e, off2);
+                if (RG > 1) t = fminf(t, tmax);
+                e[j] = (((c + j) & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t) : ex2_ftz(t);
+              }
+              a[j] = 1.f + e[j];
+            }
+            const float p01 = a[0] * a[1], p23 = a[2] * a[3];
+            if (RG == 1) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) r[j] = rcp_ftz(a[j]);   // e = inf for very negative z -> rcp gives 0
+            } else if (RG == 2) {
+              const float i01 = rcp_ftz(p01), i23 = rcp_ftz(p23);
+              r[0] = i01 * a[1]; r[1] = i01 * a[0]; r[2] = i23 * a[3]; r[3] = i23 * a[2];
+            } else {
+              const float ri = rcp_ftz(p01 * p23);
+              const float i01 = ri * p23, i23 = ri * p01;
+              r[0] = i01 * a[1]; r[1] = i01 * a[0]; r[2] = i23 * a[3]; r[3] = i23 * a[2];
+            }
+            if (STATS) {
+              if (LG > 1) {
+                prod *= p01 * p23;
+                if (((c + 4) % LG) == 0) {
+                  st_lg += lg2_ftz(prod);
+                  prod = 1.f;
+                }
+              } else {
+                st_lg += (lg2_ftz(a[0]) + lg2_ftz(a[1])) + (lg2_ftz(a[2]) + lg2_ftz(a[3]));
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                st_mx += fmaxf(z[j], 0.f);
+                st_x += z[j];
+                v[c + j] = fmaf(z[j] >= 0.f ? r[j] : e[j] * r[j], rs[j], nls * rs[j]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[c + j] = fmaf(r[j], rs[j], nls * rs[j]);
+            }
+          }
+        }
+        if (pass == 0) {
+          KGEB_TRW(11, u);
+          mbar_wait(&g_empty[bufi], gph ^ 1);  // MMA2 of this buffer's previous tile has finished reading it
+          KGEB_TRW(12, u);
+        }
+        uint8_t* gb = g_smem + (size_t)bufi * G_BYTES;
+        if (BF16) {
+          // row trow of K-slab cw0 / 64: this warp's 32 bf16 = four 16-byte chunks from (cw0 % 64) / 8 on, 128-byte swizzle
+          // (shared-window address + st.shared: through the generic pointer these are ST.E, resolved in the LSU)
+          const uint32_t rowa = smem_s + (uint32_t)(KS * RES_SLAB + bufi * G_BYTES + (cw0 / SLAB_K) * RES_SLAB + trow * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[k * 8 + j * 2 + 1]), "f"(v[k * 8 + j * 2]));
+            const int ck = (cw0 % SLAB_K) / 8 + k;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (uint32_t)((ck ^ (trow & 7)) << 4)),
+                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
+        } else {
+          // TF32: K-slabs of 32 fp32 columns; this warp's 32 columns of this pass are slab cw0 / 32
+          uint8_t* rowp = gb + (size_t)(cw0 / SLAB_K) * RES_SLAB + (size_t)trow * 128;
+#pragma unroll
+          for (int ck = 0; ck < 8; ++ck)
+            *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) =
+                make_float4(v[ck * 4], v[ck * 4 + 1], v[ck * 4 + 2], v[ck * 4 + 3]);
+        }
+        }  // pass
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive_warp(&g_full[bufi]);
+        KGEB_TRW(13, u);
+        gph ^= 1;
+      }
+#endif
       if (STATS && res_row < p.B) {
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
         const float zp = p.offset;
