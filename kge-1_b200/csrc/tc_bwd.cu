@@ -34,7 +34,7 @@ constexpr int RES_ROWS = 128;                    // UMMA M
 #endif
 constexpr int STR_ROWS = KGEB_STR_ROWS;          // UMMA N of MMA1, K of MMA2
 static_assert(STR_ROWS == 64 || STR_ROWS == 128, "KGEB_STR_ROWS must be 64 or 128");
-constexpr int PASSES = STR_ROWS / 64;            // epilogue passes of 32 columns per warp and tile
+[[maybe_unused]] constexpr int PASSES = STR_ROWS / 64;   // epilogue passes of 32 columns per warp and tile
 constexpr int RES_SLAB = RES_ROWS * 128;         // 16 KiB: 128 rows x 128 B
 constexpr int STR_SLAB = STR_ROWS * 128;         // 8 KiB:  64 rows x 128 B
 constexpr int MAX_STR = 8;                       // streamed-tile ring depth
@@ -117,6 +117,10 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
   constexpr int TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0;                 // two S buffers of 64 columns: [0,64), [64,128)
   constexpr uint32_t O_COL = 2 * STR_ROWS;      // OUT accumulator: d <= 256 columns behind the two S buffers
+#ifdef KGEB_G_TMEM
+  constexpr uint32_t G_COL = 448;               // two G buffers of STR_ROWS / 2 columns at [448, 512)
+  static_assert(STR_ROWS == 64, "KGEB_G_TMEM: the G buffers fit behind the accumulator for 64-row tiles only");
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_res);
@@ -245,7 +249,13 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
             const int kcol = km * UMMA_K;
             const uint64_t ad = abase + (uint64_t)((ga + (kcol / SLAB_K) * RES_SLAB + (kcol % SLAB_K) * Elem<BF16>::kBytes) >> 4);
             const uint64_t bd = bbase + (uint64_t)((sa + kcol * 128) >> 4);
+#ifdef KGEB_G_TMEM
+            (void)ad;
+            umma_ts_bf16(acc, tbase + G_COL + (uint32_t)(gbuf * (STR_ROWS / 2) + km * (UMMA_K / 2)), bd, idesc2,
+                         !(u == u0 && km == 0));
+#else
             umma<BF16>(acc, ad, bd, idesc2, !(u == u0 && km == 0));
+#endif
           }
           umma_commit(&str_empty[slot]);  // streamed tile free once MMA2 has read it (MMA1 of it finished long ago)
           umma_commit(&g_empty[gbuf]);
@@ -294,7 +304,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         KGEB_TRW(9, u);
         sph ^= 1;
         tc_fence_after();
-#if KGEB_STR_ROWS == 64   // the measured kernel, kept textually as it ran on hardware
+#if KGEB_STR_ROWS == 64 && !defined(KGEB_G_TMEM)   // the measured kernel, kept textually as it ran on hardware
         float v[COLS_PER_WARP];
         tmem_ld32(lane_addr + S_COL + (uint32_t)(bufi * STR_ROWS + sub * COLS_PER_WARP), v);
         tc_fence_before();
@@ -427,7 +437,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         KGEB_TRW(13, u);
         gph ^= 1;
       }
-#else                     // two passes of 32 columns per warp (tuning build, see KGEB_STR_ROWS above)
+#else   // tuning builds: PASSES passes of 32 columns per warp (KGEB_STR_ROWS) and / or G through tensor memory (KGEB_G_TMEM)
         float v[COLS_PER_WARP];
 #pragma unroll 1
         for (int pass = 0; pass < PASSES; ++pass) {
@@ -538,6 +548,17 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           mbar_wait(&g_empty[bufi], gph ^ 1);  // MMA2 of this buffer's previous tile has finished reading it
           KGEB_TRW(12, u);
         }
+#ifdef KGEB_G_TMEM
+        {
+          // G as the A operand of MMA2 in TENSOR memory (tcgen05.mma [d], [a], b-desc: A K-major, lane = row, two bf16 per
+          // 32-bit column): no shared-memory round trip of G, no generic->async proxy fence
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+          tmem_st16(lane_addr + G_COL + (uint32_t)(bufi * (STR_ROWS / 2) + cw0 / 2), w);
+        }
+#else
         uint8_t* gb = g_smem + (size_t)bufi * G_BYTES;
         if (BF16) {
           // row trow of K-slab cw0 / 64: this warp's 32 bf16 = four 16-byte chunks from (cw0 % 64) / 8 on, 128-byte swizzle
@@ -562,8 +583,14 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
             *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) =
                 make_float4(v[ck * 4], v[ck * 4 + 1], v[ck * 4 + 2], v[ck * 4 + 3]);
         }
+#endif
         }  // pass
+#ifdef KGEB_G_TMEM
+        tmem_wait_st();
+        tc_fence_before();
+#else
         fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+#endif
         mbar_arrive_warp(&g_full[bufi]);
         KGEB_TRW(13, u);
         gph ^= 1;
