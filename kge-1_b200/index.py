@@ -155,3 +155,45 @@ def merge_sorted_csr(parts: Sequence[Tuple[torch.Tensor, torch.Tensor]], num_row
     off = torch.zeros(num_rows + 1, dtype=torch.int64, device=dev)
     off[1:] = torch.cumsum(torch.bincount(r, minlength=num_rows), 0)
     return off, c.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# drill-down indexes of the evaluation job (kge/indexing.py:142-263); built once on the host like the reference does
+# ---------------------------------------------------------------------------------------------
+def relation_types(train_triples, num_relations: int) -> List[str]:
+    """"1-1" / "1-N" / "M-1" / "M-N" per relation (indexing.py:142-179, after Bordes et al. 2013): M if a (p, o) pair of
+    the relation has more than 1.5 subjects on average, N if an (s, p) pair has more than 1.5 objects on average."""
+    t = np.asarray(train_triples.cpu() if isinstance(train_triples, torch.Tensor) else train_triples).astype(np.int64)
+    out = []
+    po = np.unique(t[:, [1, 2]], axis=0)
+    sp = np.unique(t[:, [0, 1]], axis=0)
+    n_triples = np.bincount(t[:, 1], minlength=num_relations).astype(np.float32)
+    n_po = np.bincount(po[:, 0], minlength=num_relations).astype(np.float32)
+    n_sp = np.bincount(sp[:, 1], minlength=num_relations).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        is_m = (n_triples / n_po) > 1.5        # 0/0 = nan -> False, as in the reference's float tensor
+        is_n = (n_triples / n_sp) > 1.5
+    for i in range(num_relations):
+        out.append("{}-{}".format("M" if is_m[i] else "1", "N" if is_n[i] else "1"))
+    return out
+
+
+def relations_per_type(train_triples, num_relations: int) -> Dict[str, List[int]]:
+    """indexing.py:182-197."""
+    res: Dict[str, List[int]] = {}
+    for i, k in enumerate(relation_types(train_triples, num_relations)):
+        res.setdefault(k, []).append(i)
+    return res
+
+
+def frequency_percentiles(train_triples, num_entities: int, num_relations: int) -> Dict[str, Dict[str, List[int]]]:
+    """indexing.py:200-263: ids sorted by their training frequency in the slot (ascending, ties by id), cut at 25 / 50 /
+    75 % of the vocabulary: {"subject" | "relation" | "object": {"25%" | "50%" | "75%" | "top": ids}}."""
+    t = np.asarray(train_triples.cpu() if isinstance(train_triples, torch.Tensor) else train_triples).astype(np.int64)
+    res: Dict[str, Dict[str, List[int]]] = {}
+    for arg, col, num in (("subject", 0, num_entities), ("relation", 1, num_relations), ("object", 2, num_entities)):
+        order = np.argsort(np.bincount(t[:, col], minlength=num), kind="stable")
+        res[arg] = {}
+        for perc, (begin, end) in (("25%", (0.0, 0.25)), ("50%", (0.25, 0.5)), ("75%", (0.5, 0.75)), ("top", (0.75, 1.0))):
+            res[arg][perc] = sorted(int(x) for x in order[int(begin * num):int(end * num)])
+    return res

@@ -505,11 +505,13 @@ class EntityRankingJob:
 
     @torch.no_grad()
     def run(self, triples, head_and_tail: bool = False,
-            relations_per_type: Optional[Dict[str, Sequence[int]]] = None) -> Dict[str, object]:
+            relations_per_type: Optional[Dict[str, Sequence[int]]] = None,
+            frequency_percentiles: Optional[Dict[str, Dict[str, Sequence[int]]]] = None) -> Dict[str, object]:
         """Ranks every triple and reduces the ranks to histograms + metrics on the device.  `head_and_tail` adds the
         "head" / "tail" histograms of eval.py:151-171, `relations_per_type` ({type: relation ids}) the drill-down of
-        hist_per_relation_type (eval.py:173-198); metric names follow entity_ranking.py:370-381
-        ("mean_rank_filtered_head", "hits_at_10_1-N_tail", ...)."""
+        hist_per_relation_type (eval.py:173-198), `frequency_percentiles` ({"subject" | "relation" | "object": {perc:
+        ids}}, index.frequency_percentiles) that of hist_per_frequency_percentile (eval.py:201-224); metric names follow
+        entity_ranking.py:370-381 ("mean_rank_filtered_head", "hits_at_10_1-N_tail", "hits_at_1_subject_25%", ...)."""
         from . import metrics as dm
         was_training = self.model.training
         self.model.eval()
@@ -520,12 +522,19 @@ class EntityRankingJob:
         hists = {n: {"all": zeros()} for n in names}
         rel_sets = {t: torch.as_tensor(sorted(set(int(r) for r in rels)), dtype=torch.int64, device=self.device)
                     for t, rels in (relations_per_type or {}).items()}
+        as_set = lambda ids: torch.as_tensor(sorted(set(int(x) for x in ids)), dtype=torch.int64, device=self.device)  # noqa: E731
+        freq_sets = {arg: {perc: as_set(ids) for perc, ids in percs.items()}
+                     for arg, percs in (frequency_percentiles or {}).items()}
         status = torch.zeros(1, dtype=torch.int32, device=self.device)
         all_ranks: Dict[str, List[torch.Tensor]] = {}
         for lo in range(0, len(triples), self.batch_size):
             batch = triples[lo:lo + self.batch_size]
             res = self.rank_batch(batch)
             masks = {t: dm.isin_sorted(batch[:, P].to(self.device), rs) for t, rs in rel_sets.items()}
+            # eval.py:201-224: subject ranks count for the subject's percentile, object ranks for the object's, both for
+            # the relation's
+            fmask = {(arg, perc): dm.isin_sorted(batch[:, {"subject": S, "relation": P, "object": O}[arg]].to(self.device), ids)
+                     for arg, percs in freq_sets.items() for perc, ids in percs.items()}
             for k, v in res.items():
                 all_ranks.setdefault(k, []).append(v)
                 side, name = k[0], k[1:]               # "o_raw" -> tail ranks of the raw setting
@@ -534,6 +543,9 @@ class EntityRankingJob:
                 dm.rank_hist(v, E, h["all"], status=status)
                 if head_and_tail:
                     dm.rank_hist(v, E, h.setdefault("tail" if side == "o" else "head", zeros()), status=status)
+                for (arg, perc), m in fmask.items():
+                    if arg == "relation" or arg == ("object" if side == "o" else "subject"):
+                        dm.rank_hist(v, E, h.setdefault(f"{arg}_{perc}", zeros()), mask=m, status=status)
                 for t, m in masks.items():
                     dm.rank_hist(v, E, h.setdefault(t, zeros()), mask=m, status=status)
                     if head_and_tail:

@@ -596,6 +596,30 @@ def model_penalties(ent_w: torch.Tensor, rel_w: torch.Tensor, triples: torch.Ten
             lp_penalty(ent_w, p, w_ent, triples[:, O], weighted)]
 
 
+def frequency_histograms(ranks: Dict[str, torch.Tensor], triples: torch.Tensor, num_entities: int,
+                         percentiles: Dict[str, Dict[str, Sequence[int]]]) -> Dict[str, torch.Tensor]:
+    """eval.py:201-224 (hist_per_frequency_percentile) for one filter setting: "subject_<perc>" counts the subject ranks
+    of triples whose subject is in the percentile, "object_<perc>" the object ranks likewise, "relation_<perc>" both."""
+    h: Dict[str, torch.Tensor] = {}
+    for arg, percs in percentiles.items():
+        for perc in percs:
+            h[f"{arg}_{perc}"] = torch.zeros(num_entities)
+    s, p, o = (triples[:, i].tolist() for i in range(3))
+    for perc in percentiles["subject"]:
+        subj, rel, obj = (set(int(x) for x in percentiles[a][perc]) for a in ("subject", "relation", "object"))
+        for i, r in enumerate(ranks["s"].tolist()):
+            if s[i] in subj:
+                h[f"subject_{perc}"][r] += 1
+            if p[i] in rel:
+                h[f"relation_{perc}"][r] += 1
+        for i, r in enumerate(ranks["o"].tolist()):
+            if o[i] in obj:
+                h[f"object_{perc}"][r] += 1
+            if p[i] in rel:
+                h[f"relation_{perc}"][r] += 1
+    return h
+
+
 def grouped_rank_histograms(ranks: Dict[str, torch.Tensor], relations: torch.Tensor, num_entities: int,
                             relations_per_type: Optional[Dict[str, Sequence[int]]] = None,
                             head_and_tail: bool = False) -> Dict[str, torch.Tensor]:

@@ -186,3 +186,50 @@ def test_toy_config_steps_with_penalty_oracle_matches_reference(aux2):
         opt.step()
         np.testing.assert_allclose(prm.ent.detach().numpy(), aux2[pre + ".ent"], rtol=0, atol=1e-6)
         np.testing.assert_allclose(prm.rel.detach().numpy(), aux2[pre + ".rel"], rtol=0, atol=1e-6)
+
+
+@pytest.fixture(scope="module")
+def aux3():
+    return np.load(os.path.join(GOLD, "aux3.npz"), allow_pickle=False)
+
+
+def test_drilldown_indexes_match_reference(aux3):
+    """Host-side restatements in kge-1_b200/index.py against kge/indexing.py:142-263 (bit-exact sets)."""
+    from importlib import import_module
+    ix = import_module("kge-1_b200.index")
+    train, e, r = aux3["graph.train"], 53, 7
+    assert ix.relation_types(train, r) == [str(x) for x in aux3["relation_types"]]
+    rpt = ix.relations_per_type(train, r)
+    assert set(rpt) == {k.split(".", 1)[1] for k in aux3.files if k.startswith("relations_of.")}
+    for t, rels in rpt.items():
+        assert rels == aux3[f"relations_of.{t}"].tolist()
+    fp = ix.frequency_percentiles(train, e, r)
+    for arg, percs in fp.items():
+        for perc, ids in percs.items():
+            assert ids == aux3[f"percentile.{arg}.{perc}"].tolist(), (arg, perc)
+
+
+def test_argument_frequency_metrics_oracle_matches_reference(aux3):
+    """eval.py:173-224 + entity_ranking.py:370-381: per-relation-type and per-frequency-percentile metrics."""
+    from importlib import import_module
+    ix = import_module("kge-1_b200.index")
+    g = {k: aux3[f"graph.{k}"] for k in ("train", "valid", "test")}
+    e, r = 53, 7
+    ent, rel = torch.from_numpy(aux3["ent"]), torch.from_numpy(aux3["rel"])
+    _, ranks = ko.entity_ranking("distmult", ent, rel, g["valid"], [g["train"], g["valid"]], g["test"], batch_size=16,
+                                 hits_at_k=(1, 3, 10))
+    rpt, fp = ix.relations_per_type(g["train"], r), ix.frequency_percentiles(g["train"], e, r)
+    vt = torch.from_numpy(g["valid"].astype(np.int64))
+    got = {}
+    for n, sfx in {"_raw": "", "_filt": "_filtered", "_filt_test": "_filtered_with_test"}.items():
+        rk = {"s": ranks["s" + n], "o": ranks["o" + n]}
+        hs = ko.grouped_rank_histograms(rk, vt[:, 1], e, rpt, False)
+        hs.update(ko.frequency_histograms(rk, vt, e, fp))
+        for key, h in hs.items():
+            for k, v in ko.metrics_from_hist(h, (1, 3, 10)).items():
+                got[k + sfx + ("" if key == "all" else "_" + key)] = v
+    keys = [str(k) for k in aux3["keys"]]
+    assert len(keys) > 150
+    for k in keys:
+        assert k in got, k
+        assert abs(got[k] - float(aux3[f"value.{k}"])) <= 1e-6, (k, got[k], float(aux3[f"value.{k}"]))

@@ -482,3 +482,24 @@ def test_toy_config_steps_with_penalty_match_reference_golden(kb, golden):
             # Adagrad's first steps: compare in units of the learning rate (see tests/test_gpu_parity.py)
             for got, ref in ((m.get_s_embedder().weight, g[pre + ".ent"]), (m.get_p_embedder().weight, g[pre + ".rel"])):
                 assert (got.detach().cpu() - T(ref)).abs().max().item() <= 0.2 * 2e-3, (captured, step)
+
+
+@_unconfirmed
+def test_argument_frequency_metrics_match_reference_golden(kb, golden):
+    """eval.py:173-224 through the device kernels (kgeb_isin_sorted masks + kgeb_rank_hist + kgeb_rank_metrics); the
+    host control flow is verified on the CPU in tests/test_host_logic.py."""
+    g = golden("aux3")
+    graph = {k: g[f"graph.{k}"] for k in ("train", "valid", "test")}
+    ent, rel = g["ent"], g["rel"]
+    e, r = ent.shape[0], rel.shape[0]
+    m = kb.KgeModel("distmult", e, r, ent.shape[1]).cuda()
+    with torch.no_grad():
+        m.get_s_embedder().weight.copy_(T(ent))
+        m.get_p_embedder().weight.copy_(T(rel))
+    ev = kb.EntityRankingJob(m, e, [graph["train"], graph["valid"]], graph["test"], batch_size=16, hits_at_k_s=(1, 3, 10))
+    got = ev.run(graph["valid"], relations_per_type=kb.index.relations_per_type(graph["train"], r),
+                 frequency_percentiles=kb.index.frequency_percentiles(graph["train"], e, r))["metrics"]
+    keys = [str(k) for k in g["keys"]]
+    assert len(keys) > 150
+    for k in keys:
+        assert k in got and abs(got[k] - float(g[f"value.{k}"])) <= 1e-6, (k, got.get(k), float(g[f"value.{k}"]))

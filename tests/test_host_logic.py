@@ -263,3 +263,56 @@ def test_peer_memory_exchange_protocol_over_gloo_world2():
         p.join(120)
     res = dict(out.get() for _ in range(2))
     assert res == {0: "ok", 1: "ok"}, res
+
+
+def test_entity_ranking_run_control_flow_with_cpu_stand_ins(golden, monkeypatch):
+    """EntityRankingJob.run's host side (which ranks go to which histogram, metric names) with the device kernels
+    replaced by torch-CPU stand-ins and the ranks taken from the oracle: the metrics must equal the reference's golden
+    values for the head/tail, relation-type and argument-frequency drill-downs (eval.py:138-224)."""
+    from importlib import import_module
+    from oracle import kge_oracle as ko
+    jobs, dm, ix = (import_module("kge-1_b200." + m) for m in ("jobs", "metrics", "index"))
+
+    def rank_hist(ranks, num_entities, hist=None, mask=None, status=None):
+        r = ranks if mask is None else ranks[mask.bool()]
+        hist += torch.bincount(r, minlength=num_entities).float()
+        return hist
+
+    monkeypatch.setattr(dm, "rank_hist", rank_hist)
+    monkeypatch.setattr(dm, "isin_sorted", lambda v, s: torch.isin(v.long(), s).to(torch.uint8))
+    monkeypatch.setattr(dm, "rank_metrics", lambda hist, ks, suffix="": {
+        k + suffix: v for k, v in ko.metrics_from_hist(hist, tuple(ks)).items()})
+
+    class Model:
+        training = False
+
+        def eval(self):
+            pass
+
+    for name, base, head_tail in (("aux", "complex", True), ("aux3", "distmult", False)):
+        g = golden(name)
+        pre = "metrics." if name == "aux" else ""
+        graph = {k: g[f"{pre}graph.{k}"] for k in ("train", "valid", "test")}
+        ent, rel = torch.from_numpy(g[pre + "ent"]), torch.from_numpy(g[pre + "rel"])
+        e, r = ent.shape[0], 7
+        _, ranks = ko.entity_ranking(base, ent, rel, graph["valid"], [graph["train"], graph["valid"]], graph["test"],
+                                     batch_size=16, hits_at_k=(1, 3, 10))
+        job = object.__new__(jobs.EntityRankingJob)
+        job.model, job.num_entities, job.batch_size, job.hits_at_k_s = Model(), e, 16, (1, 3, 10)
+        job.test_indexes, job.device = object(), torch.device("cpu")
+        pos = {"n": 0}
+
+        def rank_batch(batch, pos=pos, ranks=ranks):
+            lo = pos["n"]
+            pos["n"] += len(batch)
+            return {k: v[lo:lo + len(batch)] for k, v in ranks.items()}
+
+        job.rank_batch = rank_batch
+        rpt = ix.relations_per_type(graph["train"], r)
+        fp = ix.frequency_percentiles(graph["train"], e, r) if name == "aux3" else None
+        got = job.run(graph["valid"].astype(np.int64), head_and_tail=head_tail, relations_per_type=rpt,
+                      frequency_percentiles=fp)["metrics"]
+        keys = [str(k) for k in g[pre + "keys"]]
+        for k in keys:
+            want = float(g[f"{pre}value.{k}"])
+            assert k in got and abs(got[k] - want) <= 1e-6, (name, k, got.get(k), want)
