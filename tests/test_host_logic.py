@@ -316,3 +316,62 @@ def test_entity_ranking_run_control_flow_with_cpu_stand_ins(golden, monkeypatch)
         for k in keys:
             want = float(g[f"{pre}value.{k}"])
             assert k in got and abs(got[k] - want) <= 1e-6, (name, k, got.get(k), want)
+
+
+def _cpu_stand_ins(monkeypatch):
+    """Replaces the kernel-backed ops used by kge-1_b200/model.py with oracle calls on host tensors, so that the model
+    API's host logic (which embeddings go where, index arithmetic, views) can be checked without a GPU."""
+    from importlib import import_module
+    from oracle import kge_oracle as ko
+    ops, lib = import_module("kge-1_b200.ops"), import_module("kge-1_b200.lib")
+
+    class Query:
+        def __init__(self, model, combine, a, p):
+            self.model, self.combine, self.a, self.p = model, combine, a, p
+
+    monkeypatch.setattr(ops, "gather_rows", lambda w, idx, sparse=False: w[idx.long()])
+    monkeypatch.setattr(ops, "score_spo_emb", lambda model, ln, s, p, o: ko.score_emb(model, s, p, o, "spo", ln).view(-1))
+    monkeypatch.setattr(ops, "score_spo_indexed",
+                        lambda model, ln, ew, rw, s, p, o: ko.score_spo(model, ew, rw, s.long(), p.long(), o.long(), ln).view(-1))
+    monkeypatch.setattr(ops, "query_build", lambda model, combine, a, p: Query(model, combine, a, p))
+    monkeypatch.setattr(ops, "score_all", lambda kind, q, cand, math=0: (
+        ko.score_emb(q.model, q.a, q.p, cand, "sp_") if q.combine == lib.SP_ else ko.score_emb(q.model, cand, q.p, q.a, "_po")))
+    return ko
+
+
+def test_model_api_host_logic_against_reference_golden(golden, monkeypatch):
+    """KgeModel / ReciprocalRelationsModel (kge_model.py:620-746, reciprocal_relations_model.py:56-106): with the kernels
+    replaced by oracle stand-ins the model API must reproduce the reference's scores bit for bit."""
+    from importlib import import_module
+    _cpu_stand_ins(monkeypatch)
+    mdl = import_module("kge-1_b200.model")
+    T = torch.from_numpy
+    g = golden("scores")
+    s, p, o, sub = (T(g[k]).long() for k in ("idx_s", "idx_p", "idx_o", "subset"))
+    for tag in ("distmult", "complex", "cp", "simple", "rescal"):
+        ent, rel = g[f"{tag}.ent"], g[f"{tag}.rel"]
+        m = mdl.KgeModel(tag, ent.shape[0], rel.shape[0], ent.shape[1], relation_dim=rel.shape[1])
+        with torch.no_grad():
+            m.get_s_embedder().weight.copy_(T(ent))
+            m.get_p_embedder().weight.copy_(T(rel))
+            for got, key in ((m.score_spo(s, p, o), "spo"), (m.score_sp(s, p), "sp"), (m.score_po(p, o), "po"),
+                             (m.score_sp(s, p, sub), "sp_sub"), (m.score_sp_po(s, p, o, sub), "sp_po_sub"),
+                             (m.score_so(s, o), "so"), (m.score_spo(s.int(), p.int(), o.int()), "spo_i32")):
+                np.testing.assert_array_equal(got.numpy().reshape(g[f"{tag}.{key}"].shape), g[f"{tag}.{key}"], err_msg=f"{tag} {key}")
+    g = golden("aux2")
+    s, p, o, sub = (T(g[k]).long() for k in ("recip.idx_s", "recip.idx_p", "recip.idx_o", "recip.subset"))
+    for tag in g["recip.cases"]:
+        tag = str(tag)
+        ent, rel = g[tag + ".ent"], g[tag + ".rel"]
+        m = mdl.ReciprocalRelationsModel(tag.split(".")[1], ent.shape[0], rel.shape[0] // 2, ent.shape[1])
+        with torch.no_grad():
+            m.get_s_embedder().weight.copy_(T(ent))
+            m.get_p_embedder().weight.copy_(T(rel))
+            for got, key in ((m.score_spo(s, p, o, "o"), "spo_o"), (m.score_spo(s, p, o, "s"), "spo_s"),
+                             (m.score_sp(s, p), "sp"), (m.score_po(p, o), "po"), (m.score_sp_po(s, p, o), "sp_po"),
+                             (m.score_sp_po(s, p, o, sub), "sp_po_sub")):
+                np.testing.assert_array_equal(got.numpy().reshape(g[f"{tag}.{key}"].shape), g[f"{tag}.{key}"], err_msg=f"{tag} {key}")
+        with pytest.raises(Exception, match="undirected"):
+            m.score_spo(s, p, o, None)
+        with pytest.raises(Exception, match="cannot score relations"):
+            m.score_so(s, o)
