@@ -375,3 +375,48 @@ def test_model_api_host_logic_against_reference_golden(golden, monkeypatch):
             m.score_spo(s, p, o, None)
         with pytest.raises(Exception, match="cannot score relations"):
             m.score_so(s, o)
+
+
+def test_training_job_bodies_host_logic_against_reference_golden(golden, monkeypatch):
+    """TrainingJob1vsAll / KvsAll / NegativeSampling._process_batch in their reference flow (train.py:679-756, 823-999,
+    1032-1062) and TrainingJob.step (train.py:309-376) with the kernels replaced by oracle stand-ins: losses, gradients
+    and post-Adagrad parameters of the reference's golden batches."""
+    import ast
+    from importlib import import_module
+    _cpu_stand_ins(monkeypatch)
+    mdl, jobs = import_module("kge-1_b200.model"), import_module("kge-1_b200.jobs")
+    T = torch.from_numpy
+    g = golden("train")
+    e, r = 53, 7
+    for tag in [str(x) for x in g["train.cases"]]:
+        _, ttype, model, loss = tag.split(".")
+        opts = dict(ast.literal_eval(str(g[tag + ".options"]))) if tag + ".options" in g else {}
+        ent0, rel0 = g[tag + ".ent0"], g[tag + ".rel0"]
+        m = mdl.KgeModel(model, e, r, ent0.shape[1], l_norm=float(opts.get(model + ".l_norm", 1.0)), relation_dim=rel0.shape[1])
+        with torch.no_grad():
+            m.get_s_embedder().weight.copy_(T(ent0))
+            m.get_p_embedder().weight.copy_(T(rel0))
+        opt = torch.optim.Adagrad(m.parameters(), lr=0.2)
+        lossf = jobs.KgeLoss.create(loss, float(opts.get("train.loss_arg", float("nan"))))
+        if ttype == "1vsAll":
+            job = jobs.TrainingJob1vsAll(m, opt, lossf, fused_path=False)
+        elif ttype == "KvsAll":
+            job = jobs.TrainingJobKvsAll(m, opt, lossf, e, r, label_smoothing=float(opts.get("KvsAll.label_smoothing", 0.0)),
+                                         fused_path=False)
+        else:
+            job = jobs.TrainingJobNegativeSampling(m, opt, lossf, fused_path=False)
+        for step in range(2):
+            pre = f"{tag}.b{step}"
+            if ttype == "KvsAll":
+                batch = {"queries": T(g[pre + ".queries"]), "label_coords": T(g[pre + ".label_coords"]),
+                         "query_type_indexes": T(g[pre + ".query_type"])}
+            else:
+                batch = {"triples": T(g[pre + ".triples"])}
+                if ttype == "negative_sampling":
+                    batch["negative_samples"] = [T(g[f"{pre}.neg{slot}"]) for slot in range(3)]
+            res = job.step(step, batch)
+            assert res.avg_loss == pytest.approx(float(g[pre + ".loss"]), rel=1e-6), tag
+            np.testing.assert_allclose(m.get_s_embedder().weight.grad.numpy(), g[pre + ".grad_ent"], rtol=0, atol=1e-7, err_msg=tag)
+            np.testing.assert_allclose(m.get_p_embedder().weight.grad.numpy(), g[pre + ".grad_rel"], rtol=0, atol=1e-7, err_msg=tag)
+            np.testing.assert_allclose(m.get_s_embedder().weight.detach().numpy(), g[pre + ".ent"], rtol=0, atol=1e-6, err_msg=tag)
+            np.testing.assert_allclose(m.get_p_embedder().weight.detach().numpy(), g[pre + ".rel"], rtol=0, atol=1e-6, err_msg=tag)
