@@ -41,6 +41,49 @@ def gather_owner_slices(flat: torch.Tensor, group) -> torch.Tensor:
     return flat
 
 
+class PeerExchange:
+    """The symmetric-memory side of csrc/p2p.cu for a stepper whose gradients live in ONE flat buffer
+    [g_table0 (n0) | g_table1 (n1) | loss]: allocates that buffer, the staging buffer [W_table0 | W_table1] and the signal
+    pads in torch symmetric memory, and issues the two kernels (exchange, apply).  FusedAllEntityStepper carries its own
+    copy of this logic (validated on 2 / 4 / 8 GPUs); this class serves the negative-sampling stepper and has NOT yet run
+    on hardware."""
+
+    def __init__(self, group, n0: int, n1: int, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if n0 % 4 or n1 % 4:
+            raise NotImplementedError("peer-memory exchange needs table sizes that are multiples of 4 elements")
+        self.group, self.n0, self.n1 = group, n0, n1
+        self.flat = symm.empty(n0 + n1 + 4, dtype=torch.float32, device=device)     # loss at [n0 + n1]
+        hg = symm.rendezvous(self.flat, group)
+        self.stage = symm.empty(n0 + n1, dtype=torch.float32, device=device)
+        hs = symm.rendezvous(self.stage, group)
+        self.pad = symm.empty(64, dtype=torch.int32, device=device)
+        hp = symm.rendezvous(self.pad, group)
+        self.flat.zero_(); self.stage.zero_(); self.pad.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(group)                 # nobody signals before every pad is zero
+        self.rank, self.world, self.handles = hg.rank, hg.world_size, (hg, hs, hp)
+        self.p_flat = lib.ptr_array([int(x) for x in hg.buffer_ptrs])
+        self.p_stage = lib.ptr_array([int(x) for x in hs.buffer_ptrs])
+        self.p_pads = lib.ptr_array([int(x) for x in hp.buffer_ptrs])
+        self.ctr = torch.zeros(2, dtype=torch.int32, device=device)         # [completed steps, block ticket]
+        self.timeout = torch.zeros(1, dtype=torch.int32, device=device)
+        self.loss_global = torch.zeros((), dtype=torch.float32, device=device)
+
+    def exchange_and_update(self, w0, state0, mirror, w1, state1, lr: float, eps: float, stream: int):
+        lib.call("kgeb_p2p_exchange", self.p_pads, self.p_flat, self.p_stage, self.rank, self.world, self.ctr.data_ptr(),
+                 self.timeout.data_ptr(), w0.data_ptr(), state0.data_ptr(), mirror, w0.numel(), w1.data_ptr(),
+                 state1.data_ptr(), w1.numel(), self.loss_global.data_ptr(), lr, eps, stream)
+        lib.call("kgeb_p2p_apply", self.p_pads, self.stage.data_ptr(), self.rank, self.world, self.ctr.data_ptr(),
+                 self.ctr[1:].data_ptr(), self.timeout.data_ptr(), w0.data_ptr(), mirror, w0.numel(), w1.data_ptr(),
+                 w1.numel(), stream)
+
+    def check(self):
+        if int(self.timeout.item()) != 0:
+            raise RuntimeError("a peer did not arrive at a peer-memory barrier")
+
+
 class FusedAllEntityStepper:
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
@@ -754,7 +797,11 @@ class FusedNegSamplingStepper:
     """
 
     def __init__(self, model: KgeModel, optimizer, batch_size: int, num_neg_s: int, num_neg_o: int, loss_kind: int,
-                 offset: float = 0.0, use_graph: bool = True):
+                 offset: float = 0.0, use_graph: bool = True, dp_group=None):
+        """`dp_group`: data-parallel replicas (every rank its own batch of `batch_size` triples; SURVEY.md 8e, second row):
+        gradients of both tables are exchanged and applied by the peer-memory kernels of csrc/p2p.cu inside the same CUDA
+        graph; loss terms are scaled by the global batch so that all replicas apply the identical update.  (Not yet
+        run on hardware -- tests/p2p_ns_check.py.)"""
         self.model, self.opt = model, optimizer
         self.B, self.N = batch_size, {0: int(num_neg_s), 2: int(num_neg_o)}
         self.loss_kind, self.offset = loss_kind, float(offset)
@@ -780,9 +827,19 @@ class FusedNegSamplingStepper:
                                   rows=torch.empty(B, **f32), Q=torch.empty(B, self.d, **f32), dQ=torch.empty(B, self.d, **f32),
                                   dC=torch.empty(B * m, self.d, **f32), da=torch.empty(B, self.d, **f32),
                                   dp=torch.empty(B, self.dr, **f32))
-        self.g_ent = torch.zeros(self.E, self.d, **f32)
-        self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
-        self.loss = torch.zeros((), **f32)
+        self.px = None
+        self.global_batch = B
+        if dp_group is not None:
+            n_e, n_r = self.E * self.d, self.rel.shape[0] * self.dr
+            self.px = PeerExchange(dp_group, n_e, n_r, dev)
+            self.global_batch = B * self.px.world
+            self.g_ent = self.px.flat[:n_e].view(self.E, self.d)
+            self.g_rel = self.px.flat[n_e:n_e + n_r].view(self.rel.shape[0], self.dr)
+            self.loss = self.px.flat[n_e + n_r:n_e + n_r + 1].view(())
+        else:
+            self.g_ent = torch.zeros(self.E, self.d, **f32)
+            self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
+            self.loss = torch.zeros((), **f32)
         nmax = B * (1 + max(self.N.values()))
         self.sws = torch.empty(lib.load().kgeb_scatter_workspace_bytes(nmax, max(self.d, self.dr)), dtype=torch.uint8,
                                device=dev)
@@ -808,7 +865,7 @@ class FusedNegSamplingStepper:
                      b["cand"].data_ptr(), st)
             lib.call("kgeb_pairs_score", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), 1, B, m, d,
                      b["scores"].data_ptr(), st)
-            lib.call("kgeb_ns_loss", self.loss_kind, b["scores"].data_ptr(), B, m, self.offset, 1.0 / B,
+            lib.call("kgeb_ns_loss", self.loss_kind, b["scores"].data_ptr(), B, m, self.offset, 1.0 / self.global_batch,
                      b["G"].data_ptr(), b["rows"].data_ptr(), st)
             lib.call("kgeb_pairs_bwd", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), 1, B, m, d,
                      b["G"].data_ptr(), b["scores"].data_ptr(), b["dQ"].data_ptr(), b["dC"].data_ptr(), st)
@@ -822,6 +879,9 @@ class FusedNegSamplingStepper:
                      self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st)
         torch.sum(torch.stack([self.buf[s]["rows"].sum() for s in self.slots]), dim=0, out=self.loss)
         s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
+        if self.px is not None:     # exchange + update of the owned slices + gather of the new weights, in this graph
+            self.px.exchange_and_update(ent, s_ent, None, rel, s_rel, self.lr, self.eps, st)
+            return
         lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), None, ent.numel(),
                  self.lr, self.eps, 0.0, None, st)
         lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(),
@@ -861,4 +921,4 @@ class FusedNegSamplingStepper:
             st["step"] += 1
         torch.autograd.graph.increment_version(self.ent)
         torch.autograd.graph.increment_version(self.rel)
-        return self.loss
+        return self.loss if self.px is None else self.px.loss_global
