@@ -330,6 +330,17 @@ int kgeb_p2p_apply(const void* const* peer_pads, const float* stage, int rank, i
                    uint32_t* timeout_flag, float* W0, void* mirror0, int64_t numel0, float* W1, int64_t numel1,
                    void* stream);
 
+/* ---- a20 (tuning path, not yet run on hardware): negative-sampling backward without materialised candidate-gradient
+ * rows.  ns_bwd_q = the dQ half of kgeb_pairs_bwd (no dC).  ns_cand_grad = the candidate half: pairs sorted by candidate
+ * id (stable), one warp per distinct candidate recomputes its occurrences' rows from Q and adds their sum to
+ * dense[vocab, d] -- replaces kgeb_pairs_bwd's dC output + kgeb_scatter_add_rows(cand, dC).  cand: int64 [B, M]. */
+int kgeb_ns_bwd_q(int kind, const float* Q, const float* table, const int64_t* cand, int64_t B, int64_t M, int d,
+                  const float* G, const float* scores, float* dQ, void* stream);
+int64_t kgeb_ns_segment_workspace_bytes(int64_t n);
+int kgeb_ns_cand_grad(int kind, const float* Q, const float* table, const int64_t* cand, int64_t B, int64_t M, int d,
+                      const float* G, const float* scores, int64_t vocab, float* dense, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ SIGNATURES = {
     "kgeb_rank_hist": [_p, _p, _l, _l, _p, _p, _p],
     "kgeb_isin_sorted": [_p, _i, _l, _p, _l, _p, _p],
     "kgeb_rank_metrics": [_p, _l, _p, _i, _p, _p, _l, _p],
+    "kgeb_ns_bwd_q": [_i, _p, _p, _p, _l, _l, _i, _p, _p, _p, _p],
+    "kgeb_ns_cand_grad": [_i, _p, _p, _p, _l, _l, _i, _p, _p, _l, _p, _p, _l, _p],
     "kgeb_p2p_exchange": [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _l, _p, _f, _f, _p],
     "kgeb_p2p_apply": [_p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p, _l, _p],
 }
@@ -95,7 +97,8 @@ def index_descs(arrays) -> "ctypes.Array":
     return out
 _INT64_RESULT = {"kgeb_fused_workspace_bytes": [_l, _i, _l, _l], "kgeb_scatter_workspace_bytes": [_l, _i],
                  "kgeb_kvsall_build_workspace_bytes": [_l, _l], "kgeb_sample_shared_workspace_bytes": [_l],
-                 "kgeb_penalty_workspace_bytes": [_l, _l], "kgeb_rank_metrics_workspace_bytes": []}
+                 "kgeb_penalty_workspace_bytes": [_l, _l], "kgeb_rank_metrics_workspace_bytes": [],
+                 "kgeb_ns_segment_workspace_bytes": [_l]}
 
 _lib: Optional[ctypes.CDLL] = None
 

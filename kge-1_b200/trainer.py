@@ -797,8 +797,11 @@ class FusedNegSamplingStepper:
     """
 
     def __init__(self, model: KgeModel, optimizer, batch_size: int, num_neg_s: int, num_neg_o: int, loss_kind: int,
-                 offset: float = 0.0, use_graph: bool = True, dp_group=None):
-        """`dp_group`: data-parallel replicas (every rank its own batch of `batch_size` triples; SURVEY.md 8e, second row):
+                 offset: float = 0.0, use_graph: bool = True, dp_group=None, segment_bwd: bool = False):
+        """`segment_bwd`: candidate gradients without materialised rows (csrc/ns_segment.cu: pairs sorted by candidate, one
+        warp per distinct candidate) instead of pairs_bwd's dC rows + the sorted scatter; tuning path, not yet run on
+        hardware.
+        `dp_group`: data-parallel replicas (every rank its own batch of `batch_size` triples; SURVEY.md 8e, second row):
         gradients of both tables are exchanged and applied by the peer-memory kernels of csrc/p2p.cu inside the same CUDA
         graph; loss terms are scaled by the global batch so that all replicas apply the identical update.  (Not yet
         run on hardware -- tests/p2p_ns_check.py.)"""
@@ -827,6 +830,10 @@ class FusedNegSamplingStepper:
                                   rows=torch.empty(B, **f32), Q=torch.empty(B, self.d, **f32), dQ=torch.empty(B, self.d, **f32),
                                   dC=torch.empty(B * m, self.d, **f32), da=torch.empty(B, self.d, **f32),
                                   dp=torch.empty(B, self.dr, **f32))
+        self.segment_bwd = bool(segment_bwd)
+        if self.segment_bwd:
+            nseg = B * (1 + max(self.N.values()))
+            self.segws = torch.empty(lib.load().kgeb_ns_segment_workspace_bytes(nseg), dtype=torch.uint8, device=dev)
         self.px = None
         self.global_batch = B
         if dp_group is not None:
@@ -867,12 +874,21 @@ class FusedNegSamplingStepper:
                      b["scores"].data_ptr(), st)
             lib.call("kgeb_ns_loss", self.loss_kind, b["scores"].data_ptr(), B, m, self.offset, 1.0 / self.global_batch,
                      b["G"].data_ptr(), b["rows"].data_ptr(), st)
-            lib.call("kgeb_pairs_bwd", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), 1, B, m, d,
-                     b["G"].data_ptr(), b["scores"].data_ptr(), b["dQ"].data_ptr(), b["dC"].data_ptr(), st)
-            lib.call("kgeb_query_bwd", model_id, combine, None, ent.data_ptr(), a_idx.data_ptr(), rel.data_ptr(),
-                     p_idx.data_ptr(), 1, B, d, b["dQ"].data_ptr(), b["da"].data_ptr(), b["dp"].data_ptr(), st)
-            lib.call("kgeb_scatter_add_rows", b["cand"].data_ptr(), 1, b["dC"].data_ptr(), B * m, d,
-                     self.g_ent.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
+            if self.segment_bwd:
+                lib.call("kgeb_ns_bwd_q", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), B, m, d,
+                         b["G"].data_ptr(), b["scores"].data_ptr(), b["dQ"].data_ptr(), st)
+                lib.call("kgeb_query_bwd", model_id, combine, None, ent.data_ptr(), a_idx.data_ptr(), rel.data_ptr(),
+                         p_idx.data_ptr(), 1, B, d, b["dQ"].data_ptr(), b["da"].data_ptr(), b["dp"].data_ptr(), st)
+                lib.call("kgeb_ns_cand_grad", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), B, m, d,
+                         b["G"].data_ptr(), b["scores"].data_ptr(), self.E, self.g_ent.data_ptr(), self.segws.data_ptr(),
+                         self.segws.numel(), st)
+            else:
+                lib.call("kgeb_pairs_bwd", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), 1, B, m, d,
+                         b["G"].data_ptr(), b["scores"].data_ptr(), b["dQ"].data_ptr(), b["dC"].data_ptr(), st)
+                lib.call("kgeb_query_bwd", model_id, combine, None, ent.data_ptr(), a_idx.data_ptr(), rel.data_ptr(),
+                         p_idx.data_ptr(), 1, B, d, b["dQ"].data_ptr(), b["da"].data_ptr(), b["dp"].data_ptr(), st)
+                lib.call("kgeb_scatter_add_rows", b["cand"].data_ptr(), 1, b["dC"].data_ptr(), B * m, d,
+                         self.g_ent.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
             lib.call("kgeb_scatter_add_rows", a_idx.data_ptr(), 1, b["da"].data_ptr(), B, d, self.g_ent.data_ptr(),
                      self.E, self.sws.data_ptr(), self.sws.numel(), st)
             lib.call("kgeb_scatter_add_rows", p_idx.data_ptr(), 1, b["dp"].data_ptr(), B, self.dr,

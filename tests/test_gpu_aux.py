@@ -503,3 +503,32 @@ def test_argument_frequency_metrics_match_reference_golden(kb, golden):
     assert len(keys) > 150
     for k in keys:
         assert k in got and abs(got[k] - float(g[f"value.{k}"])) <= 1e-6, (k, got.get(k), float(g[f"value.{k}"]))
+
+
+@_unconfirmed
+@pytest.mark.parametrize("model", ["distmult", "transe", "rotate"])
+def test_segment_backward_of_negative_sampling_equals_default_path(kb, model):
+    """FusedNegSamplingStepper(segment_bwd=True) (csrc/ns_segment.cu) against the default pairs_bwd + sorted-scatter path:
+    same batches, same negatives; gradients are sums of the same rows in a different grouping -> equal to rounding."""
+    g = kb.graph.synthetic_graph("toy", seed=1)
+    e, r, d, b, n = g["num_entities"], g["num_relations"], 32, 64, 16
+    torch.manual_seed(0)
+    models = [kb.KgeModel(model, e, r, d).cuda() for _ in range(2)]
+    models[1].load_state_dict(models[0].state_dict())
+    jobs = []
+    for m, seg in zip(models, (False, True)):
+        opt = kb.optim.create("Adagrad", m.parameters(), lr=0.1, initial_accumulator_value=0.1)
+        job = kb.TrainingJobNegativeSampling(m, opt, kb.KgeLoss.create("kl"))
+        job.enable_graph_step(b, n, n, use_graph=True, segment_bwd=seg)
+        jobs.append(job)
+    gen = torch.Generator().manual_seed(3)
+    for step in range(3):
+        triples = T(g["train"][step * b:(step + 1) * b].astype(np.int64))
+        negs = [torch.randint(0, e, (b, n), generator=gen), torch.zeros(b, 0, dtype=torch.long),
+                torch.randint(0, e, (b, n), generator=gen)]
+        negs[0][:, :4] = 3                       # a hub candidate: long segments
+        a, c = (j.step(step, {"triples": triples, "negative_samples": negs}) for j in jobs)
+        assert c.avg_loss == pytest.approx(a.avg_loss, rel=1e-6)
+        for x, y in ((models[0].get_s_embedder().weight, models[1].get_s_embedder().weight),
+                     (models[0].get_p_embedder().weight, models[1].get_p_embedder().weight)):
+            assert (x - y).abs().max().item() <= 1e-5, (model, step)

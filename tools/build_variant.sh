@@ -11,7 +11,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -O2"
 $NVCC $FLAGS $DEFS -c "$C/$SRC.cu" -o "$C/build/var_$NAME/$SRC.o"
 OBJS=""
-for f in rows tiles update batch sampler penalty metrics p2p tc_dot tc_bwd; do
+for f in rows tiles update batch sampler penalty metrics p2p ns_segment tc_dot tc_bwd; do
   if [ "$f" == "$SRC" ]; then OBJS="$OBJS $C/build/var_$NAME/$f.o"; else OBJS="$OBJS $C/build/$f.o"; fi
 done
 $NVCC -shared -o "$ROOT/kge-1_b200/variants/libkgeb200_$NAME.so" $OBJS -lcudart
