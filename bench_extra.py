@@ -115,7 +115,7 @@ def wnrr_rotate_ns(args):
     opt = kb.optim.create("Adagrad", model.parameters(), lr=0.2)
     job = kb.TrainingJobNegativeSampling(model, opt, kb.KgeLoss.create("kl"), fused_path=not args.reference_flow)
     if args.graph_step:
-        job.enable_graph_step(B, N, N)
+        job.enable_graph_step(B, N, N, segment_bwd=args.segment_bwd)
     gen = torch.Generator().manual_seed(1)
     batches = []
     for _ in range(8):
@@ -132,10 +132,10 @@ def wnrr_rotate_ns(args):
 
     ms = timed(step, args.steps, args.warmup)
     if args.kernels:
-        kernel_table(step, 3, "wnrr_rotate_ns" + ("_graph" if args.graph_step else ""))
+        kernel_table(step, 3, "wnrr_rotate_ns" + ("_graph" if args.graph_step else "") + ("_seg" if args.segment_bwd else ""))
     hbm, _ = peaks()
     bytes_step = B * 2 * (1 + N) * d * 4 * 2   # gather of each candidate row + write of its gradient row
-    return {"workload": f"RotatE NS 2x{N} negatives d=128 E={E} B={B} ({'reference flow' if args.reference_flow else ('graph-captured fused step' if args.graph_step else 'fused pairs, autograd')})",
+    return {"workload": f"RotatE NS 2x{N} negatives d=128 E={E} B={B} ({'reference flow' if args.reference_flow else ('graph-captured fused step' + (', segment backward' if args.segment_bwd else '') if args.graph_step else 'fused pairs, autograd')})",
             "metric": "training triples/s", "value": B / (ms * 1e-3), "ms_per_step": ms,
             "roofline": {"hbm_gbs": bytes_step / (ms * 1e-3) / 1e9, "hbm_frac": bytes_step / (ms * 1e-3) / 1e9 / hbm,
                          "algorithmic_bytes_per_step": bytes_step}}
@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--math", default="bf16")
     ap.add_argument("--reference-flow", action="store_true")
     ap.add_argument("--graph-step", action="store_true")
+    ap.add_argument("--segment-bwd", action="store_true", help="negative sampling: candidate gradients by segment (ns_segment.cu)")
     ap.add_argument("--kernels", action="store_true", help="also write a per-kernel time table (CUPTI) to gpurun_out/")
     args = ap.parse_args()
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:

@@ -162,6 +162,10 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
 int kgeb_loss_from_rowstat(int loss, const float* rowstat, const int64_t* lab_off, int64_t B, float label_smoothing,
                            int64_t num_entities, float inv_batch, float* rows_out, float* lse_out, float* total,
                            void* stream);
+/* What TrainingJobKvsAll logs per batch (train.py:744-747: avg_loss is overwritten once per query type, so the value of
+ * the LAST non-empty query type survives): rows_loss[B] from kgeb_loss_from_rowstat, row_type[B] (0 = sp_, 1 = _po);
+ * out[0] = sum of all rows (the cost that was back-propagated), out[1] = sum over the rows of the highest type present. */
+int kgeb_loss_report(const float* rows_loss, const int32_t* row_type, int64_t B, float* out, void* stream);
 /* fp32 -> bf16 (round to nearest even) mirror of a table / query matrix for KGEB_MATH_BF16 */
 int kgeb_to_bf16(const float* src, void* dst, int64_t numel, void* stream);
 int64_t kgeb_fused_workspace_bytes(int64_t B, int d, int64_t num_shard_entities, int64_t nnz);

@@ -83,11 +83,15 @@ ns_bwd_q_kernel(const float* __restrict__ Q, const float* __restrict__ table, co
   }
 }
 
-__global__ void ns_pack_kernel(const int64_t* __restrict__ cand, int64_t n, int32_t* __restrict__ keys,
+// ids outside [0, vocab) are mapped to the sentinel key `vocab` (the sort covers vocab + 1 values): they form ONE run
+// that the gradient kernel skips, instead of interleaving with the valid ids that share their low bits and splitting
+// those runs (two warps adding to one dense row)
+__global__ void ns_pack_kernel(const int64_t* __restrict__ cand, int64_t n, int64_t vocab, int32_t* __restrict__ keys,
                                int32_t* __restrict__ pos) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  keys[i] = (int32_t)cand[i];
+  const int64_t e = cand[i];
+  keys[i] = (e < 0 || e >= vocab) ? (int32_t)vocab : (int32_t)e;
   pos[i] = (int32_t)i;
 }
 
@@ -243,7 +247,7 @@ int kgeb_ns_cand_grad(int kind, const float* Q, const float* table, const int64_
   KGEB_REQUIRE(Q && table && cand && G && dense && workspace && B >= 0 && M >= 0 && d > 0, "ns_cand_grad: bad arguments");
   KGEB_REQUIRE(d <= 256, "ns_cand_grad: dim %d too large (<= 256)", d);
   KGEB_REQUIRE(!(kind == KGEB_NEG_L2 || kind == KGEB_ROT_L2) || scores, "ns_cand_grad: L2 kinds need the scores");
-  KGEB_REQUIRE(vocab > 0 && vocab < ((int64_t)1 << 31), "ns_cand_grad: vocabulary size out of range");
+  KGEB_REQUIRE(vocab > 0 && vocab < ((int64_t)1 << 31) - 1, "ns_cand_grad: vocabulary size out of range");
   const int64_t n = B * M;
   if (n == 0) return KGEB_OK;
   KGEB_REQUIRE(n < ((int64_t)1 << 31), "ns_cand_grad: too many pairs");
@@ -259,10 +263,10 @@ int kgeb_ns_cand_grad(int kind, const float* Q, const float* table, const int64_
   int32_t* off = reinterpret_cast<int32_t*>(ws + l.off);
   int32_t* num_runs = reinterpret_cast<int32_t*>(ws + l.num_runs);
   cudaStream_t st = as_stream(stream);
-  ns_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cand, n, keys_in, pos_in);
+  ns_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cand, n, vocab, keys_in, pos_in);
   KGEB_LAUNCH_CHECK("ns_pack");
   int bits = 1;
-  while (bits < 31 && ((int64_t)1 << bits) < vocab) ++bits;
+  while (bits < 31 && ((int64_t)1 << bits) < vocab + 1) ++bits;
   size_t cub_bytes = l.cub_bytes;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, pos_in, pos_out, (int)n, 0, bits, st);
   if (e != cudaSuccess) return cuda_status(e, "ns_cand_grad sort");

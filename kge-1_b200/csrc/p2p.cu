@@ -49,24 +49,28 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr) {
 
 // Barrier inside a kernel: block 0 signals (this GPU has finished everything that precedes this kernel on its stream),
 // every block waits until all peers signalled epoch e.  Bounded spin (~10 s): a dead peer must not hang the GPU.
-__device__ __forceinline__ void grid_peer_barrier(const PeerPtrs& pads, int rank, int world, uint32_t e, uint32_t* timeout_flag) {
+__device__ __forceinline__ bool grid_peer_barrier(const PeerPtrs& pads, int rank, int world, uint32_t e, uint32_t* timeout_flag) {
   const int t = threadIdx.x;
-  if (blockIdx.x == 0 && t < world) {
+  // sticky: once any barrier of this exchange has timed out, every later kernel returns before it writes anything
+  // (weights, optimizer state, the step counter stay as they were; the host sees the flag with the next loss read-back)
+  int bad = (*reinterpret_cast<volatile uint32_t*>(timeout_flag) != 0u);
+  if (blockIdx.x == 0 && t < world && !bad) {
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(pads.p[t]) + rank, e);
   }
-  if (t < world) {
+  if (t < world && !bad) {
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(pads.p[rank]) + t;
     long long spins = 0;
     while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
       __nanosleep(32);
       if (++spins > (1ll << 23)) {
-        *timeout_flag = 1;
+        *reinterpret_cast<volatile uint32_t*>(timeout_flag) = 1u;
+        bad = 1;
         break;
       }
     }
   }
-  __syncthreads();
+  return __syncthreads_or(bad) == 0;
 }
 
 __host__ __device__ inline void slice_of(int64_t numel, int world, int r, int64_t& lo, int64_t& hi) {
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(256)
 p2p_exchange_kernel(PeerPtrs pads, PeerPtrs flat, PeerPtrs stage, int rank, int world, const uint32_t* __restrict__ ctr,
                     uint32_t* timeout_flag, Table t0, Table t1, int64_t loss_off, float* __restrict__ loss_out, float clr,
                     float eps) {
-  grid_peer_barrier(pads, rank, world, 2u * *ctr + 1u, timeout_flag);     // every rank's gradients are complete
+  if (!grid_peer_barrier(pads, rank, world, 2u * *ctr + 1u, timeout_flag)) return;   // every rank's gradients are complete
   if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) {
     float a = 0.f;
     for (int k = 0; k < world; ++k) a += reinterpret_cast<const float*>(flat.p[k])[loss_off];
@@ -158,7 +162,7 @@ p2p_exchange_kernel(PeerPtrs pads, PeerPtrs flat, PeerPtrs stage, int rank, int 
 __global__ void __launch_bounds__(256)
 p2p_apply_kernel(PeerPtrs pads, const float* __restrict__ stage, int rank, int world, uint32_t* ctr, uint32_t* ticket,
                  uint32_t* timeout_flag, Table t0, Table t1) {
-  grid_peer_barrier(pads, rank, world, 2u * *ctr + 2u, timeout_flag);
+  if (!grid_peer_barrier(pads, rank, world, 2u * *ctr + 2u, timeout_flag)) return;   // nothing applied, *ctr not advanced
 #pragma unroll 1
   for (int ti = 0; ti < 2; ++ti) {
     const Table& tb = ti == 0 ? t0 : t1;

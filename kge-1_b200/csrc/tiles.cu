@@ -966,6 +966,42 @@ int kgeb_loss_from_rowstat(int loss, const float* rowstat, const int64_t* lab_of
   return KGEB_OK;
 }
 
+// train.py:747 overwrites the reported avg_loss once per query type: what the job logs for a batch is the value of the
+// LAST non-empty query type (sp_ = 0, _po = 1).  out[0] = sum of all rows, out[1] = sum of the rows of the highest type
+// present; one block, fixed order.
+__global__ void __launch_bounds__(1024)
+loss_report_kernel(const float* __restrict__ rows_loss, const int32_t* __restrict__ row_type, int64_t B,
+                   float* __restrict__ out) {
+  __shared__ float red[3][1024];
+  float all = 0.f, t1 = 0.f, any1 = 0.f;
+  for (int64_t r = threadIdx.x; r < B; r += blockDim.x) {
+    const float v = rows_loss[r];
+    all += v;
+    if (row_type[r] != 0) { t1 += v; any1 = 1.f; }
+  }
+  red[0][threadIdx.x] = all; red[1][threadIdx.x] = t1; red[2][threadIdx.x] = any1;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+      red[2][threadIdx.x] += red[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = red[0][0];
+    out[1] = red[2][0] > 0.f ? red[1][0] : red[0][0];
+  }
+}
+
+int kgeb_loss_report(const float* rows_loss, const int32_t* row_type, int64_t B, float* out, void* stream) {
+  KGEB_REQUIRE(rows_loss && row_type && out && B >= 0, "loss_report: bad arguments");
+  loss_report_kernel<<<1, 1024, 0, as_stream(stream)>>>(rows_loss, row_type, B, out);
+  KGEB_LAUNCH_CHECK("loss_report");
+  return KGEB_OK;
+}
+
 int kgeb_to_bf16(const float* src, void* dst, int64_t numel, void* stream) {
   KGEB_REQUIRE(src && dst && numel >= 0, "to_bf16: bad arguments");
   return tc_to_bf16(src, dst, numel, as_stream(stream));

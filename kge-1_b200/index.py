@@ -30,6 +30,20 @@ class KvsAllIndex:
         self._dev: Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
         self._index_of_key: Optional[dict] = None
 
+    @classmethod
+    def from_arrays(cls, keys, values_offset, values, key: str = "sp") -> "KvsAllIndex":
+        """Adopts the arrays of an index that already exists (the reference's own KvsAllIndex keeps the same three
+        arrays, indexing.py:36-55: `_keys` lexicographic, `_values_offset`, `_values` ascending within a key) instead of
+        sorting the triples again."""
+        self = cls.__new__(cls)
+        self.key = key
+        self._keys = torch.as_tensor(keys).long().contiguous().view(-1, 2)
+        self._values_offset = torch.as_tensor(values_offset).long().contiguous()
+        self._values = torch.as_tensor(values).long().contiguous()
+        self._dev = {}
+        self._index_of_key = None
+        return self
+
     def __len__(self):
         return len(self._keys)
 

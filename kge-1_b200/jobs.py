@@ -228,10 +228,10 @@ class TrainingJobKvsAll(TrainingJob):
         st.input_bytes.copy_(dc["staging"][slot], non_blocking=True)
         dc["consumed"][slot].record(cur)
         loss = st.step()
-        value, overflow = torch.stack((loss, dc["overflow"][slot][0].float())).tolist()   # one D2H read, as train.py:747
+        total, reported, overflow = torch.cat((st.report, dc["overflow"][slot].float())).tolist()   # one D2H read, as train.py:747
         if overflow:
             raise ValueError(f"batch has more than {st.nnz_max} labels (enable_graph_step(nnz_max=...))")
-        return self._check_cost(ProcessBatchResult(value, st.rows, value))
+        return self._check_cost(ProcessBatchResult(reported, st.rows, total))
 
     def device_inputs(self, batch):
         """Host (pinned) KvsAll batch -> device tensors (a_idx, p_idx, row_combine, lab_off, lab_col, perms)."""
@@ -294,8 +294,19 @@ class TrainingJobKvsAll(TrainingJob):
         else:
             self.stepper.set_inputs(*self.device_inputs(batch))
         loss = self.stepper.step()
-        value = loss.item()          # the reference reads the loss back every batch too (train.py:747)
-        res = ProcessBatchResult(value, self.stepper.rows, value)
+        if self.stepper.p2p is None and self.stepper.dp_world == 1:
+            # one D2H read, as train.py:747; avg_loss = value of the last non-empty query type (the reference overwrites
+            # it per type), total_loss = what was back-propagated
+            total, reported = self.stepper.report.tolist()
+        elif self.stepper.p2p is not None:
+            # the peer-memory barriers' timeout flag rides along with the loss read-back (one D2H)
+            total, timed_out = torch.stack((loss, self.stepper.p2p_timeout[0].float())).tolist()
+            if timed_out:
+                raise RuntimeError("a peer did not arrive at a peer-memory barrier; the update of this step was skipped")
+            reported = total
+        else:
+            total = reported = loss.item()
+        res = ProcessBatchResult(reported, self.stepper.rows, total)
         if self.stepper.pen is not None:
             res.penalty = float(self.stepper.penalty_values.sum().item())   # train.py:320-338 (sum of the terms)
         return self._check_cost(res)
@@ -400,7 +411,13 @@ class TrainingJobNegativeSampling(TrainingJob):
         for f in self.pre_batch_hooks:
             f(self)
         st.set_inputs(batch["triples"], negs)
-        value = st.step().item()
+        loss = st.step()
+        if st.px is not None:
+            value, timed_out = torch.stack((loss, st.px.timeout[0].float())).tolist()
+            if timed_out:
+                raise RuntimeError("a peer did not arrive at a peer-memory barrier; the update of this step was skipped")
+        else:
+            value = loss.item()
         return self._check_cost(ProcessBatchResult(value, st.B))
 
     def _process_batch(self, batch_index, batch) -> ProcessBatchResult:

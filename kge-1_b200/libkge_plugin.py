@@ -24,6 +24,10 @@ from __future__ import annotations
 
 import copy
 
+import torch
+
+from . import lib as _lib
+from . import libkge_jobs as _jobs
 from . import model as _model
 from . import ops as _ops
 
@@ -84,6 +88,49 @@ def register():
                                  init_for_load_only=init_for_load_only)
                 patch_embedder(self._entity_embedder)
                 patch_embedder(self._relation_embedder)
+                self._b200_base = base
+                self._b200_eval_math = _jobs.MATH_MODES[self._b200_options().get("eval_math", "fp32")]
+
+            def _b200_options(self) -> dict:
+                """`<model>.b200.*` (configure() creates the keys): math = fp32 | tf32 | bf16 for the fused training
+                kernels, eval_math = fp32 | tf32 for the ranking tiles, captured_step = graph-captured training step."""
+                out = {}
+                for k, default in (("math", "fp32"), ("eval_math", "fp32"), ("captured_step", False)):
+                    try:
+                        out[k] = self.get_option("b200." + k)
+                    except Exception:
+                        out[k] = default
+                return out
+
+            def _b200_lazy(self) -> bool:
+                """score_sp / score_po hand out a LazyScores handle only inside a training job whose loss was wrapped by
+                FusedKgeLoss (libkge_jobs.prepare_training_job), in training mode with autograd on, for the DOT scorers,
+                without embedder dropout (lookup_embedder.py:97-100 applies it to the whole table)."""
+                return (getattr(self, "_b200_lazy_jobs", 0) > 0 and self.training and torch.is_grad_enabled()
+                        and self._scorer._impl.kind == _lib.DOT and self._entity_embedder.dropout.p == 0
+                        and self._relation_embedder.dropout.p == 0)
+
+            def score_sp(self, s, p, o=None):
+                if o is None and self._b200_lazy():
+                    q = _ops.query_build(base, _lib.SP_, self.get_s_embedder().embed(s), self.get_p_embedder().embed(p))
+                    return _jobs.LazyScores(_lib.DOT, q, self.get_o_embedder()._embeddings.weight, self._b200_math)
+                return super().score_sp(s, p, o)
+
+            def score_po(self, p, o, s=None):
+                if s is None and self._b200_lazy():
+                    q = _ops.query_build(base, _lib._PO, self.get_o_embedder().embed(o), self.get_p_embedder().embed(p))
+                    return _jobs.LazyScores(_lib.DOT, q, self.get_s_embedder()._embeddings.weight, self._b200_math)
+                return super().score_po(p, o, s)
+
+            def prepare_job(self, job, **kwargs):
+                """kge_model.py:583-586 + the fused seams of this path (idempotent: re-run at every validation)."""
+                super().prepare_job(job, **kwargs)
+                from kge.job.train import TrainingJob
+                if isinstance(job, TrainingJob):
+                    _jobs.prepare_training_job(job, self, base, self._b200_options())
+
+            def penalty(self, **kwargs):
+                return _jobs.captured_penalties(self, super().penalty, **kwargs)
 
         Model.__name__ = Model.__qualname__ = _class_name(base)
         return Model
@@ -92,18 +139,25 @@ def register():
         setattr(km, _class_name(base), make(base))
     km.B200Scorer = B200Scorer
     km._b200_registered = True
+    _jobs.register_jobs()
     return km
 
 
-def configure(config, base: str) -> str:
+def configure(config, base: str, math: str = "fp32", eval_math: str = "fp32", captured_step: bool = False,
+              kernel_optimizer: bool = True) -> str:
     """Points `config` at the plug-in model of `base`: imports the base model's defaults, copies its option tree to
-    `b200_<base>` with `class_name` replaced, sets `model`.  Returns the model name."""
+    `b200_<base>` with `class_name` replaced, sets `model`; adds the `b200_<base>.b200.*` options (arithmetic of the fused
+    kernels, captured step) and, with `kernel_optimizer`, rewrites `train.optimizer` Adagrad | Adam to the kernel-backed
+    classes registered on torch.optim.  Call it AFTER setting `train.optimizer`.  Returns the model name."""
     if base not in BASES:
         raise ValueError(f"no B200 plug-in for model {base!r}")
     name = f"b200_{base}"
     config._import(base)
     tree = copy.deepcopy(config.options[base])
     tree["class_name"] = _class_name(base)
+    tree["b200"] = {"math": math, "eval_math": eval_math, "captured_step": bool(captured_step)}
     config.options[name] = tree
     config.set("model", name)
+    if kernel_optimizer and config.get("train.optimizer") in ("Adagrad", "Adam"):
+        config.set("train.optimizer", "B200" + config.get("train.optimizer"))     # torch.optim.B200Adagrad / B200Adam
     return name

@@ -41,6 +41,25 @@ def gather_owner_slices(flat: torch.Tensor, group) -> torch.Tensor:
     return flat
 
 
+def _require_plain_model(model: KgeModel, what: str, allow_penalty: bool = False, allow_normalize: bool = False):
+    """The captured steps read the raw tables at fixed addresses without autograd.  Options whose effect they would
+    silently drop raise here instead (the autograd paths of jobs.py serve them): embedder dropout in training
+    (lookup_embedder.py:97-100), the reciprocal-relations wrapper (its _po queries are sp_ queries on relation p + R,
+    reciprocal_relations_model.py:70-83), per-batch renormalisation (replaces the weight tensor, lookup_embedder.py:58-75)
+    and penalty terms (train.py:320-338)."""
+    from .model import ReciprocalRelationsModel
+    if isinstance(model, ReciprocalRelationsModel):
+        raise NotImplementedError(f"{what}: ReciprocalRelationsModel is served by the autograd path (fused_path=True, no "
+                                  "captured step)")
+    embs = (model.get_s_embedder(), model.get_p_embedder())
+    if any(e.dropout.p > 0 for e in embs):
+        raise NotImplementedError(f"{what}: embedder dropout > 0 is served by the autograd path only")
+    if not allow_normalize and any(e.normalize_p > 0 for e in embs):
+        raise NotImplementedError(f"{what}: per-batch renormalisation (normalize_p) is served by the autograd path only")
+    if not allow_penalty and any(e.regularize != "" and e.regularize_weight != 0.0 for e in embs):
+        raise NotImplementedError(f"{what}: penalty terms (regularize_weight != 0) are served by the autograd path only")
+
+
 class PeerExchange:
     """The symmetric-memory side of csrc/p2p.cu for a stepper whose gradients live in ONE flat buffer
     [g_table0 (n0) | g_table1 (n1) | loss]: allocates that buffer, the staging buffer [W_table0 | W_table1] and the signal
@@ -90,6 +109,7 @@ class FusedAllEntityStepper:
                  use_graph: bool = True, shard: Optional[fused.Shard] = None, dp_group=None, dp_p2p: bool = False):
         if model.get_scorer().kind != lib.DOT:
             raise NotImplementedError("the fused all-entity step serves the DOT scorers")
+        _require_plain_model(model, "FusedAllEntityStepper", allow_penalty=True)
         self.model, self.opt = model, optimizer
         self.rows, self.nnz_max, self.loss_kind, self.batch_size = rows, nnz_max, loss_kind, batch_size
         self.offset, self.ls, self.math = float(offset), float(label_smoothing), math_mode
@@ -151,6 +171,8 @@ class FusedAllEntityStepper:
         self.loss = self.gflat[2 * n_e + n_r:].view(())
         self.dp_flat = self.gflat[n_e:]                               # what the replicas exchange
         self.rowstat = torch.empty(rows, 4, **f32)
+        self.loss_rows = torch.zeros(rows, **f32)      # per-row loss values (kgeb_loss_from_rowstat rows_out)
+        self.report = torch.zeros(2, **f32)            # [total, value of the last non-empty query type] (train.py:747)
         # Data parallelism for graphs too small to shard (SURVEY.md 8e "replicas" row): every rank trains on its own
         # batch against its full replica; one all-reduce sums gradients and loss; loss terms are divided by the global
         # batch size so all replicas apply the identical update.
@@ -235,8 +257,10 @@ class FusedAllEntityStepper:
 
     def _loss_kernel(self):
         lib.call("kgeb_loss_from_rowstat", self.loss_kind, self.rowstat.data_ptr(), self.lab_off.data_ptr(), self.rows,
-                 self.ls, self.E, 1.0 / self.global_batch, None, self.lse.data_ptr(), self.loss.data_ptr(),
-                 lib.stream_ptr(self.ent))
+                 self.ls, self.E, 1.0 / self.global_batch, self.loss_rows.data_ptr(), self.lse.data_ptr(),
+                 self.loss.data_ptr(), lib.stream_ptr(self.ent))
+        lib.call("kgeb_loss_report", self.loss_rows.data_ptr(), self.row_combine.data_ptr(), self.rows,
+                 self.report.data_ptr(), lib.stream_ptr(self.ent))
 
     def _stage_backward(self):
         st = lib.stream_ptr(self.ent)
@@ -575,6 +599,7 @@ class RowShardedAllEntityStepper:
             raise NotImplementedError("the fused all-entity step serves the DOT scorers")
         if not shard.distributed:
             raise ValueError("RowShardedAllEntityStepper needs a distributed Shard (fused.Shard.of_rank)")
+        _require_plain_model(model, "RowShardedAllEntityStepper")
         self.model, self.opt, self.shard = model, optimizer, shard
         self.rows, self.nnz_max, self.loss_kind, self.batch_size = rows, nnz_max, loss_kind, batch_size
         self.offset, self.ls, self.math = float(offset), float(label_smoothing), math_mode
@@ -805,6 +830,7 @@ class FusedNegSamplingStepper:
         gradients of both tables are exchanged and applied by the peer-memory kernels of csrc/p2p.cu inside the same CUDA
         graph; loss terms are scaled by the global batch so that all replicas apply the identical update.  (Not yet
         run on hardware -- tests/p2p_ns_check.py.)"""
+        _require_plain_model(model, "FusedNegSamplingStepper")
         self.model, self.opt = model, optimizer
         self.B, self.N = batch_size, {0: int(num_neg_s), 2: int(num_neg_o)}
         self.loss_kind, self.offset = loss_kind, float(offset)

@@ -321,7 +321,8 @@ def test_graph_stepper_bf16_tiles_match_autograd_bf16_flow(kb):
     for i, batch in enumerate(batches):
         a = jr.step(i, batch)
         c = jn.step(i, jn.collate_packed(batch) if i % 2 else batch)
-        assert c.avg_loss == pytest.approx(a.total_loss, rel=1e-3)
+        assert c.total_loss == pytest.approx(a.total_loss, rel=1e-3)
+        assert c.avg_loss == pytest.approx(a.avg_loss, rel=1e-3)   # value of the last query type (train.py:747)
         close(new.get_s_embedder().weight, ref.get_s_embedder().weight, rtol=2e-3, what=f"entity table step {i}")
         close(new.get_p_embedder().weight, ref.get_p_embedder().weight, rtol=2e-3, what=f"relation table step {i}")
 
@@ -494,7 +495,8 @@ def test_graph_captured_stepper_matches_autograd_flow(kb, use_graph):
     jn.enable_graph_step(b, nnz_max, use_graph=use_graph)
     for i, batch in enumerate(batches):
         a, c = jr.step(i, batch), jn.step(i, batch)
-        assert c.avg_loss == pytest.approx(a.total_loss, rel=1e-5)
+        assert c.total_loss == pytest.approx(a.total_loss, rel=1e-5)
+        assert c.avg_loss == pytest.approx(a.avg_loss, rel=1e-5)   # value of the last query type (train.py:747)
         close(new.get_s_embedder().weight, ref.get_s_embedder().weight, rtol=1e-5, what=f"entity table step {i}")
         close(new.get_p_embedder().weight, ref.get_p_embedder().weight, rtol=1e-5, what=f"relation table step {i}")
 

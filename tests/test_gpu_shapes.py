@@ -1,0 +1,230 @@
+"""Parity at the BASELINE.json shapes (the golden vectors are E=53; these are the shapes the bench runs):
+
+* FB15k-237 shape, E = 14,541 / 4,096 query rows / d = 128 (114 entity tiles with a ragged last one, 128 dQ jobs):
+  fused forward statistics, dQ and dTable of the tensor-tile paths against the fp32 CUDA-core path on ALL rows, and the
+  fp32 path against float64 on a row / entity sample (the oracle's arithmetic in double precision).
+* Wikidata5M shape, E = 4,600,000 (int64 offsets, 35,938 tiles, multi-wave persistence, TMA reduce-add flush of a 2.4 GB
+  gradient): row-sampled scores / log-sum-exp / dQ / dTable rows against float64 (`oracle.kge_oracle.score_emb` for the
+  scores) and rank counts on dyadic tables, which must be bit-exact in fp32 AND on the TF32 tiles.
+Bounds (stated per assert): fp32 2e-5, TF32 3e-3, BF16 1e-2 (statistics) / 1.5e-2 (gradients), relative to max |ref|."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kb():
+    import kgeb200
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return kgeb200
+
+
+def close(got, ref, rtol, what):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    assert got.shape == ref.shape, what
+    err = (got - ref).abs().max().item()
+    assert err <= rtol * max(ref.abs().max().item(), 1e-30), f"{what}: max err {err:.3e} vs bound {rtol * ref.abs().max().item():.3e}"
+
+
+def _problem(kb, model, e, r, d, b, nlab_max, seed):
+    """Queries of a real model (normal(0, 0.1) tables), rows sp_ then _po, and a ragged label CSR."""
+    torch.manual_seed(seed)
+    m = kb.KgeModel(model, e, r, d).cuda()
+    gen = torch.Generator().manual_seed(seed + 1)
+    a = torch.randint(0, e, (b,), generator=gen).cuda()
+    p = torch.randint(0, r, (b,), generator=gen).cuda()
+    with torch.no_grad():
+        q = torch.cat((m.queries(kb.lib.SP_, a[: b // 2], p[: b // 2]), m.queries(kb.lib._PO, a[b // 2:], p[b // 2:]))).contiguous()
+        q *= 8.0          # scores of a partly trained model (O(1)), so that sigmoid / softmax are not flat
+    n = torch.randint(0, nlab_max + 1, (b,), generator=gen)
+    n[0], n[1] = 0, nlab_max                      # an empty row and a full one
+    lab_off = torch.zeros(b + 1, dtype=torch.int64)
+    lab_off[1:] = torch.cumsum(n, 0)
+    cols = [torch.randperm(min(e, 100000), generator=gen)[: int(k)].sort().values * (e // min(e, 100000)) for k in n.tolist()]
+    cols[1][-1] = e - 1                            # the last entity (ragged tile)
+    lab_col = torch.cat(cols).long()
+    return m, q, lab_off.cuda(), lab_col.cuda()
+
+
+def _float64_rows(q, w, lab_off, lab_col, rows, loss, offset, inv_batch):
+    """Reference arithmetic in double precision for a sample of query rows: per-row loss, lse, dQ rows."""
+    out_loss, out_lse, out_dq = [], [], []
+    wd = w.double()
+    for r in rows:
+        qd = q[r].double().requires_grad_(True)
+        x = wd @ qd
+        cols = lab_col[lab_off[r]:lab_off[r + 1]]
+        if loss == "kl":
+            lse = torch.logsumexp(x, 0)
+            val = (lse - x[cols].sum() / max(len(cols), 1) - np.log(max(len(cols), 1))) if len(cols) else x.sum() * 0
+            out_lse.append(lse.item())
+        else:
+            val = torch.nn.functional.softplus(x + offset).sum() - (x[cols] + offset).sum()
+        (val * inv_batch).backward()
+        out_loss.append(val.item() * inv_batch)
+        out_dq.append(qd.grad.float())
+    return torch.tensor(out_loss), torch.tensor(out_lse), torch.stack(out_dq)
+
+
+def _float64_table_rows(q, w, lab_off, lab_col, ents, loss, offset, inv_batch, lse):
+    """dTable rows of a sample of entities in double precision: sum_q G[q, e] * Q[q]."""
+    qd = q.double()
+    x = qd @ w[ents].double().t()                                 # [B, n_sample]
+    if loss == "kl":
+        nnz = (lab_off[1:] - lab_off[:-1]).double()
+        g = torch.exp(x - lse.double()[:, None]) * (nnz > 0).double()[:, None]
+        tval = torch.where(nnz > 0, 1.0 / nnz.clamp(min=1), torch.zeros_like(nnz))
+    else:
+        g = torch.sigmoid(x + offset)
+        tval = torch.ones(q.shape[0], dtype=torch.float64, device=q.device)
+    rows = torch.repeat_interleave(torch.arange(q.shape[0], device=q.device), lab_off[1:] - lab_off[:-1])
+    for j, e in enumerate(ents.tolist()):
+        hit = rows[lab_col == e]
+        if len(hit):
+            g[:, j].index_add_(0, hit, -tval[hit])
+    return (g.t() @ qd * inv_batch).float()
+
+
+@pytest.mark.parametrize("loss", ["bce", "kl"])
+def test_fb15k237_shape_fused_kernels(kb, loss):
+    e, r, d, b = 14541, 237, 128, 4096
+    m, q, lab_off, lab_col = _problem(kb, "complex", e, r, d, b, 6, seed=3)
+    w = m.get_s_embedder().weight.detach()
+    kind = kb.lib.LOSS_KL if loss == "kl" else kb.lib.LOSS_BCE
+    offset = 0.1 if loss == "bce" else 0.0
+    shard = kb.fused.Shard.full(e)
+    res = {}
+    for name, mode in (("fp32", kb.lib.MATH_FP32), ("tf32", kb.lib.MATH_TF32), ("bf16", kb.lib.MATH_BF16)):
+        st = kb.fused.fused_rowstats(q, w, lab_off, lab_col, kind, 0.0, offset, mode, shard)
+        rows, lse = kb.fused.rows_loss(st, lab_off, kind, 0.0, e)
+        dw = torch.zeros_like(w)
+        dq = kb.fused.fused_backward(q, w, lab_off, lab_col, kind, 0.0, offset, lse, 1.0 / b, None, mode, shard, dw)
+        res[name] = (rows / b, lse, dq, dw)
+    # fp32 CUDA-core path against float64 on a sample of rows / entities
+    sample = [0, 1, 2, 127, 128, 2047, 2048, 4095]
+    l64, lse64, dq64 = _float64_rows(q, w, lab_off, lab_col, sample, loss, offset, 1.0 / b)
+    close(res["fp32"][0][sample], l64, 2e-5, f"{loss} fp32 row losses vs float64")
+    close(res["fp32"][2][sample], dq64, 2e-5, f"{loss} fp32 dQ rows vs float64")
+    if loss == "kl":
+        close(res["fp32"][1][sample], lse64, 2e-6, "kl fp32 lse vs float64")
+    ents = torch.tensor([0, 1, 63, 64, 127, 128, 14463, 14464, 14539, 14540, int(lab_col[3])], device="cuda")
+    dt64 = _float64_table_rows(q, w, lab_off, lab_col, ents, loss, offset, 1.0 / b, res["fp32"][1] if loss == "kl" else None)
+    close(res["fp32"][3][ents], dt64, 2e-5, f"{loss} fp32 dTable rows vs float64")
+    # tensor-tile paths against the fp32 path on ALL rows
+    for name, st_tol, g_tol in (("tf32", 3e-3, 3e-3), ("bf16", 1e-2, 1.5e-2)):
+        close(res[name][0], res["fp32"][0], st_tol, f"{loss} {name} row losses (all {b} rows)")
+        close(res[name][2], res["fp32"][2], g_tol, f"{loss} {name} dQ (all rows)")
+        close(res[name][3], res["fp32"][3], g_tol, f"{loss} {name} dTable (all {e} rows)")
+
+
+def test_fb15k237_shape_captured_step_matches_autograd_fp32(kb):
+    """The bench's configuration (ComplEx KvsAll + BCE, B = 4096, bf16 tiles, CUDA graph) against the fp32 autograd flow
+    on the same batch: loss 1e-3 relative, post-Adagrad tables 2e-3 of the learning rate scale."""
+    g = kb.graph.synthetic_graph("fb15k-237", seed=0)
+    e, r, d, b = g["num_entities"], g["num_relations"], 128, 4096
+    idx = [kb.index.KvsAllIndex(g["train"], "sp"), kb.index.KvsAllIndex(g["train"], "po")]
+    ids = torch.from_numpy(np.random.default_rng(5).choice(len(idx[0]) + len(idx[1]), b, replace=False)).cuda()
+    a, p, rc, lab_off, lab_col, _ = kb.index.kvsall_batch(idx[0], idx[1], ids)
+    rows = torch.repeat_interleave(torch.arange(b, device="cuda"), lab_off[1:] - lab_off[:-1])
+    batch = {"queries": torch.where(rc[:, None] == 0, torch.stack((a, p), 1), torch.stack((p, a), 1)),
+             "label_coords": torch.stack((rows, lab_col), 1).int(), "query_type_indexes": rc.long().cpu()}
+    torch.manual_seed(0)
+    ref = kb.KgeModel("complex", e, r, d).cuda()
+    new = kb.KgeModel("complex", e, r, d).cuda()
+    new.load_state_dict(ref.state_dict())
+    mk = lambda m, mode: kb.TrainingJobKvsAll(m, kb.optim.create("Adagrad", m.parameters(), lr=0.2, initial_accumulator_value=0.1),  # noqa: E731
+                                              kb.KgeLoss.create("bce"), e, r, math_mode=mode)
+    jr, jn = mk(ref, kb.lib.MATH_FP32), mk(new, kb.lib.MATH_BF16)
+    jn.enable_graph_step(b, int(lab_col.numel()))
+    ra, rn = jr.step(0, batch), jn.step(0, batch)
+    assert rn.total_loss == pytest.approx(ra.total_loss, rel=1e-3)
+    assert rn.avg_loss == pytest.approx(ra.avg_loss, rel=1e-3)
+    for x, y in ((new.get_s_embedder().weight, ref.get_s_embedder().weight), (new.get_p_embedder().weight, ref.get_p_embedder().weight)):
+        assert (x - y).abs().max().item() <= 0.2 * 2e-2, (x - y).abs().max().item()
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_wikidata5m_shape_kl_rows_against_float64(kb, mode):
+    """DistMult 1vsAll + KL at E = 4.6 M: log-sum-exp / loss / dQ of sampled query rows and dTable rows of sampled entities
+    (first / last tile, a label entity) against float64.  fp32 CUDA-core tiles with a small batch (they are 20x slower),
+    bf16 tensor tiles with 512 query rows."""
+    e, r, d = 4_600_000, 822, 128
+    b = 512 if mode == "bf16" else 128
+    m, q, lab_off, lab_col = _problem(kb, "distmult", e, r, d, b, 1, seed=11)
+    lab_off = torch.arange(b + 1, dtype=torch.int64, device="cuda")            # 1vsAll: exactly one label per row
+    lab_col = torch.randint(0, e, (b,), generator=torch.Generator().manual_seed(2)).cuda()
+    lab_col[0], lab_col[1] = e - 1, 0
+    w = m.get_s_embedder().weight.detach()
+    math_mode = kb.lib.MATH_BF16 if mode == "bf16" else kb.lib.MATH_FP32
+    st_tol, g_tol = (1e-2, 1.5e-2) if mode == "bf16" else (2e-5, 2e-5)
+    shard = kb.fused.Shard.full(e)
+    st = kb.fused.fused_rowstats(q, w, lab_off, lab_col, kb.lib.LOSS_KL, 0.0, 0.0, math_mode, shard)
+    rows, lse = kb.fused.rows_loss(st, lab_off, kb.lib.LOSS_KL, 0.0, e)
+    dw = torch.zeros_like(w)
+    dq = kb.fused.fused_backward(q, w, lab_off, lab_col, kb.lib.LOSS_KL, 0.0, 0.0, lse, 1.0 / b, None, math_mode, shard, dw)
+    sample = [0, 1, b // 2 - 1, b // 2, b - 1]
+    l64, lse64, dq64 = _float64_rows(q, w, lab_off, lab_col, sample, "kl", 0.0, 1.0 / b)
+    # lse ~ log(4.6e6) + O(1) = 15.3: an absolute bound in nats is the meaningful one for the tensor tiles
+    assert (lse[sample].double().cpu() - lse64.double()).abs().max().item() <= (2e-3 if mode == "bf16" else 2e-5)
+    close(rows[sample] / b, l64, st_tol if mode == "bf16" else 2e-5, f"wd5m {mode} row losses vs float64")
+    close(dq[sample], dq64, g_tol, f"wd5m {mode} dQ rows vs float64")
+    ents = torch.tensor([0, 1, 127, 128, 2_300_000, e - 129, e - 128, e - 2, e - 1, int(lab_col[5])], device="cuda")
+    # float64 reference with the float64 lse of ALL rows is too slow; the kernel's own lse was just checked on the sample
+    dt64 = _float64_table_rows(q, w, lab_off, lab_col, ents, "kl", 0.0, 1.0 / b, lse)
+    close(dw[ents], dt64, g_tol, f"wd5m {mode} dTable rows vs float64")
+    # rows of entities that are nobody's label and far from any query stay tiny but non-zero: the TMA reduce-add flush
+    # must have touched every tile exactly once
+    assert torch.isfinite(dw).all() and (dw[e - 1].abs().sum() > 0)
+
+
+def test_wikidata5m_shape_scores_match_oracle_rows(kb):
+    """score_sp rows at E = 4.6 M against the CPU oracle (kge_oracle.score_emb) for sampled queries, fp32 1e-5."""
+    from oracle import kge_oracle as ko
+    e, r, d = 4_600_000, 822, 128
+    torch.manual_seed(4)
+    m = kb.KgeModel("distmult", e, r, d, math_mode=kb.lib.MATH_FP32).cuda()
+    s = torch.tensor([0, e - 1, 12345], device="cuda")
+    p = torch.tensor([0, 821, 7], device="cuda")
+    with torch.no_grad():
+        got = m.score_sp(s, p)
+        ent, rel = m.get_s_embedder().weight.detach().cpu(), m.get_p_embedder().weight.detach().cpu()
+        want = ko.score_emb("distmult", ent[s.cpu()], rel[p.cpu()], ent, "sp_")
+    close(got, want, 1e-5, "score_sp rows at E=4.6M vs oracle")
+
+
+@pytest.mark.parametrize("model,math", [("complex", "tf32"), ("complex", "fp32"), ("transe", "fp32")])
+def test_wikidata5m_shape_rank_counts_bit_exact_on_dyadic_tables(kb, model, math):
+    """Filtered rank / tie counts at E = 4.6 M on dyadic tables (entries k/8, |k| <= 4: every product and partial sum is
+    exact in fp32 and in TF32), against exact integer counting in float64 -- bit-exact, ties included."""
+    e, r, d, b = 4_600_000, 822, 128, 64
+    gen = torch.Generator().manual_seed(9)
+    math_mode = kb.lib.MATH_TF32 if math == "tf32" else kb.lib.MATH_FP32
+    m = kb.KgeModel(model, e, r, d, math_mode=math_mode).cuda()
+    with torch.no_grad():
+        m.get_s_embedder().weight.copy_((torch.randint(-4, 5, (e, d), generator=gen, dtype=torch.int8).float() / 8).cuda())
+        m.get_p_embedder().weight.copy_((torch.randint(-4, 5, tuple(m.get_p_embedder().weight.shape), generator=gen).float() / 8).cuda())
+    rng = np.random.default_rng(1)
+    train = np.stack([rng.integers(0, e, 200000), rng.integers(0, 20, 200000), rng.integers(0, e, 200000)], 1).astype(np.int32)
+    train[:, 0] = train[:, 0] % 5000                     # dense (s, p) keys: filters with many entries per row
+    batch = torch.from_numpy(train[:b].copy())
+    job = kb.EntityRankingJob(m, e, [train], None, batch_size=b, math_mode=math_mode, hits_at_k_s=(1, 10))
+    got = job.rank_batch(batch)
+    # exact reference for the sp_ direction of a few rows
+    ent, rel = m.get_s_embedder().weight.detach(), m.get_p_embedder().weight.detach()
+    sp = kb.index.KvsAllIndex(train, "sp")
+    for i in (0, 1, 17, 63):
+        s_i, p_i, o_i = (int(x) for x in train[i])
+        with torch.no_grad():
+            row = m.score_sp(torch.tensor([s_i], device="cuda"), torch.tensor([p_i], device="cuda")).double().view(-1)
+            t = m.score_spo(torch.tensor([s_i], device="cuda"), torch.tensor([p_i], device="cuda"),
+                            torch.tensor([o_i], device="cuda"), "o").double().view(-1)
+        row[o_i] = t
+        raw = int((row > t).sum()) + int((row == t).sum()) // 2
+        known = sp.get((s_i, p_i)).cuda()
+        row[known[known != o_i]] = float("-inf")
+        filt = int((row > t).sum()) + int((row == t).sum()) // 2
+        assert int(got["o_raw"][i]) == raw, (model, math, i, int(got["o_raw"][i]), raw)
+        assert int(got["o_filt"][i]) == filt, (model, math, i, int(got["o_filt"][i]), filt)
