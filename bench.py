@@ -1,23 +1,32 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path on the workload BASELINE.json quotes for one GPU (configs[1]):
-ComplEx KvsAll + BCE, dim 128, synthetic FB15k-237-shaped graph (14,541 entities, 237 relations, 272,115
-train triples).  A step = one KvsAll batch (gather -> query transform -> fused score+loss -> backward ->
-scatter -> Adagrad on both tables).  Metric: training queries/s (a KvsAll example = one sp_ / _po query).
+"""Benchmark of the hot path on the workload the north star scales over GPUs (BASELINE.json configs[3]):
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--math bf16|tf32|fp32]
+    DistMult 1vsAll + KL, dim 128, synthetic Wikidata5M-shaped graph (4,600,000 entities, 822 relations),
+    Adagrad lr 0.2, 1,024 triples (= 2,048 sp_ / _po queries) per step -- the SAME batch at every GPU count.
 
-Prints ONE JSON line (see the build contract): `value` = device-resident inputs, CUDA-event timed;
-`e2e` = through TrainingJobKvsAll.step() with pinned host batches, host->device copies and the loss read
-back inside the timed region; `roofline` for the dominant kernel; `cpu_baseline` = the oracle (a torch-CPU
-port of the reference's path) on a bounded sample on this box's host cores.
-`--impl reference` times that CPU port alone (the reference is pure Python and does not travel to the box).
+A step = TrainingJob1vsAll's batch body + optimizer step (train.py:1032-1062, 309-376): gather -> query transform ->
+fused score + log-sum-exp -> backward (dQ, dense table gradient) -> scatter of the query-side / label rows -> Adagrad
+on both tables.  Metric: training triples/s.  The table (2.36 GB fp32 + 1.18 GB bf16 mirror + 2.36 GB Adagrad state)
+fits one GPU, so N = 1 runs the same workload; for N > 1 the entity table, its optimizer state and its gradient are
+sharded BY ROW over the ranks (trainer.RowShardedAllEntityStepper: three O(batch * d) all-reduces per step) and the
+per-step batch stays 1,024 triples: strong scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line.  `value`: batches resident in HBM, CUDA-event timed, max over ranks.  `e2e`: the same step through
+the REFERENCE's own job object (baseline/_ref, unmodified `TrainingJob1vsAll` created by `Job.create` with the B200
+plug-in model: `job._process_batch(...)` + `job.optimizer.step()`), pinned host batches, H2D copy and loss read-back
+inside the timed region (N > 1: this repo's sharded stepper fed from pinned host batches).  `roofline`: the dominant
+tile kernel timed alone + the whole step against SURVEY.md 8(d)'s 12*E*d FLOP per triple.  `cpu_baseline` /
+`--impl reference`: the unmodified reference (`kge` from baseline/_ref, model distmult, job.device cpu) on the box's host
+cores.  `parity`: loss of the same batch from the same tables on both arms.  `extra.fb15k237`: round 1's line
+(ComplEx KvsAll + BCE, bench_fb237.py), N = 1 only.
 """
 import argparse
+import contextlib
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -25,454 +34,400 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+import bench_fb237  # noqa: E402  (ClockSampler, peaks, the configs[1] workload)
 
-WORKLOAD = "ComplEx KvsAll+BCE d=128, synthetic FB15k-237 shape (E=14541, R=237, 272115 train triples)"
-DIM, LR = 128, 0.2
-
-
-def peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        p = json.load(open(path))
-        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
-                "source": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+E, R, DIM, LR, B = 4_600_000, 822, 128, 0.2, 1024
+E = int(os.environ.get("KGEB_BENCH_ENTITIES", E))      # dry runs of this script on a small table; never set by the driver
+WORKLOAD = (f"DistMult 1vsAll+KL d=128, synthetic Wikidata5M shape (E={E}, R=822), 1024 triples "
+            "(2048 sp_/_po queries) per step")
 
 
-# ---------------------------------------------------------------------------------------------
-# workload: graph, KvsAll examples, batches (host side, vectorised; the reference does this in Python loops)
-# ---------------------------------------------------------------------------------------------
-def build_batches(num_batches, batch_size, seed, rank=0):
-    import kgeb200 as kb
-    g = kb.graph.synthetic_graph("fb15k-237", seed=0)
-    idx = [kb.index.KvsAllIndex(g["train"], "sp"), kb.index.KvsAllIndex(g["train"], "po")]
-    n_sp = len(idx[0])
-    n_ex = n_sp + len(idx[1])
-    rng = np.random.default_rng(seed + 1000 * rank)
-    batches = []
-    keys = [i._keys.numpy() for i in idx]
-    offs = [i._values_offset.numpy() for i in idx]
-    vals = [i._values.numpy() for i in idx]
-    for _ in range(num_batches):
-        ex = rng.choice(n_ex, batch_size, replace=False)
-        qt = (ex >= n_sp).astype(np.int64)
-        loc = np.where(qt == 0, ex, ex - n_sp)
-        queries = np.where(qt[:, None] == 0, keys[0][np.minimum(loc, len(keys[0]) - 1)],
-                           keys[1][np.minimum(loc, len(keys[1]) - 1)])
-        start = np.where(qt == 0, offs[0][np.minimum(loc, len(keys[0]) - 1)], offs[1][np.minimum(loc, len(keys[1]) - 1)])
-        end = np.where(qt == 0, offs[0][np.minimum(loc, len(keys[0]) - 1) + 1],
-                       offs[1][np.minimum(loc, len(keys[1]) - 1) + 1])
-        n = end - start
-        lab_off = np.zeros(batch_size + 1, dtype=np.int64)
-        lab_off[1:] = np.cumsum(n)
-        rows = np.repeat(np.arange(batch_size), n)
-        pos = np.arange(lab_off[-1]) - lab_off[rows] + start[rows]
-        lab = np.where(qt[rows] == 0, vals[0][np.minimum(pos, len(vals[0]) - 1)], vals[1][np.minimum(pos, len(vals[1]) - 1)])
-        coords = np.stack([rows, lab], 1).astype(np.int32)
-        batches.append({"example_ids": torch.from_numpy(ex.astype(np.int64)),
-                        "queries": torch.from_numpy(queries.astype(np.int64)),
-                        "label_coords": torch.from_numpy(coords),
-                        "query_type_indexes": torch.from_numpy(qt)})
-    g["_indexes"] = idx
-    return g, batches
+def config(world: int, math: str) -> dict:
+    """The `config` object of both arms' JSON lines (same keys, same workload string)."""
+    return {"workload": WORKLOAD, "batch": B, "global_batch": B, "optimizer": f"Adagrad lr {LR}",
+            "entities": E, "relations": R, "dim": DIM, "loss": "kl", "train_type": "1vsAll",
+            "parallelism": "1 GPU" if world == 1 else
+            f"entity table, Adagrad state and gradient row-sharded over {world} GPUs; every rank sees the whole batch; "
+            "all-reduce of the query-side rows, the row statistics and dQ ([2048,128] fp32 each) per step",
+            "l2": "inputs larger than L2 (bf16 table 1.18 GB vs 126 MB): no flush between timed steps"}
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+def make_batches(n: int, seed: int = 7):
+    """n batches of B synthetic triples: s, o from a truncated Zipf over a permutation of the entity ids, p from a Zipf
+    over the relations; int64 [B,3] pinned host tensors, as the reference's collate emits them
+    (train.py:1016-1020)."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(E)
+    zipf = lambda m, size: np.minimum((np.exp(rng.random(size) * np.log(m + 1.0)) - 1.0).astype(np.int64), m - 1)  # noqa: E731
+    out = []
+    for _ in range(n):
+        t = np.stack([perm[zipf(E, B)], zipf(R, B), perm[zipf(E, B)]], 1).astype(np.int64)
+        out.append(torch.from_numpy(t))
+    return out
 
-    def __init__(self, index):
-        self.proc, self.lines, self.index = None, [], index
 
-    def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-        return self
-
-    def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.25)
-            self.proc.terminate()
-            self.t.join(timeout=2)
-
-    def summary(self):
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6 or not f[0].isdigit():
-                continue
-            sm.append(int(f[0])); mx.append(int(f[1]))
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
+def quiet():
+    """The reference logs to stdout; this program's stdout carries exactly one JSON line."""
+    return contextlib.redirect_stdout(sys.stderr)
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle (torch-CPU port of the reference's KvsAll batch body + Adagrad)
+# reference arm: the unmodified reference on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(batches, graph, steps, warmup, batch_size):
-    from oracle import kge_oracle as ko
+def cpu_batch_size() -> int:
+    """Largest batch (<= B) whose [batch, E] fp32 score / softmax / gradient matrices (train.py:1040-1057, ~3 live copies
+    per direction) plus the table-sized tensors (parameters, gradients, Adagrad state, embed_all copies: ~8 x 2.36 GB)
+    fit in 70 % of the host's available memory."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    b = B
+    while b > 16 and (3 * b * E * 4 + 8 * E * DIM * 4) > 0.7 * avail:
+        b //= 2
+    return b
+
+
+def reference_job(device="cpu", plugin=False, plugin_args=None, batch=B):
+    from baseline import ref_env
+    graph = {"train": np.zeros((8, 3), dtype=np.int32), "valid": np.zeros((8, 3), dtype=np.int32),
+             "test": np.zeros((8, 3), dtype=np.int32)}
+    opts = {"train.type": "1vsAll", "train.loss": "kl", "train.batch_size": batch, "train.optimizer": "Adagrad",
+            "train.optimizer_args": {"lr": LR}, "train.num_workers": 0,
+            # SURVEY.md 8(d): tables normal_(0, 0.1) as in examples/toy-complex-train.yaml:17-21
+            "lookup_embedder.initialize_args.normal_.std": 0.1}
+    with quiet():
+        job = ref_env.make_job("distmult", graph, E, R, DIM, opts, device=device, plugin=plugin, plugin_args=plugin_args,
+                               seed=0)
+        job._prepare()
+    return job
+
+
+def reference_step(job, i, triples):
+    """run_epoch's body for one batch (train.py:309-376) on the reference's own objects."""
+    job.optimizer.zero_grad()
+    res = job._process_batch(i, {"triples": triples})
+    for _, v in job.model.penalty(epoch=1, batch_index=i, num_batches=1, batch={"triples": triples}):
+        v.backward()
+    job.optimizer.step()
+    return res.avg_loss
+
+
+def run_cpu_reference(batches, steps, warmup, job=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    e, r = graph["num_entities"], graph["num_relations"]
-    gen = torch.Generator().manual_seed(0)
-    prm = ko.Params(torch.randn(e, DIM, generator=gen) * 0.1, torch.randn(r, DIM, generator=gen) * 0.1)
-    opt = ko.make_optimizer("Adagrad", prm, lr=LR)
-    times = []
-    for i in range(warmup + steps):
-        b = batches[i % len(batches)]
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        ko.batch_kvsall("complex", prm, b["queries"].numpy(), b["label_coords"].numpy(), b["query_type_indexes"].numpy(),
-                        e, r, "bce")
-        opt.step()
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    bc = cpu_batch_size()
+    if job is None:
+        job = reference_job("cpu", batch=bc)
+    losses, times = [], []
+    with quiet():
+        for i in range(warmup + steps):
+            t = batches[i % len(batches)][:bc]
+            t0 = time.perf_counter()
+            losses.append(reference_step(job, i, t))
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
     ms = 1e3 * float(np.mean(times))
-    return {"value": batch_size / (ms / 1e3), "ms_per_step": ms, "cores": cores}
+    sample = (f"{steps} step(s) + {warmup} warm-up of kge.job.train.TrainingJob1vsAll._process_batch + optimizer.step() from "
+              f"baseline/_ref (unmodified reference, model distmult, job.device cpu, {cores} threads) on {bc} triples per step")
+    if bc < B:
+        sample += (f" -- the first {bc} of the step's {B} triples: the reference materialises [batch, E] fp32 score, "
+                   f"softmax and gradient matrices and {B} triples do not fit this host's memory; its per-step cost has a "
+                   "batch-independent part (table-sized gradient + dense Adagrad), so triples/s at the full batch would be "
+                   "higher than this figure by up to the batch ratio")
+    return {"value": bc / (ms / 1e3), "ms_per_step": ms, "cores": cores, "sample": sample, "batch": bc,
+            "loss_step0": losses[0], "job": job}
+
+
+def reference_arm(args):
+    from baseline import ref_env
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not ref_env.available():
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed (baseline/install_ref.sh)"}))
+        return
+    # a reference step at this shape takes tens of seconds: the run is bounded to a few minutes
+    steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    batches = make_batches(steps + warm)
+    res = run_cpu_reference(batches, steps, warm)
+    print(json.dumps({
+        "impl": "reference", "metric": "training triples/s", "value": res["value"], "unit": "triples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config(args.gpus, "fp32"),
+        "cpu_baseline": {"value": res["value"], "unit": "triples/s", "cores": res["cores"], "kind": "reference",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss_step0": res["loss_step0"], "gpu_launches": 0}))
 
 
 # ---------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="KvsAll queries per step per GPU")
-    ap.add_argument("--math", default="bf16", choices=["bf16", "tf32", "fp32"])
-    ap.add_argument("--cpu-steps", type=int, default=8, help="steps of the bounded CPU-baseline sample")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--skip-e2e", action="store_true", help="tuning runs: device-resident value + kernel roofline only")
-    ap.add_argument("--parallel", default="p2p", choices=["dp", "p2p", "shard"],
-                    help="N>1: dp = data-parallel replicas + one NCCL all-reduce of the gradients (graphs too small to "
-                         "shard); p2p = the same replicas with the exchange fused into the Adagrad update over NVLink "
-                         "peer memory, whole step in one CUDA graph; shard = entity-sharded scoring (SURVEY.md 8e)")
-    ap.add_argument("--profile-calls", action="store_true", help="print GPU time per C-ABI call of one step and exit")
-    ap.add_argument("--timeline", action="store_true",
-                    help="write the kernel timeline of one step (CUPTI) to gpurun_out/timeline_bench.txt and exit")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    B = args.batch
+# our arm
+# ---------------------------------------------------------------------------------------------
+def count_library_launches(fn) -> int:
+    """Kernels of libkgeb200.so launched by one call of fn (CUPTI activity records; not inside a timed region)."""
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    names = ("kgeb", "label_weight_kernel", "loss_rows_kernel", "loss_report_kernel")
+    return sum(1 for ev in prof.events()
+               if ev.device_type == torch.autograd.DeviceType.CUDA and any(n in ev.name for n in names))
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        steps, warm = min(args.steps, 10), min(args.warmup, 2)
-        graph, batches = build_batches(steps + warm, B, seed=7)
-        res = cpu_reference(batches, graph, steps, warm, B)
-        sample = f"{steps} KvsAll steps of {B} queries (torch-CPU port of the reference's path; oracle/kge_oracle.py)"
-        print(json.dumps({
-            "impl": "reference", "metric": "training queries/s", "value": res["value"], "unit": "queries/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": res["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch": B, "optimizer": "Adagrad lr 0.2"},
-            "cpu_baseline": {"value": res["value"], "unit": "queries/s", "cores": res["cores"], "kind": "port",
-                             "sample": sample},
-            "e2e": {"value": res["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
-        return
 
+def device_batch(t: torch.Tensor, dev):
+    """[B,3] triples -> the stepper's static inputs: rows 0..B-1 = sp_ queries, B..2B-1 = _po queries (both directions
+    of 1vsAll in one launch; their gradients accumulate before one step, train.py:1041-1057, 375)."""
+    t = t.to(dev, non_blocking=True)
+    s, p, o = t[:, 0], t[:, 1], t[:, 2]
+    z = torch.zeros(len(t), dtype=torch.int32, device=dev)
+    return (torch.cat((s, o)), torch.cat((p, p)), torch.cat((z, z + 1)),
+            torch.arange(2 * len(t) + 1, dtype=torch.int64, device=dev), torch.cat((o, s)))
+
+
+def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
+    """The tile kernels of the step timed alone (CUDA events on the launching stream, empty label CSR so that only the
+    tile kernel and its tiny pre / post kernels run; the operands are far larger than L2) and the whole step against
+    SURVEY.md 8(d)'s algorithmic count."""
+    pk = bench_fb237.peaks()
+    L, d, dev = kb.lib, st.d, st.ent.device
+    table = st.ent.detach() if not hasattr(st, "e_lo") else st.ent.detach()[st.e_lo:st.e_hi]
+    e_lo, e_hi = (0, st.E) if not hasattr(st, "e_lo") else (st.e_lo, st.e_hi)
+    mp = st.mirror.data_ptr()
+    off0 = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
+    lse = torch.full((rows,), 15.3, device=dev)
+    gtmp = torch.empty(n_ent, d, device=dev)
+    rowstat = torch.empty(rows, 4, device=dev)
+    dq = torch.empty(rows, d, device=dev)
+    ws = st.ws
+
+    def fwd():
+        L.call("kgeb_fused_fwd", L.LOSS_KL, L.MATH_BF16, st.Q.data_ptr(), rows, d, table.data_ptr(), e_lo, e_hi, st.E,
+               off0.data_ptr(), st.lab_col.data_ptr(), 0, 0.0, 0.0, mp, rowstat.data_ptr(), ws.data_ptr(), ws.numel(),
+               L.stream_ptr(table))
+
+    def bwd(want_dq, want_dt):
+        L.call("kgeb_fused_bwd", L.LOSS_KL, L.MATH_BF16, st.Q.data_ptr(), rows, d, table.data_ptr(), e_lo, e_hi, st.E,
+               off0.data_ptr(), st.lab_col.data_ptr(), 0, None, 0.0, 0.0, lse.data_ptr(), 1.0 / B, None, mp,
+               dq.data_ptr() if want_dq else None, gtmp.data_ptr() if want_dt else None, None,
+               L.BWD_OVERWRITE_TABLE if want_dt else 0, ws.data_ptr(), ws.numel(), L.stream_ptr(table))
+
+    # name -> (launcher, GEMMs the launch EXECUTES, GEMMs of the algorithm it stands for, ncu kernel name)
+    cases = {"tc_tiles_kernel<stats> (kgeb_fused_fwd: scores + online log-sum-exp)": (fwd, 1, 1, "tc_tiles_kernel<1, 2, 1>"),
+             "tc_bwd_kernel<dQ> (kgeb_fused_bwd: S recomputed, dQ += G*T)": (lambda: bwd(True, False), 2, 1, "tc_bwd_kernel<1, 1, 0, 0, 0>"),
+             "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": (lambda: bwd(False, True), 2, 1, "tc_bwd_kernel<0, 1, 0, 0, 0>")}
+    if getattr(st, "flash", False):
+        cases.pop(next(iter(cases)))      # the forward statistics come out of the dQ pass
+    res = {}
+    for name, (fn, executed, algorithmic, _) in cases.items():
+        ts = []
+        for i in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        res[name] = float(np.mean(ts))
+    name = max(res, key=res.get)
+    ms = res[name]
+    gemm = 2.0 * rows * n_ent * d
+    achieved = cases[name][2] * gemm / (ms * 1e-3) / 1e12
+    # the whole step: 12*E*d FLOP per triple (3 GEMMs of 2*(2B)*E*d: forward, dQ, dTable), SURVEY.md 8(d) C4
+    step_flops = 12.0 * E * DIM * B
+    step_achieved = step_flops / (step_ms * 1e-3) / 1e12 / world
+    traffic = None
+    path = os.path.join(ROOT, "profiles", "ncu_full_latest_summary.json")
+    if os.path.exists(path):
+        k = json.load(open(path)).get("wd5m " + cases[name][3])
+        if k:
+            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
+    return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_burst"], "traffic": traffic,
+            "executed_tflops": cases[name][1] * gemm / (ms * 1e-3) / 1e12,
+            "step": {"achieved": step_achieved, "peak": pk["bf16_sustained"], "frac": step_achieved / pk["bf16_sustained"],
+                     "unit": "TFLOP/s per GPU", "flops_per_triple": 12.0 * E * DIM},
+            "note": ("achieved = ALGORITHMIC FLOPs of the launch (one GEMM of 2*rows*E*d: the score tile a backward kernel "
+                     "recomputes is not counted; executed_tflops counts it) / CUDA-event time of the kernel run alone incl. "
+                     "its bf16(Q) / reduce helpers; peak = %s dense bf16 burst.  step = 12*E*d FLOP per triple / step time "
+                     "(per GPU) against the sustained bf16 figure.  rows = %d, shard entities = %d" % (pk["source"], rows, n_ent)),
+            "all_ms": res}
+
+
+def our_arm(args):
     import kgeb200 as kb
+    from baseline import ref_env
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    math_mode = {"bf16": kb.lib.MATH_BF16, "tf32": kb.lib.MATH_TF32, "fp32": kb.lib.MATH_FP32}[args.math]
-    n_batches = args.steps + args.warmup
-    # entity-sharded scoring: every rank processes the whole global batch (world * B queries) against its own
-    # entity range, so all ranks build the same batches (weak scaling: per-GPU work B x E stays fixed)
-    sharded = world > 1 and args.parallel == "shard"
-    GB = B * world if sharded else B          # rows each rank processes per step
-    graph, batches = build_batches(n_batches, GB, seed=7, rank=0 if sharded else rank)
-    E, R = graph["num_entities"], graph["num_relations"]
-    nnz_max = max(int(b["label_coords"].shape[0]) for b in batches)
-    for b in batches:
-        for k in b:
-            b[k] = b[k].pin_memory()
-
-    torch.manual_seed(0)
-    model = kb.KgeModel("complex", E, R, DIM).to(dev)
-    opt = kb.optim.create("Adagrad", model.parameters(), lr=LR)
-    shard = kb.fused.Shard.of_rank(E, rank, world, dist.group.WORLD) if sharded else None
-    job = kb.TrainingJobKvsAll(model, opt, kb.KgeLoss.create("bce"), E, R, fused_path=True, math_mode=math_mode,
-                               shard=shard)
-    try:
-        job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph,
-                              dp_group=dist.group.WORLD if (world > 1 and not sharded) else None,
-                              dp_p2p=args.parallel == "p2p")
-    except (RuntimeError, ImportError) as exc:
-        # peer-mapped (symmetric) memory is a property of the box (NVLink / NVSwitch + fabric handles): where it cannot be
-        # set up -- on every rank alike -- the replicas exchange gradients through NCCL instead, and the line says so
-        if not (world > 1 and args.parallel == "p2p"):
-            raise
-        print(f"[bench] peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using the NCCL mode", file=sys.stderr)
-        args.parallel = "dp"
-        job.enable_graph_step(GB, nnz_max, use_graph=not args.no_graph, dp_group=dist.group.WORLD, dp_p2p=False)
-    stepper = job.stepper
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    if args.profile_calls:
-        profile_calls(kb, job, stepper, batches)
-        return
-    if args.timeline:
-        step_timeline(job, stepper, batches, flush)
-        return
+    steps, warm = args.steps, max(args.warmup, 3)
+    batches = [b.pin_memory() for b in make_batches(steps + warm)]
+    math_mode = kb.lib.MATH_BF16
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---------------- value: inputs resident in HBM, CUDA-event timed -----------------------------
-    dev_inputs = [job.device_inputs(b) for b in batches]
-    for i in range(args.warmup):
-        stepper.set_inputs(*dev_inputs[i])
-        stepper.step()
+    ref_job, parity, cpu = None, None, None
+    use_ref = world == 1 and ref_env.available() and not args.no_reference_job
+    if use_ref:
+        # the reference's own TrainingJob1vsAll, created by its factories with the plug-in model on cuda
+        ref_job = reference_job(f"cuda:{local_rank}", plugin=True, plugin_args={"math": "bf16", "captured_step": True})
+        model_ent = ref_job.model.get_s_embedder()._embeddings.weight
+    else:
+        torch.manual_seed(0)
+        model = kb.KgeModel("distmult", E, R, DIM).to(dev)
+        opt = kb.optim.create("Adagrad", model.parameters(), lr=LR)
+
+    # ---------------- cpu baseline + parity (N = 1, rank 0): same tables, same batch, both arms ----------------------
+    if use_ref and args.cpu_steps > 0:
+        cpu_job = reference_job("cpu", batch=cpu_batch_size())
+        with torch.no_grad():                         # both arms start from the CPU reference's tables
+            ref_job.model.load_state_dict(cpu_job.model.state_dict())
+        bc = cpu_batch_size()
+        with torch.no_grad(), quiet():
+            t = batches[0][:bc].to(dev)
+            q = torch.cat((kb.ops.query_build("distmult", kb.lib.SP_, ref_job.model.get_s_embedder().embed(t[:, 0]),
+                                              ref_job.model.get_p_embedder().embed(t[:, 1])),
+                           kb.ops.query_build("distmult", kb.lib._PO, ref_job.model.get_o_embedder().embed(t[:, 2]),
+                                              ref_job.model.get_p_embedder().embed(t[:, 1]))))
+            rows = kb.fused.all_entity_loss(q, model_ent.detach(), torch.arange(2 * bc + 1, device=dev),
+                                            torch.cat((t[:, 2], t[:, 0])).contiguous(), kb.lib.LOSS_KL, bc, 0.0, 0.0, math_mode)
+            loss_gpu = float(rows.sum().item())
+        cpu = run_cpu_reference(batches, args.cpu_steps, 1, job=cpu_job)
+        cpu.pop("job")
+        del cpu_job
+        rel = abs(loss_gpu - cpu["loss_step0"]) / abs(cpu["loss_step0"])
+        parity = {"what": f"loss of batch 0 (first {bc} triples) from the same initial tables: unmodified reference on the "
+                          "CPU vs the fused bf16-tile kernels", "loss_cpu": cpu["loss_step0"], "loss_gpu": loss_gpu,
+                  "rel_diff": rel, "bound": 1e-3, "ok": bool(rel <= 1e-3)}
+
+    # ---------------- the stepper --------------------------------------------------------------------------------------
+    if use_ref:
+        with quiet():
+            reference_step(ref_job, 0, batches[0])       # builds + captures the stepper inside the reference's job
+        st = ref_job.model._b200_stepper
+        n_ent = E
+    elif world == 1:
+        st = kb.trainer.FusedAllEntityStepper(model, opt, 2 * B, 2 * B, kb.lib.LOSS_KL, B, math_mode=math_mode)
+        n_ent = E
+    else:
+        sh = kb.fused.Shard.of_rank(E, rank, world, dist.group.WORLD)
+        st = kb.trainer.RowShardedAllEntityStepper(model, opt, 2 * B, 2 * B, kb.lib.LOSS_KL, B, sh, math_mode=math_mode)
+        n_ent = sh.e_hi - sh.e_lo
+
+    # ---------------- value: batches resident in HBM, CUDA events ---------------------------------------------------
+    dev_inputs = [device_batch(b, dev) for b in batches]
+    for i in range(warm):
+        st.set_inputs(*dev_inputs[i])
+        st.step()
     barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with bench_fb237.ClockSampler(local_rank) as clocks:
         barrier()
-        for i in range(args.steps):
-            stepper.set_inputs(*dev_inputs[args.warmup + i])
-            flush.fill_(i & 0xFF)           # evict L2 between timed steps (not timed)
+        for i in range(steps):
+            st.set_inputs(*dev_inputs[warm + i])
             evs[i][0].record()
-            stepper.step()
+            st.step()
             evs[i][1].record()
         barrier()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(np.sum(step_ms))
+    total_ms = float(np.sum([a.elapsed_time(b) for a, b in evs]))
     if world > 1:
-        import torch.distributed as dist
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = t.item()
-    value = world * B * args.steps / (total_ms / 1e3)
-    final_loss = (stepper.loss if getattr(stepper, "p2p", None) is None else stepper.loss_global).item()
-    if getattr(stepper, "p2p", None) is not None:
-        stepper.check_p2p()
+    value = B * steps / (total_ms / 1e3)
+    final_loss = float(st.loss.item())
 
-    # ---------------- e2e: public API, pinned host batches, H2D + loss D2H inside the timed region -------
+    # ---------------- e2e: host batches, H2D + step + loss read-back inside the timed region ------------------------
     e2e_s = 0.0
-    packed = [job.collate_packed(b) for b in batches]   # host collate output (pinned), as a DataLoader worker emits it
-    for i in range(0 if args.skip_e2e else args.warmup + args.steps):
-        b = packed[i]
-        flush.fill_(i & 0xFF)
+    for i in range(0 if args.skip_e2e else warm + steps):
+        b = batches[i]
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        # (job.prefetch_packed() -- the next batch's H2D copy underneath the running step -- measured no better here:
-        # 21.5 M against 24.3 M queries/s; with a synchronize per step its D2D copy and events cost more than they hide)
-        res = job.step(i, b)            # copies the batch to the device, runs the step, reads the loss back
+        if use_ref:
+            with quiet():
+                reference_step(ref_job, i, b)           # copies the triples to the device, replays the step, reads the loss
+        else:
+            st.set_inputs(*device_batch(b, dev))
+            st.step().item()
         torch.cuda.synchronize()
-        if i >= args.warmup:
+        if i >= warm:
             e2e_s += time.perf_counter() - t0
     if world > 1:
-        import torch.distributed as dist
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
-    e2e_value = None if args.skip_e2e else world * B * args.steps / e2e_s
-    h2d = int(packed[0]["packed"].numel())
+    e2e_value = None if args.skip_e2e else B * steps / e2e_s
 
-    # ---------------- e2e with on-device batch construction: the host sends example ids only ------------------
-    # (SURVEY.md 8f-1) batch i+1 is built on the collate stream while step i runs; every timed step contains one
-    # H2D copy of 8*B bytes of ids, one batch construction, one step and the loss read-back
-    e2e_dc = None
-    if world == 1 and not args.skip_e2e:
-        job.enable_device_collate(*graph["_indexes"])
-        ids = [b["example_ids"].pin_memory() for b in batches]
-        dc_s = 0.0
-        job.prefetch_ids(ids[0])
-        for i in range(args.warmup + args.steps):
-            flush.fill_(i & 0xFF)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            if i + 1 < len(ids):
-                job.prefetch_ids(ids[i + 1])
-            job.step_ids()
-            torch.cuda.synchronize()
-            if i >= args.warmup:
-                dc_s += time.perf_counter() - t0
-        e2e_dc = {"value": world * B * args.steps / dc_s, "unit": "queries/s", "h2d_bytes_per_step": 8 * B,
-                  "d2h_bytes_per_step": 8, "note": "KvsAll batches built on the device from example ids "
-                  "(kgeb_kvsall_batch_*), double-buffered on a collate stream"}
+    launches = count_library_launches(lambda: (st.set_inputs(*dev_inputs[0]), st.step()))
+    roof = kernel_roofline(kb, st, 2 * B, n_ent, total_ms / steps, world)
 
-    # ---------------- roofline of the dominant kernel (timed alone with CUDA events) ---------------------
-    roof = kernel_roofline(kb, stepper, math_mode, GB, E)
-
+    extra = None
+    if world == 1 and not args.skip_extra:
+        del dev_inputs
+        fb_args = bench_fb237.parser().parse_args(["--steps", str(max(steps, 20)), "--warmup", "5", "--cpu-steps", "3"])
+        with quiet():
+            extra = {"fb15k237": bench_fb237.run(fb_args)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---------------- cpu baseline: bounded sample of the same workload on the host cores -----------------
-    cpu = cpu_reference(batches, graph, args.cpu_steps, 1, B) if args.cpu_steps > 0 else {"value": None, "cores": 0}
     out = {
-        "metric": "training queries/s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.math], "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "optimizer": "Adagrad lr 0.2",
-                   "math": args.math + " tensor tiles, fp32 accumulate, fp32 master tables and optimizer",
-                   "parallelism": "1 GPU" if world == 1 else (
-                       f"entity-sharded scoring over {world} GPUs (all-reduce of row statistics, dQ, dense gradient)"
-                       if sharded else (f"dp{world}: replicas; gradient exchange fused with the Adagrad update over "
-                                        "NVLink peer memory (reduce-scatter of gradients, all-gather of updated "
-                                        "weights, sharded optimizer state), one CUDA graph per step"
-                                        if args.parallel == "p2p" else
-                                        f"dp{world}: replicas with one all-reduce of both tables' gradients + loss per "
-                                        "step (FB15k-237-sized tables are too small to shard, SURVEY.md 8e)")),
-                   "l2": "flushed between timed steps (256 MiB write, untimed); table is 7.4 MB",
-                   "cuda_graph": stepper.graph is not None, "final_loss": final_loss},
+        "metric": "training triples/s", "value": value, "unit": "triples/s", "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": config(world, "bf16"),
+        "details": {"math": "bf16 tensor tiles (tcgen05, bf16 mirror of the table), fp32 accumulate, fp32 master tables "
+                            "and optimizer", "cuda_graph": True, "final_loss": final_loss,
+                    "stepper": type(st).__name__ + (" inside the reference's TrainingJob1vsAll" if use_ref else "")},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "note": "TrainingJobKvsAll.step() on packed pinned host batches; each timed step contains the H2D copy of "
-                        "its batch, the step and the loss read-back"},
-        "e2e_device_collate": e2e_dc,
-        "gpu_launches": int(stepper.kernel_launches_per_step * args.steps),
+        "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": int(batches[0].numel() * 8),
+                "d2h_bytes_per_step": 8,
+                "note": ("the reference's own TrainingJob1vsAll from baseline/_ref (Job.create, plug-in model b200_distmult, "
+                         "b200.captured_step): zero_grad + job._process_batch(pinned [1024,3] int64 triples) + penalties + "
+                         "job.optimizer.step() per timed step" if use_ref else
+                         "this repo's stepper fed from pinned host batches: H2D copy of the triples, step, loss.item() per "
+                         "timed step")},
+        "gpu_launches": int(launches * steps), "gpu_launches_per_step": launches,
         "roofline": roof,
-        "cpu_baseline": {"value": cpu["value"], "unit": "queries/s", "cores": cpu["cores"], "kind": "port",
-                         "sample": f"{args.cpu_steps} KvsAll steps of {B} queries, same graph/batches, torch-CPU port "
-                                   "of the reference's path (oracle/kge_oracle.py)"},
+        "cpu_baseline": ({"value": cpu["value"], "unit": "triples/s", "cores": cpu["cores"], "kind": "reference",
+                          "sample": cpu["sample"], "ms_per_step": cpu["ms_per_step"]} if cpu else
+                         {"value": None, "unit": "triples/s", "cores": 0, "kind": "reference",
+                          "sample": "not run (N > 1, --cpu-steps 0 or baseline/_ref missing)"}),
+        "parity": parity,
+        "extra": extra,
     }
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def profile_calls(kb, job, stepper, batches):
-    """GPU time of every C-ABI call of a step (sync + CUDA events around each call; eager mode)."""
-    import collections
-    acc = collections.OrderedDict()
-    orig = kb.lib.call
-
-    def timed(name, *a):
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); orig(name, *a); e1.record()
-        torch.cuda.synchronize()
-        key = name + ("" if name != "kgeb_fused_bwd" else ("(dQ+dTable)"))
-        acc.setdefault(key, []).append(e0.elapsed_time(e1) * 1e3)
-
-    for m in (kb.lib, kb.trainer.lib):
-        m.call = timed
-    for i in range(6):
-        stepper.set_inputs(*job.device_inputs(batches[i]))
-        stepper._launch()
-        if i == 1:
-            acc.clear()
-    for m in (kb.lib, kb.trainer.lib):
-        m.call = orig
-    tot = 0.0
-    for k, v in acc.items():
-        per_step = float(np.sum(v)) / 4
-        tot += per_step
-        print(f"{per_step:9.1f} us/step  {len(v) // 4} call(s)  {k}")
-    print(f"{tot:9.1f} us/step  total of C-ABI calls")
-
-
-def step_timeline(job, stepper, batches, flush):
-    """Start / duration / stream of every kernel of one step as CUPTI sees it (diagnostic; not a bench number)."""
-    from torch.profiler import profile, ProfilerActivity
-    for i in range(3):
-        stepper.set_inputs(*job.device_inputs(batches[i]))
-        stepper.step()
-    torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for i in range(3, 6):
-            stepper.set_inputs(*job.device_inputs(batches[i]))
-            flush.fill_(i)
-            torch.cuda.synchronize()
-            stepper.step()
-            torch.cuda.synchronize()
-    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-    evs.sort(key=lambda e: e.time_range.start)
-    # last step = everything after the last L2-flush fill
-    last = max(i for i, e in enumerate(evs) if "FillFunctor<unsigned char>" in e.name)
-    evs = evs[last + 1:]
-    t0 = evs[0].time_range.start
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    rank = int(os.environ.get("RANK", "0"))
-    with open(os.path.join(ROOT, "gpurun_out", "timeline_bench.txt" if rank == 0 else f"timeline_bench_rank{rank}.txt"), "w") as f:
-        f.write("# start_us  dur_us  end_us  name   (one CUDA-graph replay of the training step)\n")
-        for e in evs:
-            st = e.time_range.start - t0
-            f.write(f"{st:9.1f} {e.device_time:8.1f} {st + e.device_time:9.1f}  {e.name[:110]}\n")
-
-
-def kernel_roofline(kb, stepper, math_mode, B, E):
-    """Times the three tensor-tile kernels of a step in isolation (CUDA events on the launching stream, L2 flushed
-    between launches; an empty label CSR so that only the tile kernel and its tiny pre/post kernels run) and reports the
-    dominant one against the measured dense-bf16 peak.  `traffic` = dram bytes of that kernel from the committed
-    ncu --set full capture (profiles/ncu_full_latest_summary.json)."""
-    pk = peaks()
-    st = stepper
-    d = st.d
-    dev = st.ent.device
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    lse = torch.zeros(B, device=dev)
-    mp = None if st.mirror is None else st.mirror.data_ptr()
-    L = kb.lib
-    ent = st.ent.detach()
-    gtmp = torch.zeros_like(ent)
-    off0 = torch.zeros(B + 1, dtype=torch.int64, device=dev)   # no labels: isolates the dense tile kernels
-
-    def fwd():
-        L.call("kgeb_fused_fwd", st.loss_kind, math_mode, st.Q.data_ptr(), B, d, ent.data_ptr(), 0, E, E,
-               off0.data_ptr(), st.lab_col.data_ptr(), 0, st.ls, st.offset, mp, st.rowstat.data_ptr(),
-               st.ws.data_ptr(), st.ws.numel(), L.stream_ptr(ent))
-
-    def bwd(dq, dt):
-        L.call("kgeb_fused_bwd", st.loss_kind, math_mode, st.Q.data_ptr(), B, d, ent.data_ptr(), 0, E, E,
-               off0.data_ptr(), st.lab_col.data_ptr(), 0, None, st.ls, st.offset, lse.data_ptr(), 1.0 / B, None,
-               mp, st.dQ.data_ptr() if dq else None, gtmp.data_ptr() if dt else None, None, st.ws.data_ptr(), st.ws.numel(),
-               L.stream_ptr(ent))
-
-    cases = {"tc_tiles_kernel<stats> (fused_fwd)": (fwd, 1, "tc::tc_tiles_kernel<1, 2, 1>"),
-             "tc_bwd_kernel<dQ> (fused_bwd)": (lambda: bwd(True, False), 2, "tc_bwd_kernel<1, 1, 1, 0, 1>"),
-             "tc_bwd_kernel<dTable> (fused_bwd)": (lambda: bwd(False, True), 2, "tc_bwd_kernel<0, 1, 1, 0, 0>")}
-    res = {}
-    for name, (fn, gemms, _) in cases.items():
-        ts = []
-        for i in range(8):
-            flush.fill_(i)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                ts.append(a.elapsed_time(b))
-        res[name] = (float(np.mean(ts)), gemms * 2.0 * B * E * d)
-    name = max(res, key=lambda k: res[k][0])
-    ms, flops = res[name]
-    achieved = flops / (ms * 1e-3) / 1e12
-    traffic = None
-    path = os.path.join(ROOT, "profiles", "ncu_full_latest_summary.json")
-    if os.path.exists(path):
-        k = json.load(open(path)).get(cases[name][2])
-        if k:
-            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
-    tensor = math_mode != kb.lib.MATH_FP32
-    return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_burst"], "traffic": traffic,
-            "note": ("algorithmic FLOPs = %d GEMM(s) x 2*B*E*d per launch (backward kernels recompute the score tile); "
-                     "peak = %s dense bf16 burst; kernel timed alone incl. its bf16(Q) / reduce helpers, L2 flushed; "
-                     "these fused kernels are MUFU-bound (ex2+rcp per score), see DESIGN.md 4.1; "
-                     % (cases[name][1], pk["source"])) + ("tcgen05 tiles" if tensor else "CUDA-core fp32 tiles"),
-            "all_ms": {k: v[0] for k, v in res.items()}}
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=1, help="timed steps of the bounded CPU-baseline sample (N = 1)")
+    ap.add_argument("--skip-e2e", action="store_true", help="tuning runs: device-resident value + kernel roofline only")
+    ap.add_argument("--skip-extra", action="store_true", help="do not run the FB15k-237 workload (extra key)")
+    ap.add_argument("--no-reference-job", action="store_true", help="e2e through this repo's stepper instead of the reference's job object")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
 
 
 if __name__ == "__main__":

@@ -143,7 +143,12 @@ int kgeb_fused_label_rows(int loss, const float* Q, int64_t B, int d, const floa
 int kgeb_fused_fwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
                    int64_t nnz /* size of lab_col (>= lab_off[B]; the tail may be padding) */, float label_smoothing, float offset, const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */,
-                   float* rowstat /*[B,4]*/, void* workspace, int64_t workspace_bytes, void* stream);
+                   float* rowstat /* kgeb_fused_bwd flags.  KGEB_BWD_OVERWRITE_TABLE: dTable[e_lo..e_hi) is OVERWRITTEN with the gradient (dense part stored by
+ * the tile kernel with plain TMA stores, label rows scattered on top afterwards) instead of accumulated into: the caller
+ * needs no cleared buffer and the L2 does no read-modify-write -- at the Wikidata5M shape that is 2 x 2.4 GB of HBM traffic
+ * per step (embedding_dense_backward of the reference zero-fills and accumulates, K3). */
+#define KGEB_BWD_OVERWRITE_TABLE 1
+/*[B,4]*/, void* workspace, int64_t workspace_bytes, void* stream);
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col,
                    int64_t nnz /* size of lab_col (>= lab_off[B]; the tail may be padding) */,
@@ -155,13 +160,35 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
                    const void* table_bf16 /* mirror, KGEB_MATH_BF16 only */, float* dQ, float* dTable,
                    float* rowstat_out /* [B,4] or NULL: also produce the forward statistics of kgeb_fused_fwd (BCE on the
                                          bf16 tiles gets them from the same pass; otherwise the forward kernels run) */,
-                   void* workspace, int64_t workspace_bytes, void* stream);
+                   int flags /* 0 | KGEB_BWD_OVERWRITE_TABLE */, void* workspace, int64_t workspace_bytes, void* stream);
 /* loss(scores, labels) / batch_size from the (shard-combined) forward statistics, as the reference's loss objects
  * return it (loss.py:153-159, 198-213): rows_out[B] per-row values (may be NULL), lse_out[B] log-sum-exp per row for
  * the KL backward (may be NULL), total[1] their sum in a fixed order. */
 int kgeb_loss_from_rowstat(int loss, const float* rowstat, const int64_t* lab_off, int64_t B, float label_smoothing,
                            int64_t num_entities, float inv_batch, float* rows_out, float* lse_out, float* total,
                            void* stream);
+/* KL on the bf16 tiles with the forward statistics and the query gradient in ONE pass over the table (the forward kernel of
+ * kgeb_fused_fwd and the score recomputation of the dQ half of kgeb_fused_bwd fall away: 4 instead of 5 GEMM passes and 2
+ * instead of 3 exponentials per score and step).  Per score P = exp(x - mref_q) is computed once against a FIXED per-row
+ * reference (mref_q = max of x over a strided sample of 256 entities of the shard); the row sums of P accumulate in
+ * registers, o_sum[q,:] = sum_e P[q,e] * table[e,:] in tensor memory.  No online rescaling: bf16 operands and fp32
+ * accumulators keep 8 exponent bits, so P is representable for x within [-87, +88] nats of mref -- beyond that the sums
+ * read inf, the loss NaN and the job raises FloatingPointError (train.py:343-345).
+ *   rowstat[B,4] = (mref, sum_e exp(x - mref), 0, sum of x over the row's labels in this shard)  -- kgeb_fused_fwd's layout,
+ *                  i.e. kgeb_loss_from_rowstat and the shard combination (max + rescaled sums) apply unchanged
+ *   o_sum[B,d]
+ * Replaces K4 + K8 of SURVEY.md 2.3 (mm + log_softmax, distmult.py:20-22, loss.py:199-213) and the dQ half of their backward. */
+int kgeb_fused_flash_fwd(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
+                         int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
+                         const void* table_bf16, float* rowstat, float* o_sum, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+/* dQ[q,:] = w_q * exp(mref_q - lse_q) * o_sum[q,:] - (w_q / nnz_q) * sum over the row's labels in this shard of table[e,:],
+ * w_q = inv_batch * grad_scale[q] * (row q has labels).  rowstat_local = THIS shard's kgeb_fused_flash_fwd output (its
+ * mref), lse = the global log-sum-exp (kgeb_loss_from_rowstat on the combined statistics).  No pass over the table. */
+int kgeb_fused_flash_dq(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
+                        const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const float* rowstat_local,
+                        const float* lse, float inv_batch, const float* grad_scale /* [B] or NULL */, const float* o_sum,
+                        float* dQ, void* workspace, int64_t workspace_bytes, void* stream);
 /* What TrainingJobKvsAll logs per batch (train.py:744-747: avg_loss is overwritten once per query type, so the value of
  * the LAST non-empty query type survives): rows_loss[B] from kgeb_loss_from_rowstat, row_type[B] (0 = sp_, 1 = _po);
  * out[0] = sum of all rows (the cost that was back-propagated), out[1] = sum over the rows of the highest type present. */

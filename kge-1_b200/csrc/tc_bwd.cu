@@ -77,9 +77,15 @@ struct Params {
   const float* row_scale;  // [B] or NULL
   float* out;              // RES_IS_Q: partial [chunks][B][d] ; else dTable [n_res][d] (+=)
   float* stat_partial;     // STATS: [chunks][4 column parts][B][2] = (sum softplus(x+off), sum (x+off)) over valid entities
+  int overwrite;           // !RES_IS_Q: the accumulator is STORED into dTable (plain TMA store) instead of added to it
+  const float* mref;       // FLASH: [B] reference score per row (natural units); P = exp(x - mref)
 };
 
-template <bool RES_IS_Q, bool BF16, int LOSS, bool HAS_RS, bool STATS>
+// FLASH (RES_IS_Q, KL): the forward statistics and the softmax part of dQ in one pass.  The epilogue computes
+// P = exp(x - mref_row) against a FIXED per-row reference (a sampled row maximum: bf16 operands and fp32 accumulators keep 8
+// exponent bits, so no online rescaling of the accumulator is needed), accumulates the row sums of P in registers and
+// OUT += P * STR in tensor memory:  lse = mref + log(sum P),  dQ_dense = rs * exp(mref - lse) * OUT.
+template <bool RES_IS_Q, bool BF16, int LOSS, bool HAS_RS, bool STATS, bool FLASH = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_str,
               const __grid_constant__ CUtensorMap tm_out, const Params p) {
@@ -290,7 +296,10 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
       //   sum softplus(z) = ln2 * sum lg2(1 + e^-|z|) + sum max(z, 0)   (no cancellation between the sums)
       float st_lg = 0.f, st_mx = 0.f, st_x = 0.f;
       int n_pad = 0;
-      if (RES_IS_Q && res_row < p.B) {
+      float fl_m2 = 0.f, fl_l[4] = {0.f, 0.f, 0.f, 0.f};   // FLASH: -mref * log2(e) of this row; four partial row sums of P
+      if (FLASH) {
+        if (res_row < p.B) fl_m2 = -p.mref[res_row] * 1.4426950408889634f;
+      } else if (RES_IS_Q && res_row < p.B) {
         my_rs = p.inv_batch * (HAS_RS ? p.row_scale[res_row] : 1.f);
         if (LOSS == KGEB_LOSS_KL) my_lse = p.lse[res_row];
       }
@@ -304,7 +313,6 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         KGEB_TRW(9, u);
         sph ^= 1;
         tc_fence_after();
-#if KGEB_STR_ROWS == 64 && !defined(KGEB_G_TMEM)   // the measured kernel, kept textually as it ran on hardware
         float v[COLS_PER_WARP];
         tmem_ld32(lane_addr + S_COL + (uint32_t)(bufi * STR_ROWS + sub * COLS_PER_WARP), v);
         tc_fence_before();
@@ -315,12 +323,14 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         const int64_t qbase = u * STR_ROWS + sub * COLS_PER_WARP;
         // STATS: entity columns beyond the table end were zero-filled, their score is exactly 0: count them here
         // and take their known contribution (softplus(off), off) out once per job instead of masking per element
-        if (STATS) n_pad += COLS_PER_WARP - (int)max((int64_t)0, min((int64_t)COLS_PER_WARP, p.n_str - qbase));
+        if (STATS || FLASH) n_pad += COLS_PER_WARP - (int)max((int64_t)0, min((int64_t)COLS_PER_WARP, p.n_str - qbase));
         // Per-column parameters (columns are query rows when RES is the entity tile): lane c of the warp loads
         // those of column c once per tile, the element loop fetches them with one shuffle.  KL folds everything
         // into one exponent offset:  rs * exp(x - lse) = ex2(x * log2e + kc),  kc = (log(rs) - lse) * log2e.
         float col_k = 0.f, col_rs = my_rs;
-        if (!RES_IS_Q) {
+        if (FLASH) {
+          col_k = fl_m2;
+        } else if (!RES_IS_Q) {
           const int64_t q = min(qbase + lane, p.B - 1);
           col_rs = HAS_RS ? p.inv_batch * __ldg(p.row_scale + q) : p.inv_batch;
           if (LOSS == KGEB_LOSS_KL) col_k = (__logf(col_rs) - __ldg(p.lse + q)) * kLog2e;
@@ -333,6 +343,7 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
             const float kc = RES_IS_Q ? col_k : __shfl_sync(0xffffffffu, col_k, c);
             const float a = fmaf(v[c], kLog2e, kc);
             v[c] = ((c & 7) < KGEB_POLY8_KL) ? ex2_poly<3, false>(a) : ex2_ftz(a);
+            if (FLASH) fl_l[c & 3] += v[c];
           }
         } else {
           // BCE, four columns per iteration.  MUFU diet (the XU pipe has 16 lanes/clk/SM, the FMA pipe 128; the pipeline
@@ -437,165 +448,13 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         KGEB_TRW(13, u);
         gph ^= 1;
       }
-#else   // tuning builds: PASSES passes of 32 columns per warp (KGEB_STR_ROWS) and / or G through tensor memory (KGEB_G_TMEM)
-        float v[COLS_PER_WARP];
-#pragma unroll 1
-        for (int pass = 0; pass < PASSES; ++pass) {
-        const int cw0 = sub * (COLS_PER_WARP * PASSES) + pass * COLS_PER_WARP;   // first tile column of this warp and pass
-        tmem_ld32(lane_addr + S_COL + (uint32_t)(bufi * STR_ROWS + cw0), v);
-        if (pass == PASSES - 1) {
-          tc_fence_before();
-          mbar_arrive_warp(&s_empty[bufi]);
-          KGEB_TRW(10, u);  // S values are in registers: MMA1 of the tile after next may overwrite them
-        }
-        // Rows / columns beyond the matrices were zero-filled by TMA, so whatever finite G they get multiplies
-        // zeros in MMA2; only the parameter loads are clamped.
-        const int64_t qbase = u * STR_ROWS + cw0;
-        // STATS: entity columns beyond the table end were zero-filled, their score is exactly 0: count them here
-        // and take their known contribution (softplus(off), off) out once per job instead of masking per element
-        if (STATS) n_pad += COLS_PER_WARP - (int)max((int64_t)0, min((int64_t)COLS_PER_WARP, p.n_str - qbase));
-        // Per-column parameters (columns are query rows when RES is the entity tile): lane c of the warp loads
-        // those of column c once per tile, the element loop fetches them with one shuffle.  KL folds everything
-        // into one exponent offset:  rs * exp(x - lse) = ex2(x * log2e + kc),  kc = (log(rs) - lse) * log2e.
-        float col_k = 0.f, col_rs = my_rs;
-        if (!RES_IS_Q) {
-          const int64_t q = min(qbase + lane, p.B - 1);
-          col_rs = HAS_RS ? p.inv_batch * __ldg(p.row_scale + q) : p.inv_batch;
-          if (LOSS == KGEB_LOSS_KL) col_k = (__logf(col_rs) - __ldg(p.lse + q)) * kLog2e;
-        } else if (LOSS == KGEB_LOSS_KL) {
-          col_k = (__logf(my_rs) - my_lse) * kLog2e;   // rows beyond B: log(0) = -inf -> G = 0
-        }
-        if (LOSS == KGEB_LOSS_KL) {
-#pragma unroll
-          for (int c = 0; c < COLS_PER_WARP; ++c) {
-            const float kc = RES_IS_Q ? col_k : __shfl_sync(0xffffffffu, col_k, c);
-            const float a = fmaf(v[c], kLog2e, kc);
-            v[c] = ((c & 7) < KGEB_POLY8_KL) ? ex2_poly<3, false>(a) : ex2_ftz(a);
-          }
-        } else {
-          // BCE, four columns per iteration.  MUFU diet (the XU pipe has 16 lanes/clk/SM, the FMA pipe 128; the pipeline
-          // trace (tools/trace_bwd.py) shows the epilogue warps spending 55-75 % of a tile in this loop with the XU pipe
-          // ~80 % busy, i.e. these kernels are bound by MUFU throughput):
-          //  * KGEB_RCP_GROUP = 2 | 4: the reciprocals of a group come from ONE rcp of the product of the group (batch
-          //    inversion, 1/a0 = a1 / (a0 a1) ...): 1 MUFU + 3 | 9 FMUL instead of 2 | 4 MUFU; relative error ~4 ulp;
-          //  * KGEB_LG2_GROUP = 4..32: sum lg2(a_i) = lg2(prod a_i); a_i in [1, 2], so a product of <= 32 factors stays
-          //    far inside the fp32 range and costs one FMUL per factor instead of one MUFU.
-          constexpr int RG = KGEB_RCP_GROUP, LG = KGEB_LG2_GROUP;
-          static_assert(RG == 1 || RG == 2 || RG == 4, "KGEB_RCP_GROUP must be 1, 2 or 4");
-          static_assert(LG == 1 || (LG % 4 == 0 && COLS_PER_WARP % LG == 0), "KGEB_LG2_GROUP must be 1 or a multiple of 4");
-          float prod = 1.f;
-          const float nls = -p.ls_add;
-          // exponent clamp of the non-STATS form: the product of a group must stay finite (the sigmoid of z < -20.8
-          // (-41.6) then reads 9e-10 (9e-19), far below the bf16 resolution of G next to any other entry)
-          const float tmax = RG == 4 ? 30.f : 60.f;
-#pragma unroll
-          for (int c = 0; c < COLS_PER_WARP; c += 4) {
-            float z[4], e[4], a[4], r[4], rs[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              rs[j] = (!RES_IS_Q && HAS_RS) ? __shfl_sync(0xffffffffu, col_rs, c + j) : col_rs;
-              float t;
-              if (STATS) {
-                // sigmoid and softplus from one exponential, cancellation-free:
-                //   e = exp(-|z|), a = 1 + e, r = 1/a;  sigma = z >= 0 ? r : e r;  softplus(z) = max(z,0) + log(a)
-                z[j] = v[c + j] + p.offset;
-                t = fabsf(z[j]) * -kLog2e;
-                e[j] = (((c + j) & 7) < KGEB_POLY8_STATS) ? ex2_poly<4, false>(t) : ex2_ftz(t);
-              } else {
-                // rs * (sigmoid(x + offset) - ls_add) = rs / (1 + exp(-(x + offset))) - rs ls_add
-                t = fmaf(v[c + j], -kLog2e, off2);
-                if (RG > 1) t = fminf(t, tmax);
-                e[j] = (((c + j) & 7) < KGEB_POLY8_BCE) ? ex2_poly<3, true>(t) : ex2_ftz(t);
-              }
-              a[j] = 1.f + e[j];
-            }
-            const float p01 = a[0] * a[1], p23 = a[2] * a[3];
-            if (RG == 1) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) r[j] = rcp_ftz(a[j]);   // e = inf for very negative z -> rcp gives 0
-            } else if (RG == 2) {
-              const float i01 = rcp_ftz(p01), i23 = rcp_ftz(p23);
-              r[0] = i01 * a[1]; r[1] = i01 * a[0]; r[2] = i23 * a[3]; r[3] = i23 * a[2];
-            } else {
-              const float ri = rcp_ftz(p01 * p23);
-              const float i01 = ri * p23, i23 = ri * p01;
-              r[0] = i01 * a[1]; r[1] = i01 * a[0]; r[2] = i23 * a[3]; r[3] = i23 * a[2];
-            }
-            if (STATS) {
-              if (LG > 1) {
-                prod *= p01 * p23;
-                if (((c + 4) % LG) == 0) {
-                  st_lg += lg2_ftz(prod);
-                  prod = 1.f;
-                }
-              } else {
-                st_lg += (lg2_ftz(a[0]) + lg2_ftz(a[1])) + (lg2_ftz(a[2]) + lg2_ftz(a[3]));
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                st_mx += fmaxf(z[j], 0.f);
-                st_x += z[j];
-                v[c + j] = fmaf(z[j] >= 0.f ? r[j] : e[j] * r[j], rs[j], nls * rs[j]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[c + j] = fmaf(r[j], rs[j], nls * rs[j]);
-            }
-          }
-        }
-        if (pass == 0) {
-          KGEB_TRW(11, u);
-          mbar_wait(&g_empty[bufi], gph ^ 1);  // MMA2 of this buffer's previous tile has finished reading it
-          KGEB_TRW(12, u);
-        }
-#ifdef KGEB_G_TMEM
-        {
-          // G as the A operand of MMA2 in TENSOR memory (tcgen05.mma [d], [a], b-desc: A K-major, lane = row, two bf16 per
-          // 32-bit column): no shared-memory round trip of G, no generic->async proxy fence
-          uint32_t w[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
-          tmem_st16(lane_addr + G_COL + (uint32_t)(bufi * (STR_ROWS / 2) + cw0 / 2), w);
-        }
-#else
-        uint8_t* gb = g_smem + (size_t)bufi * G_BYTES;
-        if (BF16) {
-          // row trow of K-slab cw0 / 64: this warp's 32 bf16 = four 16-byte chunks from (cw0 % 64) / 8 on, 128-byte swizzle
-          // (shared-window address + st.shared: through the generic pointer these are ST.E, resolved in the LSU)
-          const uint32_t rowa = smem_s + (uint32_t)(KS * RES_SLAB + bufi * G_BYTES + (cw0 / SLAB_K) * RES_SLAB + trow * 128);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[k * 8 + j * 2 + 1]), "f"(v[k * 8 + j * 2]));
-            const int ck = (cw0 % SLAB_K) / 8 + k;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (uint32_t)((ck ^ (trow & 7)) << 4)),
-                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                         : "memory");
-          }
-        } else {
-          // TF32: K-slabs of 32 fp32 columns; this warp's 32 columns of this pass are slab cw0 / 32
-          uint8_t* rowp = gb + (size_t)(cw0 / SLAB_K) * RES_SLAB + (size_t)trow * 128;
-#pragma unroll
-          for (int ck = 0; ck < 8; ++ck)
-            *reinterpret_cast<float4*>(rowp + ((ck ^ (trow & 7)) << 4)) =
-                make_float4(v[ck * 4], v[ck * 4 + 1], v[ck * 4 + 2], v[ck * 4 + 3]);
-        }
-#endif
-        }  // pass
-#ifdef KGEB_G_TMEM
-        tmem_wait_st();
-        tc_fence_before();
-#else
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-#endif
-        mbar_arrive_warp(&g_full[bufi]);
-        KGEB_TRW(13, u);
-        gph ^= 1;
+      if (FLASH && res_row < p.B) {
+        // row sum of P over this job's (chunk, column part); zero-filled entity columns beyond the table end scored
+        // exactly 0, i.e. P = exp(-mref): taken out once per job
+        float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
+        sp[0] = ((fl_l[0] + fl_l[1]) + (fl_l[2] + fl_l[3])) - (float)n_pad * ex2_ftz(fl_m2);
+        sp[1] = 0.f;
       }
-#endif
       if (STATS && res_row < p.B) {
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
         const float zp = p.offset;
@@ -643,7 +502,10 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           fence_proxy_async();
           named_bar_sync(1 + part, 128);
           if (leader) {
-            tma_reduce_add_2d(&tm_out, stage, box * 32, (int32_t)(rb * RES_ROWS));  // rows / columns past the end are clipped
+            // rows / columns past the end are clipped.  overwrite: this CTA is the only writer of these rows and K (all
+            // query tiles) is complete, so a plain store does -- no cleared buffer, no read-modify-write in L2
+            if (p.overwrite) tma_store_2d(&tm_out, stage, box * 32, (int32_t)(rb * RES_ROWS));
+            else tma_reduce_add_2d(&tm_out, stage, box * 32, (int32_t)(rb * RES_ROWS));
             bulk_commit();
           }
         }
@@ -725,7 +587,7 @@ label_entry_rows_kernel(const float* __restrict__ Q, const float* __restrict__ t
     if (real) {
       e = lab_col[i] - e_lo;
       in_shard = (e >= 0 && e < n_ent);
-      if (in_shard) w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
+      if (in_shard && tscale) w = tscale[q] * inv_batch * (row_scale ? row_scale[q] : 1.f);
       else e = e < 0 ? 0 : n_ent - 1;   // zero row; the monotone clamp keeps ent[] in the order of lab_col (lab_perm)
     }
     const int64_t qq = real ? q : 0;
@@ -787,7 +649,7 @@ static Plan make_plan(bool res_is_q, bool bf16, int64_t B, int d, int64_t n_ent)
 
 template <bool RES_IS_Q>
 static int launch_bwd(const Plan& pl, const CUtensorMap& m_res, const CUtensorMap& m_str, const CUtensorMap& m_out,
-                      int64_t jobs, cudaStream_t st) {
+                      int64_t jobs, cudaStream_t st, bool flash = false) {
   const int grid = (int)(jobs < kNumSMs ? jobs : kNumSMs);
   cudaError_t e = cudaSuccess;
   // (A raised launch priority for this kernel was tried and measured worse: it starts a few microseconds earlier but
@@ -810,7 +672,15 @@ static int launch_bwd(const Plan& pl, const CUtensorMap& m_res, const CUtensorMa
   }
   const bool rs = pl.p.row_scale != nullptr;
   const bool stats = RES_IS_Q && pl.p.stat_partial != nullptr && pl.p.loss == KGEB_LOSS_BCE;
-  if (pl.p.loss == KGEB_LOSS_KL) {
+  if (flash) {
+    if (RES_IS_Q) {
+      e = cudaFuncSetAttribute(tc_bwd_kernel<RES_IS_Q, true, KGEB_LOSS_KL, false, false, RES_IS_Q>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      if (e != cudaSuccess) return cuda_status(e, "tc_bwd smem attribute");
+      e = cudaLaunchKernelEx(&cfg, tc_bwd_kernel<RES_IS_Q, true, KGEB_LOSS_KL, false, false, RES_IS_Q>, m_res, m_str, m_out, pl.p);
+      if (e != cudaSuccess) return cuda_status(e, "tc_bwd launch");
+    }
+  } else if (pl.p.loss == KGEB_LOSS_KL) {
     if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_KL, true, false) else KGEB_BWD_LAUNCH(KGEB_LOSS_KL, false, false)
   } else if (stats) {
     if (rs) KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, true, RES_IS_Q) else KGEB_BWD_LAUNCH(KGEB_LOSS_BCE, false, RES_IS_Q)
@@ -862,6 +732,63 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __r
   if (i < n) for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
 }
 
+// FLASH reference score: mref[q] = max over a strided sample of <= 256 entities of this shard of Q[q] . table[e] (fp32).
+// Any value within ~[-87, +88] nats of the row's true maximum works (see tc_bwd_kernel); a sampled maximum is below the
+// true one by construction and, for any score distribution a trained model produces, far inside that window.
+__global__ void __launch_bounds__(256)
+sample_max_kernel(const float* __restrict__ Q, const float* __restrict__ table, int64_t B, int d, int64_t n_ent,
+                  float* __restrict__ mref) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= B) return;
+  const int64_t ns = n_ent < 256 ? n_ent : 256;
+  float q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = lane + 32 * i < d ? Q[r * d + lane + 32 * i] : 0.f;   // d <= 256
+  float best = -INFINITY;
+  for (int64_t k = 0; k < ns; ++k) {
+    const float* t = table + ((k * n_ent) / ns) * d;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (lane + 32 * i < d) acc = fmaf(q[i], __ldg(t + lane + 32 * i), acc);
+    best = fmaxf(best, warp_sum(acc));
+  }
+  if (lane == 0) mref[r] = best;
+}
+
+// rowstat[r] = (mref, sum_e exp(x - mref), 0, sum of x over the row's labels) -- the layout of the forward statistics
+__global__ void flash_rowstat_kernel(const float* __restrict__ sp, int64_t chunks, int64_t B, const float* __restrict__ mref,
+                                     const float* __restrict__ label_dot, float* __restrict__ rowstat) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  float l = 0.f;
+  for (int64_t k = 0; k < chunks * 4; ++k) l += sp[(k * B + r) * 2];     // fixed order
+  float* o = rowstat + r * 4;
+  o[0] = mref ? mref[r] : -INFINITY; o[1] = l; o[2] = 0.f; o[3] = label_dot[r];
+}
+
+// dQ[r,:] = w_r * exp(mref_r - lse_r) * o_sum[r,:] + label rows,  w_r = inv_batch * row_scale[r] * (row r has labels)
+__global__ void flash_dq_kernel(const float* __restrict__ o_sum, const float* __restrict__ rowstat_local,
+                                const float* __restrict__ lse, const int64_t* __restrict__ lab_off, float inv_batch,
+                                const float* __restrict__ row_scale, const float* __restrict__ dq_lab, int64_t B, int d,
+                                float* __restrict__ dQ) {
+  const int64_t numel = B * d;
+  int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  for (; i < numel; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    const int64_t r = i / d;
+    const bool has = lab_off[r + 1] > lab_off[r];
+    const float w = has ? inv_batch * (row_scale ? row_scale[r] : 1.f) * __expf(rowstat_local[r * 4] - lse[r]) : 0.f;
+    const float4 o = *reinterpret_cast<const float4*>(o_sum + i);
+    float4 v = make_float4(w * o.x, w * o.y, w * o.z, w * o.w);
+    if (dq_lab) {
+      const float4 a = *reinterpret_cast<const float4*>(dq_lab + i);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    *reinterpret_cast<float4*>(dQ + i) = v;
+  }
+}
+
 }  // namespace tcb
 
 bool tc_bwd_supported(int math, int d) { return math == KGEB_MATH_BF16 && d % 16 == 0 && d <= 256; }
@@ -889,7 +816,7 @@ static int64_t a256(int64_t x) { return (x + 255) / 256 * 256; }
 int64_t tc_bwd_workspace_bytes(int64_t B, int d, int64_t n_ent, int64_t nnz) {
   if (nnz < 1) nnz = 1;
   return a256((int64_t)kNumSMs * B * d * 4) + a256(B * (int64_t)d * 4) + 2 * a256(nnz * (int64_t)d * 4) + 2 * a256(nnz * 8) +
-         a256((int64_t)kNumSMs * 4 * B * 2 * 4) + a256(nnz * 4) + a256(B * 4) + kgeb_scatter_workspace_bytes(nnz, d) + 4096;
+         a256((int64_t)kNumSMs * 4 * B * 2 * 4) + a256(nnz * 4) + 2 * a256(B * 4) + kgeb_scatter_workspace_bytes(nnz, d) + 4096;
 }
 
 // A library-owned side stream per device: the sparse label part of a call is independent of its tile kernel, so it
@@ -921,9 +848,12 @@ static SideStream* side_stream(int which) {
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                  const int32_t* lab_perm, const float* tscale, float ls_add, float offset, const float* lse,
-                 float inv_batch, const float* row_scale, float* dQ, float* dTable, float* rowstat_out, void* ws,
-                 int64_t ws_bytes, cudaStream_t st) {
+                 float inv_batch, const float* row_scale, float* dQ, float* dTable, float* rowstat_out, int flags,
+                 void* ws, int64_t ws_bytes, cudaStream_t st) {
   using namespace tcb;
+  // KGEB_BWD_OVERWRITE_TABLE: the dense part is stored into dTable (no cleared buffer needed, no RMW); the label rows
+  // are then scattered in AFTER the tile kernel instead of before it
+  const bool overwrite = dTable && (flags & KGEB_BWD_OVERWRITE_TABLE);
   KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_bwd(bf16): entity dim must be a multiple of 16 and <= 256 (got %d)", d);
   KGEB_REQUIRE(Qb && tableb, "fused_bwd(bf16): the bf16 mirrors of Q and of the table are required");
   KGEB_REQUIRE(((reinterpret_cast<uintptr_t>(Qb) | reinterpret_cast<uintptr_t>(tableb)) & 15) == 0,
@@ -959,7 +889,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
           Q, table, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale, inv_batch, nnz, dQ ? rows_dq : nullptr,
           dTable ? rows_dt : nullptr, lab_ent, lab_row, want_stats ? entry_dot : nullptr, offset);
       KGEB_LAUNCH_CHECK("label_entry_rows");
-      if (dTable) {
+      if (dTable && !overwrite) {
         // label rows into the dense gradient before the tile kernel adds on top (it owns its rows; the order is fixed)
         rc = lab_perm ? kgeb_scatter_add_rows_perm(lab_ent, 1, lab_perm, rows_dt, nnz, d, dTable, n_ent, scatter_ws,
                                                    scatter_bytes, sd)
@@ -1014,16 +944,115 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
       pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = dTable;
+      pl.p.overwrite = overwrite ? 1 : 0;
       CUtensorMap m_out;   // fp32 [n_ent, d], boxes of 32 columns x 128 rows for the reduce-add flush
       if ((rc = make_map(&m_res, tableb, n_ent, d, RES_ROWS, true)) || (rc = make_map(&m_str, Qb, B, d, STR_ROWS, true)) ||
           (rc = make_map(&m_out, dTable, n_ent, d, RES_ROWS, false)))
         return rc;
       const int64_t jobs = pl.p.n_res_blocks;
       if ((rc = launch_bwd<false>(pl, m_res, m_str, m_out, jobs, st))) return rc;
+      if (overwrite && nnz > 0) {   // label rows on top of the stored dense part (joined with the side stream above)
+        rc = lab_perm ? kgeb_scatter_add_rows_perm(lab_ent, 1, lab_perm, rows_dt, nnz, d, dTable, n_ent, scatter_ws,
+                                                   scatter_bytes, st)
+                      : kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dTable, n_ent, scatter_ws, scatter_bytes, st);
+        if (rc) return rc;
+      }
     }
-  } else if (dQ && B > 0) {
-    cudaMemsetAsync(dQ, 0, (size_t)B * d * 4, st);
+  } else {
+    if (dQ && B > 0) cudaMemsetAsync(dQ, 0, (size_t)B * d * 4, st);
+    if (overwrite && n_ent > 0) cudaMemsetAsync(dTable, 0, (size_t)n_ent * d * 4, st);
   }
+  return KGEB_OK;
+}
+
+// FLASH forward (KL, bf16 tiles): row statistics and o_sum = sum_e exp(x - mref) * table[e] in one pass over the table.
+int tc_flash_fwd(const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb, int64_t e_lo,
+                 int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, float* rowstat, float* o_sum,
+                 void* ws, int64_t ws_bytes, cudaStream_t st) {
+  using namespace tcb;
+  KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_flash_fwd: entity dim must be a multiple of 16 and <= 256 (got %d)", d);
+  KGEB_REQUIRE(Qb && tableb, "fused_flash_fwd: the bf16 mirrors of Q and of the table are required");
+  KGEB_REQUIRE(ws_bytes >= tc_bwd_workspace_bytes(B, d, n_ent, nnz), "fused_flash_fwd: workspace too small");
+  const int64_t nz = nnz < 1 ? 1 : nnz;
+  char* wp = reinterpret_cast<char*>(ws);
+  float* partial = reinterpret_cast<float*>(wp);      wp += a256((int64_t)kNumSMs * B * d * 4);
+  wp += a256(B * (int64_t)d * 4) + 2 * a256(nz * (int64_t)d * 4);
+  int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
+  int64_t* lab_row = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
+  float* stat_partial = reinterpret_cast<float*>(wp); wp += a256((int64_t)kNumSMs * 4 * B * 2 * 4);
+  float* entry_dot = reinterpret_cast<float*>(wp);    wp += a256(nz * 4);
+  float* label_dot = reinterpret_cast<float*>(wp);    wp += a256(B * 4);
+  float* mref = reinterpret_cast<float*>(wp);         wp += a256(B * 4);
+  if (B == 0) return KGEB_OK;
+  // exact fp32 scores at the label entries of this shard (their sum per row enters the loss value)
+  if (nnz > 0) {
+    label_entry_rows_kernel<<<(unsigned)((nnz + 8 * LABEL_EPW - 1) / (8 * LABEL_EPW)), 256, 0, st>>>(
+        Q, table, B, d, e_lo, n_ent, lab_off, lab_col, nullptr, nullptr, 1.f, nnz, nullptr, nullptr, lab_ent, lab_row,
+        entry_dot, 0.f);
+    KGEB_LAUNCH_CHECK("label_entry_rows");
+    label_row_sum2_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(entry_dot, lab_off, B, label_dot);
+  } else {
+    cudaMemsetAsync(label_dot, 0, (size_t)B * 4, st);
+  }
+  if (n_ent <= 0) {   // an empty shard contributes nothing: (max, sum) = (-inf, 0)
+    cudaMemsetAsync(o_sum, 0, (size_t)B * d * 4, st);
+    flash_rowstat_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(nullptr, 0, B, nullptr, label_dot, rowstat);
+    KGEB_LAUNCH_CHECK("flash_rowstat");
+    return KGEB_OK;
+  }
+  sample_max_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(Q, table, B, d, n_ent, mref);
+  KGEB_LAUNCH_CHECK("sample_max");
+  Plan pl = make_plan(true, true, B, d, n_ent);
+  if (pl.p.nstr < 2) { set_error("fused_flash_fwd: not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
+  pl.p.loss = KGEB_LOSS_KL; pl.p.inv_batch = 1.f; pl.p.out = partial; pl.p.stat_partial = stat_partial; pl.p.mref = mref;
+  CUtensorMap m_res, m_str;
+  int rc;
+  if ((rc = make_map(&m_res, Qb, B, d, RES_ROWS, true)) || (rc = make_map(&m_str, tableb, n_ent, d, STR_ROWS, true))) return rc;
+  if ((rc = launch_bwd<true>(pl, m_res, m_str, m_res, pl.p.n_res_blocks * pl.p.chunks, st, true))) return rc;
+  if (SideStream* s0 = side_stream(0)) cudaEventRecord(s0->tiles, st);
+  const int64_t numel = B * (int64_t)d;
+  const int64_t rblocks = (numel / 4 + 255) / 256;
+  reduce_dq_partials_kernel<<<(unsigned)(rblocks > 4096 ? 4096 : rblocks), 256, 0, st>>>(partial, pl.p.chunks, numel, nullptr, o_sum);
+  KGEB_LAUNCH_CHECK("reduce_dq_partials");
+  flash_rowstat_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(stat_partial, pl.p.chunks, B, mref, label_dot, rowstat);
+  KGEB_LAUNCH_CHECK("flash_rowstat");
+  return KGEB_OK;
+}
+
+// FLASH backward for the queries: no table pass -- o_sum is rescaled by the (global) log-sum-exp and the exact fp32 label
+// rows are added.
+int tc_flash_dq(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent, const int64_t* lab_off,
+                const int64_t* lab_col, int64_t nnz, const float* tscale, const float* rowstat_local, const float* lse,
+                float inv_batch, const float* row_scale, const float* o_sum, float* dQ, void* ws, int64_t ws_bytes,
+                cudaStream_t st) {
+  using namespace tcb;
+  KGEB_REQUIRE(ws_bytes >= tc_bwd_workspace_bytes(B, d, n_ent, nnz), "fused_flash_dq: workspace too small");
+  if (B == 0) return KGEB_OK;
+  const int64_t nz = nnz < 1 ? 1 : nnz;
+  char* wp = reinterpret_cast<char*>(ws);
+  wp += a256((int64_t)kNumSMs * B * d * 4);
+  float* dq_lab = reinterpret_cast<float*>(wp);       wp += a256(B * (int64_t)d * 4);
+  float* rows_dq = reinterpret_cast<float*>(wp);      wp += 2 * a256(nz * (int64_t)d * 4);
+  int64_t* lab_ent = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
+  int64_t* lab_row = reinterpret_cast<int64_t*>(wp);  wp += a256(nz * 8);
+  wp += a256((int64_t)kNumSMs * 4 * B * 2 * 4) + a256(nz * 4) + 2 * a256(B * 4);
+  void* scatter_ws = wp;
+  const int64_t scatter_bytes = ws_bytes - (wp - reinterpret_cast<char*>(ws));
+  int rc;
+  const bool labels = nnz > 0 && n_ent > 0;
+  if (labels) {
+    label_entry_rows_kernel<<<(unsigned)((nnz + 8 * LABEL_EPW - 1) / (8 * LABEL_EPW)), 256, 0, st>>>(
+        Q, table, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale, inv_batch, nnz, rows_dq, nullptr, lab_ent, lab_row,
+        nullptr, 0.f);
+    KGEB_LAUNCH_CHECK("label_entry_rows");
+    cudaError_t e = cudaMemsetAsync(dq_lab, 0, (size_t)B * d * 4, st);
+    if (e != cudaSuccess) return cuda_status(e, "fused_flash_dq memset");
+    if ((rc = scatter_add_rows_presorted(lab_row, rows_dq, nnz, d, dq_lab, B, scatter_ws, scatter_bytes, st))) return rc;
+  }
+  const int64_t rblocks = (B * (int64_t)d / 4 + 255) / 256;
+  flash_dq_kernel<<<(unsigned)(rblocks > 4096 ? 4096 : rblocks), 256, 0, st>>>(o_sum, rowstat_local, lse, lab_off, inv_batch,
+                                                                              row_scale, labels ? dq_lab : nullptr, B, d, dQ);
+  KGEB_LAUNCH_CHECK("flash_dq");
   return KGEB_OK;
 }
 

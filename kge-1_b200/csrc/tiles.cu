@@ -28,8 +28,15 @@ int tc_label_rows(const float* Q, int64_t B, int d, const float* table, int64_t 
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                  const int32_t* lab_perm, const float* tscale, float ls_add, float offset, const float* lse,
-                 float inv_batch, const float* row_scale, float* dQ, float* dTable, float* rowstat_out, void* ws,
-                 int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
+                 float inv_batch, const float* row_scale, float* dQ, float* dTable, float* rowstat_out, int flags,
+                 void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
+int tc_flash_fwd(const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb, int64_t e_lo,
+                 int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, float* rowstat, float* o_sum,
+                 void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
+int tc_flash_dq(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent, const int64_t* lab_off,
+                const int64_t* lab_col, int64_t nnz, const float* tscale, const float* rowstat_local, const float* lse,
+                float inv_batch, const float* row_scale, const float* o_sum, float* dQ, void* ws, int64_t ws_bytes,
+                cudaStream_t st);  // tc_bwd.cu
 int tc_rank_count(const float* Q, int64_t nq, int d, const float* table, int64_t e_lo, int64_t n_ent,
                   const float* true_score, const void* true_ent, int idx64, const int64_t* f_off,
                   const int64_t* f_col, const int64_t* t_off, const int64_t* t_col, int64_t* counts,
@@ -859,14 +866,18 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
                    int64_t e_hi, int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                    const int32_t* lab_perm, float label_smoothing, float offset, const float* lse, float inv_batch,
                    const float* grad_scale, const void* table_bf16, float* dQ, float* dTable, float* rowstat_out,
-                   void* workspace, int64_t workspace_bytes, void* stream) {
+                   int flags, void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
   if (rc) return rc;
   KGEB_REQUIRE(loss != KGEB_LOSS_KL || lse, "fused_bwd: KL needs the per-row log-sum-exp");
+  KGEB_REQUIRE((flags & ~KGEB_BWD_OVERWRITE_TABLE) == 0, "fused_bwd: unknown flags %d", flags);
   KGEB_REQUIRE(lab_off && lab_col, "fused_bwd: label CSR is NULL");
   const int64_t n_ent = e_hi - e_lo;
-  if (B == 0) return KGEB_OK;
   cudaStream_t st = as_stream(stream);
+  if (B == 0) {   // no rows: the gradient of an overwritten table is all zeros
+    if (dTable && (flags & KGEB_BWD_OVERWRITE_TABLE) && n_ent > 0) cudaMemsetAsync(dTable, 0, (size_t)n_ent * d * 4, st);
+    return KGEB_OK;
+  }
   KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, nnz), "fused_bwd: workspace too small");
   LossParams lp{loss, 1.f - label_smoothing, label_smoothing > 0.f ? 1.f / (float)num_entities : 0.f, offset,
                 inv_batch};
@@ -890,7 +901,7 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
       return rc;
     return tc_fused_bwd(loss, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, lab_perm, tail.tscale,
                         lp.ls_add, offset, lse, inv_batch, grad_scale, dQ, dTable, fused_stats ? rowstat_out : nullptr,
-                        workspace, tail.usable, st);
+                        flags, workspace, tail.usable, st);
   }
   if (rowstat_out && (rc = kgeb_fused_fwd(loss, math, Q, B, d, table, e_lo, e_hi, num_entities, lab_off, lab_col, nnz,
                                           label_smoothing, offset, table_bf16, rowstat_out, workspace, workspace_bytes,
@@ -900,6 +911,8 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
   // dims outside the BF16 tile build use the fp32 CUDA-core tiles below
   label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, tscale);
   KGEB_LAUNCH_CHECK("label_weight");
+  if (dTable && (flags & KGEB_BWD_OVERWRITE_TABLE) && n_ent > 0)   // the fp32 tiles add: overwrite = clear first
+    cudaMemsetAsync(dTable, 0, (size_t)n_ent * d * 4, st);
   const int nc = (d + 31) / 32;
 #define LAUNCH_BWD(NC)                                                                                              \
   {                                                                                                                 \
@@ -922,6 +935,42 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
   return KGEB_OK;
 }
 
+
+int kgeb_fused_flash_fwd(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
+                         int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
+                         const void* table_bf16, float* rowstat, float* o_sum, void* workspace, int64_t workspace_bytes,
+                         void* stream) {
+  int rc = check_fused(KGEB_LOSS_KL, d, 0.f, Q, table, e_lo, e_hi);
+  if (rc) return rc;
+  KGEB_REQUIRE(lab_off && lab_col && rowstat && o_sum && table_bf16, "fused_flash_fwd: bad arguments");
+  KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_flash_fwd: needs the bf16 tiles (dim %% 16 == 0, <= 256; got %d)", d);
+  (void)num_entities;
+  const int64_t n_ent = e_hi - e_lo;
+  if (B == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, nnz), "fused_flash_fwd: workspace too small");
+  TailWs tail = carve_tail(workspace, workspace_bytes, B, d);
+  if ((rc = tc_to_bf16(Q, tail.qb, B * (int64_t)d, st))) return rc;
+  return tc_flash_fwd(Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, rowstat, o_sum, workspace,
+                      tail.usable, st);
+}
+
+int kgeb_fused_flash_dq(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
+                        const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const float* rowstat_local,
+                        const float* lse, float inv_batch, const float* grad_scale, const float* o_sum, float* dQ,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  KGEB_REQUIRE(Q && table && lab_off && lab_col && rowstat_local && lse && o_sum && dQ && d > 0 && e_hi >= e_lo,
+               "fused_flash_dq: bad arguments");
+  const int64_t n_ent = e_hi - e_lo;
+  if (B == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, nnz), "fused_flash_dq: workspace too small");
+  TailWs tail = carve_tail(workspace, workspace_bytes, B, d);
+  label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(KGEB_LOSS_KL, lab_off, B, 1.f, tail.tscale);
+  KGEB_LAUNCH_CHECK("label_weight");
+  return tc_flash_dq(Q, B, d, table, e_lo, n_ent, lab_off, lab_col, nnz, tail.tscale, rowstat_local, lse, inv_batch,
+                     grad_scale, o_sum, dQ, workspace, tail.usable, st);
+}
 
 // per-row loss values, log-sum-exp and the batch loss from the fused forward statistics: one block, fixed order
 __global__ void __launch_bounds__(1024)

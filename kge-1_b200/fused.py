@@ -106,9 +106,10 @@ def rows_loss(rowstat: torch.Tensor, lab_off: torch.Tensor, loss: int, label_smo
 
 def fused_backward(q, table, lab_off, lab_col, loss, label_smoothing, offset, lse, inv_batch, grad_scale, math,
                    shard: Shard, d_table: Optional[torch.Tensor], want_dq: bool = True,
-                   lab_perm: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-    """dQ (returned, all-reduced over shards) and d_table += G^T Q for the rows of this shard.  lab_perm (int32,
-    optional): stable argsort of lab_col from the collate (spares the device sort of the label scatter)."""
+                   lab_perm: Optional[torch.Tensor] = None, overwrite: bool = False) -> Optional[torch.Tensor]:
+    """dQ (returned, all-reduced over shards) and d_table += G^T Q for the rows of this shard (`overwrite`: d_table = ...,
+    KGEB_BWD_OVERWRITE_TABLE -- the buffer need not be cleared).  lab_perm (int32, optional): stable argsort of lab_col
+    from the collate (spares the device sort of the label scatter)."""
     b, d = q.shape
     n_ent = shard.e_hi - shard.e_lo
     dq = torch.empty(b, d, dtype=torch.float32, device=q.device) if want_dq else None
@@ -118,7 +119,8 @@ def fused_backward(q, table, lab_off, lab_col, loss, label_smoothing, offset, ls
              None if lab_perm is None else lab_perm.data_ptr(), float(label_smoothing), float(offset), None if lse is None else lib.f32(lse, "lse"), float(inv_batch),
              None if grad_scale is None else lib.f32(grad_scale, "grad scale"), _mirror_ptr(table, math, b, d),
              None if dq is None else dq.data_ptr(), None if d_table is None else lib.f32(d_table, "table gradient"),
-             None, ws.data_ptr(), ws.numel(), lib.stream_ptr(q))
+             None, lib.BWD_OVERWRITE_TABLE if (overwrite and d_table is not None) else 0, ws.data_ptr(), ws.numel(),
+             lib.stream_ptr(q))
     if dq is not None and n_ent == 0:
         dq.zero_()
     if dq is not None and shard.distributed:
@@ -144,10 +146,14 @@ class AllEntityLoss(torch.autograd.Function):
     def backward(ctx, g):
         qd, td, lab_off, lab_col, lse = ctx.saved_tensors
         loss, ls, offset, inv_batch, math, shard = ctx.cfg
-        d_table = torch.zeros_like(td) if ctx.needs_input_grad[1] else None
+        # a table-sized gradient: written once by the kernels (no zero-fill pass) when this rank scores every row
+        whole = shard.e_lo == 0 and shard.e_hi == td.shape[0]
+        d_table = None
+        if ctx.needs_input_grad[1]:
+            d_table = torch.empty_like(td) if whole else torch.zeros_like(td)
         gs = g.detach().float().contiguous()  # upstream gradient per row; stays on the device
         dq = fused_backward(qd, td, lab_off, lab_col, loss, ls, offset, lse, inv_batch, gs, math, shard, d_table,
-                            want_dq=ctx.needs_input_grad[0])
+                            want_dq=ctx.needs_input_grad[0], overwrite=whole)
         return dq, d_table, None, None, None, None, None, None, None, None
 
 

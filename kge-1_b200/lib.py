@@ -21,6 +21,7 @@ SP_, _PO = 0, 1
 DOT, NEG_L1, NEG_L2, ROT_L1, ROT_L2 = 0, 1, 2, 3, 4
 LOSS_KL, LOSS_BCE = 0, 1
 MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
+BWD_OVERWRITE_TABLE = 1
 
 _c = ctypes
 _p, _i, _l, _f, _u = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_uint64
@@ -40,7 +41,9 @@ SIGNATURES = {
     "kgeb_score_all": [_i, _i, _p, _l, _i, _p, _p, _i, _l, _p, _l, _l, _p],
     "kgeb_score_all_bwd": [_i, _p, _l, _i, _p, _p, _i, _l, _p, _p, _l, _l, _p, _p, _p],
     "kgeb_fused_fwd": [_i, _i, _p, _l, _i, _p, _l, _l, _l, _p, _p, _l, _f, _f, _p, _p, _p, _l, _p],
-    "kgeb_fused_bwd": [_i, _i, _p, _l, _i, _p, _l, _l, _l, _p, _p, _l, _p, _f, _f, _p, _f, _p, _p, _p, _p, _p, _p, _l, _p],
+    "kgeb_fused_bwd": [_i, _i, _p, _l, _i, _p, _l, _l, _l, _p, _p, _l, _p, _f, _f, _p, _f, _p, _p, _p, _p, _p, _i, _p, _l, _p],
+    "kgeb_fused_flash_fwd": [_p, _l, _i, _p, _l, _l, _l, _p, _p, _l, _p, _p, _p, _p, _l, _p],
+    "kgeb_fused_flash_dq": [_p, _l, _i, _p, _l, _l, _p, _p, _l, _p, _p, _f, _p, _p, _p, _p, _l, _p],
     "kgeb_fused_label_rows": [_i, _p, _l, _i, _p, _l, _l, _p, _p, _l, _p, _f, _f, _p, _p, _p, _l, _p],
     "kgeb_fused_bwd_wait_tiles": [_p],
     "kgeb_to_bf16": [_p, _p, _l, _p],

@@ -161,14 +161,24 @@ class FusedAllEntityStepper:
         n_e, n_r = self.E * self.d, self.rel.shape[0] * self.dr
         # layout [g_q | g_ent | g_rel | loss]: data-parallel replicas fold g_q into g_ent and all-reduce the tail only
         self.p2p = None
+        # Large tables (Wikidata5M: 2.4 GB per [E,d] buffer): ONE gradient buffer that is never cleared.  The dense dTable
+        # tile kernel STORES its rows (KGEB_BWD_OVERWRITE_TABLE), the sparse parts (label rows, query-side rows) are
+        # scattered on top afterwards, Adagrad reads one buffer: per step 2 x E*d*4 bytes of clears and one E*d*4 read
+        # less than the overlapped two-buffer flow that small tables (FB15k-237: 7.4 MB, latency-bound) keep.
+        self.seq = (math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256 and dp_group is None
+                    and not (shard is not None and shard.distributed) and self.pen is None and nnz_max > 0
+                    and n_e * 4 >= (64 << 20))
         if dp_group is not None and dp_p2p:
             self._setup_p2p(dp_group, n_e, n_r, dev)      # gradients live in peer-mapped (symmetric) memory
+        elif self.seq:
+            self.gflat = torch.zeros(n_e + n_r + 1, **f32)
         else:
             self.gflat = torch.zeros(2 * n_e + n_r + 1, **f32)
+        g0 = 0 if self.seq else n_e
         self.g_q = self.gflat[:n_e].view(self.E, self.d)              # query-side rows (da scattered by entity id)
-        self.g_ent = self.gflat[n_e:2 * n_e].view(self.E, self.d)     # dense part (G^T Q) + label rows (side stream)
-        self.g_rel = self.gflat[2 * n_e:2 * n_e + n_r].view(self.rel.shape[0], self.dr)
-        self.loss = self.gflat[2 * n_e + n_r:].view(())
+        self.g_ent = self.gflat[g0:g0 + n_e].view(self.E, self.d)     # dense part (G^T Q) + label rows (side stream)
+        self.g_rel = self.gflat[g0 + n_e:g0 + n_e + n_r].view(self.rel.shape[0], self.dr)
+        self.loss = self.gflat[g0 + n_e + n_r:].view(())
         self.dp_flat = self.gflat[n_e:]                               # what the replicas exchange
         self.rowstat = torch.empty(rows, 4, **f32)
         self.loss_rows = torch.zeros(rows, **f32)      # per-row loss values (kgeb_loss_from_rowstat rows_out)
@@ -230,11 +240,14 @@ class FusedAllEntityStepper:
         cur = torch.cuda.current_stream()
         self.side2.wait_stream(cur)
         with torch.cuda.stream(self.side2):
-            self.gflat.zero_()
+            if self.seq:
+                self.gflat[self.E * self.d:].zero_()      # relation gradient + loss only
+            else:
+                self.gflat.zero_()
             self.ev_clear.record()
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), ent.data_ptr(), self.a_idx.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
-        if self._split_label_rows():
+        if self._split_label_rows() and not self.seq:
             # Label rows of the dense table gradient go to g_q (the optimizer adds g_ent + g_q), on the third stream
             # and underneath the dQ tile kernel: the dTable tile kernel then depends on nothing but the cleared g_ent
             # and starts the moment dQ releases the SMs.  (Scattered into g_ent in front of the tile kernel, as
@@ -281,23 +294,25 @@ class FusedAllEntityStepper:
         if self._split_label_rows():
             # dQ first; the dense-only dTable kernel (nnz = 0: no label part) queues behind it on the second stream
             lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late_stats else None,
-                     self.ws.data_ptr(), self.ws.numel(), st)
+                     0, self.ws.data_ptr(), self.ws.numel(), st)
             dense = list(common)
             dense[11], dense[12] = 0, None          # nnz, lab_perm
             with torch.cuda.stream(self.side):
                 lib.call("kgeb_fused_bwd_wait_tiles", lib.stream_ptr(self.ent))   # the dQ tile kernel, not its reductions
-                self.side.wait_event(self.ev_clear)
-                lib.call("kgeb_fused_bwd", *dense, None, self.g_ent.data_ptr(), None, self.ws3.data_ptr(), self.ws3.numel(),
+                if not self.seq:
+                    self.side.wait_event(self.ev_clear)
+                lib.call("kgeb_fused_bwd", *dense, None, self.g_ent.data_ptr(), None,
+                         lib.BWD_OVERWRITE_TABLE if self.seq else 0, self.ws3.data_ptr(), self.ws3.numel(),
                          lib.stream_ptr(self.ent))
             return
         self.side.wait_stream(cur)
         if not sh.distributed:
             self.side.wait_stream(self.side2)     # cleared gradient buffers
         with torch.cuda.stream(self.side):
-            lib.call("kgeb_fused_bwd", *common, None, self.g_ent[sh.e_lo:sh.e_hi].data_ptr(), None, self.ws2.data_ptr(),
+            lib.call("kgeb_fused_bwd", *common, None, self.g_ent[sh.e_lo:sh.e_hi].data_ptr(), None, 0, self.ws2.data_ptr(),
                      self.ws2.numel(), lib.stream_ptr(self.ent))
         lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late_stats else None,
-                 self.ws.data_ptr(), self.ws.numel(), st)
+                 0, self.ws.data_ptr(), self.ws.numel(), st)
         if sh.distributed:
             self._join_side()     # the collectives that follow need the complete dense gradient
 
@@ -336,6 +351,13 @@ class FusedAllEntityStepper:
                 else:
                     lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None,
                              rel.numel(), self.lr, self.eps, 0.0, None, st2)
+        if self.seq:
+            # the dense part has been STORED into the one gradient buffer: label rows and query-side rows go on top
+            self._join_side()
+            lib.call("kgeb_fused_label_rows", self.loss_kind, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
+                     self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.lab_perm.data_ptr(),
+                     self.ls, 1.0 / self.global_batch, None, self.g_ent.data_ptr(), self.ws2.data_ptr(),
+                     self.ws2.numel(), st)
         lib.call("kgeb_scatter_add_rows_perm", self.a_idx.data_ptr(), 1, self.a_perm.data_ptr(), self.da.data_ptr(),
                  self.rows, self.d, self.g_q.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
         if self.dp_world > 1:
@@ -352,8 +374,8 @@ class FusedAllEntityStepper:
                      ent.numel(), self.lr, self.eps, 0.0, self.pen["ent"][0], self.pen["ent"][1], mirror,
                      self.penalty_values.data_ptr(), self.pen_ws[0].data_ptr(), self.pen_ws[0].numel(), st)
         else:
-            lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(), self.g_q.data_ptr(),
-                     ent.numel(), self.lr, self.eps, 0.0, mirror, st)
+            lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(),
+                     None if self.seq else self.g_q.data_ptr(), ent.numel(), self.lr, self.eps, 0.0, mirror, st)
         cur.wait_stream(self.side2)
 
     # -- data-parallel exchange fused with the update over NVLink peer memory (csrc/p2p.cu) ---------------------------
@@ -625,8 +647,13 @@ class RowShardedAllEntityStepper:
         self.A = torch.zeros(rows, self.d, **f32)          # query-side entity rows, assembled by all-reduce
         self.Q, self.dQ = torch.empty(rows, self.d, **f32), torch.empty(rows, self.d, **f32)
         self.da, self.dp = torch.empty(rows, self.d, **f32), torch.empty(rows, self.dr, **f32)
-        self.g_ent = torch.zeros(max(self.n_loc, 1), self.d, **f32)       # dense part + label rows, local rows only
-        self.g_q = torch.zeros(self.n_loc + 1, self.d, **f32)             # query-side rows; last row = "not mine"
+        # bf16 tiles: ONE gradient buffer [n_loc + 1, d] that is never cleared -- the tile kernel stores the dense part
+        # (KGEB_BWD_OVERWRITE_TABLE), label rows and query-side rows are scattered on top; row n_loc collects the
+        # query-side rows of other owners ("not mine") and is the only row zeroed per step.  fp32 tiles: two cleared buffers.
+        self.one_buffer = math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256
+        self.g_all = torch.zeros(self.n_loc + 1, self.d, **f32)
+        self.g_ent = self.g_all[:max(self.n_loc, 1)]                      # dense part + label rows, local rows only
+        self.g_q = self.g_all if self.one_buffer else torch.zeros(self.n_loc + 1, self.d, **f32)   # last row = "not mine"
         self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
         self.loss = torch.zeros((), **f32)
         self.rowstat = torch.empty(rows, 4, **f32)
@@ -665,7 +692,11 @@ class RowShardedAllEntityStepper:
     # -- compute stages (each one CUDA graph) and the collectives between them ----------------------------------
     def _stage_gather(self):
         st = lib.stream_ptr(self.ent)
-        self.g_ent.zero_(); self.g_q.zero_(); self.g_rel.zero_()
+        if self.one_buffer:
+            self.g_all[self.n_loc:].zero_()
+        else:
+            self.g_ent.zero_(); self.g_q.zero_()
+        self.g_rel.zero_()
         lib.call("kgeb_gather_rows_shard", self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.d, self.a_idx.data_ptr(),
                  1, self.rows, self.A.data_ptr(), self.loc_ids.data_ptr(), st)
 
@@ -694,10 +725,12 @@ class RowShardedAllEntityStepper:
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
-            lib.call("kgeb_fused_bwd", *common, None, self.g_ent.data_ptr(), None, self.ws2.data_ptr(), self.ws2.numel(),
+            # the dense part is stored (no cleared buffer), the label rows of this shard are scattered on top by the call
+            lib.call("kgeb_fused_bwd", *common, None, self.g_ent.data_ptr(), None,
+                     lib.BWD_OVERWRITE_TABLE if self.mirror is not None else 0, self.ws2.data_ptr(), self.ws2.numel(),
                      lib.stream_ptr(self.ent))
         lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late else None,
-                 self.ws.data_ptr(), self.ws.numel(), st)
+                 0, self.ws.data_ptr(), self.ws.numel(), st)
         cur.wait_stream(self.side)
 
     def _stage_update(self):
@@ -720,7 +753,7 @@ class RowShardedAllEntityStepper:
         if self.n_loc > 0:
             s_loc = self.opt.state[self.ent]["sum"][self.e_lo:self.e_hi]
             lib.call("kgeb_adagrad_dense", self._ent_loc().data_ptr(), s_loc.data_ptr(), self.g_ent.data_ptr(),
-                     self.g_q.data_ptr(), self.n_loc * self.d, self.lr, self.eps, 0.0,
+                     None if self.one_buffer else self.g_q.data_ptr(), self.n_loc * self.d, self.lr, self.eps, 0.0,
                      None if self.mirror is None else self.mirror.data_ptr(), st)
 
     def _exchange(self, which: int):

@@ -25,11 +25,14 @@ def kb():
 def close(got, ref, rtol, what):
     got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
     assert got.shape == ref.shape, what
-    err = (got - ref).abs().max().item()
-    assert err <= rtol * max(ref.abs().max().item(), 1e-30), f"{what}: max err {err:.3e} vs bound {rtol * ref.abs().max().item():.3e}"
+    diff = (got - ref).abs()
+    err = diff.max().item()
+    where = np.unravel_index(int(diff.argmax()), tuple(diff.shape)) if diff.numel() else ()
+    assert err <= rtol * max(ref.abs().max().item(), 1e-30), \
+        f"{what}: max err {err:.3e} at {where} vs bound {rtol * ref.abs().max().item():.3e}"
 
 
-def _problem(kb, model, e, r, d, b, nlab_max, seed):
+def _problem(kb, model, e, r, d, b, nlab_max, seed, empty_row=True):
     """Queries of a real model (normal(0, 0.1) tables), rows sp_ then _po, and a ragged label CSR."""
     torch.manual_seed(seed)
     m = kb.KgeModel(model, e, r, d).cuda()
@@ -39,8 +42,10 @@ def _problem(kb, model, e, r, d, b, nlab_max, seed):
     with torch.no_grad():
         q = torch.cat((m.queries(kb.lib.SP_, a[: b // 2], p[: b // 2]), m.queries(kb.lib._PO, a[b // 2:], p[b // 2:]))).contiguous()
         q *= 8.0          # scores of a partly trained model (O(1)), so that sigmoid / softmax are not flat
-    n = torch.randint(0, nlab_max + 1, (b,), generator=gen)
-    n[0], n[1] = 0, nlab_max                      # an empty row and a full one
+    n = torch.randint(0 if empty_row else 1, nlab_max + 1, (b,), generator=gen)
+    # empty rows (BCE only: a KvsAll / 1vsAll query always has a label, and the reference's KL of an all-zero label row
+    # is 0 by F.normalize's eps, loss.py:211-213 -- not a case its jobs can produce) and a full one
+    n[0], n[1] = (0 if empty_row else 1), nlab_max
     lab_off = torch.zeros(b + 1, dtype=torch.int64)
     lab_off[1:] = torch.cumsum(n, 0)
     cols = [torch.randperm(min(e, 100000), generator=gen)[: int(k)].sort().values * (e // min(e, 100000)) for k in n.tolist()]
@@ -91,7 +96,7 @@ def _float64_table_rows(q, w, lab_off, lab_col, ents, loss, offset, inv_batch, l
 @pytest.mark.parametrize("loss", ["bce", "kl"])
 def test_fb15k237_shape_fused_kernels(kb, loss):
     e, r, d, b = 14541, 237, 128, 4096
-    m, q, lab_off, lab_col = _problem(kb, "complex", e, r, d, b, 6, seed=3)
+    m, q, lab_off, lab_col = _problem(kb, "complex", e, r, d, b, 6, seed=3, empty_row=(loss == "bce"))
     w = m.get_s_embedder().weight.detach()
     kind = kb.lib.LOSS_KL if loss == "kl" else kb.lib.LOSS_BCE
     offset = 0.1 if loss == "bce" else 0.0
@@ -228,3 +233,33 @@ def test_wikidata5m_shape_rank_counts_bit_exact_on_dyadic_tables(kb, model, math
         filt = int((row > t).sum()) + int((row == t).sum()) // 2
         assert int(got["o_raw"][i]) == raw, (model, math, i, int(got["o_raw"][i]), raw)
         assert int(got["o_filt"][i]) == filt, (model, math, i, int(got["o_filt"][i]), filt)
+
+
+@pytest.mark.parametrize("loss", ["kl", "bce"])
+def test_large_table_captured_step_one_gradient_buffer(kb, loss):
+    """Tables of >= 64 MB take the one-buffer flow of FusedAllEntityStepper (dense gradient STORED by the tile kernel,
+    KGEB_BWD_OVERWRITE_TABLE; label and query-side rows scattered on top; nothing cleared): three 1vsAll steps must equal
+    the autograd flow on the same bf16 tiles (same arithmetic, different buffer handling) to fp32 rounding."""
+    e, r, d, b = 140_000, 50, 128, 256
+    torch.manual_seed(0)
+    ref = kb.KgeModel("distmult", e, r, d).cuda()
+    new = kb.KgeModel("distmult", e, r, d).cuda()
+    new.load_state_dict(ref.state_dict())
+    mk = lambda m: kb.optim.create("Adagrad", m.parameters(), lr=0.2, initial_accumulator_value=0.1)   # noqa: E731
+    jr = kb.TrainingJob1vsAll(ref, mk(ref), kb.KgeLoss.create(loss), math_mode=kb.lib.MATH_BF16)
+    kind = kb.lib.LOSS_KL if loss == "kl" else kb.lib.LOSS_BCE
+    st = kb.trainer.FusedAllEntityStepper(new, mk(new), 2 * b, 2 * b, kind, b, math_mode=kb.lib.MATH_BF16)
+    assert st.seq, "the one-buffer flow was not selected"
+    gen = torch.Generator().manual_seed(1)
+    for step in range(3):
+        t = torch.stack((torch.randint(0, e, (b,), generator=gen), torch.randint(0, r, (b,), generator=gen),
+                         torch.randint(0, e, (b,), generator=gen)), 1).cuda()
+        t[:8, 2] = t[0, 2]                                  # a hub object: several label rows on one entity
+        a = jr.step(step, {"triples": t})
+        z = torch.zeros(b, dtype=torch.int32, device="cuda")
+        st.set_inputs(torch.cat((t[:, 0], t[:, 2])), torch.cat((t[:, 1], t[:, 1])), torch.cat((z, z + 1)),
+                      torch.arange(2 * b + 1, device="cuda"), torch.cat((t[:, 2], t[:, 0])))
+        got = st.step().item()
+        assert got == pytest.approx(a.avg_loss, rel=2e-5), (loss, step)
+        for x, y in ((new.get_s_embedder().weight, ref.get_s_embedder().weight), (new.get_p_embedder().weight, ref.get_p_embedder().weight)):
+            assert (x - y).abs().max().item() <= 0.2 * 1e-3, (loss, step, (x - y).abs().max().item())
