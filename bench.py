@@ -220,7 +220,18 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
              "tc_bwd_kernel<dQ> (kgeb_fused_bwd: S recomputed, dQ += G*T)": (lambda: bwd(True, False), 2, 1, "tc_bwd_kernel<1, 1, 0, 0, 0>"),
              "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": (lambda: bwd(False, True), 2, 1, "tc_bwd_kernel<0, 1, 0, 0, 0>")}
     if getattr(st, "flash", False):
-        cases.pop(next(iter(cases)))      # the forward statistics come out of the dQ pass
+        # forward statistics and dQ come out of ONE table pass (kgeb_fused_flash_fwd): two GEMMs executed, both algorithmic
+        o_sum = torch.empty(rows, d, device=dev)
+
+        def flash():
+            L.call("kgeb_fused_flash_fwd", st.Q.data_ptr(), rows, d, table.data_ptr(), e_lo, e_hi, st.E, off0.data_ptr(),
+                   st.lab_col.data_ptr(), 0, mp, rowstat.data_ptr(), o_sum.data_ptr(), ws.data_ptr(), ws.numel(),
+                   L.stream_ptr(table))
+
+        dt = [v for k, v in cases.items() if "dTable" in k][0]
+        cases = {"tc_bwd_kernel<flash> (kgeb_fused_flash_fwd: scores + log-sum-exp + o_sum for dQ, one pass)":
+                 (flash, 2, 2, "tc_bwd_kernel<1, 1, 0, 0, 0, 1>"),
+                 "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": dt}
     res = {}
     for name, (fn, executed, algorithmic, _) in cases.items():
         ts = []

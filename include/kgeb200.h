@@ -170,7 +170,7 @@ int kgeb_loss_from_rowstat(int loss, const float* rowstat, const int64_t* lab_of
 /* KL on the bf16 tiles with the forward statistics and the query gradient in ONE pass over the table (the forward kernel of
  * kgeb_fused_fwd and the score recomputation of the dQ half of kgeb_fused_bwd fall away: 4 instead of 5 GEMM passes and 2
  * instead of 3 exponentials per score and step).  Per score P = exp(x - mref_q) is computed once against a FIXED per-row
- * reference (mref_q = max of x over a strided sample of 256 entities of the shard); the row sums of P accumulate in
+ * reference (mref_q = max of x over a strided sample of 64 entities of the shard); the row sums of P accumulate in
  * registers, o_sum[q,:] = sum_e P[q,e] * table[e,:] in tensor memory.  No online rescaling: bf16 operands and fp32
  * accumulators keep 8 exponent bits, so P is representable for x within [-87, +88] nats of mref -- beyond that the sums
  * read inf, the loss NaN and the job raises FloatingPointError (train.py:343-345).

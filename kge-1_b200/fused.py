@@ -80,6 +80,40 @@ def fused_rowstats(q, table, lab_off, lab_col, loss, label_smoothing, offset, ma
     return rowstat
 
 
+def flash_supported(loss: int, math: int, d: int, label_smoothing: float) -> bool:
+    """KL on the bf16 tiles: forward statistics + query gradient in one table pass (kgeb_fused_flash_fwd)."""
+    return loss == lib.LOSS_KL and math == lib.MATH_BF16 and d % 16 == 0 and d <= 256 and label_smoothing == 0.0
+
+
+def flash_forward(q, table, lab_off, lab_col, shard: Shard):
+    """(rowstat_local [B,4] = (mref, sum exp(x - mref), 0, label dot), o_sum [B,d]) of this shard."""
+    b, d = q.shape
+    rowstat = torch.empty(b, 4, dtype=torch.float32, device=q.device)
+    o_sum = torch.empty(b, d, dtype=torch.float32, device=q.device)
+    n_ent = shard.e_hi - shard.e_lo
+    ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent, lab_col.numel()))
+    lib.call("kgeb_fused_flash_fwd", lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo, shard.e_hi,
+             shard.num_entities, lib.i64(lab_off), lib.i64(lab_col), lab_col.numel(),
+             _mirror_ptr(table, lib.MATH_BF16, b, d), rowstat.data_ptr(), o_sum.data_ptr(), ws.data_ptr(), ws.numel(),
+             lib.stream_ptr(q))
+    return rowstat, o_sum
+
+
+def flash_dq(q, table, lab_off, lab_col, rowstat_local, lse, inv_batch, grad_scale, o_sum, shard: Shard) -> torch.Tensor:
+    """dQ from the flash forward's o_sum (no table pass); summed over the shards."""
+    b, d = q.shape
+    n_ent = shard.e_hi - shard.e_lo
+    dq = torch.empty(b, d, dtype=torch.float32, device=q.device)
+    ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent, lab_col.numel()))
+    lib.call("kgeb_fused_flash_dq", lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo, shard.e_hi,
+             lib.i64(lab_off), lib.i64(lab_col), lab_col.numel(), lib.f32(rowstat_local), lib.f32(lse, "lse"),
+             float(inv_batch), None if grad_scale is None else lib.f32(grad_scale, "grad scale"), lib.f32(o_sum),
+             dq.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream_ptr(q))
+    if shard.distributed:
+        dist.all_reduce(dq, op=dist.ReduceOp.SUM, group=shard.group)
+    return dq
+
+
 def _mirror_ptr(table, math, b, d):
     """bf16 mirror of the table for KGEB_MATH_BF16 (None when the tensor tiles will not be used)."""
     if math != lib.MATH_BF16 or d % 16 != 0 or d > 256:
@@ -135,16 +169,22 @@ class AllEntityLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, table, lab_off, lab_col, loss, label_smoothing, offset, batch_size, math, shard):
         qd, td = q.detach().contiguous(), table.detach()
-        rowstat = combine_rowstats(
-            fused_rowstats(qd, td, lab_off, lab_col, loss, label_smoothing, offset, math, shard), loss, shard)
+        flash = flash_supported(loss, math, qd.shape[1], label_smoothing) and qd.shape[0] > 0
+        if flash:
+            local, o_sum = flash_forward(qd, td, lab_off, lab_col, shard)
+            rowstat = combine_rowstats(local, loss, shard)
+        else:
+            local = o_sum = None
+            rowstat = combine_rowstats(
+                fused_rowstats(qd, td, lab_off, lab_col, loss, label_smoothing, offset, math, shard), loss, shard)
         per_row, lse = rows_loss(rowstat, lab_off, loss, label_smoothing, shard.num_entities)
-        ctx.save_for_backward(qd, td, lab_off, lab_col, lse)
+        ctx.save_for_backward(qd, td, lab_off, lab_col, lse, local, o_sum)
         ctx.cfg = (loss, label_smoothing, offset, 1.0 / batch_size, math, shard)
         return per_row / batch_size
 
     @staticmethod
     def backward(ctx, g):
-        qd, td, lab_off, lab_col, lse = ctx.saved_tensors
+        qd, td, lab_off, lab_col, lse, local, o_sum = ctx.saved_tensors
         loss, ls, offset, inv_batch, math, shard = ctx.cfg
         # a table-sized gradient: written once by the kernels (no zero-fill pass) when this rank scores every row
         whole = shard.e_lo == 0 and shard.e_hi == td.shape[0]
@@ -152,8 +192,14 @@ class AllEntityLoss(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             d_table = torch.empty_like(td) if whole else torch.zeros_like(td)
         gs = g.detach().float().contiguous()  # upstream gradient per row; stays on the device
-        dq = fused_backward(qd, td, lab_off, lab_col, loss, ls, offset, lse, inv_batch, gs, math, shard, d_table,
-                            want_dq=ctx.needs_input_grad[0], overwrite=whole)
+        if local is not None:     # flash forward: dQ needs no table pass, only the table gradient recomputes the scores
+            dq = flash_dq(qd, td, lab_off, lab_col, local, lse, inv_batch, gs, o_sum, shard) if ctx.needs_input_grad[0] else None
+            if d_table is not None:
+                fused_backward(qd, td, lab_off, lab_col, loss, ls, offset, lse, inv_batch, gs, math, shard, d_table,
+                               want_dq=False, overwrite=whole)
+        else:
+            dq = fused_backward(qd, td, lab_off, lab_col, loss, ls, offset, lse, inv_batch, gs, math, shard, d_table,
+                                want_dq=ctx.needs_input_grad[0], overwrite=whole)
         return dq, d_table, None, None, None, None, None, None, None, None
 
 

@@ -181,6 +181,11 @@ class FusedAllEntityStepper:
         self.loss = self.gflat[g0 + n_e + n_r:].view(())
         self.dp_flat = self.gflat[n_e:]                               # what the replicas exchange
         self.rowstat = torch.empty(rows, 4, **f32)
+        # KL on the bf16 tiles: forward statistics and dQ from ONE table pass (kgeb_fused_flash_fwd / _dq)
+        self.flash = fused.flash_supported(loss_kind, math_mode, self.d, self.ls)
+        if self.flash:
+            self.rowstat_local = torch.empty(rows, 4, **f32)      # this shard's statistics (its mref) before the combine
+            self.o_sum = torch.empty(rows, self.d, **f32)
         self.loss_rows = torch.zeros(rows, **f32)      # per-row loss values (kgeb_loss_from_rowstat rows_out)
         self.report = torch.zeros(2, **f32)            # [total, value of the last non-empty query type] (train.py:747)
         # Data parallelism for graphs too small to shard (SURVEY.md 8e "replicas" row): every rank trains on its own
@@ -260,7 +265,12 @@ class FusedAllEntityStepper:
                          self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.lab_perm.data_ptr(),
                          self.ls, 1.0 / self.global_batch, None, self.g_q.data_ptr(), self.ws2.data_ptr(),
                          self.ws2.numel(), lib.stream_ptr(self.ent))
-        if not self._fused_stats_in_backward():
+        if self.flash:
+            lib.call("kgeb_fused_flash_fwd", self.Q.data_ptr(), self.rows, self.d, ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo,
+                     sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self._mirror_ptr(),
+                     self.rowstat.data_ptr(), self.o_sum.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
+            self.rowstat_local.copy_(self.rowstat)
+        elif not self._fused_stats_in_backward():
             lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
                      ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo, sh.e_hi, self.E, self.lab_off.data_ptr(),
                      self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset, self._mirror_ptr(),
@@ -291,6 +301,33 @@ class FusedAllEntityStepper:
         # stream, so that the chain of small latency-bound kernels that follows dQ on this stream (partial reduce, label
         # scatter, query-transform backward, sorted scatters) runs underneath the dTable tile kernel.
         cur = torch.cuda.current_stream()
+        if self.flash:
+            # the log-sum-exp is known (loss kernel above): the dense table gradient -- the only remaining table pass -- goes
+            # to the second stream; dQ = rescaled o_sum + label rows is a [rows, d] elementwise kernel on this one
+            self.ev_q.record()
+            split = self._split_label_rows()
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.ev_q)
+                if split:
+                    dense = list(common)
+                    dense[11], dense[12] = 0, None          # nnz, lab_perm: label rows are scattered separately
+                    if not self.seq:
+                        self.side.wait_event(self.ev_clear)
+                    lib.call("kgeb_fused_bwd", *dense, None, self.g_ent.data_ptr(), None,
+                             lib.BWD_OVERWRITE_TABLE if self.seq else 0, self.ws3.data_ptr(), self.ws3.numel(),
+                             lib.stream_ptr(self.ent))
+                else:
+                    if not sh.distributed:
+                        self.side.wait_stream(self.side2)     # cleared gradient buffers
+                    lib.call("kgeb_fused_bwd", *common, None, self.g_ent[sh.e_lo:sh.e_hi].data_ptr(), None, 0,
+                             self.ws2.data_ptr(), self.ws2.numel(), lib.stream_ptr(self.ent))
+            lib.call("kgeb_fused_flash_dq", self.Q.data_ptr(), self.rows, self.d, ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo,
+                     sh.e_hi, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.rowstat_local.data_ptr(),
+                     self.lse.data_ptr(), 1.0 / self.global_batch, None, self.o_sum.data_ptr(), self.dQ.data_ptr(),
+                     self.ws.data_ptr(), self.ws.numel(), st)
+            if sh.distributed:
+                self._join_side()
+            return
         if self._split_label_rows():
             # dQ first; the dense-only dTable kernel (nnz = 0: no label part) queues behind it on the second stream
             lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late_stats else None,
@@ -657,6 +694,10 @@ class RowShardedAllEntityStepper:
         self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
         self.loss = torch.zeros((), **f32)
         self.rowstat = torch.empty(rows, 4, **f32)
+        self.flash = fused.flash_supported(loss_kind, math_mode, self.d, self.ls)
+        if self.flash:
+            self.rowstat_local = torch.empty(rows, 4, **f32)
+            self.o_sum = torch.empty(rows, self.d, **f32)
         self.lse = torch.zeros(rows, **f32)
         L = lib.load()
         self.ws = torch.empty(L.kgeb_fused_workspace_bytes(rows, self.d, max(self.n_loc, 1), nz), dtype=torch.uint8, device=dev)
@@ -706,7 +747,13 @@ class RowShardedAllEntityStepper:
         rel = self.rel.detach()
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), self.A.data_ptr(), self.iota.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
-        if not self._late_stats():
+        if self.flash:
+            lib.call("kgeb_fused_flash_fwd", self.Q.data_ptr(), self.rows, self.d, self._ent_loc().data_ptr(), self.e_lo,
+                     self.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
+                     self.mirror.data_ptr(), self.rowstat.data_ptr(), self.o_sum.data_ptr(), self.ws.data_ptr(),
+                     self.ws.numel(), st)
+            self.rowstat_local.copy_(self.rowstat)
+        elif not self._late_stats():
             lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
                      self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.E, self.lab_off.data_ptr(),
                      self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
@@ -729,8 +776,14 @@ class RowShardedAllEntityStepper:
             lib.call("kgeb_fused_bwd", *common, None, self.g_ent.data_ptr(), None,
                      lib.BWD_OVERWRITE_TABLE if self.mirror is not None else 0, self.ws2.data_ptr(), self.ws2.numel(),
                      lib.stream_ptr(self.ent))
-        lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late else None,
-                 0, self.ws.data_ptr(), self.ws.numel(), st)
+        if self.flash:      # dQ partial of this shard from o_sum and the GLOBAL log-sum-exp: no second table pass
+            lib.call("kgeb_fused_flash_dq", self.Q.data_ptr(), self.rows, self.d, self._ent_loc().data_ptr(), self.e_lo,
+                     self.e_hi, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
+                     self.rowstat_local.data_ptr(), self.lse.data_ptr(), 1.0 / self.batch_size, None, self.o_sum.data_ptr(),
+                     self.dQ.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
+        else:
+            lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late else None,
+                     0, self.ws.data_ptr(), self.ws.numel(), st)
         cur.wait_stream(self.side)
 
     def _stage_update(self):

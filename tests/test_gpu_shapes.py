@@ -263,3 +263,34 @@ def test_large_table_captured_step_one_gradient_buffer(kb, loss):
         assert got == pytest.approx(a.avg_loss, rel=2e-5), (loss, step)
         for x, y in ((new.get_s_embedder().weight, ref.get_s_embedder().weight), (new.get_p_embedder().weight, ref.get_p_embedder().weight)):
             assert (x - y).abs().max().item() <= 0.2 * 1e-3, (loss, step, (x - y).abs().max().item())
+
+
+@pytest.mark.parametrize("e,b,scale", [(14541, 4096, 8.0), (14541, 512, 1500.0), (4_600_000, 256, 8.0), (1000, 130, 8.0)])
+def test_flash_kl_forward_and_dq_match_float64(kb, e, b, scale):
+    """kgeb_fused_flash_fwd / _dq (KL, bf16 tiles: log-sum-exp and dQ from one table pass against a sampled per-row
+    reference score) vs float64 on sampled rows, and vs the two-pass bf16 kernels on all rows.  scale = 1500 gives scores
+    with a standard deviation of ~17 nats, the row maximum ~20 nats above the sampled reference and a softmax dominated by
+    a few entities: the fixed-reference exponentials must hold (compared with the two-pass bf16 kernels there: the bf16
+    rounding of the operands alone moves such a sharp softmax by several percent against float64)."""
+    r, d = 50, 128
+    m, q, lab_off, lab_col = _problem(kb, "distmult", e, r, d, b, 3, seed=21, empty_row=False)
+    q = (q * (scale / 8.0)).contiguous()
+    w = m.get_s_embedder().weight.detach()
+    shard = kb.fused.Shard.full(e)
+    local, o_sum = kb.fused.flash_forward(q, w, lab_off, lab_col, shard)
+    rows, lse = kb.fused.rows_loss(local, lab_off, kb.lib.LOSS_KL, 0.0, e)
+    assert torch.isfinite(lse).all() and torch.isfinite(o_sum).all()
+    dq = kb.fused.flash_dq(q, w, lab_off, lab_col, local, lse, 1.0 / b, None, o_sum, shard)
+    sample = [0, 1, b // 2, b - 1]
+    l64, lse64, dq64 = _float64_rows(q, w, lab_off, lab_col, sample, "kl", 0.0, 1.0 / b)
+    assert (lse[sample].double().cpu() - lse64.double()).abs().max().item() <= 2e-3 * max(1.0, scale / 40)
+    if scale <= 8.0:
+        close(rows[sample] / b, l64, 1e-2, "flash row losses vs float64")
+        close(dq[sample], dq64, 1.5e-2, "flash dQ rows vs float64")
+    # the two-pass bf16 kernels (same operand rounding) on all rows
+    st = kb.fused.fused_rowstats(q, w, lab_off, lab_col, kb.lib.LOSS_KL, 0.0, 0.0, kb.lib.MATH_BF16, shard)
+    rows2, lse2 = kb.fused.rows_loss(st, lab_off, kb.lib.LOSS_KL, 0.0, e)
+    dq2 = kb.fused.fused_backward(q, w, lab_off, lab_col, kb.lib.LOSS_KL, 0.0, 0.0, lse2, 1.0 / b, None, kb.lib.MATH_BF16,
+                                  shard, None)
+    assert (lse - lse2).abs().max().item() <= 2e-3 * max(1.0, scale / 40)
+    close(dq, dq2, 1.5e-2, "flash dQ vs two-pass bf16 dQ (all rows)")
