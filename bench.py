@@ -332,7 +332,8 @@ def our_arm(args):
         n_ent = E
     else:
         sh = kb.fused.Shard.of_rank(E, rank, world, dist.group.WORLD)
-        st = kb.trainer.RowShardedAllEntityStepper(model, opt, 2 * B, 2 * B, kb.lib.LOSS_KL, B, sh, math_mode=math_mode)
+        st = kb.trainer.RowShardedAllEntityStepper(model, opt, 2 * B, 2 * B, kb.lib.LOSS_KL, B, sh, math_mode=math_mode,
+                                                   peer_memory=not os.environ.get("KGEB_NO_PEER"))
         n_ent = sh.e_hi - sh.e_lo
 
     # ---------------- value: batches resident in HBM, CUDA events ---------------------------------------------------
@@ -357,6 +358,8 @@ def our_arm(args):
         total_ms = t.item()
     value = B * steps / (total_ms / 1e3)
     final_loss = float(st.loss.item())
+    if hasattr(st, "check_peer"):
+        st.check_peer()          # no peer-memory barrier timed out
 
     # ---------------- e2e: host batches, H2D + step + loss read-back inside the timed region ------------------------
     e2e_s = 0.0
@@ -401,7 +404,10 @@ def our_arm(args):
         "config": config(world, "bf16"),
         "details": {"math": "bf16 tensor tiles (tcgen05, bf16 mirror of the table), fp32 accumulate, fp32 master tables "
                             "and optimizer", "cuda_graph": True, "final_loss": final_loss,
-                    "stepper": type(st).__name__ + (" inside the reference's TrainingJob1vsAll" if use_ref else "")},
+                    "stepper": type(st).__name__ + (" inside the reference's TrainingJob1vsAll" if use_ref else ""),
+                    "exchange": (None if world == 1 else ("one-shot all-reduce kernels over NVLink peer memory inside the "
+                                 "step's CUDA graph (kgeb_p2p_allreduce)" if getattr(st, "px", None) is not None else
+                                 "NCCL all-reduces between four CUDA graphs"))},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": int(batches[0].numel() * 8),
                 "d2h_bytes_per_step": 8,

@@ -340,6 +340,15 @@ int64_t kgeb_rank_metrics_workspace_bytes(void);
 int kgeb_rank_metrics(const float* hist, int64_t num_entities, const int32_t* hits_at_k, int num_k, double* out,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* One-shot all-reduce of a small fp32 buffer over peer-mapped (symmetric) memory, as a plain kernel that sits in the same
+ * CUDA graph as the compute around it: the three O(batch * d) exchanges of the row-sharded all-entity step (SURVEY.md 8e:
+ * query-side rows, row statistics, dQ).  peer_bufs[k] = rank k's partial (this rank's own partial is peer_bufs[rank]);
+ * out (local) = reduction over the ranks in rank order (bit-identical everywhere).  mode 0: sum; mode 1: every 4 floats
+ * are a row statistic (max, sum-exp relative to max, sum x, label dot) combined as log-sum-exp partials.  epoch = two
+ * device words [barrier epoch, block ticket], zero-initialised, shared by all collectives of a stepper.  A buffer may be
+ * rewritten after the NEXT collective on the same epoch counter has completed. */
+int kgeb_p2p_allreduce(const void* const* peer_pads, const void* const* peer_bufs, int rank, int world, uint32_t* epoch,
+                       uint32_t* timeout_flag, int64_t numel, int mode, float* out, void* stream);
 /* ---- 8e (replicas row): data-parallel gradient exchange fused with the Adagrad update over NVLink peer memory.
  * All pointer arrays are HOST arrays of `world` device pointers, entry k = rank k's buffer mapped into this process
  * (torch symmetric memory / cuMem VMM + IPC).  Replaces  all-reduce(grad) ; torch.optim.Adagrad.step  (train.py:375)

@@ -188,6 +188,56 @@ p2p_apply_kernel(PeerPtrs pads, const float* __restrict__ stage, int rank, int w
   }
 }
 
+// One-shot all-reduce of a small buffer over peer memory (the O(batch * d) exchanges of the row-sharded training step:
+// query-side rows, row statistics, dQ -- 1 MB each at the Wikidata5M bench shape).  Every rank has written its partial
+// into ITS symmetric buffer; after the barrier each rank reads all partials (P2P loads) and reduces them in rank order,
+// so all ranks hold bit-identical results.  A plain kernel: it sits in the same CUDA graph as the compute around it (NCCL
+// calls between separately captured graphs cost ~10x the transfer time in launch gaps at this size).
+//   mode 0: sum.   mode 1: each float4 is a row statistic (max m, sum l relative to m, sum x, label dot): the combined
+//   row is (M = max_k m_k, sum_k l_k exp(m_k - M), sum_k x_k, sum_k d_k) -- log-sum-exp partials of entity shards.
+// The barrier epoch is a device counter the last block advances; buffers may be reused by the NEXT BUT ONE collective
+// (a rank enters collective c + 1 only after its own reads of collective c finished, and nobody passes the barrier of
+// c + 1 before every rank entered it).
+__global__ void __launch_bounds__(256)
+p2p_allreduce_kernel(PeerPtrs pads, PeerPtrs bufs, int rank, int world, uint32_t* epoch, uint32_t* ticket,
+                     uint32_t* timeout_flag, int64_t n4, int mode, float* __restrict__ out) {
+  const bool ok = grid_peer_barrier(pads, rank, world, *epoch + 1u, timeout_flag);
+  if (ok) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 acc;
+      if (mode == 0) {
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < world; ++k) {
+          const float4 v = reinterpret_cast<const float4*>(bufs.p[k])[i];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      } else {
+        float4 v[kMaxWorld];
+        float m = -INFINITY;
+        for (int k = 0; k < world; ++k) {
+          v[k] = reinterpret_cast<const float4*>(bufs.p[k])[i];
+          m = fmaxf(m, v[k].x);
+        }
+        acc = make_float4(m, 0.f, 0.f, 0.f);
+        for (int k = 0; k < world; ++k) {
+          acc.y += v[k].x == -INFINITY ? 0.f : v[k].y * __expf(v[k].x - m);
+          acc.z += v[k].z;
+          acc.w += v[k].w;
+        }
+      }
+      reinterpret_cast<float4*>(out)[i] = acc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0;
+      if (ok) *epoch = *epoch + 1;
+    }
+  }
+}
+
 static int fill_ptrs(PeerPtrs& pp, const void* const* host_ptrs, int world) {
   for (int k = 0; k < kMaxWorld; ++k) pp.p[k] = k < world ? const_cast<void*>(host_ptrs[k]) : nullptr;
   return 0;
@@ -224,6 +274,28 @@ int kgeb_p2p_exchange(const void* const* peer_pads, const void* const* peer_flat
   p2p_exchange_kernel<<<grid, 256, 0, as_stream(stream)>>>(pads, flat, stage, rank, world, ctr, timeout_flag, t0, t1,
                                                           numel0 + numel1, loss_out, clr, eps);
   KGEB_LAUNCH_CHECK("p2p_exchange");
+  return KGEB_OK;
+}
+
+int kgeb_p2p_allreduce(const void* const* peer_pads, const void* const* peer_bufs, int rank, int world, uint32_t* epoch,
+                       uint32_t* timeout_flag, int64_t numel, int mode, float* out, void* stream) {
+  KGEB_REQUIRE(peer_pads && peer_bufs && epoch && timeout_flag && out && numel >= 0 && world >= 1 && world <= kMaxWorld &&
+                   rank >= 0 && rank < world && (mode == 0 || mode == 1),
+               "p2p_allreduce: bad arguments");
+  KGEB_REQUIRE(numel % 4 == 0, "p2p_allreduce: the element count must be a multiple of 4");
+  PeerPtrs pads, bufs;
+  fill_ptrs(pads, peer_pads, world);
+  fill_ptrs(bufs, peer_bufs, world);
+  uintptr_t bits = reinterpret_cast<uintptr_t>(out);
+  for (int k = 0; k < world; ++k) bits |= reinterpret_cast<uintptr_t>(bufs.p[k]);
+  KGEB_REQUIRE((bits & 15) == 0, "p2p_allreduce: pointers must be 16-byte aligned");
+  const int64_t n4 = numel / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  const int grid = (int)(blocks > (int64_t)kNumSMs * 2 ? (int64_t)kNumSMs * 2 : blocks);
+  p2p_allreduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(pads, bufs, rank, world, epoch, epoch + 1, timeout_flag, n4,
+                                                            mode, out);
+  KGEB_LAUNCH_CHECK("p2p_allreduce");
   return KGEB_OK;
 }
 

@@ -80,6 +80,9 @@ struct Params {
   float* stat_partial;     // STATS: [chunks][4 column parts][B][2] = (sum softplus(x+off), sum (x+off)) over valid entities
   int overwrite;           // !RES_IS_Q: the accumulator is STORED into dTable (plain TMA store) instead of added to it
   const float* mref;       // FLASH: [B] reference score per row (natural units); P = exp(x - mref)
+  int a_tmem;              // v2: the resident operand is copied to tensor memory once per job (MMA1 with A in TMEM)
+  const float* colk;       // !RES_IS_Q, KL: [colk_n] exponent offsets (log(rs_q) - lse_q) * log2(e) per streamed (query) row,
+  int colk_n;              //   padded with zeros to a multiple of 64; staged in shared memory by the v2 kernel (0 = unused)
 };
 
 // Per-row state of an epilogue thread over one job (one resident row = one TMEM lane).
@@ -95,7 +98,7 @@ struct EpiRow {
 // S values of 32 consecutive tile columns (first one = streamed row `qbase`) of this thread's resident row -> G (or P).
 template <bool RES_IS_Q, int LOSS, bool HAS_RS, bool STATS, bool FLASH>
 __device__ __forceinline__ void epi_math(float (&v)[COLS_PER_WARP], const Params& p, EpiRow& row, const int64_t qbase,
-                                         const int lane) {
+                                         const int lane, const float* kc_s = nullptr) {
   constexpr float kLog2e = 1.4426950408889634f;
   const float off2 = -p.offset * kLog2e;   // ex2(fma(x, -log2e, off2)) = exp(-(x + offset))
   // STATS: entity columns beyond the table end were zero-filled, their score is exactly 0: count them here
@@ -107,14 +110,24 @@ __device__ __forceinline__ void epi_math(float (&v)[COLS_PER_WARP], const Params
   float col_k = 0.f, col_rs = row.my_rs;
   if (FLASH) {
     col_k = row.fl_m2;
-  } else if (!RES_IS_Q) {
+  } else if (!RES_IS_Q && !(LOSS == KGEB_LOSS_KL && kc_s != nullptr)) {
     const int64_t q = min(qbase + lane, p.B - 1);
     col_rs = HAS_RS ? p.inv_batch * __ldg(p.row_scale + q) : p.inv_batch;
     if (LOSS == KGEB_LOSS_KL) col_k = (__logf(col_rs) - __ldg(p.lse + q)) * kLog2e;
   } else if (LOSS == KGEB_LOSS_KL) {
     col_k = (__logf(row.my_rs) - row.my_lse) * kLog2e;   // rows beyond B: log(0) = -inf -> G = 0
   }
-  if (LOSS == KGEB_LOSS_KL) {
+  if (LOSS == KGEB_LOSS_KL && !RES_IS_Q && kc_s != nullptr) {
+    // per-column exponent offsets from shared memory (broadcast 128-bit loads: 8 per 32 columns instead of 32 shuffles)
+#pragma unroll
+    for (int c4 = 0; c4 < COLS_PER_WARP; c4 += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(kc_s + qbase + c4);
+      v[c4] = ex2_ftz(fmaf(v[c4], kLog2e, k4.x));
+      v[c4 + 1] = ex2_ftz(fmaf(v[c4 + 1], kLog2e, k4.y));
+      v[c4 + 2] = ex2_ftz(fmaf(v[c4 + 2], kLog2e, k4.z));
+      v[c4 + 3] = ex2_ftz(fmaf(v[c4 + 3], kLog2e, k4.w));
+    }
+  } else if (LOSS == KGEB_LOSS_KL) {
 #pragma unroll
     for (int c = 0; c < COLS_PER_WARP; ++c) {
       const float kc = RES_IS_Q ? col_k : __shfl_sync(0xffffffffu, col_k, c);
@@ -581,10 +594,22 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
   uint64_t* buf_free = g_full + NG;             // [NG] MMA2 read G -> MMA1 may overwrite the buffer
   uint64_t* o_full = buf_free + NG;             // job accumulator complete -> epilogue
   uint64_t* o_empty = o_full + 1;               // epilogue flushed -> MMA2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  uint64_t* a_full = o_empty + 1;               // a_tmem: epilogue copied the resident block to tensor memory -> MMA1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+  // !RES_IS_Q, KL: the per-query exponent offsets of ALL streamed rows (the same for every job), 16-byte aligned
+  float* kc_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  const float* kc_s = (!RES_IS_Q && LOSS == KGEB_LOSS_KL && p.colk_n > 0) ? kc_smem : nullptr;
+  if (kc_s)
+    for (int i = threadIdx.x; i < p.colk_n; i += NUM_THREADS) kc_smem[i] = p.colk[i];
   constexpr int TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0;                 // NG S buffers of 64 columns; G aliases the first 32 columns of each
   constexpr uint32_t O_COL = NG * STR_ROWS;     // OUT accumulator: d <= 256 columns behind them
+  // a_tmem (d <= 128): the resident operand as MMA1's A in TENSOR memory, 64 columns at the top.  MMA1 in the SS form reads
+  // 4 KB of A + 2 KB of B from shared memory per K step (48 clk at 128 B/clk against a 32 clk tensor floor: ncu shows the
+  // tensor pipe 66 % busy = 640 clk of MMA per ~975 clk tile); with A in tensor memory only B streams from shared memory.
+  constexpr uint32_t A_COL = 448;
+  const bool a_tmem = p.a_tmem != 0;
+  const int a_groups = a_tmem ? (p.d + 31) / 32 : 0;      // epilogue groups that copy 16 columns (= 32 bf16) each
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_res);
@@ -596,7 +621,9 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
       mbar_init(&str_empty[s], 1);
     }
     mbar_init(res_full, 1);
-    mbar_init(res_empty, 1);
+    // a_tmem: the copying epilogue warps, not MMA1, are the readers of the resident block in shared memory
+    mbar_init(res_empty, a_tmem ? 4 * a_groups : 1);
+    mbar_init(a_full, a_tmem ? 4 * a_groups : 1);
     for (int b = 0; b < NG; ++b) {
       mbar_init(&s_full[b], 1);
       mbar_init(&g_full[b], 4);                 // the four warps (lane quadrants) of the group
@@ -648,26 +675,36 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
       for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         const int64_t ch = job / p.n_res_blocks;
         const int64_t u0 = ch * p.tiles_per_chunk, u1 = min(p.n_str_tiles, u0 + p.tiles_per_chunk);
-        mbar_wait(res_full, rphase);
+        mbar_wait(a_tmem ? a_full : res_full, rphase);
         rphase ^= 1;
         for (int64_t u = u0; u < u1; ++u) {
           mbar_wait(&str_full[slot], ph);
           mbar_wait(&buf_free[sbuf], ((bph >> sbuf) & 1u) ^ 1u);   // MMA2 of tile u - NG has consumed this buffer's G
           tc_fence_after();
           const uint32_t acc = tbase + S_COL + (uint32_t)(sbuf * STR_ROWS);
-          for (int k = 0; k < KS; ++k) {
-            const uint64_t ra = dbase + (uint64_t)((res0 + (uint32_t)k * RES_SLAB) >> 4);
-            const uint64_t sa = dbase + (uint64_t)((str0 + (uint32_t)(slot * KS + k) * STR_SLAB) >> 4);
+          if (a_tmem) {
+            for (int k = 0; k < KS; ++k) {
+              const uint64_t sa = dbase + (uint64_t)((str0 + (uint32_t)(slot * KS + k) * STR_SLAB) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk)   // +32 B (= 2 in descriptor units) per K step
-              umma<BF16>(acc, ra + 2 * kk, sa + 2 * kk, idesc1, (k | kk) != 0);
+              for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk)   // A: 8 columns (16 bf16) per K step; B: +32 B per K step
+                umma_ts_bf16(acc, tbase + A_COL + (uint32_t)((k * SLAB_K + kk * UMMA_K) / 2), sa + 2 * kk, idesc1,
+                             (k | kk) != 0);
+            }
+          } else {
+            for (int k = 0; k < KS; ++k) {
+              const uint64_t ra = dbase + (uint64_t)((res0 + (uint32_t)k * RES_SLAB) >> 4);
+              const uint64_t sa = dbase + (uint64_t)((str0 + (uint32_t)(slot * KS + k) * STR_SLAB) >> 4);
+#pragma unroll
+              for (int kk = 0; kk < SLAB_K / UMMA_K; ++kk)   // +32 B (= 2 in descriptor units) per K step
+                umma<BF16>(acc, ra + 2 * kk, sa + 2 * kk, idesc1, (k | kk) != 0);
+            }
           }
           umma_commit(&s_full[sbuf]);
           bph ^= 1u << sbuf;
           if (++sbuf == NG) sbuf = 0;
           if (++slot == NSTR) { slot = 0; ph ^= 1; }
         }
-        umma_commit(res_empty);   // all MMA1 of the job issued before this commit have read the resident block
+        if (!a_tmem) umma_commit(res_empty);   // all MMA1 of the job issued before this commit have read the resident block
       }
     }
   } else if (warp == 3) {
@@ -714,7 +751,7 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
     const int trow = quad * 32 + lane;                     // resident row (TMEM lane) of this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t buf_addr = lane_addr + S_COL + (uint32_t)(part * STR_ROWS);
-    uint32_t sph = 0, ophase = 0;
+    uint32_t sph = 0, ophase = 0, aphase = 0;
     int64_t gunit = 0;                                     // global tile counter (buffers rotate across jobs too)
     for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int64_t rb = job % p.n_res_blocks, ch = job / p.n_res_blocks;
@@ -727,6 +764,27 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
         er.my_rs = p.inv_batch * (HAS_RS ? p.row_scale[res_row] : 1.f);
         if (LOSS == KGEB_LOSS_KL) er.my_lse = p.lse[res_row];
       }
+      if (a_tmem && part < a_groups) {
+        // resident block: shared memory (TMA, 128-byte swizzle) -> tensor memory columns [A_COL + 16 part, + 16) of this
+        // thread's lane: 32 bf16 = bytes [64 part, 64 part + 64) of the row = four 16-byte chunks of slab part / 2.
+        // (Every MMA of the previous job has completed: this warp passed o_full.)
+        mbar_wait(res_full, aphase);
+        const uint32_t rowa = smem_s + (uint32_t)((part >> 1) * RES_SLAB + trow * 128);
+        uint32_t w[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int ck = (part & 1) * 4 + c;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w[4 * c]), "=r"(w[4 * c + 1]), "=r"(w[4 * c + 2]), "=r"(w[4 * c + 3])
+                       : "r"(rowa + (uint32_t)((ck ^ (trow & 7)) << 4)));
+        }
+        tmem_st16(lane_addr + A_COL + (uint32_t)(16 * part), w);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive_warp(a_full);
+        mbar_arrive_warp(res_empty);      // the producer may prefetch the next job's block
+      }
+      aphase ^= 1;
       // first tile of this job that belongs to this group
       int64_t u = u0 + (((int64_t)part - gunit) % NG + NG) % NG;
       for (; u < u1; u += NG) {
@@ -737,7 +795,7 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
           tmem_ld32(buf_addr + (uint32_t)(pass * COLS_PER_WARP), v);
-          epi_math<RES_IS_Q, LOSS, HAS_RS, STATS, FLASH>(v, p, er, u * STR_ROWS + pass * COLS_PER_WARP, lane);
+          epi_math<RES_IS_Q, LOSS, HAS_RS, STATS, FLASH>(v, p, er, u * STR_ROWS + pass * COLS_PER_WARP, lane, kc_s);
           // G of these 32 columns: 16 words of two bf16 -> columns [16 pass, 16 pass + 16) of the same buffer.  All 64 S
           // columns of this warp's rows are in registers / consumed before the first word of pass 1 is written
           // (pass 0 only touches columns [0, 16), which it has loaded itself).
@@ -942,13 +1000,18 @@ static Plan make_plan(bool res_is_q, bool bf16, int64_t B, int d, int64_t n_ent)
     p.chunks = 1;
     p.tiles_per_chunk = p.n_str_tiles > 0 ? p.n_str_tiles : 1;
   }
-  const size_t fixed = 1024 + 512;
+  // barriers / tensor-memory slot (512 B) + 1 KiB alignment slack; v2 dTable kernel: + the per-query exponent offsets of
+  // all streamed rows (KL; up to 4096 rows -- larger batches use the shuffle path)
+  const int64_t colk_n = (!res_is_q && use_v2() && bf16 && B <= 4096) ? ((B + 63) / 64) * 64 : 0;
+  p.colk_n = (int)colk_n;
+  const size_t fixed = 1024 + 512 + (size_t)colk_n * 4;
   const size_t g_bytes = (use_v2() && bf16) ? 0 : (size_t)(STR_ROWS / slab_k) * RES_SLAB;   // v2: G lives in tensor memory
   const size_t base = (size_t)p.ks * RES_SLAB + 2 * g_bytes + (res_is_q ? 0 : (size_t)EPQ * STAGE_BYTES);
   int nstr = (int)((SMEM_BUDGET - fixed - base) / ((size_t)p.ks * STR_SLAB));
   if (nstr > MAX_STR) nstr = MAX_STR;
   p.nstr = nstr;
   pl.smem = base + (size_t)nstr * p.ks * STR_SLAB + fixed;
+  p.a_tmem = (use_v2() && bf16 && d <= 128 && !getenv("KGEB_NO_A_TMEM")) ? 1 : 0;
   return pl;
 }
 
@@ -1017,6 +1080,16 @@ static int launch_bwd(const Plan& pl, const CUtensorMap& m_res, const CUtensorMa
 #undef KGEB_BWD_LAUNCH
   KGEB_LAUNCH_CHECK("tc_bwd_kernel");
   return KGEB_OK;
+}
+
+// colk[q] = (log(inv_batch * row_scale[q]) - lse[q]) * log2(e) for q < B, 0 for the padding up to n (KL dTable kernel)
+__global__ void colk_kernel(const float* __restrict__ lse, const float* __restrict__ row_scale, float inv_batch, int64_t B,
+                            int n, float* __restrict__ colk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = 0.f;
+  if (i < B) v = (__logf(inv_batch * (row_scale ? row_scale[i] : 1.f)) - lse[i]) * 1.4426950408889634f;
+  colk[i] = v;
 }
 
 // rowstat[r] = (sum softplus, 0, sum (x+off), label_dot[r]) from the per-(chunk, column part) partials, fixed order
@@ -1281,6 +1354,16 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = dTable;
       pl.p.overwrite = overwrite ? 1 : 0;
+      if (loss == KGEB_LOSS_KL && pl.p.colk_n > 0) {
+        // (label_dot's slot of the workspace is free in a dTable-only call; with dQ in the same call it is used by the
+        // BCE statistics only, never by KL)
+        float* colk = reinterpret_cast<float*>(dq_lab);     // [B * d] floats: room for colk_n <= 4096 + 63
+        colk_kernel<<<(pl.p.colk_n + 255) / 256, 256, 0, st>>>(lse, row_scale, inv_batch, B, pl.p.colk_n, colk);
+        KGEB_LAUNCH_CHECK("colk");
+        pl.p.colk = colk;
+      } else {
+        pl.p.colk_n = 0;
+      }
       CUtensorMap m_out;   // fp32 [n_ent, d], boxes of 32 columns x 128 rows for the reduce-add flush
       if ((rc = make_map(&m_res, tableb, n_ent, d, RES_ROWS, true)) || (rc = make_map(&m_str, Qb, B, d, STR_ROWS, true)) ||
           (rc = make_map(&m_out, dTable, n_ent, d, RES_ROWS, false)))

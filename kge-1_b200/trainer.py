@@ -653,7 +653,10 @@ class RowShardedAllEntityStepper:
 
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  shard: fused.Shard, offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
-                 use_graph: bool = True):
+                 use_graph: bool = True, peer_memory: bool = True):
+        """`peer_memory`: the three exchanges run as one-shot all-reduce KERNELS over torch symmetric memory
+        (kgeb_p2p_allreduce, csrc/p2p.cu) inside ONE CUDA graph with the compute stages; where symmetric memory cannot be
+        set up (or peer_memory=False) they are NCCL all-reduces between four separately captured graphs."""
         if model.get_scorer().kind != lib.DOT:
             raise NotImplementedError("the fused all-entity step serves the DOT scorers")
         if not shard.distributed:
@@ -683,6 +686,14 @@ class RowShardedAllEntityStepper:
         self.loc_ids = torch.zeros(rows, **i64)
         self.A = torch.zeros(rows, self.d, **f32)          # query-side entity rows, assembled by all-reduce
         self.Q, self.dQ = torch.empty(rows, self.d, **f32), torch.empty(rows, self.d, **f32)
+        self.px = None
+        if peer_memory:
+            try:
+                self._setup_peer(rows, dev)
+            except (RuntimeError, ImportError, AttributeError) as exc:      # no symmetric memory on this box / build
+                import sys
+                print(f"[kgeb200] peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+                self.px = None
         self.da, self.dp = torch.empty(rows, self.d, **f32), torch.empty(rows, self.dr, **f32)
         # bf16 tiles: ONE gradient buffer [n_loc + 1, d] that is never cleared -- the tile kernel stores the dense part
         # (KGEB_BWD_OVERWRITE_TABLE), label rows and query-side rows are scattered on top; row n_loc collects the
@@ -714,6 +725,13 @@ class RowShardedAllEntityStepper:
             self._capture()
 
     # -- helpers -------------------------------------------------------------------------------------
+    def _dst(self, which: str) -> torch.Tensor:
+        """Where a producer writes this rank's PARTIAL of an exchanged quantity: the symmetric buffer the peers read
+        (peer-memory mode) or the tensor NCCL reduces in place."""
+        if self.px is not None:
+            return {"A": self.A_part, "stat": self.stat_part, "dQ": self.dQ_part}[which]
+        return {"A": self.A, "stat": self.rowstat, "dQ": self.dQ}[which]
+
     def _ent_loc(self):
         return self.ent.detach()[self.e_lo:self.e_hi]
 
@@ -739,7 +757,7 @@ class RowShardedAllEntityStepper:
             self.g_ent.zero_(); self.g_q.zero_()
         self.g_rel.zero_()
         lib.call("kgeb_gather_rows_shard", self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.d, self.a_idx.data_ptr(),
-                 1, self.rows, self.A.data_ptr(), self.loc_ids.data_ptr(), st)
+                 1, self.rows, self._dst("A").data_ptr(), self.loc_ids.data_ptr(), st)
 
     def _stage_forward(self):
         st = lib.stream_ptr(self.ent)
@@ -750,14 +768,14 @@ class RowShardedAllEntityStepper:
         if self.flash:
             lib.call("kgeb_fused_flash_fwd", self.Q.data_ptr(), self.rows, self.d, self._ent_loc().data_ptr(), self.e_lo,
                      self.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
-                     self.mirror.data_ptr(), self.rowstat.data_ptr(), self.o_sum.data_ptr(), self.ws.data_ptr(),
+                     self.mirror.data_ptr(), self._dst("stat").data_ptr(), self.o_sum.data_ptr(), self.ws.data_ptr(),
                      self.ws.numel(), st)
-            self.rowstat_local.copy_(self.rowstat)
+            self.rowstat_local.copy_(self._dst("stat"))
         elif not self._late_stats():
             lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
                      self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.E, self.lab_off.data_ptr(),
                      self.lab_col.data_ptr(), self.nnz_max, self.ls, self.offset,
-                     None if self.mirror is None else self.mirror.data_ptr(), self.rowstat.data_ptr(),
+                     None if self.mirror is None else self.mirror.data_ptr(), self._dst("stat").data_ptr(),
                      self.ws.data_ptr(), self.ws.numel(), st)
 
     def _stage_backward(self):
@@ -780,10 +798,10 @@ class RowShardedAllEntityStepper:
             lib.call("kgeb_fused_flash_dq", self.Q.data_ptr(), self.rows, self.d, self._ent_loc().data_ptr(), self.e_lo,
                      self.e_hi, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
                      self.rowstat_local.data_ptr(), self.lse.data_ptr(), 1.0 / self.batch_size, None, self.o_sum.data_ptr(),
-                     self.dQ.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
+                     self._dst("dQ").data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
         else:
-            lib.call("kgeb_fused_bwd", *common, self.dQ.data_ptr(), None, self.rowstat.data_ptr() if late else None,
-                     0, self.ws.data_ptr(), self.ws.numel(), st)
+            lib.call("kgeb_fused_bwd", *common, self._dst("dQ").data_ptr(), None,
+                     self._dst("stat").data_ptr() if late else None, 0, self.ws.data_ptr(), self.ws.numel(), st)
         cur.wait_stream(self.side)
 
     def _stage_update(self):
@@ -809,9 +827,55 @@ class RowShardedAllEntityStepper:
                      None if self.one_buffer else self.g_q.data_ptr(), self.n_loc * self.d, self.lr, self.eps, 0.0,
                      None if self.mirror is None else self.mirror.data_ptr(), st)
 
+    def _setup_peer(self, rows: int, dev):
+        """Partials of the three exchanges in ONE symmetric allocation [A_part | dQ_part | rowstat_part] + signal pad."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        n_a, n_s = rows * self.d, rows * 4
+        flat = symm.empty(2 * n_a + n_s, dtype=torch.float32, device=dev)
+        hf = symm.rendezvous(flat, self.shard.group)
+        pad = symm.empty(64, dtype=torch.int32, device=dev)
+        hp = symm.rendezvous(pad, self.shard.group)
+        flat.zero_(); pad.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(self.shard.group)             # nobody signals before every pad is zero
+        ptrs = [int(x) for x in hf.buffer_ptrs]
+        self.px = dict(rank=hf.rank, world=hf.world_size, handles=(hf, hp), flat=flat, pad=pad,
+                       pads=lib.ptr_array([int(x) for x in hp.buffer_ptrs]),
+                       A=lib.ptr_array(ptrs), dQ=lib.ptr_array([x + 4 * n_a for x in ptrs]),
+                       stat=lib.ptr_array([x + 8 * n_a for x in ptrs]),
+                       epoch=torch.zeros(2, dtype=torch.int32, device=dev),
+                       timeout=torch.zeros(1, dtype=torch.int32, device=dev))
+        self.A_part = flat[:n_a].view(rows, self.d)
+        self.dQ_part = flat[n_a:2 * n_a].view(rows, self.d)
+        self.stat_part = flat[2 * n_a:].view(rows, 4)
+
+    def _peer_allreduce(self, which: str, numel: int, mode: int, out: torch.Tensor):
+        x = self.px
+        lib.call("kgeb_p2p_allreduce", x["pads"], x[which], x["rank"], x["world"], x["epoch"].data_ptr(),
+                 x["timeout"].data_ptr(), numel, mode, out.data_ptr(), lib.stream_ptr(self.ent))
+
+    def check_peer(self):
+        """Host check (one sync): no peer-memory barrier ran into its timeout."""
+        if self.px is not None and int(self.px["timeout"].item()) != 0:
+            raise RuntimeError("a peer did not arrive at a peer-memory barrier")
+
     def _exchange(self, which: int):
         import torch.distributed as dist
         grp = self.shard.group
+        if self.px is not None:
+            # producers wrote their partials into the symmetric buffers (A_part / stat_part / dQ_part); results land in the
+            # local tensors the next stage reads
+            if which == 0:
+                self._peer_allreduce("A", self.A.numel(), 0, self.A)
+            elif which == 1:
+                if not self._late_stats():
+                    self._peer_allreduce("stat", self.rowstat.numel(), 1 if self.loss_kind == lib.LOSS_KL else 0, self.rowstat)
+            else:
+                self._peer_allreduce("dQ", self.dQ.numel(), 0, self.dQ)
+                if self._late_stats():
+                    self._peer_allreduce("stat", self.rowstat.numel(), 0, self.rowstat)
+            return
         if which == 0:
             dist.all_reduce(self.A, group=grp)
         elif which == 1:
@@ -841,11 +905,21 @@ class RowShardedAllEntityStepper:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graphs = []
-        for fn in self._stages():
+        if self.px is not None:
+            # compute stages AND exchanges in one graph.  The capture itself launches nothing, but every rank must replay
+            # the same number of collectives: the warm-up above ran exactly one step on every rank.
+            import torch.distributed as dist
+            dist.barrier(self.shard.group)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                fn()
+                self._launch()
             self.graphs.append(g)
+        else:
+            for fn in self._stages():
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                self.graphs.append(g)
         torch.cuda.synchronize()
         with torch.no_grad():
             for dst, src in zip((self.ent, self.rel, self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]), keep):
@@ -866,6 +940,8 @@ class RowShardedAllEntityStepper:
     def step(self) -> torch.Tensor:
         if self.graphs is None:
             self._launch()
+        elif len(self.graphs) == 1:
+            self.graphs[0].replay()
         else:
             for i, g in enumerate(self.graphs):
                 g.replay()
@@ -1050,3 +1126,180 @@ class FusedNegSamplingStepper:
         torch.autograd.graph.increment_version(self.ent)
         torch.autograd.graph.increment_version(self.rel)
         return self.loss if self.px is None else self.px.loss_global
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md 8(e), second row: negative sampling, data-parallel over triples with ROW-SHARDED embedding tables
+# ---------------------------------------------------------------------------------------------
+class RowExchange:
+    """Routing of embedding-row requests to their owners and of row gradients back (all-to-all-v over the process group).
+    Rank g owns the rows [g * per, (g + 1) * per) of a table of `num_rows` rows, per = ceil(num_rows / world).
+    Works on CPU tensors with gloo as well (tests/test_host_logic.py) -- it is index arithmetic plus three collectives."""
+
+    def __init__(self, num_rows: int, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.per = (num_rows + self.world - 1) // self.world
+        self.lo = min(self.rank * self.per, num_rows)
+        self.hi = min(self.lo + self.per, num_rows)
+
+    def _a2a(self, x: torch.Tensor, send: list, recv: list) -> torch.Tensor:
+        import torch.distributed as dist
+        out = torch.empty((sum(recv),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_to_all_single(out, x.contiguous(), output_split_sizes=recv, input_split_sizes=send, group=self.group)
+        return out
+
+    def plan(self, ids: torch.Tensor) -> dict:
+        """ids int64 [n] (duplicates allowed) -> routing plan.  One host sync (the split sizes)."""
+        import torch.distributed as dist
+        owner = torch.div(ids, self.per, rounding_mode="floor")
+        order = torch.sort(owner, stable=True).indices           # requests grouped by owner, original order within one
+        send = torch.bincount(owner, minlength=self.world)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        send_l, recv_l = send.tolist(), recv.tolist()
+        wanted = self._a2a(ids[order], send_l, recv_l) - self.lo     # local row numbers other ranks ask me for
+        return {"order": order, "send": send_l, "recv": recv_l, "wanted": wanted, "n": ids.numel()}
+
+    def fetch(self, plan: dict, gather) -> torch.Tensor:
+        """rows [n, d] of the requested ids; `gather(local_rows int64) -> [m, d]` reads this rank's shard."""
+        back = self._a2a(gather(plan["wanted"]), plan["recv"], plan["send"])
+        rows = torch.empty_like(back)
+        rows[plan["order"]] = back
+        return rows
+
+    def push(self, plan: dict, grad_rows: torch.Tensor):
+        """Row gradients [n, d] (one per requested id) -> (local row numbers, rows) at their owners, ordered by
+        (sender rank, position in the sender's request list): a deterministic order for the owner's segment sums."""
+        return plan["wanted"], self._a2a(grad_rows[plan["order"]], plan["send"], plan["recv"])
+
+
+class ShardedNegSamplingStepper:
+    """Negative-sampling training step (train.py:823-999, implementation "triple", slots S and O) data-parallel over the
+    triples of a batch with the ENTITY TABLE SHARDED BY ROW over the ranks (second row):
+
+        every rank: its share of the batch -> ids of all rows it needs (positives' s / o, negatives of both slots)
+        all-to-all-v   ids to the row owners, rows back                                  (RowExchange.fetch)
+        local          query vectors -> pair scores -> loss -> pair backward on the fetched rows (the kernels of
+                       FusedNegSamplingStepper, the fetched rows being the "table")
+        all-to-all-v   one gradient row per requested row back to its owner               (RowExchange.push)
+        owner          sorted, deterministic segment sum into its rows' gradient + Adagrad on its rows + state
+        relation table replicated: its (small) gradient and the loss are all-reduced, every rank applies the same update
+
+    The model object keeps a full-size table whose foreign rows go stale; sync_tables() gathers the owners' rows.
+    Eager (the all-to-all sizes change per batch); the single-GPU step stays FusedNegSamplingStepper."""
+
+    def __init__(self, model: KgeModel, optimizer, batch_size: int, num_neg_s: int, num_neg_o: int, loss_kind: int,
+                 group=None, offset: float = 0.0):
+        import torch.distributed as dist
+        _require_plain_model(model, "ShardedNegSamplingStepper")
+        self.model, self.opt, self.group = model, optimizer, group
+        self.B, self.N = batch_size, {0: int(num_neg_s), 2: int(num_neg_o)}
+        self.loss_kind, self.offset = loss_kind, float(offset)
+        self.kind = model.get_scorer().kind
+        self.ent, self.rel = model.get_s_embedder().weight, model.get_p_embedder().weight
+        self.E, self.d = self.ent.shape
+        self.dr = self.rel.shape[1]
+        pg = optimizer.param_groups[0]
+        if pg.get("lr_decay", 0.0) != 0.0 or pg.get("weight_decay", 0.0) != 0.0:
+            raise NotImplementedError("lr_decay / weight_decay are not part of this step")
+        self.lr, self.eps = float(pg["lr"]), float(pg["eps"])
+        self.ex = RowExchange(self.E, group)
+        self.world = self.ex.world
+        self.global_batch = batch_size * self.world
+        dev = self.ent.device
+        self.n_loc = self.ex.hi - self.ex.lo
+        self.g_loc = torch.zeros(max(self.n_loc, 1), self.d, dtype=torch.float32, device=dev)
+        self.g_rel = torch.zeros_like(self.rel)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.slots = [s for s in (0, 2) if self.N[s] > 0]
+
+    def _ws(self, n: int) -> torch.Tensor:
+        return ops._workspace(self.ent.device, lib.load().kgeb_scatter_workspace_bytes(max(n, 1), max(self.d, self.dr)))
+
+    def step(self, triples: torch.Tensor, negative_samples) -> torch.Tensor:
+        """triples [B,3] and negative_samples (list per slot S, P, O of [B, N_slot]) of THIS rank's share of the batch."""
+        import torch.distributed as dist
+        dev, B, d = self.ent.device, self.B, self.d
+        st = lib.stream_ptr(self.ent)
+        model_id = lib.MODELS[self.model.model]
+        ent, rel = self.ent.detach(), self.rel.detach()
+        t = triples.to(dev).long()
+        s_idx, p_idx, o_idx = t[:, 0].contiguous(), t[:, 1].contiguous(), t[:, 2].contiguous()
+        negs = {slot: negative_samples[slot].to(dev).long().contiguous() for slot in self.slots}
+        # requested rows: [s (B) | o (B) | negatives of slot S (B*N_S) | negatives of slot O (B*N_O)]
+        parts, base = [s_idx, o_idx], {}
+        off = 2 * B
+        for slot in self.slots:
+            base[slot] = off
+            parts.append(negs[slot].view(-1))
+            off += B * self.N[slot]
+        ids = torch.cat(parts)
+        plan = self.ex.plan(ids)
+        loc = ent[self.ex.lo:self.ex.hi]
+        rows = self.ex.fetch(plan, lambda w: ops.gather_rows(loc, w) if w.numel() else loc.new_zeros(0, d))
+        g_rows = torch.zeros_like(rows)                    # gradient of every fetched row (each is referenced by position)
+        self.g_rel.zero_()
+        ar = torch.arange(B, dtype=torch.int64, device=dev)
+        slot_loss = []
+        for slot in self.slots:
+            m = 1 + self.N[slot]
+            # slot O: query (s,p) against [o | negatives]; slot S: query (p,o) against [s | negatives]
+            combine, a_pos, tgt_pos = (lib.SP_, ar, ar + B) if slot == 2 else (lib._PO, ar + B, ar)
+            Q = torch.empty(B, d, dtype=torch.float32, device=dev)
+            lib.call("kgeb_query_build", model_id, combine, None, rows.data_ptr(), a_pos.data_ptr(), rel.data_ptr(),
+                     p_idx.data_ptr(), 1, B, d, Q.data_ptr(), st)
+            cand = torch.cat((tgt_pos[:, None], base[slot] + torch.arange(B * self.N[slot], device=dev).view(B, -1)), 1).contiguous()
+            scores = torch.empty(B, m, dtype=torch.float32, device=dev)
+            G, lrows = torch.empty_like(scores), torch.empty(B, dtype=torch.float32, device=dev)
+            lib.call("kgeb_pairs_score", self.kind, Q.data_ptr(), rows.data_ptr(), cand.data_ptr(), 1, B, m, d,
+                     scores.data_ptr(), st)
+            lib.call("kgeb_ns_loss", self.loss_kind, scores.data_ptr(), B, m, self.offset, 1.0 / self.global_batch,
+                     G.data_ptr(), lrows.data_ptr(), st)
+            dQ, dC = torch.empty_like(Q), torch.empty(B * m, d, dtype=torch.float32, device=dev)
+            lib.call("kgeb_pairs_bwd", self.kind, Q.data_ptr(), rows.data_ptr(), cand.data_ptr(), 1, B, m, d, G.data_ptr(),
+                     scores.data_ptr(), dQ.data_ptr(), dC.data_ptr(), st)
+            da, dp = torch.empty_like(Q), torch.empty(B, self.dr, dtype=torch.float32, device=dev)
+            lib.call("kgeb_query_bwd", model_id, combine, None, rows.data_ptr(), a_pos.data_ptr(), rel.data_ptr(),
+                     p_idx.data_ptr(), 1, B, d, dQ.data_ptr(), da.data_ptr(), dp.data_ptr(), st)
+            g_rows.index_add_(0, cand.view(-1), dC)          # positions are distinct within a slot: a plain placement
+            g_rows.index_add_(0, a_pos, da)
+            lib.call("kgeb_scatter_add_rows", p_idx.data_ptr(), 1, dp.data_ptr(), B, self.dr, self.g_rel.data_ptr(),
+                     self.rel.shape[0], self._ws(B).data_ptr(), self._ws(B).numel(), st)
+            slot_loss.append(lrows.sum())
+        # gradient rows to their owners; the owners' deterministic segment sums + update of the local rows
+        wanted, recv = self.ex.push(plan, g_rows)
+        self.g_loc.zero_()
+        if wanted.numel() and self.n_loc > 0:
+            ws = self._ws(wanted.numel())
+            lib.call("kgeb_scatter_add_rows", wanted.contiguous().data_ptr(), 1, recv.data_ptr(), wanted.numel(), d,
+                     self.g_loc.data_ptr(), self.n_loc, ws.data_ptr(), ws.numel(), st)
+        flat = torch.cat((self.g_rel.view(-1), torch.stack(slot_loss).sum().view(1)))
+        dist.all_reduce(flat, group=self.group)
+        self.g_rel.copy_(flat[:-1].view_as(self.g_rel))
+        self.loss.copy_(flat[-1])
+        s_ent, s_rel = self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]
+        if self.n_loc > 0:
+            lib.call("kgeb_adagrad_dense", loc.data_ptr(), s_ent[self.ex.lo:self.ex.hi].data_ptr(), self.g_loc.data_ptr(), None,
+                     self.n_loc * d, self.lr, self.eps, 0.0, None, st)
+        lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None, rel.numel(), self.lr,
+                 self.eps, 0.0, None, st)
+        for stt in (self.opt.state[self.ent], self.opt.state[self.rel]):
+            stt["step"] += 1
+        torch.autograd.graph.increment_version(self.ent)
+        torch.autograd.graph.increment_version(self.rel)
+        return self.loss
+
+    def sync_tables(self):
+        """Every owner broadcasts its rows of the entity table and of the Adagrad state (evaluation, checkpoints)."""
+        import torch.distributed as dist
+        ranks = dist.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
+        with torch.no_grad():
+            for r in range(self.world):
+                lo = min(r * self.ex.per, self.E)
+                hi = min(lo + self.ex.per, self.E)
+                if hi > lo:
+                    dist.broadcast(self.ent.data[lo:hi], src=ranks[r], group=self.group)
+                    dist.broadcast(self.opt.state[self.ent]["sum"][lo:hi], src=ranks[r], group=self.group)
+        torch.autograd.graph.increment_version(self.ent)

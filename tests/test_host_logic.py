@@ -420,3 +420,47 @@ def test_training_job_bodies_host_logic_against_reference_golden(golden, monkeyp
             np.testing.assert_allclose(m.get_p_embedder().weight.grad.numpy(), g[pre + ".grad_rel"], rtol=0, atol=1e-7, err_msg=tag)
             np.testing.assert_allclose(m.get_s_embedder().weight.detach().numpy(), g[pre + ".ent"], rtol=0, atol=1e-6, err_msg=tag)
             np.testing.assert_allclose(m.get_p_embedder().weight.detach().numpy(), g[pre + ".rel"], rtol=0, atol=1e-6, err_msg=tag)
+
+
+def _row_exchange_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        e, d = 37, 6
+        gen = torch.Generator().manual_seed(5)
+        table = torch.randn(e, d, generator=gen)                      # the same full table on every rank (the oracle)
+        ex = kb.trainer.RowExchange(e, dist.group.WORLD)
+        shard = table[ex.lo:ex.hi].clone()
+        g2 = torch.Generator().manual_seed(100 + rank)
+        ids = torch.randint(0, e, (23 + 5 * rank,), generator=g2)
+        ids[:4] = 0                                                   # duplicates, rows of the first owner
+        ids[4] = e - 1                                                # the last row (short last shard)
+        plan = ex.plan(ids)
+        rows = ex.fetch(plan, lambda w: shard[w])
+        assert torch.equal(rows, table[ids]), "fetched rows"
+        # gradient rows back to the owners: what arrives, summed per local row, equals index_add over ALL ranks' requests
+        grads = torch.randn(ids.numel(), d, generator=g2)
+        wanted, recv = ex.push(plan, grads)
+        mine = torch.zeros(ex.hi - ex.lo, d).index_add_(0, wanted, recv)
+        full = torch.zeros(e, d).index_add_(0, ids, grads)
+        dist.all_reduce(full)
+        torch.testing.assert_close(mine, full[ex.lo:ex.hi], rtol=1e-6, atol=1e-6)
+        out.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        out.put((rank, repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_exchange_routes_requests_and_gradients_over_gloo_world2():
+    """SURVEY.md 8e second row (negative sampling with sharded rows): RowExchange.plan / fetch / push -- requested rows come
+    back in request order, gradient rows reach their owners; world_size-2 gloo."""
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_row_exchange_worker, args=(r, 2, 29633, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get() for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
