@@ -222,11 +222,12 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
     if getattr(st, "flash", False):
         # forward statistics and dQ come out of ONE table pass (kgeb_fused_flash_fwd): two GEMMs executed, both algorithmic
         o_sum = torch.empty(rows, d, device=dev)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
 
         def flash():
             L.call("kgeb_fused_flash_fwd", st.Q.data_ptr(), rows, d, table.data_ptr(), e_lo, e_hi, st.E, off0.data_ptr(),
-                   st.lab_col.data_ptr(), 0, mp, rowstat.data_ptr(), o_sum.data_ptr(), ws.data_ptr(), ws.numel(),
-                   L.stream_ptr(table))
+                   st.lab_col.data_ptr(), 0, mp, rowstat.data_ptr(), o_sum.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                   ws.numel(), L.stream_ptr(table))
 
         dt = [v for k, v in cases.items() if "dTable" in k][0]
         cases = {"tc_bwd_kernel<flash> (kgeb_fused_flash_fwd: scores + log-sum-exp + o_sum for dQ, one pass)":
@@ -404,6 +405,7 @@ def our_arm(args):
         "config": config(world, "bf16"),
         "details": {"math": "bf16 tensor tiles (tcgen05, bf16 mirror of the table), fp32 accumulate, fp32 master tables "
                             "and optimizer", "cuda_graph": True, "final_loss": final_loss,
+                    "flash_fallbacks": getattr(st, "flash_fallbacks", None),
                     "stepper": type(st).__name__ + (" inside the reference's TrainingJob1vsAll" if use_ref else ""),
                     "exchange": (None if world == 1 else ("one-shot all-reduce kernels over NVLink peer memory inside the "
                                  "step's CUDA graph (kgeb_p2p_allreduce)" if getattr(st, "px", None) is not None else

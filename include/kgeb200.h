@@ -170,18 +170,21 @@ int kgeb_loss_from_rowstat(int loss, const float* rowstat, const int64_t* lab_of
 /* KL on the bf16 tiles with the forward statistics and the query gradient in ONE pass over the table (the forward kernel of
  * kgeb_fused_fwd and the score recomputation of the dQ half of kgeb_fused_bwd fall away: 4 instead of 5 GEMM passes and 2
  * instead of 3 exponentials per score and step).  Per score P = exp(x - mref_q) is computed once against a FIXED per-row
- * reference (mref_q = max of x over a strided sample of 64 entities of the shard); the row sums of P accumulate in
+ * reference (mref_q = max of x over a strided sample of 64 entities of the shard, shifted by min(2 sigma, 40)); the row sums of P accumulate in
  * registers, o_sum[q,:] = sum_e P[q,e] * table[e,:] in tensor memory.  No online rescaling: bf16 operands and fp32
- * accumulators keep 8 exponent bits, so P is representable for x within [-87, +88] nats of mref -- beyond that the sums
- * read inf, the loss NaN and the job raises FloatingPointError (train.py:343-345).
+ * accumulators keep 8 exponent bits, so P is representable for x up to ~88 nats above mref (terms far below it underflow
+ * harmlessly).  mref also covers the batch's label entities and the row's own labels -- where a trained model puts its
+ * large scores.  It remains a guess: *status (device, int32; the caller zeroes it) is set to 1 when a row sum or an
+ * accumulator left the fp32 range; the results of such a call are invalid and the caller repeats the step with
+ * kgeb_fused_fwd + kgeb_fused_bwd (online maximum), as fused.AllEntityLoss and the steppers do.
  *   rowstat[B,4] = (mref, sum_e exp(x - mref), 0, sum of x over the row's labels in this shard)  -- kgeb_fused_fwd's layout,
  *                  i.e. kgeb_loss_from_rowstat and the shard combination (max + rescaled sums) apply unchanged
  *   o_sum[B,d]
  * Replaces K4 + K8 of SURVEY.md 2.3 (mm + log_softmax, distmult.py:20-22, loss.py:199-213) and the dQ half of their backward. */
 int kgeb_fused_flash_fwd(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
                          int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
-                         const void* table_bf16, float* rowstat, float* o_sum, void* workspace, int64_t workspace_bytes,
-                         void* stream);
+                         const void* table_bf16, float* rowstat, float* o_sum, int32_t* status, void* workspace,
+                         int64_t workspace_bytes, void* stream);
 /* dQ[q,:] = w_q * exp(mref_q - lse_q) * o_sum[q,:] - (w_q / nnz_q) * sum over the row's labels in this shard of table[e,:],
  * w_q = inv_batch * grad_scale[q] * (row q has labels).  rowstat_local = THIS shard's kgeb_fused_flash_fwd output (its
  * mref), lse = the global log-sum-exp (kgeb_loss_from_rowstat on the combined statistics).  No pass over the table. */
@@ -189,6 +192,10 @@ int kgeb_fused_flash_dq(const float* Q, int64_t B, int d, const float* table, in
                         const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const float* rowstat_local,
                         const float* lse, float inv_batch, const float* grad_scale /* [B] or NULL */, const float* o_sum,
                         float* dQ, void* workspace, int64_t workspace_bytes, void* stream);
+/* buf[0..numel) = 0 if *flag != 0 (any non-zero 32-bit word), else nothing.  Guard between the gradient computation and
+ * the optimizer kernels of a captured step whose kgeb_fused_flash_fwd reported a failure: zero gradients make the Adagrad
+ * kernels exact no-ops, the host then repeats the step with the two-pass kernels. */
+int kgeb_zero_if(const int32_t* flag, float* buf, int64_t numel, void* stream);
 /* What TrainingJobKvsAll logs per batch (train.py:744-747: avg_loss is overwritten once per query type, so the value of
  * the LAST non-empty query type survives): rows_loss[B] from kgeb_loss_from_rowstat, row_type[B] (0 = sp_, 1 = _po);
  * out[0] = sum of all rows (the cost that was back-propagated), out[1] = sum over the rows of the highest type present. */

@@ -81,6 +81,7 @@ struct Params {
   int overwrite;           // !RES_IS_Q: the accumulator is STORED into dTable (plain TMA store) instead of added to it
   const float* mref;       // FLASH: [B] reference score per row (natural units); P = exp(x - mref)
   int a_tmem;              // v2: the resident operand is copied to tensor memory once per job (MMA1 with A in TMEM)
+  int* status;             // FLASH: set to 1 when a row sum or an accumulator entry is not finite (reference too low)
   const float* colk;       // !RES_IS_Q, KL: [colk_n] exponent offsets (log(rs_q) - lse_q) * log2(e) per streamed (query) row,
   int colk_n;              //   padded with zeros to a multiple of 64; staged in shared memory by the v2 kernel (0 = unused)
 };
@@ -477,8 +478,12 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
         // row sum of P over this job's (chunk, column part); zero-filled entity columns beyond the table end scored
         // exactly 0, i.e. P = exp(-mref): taken out once per job
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
-        sp[0] = ((er.fl_l[0] + er.fl_l[1]) + (er.fl_l[2] + er.fl_l[3])) - (float)er.n_pad * ex2_ftz(er.fl_m2);
+        const float l = ((er.fl_l[0] + er.fl_l[1]) + (er.fl_l[2] + er.fl_l[3])) - (float)er.n_pad * ex2_ftz(er.fl_m2);
+        sp[0] = l;
         sp[1] = 0.f;
+        // exp(x - mref) left the fp32 / bf16 range (a score > 88 nats above the reference): the caller re-runs the step
+        // with the two-pass kernels (online maximum).  Finite sums are exact whatever their magnitude.
+        if (!(fabsf(l) <= 3.0e38f)) *p.status = 1;
       }
       if (STATS && res_row < p.B) {
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
@@ -498,9 +503,13 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
           tmem_ld16(lane_addr + O_COL + (uint32_t)c0, o);
           if (res_row < p.n_res) {
             float* dst = p.out + ((size_t)ch * p.B + res_row) * p.d + c0;
+            float big = 0.f;
 #pragma unroll
-            for (int c = 0; c < 16; c += 4)
+            for (int c = 0; c < 16; c += 4) {
               *reinterpret_cast<float4*>(dst + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+              if (FLASH) big = fmaxf(fmaxf(big, fmaxf(fabsf(o[c]), fabsf(o[c + 1]))), fmaxf(fabsf(o[c + 2]), fabsf(o[c + 3])));
+            }
+            if (FLASH && !(big <= 3.0e38f)) *p.status = 1;   // inf or NaN in the accumulator
           }
         }
       } else {
@@ -812,8 +821,12 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
       gunit += u1 - u0;
       if (FLASH && res_row < p.B) {
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
-        sp[0] = ((er.fl_l[0] + er.fl_l[1]) + (er.fl_l[2] + er.fl_l[3])) - (float)er.n_pad * ex2_ftz(er.fl_m2);
+        const float l = ((er.fl_l[0] + er.fl_l[1]) + (er.fl_l[2] + er.fl_l[3])) - (float)er.n_pad * ex2_ftz(er.fl_m2);
+        sp[0] = l;
         sp[1] = 0.f;
+        // exp(x - mref) left the fp32 / bf16 range (a score > 88 nats above the reference): the caller re-runs the step
+        // with the two-pass kernels (online maximum).  Finite sums are exact whatever their magnitude.
+        if (!(fabsf(l) <= 3.0e38f)) *p.status = 1;
       }
       if (STATS && res_row < p.B) {
         float* sp = p.stat_partial + (((size_t)ch * 4 + part) * p.B + res_row) * 2;
@@ -832,9 +845,13 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
           tmem_ld16(lane_addr + O_COL + (uint32_t)c0, o);
           if (res_row < p.n_res) {
             float* dst = p.out + ((size_t)ch * p.B + res_row) * p.d + c0;
+            float big = 0.f;
 #pragma unroll
-            for (int c = 0; c < 16; c += 4)
+            for (int c = 0; c < 16; c += 4) {
               *reinterpret_cast<float4*>(dst + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+              if (FLASH) big = fmaxf(fmaxf(big, fmaxf(fabsf(o[c]), fabsf(o[c + 1]))), fmaxf(fabsf(o[c + 2]), fabsf(o[c + 3])));
+            }
+            if (FLASH && !(big <= 3.0e38f)) *p.status = 1;   // inf or NaN in the accumulator
           }
         }
       } else {
@@ -1132,28 +1149,42 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __r
   if (i < n) for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
 }
 
-// FLASH reference score: mref[q] = max over a strided sample of <= 64 entities of this shard of Q[q] . table[e] (fp32).
-// Any value within ~[-87, +88] nats of the row's true maximum works (see tc_bwd_kernel); a sampled maximum is below the
-// true one by construction and, for any score distribution a trained model produces, far inside that window.
-// One warp per row, four sampled rows in flight per iteration (the loop is pure L2 latency otherwise).
-constexpr int kFlashSamples = 64;
+// FLASH reference score of row q (fp32):
+//   mref[q] = max( max over a strided sample of <= 64 entities of the shard + min(2 sigma, 40),
+//                  max over <= 192 of THIS BATCH's label entities (strided over lab_col, those inside the shard),
+//                  the largest score among the row's own labels )
+// exp(x - mref) must stay inside the fp32 / bf16 range for every entity: x - mref < ~88 nats.  The strided sample centres
+// the window for bell-shaped rows (the shard maximum lies ~3 sigma above the maximum of 64 samples); the label entities
+// are where a trained model puts its large scores -- the row's own answers, and the popular answers that recur in every
+// batch and carry the largest norms.  This is a heuristic: the kernel reports rows it failed on (Params::status) and the
+// caller repeats the step with the two-pass kernels, so a wrong guess costs time, never a wrong result.
+// One warp per row, four candidate rows in flight per iteration (the loop is pure L2 latency otherwise).
+constexpr int kFlashSamples = 64, kFlashLabelSamples = 192;
 __global__ void __launch_bounds__(256)
-sample_max_kernel(const float* __restrict__ Q, const float* __restrict__ table, int64_t B, int d, int64_t n_ent,
+sample_max_kernel(const float* __restrict__ Q, const float* __restrict__ table, int64_t B, int d, int64_t e_lo, int64_t n_ent,
+                  const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col, const float* __restrict__ entry_dot,
                   float* __restrict__ mref) {
   const int lane = threadIdx.x & 31;
   const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= B) return;
   const int64_t ns = n_ent < kFlashSamples ? n_ent : kFlashSamples;
+  const int64_t n_lab = lab_off[B];
+  const int64_t nl = n_lab < kFlashLabelSamples ? n_lab : kFlashLabelSamples;
   float q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) q[i] = lane + 32 * i < d ? Q[r * d + lane + 32 * i] : 0.f;   // d <= 256
-  float best = -INFINITY;
-  for (int64_t k0 = 0; k0 < ns; k0 += 4) {
+  float best = -INFINITY, sum = 0.f, sum2 = 0.f, best_lab = -INFINITY;
+  for (int64_t k0 = 0; k0 < ns + nl; k0 += 4) {
     float acc[4];
+    bool ok[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int64_t k = k0 + j < ns ? k0 + j : ns - 1;
-      const float* t = table + ((k * n_ent) / ns) * d;
+      const int64_t k = k0 + j;
+      int64_t e = -1;
+      if (k < ns) e = (k * n_ent) / ns;
+      else if (k < ns + nl) e = lab_col[((k - ns) * n_lab) / nl] - e_lo;
+      ok[j] = e >= 0 && e < n_ent;
+      const float* t = table + (ok[j] ? e : 0) * d;
       float a = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -1161,9 +1192,23 @@ sample_max_kernel(const float* __restrict__ Q, const float* __restrict__ table, 
       acc[j] = a;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) best = fmaxf(best, warp_sum(acc[j]));
+    for (int j = 0; j < 4; ++j) {
+      const float x = warp_sum(acc[j]);
+      if (!ok[j]) continue;
+      if (k0 + j < ns) { best = fmaxf(best, x); sum += x; sum2 = fmaf(x, x, sum2); }
+      else best_lab = fmaxf(best_lab, x);
+    }
   }
-  if (lane == 0) mref[r] = best;
+  const float mean = sum / (float)ns;
+  const float sigma = sqrtf(fmaxf(sum2 / (float)ns - mean * mean, 0.f));
+  float m = fmaxf(best + fminf(2.f * sigma, 40.f), best_lab);
+  if (entry_dot)   // exact scores at the row's own labels inside this shard
+    for (int64_t i = lab_off[r] + lane; i < lab_off[r + 1]; i += 32) {
+      const int64_t e = lab_col[i] - e_lo;
+      if (e >= 0 && e < n_ent) m = fmaxf(m, entry_dot[i]);
+    }
+  m = warp_max(m);
+  if (lane == 0) mref[r] = m;
 }
 
 // rowstat[r] = (mref, sum_e exp(x - mref), 0, sum of x over the row's labels) -- the layout of the forward statistics
@@ -1387,7 +1432,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
 // FLASH forward (KL, bf16 tiles): row statistics and o_sum = sum_e exp(x - mref) * table[e] in one pass over the table.
 int tc_flash_fwd(const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb, int64_t e_lo,
                  int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, float* rowstat, float* o_sum,
-                 void* ws, int64_t ws_bytes, cudaStream_t st) {
+                 int* status, void* ws, int64_t ws_bytes, cudaStream_t st) {
   using namespace tcb;
   KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_flash_fwd: entity dim must be a multiple of 16 and <= 256 (got %d)", d);
   KGEB_REQUIRE(Qb && tableb, "fused_flash_fwd: the bf16 mirrors of Q and of the table are required");
@@ -1419,11 +1464,13 @@ int tc_flash_fwd(const float* Q, const void* Qb, int64_t B, int d, const float* 
     KGEB_LAUNCH_CHECK("flash_rowstat");
     return KGEB_OK;
   }
-  sample_max_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(Q, table, B, d, n_ent, mref);
+  sample_max_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(Q, table, B, d, e_lo, n_ent, lab_off, lab_col,
+                                                             nnz > 0 ? entry_dot : nullptr, mref);
   KGEB_LAUNCH_CHECK("sample_max");
   Plan pl = make_plan(true, true, B, d, n_ent);
   if (pl.p.nstr < 2) { set_error("fused_flash_fwd: not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
   pl.p.loss = KGEB_LOSS_KL; pl.p.inv_batch = 1.f; pl.p.out = partial; pl.p.stat_partial = stat_partial; pl.p.mref = mref;
+  pl.p.status = status;
   CUtensorMap m_res, m_str;
   int rc;
   if ((rc = make_map(&m_res, Qb, B, d, RES_ROWS, true)) || (rc = make_map(&m_str, tableb, n_ent, d, STR_ROWS, true))) return rc;

@@ -32,7 +32,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
                  void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
 int tc_flash_fwd(const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb, int64_t e_lo,
                  int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, float* rowstat, float* o_sum,
-                 void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
+                 int* status, void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
 int tc_flash_dq(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent, const int64_t* lab_off,
                 const int64_t* lab_col, int64_t nnz, const float* tscale, const float* rowstat_local, const float* lse,
                 float inv_batch, const float* row_scale, const float* o_sum, float* dQ, void* ws, int64_t ws_bytes,
@@ -938,11 +938,11 @@ int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const f
 
 int kgeb_fused_flash_fwd(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
                          int64_t num_entities, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
-                         const void* table_bf16, float* rowstat, float* o_sum, void* workspace, int64_t workspace_bytes,
-                         void* stream) {
+                         const void* table_bf16, float* rowstat, float* o_sum, int32_t* status, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
   int rc = check_fused(KGEB_LOSS_KL, d, 0.f, Q, table, e_lo, e_hi);
   if (rc) return rc;
-  KGEB_REQUIRE(lab_off && lab_col && rowstat && o_sum && table_bf16, "fused_flash_fwd: bad arguments");
+  KGEB_REQUIRE(lab_off && lab_col && rowstat && o_sum && table_bf16 && status, "fused_flash_fwd: bad arguments");
   KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_flash_fwd: needs the bf16 tiles (dim %% 16 == 0, <= 256; got %d)", d);
   (void)num_entities;
   const int64_t n_ent = e_hi - e_lo;
@@ -951,8 +951,8 @@ int kgeb_fused_flash_fwd(const float* Q, int64_t B, int d, const float* table, i
   KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, nnz), "fused_flash_fwd: workspace too small");
   TailWs tail = carve_tail(workspace, workspace_bytes, B, d);
   if ((rc = tc_to_bf16(Q, tail.qb, B * (int64_t)d, st))) return rc;
-  return tc_flash_fwd(Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, rowstat, o_sum, workspace,
-                      tail.usable, st);
+  return tc_flash_fwd(Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_col, nnz, rowstat, o_sum, status,
+                      workspace, tail.usable, st);
 }
 
 int kgeb_fused_flash_dq(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
@@ -970,6 +970,24 @@ int kgeb_fused_flash_dq(const float* Q, int64_t B, int d, const float* table, in
   KGEB_LAUNCH_CHECK("label_weight");
   return tc_flash_dq(Q, B, d, table, e_lo, n_ent, lab_off, lab_col, nnz, tail.tscale, rowstat_local, lse, inv_batch,
                      grad_scale, o_sum, dQ, workspace, tail.usable, st);
+}
+
+// Guard of a captured step whose optimistic path can fail (kgeb_fused_flash_fwd's status): when *flag != 0 the gradient
+// buffers are cleared, which makes the Adagrad kernels that follow exact no-ops (state += 0, w -= lr * 0 / ...), so the
+// tables and the optimizer state are untouched and the host can repeat the step on the robust path.
+__global__ void zero_if_kernel(const int32_t* __restrict__ flag, float4* __restrict__ buf, int64_t n4) {
+  if (*flag == 0) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+int kgeb_zero_if(const int32_t* flag, float* buf, int64_t numel, void* stream) {
+  KGEB_REQUIRE(flag && buf && numel >= 0 && numel % 4 == 0 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0,
+               "zero_if: bad arguments (16-byte aligned buffer, multiple of 4 elements)");
+  if (numel == 0) return KGEB_OK;
+  zero_if_kernel<<<kNumSMs * 4, 256, 0, as_stream(stream)>>>(flag, reinterpret_cast<float4*>(buf), numel / 4);
+  KGEB_LAUNCH_CHECK("zero_if");
+  return KGEB_OK;
 }
 
 // per-row loss values, log-sum-exp and the batch loss from the fused forward statistics: one block, fixed order

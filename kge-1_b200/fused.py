@@ -86,17 +86,20 @@ def flash_supported(loss: int, math: int, d: int, label_smoothing: float) -> boo
 
 
 def flash_forward(q, table, lab_off, lab_col, shard: Shard):
-    """(rowstat_local [B,4] = (mref, sum exp(x - mref), 0, label dot), o_sum [B,d]) of this shard."""
+    """(rowstat_local [B,4] = (mref, sum exp(x - mref), 0, label dot), o_sum [B,d], status int32 [1]) of this shard.
+    status != 0: a score lay more than ~88 nats above the row's reference -- the results are invalid, use the two-pass
+    kernels (fused_rowstats / fused_backward)."""
     b, d = q.shape
     rowstat = torch.empty(b, 4, dtype=torch.float32, device=q.device)
     o_sum = torch.empty(b, d, dtype=torch.float32, device=q.device)
+    status = torch.zeros(1, dtype=torch.int32, device=q.device)
     n_ent = shard.e_hi - shard.e_lo
     ws = ops._workspace(q.device, lib.load().kgeb_fused_workspace_bytes(b, d, n_ent, lab_col.numel()))
     lib.call("kgeb_fused_flash_fwd", lib.f32(q, "queries"), b, d, lib.f32(table, "table"), shard.e_lo, shard.e_hi,
              shard.num_entities, lib.i64(lab_off), lib.i64(lab_col), lab_col.numel(),
-             _mirror_ptr(table, lib.MATH_BF16, b, d), rowstat.data_ptr(), o_sum.data_ptr(), ws.data_ptr(), ws.numel(),
-             lib.stream_ptr(q))
-    return rowstat, o_sum
+             _mirror_ptr(table, lib.MATH_BF16, b, d), rowstat.data_ptr(), o_sum.data_ptr(), status.data_ptr(), ws.data_ptr(),
+             ws.numel(), lib.stream_ptr(q))
+    return rowstat, o_sum, status
 
 
 def flash_dq(q, table, lab_off, lab_col, rowstat_local, lse, inv_batch, grad_scale, o_sum, shard: Shard) -> torch.Tensor:
@@ -171,7 +174,11 @@ class AllEntityLoss(torch.autograd.Function):
         qd, td = q.detach().contiguous(), table.detach()
         flash = flash_supported(loss, math, qd.shape[1], label_smoothing) and qd.shape[0] > 0
         if flash:
-            local, o_sum = flash_forward(qd, td, lab_off, lab_col, shard)
+            local, o_sum, status = flash_forward(qd, td, lab_off, lab_col, shard)
+            if shard.distributed:      # every rank must take the same path
+                dist.all_reduce(status, op=dist.ReduceOp.MAX, group=shard.group)
+            flash = int(status.item()) == 0     # (the job reads the loss back every batch anyway, train.py:747, 1043)
+        if flash:
             rowstat = combine_rowstats(local, loss, shard)
         else:
             local = o_sum = None

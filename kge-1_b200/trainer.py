@@ -182,10 +182,16 @@ class FusedAllEntityStepper:
         self.dp_flat = self.gflat[n_e:]                               # what the replicas exchange
         self.rowstat = torch.empty(rows, 4, **f32)
         # KL on the bf16 tiles: forward statistics and dQ from ONE table pass (kgeb_fused_flash_fwd / _dq)
-        self.flash = fused.flash_supported(loss_kind, math_mode, self.d, self.ls)
+        # (single GPU, no folded penalty: a failed flash pass is undone by clearing the gradients -- Adagrad is then a no-op --
+        # and the step repeats on the two-pass graph; with a penalty gradient folded into Adagrad that is not a no-op)
+        self.flash = (fused.flash_supported(loss_kind, math_mode, self.d, self.ls) and dp_group is None
+                      and not (shard is not None and shard.distributed) and self.pen is None)
+        self._use_flash = self.flash          # which forward / backward the stage functions issue (graph capture toggles it)
+        self.flash_fallbacks = 0              # steps that had to be repeated on the two-pass kernels
         if self.flash:
             self.rowstat_local = torch.empty(rows, 4, **f32)      # this shard's statistics (its mref) before the combine
             self.o_sum = torch.empty(rows, self.d, **f32)
+            self.flash_status = torch.zeros(4, dtype=torch.int32, device=dev)
         self.loss_rows = torch.zeros(rows, **f32)      # per-row loss values (kgeb_loss_from_rowstat rows_out)
         self.report = torch.zeros(2, **f32)            # [total, value of the last non-empty query type] (train.py:747)
         # Data parallelism for graphs too small to shard (SURVEY.md 8e "replicas" row): every rank trains on its own
@@ -265,10 +271,12 @@ class FusedAllEntityStepper:
                          self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.lab_perm.data_ptr(),
                          self.ls, 1.0 / self.global_batch, None, self.g_q.data_ptr(), self.ws2.data_ptr(),
                          self.ws2.numel(), lib.stream_ptr(self.ent))
-        if self.flash:
+        if self._use_flash:
+            self.flash_status.zero_()
             lib.call("kgeb_fused_flash_fwd", self.Q.data_ptr(), self.rows, self.d, ent[sh.e_lo:sh.e_hi].data_ptr(), sh.e_lo,
                      sh.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self._mirror_ptr(),
-                     self.rowstat.data_ptr(), self.o_sum.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
+                     self.rowstat.data_ptr(), self.o_sum.data_ptr(), self.flash_status.data_ptr(), self.ws.data_ptr(),
+                     self.ws.numel(), st)
             self.rowstat_local.copy_(self.rowstat)
         elif not self._fused_stats_in_backward():
             lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
@@ -301,7 +309,7 @@ class FusedAllEntityStepper:
         # stream, so that the chain of small latency-bound kernels that follows dQ on this stream (partial reduce, label
         # scatter, query-transform backward, sorted scatters) runs underneath the dTable tile kernel.
         cur = torch.cuda.current_stream()
-        if self.flash:
+        if self._use_flash:
             # the log-sum-exp is known (loss kernel above): the dense table gradient -- the only remaining table pass -- goes
             # to the second stream; dQ = rescaled o_sum + label rows is a [rows, d] elementwise kernel on this one
             self.ev_q.record()
@@ -360,6 +368,12 @@ class FusedAllEntityStepper:
         """bf16 tile path on an unsharded table with labels: see _stage_forward."""
         return self.mirror is not None and not self.shard.distributed and self.nnz_max > 0
 
+    def _guard_flash(self, buf: torch.Tensor):
+        """A failed flash pass (flash_status != 0) left garbage in the gradients: clear `buf` right before its Adagrad
+        kernel, which then is an exact no-op; step() sees the status and repeats the step on the two-pass graph."""
+        if self._use_flash:
+            lib.call("kgeb_zero_if", self.flash_status.data_ptr(), buf.data_ptr(), buf.numel(), lib.stream_ptr(self.ent))
+
     def _stage_update(self):
         st = lib.stream_ptr(self.ent)
         model_id = lib.MODELS[self.model.model]
@@ -386,6 +400,7 @@ class FusedAllEntityStepper:
                              rel.numel(), self.lr, self.eps, 0.0, self.pen["rel"][0], self.pen["rel"][1], None,
                              self.penalty_values[1:].data_ptr(), self.pen_ws[1].data_ptr(), self.pen_ws[1].numel(), st2)
                 else:
+                    self._guard_flash(self.g_rel)
                     lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None,
                              rel.numel(), self.lr, self.eps, 0.0, None, st2)
         if self.seq:
@@ -411,6 +426,7 @@ class FusedAllEntityStepper:
                      ent.numel(), self.lr, self.eps, 0.0, self.pen["ent"][0], self.pen["ent"][1], mirror,
                      self.penalty_values.data_ptr(), self.pen_ws[0].data_ptr(), self.pen_ws[0].numel(), st)
         else:
+            self._guard_flash(self.gflat[:(1 if self.seq else 2) * self.E * self.d])       # g_ent (and g_q)
             lib.call("kgeb_adagrad_dense", ent.data_ptr(), s_ent.data_ptr(), self.g_ent.data_ptr(),
                      None if self.seq else self.g_q.data_ptr(), ent.numel(), self.lr, self.eps, 0.0, mirror, st)
         cur.wait_stream(self.side2)
@@ -549,6 +565,18 @@ class FusedAllEntityStepper:
                 fn()
             self.graphs.append(g)
         self.graph = self.graphs[0]
+        self.graph_two_pass = None
+        if self.flash:        # the same step on the two-pass kernels (online maximum): replayed when the flash pass failed
+            self._use_flash = False
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                whole()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph_two_pass = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_two_pass):
+                whole()
+            self._use_flash = True
         torch.cuda.synchronize()
         with torch.no_grad():   # the warm-up / capture runs must not count as training steps
             for dst, src in zip((self.ent, self.rel, self.opt.state[self.ent]["sum"], self.opt.state[self.rel]["sum"]),
@@ -617,8 +645,18 @@ class FusedAllEntityStepper:
         """Runs one training step; returns the (device) loss tensor of this batch."""
         if self.graph is None:
             self._launch()
+            if self.flash and int(self.flash_status[0].item()) != 0:
+                self.flash_fallbacks += 1
+                self._use_flash = False
+                self._launch()
+                self._use_flash = True
         elif len(self.graphs) == 1:
             self.graphs[0].replay()
+            # flash pass: one 4-byte read-back per step (the job reads the loss back every step as well, train.py:747,
+            # 1043); a failed pass cleared its gradients, so nothing was updated and the step repeats on the two-pass graph
+            if self.flash and int(self.flash_status[0].item()) != 0:
+                self.flash_fallbacks += 1
+                self.graph_two_pass.replay()
         elif self.dp_world > 1:
             self.graphs[0].replay()
             self._exchange_dp()
@@ -705,10 +743,14 @@ class RowShardedAllEntityStepper:
         self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
         self.loss = torch.zeros((), **f32)
         self.rowstat = torch.empty(rows, 4, **f32)
-        self.flash = fused.flash_supported(loss_kind, math_mode, self.d, self.ls)
+        # flash pass (KL, bf16 tiles) in the peer-memory mode only: its status must be agreed on by all ranks inside the graph
+        self.flash = fused.flash_supported(loss_kind, math_mode, self.d, self.ls) and self.px is not None
+        self._use_flash = self.flash
+        self.flash_fallbacks = 0
         if self.flash:
             self.rowstat_local = torch.empty(rows, 4, **f32)
             self.o_sum = torch.empty(rows, self.d, **f32)
+            self.flash_status = torch.zeros(4, dtype=torch.int32, device=dev)      # reduced over the ranks (non-zero = failed)
         self.lse = torch.zeros(rows, **f32)
         L = lib.load()
         self.ws = torch.empty(L.kgeb_fused_workspace_bytes(rows, self.d, max(self.n_loc, 1), nz), dtype=torch.uint8, device=dev)
@@ -731,6 +773,11 @@ class RowShardedAllEntityStepper:
         if self.px is not None:
             return {"A": self.A_part, "stat": self.stat_part, "dQ": self.dQ_part}[which]
         return {"A": self.A, "stat": self.rowstat, "dQ": self.dQ}[which]
+
+    def _guard_flash(self, buf: torch.Tensor):
+        """A failed flash pass on ANY rank: clear `buf` right before its Adagrad kernel (an exact no-op then)."""
+        if self._use_flash:
+            lib.call("kgeb_zero_if", self.flash_status.data_ptr(), buf.data_ptr(), buf.numel(), lib.stream_ptr(self.ent))
 
     def _ent_loc(self):
         return self.ent.detach()[self.e_lo:self.e_hi]
@@ -765,12 +812,16 @@ class RowShardedAllEntityStepper:
         rel = self.rel.detach()
         lib.call("kgeb_query_build", model_id, 0, self.row_combine.data_ptr(), self.A.data_ptr(), self.iota.data_ptr(),
                  rel.data_ptr(), self.p_idx.data_ptr(), 1, self.rows, self.d, self.Q.data_ptr(), st)
-        if self.flash:
+        if self._use_flash:
+            self.status_part.zero_()
             lib.call("kgeb_fused_flash_fwd", self.Q.data_ptr(), self.rows, self.d, self._ent_loc().data_ptr(), self.e_lo,
                      self.e_hi, self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
-                     self.mirror.data_ptr(), self._dst("stat").data_ptr(), self.o_sum.data_ptr(), self.ws.data_ptr(),
-                     self.ws.numel(), st)
+                     self.mirror.data_ptr(), self._dst("stat").data_ptr(), self.o_sum.data_ptr(), self.status_part.data_ptr(),
+                     self.ws.data_ptr(), self.ws.numel(), st)
             self.rowstat_local.copy_(self._dst("stat"))
+            # every rank learns whether ANY rank's pass failed (sum of the status words; an int 1 read as a float is a
+            # non-zero denormal, the guard tests the 32-bit word)
+            self._peer_allreduce("status", 4, 0, self.flash_status)
         elif not self._late_stats():
             lib.call("kgeb_fused_fwd", self.loss_kind, self.math, self.Q.data_ptr(), self.rows, self.d,
                      self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.E, self.lab_off.data_ptr(),
@@ -794,7 +845,7 @@ class RowShardedAllEntityStepper:
             lib.call("kgeb_fused_bwd", *common, None, self.g_ent.data_ptr(), None,
                      lib.BWD_OVERWRITE_TABLE if self.mirror is not None else 0, self.ws2.data_ptr(), self.ws2.numel(),
                      lib.stream_ptr(self.ent))
-        if self.flash:      # dQ partial of this shard from o_sum and the GLOBAL log-sum-exp: no second table pass
+        if self._use_flash:      # dQ partial of this shard from o_sum and the GLOBAL log-sum-exp: no second table pass
             lib.call("kgeb_fused_flash_dq", self.Q.data_ptr(), self.rows, self.d, self._ent_loc().data_ptr(), self.e_lo,
                      self.e_hi, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
                      self.rowstat_local.data_ptr(), self.lse.data_ptr(), 1.0 / self.batch_size, None, self.o_sum.data_ptr(),
@@ -815,6 +866,7 @@ class RowShardedAllEntityStepper:
                  self.dp.data_ptr(), st)
         lib.call("kgeb_scatter_add_rows", self.p_idx.data_ptr(), 1, self.dp.data_ptr(), self.rows, self.dr,
                  self.g_rel.data_ptr(), self.rel.shape[0], self.sws2.data_ptr(), self.sws2.numel(), st)
+        self._guard_flash(self.g_rel)
         lib.call("kgeb_adagrad_dense", rel.data_ptr(), self.opt.state[self.rel]["sum"].data_ptr(), self.g_rel.data_ptr(),
                  None, rel.numel(), self.lr, self.eps, 0.0, None, st)
         # query-side rows: every rank has the same da (dQ was all-reduced); each adds the rows it owns, the others go
@@ -822,6 +874,7 @@ class RowShardedAllEntityStepper:
         lib.call("kgeb_scatter_add_rows", self.loc_ids.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
                  self.g_q.data_ptr(), self.n_loc + 1, self.sws.data_ptr(), self.sws.numel(), st)
         if self.n_loc > 0:
+            self._guard_flash(self.g_all[:self.n_loc])
             s_loc = self.opt.state[self.ent]["sum"][self.e_lo:self.e_hi]
             lib.call("kgeb_adagrad_dense", self._ent_loc().data_ptr(), s_loc.data_ptr(), self.g_ent.data_ptr(),
                      None if self.one_buffer else self.g_q.data_ptr(), self.n_loc * self.d, self.lr, self.eps, 0.0,
@@ -832,7 +885,7 @@ class RowShardedAllEntityStepper:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         n_a, n_s = rows * self.d, rows * 4
-        flat = symm.empty(2 * n_a + n_s, dtype=torch.float32, device=dev)
+        flat = symm.empty(2 * n_a + n_s + 4, dtype=torch.float32, device=dev)
         hf = symm.rendezvous(flat, self.shard.group)
         pad = symm.empty(64, dtype=torch.int32, device=dev)
         hp = symm.rendezvous(pad, self.shard.group)
@@ -844,11 +897,13 @@ class RowShardedAllEntityStepper:
                        pads=lib.ptr_array([int(x) for x in hp.buffer_ptrs]),
                        A=lib.ptr_array(ptrs), dQ=lib.ptr_array([x + 4 * n_a for x in ptrs]),
                        stat=lib.ptr_array([x + 8 * n_a for x in ptrs]),
+                       status=lib.ptr_array([x + 8 * n_a + 4 * n_s for x in ptrs]),
                        epoch=torch.zeros(2, dtype=torch.int32, device=dev),
                        timeout=torch.zeros(1, dtype=torch.int32, device=dev))
         self.A_part = flat[:n_a].view(rows, self.d)
         self.dQ_part = flat[n_a:2 * n_a].view(rows, self.d)
-        self.stat_part = flat[2 * n_a:].view(rows, 4)
+        self.stat_part = flat[2 * n_a:2 * n_a + n_s].view(rows, 4)
+        self.status_part = flat[2 * n_a + n_s:].view(torch.int32)       # this rank's flash status (4 words)
 
     def _peer_allreduce(self, which: str, numel: int, mode: int, out: torch.Tensor):
         x = self.px
@@ -914,6 +969,18 @@ class RowShardedAllEntityStepper:
             with torch.cuda.graph(g):
                 self._launch()
             self.graphs.append(g)
+            self.graph_two_pass = None
+            if self.flash:     # the same step on the two-pass kernels, replayed by every rank when any rank's flash pass failed
+                self._use_flash = False
+                with torch.cuda.stream(side):
+                    self._launch()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                dist.barrier(self.shard.group)
+                self.graph_two_pass = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_two_pass):
+                    self._launch()
+                self._use_flash = True
         else:
             for fn in self._stages():
                 g = torch.cuda.CUDAGraph()
@@ -940,8 +1007,16 @@ class RowShardedAllEntityStepper:
     def step(self) -> torch.Tensor:
         if self.graphs is None:
             self._launch()
+            if self.flash and int(self.flash_status[0].item()) != 0:
+                self.flash_fallbacks += 1
+                self._use_flash = False
+                self._launch()
+                self._use_flash = True
         elif len(self.graphs) == 1:
             self.graphs[0].replay()
+            if self.flash and int(self.flash_status[0].item()) != 0:       # the same on every rank
+                self.flash_fallbacks += 1
+                self.graph_two_pass.replay()
         else:
             for i, g in enumerate(self.graphs):
                 g.replay()

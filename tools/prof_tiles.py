@@ -15,7 +15,7 @@ lab_col = torch.randint(0, e, (b,), device="cuda")
 sh = kb.fused.Shard.full(e)
 for it in range(3):
     if loss == kb.lib.LOSS_KL:
-        loc, o_sum = kb.fused.flash_forward(q, w, lab_off, lab_col, sh)
+        loc, o_sum, _ = kb.fused.flash_forward(q, w, lab_off, lab_col, sh)
         rows, lse = kb.fused.rows_loss(loc, lab_off, loss, 0.0, e)
         dw = torch.empty_like(w)
         kb.fused.fused_backward(q, w, lab_off, lab_col, loss, 0.0, 0.0, lse, 1.0 / b, None, kb.lib.MATH_BF16, sh, dw, want_dq=False, overwrite=True)
