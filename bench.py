@@ -217,8 +217,8 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
 
     # name -> (launcher, GEMMs the launch EXECUTES, GEMMs of the algorithm it stands for, ncu kernel name)
     cases = {"tc_tiles_kernel<stats> (kgeb_fused_fwd: scores + online log-sum-exp)": (fwd, 1, 1, "tc_tiles_kernel<1, 2, 1>"),
-             "tc_bwd_kernel<dQ> (kgeb_fused_bwd: S recomputed, dQ += G*T)": (lambda: bwd(True, False), 2, 1, "tc_bwd_kernel<1, 1, 0, 0, 0>"),
-             "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": (lambda: bwd(False, True), 2, 1, "tc_bwd_kernel<0, 1, 0, 0, 0>")}
+             "tc_bwd_kernel<dQ> (kgeb_fused_bwd: S recomputed, dQ += G*T)": (lambda: bwd(True, False), 2, 1, "tc_bwd4_kernel<1, 0, 0, 0, 0>"),
+             "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": (lambda: bwd(False, True), 2, 1, "tc_bwd4_kernel<0, 0, 0, 0, 0>")}
     if getattr(st, "flash", False):
         # forward statistics and dQ come out of ONE table pass (kgeb_fused_flash_fwd): two GEMMs executed, both algorithmic
         o_sum = torch.empty(rows, d, device=dev)
@@ -231,7 +231,7 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
 
         dt = [v for k, v in cases.items() if "dTable" in k][0]
         cases = {"tc_bwd_kernel<flash> (kgeb_fused_flash_fwd: scores + log-sum-exp + o_sum for dQ, one pass)":
-                 (flash, 2, 2, "tc_bwd_kernel<1, 1, 0, 0, 0, 1>"),
+                 (flash, 2, 2, "tc_bwd4_kernel<1, 0, 0, 0, 1>"),
                  "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": dt}
     res = {}
     for name, (fn, executed, algorithmic, _) in cases.items():

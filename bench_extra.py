@@ -115,7 +115,8 @@ def wnrr_rotate_ns(args):
     opt = kb.optim.create("Adagrad", model.parameters(), lr=0.2)
     job = kb.TrainingJobNegativeSampling(model, opt, kb.KgeLoss.create("kl"), fused_path=not args.reference_flow)
     if args.graph_step:
-        job.enable_graph_step(B, N, N, segment_bwd=args.segment_bwd)
+        job.enable_graph_step(B, N, N, segment_bwd=args.segment_bwd, fused_slot=not args.no_fused_slot,
+                              deterministic=not args.atomic)
     gen = torch.Generator().manual_seed(1)
     batches = []
     for _ in range(8):
@@ -132,10 +133,11 @@ def wnrr_rotate_ns(args):
 
     ms = timed(step, args.steps, args.warmup)
     if args.kernels:
-        kernel_table(step, 3, "wnrr_rotate_ns" + ("_graph" if args.graph_step else "") + ("_seg" if args.segment_bwd else ""))
+        kernel_table(step, 3, "wnrr_rotate_ns" + ("_graph" if args.graph_step else "") + ("_seg" if args.segment_bwd else "")
+                     + ("_3k" if args.no_fused_slot else "") + ("_atomic" if args.atomic else ""))
     hbm, _ = peaks()
     bytes_step = B * 2 * (1 + N) * d * 4 * 2   # gather of each candidate row + write of its gradient row
-    return {"workload": f"RotatE NS 2x{N} negatives d=128 E={E} B={B} ({'reference flow' if args.reference_flow else ('graph-captured fused step' + (', segment backward' if args.segment_bwd else '') if args.graph_step else 'fused pairs, autograd')})",
+    return {"workload": f"RotatE NS 2x{N} negatives d=128 E={E} B={B} ({'reference flow' if args.reference_flow else ('graph-captured fused step' + (', segment backward' if args.segment_bwd else '') + (', three kernels per slot' if args.no_fused_slot else ', one kernel per slot') + (', vector-reduction candidate gradients (not bit-reproducible)' if args.atomic else ', deterministic sorted scatter') if args.graph_step else 'fused pairs, autograd')})",
             "metric": "training triples/s", "value": B / (ms * 1e-3), "ms_per_step": ms,
             "roofline": {"hbm_gbs": bytes_step / (ms * 1e-3) / 1e9, "hbm_frac": bytes_step / (ms * 1e-3) / 1e9 / hbm,
                          "algorithmic_bytes_per_step": bytes_step}}
@@ -155,6 +157,37 @@ def wd5m_eval(args, model_name):
     if world > 1:   # every rank scores the whole batch against its own entity rows; int64 counts are all-reduced
         import torch.distributed as dist
         shard = kb.fused.Shard.of_rank(E, int(os.environ["RANK"]), world, dist.group.WORLD)
+    if args.real_filter:
+        # SURVEY.md 8(d) C5 as specified: the synthetic Wikidata5M-shaped graph (App. C generator, 20 M train + 5,000 valid +
+        # 5,000 test triples), filter = train + valid (+ test for the filtered_with_test numbers) over the FULL splits,
+        # every one of the 5,000 validation triples ranked once (10,000 queries), histograms and metrics included
+        t0 = time.time()
+        g = kb.graph.synthetic_graph("wikidata5m", seed=0, scale=args.scale)
+        t1 = time.time()
+        job = kb.EntityRankingJob(model, E, [g["train"], g["valid"]], g["test"], batch_size=B, math_mode=math_mode,
+                                  hits_at_k_s=(1, 3, 10), shard=shard)
+        t2 = time.time()
+        job.run(g["valid"][:2 * B])                      # warm-up (index arrays to the device, kernels loaded)
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res = job.run(g["valid"])
+        b_.record()
+        torch.cuda.synchronize()
+        total_ms = a.elapsed_time(b_)
+        nq = 2 * len(g["valid"])
+        ops = 2.0 * nq * E * d
+        hbm, tf = peaks()
+        return {"workload": f"filtered ranking {model_name} d=128 E={E}, ALL {len(g['valid'])} validation triples ({nq} queries) in "
+                            f"batches of {B}, filter = full train ({len(g['train'])}) + valid + test splits, "
+                            f"{'tf32 tcgen05 tiles' if math_mode == kb.lib.MATH_TF32 else 'fp32 CUDA-core tiles'}"
+                            + (f", scoring sharded by entity over {world} GPUs" if world > 1 else ""),
+                "metric": "eval queries/s", "value": nq / (total_ms * 1e-3), "ms_per_batch": total_ms / (len(g["valid"]) / B),
+                "n_gpus": world, "mrr_filtered": res["metrics"]["mean_reciprocal_rank_filtered"],
+                "host_seconds": {"graph": t1 - t0, "indexes": t2 - t1},
+                "roofline": {"ops_per_s_T": ops / (total_ms * 1e-3) / 1e12,
+                             "frac_of_fp32_alu_nominal_37T": ops / (total_ms * 1e-3) / 1e12 / 37.2 if math_mode == kb.lib.MATH_FP32 else None,
+                             "frac_of_bf16_sustained": ops / (total_ms * 1e-3) / 1e12 / tf if math_mode != kb.lib.MATH_FP32 else None}}
     job = kb.EntityRankingJob(model, E, [known], None, batch_size=B, math_mode=math_mode, hits_at_k_s=(1, 3, 10),
                               shard=shard)
     batch = torch.from_numpy(known[:B].copy())
@@ -188,6 +221,9 @@ def main():
     ap.add_argument("--reference-flow", action="store_true")
     ap.add_argument("--graph-step", action="store_true")
     ap.add_argument("--segment-bwd", action="store_true", help="negative sampling: candidate gradients by segment (ns_segment.cu)")
+    ap.add_argument("--no-fused-slot", action="store_true", help="negative sampling: the three-kernel slot of round 1")
+    ap.add_argument("--atomic", action="store_true", help="negative sampling: candidate gradients by vector reductions (not bit-reproducible)")
+    ap.add_argument("--real-filter", action="store_true", help="eval workloads: the full synthetic graph as filter, all 5,000 validation triples")
     ap.add_argument("--kernels", action="store_true", help="also write a per-kernel time table (CUPTI) to gpurun_out/")
     args = ap.parse_args()
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:

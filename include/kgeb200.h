@@ -377,6 +377,13 @@ int kgeb_p2p_apply(const void* const* peer_pads, const float* stage, int rank, i
                    uint32_t* timeout_flag, float* W0, void* mirror0, int64_t numel0, float* W1, int64_t numel1,
                    void* stream);
 
+/* One slot of a negative-sampling batch in one kernel (train.py:860-999, implementation "triple"; replaces
+ * kgeb_pairs_score + kgeb_ns_loss + kgeb_pairs_bwd): cand int64 [B, M], column 0 = the positive.  Outputs dQ [B,d], row_loss
+ * [B] (scaled by inv_batch) and the candidate gradient: dense == NULL -> rows dC [B*M, d] for the deterministic sorted
+ * scatter; dense != NULL -> added to dense[cand, :] with vector reductions (no rows, no sort; order-dependent rounding:
+ * the opt-in, not bit-reproducible fast path).  d % 4 == 0. */
+int kgeb_ns_fused(int kind, int loss, const float* Q, const float* table, const int64_t* cand, int64_t B, int64_t M, int d,
+                  float offset, float inv_batch, float* dQ, float* dC, float* dense, float* row_loss, void* stream);
 /* ---- a20 (tuning path, not yet run on hardware): negative-sampling backward without materialised candidate-gradient
  * rows.  ns_bwd_q = the dQ half of kgeb_pairs_bwd (no dC).  ns_cand_grad = the candidate half: pairs sorted by candidate
  * id (stable), one warp per distinct candidate recomputes its occurrences' rows from Q and adds their sum to

@@ -619,6 +619,133 @@ ns_loss_kernel(int loss, const float* __restrict__ scores, int64_t B, int64_t M,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// One slot of a negative-sampling batch in ONE kernel (train.py:860-999, implementation "triple"): block per positive
+// triple -- pair scores of its 1 + N candidates (rows gathered from the L2-resident table), the loss of the row and
+// dL/dscores in shared memory, dQ (warps combined in fixed order) and the candidate gradient.  Replaces kgeb_pairs_score +
+// kgeb_ns_loss + kgeb_pairs_bwd (three launches, the [B, 1+N] score and gradient matrices through global memory, the
+// candidate rows gathered twice from L2 -- the second gather here hits L1).
+//   dense == NULL : candidate gradient rows are written to dC[pair, :] for the deterministic sorted scatter (as before);
+//   dense != NULL : they are ADDED to dense[cand, :] with vector reductions (red.global.add.v2/v4.f32).  No rows are
+//                   materialised and no sort runs, but the order of the additions -- hence the last bits of the sum -- is
+//                   not reproducible: the opt-in fast path (deterministic=False).
+// ------------------------------------------------------------------------------------------
+constexpr int kNsFusedWarps = 8;
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kNsFusedWarps * 32)
+ns_fused_kernel(int loss, const float* __restrict__ Q, const float* __restrict__ table, const int64_t* __restrict__ cand,
+                int64_t B, int64_t M, int d, float offset, float inv_batch, float* __restrict__ dQ, float* __restrict__ dC,
+                float* __restrict__ dense, float* __restrict__ row_loss) {
+  extern __shared__ float smem[];                 // [kNsFusedWarps][d] dQ partials | [M] scores | [M] dL/dscores
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = d >> 1;
+  const int64_t row = blockIdx.x;
+  const float* q = Q + row * d;
+  float* acc = smem + warp * d;
+  float* sc = smem + kNsFusedWarps * d;
+  float* g_s = sc + M;
+  for (int k = lane; k < d; k += 32) acc[k] = 0.f;
+  // ---- scores ----
+  for (int64_t j = warp; j < M; j += kNsFusedWarps) {
+    const float* c = table + cand[row * M + j] * (int64_t)d;
+    const float a = pair_accumulate<KIND>(q, c, d, lane);
+    if (lane == 0) sc[j] = pair_finish<KIND>(a);
+  }
+  __syncthreads();
+  // ---- loss of the row and dL/dscores (column 0 is the positive, train.py:864-867); warp 0, as ns_loss_kernel ----
+  if (warp == 0) {
+    if (loss == KGEB_LOSS_KL) {
+      float mx = -INFINITY;
+      for (int64_t j = lane; j < M; j += 32) mx = fmaxf(mx, sc[j]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int64_t j = lane; j < M; j += 32) sum += __expf(sc[j] - mx);
+      sum = warp_sum(sum);
+      const float lse = mx + __logf(sum), inv = 1.f / sum;
+      for (int64_t j = lane; j < M; j += 32) g_s[j] = inv_batch * (__expf(sc[j] - mx) * inv - (j == 0 ? 1.f : 0.f));
+      if (lane == 0) row_loss[row] = inv_batch * (lse - sc[0]);
+    } else {
+      float a = 0.f;
+      for (int64_t j = lane; j < M; j += 32) {
+        const float z = sc[j] + offset;
+        a += softplusf(z) - (j == 0 ? z : 0.f);
+        g_s[j] = inv_batch * (sigmoidf(z) - (j == 0 ? 1.f : 0.f));
+      }
+      a = warp_sum(a);
+      if (lane == 0) row_loss[row] = inv_batch * a;
+    }
+  }
+  __syncthreads();
+  // ---- backward: dQ partial of this warp, candidate gradient of every pair ----
+  for (int64_t j = warp; j < M; j += kNsFusedWarps) {
+    const int64_t pair = row * M + j;
+    const float g = g_s[j];
+    const int64_t e = cand[pair];
+    const float* c = table + e * (int64_t)d;
+    float* gc = dense ? dense + e * (int64_t)d : dC + pair * d;
+    if (KIND == KGEB_ROT_L1 || KIND == KGEB_ROT_L2) {
+      // two complex dimensions per lane: re = columns [2k, 2k+2), im = columns [h + 2k, h + 2k + 2)   (d % 4 == 0)
+      const float coef2 = KIND == KGEB_ROT_L2 ? (fabsf(sc[j]) == 0.f ? 0.f : g / fabsf(sc[j])) : 0.f;
+      for (int k = 2 * lane; k < h; k += 64) {
+        const float2 qr = *reinterpret_cast<const float2*>(q + k), qi = *reinterpret_cast<const float2*>(q + h + k);
+        const float2 cr = __ldg(reinterpret_cast<const float2*>(c + k)), ci = __ldg(reinterpret_cast<const float2*>(c + h + k));
+        float tr[2], ti[2];
+        const float re[2] = {qr.x - cr.x, qr.y - cr.y}, im[2] = {qi.x - ci.x, qi.y - ci.y};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (KIND == KGEB_ROT_L1) {
+            const float m = sqrtf(re[u] * re[u] + im[u] * im[u]);
+            const float inv = m == 0.f ? 0.f : g / m;
+            tr[u] = re[u] * inv; ti[u] = im[u] * inv;
+          } else {
+            tr[u] = coef2 * re[u]; ti[u] = coef2 * im[u];
+          }
+        }
+        acc[k] += tr[0]; acc[k + 1] += tr[1]; acc[h + k] += ti[0]; acc[h + k + 1] += ti[1];
+        if (dense) {
+          red_add_v2(gc + k, -tr[0], -tr[1]);
+          red_add_v2(gc + h + k, -ti[0], -ti[1]);
+        } else {
+          *reinterpret_cast<float2*>(gc + k) = make_float2(-tr[0], -tr[1]);
+          *reinterpret_cast<float2*>(gc + h + k) = make_float2(-ti[0], -ti[1]);
+        }
+      }
+    } else {
+      const float dist = fabsf(sc[j]);
+      const float coef = KIND == KGEB_NEG_L2 ? (dist == 0.f ? 0.f : -g / dist) : 0.f;
+      for (int k = 4 * lane; k < d; k += 128) {                                        // d % 4 == 0
+        const float4 qv = *reinterpret_cast<const float4*>(q + k);
+        const float4 cv = __ldg(reinterpret_cast<const float4*>(c + k));
+        float t[4], o[4];
+        const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (KIND == KGEB_DOT) { t[u] = g * ca[u]; o[u] = g * qa[u]; }
+          else if (KIND == KGEB_NEG_L1) { t[u] = -g * sgnf(qa[u] - ca[u]); o[u] = -t[u]; }
+          else { t[u] = coef * (qa[u] - ca[u]); o[u] = -t[u]; }
+          acc[k + u] += t[u];
+        }
+        if (dense) red_add_v4(gc + k, o[0], o[1], o[2], o[3]);
+        else *reinterpret_cast<float4*>(gc + k) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kNsFusedWarps; ++w) s += smem[w * d + k];
+    dQ[row * d + k] = s;
+  }
+}
+
 // cand[i,0] = target[i]; cand[i,1+j] = negatives[i,j]
 __global__ void ns_candidates_kernel(const int64_t* __restrict__ target, const int64_t* __restrict__ neg, int64_t B,
                                      int64_t N, int64_t* __restrict__ cand) {
@@ -816,6 +943,22 @@ int kgeb_pairs_bwd(int kind, const float* Q, const float* table, const void* can
   DISPATCH_KIND(kind, (pairs_bwd_kernel<K_><<<(unsigned)B, kPairBwdWarps * 32, smem, st>>>(
                           Q, table, cand, idx64, B, M, d, G, scores, dQ, dC)));
   KGEB_LAUNCH_CHECK("pairs_bwd");
+  return KGEB_OK;
+}
+
+int kgeb_ns_fused(int kind, int loss, const float* Q, const float* table, const int64_t* cand, int64_t B, int64_t M, int d,
+                  float offset, float inv_batch, float* dQ, float* dC, float* dense, float* row_loss, void* stream) {
+  KGEB_REQUIRE(kind >= KGEB_DOT && kind <= KGEB_ROT_L2, "ns_fused: unknown kind %d", kind);
+  KGEB_REQUIRE(loss == KGEB_LOSS_KL || loss == KGEB_LOSS_BCE, "ns_fused: unknown loss %d", loss);
+  KGEB_REQUIRE(Q && table && cand && dQ && row_loss && (dC || dense) && B >= 0 && M >= 1 && d > 0, "ns_fused: bad arguments");
+  KGEB_REQUIRE(d % 4 == 0, "ns_fused: the embedding dim must be a multiple of 4 (got %d)", d);
+  if (B == 0) return KGEB_OK;
+  const size_t smem = ((size_t)kNsFusedWarps * d + 2 * (size_t)M) * sizeof(float);
+  KGEB_REQUIRE(smem <= 48 * 1024, "ns_fused: dim %d x %lld candidates do not fit the shared memory of a block", d, (long long)M);
+  cudaStream_t st = as_stream(stream);
+  DISPATCH_KIND(kind, (ns_fused_kernel<K_><<<(unsigned)B, kNsFusedWarps * 32, smem, st>>>(
+                          loss, Q, table, cand, B, M, d, offset, inv_batch, dQ, dC, dense, row_loss)));
+  KGEB_LAUNCH_CHECK("ns_fused");
   return KGEB_OK;
 }
 

@@ -1159,56 +1159,72 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __r
 // batch and carry the largest norms.  This is a heuristic: the kernel reports rows it failed on (Params::status) and the
 // caller repeats the step with the two-pass kernels, so a wrong guess costs time, never a wrong result.
 // One warp per row, four candidate rows in flight per iteration (the loop is pure L2 latency otherwise).
-constexpr int kFlashSamples = 64, kFlashLabelSamples = 192;
-__global__ void __launch_bounds__(256)
+constexpr int kFlashSamples = 64, kFlashLabelSamples = 192, kFlashWarps = 4, kFlashRows = 8;
+__global__ void __launch_bounds__(kFlashWarps * 32)
 sample_max_kernel(const float* __restrict__ Q, const float* __restrict__ table, int64_t B, int d, int64_t e_lo, int64_t n_ent,
                   const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col, const float* __restrict__ entry_dot,
                   float* __restrict__ mref) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= B) return;
+  // A block scores kFlashRows query rows against the (row-independent) candidate list: every candidate row is read once
+  // per block and dotted with all of the block's query rows (one candidate per warp at a time, lanes over the dimension).
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = blockIdx.x * (int64_t)kFlashRows;
+  __shared__ float s_q[kFlashRows][256];
+  __shared__ float s_best[kFlashWarps][kFlashRows], s_lab[kFlashWarps][kFlashRows], s_sum[kFlashWarps][kFlashRows],
+      s_sum2[kFlashWarps][kFlashRows];
+  for (int i = threadIdx.x; i < kFlashRows * 256; i += blockDim.x) {
+    const int rr = i >> 8, c = i & 255;
+    s_q[rr][c] = (r0 + rr < B && c < d) ? Q[(r0 + rr) * d + c] : 0.f;
+  }
+  __syncthreads();
   const int64_t ns = n_ent < kFlashSamples ? n_ent : kFlashSamples;
   const int64_t n_lab = lab_off[B];
   const int64_t nl = n_lab < kFlashLabelSamples ? n_lab : kFlashLabelSamples;
-  float q[8];
+  float best[kFlashRows], blab[kFlashRows], sum[kFlashRows], sum2[kFlashRows];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) q[i] = lane + 32 * i < d ? Q[r * d + lane + 32 * i] : 0.f;   // d <= 256
-  float best = -INFINITY, sum = 0.f, sum2 = 0.f, best_lab = -INFINITY;
-  for (int64_t k0 = 0; k0 < ns + nl; k0 += 4) {
-    float acc[4];
-    bool ok[4];
+  for (int rr = 0; rr < kFlashRows; ++rr) { best[rr] = -INFINITY; blab[rr] = -INFINITY; sum[rr] = 0.f; sum2[rr] = 0.f; }
+  for (int64_t k = warp; k < ns + nl; k += kFlashWarps) {
+    const int64_t e = k < ns ? (k * n_ent) / ns : lab_col[((k - ns) * n_lab) / nl] - e_lo;
+    if (e < 0 || e >= n_ent) continue;                       // a label entity of another shard (warp-uniform)
+    float t[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t k = k0 + j;
-      int64_t e = -1;
-      if (k < ns) e = (k * n_ent) / ns;
-      else if (k < ns + nl) e = lab_col[((k - ns) * n_lab) / nl] - e_lo;
-      ok[j] = e >= 0 && e < n_ent;
-      const float* t = table + (ok[j] ? e : 0) * d;
+    for (int i = 0; i < 8; ++i) t[i] = lane + 32 * i < d ? __ldg(table + e * d + lane + 32 * i) : 0.f;
+#pragma unroll
+    for (int rr = 0; rr < kFlashRows; ++rr) {
       float a = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (lane + 32 * i < d) a = fmaf(q[i], __ldg(t + lane + 32 * i), a);
-      acc[j] = a;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = warp_sum(acc[j]);
-      if (!ok[j]) continue;
-      if (k0 + j < ns) { best = fmaxf(best, x); sum += x; sum2 = fmaf(x, x, sum2); }
-      else best_lab = fmaxf(best_lab, x);
+      for (int i = 0; i < 8; ++i) a = fmaf(s_q[rr][lane + 32 * i], t[i], a);
+      const float x = warp_sum(a);
+      if (k < ns) { best[rr] = fmaxf(best[rr], x); sum[rr] += x; sum2[rr] = fmaf(x, x, sum2[rr]); }
+      else blab[rr] = fmaxf(blab[rr], x);
     }
   }
-  const float mean = sum / (float)ns;
-  const float sigma = sqrtf(fmaxf(sum2 / (float)ns - mean * mean, 0.f));
-  float m = fmaxf(best + fminf(2.f * sigma, 40.f), best_lab);
-  if (entry_dot)   // exact scores at the row's own labels inside this shard
-    for (int64_t i = lab_off[r] + lane; i < lab_off[r + 1]; i += 32) {
-      const int64_t e = lab_col[i] - e_lo;
-      if (e >= 0 && e < n_ent) m = fmaxf(m, entry_dot[i]);
+  if (lane == 0)
+#pragma unroll
+    for (int rr = 0; rr < kFlashRows; ++rr) {
+      s_best[warp][rr] = best[rr]; s_lab[warp][rr] = blab[rr]; s_sum[warp][rr] = sum[rr]; s_sum2[warp][rr] = sum2[rr];
     }
-  m = warp_max(m);
-  if (lane == 0) mref[r] = m;
+  __syncthreads();
+  // one warp per row finishes: combine the warps' partials (fixed order) and add the row's own label scores
+  for (int rr = warp; rr < kFlashRows; rr += kFlashWarps) {
+    const int64_t r = r0 + rr;
+    if (r >= B) continue;
+    float m_lab = -INFINITY;
+    if (entry_dot)   // exact scores at the row's own labels inside this shard
+      for (int64_t i = lab_off[r] + lane; i < lab_off[r + 1]; i += 32) {
+        const int64_t e = lab_col[i] - e_lo;
+        if (e >= 0 && e < n_ent) m_lab = fmaxf(m_lab, entry_dot[i]);
+      }
+    m_lab = warp_max(m_lab);
+    if (lane == 0) {
+      float bs = -INFINITY, sm = 0.f, sm2 = 0.f;
+      for (int w = 0; w < kFlashWarps; ++w) {
+        bs = fmaxf(bs, s_best[w][rr]); m_lab = fmaxf(m_lab, s_lab[w][rr]); sm += s_sum[w][rr]; sm2 += s_sum2[w][rr];
+      }
+      const float mean = sm / (float)ns;
+      const float sigma = sqrtf(fmaxf(sm2 / (float)ns - mean * mean, 0.f));
+      mref[r] = fmaxf(bs + fminf(2.f * sigma, 40.f), m_lab);
+    }
+  }
 }
 
 // rowstat[r] = (mref, sum_e exp(x - mref), 0, sum of x over the row's labels) -- the layout of the forward statistics
@@ -1464,8 +1480,8 @@ int tc_flash_fwd(const float* Q, const void* Qb, int64_t B, int d, const float* 
     KGEB_LAUNCH_CHECK("flash_rowstat");
     return KGEB_OK;
   }
-  sample_max_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(Q, table, B, d, e_lo, n_ent, lab_off, lab_col,
-                                                             nnz > 0 ? entry_dot : nullptr, mref);
+  sample_max_kernel<<<(unsigned)((B + kFlashRows - 1) / kFlashRows), kFlashWarps * 32, 0, st>>>(
+      Q, table, B, d, e_lo, n_ent, lab_off, lab_col, nnz > 0 ? entry_dot : nullptr, mref);
   KGEB_LAUNCH_CHECK("sample_max");
   Plan pl = make_plan(true, true, B, d, n_ent);
   if (pl.p.nstr < 2) { set_error("fused_flash_fwd: not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }

@@ -22,7 +22,17 @@ class KvsAllIndex:
         # stable multi-key sort = lexsort by (value, key1, key0); same order as indexing.py:86-98
         order = np.lexsort((t[:, value_col], t[:, key_cols[1]], t[:, key_cols[0]]))
         t = t[order]
-        keys, first = np.unique(t[:, list(key_cols)], axis=0, return_index=True)
+        # unique keys + first row of each: the rows are sorted, so a key starts wherever it differs from the row above
+        # (what np.unique(axis=0, return_index=True) returns, indexing.py:41-44, without its void-dtype sort: 20 M triples
+        # of the Wikidata5M shape take seconds instead of minutes)
+        kk = t[:, list(key_cols)]
+        if len(kk):
+            start = np.ones(len(kk), dtype=bool)
+            start[1:] = (kk[1:] != kk[:-1]).any(axis=1)
+            first = np.flatnonzero(start)
+            keys = kk[first]
+        else:
+            first, keys = np.zeros(0, dtype=np.int64), kk.reshape(0, 2)
         self.key = key
         self._keys = torch.from_numpy(np.ascontiguousarray(keys)).long()
         self._values_offset = torch.from_numpy(np.append(first, len(t)).astype(np.int64))

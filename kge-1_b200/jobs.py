@@ -370,13 +370,14 @@ class TrainingJobNegativeSampling(TrainingJob):
     stepper = None
 
     def enable_graph_step(self, batch_size: int, num_neg_s: int, num_neg_o: int, use_graph: bool = True, dp_group=None,
-                          segment_bwd: bool = False):
+                          segment_bwd: bool = False, fused_slot: bool = True, deterministic: bool = True):
         """Routes step() through FusedNegSamplingStepper (no autograd, one CUDA-graph replay per step) for batches of
         exactly `batch_size` triples with these negative counts for the S and O slots (no relation negatives).
         `dp_group`: data-parallel replicas with the peer-memory gradient exchange (trainer.PeerExchange)."""
         from .trainer import FusedNegSamplingStepper
         self.stepper = FusedNegSamplingStepper(self.model, self.optimizer, batch_size, num_neg_s, num_neg_o,
-                                               self.loss.kind, self.loss.offset, use_graph, dp_group, segment_bwd)
+                                               self.loss.kind, self.loss.offset, use_graph, dp_group, segment_bwd,
+                                               fused_slot, deterministic)
         return self.stepper
 
     def enable_device_sampling(self, sampler):

@@ -74,6 +74,7 @@ SIGNATURES = {
     "kgeb_rank_hist": [_p, _p, _l, _l, _p, _p, _p],
     "kgeb_isin_sorted": [_p, _i, _l, _p, _l, _p, _p],
     "kgeb_rank_metrics": [_p, _l, _p, _i, _p, _p, _l, _p],
+    "kgeb_ns_fused": [_i, _i, _p, _p, _p, _l, _l, _i, _f, _f, _p, _p, _p, _p, _p],
     "kgeb_ns_bwd_q": [_i, _p, _p, _p, _l, _l, _i, _p, _p, _p, _p],
     "kgeb_ns_cand_grad": [_i, _p, _p, _p, _l, _l, _i, _p, _p, _l, _p, _p, _l, _p],
     "kgeb_p2p_exchange": [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _l, _p, _p, _l, _p, _f, _f, _p],

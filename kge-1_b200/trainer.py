@@ -853,7 +853,8 @@ class RowShardedAllEntityStepper:
         else:
             lib.call("kgeb_fused_bwd", *common, self._dst("dQ").data_ptr(), None,
                      self._dst("stat").data_ptr() if late else None, 0, self.ws.data_ptr(), self.ws.numel(), st)
-        cur.wait_stream(self.side)
+        if self.px is None:      # separately captured stage graphs: nothing may stay forked at the end of one
+            cur.wait_stream(self.side)
 
     def _stage_update(self):
         st = lib.stream_ptr(self.ent)
@@ -869,6 +870,11 @@ class RowShardedAllEntityStepper:
         self._guard_flash(self.g_rel)
         lib.call("kgeb_adagrad_dense", rel.data_ptr(), self.opt.state[self.rel]["sum"].data_ptr(), self.g_rel.data_ptr(),
                  None, rel.numel(), self.lr, self.eps, 0.0, None, st)
+        if self.px is not None:
+            # one graph for the whole step: the dense table gradient (second stream) is joined only here -- the dQ exchange,
+            # the query-transform backward and the relation chain ran underneath the dTable tile kernel.  The query-side
+            # rows below go ON TOP of what that kernel stored, so they must follow it.
+            torch.cuda.current_stream().wait_stream(self.side)
         # query-side rows: every rank has the same da (dQ was all-reduced); each adds the rows it owns, the others go
         # to the dummy row n_loc
         lib.call("kgeb_scatter_add_rows", self.loc_ids.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
@@ -1059,7 +1065,8 @@ class FusedNegSamplingStepper:
     """
 
     def __init__(self, model: KgeModel, optimizer, batch_size: int, num_neg_s: int, num_neg_o: int, loss_kind: int,
-                 offset: float = 0.0, use_graph: bool = True, dp_group=None, segment_bwd: bool = False):
+                 offset: float = 0.0, use_graph: bool = True, dp_group=None, segment_bwd: bool = False,
+                 fused_slot: bool = True, deterministic: bool = True):
         """`segment_bwd`: candidate gradients without materialised rows (csrc/ns_segment.cu: pairs sorted by candidate, one
         warp per distinct candidate) instead of pairs_bwd's dC rows + the sorted scatter; tuning path, not yet run on
         hardware.
@@ -1068,7 +1075,13 @@ class FusedNegSamplingStepper:
         graph; loss terms are scaled by the global batch so that all replicas apply the identical update.  (Not yet
         run on hardware -- tests/p2p_ns_check.py.)"""
         _require_plain_model(model, "FusedNegSamplingStepper")
+        # fused_slot: scores, loss, dQ and the candidate gradient of a slot in ONE kernel (kgeb_ns_fused) instead of
+        # kgeb_pairs_score + kgeb_ns_loss + kgeb_pairs_bwd -- same sums in the same order, bit-identical results.
+        # deterministic=False (opt-in): that kernel adds the candidate gradients straight into the dense gradient with
+        # vector reductions -- no materialised gradient rows, no sort -- at the price of order-dependent rounding.
         self.model, self.opt = model, optimizer
+        self.fused_slot = bool(fused_slot) and not segment_bwd and model.get_s_embedder().weight.shape[1] % 4 == 0
+        self.deterministic = bool(deterministic) or not self.fused_slot
         self.B, self.N = batch_size, {0: int(num_neg_s), 2: int(num_neg_o)}
         self.loss_kind, self.offset = loss_kind, float(offset)
         self.kind = model.get_scorer().kind
@@ -1133,6 +1146,21 @@ class FusedNegSamplingStepper:
                      p_idx.data_ptr(), 1, B, d, b["Q"].data_ptr(), st)
             lib.call("kgeb_ns_candidates", target.data_ptr(), self.neg[slot].data_ptr(), B, self.N[slot],
                      b["cand"].data_ptr(), st)
+            if self.fused_slot:
+                lib.call("kgeb_ns_fused", self.kind, self.loss_kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), B, m,
+                         d, self.offset, 1.0 / self.global_batch, b["dQ"].data_ptr(),
+                         b["dC"].data_ptr() if self.deterministic else None,
+                         None if self.deterministic else self.g_ent.data_ptr(), b["rows"].data_ptr(), st)
+                lib.call("kgeb_query_bwd", model_id, combine, None, ent.data_ptr(), a_idx.data_ptr(), rel.data_ptr(),
+                         p_idx.data_ptr(), 1, B, d, b["dQ"].data_ptr(), b["da"].data_ptr(), b["dp"].data_ptr(), st)
+                if self.deterministic:
+                    lib.call("kgeb_scatter_add_rows", b["cand"].data_ptr(), 1, b["dC"].data_ptr(), B * m, d,
+                             self.g_ent.data_ptr(), self.E, self.sws.data_ptr(), self.sws.numel(), st)
+                lib.call("kgeb_scatter_add_rows", a_idx.data_ptr(), 1, b["da"].data_ptr(), B, d, self.g_ent.data_ptr(),
+                         self.E, self.sws.data_ptr(), self.sws.numel(), st)
+                lib.call("kgeb_scatter_add_rows", p_idx.data_ptr(), 1, b["dp"].data_ptr(), B, self.dr,
+                         self.g_rel.data_ptr(), self.rel.shape[0], self.sws.data_ptr(), self.sws.numel(), st)
+                continue
             lib.call("kgeb_pairs_score", self.kind, b["Q"].data_ptr(), ent.data_ptr(), b["cand"].data_ptr(), 1, B, m, d,
                      b["scores"].data_ptr(), st)
             lib.call("kgeb_ns_loss", self.loss_kind, b["scores"].data_ptr(), B, m, self.offset, 1.0 / self.global_batch,

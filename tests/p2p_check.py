@@ -71,7 +71,9 @@ def main():
         s0 = jobs[0].optimizer.state[models[0].get_s_embedder().weight]["sum"]
         s1 = jobs[1].optimizer.state[models[1].get_s_embedder().weight]["sum"]
         err = (s0 - s1).abs().max().item()
-        assert err == 0.0 if world == 2 else err <= 1e-6 * s0.abs().max().item(), err
+        # (sum of g^2 over three steps; the two modes add the ranks' gradients in different orders: world - 1 roundings of 2^-24
+        # per sum, squared and accumulated -- 1.4e-6 relative measured at world 8)
+        assert err == 0.0 if world == 2 else err <= 5e-6 * s0.abs().max().item(), err
         if rank == 0:
             print(f"peer-memory data-parallel step == NCCL data-parallel step (world {world}, math={math_mode}); "
                   f"loss {c.avg_loss}", flush=True)

@@ -525,3 +525,35 @@ def test_segment_backward_of_negative_sampling_equals_default_path(kb, model):
         for x, y in ((models[0].get_s_embedder().weight, models[1].get_s_embedder().weight),
                      (models[0].get_p_embedder().weight, models[1].get_p_embedder().weight)):
             assert (x - y).abs().max().item() <= 1e-5, (model, step)
+
+
+@pytest.mark.parametrize("model,loss", [("rotate", "kl"), ("transe", "bce"), ("distmult", "kl"), ("complex", "bce")])
+def test_fused_negative_sampling_slot_kernel(kb, model, loss):
+    """kgeb_ns_fused (scores + loss + dQ + candidate gradient of a slot in one kernel) against the three-kernel slot it
+    replaces: the same sums in the same order -> BIT-IDENTICAL tables after three steps; the opt-in vector-reduction form
+    (deterministic=False) agrees to rounding."""
+    g = kb.graph.synthetic_graph("toy", seed=1)
+    e, r, d, b, n = g["num_entities"], g["num_relations"], 64, 64, 16
+    l_norm = 2.0 if model == "transe" else 1.0
+    torch.manual_seed(0)
+    models = [kb.KgeModel(model, e, r, d, l_norm=l_norm).cuda() for _ in range(3)]
+    for m in models[1:]:
+        m.load_state_dict(models[0].state_dict())
+    jobs = []
+    for m, kw in zip(models, (dict(fused_slot=False), dict(fused_slot=True), dict(fused_slot=True, deterministic=False))):
+        opt = kb.optim.create("Adagrad", m.parameters(), lr=0.1, initial_accumulator_value=0.1)
+        job = kb.TrainingJobNegativeSampling(m, opt, kb.KgeLoss.create(loss))
+        job.enable_graph_step(b, n, n, use_graph=True, **kw)
+        jobs.append(job)
+    gen = torch.Generator().manual_seed(3)
+    for step in range(3):
+        triples = T(g["train"][step * b:(step + 1) * b].astype(np.int64))
+        negs = [torch.randint(0, e, (b, n), generator=gen), torch.zeros(b, 0, dtype=torch.long),
+                torch.randint(0, e, (b, n), generator=gen)]
+        negs[2][:, :3] = 7                       # a hub candidate: many additions to one row
+        res = [j.step(step, {"triples": triples, "negative_samples": negs}) for j in jobs]
+        assert res[1].avg_loss == res[0].avg_loss
+        assert res[2].avg_loss == pytest.approx(res[0].avg_loss, rel=1e-6)
+        for get in (lambda m: m.get_s_embedder().weight, lambda m: m.get_p_embedder().weight):
+            assert torch.equal(get(models[1]), get(models[0])), (model, step)
+            assert (get(models[2]) - get(models[0])).abs().max().item() <= 1e-5, (model, step)
