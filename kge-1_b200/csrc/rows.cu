@@ -465,8 +465,8 @@ query_bwd_kernel(int combine, const int32_t* __restrict__ row_combine, const flo
 // negative-sampling pair scoring: warp per (row, candidate); the query row is read from L1/L2
 // ------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __forceinline__ float pair_accumulate(const float* __restrict__ q, const float* __restrict__ c,
-                                                 int d, int lane) {
+__device__ __forceinline__ float pair_accumulate_nosum(const float* __restrict__ q, const float* __restrict__ c,
+                                                       int d, int lane) {
   float acc = 0.f;
   if (KIND == KGEB_ROT_L1) {
     const int h = d >> 1;
@@ -494,7 +494,11 @@ __device__ __forceinline__ float pair_accumulate(const float* __restrict__ q, co
       acc += (KIND == KGEB_DOT) ? q[k] * c[k] : (KIND == KGEB_NEG_L1 ? fabsf(x) : x * x);
     }
   }
-  return warp_sum(acc);
+  return acc;      // this lane's part: warp_sum() of it is the pair's sum
+}
+template <int KIND>
+__device__ __forceinline__ float pair_accumulate(const float* __restrict__ q, const float* __restrict__ c, int d, int lane) {
+  return warp_sum(pair_accumulate_nosum<KIND>(q, c, d, lane));
 }
 template <int KIND>
 __device__ __forceinline__ float pair_finish(float acc) {
@@ -652,11 +656,23 @@ ns_fused_kernel(int loss, const float* __restrict__ Q, const float* __restrict__
   float* sc = smem + kNsFusedWarps * d;
   float* g_s = sc + M;
   for (int k = lane; k < d; k += 32) acc[k] = 0.f;
-  // ---- scores ----
-  for (int64_t j = warp; j < M; j += kNsFusedWarps) {
-    const float* c = table + cand[row * M + j] * (int64_t)d;
-    const float a = pair_accumulate<KIND>(q, c, d, lane);
-    if (lane == 0) sc[j] = pair_finish<KIND>(a);
+  // ---- scores: four candidates of a warp in flight (the loop is L2 latency: index -> row -> shuffle reduction) ----
+  for (int64_t j0 = warp; j0 < M; j0 += 4 * kNsFusedWarps) {
+    int64_t e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = j0 + u * kNsFusedWarps;
+      e[u] = cand[row * M + (j < M ? j : j0)];
+    }
+    float a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = pair_accumulate_nosum<KIND>(q, table + e[u] * (int64_t)d, d, lane);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_sum(a[u]);
+      const int64_t j = j0 + u * kNsFusedWarps;
+      if (lane == 0 && j < M) sc[j] = pair_finish<KIND>(t);
+    }
   }
   __syncthreads();
   // ---- loss of the row and dL/dscores (column 0 is the positive, train.py:864-867); warp 0, as ns_loss_kernel ----
@@ -684,12 +700,18 @@ ns_fused_kernel(int loss, const float* __restrict__ Q, const float* __restrict__
   }
   __syncthreads();
   // ---- backward: dQ partial of this warp, candidate gradient of every pair ----
+  int64_t e_next = warp < M ? cand[row * M + warp] : 0;
   for (int64_t j = warp; j < M; j += kNsFusedWarps) {
     const int64_t pair = row * M + j;
     const float g = g_s[j];
-    const int64_t e = cand[pair];
+    const int64_t e = e_next;
     const float* c = table + e * (int64_t)d;
     float* gc = dense ? dense + e * (int64_t)d : dC + pair * d;
+    if (j + kNsFusedWarps < M) {          // the next candidate's row on its way to L1 while this one is processed
+      e_next = cand[pair + kNsFusedWarps];
+      const float* cn = table + e_next * (int64_t)d;
+      for (int k = 4 * lane; k < d; k += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(cn + k));
+    }
     if (KIND == KGEB_ROT_L1 || KIND == KGEB_ROT_L2) {
       // two complex dimensions per lane: re = columns [2k, 2k+2), im = columns [h + 2k, h + 2k + 2)   (d % 4 == 0)
       const float coef2 = KIND == KGEB_ROT_L2 ? (fabsf(sc[j]) == 0.f ? 0.f : g / fabsf(sc[j])) : 0.f;
