@@ -217,8 +217,8 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
 
     # name -> (launcher, GEMMs the launch EXECUTES, GEMMs of the algorithm it stands for, ncu kernel name)
     cases = {"tc_tiles_kernel<stats> (kgeb_fused_fwd: scores + online log-sum-exp)": (fwd, 1, 1, "tc_tiles_kernel<1, 2, 1>"),
-             "tc_bwd_kernel<dQ> (kgeb_fused_bwd: S recomputed, dQ += G*T)": (lambda: bwd(True, False), 2, 1, "tc_bwd4_kernel<1, 0, 0, 0, 0>"),
-             "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": (lambda: bwd(False, True), 2, 1, "tc_bwd4_kernel<0, 0, 0, 0, 0>")}
+             "tc_bwd_kernel<dQ> (kgeb_fused_bwd: S recomputed, dQ += G*T)": (lambda: bwd(True, False), 2, 1, "tc_bwd4_kernel<1, 0, 0, 0, 0, 0>"),
+             "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": (lambda: bwd(False, True), 2, 1, "tc_bwd4_kernel<0, 0, 0, 0, 0, 0>")}
     if getattr(st, "flash", False):
         # forward statistics and dQ come out of ONE table pass (kgeb_fused_flash_fwd): two GEMMs executed, both algorithmic
         o_sum = torch.empty(rows, d, device=dev)
@@ -231,8 +231,32 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
 
         dt = [v for k, v in cases.items() if "dTable" in k][0]
         cases = {"tc_bwd_kernel<flash> (kgeb_fused_flash_fwd: scores + log-sum-exp + o_sum for dQ, one pass)":
-                 (flash, 2, 2, "tc_bwd4_kernel<1, 0, 0, 0, 1>"),
+                 (flash, 2, 2, "tc_bwd4_kernel<1, 0, 0, 0, 1, 0>"),
                  "tc_bwd_kernel<dTable> (kgeb_fused_bwd: S recomputed, dT = G^T*Q)": dt}
+    if getattr(st, "fuse_update", False):
+        # what the step runs instead of the storing dTable kernel + kgeb_adagrad_dense: Adagrad applied by that kernel's
+        # update warps (lr 0 here: W and the mirror are written back unchanged; scratch state; no touched rows)
+        gtmp.fill_(0.1)
+        t = st.touched
+
+        def upd():
+            L.call("kgeb_fused_bwd_update", L.LOSS_KL, st.Q.data_ptr(), rows, d, table.data_ptr(), e_lo, e_hi, st.E,
+                   off0.data_ptr(), 0.0, 0.0, lse.data_ptr(), 1.0 / B, None, mp, gtmp.data_ptr(), 0.0, 1e-10,
+                   t.slot_of.data_ptr(), t.g_dense.data_ptr(), None, ws.data_ptr(), ws.numel(), L.stream_ptr(table))
+
+        state2 = None
+
+        def adagrad():      # the pass the fused kernel replaces (reads the stored gradient; lr 0)
+            L.call("kgeb_adagrad_dense", table.data_ptr(), state2.data_ptr(), gtmp.data_ptr(), None, table.numel(), 0.0, 1e-10,
+                   0.0, mp, L.stream_ptr(table))
+
+        cases["tc_bwd_kernel<dTable + Adagrad> (kgeb_fused_bwd_update: dT = G^T*Q applied to W / state / bf16 mirror by "
+              "update warps)"] = (upd, 2, 1, "tc_bwd4_kernel<0, 0, 0, 0, 0, 1>")
+        try:
+            state2 = torch.full_like(gtmp, 0.1)
+            cases["kgeb_adagrad_dense (separate pass, for comparison: not part of the step)"] = (adagrad, 0, 0, "adagrad_dense_kernel")
+        except torch.OutOfMemoryError:
+            pass
     res = {}
     for name, (fn, executed, algorithmic, _) in cases.items():
         ts = []
@@ -243,7 +267,9 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
             if i >= 2:
                 ts.append(a.elapsed_time(b))
         res[name] = float(np.mean(ts))
-    name = max(res, key=res.get)
+    in_step = {k: v for k, v in res.items() if "for comparison" not in k and not (getattr(st, "fuse_update", False) and
+                                                                                   "dTable>" in k)}
+    name = max(in_step, key=in_step.get)
     ms = res[name]
     gemm = 2.0 * rows * n_ent * d
     achieved = cases[name][2] * gemm / (ms * 1e-3) / 1e12
@@ -253,7 +279,8 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
     traffic = None
     path = os.path.join(ROOT, "profiles", "ncu_full_latest_summary.json")
     if os.path.exists(path):
-        k = json.load(open(path)).get("wd5m " + cases[name][3])
+        summ = json.load(open(path))
+        k = summ.get("wd5m " + cases[name][3]) or summ.get("wd5m " + cases[name][3].replace(", 0>", ">"))
         if k:
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
@@ -262,7 +289,8 @@ def kernel_roofline(kb, st, rows, n_ent, step_ms, world):
             "step": {"achieved": step_achieved, "peak": pk["bf16_sustained"], "frac": step_achieved / pk["bf16_sustained"],
                      "unit": "TFLOP/s per GPU", "flops_per_triple": 12.0 * E * DIM},
             "note": ("achieved = ALGORITHMIC FLOPs of the launch (one GEMM of 2*rows*E*d: the score tile a backward kernel "
-                     "recomputes is not counted; executed_tflops counts it) / CUDA-event time of the kernel run alone incl. "
+                     "recomputes is not counted; executed_tflops counts it; the Adagrad update the dTable kernel applies -- "
+                     "9 bytes read + 9 written per table element -- is not counted either) / CUDA-event time of the kernel run alone incl. "
                      "its bf16(Q) / reduce helpers; peak = %s dense bf16 burst.  step = 12*E*d FLOP per triple / step time "
                      "(per GPU) against the sustained bf16 figure.  rows = %d, shard entities = %d" % (pk["source"], rows, n_ent)),
             "all_ms": res}

@@ -87,29 +87,39 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.proc, self.lines, self.index = None, [], index
+        self.proc, self.lines, self.index, self.n0 = None, [], index, 0
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
 
     def __enter__(self):
         self.t_enter = time.time()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
+            # nvidia-smi needs a few hundred ms before its first line: wait for it HERE (before the timed region), so that a
+            # region of ~0.1 s is sampled too; lines from before the region are not used unless nothing else arrived
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.01)
+            self.n0 = len(self.lines)
         except Exception:
             self.proc = None
         return self
 
     def __exit__(self, *a):
         if self.proc is not None:
-            time.sleep(0.25)
+            time.sleep(0.06)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in (self.lines[self.n0:] or self.lines):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6 or not f[0].isdigit():
                 continue

@@ -123,6 +123,43 @@ int kgeb_fused_label_rows(int loss, const float* Q, int64_t B, int d, const floa
                           float label_smoothing, float inv_batch, const float* grad_scale, float* dTable_out,
                           void* workspace, int64_t workspace_bytes, void* stream);
 
+/* kgeb_fused_label_rows with entry i routed to dense_out[out_rows[i]] ([n_out, d]) instead of dense_out[entity - e_lo]
+ * (lab_perm, when given, must keep equal out_rows values contiguous: true for slots numbered in entity order). */
+int kgeb_fused_label_rows_to(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
+                             const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const int32_t* lab_perm,
+                             float label_smoothing, float inv_batch, const float* grad_scale, const int64_t* out_rows,
+                             int64_t n_out, float* dense_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- optimizer.step() inside the table-gradient kernel (train.py:323 backward + :375 optimizer.step for the entity table).
+ * For an [E, d] table the dense gradient G^T Q is as large as the table; storing it and reading it back in an Adagrad pass
+ * costs 2 x E*d*4 bytes of HBM traffic per step.  A CTA of the tile kernel that has finished an entity tile holds the
+ * complete dense gradient of its 128 rows in tensor memory and applies Adagrad from there.  Rows that also receive sparse
+ * gradient rows in this step (label rows, query-side rows: <= 8192 ids) are excluded and handled by a row kernel:
+ *   kgeb_touched_build   sorts the ids (ids_a ++ ids_b, global entity ids; those outside [e_lo, e_hi) are ignored), numbers
+ *                        the distinct ones 0..n-1 in ascending order: slot_of[id - e_lo] = slot (the caller keeps slot_of
+ *                        [e_hi - e_lo] at -1 between steps), uniq_rows[slot] = id - e_lo, *num_uniq = n, and
+ *                        slot_a[i] / slot_b[i] = slot of position i (n_a + n_b = the dummy slot for ids of other shards);
+ *   kgeb_fused_bwd_update  the dense part (bf16 tiles, KGEB_LOSS_*; arguments as kgeb_fused_bwd): slot_of[row] < 0 ->
+ *                        Adagrad on W / state / bf16 mirror in the flush; else the row goes to gbuf[slot];
+ *   (the caller scatters its sparse rows into g_sparse [n_a + n_b + 1, d] by slot: kgeb_fused_label_rows_to,
+ *    kgeb_scatter_add_rows[_perm] with slot_a as the index)
+ *   kgeb_touched_update  Adagrad on the touched rows with gbuf[slot] + g_sparse[slot]; clears g_sparse and slot_of again.
+ * skip_flag (optional device word): non-zero = neither kernel changes W, the state or the mirror (failed flash pass).
+ * The arithmetic is kgeb_adagrad_dense's, operation for operation (weight_decay = 0). */
+int kgeb_touched_capacity(void);
+int kgeb_touched_build(const int64_t* ids_a, int64_t n_a, const int64_t* ids_b, int64_t n_b,
+                       const int64_t* n_b_real /* device: ids_b past this count are padding (slot 0, not touched); or NULL */,
+                       int64_t e_lo, int64_t e_hi, int32_t* slot_of, int64_t* uniq_rows, int64_t* num_uniq, int64_t* slot_a,
+                       int64_t* slot_b, void* stream);
+int kgeb_fused_bwd_update(int loss, const float* Q, int64_t B, int d, float* table, int64_t e_lo, int64_t e_hi,
+                          int64_t num_entities, const int64_t* lab_off, float label_smoothing, float offset,
+                          const float* lse, float inv_batch, const float* grad_scale, void* table_bf16, float* state,
+                          float clr, float eps, const int32_t* slot_of, float* gbuf, const int32_t* skip_flag,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int kgeb_touched_update(float* W, float* state, void* bf16_mirror, int32_t* slot_of, const int64_t* uniq_rows,
+                        const int64_t* num_uniq, int64_t capacity /* n_a + n_b */, const float* g_dense, float* g_sparse,
+                        int d, float clr, float eps, const int32_t* skip_flag, void* stream);
+
 /* ---- K4+K8+K9 fused all-entity training (DOT kinds): scores are never materialised.
  * Labels are a CSR over the batch rows: lab_off[B+1] (int64), lab_col[nnz] (int64, ascending within a
  * row, entity ids).  For 1vsAll each row has exactly one label.  Targets t_ij:

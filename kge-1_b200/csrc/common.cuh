@@ -57,6 +57,17 @@ __device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f 
 
 constexpr int kNumSMs = 148;  // B200
 
+// Adagrad applied by the flush of the dense table-gradient tile kernel (kgeb_fused_bwd_update; tc_bwd.cu)
+struct TableUpdate {
+  float* w;                 // [n_ent, d] fp32 master rows of the shard
+  float* state;             // [n_ent, d] Adagrad sum of squares
+  void* mirror;             // [n_ent, d] bf16 mirror (= the tile operand)
+  const int32_t* slot_of;   // [n_ent]: >= 0 = row also gets sparse gradient rows this step: parked in gbuf[slot]
+  float* gbuf;              // [slots, d]
+  const int* skip;          // optional device word: non-zero = abandon the step, touch nothing
+  float clr, eps;
+};
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace kgeb

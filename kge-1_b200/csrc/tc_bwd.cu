@@ -84,6 +84,19 @@ struct Params {
   int* status;             // FLASH: set to 1 when a row sum or an accumulator entry is not finite (reference too low)
   const float* colk;       // !RES_IS_Q, KL: [colk_n] exponent offsets (log(rs_q) - lse_q) * log2(e) per streamed (query) row,
   int colk_n;              //   padded with zeros to a multiple of 64; staged in shared memory by the v2 kernel (0 = unused)
+  int colk_n_alloc;        //   floats reserved for it in shared memory (colk_n may be reset to 0 for BCE)
+  // !RES_IS_Q, v2: Adagrad in the flush (kgeb_fused_bwd_update).  A finished entity tile holds the COMPLETE dense gradient of
+  // its 128 rows; rows that also receive sparse gradient rows this step (upd_slot[row] >= 0) are parked in upd_gbuf[slot]
+  // for the row kernel that follows, every other row is updated in place: W, state and the bf16 mirror.
+  float* upd_w;            // [n_res, d] fp32 master rows (NULL = no fused update)
+  float* upd_state;        // [n_res, d] Adagrad sum of squares
+  __nv_bfloat16* upd_mirror;   // [n_res, d] = the resident operand of this kernel (each tile is read once, before its flush)
+  const int32_t* upd_slot; // [n_res]
+  float* upd_gbuf;         // [slots, d]
+  const int* upd_skip;     // non-zero word: the step is being abandoned (failed flash pass) -- touch nothing
+  float upd_clr, upd_eps;
+  int stagger_clk;         // fused update: CTA b starts b * stagger_clk clocks late (see the producer warp of the v2 kernel)
+  int upd_debug;           // tuning only (KGEB_UPD_DEBUG): 1 = no loads of W / state, 2 = no stores, 4 = no arithmetic, 8 = no prefetch, 16 = no phase 2
 };
 
 // Per-row state of an epilogue thread over one job (one resident row = one TMEM lane).
@@ -578,8 +591,26 @@ tc_bwd_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 constexpr int NG = 4;   // tiles in flight = S/G buffers = epilogue groups
 
-template <bool RES_IS_Q, int LOSS, bool HAS_RS, bool STATS, bool FLASH = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// Register split of the 768-thread fused-update kernel.  The pool is what the CTA got at launch (768 x 80 = 61440): the
+// epilogue warps can only grow by what the other two warpgroups release, 128 c + 512 e + 128 u <= 61440.  (A first version
+// asked for 40 / 96 / 72 = 63488: the fourth epilogue warpgroup waited for registers forever.)
+#ifndef KGEB_UPD_REG_CTRL
+#define KGEB_UPD_REG_CTRL 40
+#define KGEB_UPD_REG_EPI 88
+#define KGEB_UPD_REG_UPD 88
+#endif
+static_assert(128 * KGEB_UPD_REG_CTRL + 512 * KGEB_UPD_REG_EPI + 128 * KGEB_UPD_REG_UPD <= 768 * 80, "register pool of the CTA");
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr int UPD_THREADS = 128;   // fused update: one more warpgroup, warp 20 + p applies Adagrad to the box of column part p
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <bool RES_IS_Q, int LOSS, bool HAS_RS, bool STATS, bool FLASH = false, bool UPD = false>
+__global__ void __launch_bounds__(NUM_THREADS + (UPD ? UPD_THREADS : 0), 1)
 tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_str,
                const __grid_constant__ CUtensorMap tm_out, const Params p) {
   static_assert(STR_ROWS == 64, "the v2 pipeline is laid out for 64-row streamed tiles");
@@ -605,11 +636,14 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
   uint64_t* o_empty = o_full + 1;               // epilogue flushed -> MMA2
   uint64_t* a_full = o_empty + 1;               // a_tmem: epilogue copied the resident block to tensor memory -> MMA1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+  uint64_t* stage_full = a_full + 2;            // UPD [EPQ]: the part's epilogue warps staged the gradient box -> update warp
+  uint64_t* stage_free = stage_full + EPQ;      // UPD [EPQ]: update warp has consumed the staging box (and its slots)
   // !RES_IS_Q, KL: the per-query exponent offsets of ALL streamed rows (the same for every job), 16-byte aligned
   float* kc_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
   const float* kc_s = (!RES_IS_Q && LOSS == KGEB_LOSS_KL && p.colk_n > 0) ? kc_smem : nullptr;
   if (kc_s)
-    for (int i = threadIdx.x; i < p.colk_n; i += NUM_THREADS) kc_smem[i] = p.colk[i];
+    for (int i = threadIdx.x; i < p.colk_n; i += blockDim.x) kc_smem[i] = p.colk[i];
+  int32_t* slot_s = reinterpret_cast<int32_t*>(kc_smem + p.colk_n_alloc);   // !RES_IS_Q: [EPQ][RES_ROWS] (fused update)
   constexpr int TMEM_COLS = 512;
   constexpr uint32_t S_COL = 0;                 // NG S buffers of 64 columns; G aliases the first 32 columns of each
   constexpr uint32_t O_COL = NG * STR_ROWS;     // OUT accumulator: d <= 256 columns behind them
@@ -640,6 +674,11 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
     }
     mbar_init(o_full, 1);
     mbar_init(o_empty, NUM_EPI_THREADS / 32);
+    if (UPD)
+      for (int b = 0; b < EPQ; ++b) {
+        mbar_init(&stage_full[b], 4);
+        mbar_init(&stage_free[b], 1);
+      }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -649,11 +688,22 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const int64_t n_jobs = p.n_res_blocks * p.chunks;
 
+  // UPD: 768 threads start with 80 registers each; the control warpgroup (warps 0-3) and the update warpgroup hand part of
+  // theirs to the epilogue warps (setmaxnreg at the top of every role branch, so that it dominates the role's code)
   if (warp == 0) {
+    if (UPD) setmaxnreg_dec<KGEB_UPD_REG_CTRL>();
     // ================================ TMA producer ================================
     if (elect_one()) {
       int slot = 0;
       uint32_t phase = 0, rphase = 0;
+      if (UPD && p.stagger_clk > 0) {
+        // Fused update: all CTAs run jobs of the same length, so without this their flushes -- 288 KB of HBM traffic each at
+        // d = 128 -- coincide: 43 MB bursts that take 7 us while HBM idles for the rest of the ~16 us job (measured: the
+        // kernel 2.3 ms longer than without the update).  Spreading the CTAs' phases over one job period keeps the update
+        // traffic continuous; the data-dependent pipeline behind this warp inherits the delay.
+        const long long t0 = clock64(), wait = (long long)blockIdx.x * p.stagger_clk;
+        while (clock64() - t0 < wait) __nanosleep(100);
+      }
       for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         const int64_t rb = job % p.n_res_blocks, ch = job / p.n_res_blocks;
         mbar_wait(res_empty, rphase ^ 1);
@@ -673,6 +723,7 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
       }
     }
   } else if (warp == 1) {
+    if (UPD) setmaxnreg_dec<KGEB_UPD_REG_CTRL>();
     // ================================ MMA1 issuer: S = RES * STR^T ================================
     if (elect_one()) {   // one elected thread for the whole loop: descriptors stay in uniform registers
       const uint32_t idesc1 = make_idesc(RES_ROWS, STR_ROWS, 0, 0, Elem<BF16>::kFmt);  // (K-major, K-major)
@@ -716,7 +767,10 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
         if (!a_tmem) umma_commit(res_empty);   // all MMA1 of the job issued before this commit have read the resident block
       }
     }
+  } else if (warp == 2) {
+    if (UPD) setmaxnreg_dec<KGEB_UPD_REG_CTRL>();
   } else if (warp == 3) {
+    if (UPD) setmaxnreg_dec<KGEB_UPD_REG_CTRL>();
     // ================================ MMA2 issuer: OUT += G * STR  (A = G from tensor memory) ================================
     if (elect_one()) {
       const uint32_t idesc2 = make_idesc(RES_ROWS, p.d, 0, 1, Elem<BF16>::kFmt);       // (K-major, MN-major)
@@ -752,7 +806,79 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
         ophase ^= 1;
       }
     }
+  } else if (UPD && warp >= 4 + 4 * EPQ) {
+    // ================================ update warp of column part `part` ================================
+    // Adagrad on the gradient box the part's epilogue warps staged in shared memory (128 rows x 32 columns, 128-byte
+    // swizzle): a warp instruction covers 4 rows x 128 contiguous bytes of W / state.  Runs beside the next job's tiles:
+    // measured inside the epilogue warps (which the MUFU-bound tile loop needs), the same code added 1.6 ms to a 4.0 ms kernel.
+    if (KGEB_UPD_REG_UPD >= 80) setmaxnreg_inc<KGEB_UPD_REG_UPD>(); else setmaxnreg_dec<KGEB_UPD_REG_UPD>();
+    const int part = warp - (4 + 4 * EPQ);
+    const int sub = lane >> 3, ck = lane & 7;   // row within a group of 4, 16-byte chunk of the 128-byte box row
+    const bool live = p.upd_skip == nullptr || __ldg(p.upd_skip) == 0;
+    const int nbox = (p.d + 31) / 32;
+    uint8_t* stage = stage_smem + (size_t)part * STAGE_BYTES;
+    uint32_t fphase = 0;
+    for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+      const int64_t rb = job % p.n_res_blocks;
+      for (int box = part; box < nbox; box += EPQ) {
+        mbar_wait(&stage_full[part], fphase);
+        fphase ^= 1;
+        const int col = box * 32 + ck * 4;
+        if (live && col < p.d && !(p.upd_debug & 16)) {
+#pragma unroll 1
+          for (int it = 0; it < 4; ++it) {
+            // 8 rows per round: 16 loads of 16 bytes in flight per lane (the warp has ~16 us per box and pays ~1 us of
+            // latency per round); the gradient and the slot are re-read from shared memory where they are consumed
+            float4 w8[8], s8[8];
+            const int r0 = it * 32 + sub;                                  // rows r0 + 4 i of the box
+            const size_t base = ((size_t)rb * RES_ROWS + r0) * p.d + col;  // element offset of row r0
+            const int64_t left = p.n_res - (rb * RES_ROWS + r0);           // row r0 + 4 i exists iff 4 i < left
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int sl = 4 * i < left ? slot_s[part * RES_ROWS + r0 + 4 * i] : -2;
+              if (sl == -1 && !(p.upd_debug & 1)) {
+                w8[i] = *reinterpret_cast<const float4*>(p.upd_w + base + (size_t)(4 * i) * p.d);
+                s8[i] = *reinterpret_cast<const float4*>(p.upd_state + base + (size_t)(4 * i) * p.d);
+              } else {
+                w8[i] = s8[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = r0 + 4 * i;
+              const int sl = 4 * i < left ? slot_s[part * RES_ROWS + r] : -2;
+              if (sl == -2) continue;
+              const float4 g = *reinterpret_cast<const float4*>(stage + (size_t)r * 128 + ((ck ^ (r & 7)) << 4));
+              if (sl >= 0) {
+                *reinterpret_cast<float4*>(p.upd_gbuf + (size_t)sl * p.d + col) = g;
+                continue;
+              }
+              // Adagrad with MUFU square root and reciprocal (sqrt.approx, rcp.approx: the update term is within ~3 ulp of
+              // adagrad_dense_kernel's IEEE sqrt / division, i.e. ~1e-7 * |dw|).  The IEEE sequences are ~45 instructions
+              // per element; this warp shares its scheduler with four epilogue warps that already use ~80 % of the issue
+              // slots, and with them the update warp fell behind the tile pipeline (kernel 5.7 instead of 4.1 ms).
+              float4 w = w8[i], st = s8[i];
+              st.x = fmaf(g.x, g.x, st.x); st.y = fmaf(g.y, g.y, st.y); st.z = fmaf(g.z, g.z, st.z); st.w = fmaf(g.w, g.w, st.w);
+              w.x = fmaf(-p.upd_clr * g.x, rcp_approx(sqrt_approx(st.x) + p.upd_eps), w.x);
+              w.y = fmaf(-p.upd_clr * g.y, rcp_approx(sqrt_approx(st.y) + p.upd_eps), w.y);
+              w.z = fmaf(-p.upd_clr * g.z, rcp_approx(sqrt_approx(st.z) + p.upd_eps), w.z);
+              w.w = fmaf(-p.upd_clr * g.w, rcp_approx(sqrt_approx(st.w) + p.upd_eps), w.w);
+              if (p.upd_debug & 2) continue;
+              const size_t off = base + (size_t)(4 * i) * p.d;
+              *reinterpret_cast<float4*>(p.upd_w + off) = w;
+              *reinterpret_cast<float4*>(p.upd_state + off) = st;
+              uint2 mb;
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mb.x) : "f"(w.y), "f"(w.x));
+              asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mb.y) : "f"(w.w), "f"(w.z));
+              *reinterpret_cast<uint2*>(p.upd_mirror + off) = mb;
+            }
+          }
+        }
+        mbar_arrive_warp(&stage_free[part]);      // (all lanes have read the staging box and the slots: __syncwarp inside)
+      }
+    }
   } else if (warp >= 4) {
+    if (UPD) setmaxnreg_inc<KGEB_UPD_REG_EPI>();
     // ================================ epilogue ================================
     const int ew = warp - 4;
     const int quad = ew & 3;                               // == warp % 4 : TMEM lane quadrant this warp may access
@@ -760,7 +886,7 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
     const int trow = quad * 32 + lane;                     // resident row (TMEM lane) of this thread
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t buf_addr = lane_addr + S_COL + (uint32_t)(part * STR_ROWS);
-    uint32_t sph = 0, ophase = 0, aphase = 0;
+    uint32_t sph = 0, ophase = 0, aphase = 0, uphase = 0;
     int64_t gunit = 0;                                     // global tile counter (buffers rotate across jobs too)
     for (int64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
       const int64_t rb = job % p.n_res_blocks, ch = job / p.n_res_blocks;
@@ -772,6 +898,17 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
       } else if (RES_IS_Q && res_row < p.B) {
         er.my_rs = p.inv_batch * (HAS_RS ? p.row_scale[res_row] : 1.f);
         if (LOSS == KGEB_LOSS_KL) er.my_lse = p.lse[res_row];
+      }
+      int upd_slot = 0;
+      if (UPD && res_row < p.n_res) {
+        // fused update: the slot of this thread's row (consumed at the flush: the load stays in flight under the job), and
+        // the row's lines of W and of the Adagrad state pulled into L2 -- they are wanted ~15 us from now
+        upd_slot = __ldg(p.upd_slot + res_row);
+        if (!(p.upd_debug & 8))
+        for (int box = part; box * 32 < p.d; box += EPQ) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.upd_w + (size_t)res_row * p.d + box * 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.upd_state + (size_t)res_row * p.d + box * 32));
+        }
       }
       if (a_tmem && part < a_groups) {
         // resident block: shared memory (TMA, 128-byte swizzle) -> tensor memory columns [A_COL + 16 part, + 16) of this
@@ -839,6 +976,7 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
       mbar_wait(o_full, ophase);
       ophase ^= 1;
       tc_fence_after();
+      bool o_released = false;
       if (RES_IS_Q) {
         for (int c0 = part * 16; c0 < p.d; c0 += 16 * EPQ) {
           float o[16];
@@ -852,6 +990,32 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
               if (FLASH) big = fmaxf(fmaxf(big, fmaxf(fabsf(o[c]), fabsf(o[c + 1]))), fmaxf(fabsf(o[c + 2]), fabsf(o[c + 3])));
             }
             if (FLASH && !(big <= 3.0e38f)) *p.status = 1;   // inf or NaN in the accumulator
+          }
+        }
+      } else if (UPD) {
+        // Adagrad by the update warp of this column part: stage the accumulator box (128 rows x 32 columns) and the rows'
+        // slots in shared memory and hand them over; the tensor-memory accumulator is free as soon as it has been read
+        uint8_t* stage = stage_smem + (size_t)part * STAGE_BYTES;
+        const int nbox = (p.d + 31) / 32;
+        for (int box = part; box < nbox; box += EPQ) {
+          mbar_wait(&stage_free[part], uphase ^ 1);      // the update warp is done with the previous box
+          uphase ^= 1;
+          slot_s[part * RES_ROWS + trow] = upd_slot;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float o[16];
+            tmem_ld16(lane_addr + O_COL + (uint32_t)(box * 32 + h * 16), o);
+            uint8_t* rowp = stage + (size_t)trow * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(rowp + (((h * 4 + j) ^ (trow & 7)) << 4)) =
+                  make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          mbar_arrive_warp(&stage_full[part]);
+          if (box + EPQ >= nbox) {     // the accumulator has been read: MMA2 of the next job may start
+            tc_fence_before();
+            mbar_arrive_warp(o_empty);
+            o_released = true;
           }
         }
       } else {
@@ -880,8 +1044,10 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive_warp(o_empty);
+      if (!o_released) {
+        tc_fence_before();
+        mbar_arrive_warp(o_empty);
+      }
     }
   }
 
@@ -1021,7 +1187,9 @@ static Plan make_plan(bool res_is_q, bool bf16, int64_t B, int d, int64_t n_ent)
   // all streamed rows (KL; up to 4096 rows -- larger batches use the shuffle path)
   const int64_t colk_n = (!res_is_q && use_v2() && bf16 && B <= 4096) ? ((B + 63) / 64) * 64 : 0;
   p.colk_n = (int)colk_n;
-  const size_t fixed = 1024 + 512 + (size_t)colk_n * 4;
+  p.colk_n_alloc = (int)colk_n;
+  // (+ 2 KiB: the touched-row slots of the tile, one copy per column part, for the fused update)
+  const size_t fixed = 1024 + 512 + (size_t)colk_n * 4 + (res_is_q ? 0 : (size_t)EPQ * RES_ROWS * 4);
   const size_t g_bytes = (use_v2() && bf16) ? 0 : (size_t)(STR_ROWS / slab_k) * RES_SLAB;   // v2: G lives in tensor memory
   const size_t base = (size_t)p.ks * RES_SLAB + 2 * g_bytes + (res_is_q ? 0 : (size_t)EPQ * STAGE_BYTES);
   int nstr = (int)((SMEM_BUDGET - fixed - base) / ((size_t)p.ks * STR_SLAB));
@@ -1066,7 +1234,23 @@ static int launch_bwd(const Plan& pl, const CUtensorMap& m_res, const CUtensorMa
     e = cudaLaunchKernelEx(&cfg, tc_bwd4_kernel<RES_IS_Q, LOSS_, RS_, ST_, FL_>, m_res, m_str, m_out, pl.p);           \
     if (e != cudaSuccess) return cuda_status(e, "tc_bwd4 launch");                                                    \
   }
-    if (flash) {
+    if (!RES_IS_Q && pl.p.upd_w != nullptr) {
+      cfg.blockDim = dim3(NUM_THREADS + UPD_THREADS);
+#define KGEB_UPD_LAUNCH(LOSS_, RS_)                                                                                   \
+  {                                                                                                                   \
+    e = cudaFuncSetAttribute(tc_bwd4_kernel<false, LOSS_, RS_, false, false, true>,                                   \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);                              \
+    if (e != cudaSuccess) return cuda_status(e, "tc_bwd4 smem attribute");                                            \
+    e = cudaLaunchKernelEx(&cfg, tc_bwd4_kernel<false, LOSS_, RS_, false, false, true>, m_res, m_str, m_out, pl.p);    \
+    if (e != cudaSuccess) return cuda_status(e, "tc_bwd4 launch");                                                    \
+  }
+      if (pl.p.loss == KGEB_LOSS_KL) {
+        if (rs) KGEB_UPD_LAUNCH(KGEB_LOSS_KL, true) else KGEB_UPD_LAUNCH(KGEB_LOSS_KL, false)
+      } else {
+        if (rs) KGEB_UPD_LAUNCH(KGEB_LOSS_BCE, true) else KGEB_UPD_LAUNCH(KGEB_LOSS_BCE, false)
+      }
+#undef KGEB_UPD_LAUNCH
+    } else if (flash) {
       KGEB_BWD4_LAUNCH(KGEB_LOSS_KL, false, false, RES_IS_Q)
     } else if (pl.p.loss == KGEB_LOSS_KL) {
       if (rs) KGEB_BWD4_LAUNCH(KGEB_LOSS_KL, true, false, false) else KGEB_BWD4_LAUNCH(KGEB_LOSS_KL, false, false, false)
@@ -1319,8 +1503,14 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                  const int32_t* lab_perm, const float* tscale, float ls_add, float offset, const float* lse,
                  float inv_batch, const float* row_scale, float* dQ, float* dTable, float* rowstat_out, int flags,
-                 void* ws, int64_t ws_bytes, cudaStream_t st) {
+                 void* ws, int64_t ws_bytes, cudaStream_t st, const TableUpdate* upd) {
   using namespace tcb;
+  if (upd) {
+    KGEB_REQUIRE(!dQ && !dTable && nnz == 0, "fused_bwd_update: dense table part only (label rows go through kgeb_fused_label_rows_to)");
+    KGEB_REQUIRE(use_v2(), "fused_bwd_update: needs the v2 tile kernel (KGEB_BWD_V2=0 is set)");
+    KGEB_REQUIRE(upd->w && upd->state && upd->mirror && upd->slot_of && upd->gbuf, "fused_bwd_update: NULL buffer");
+    KGEB_REQUIRE(upd->mirror == tableb, "fused_bwd_update: the mirror to update must be the tile operand");
+  }
   // KGEB_BWD_OVERWRITE_TABLE: the dense part is stored into dTable (no cleared buffer needed, no RMW); the label rows
   // are then scattered in AFTER the tile kernel instead of before it
   const bool overwrite = dTable && (flags & KGEB_BWD_OVERWRITE_TABLE);
@@ -1409,12 +1599,22 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       cudaError_t e = cudaStreamWaitEvent(st, ss->join, 0);
       if (e != cudaSuccess) return cuda_status(e, "fused_bwd join wait");
     }
-    if (dTable) {
+    if (dTable || upd) {
       Plan pl = make_plan(false, true, B, d, n_ent);
       if (pl.p.nstr < 2) { set_error("fused_bwd(bf16): not enough shared memory for dim %d", d); return KGEB_ERR_UNSUPPORTED; }
       pl.p.loss = loss; pl.p.offset = offset; pl.p.ls_add = ls_add; pl.p.inv_batch = inv_batch;
       pl.p.lse = lse; pl.p.row_scale = row_scale; pl.p.out = dTable;
       pl.p.overwrite = overwrite ? 1 : 0;
+      if (upd) {
+        pl.p.upd_w = upd->w; pl.p.upd_state = upd->state; pl.p.upd_mirror = reinterpret_cast<__nv_bfloat16*>(upd->mirror);
+        pl.p.upd_slot = upd->slot_of; pl.p.upd_gbuf = upd->gbuf; pl.p.upd_skip = upd->skip;
+        pl.p.upd_clr = upd->clr; pl.p.upd_eps = upd->eps;
+        pl.p.upd_debug = getenv("KGEB_UPD_DEBUG") ? atoi(getenv("KGEB_UPD_DEBUG")) : 0;
+        // one job = n_str_tiles tiles of ~1000 clk (measured: 975 at d = 128) + the flush; phases spread over one period
+        static const int stagger_tile_clk = getenv("KGEB_UPD_STAGGER") ? atoi(getenv("KGEB_UPD_STAGGER")) : 1100;
+        const int64_t grid = pl.p.n_res_blocks < kNumSMs ? pl.p.n_res_blocks : kNumSMs;
+        pl.p.stagger_clk = pl.p.n_res_blocks > 2 * grid ? (int)(pl.p.n_str_tiles * stagger_tile_clk / grid) : 0;
+      }
       if (loss == KGEB_LOSS_KL && pl.p.colk_n > 0) {
         // (label_dot's slot of the workspace is free in a dTable-only call; with dQ in the same call it is used by the
         // BCE statistics only, never by KL)
@@ -1427,7 +1627,7 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
       }
       CUtensorMap m_out;   // fp32 [n_ent, d], boxes of 32 columns x 128 rows for the reduce-add flush
       if ((rc = make_map(&m_res, tableb, n_ent, d, RES_ROWS, true)) || (rc = make_map(&m_str, Qb, B, d, STR_ROWS, true)) ||
-          (rc = make_map(&m_out, dTable, n_ent, d, RES_ROWS, false)))
+          (rc = make_map(&m_out, upd ? upd->w : dTable, n_ent, d, RES_ROWS, false)))     // (unused by the fused update)
         return rc;
       const int64_t jobs = pl.p.n_res_blocks;
       if ((rc = launch_bwd<false>(pl, m_res, m_str, m_out, jobs, st))) return rc;
@@ -1542,7 +1742,8 @@ int tc_flash_dq(const float* Q, int64_t B, int d, const float* table, int64_t e_
 // rows into a different buffer than the tile kernel's output, so that the tile kernel does not have to wait for them.
 int tc_label_rows(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent, const int64_t* lab_off,
                   const int64_t* lab_col, int64_t nnz, const int32_t* lab_perm, const float* tscale, const float* row_scale,
-                  float inv_batch, float* dense_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                  float inv_batch, float* dense_out, void* ws, int64_t ws_bytes, cudaStream_t st, const int64_t* out_rows,
+                  int64_t n_out) {
   using namespace tcb;
   if (nnz <= 0 || n_ent <= 0 || B <= 0) return KGEB_OK;
   char* wp = reinterpret_cast<char*>(ws);
@@ -1555,8 +1756,12 @@ int tc_label_rows(const float* Q, int64_t B, int d, const float* table, int64_t 
       Q, table, B, d, e_lo, n_ent, lab_off, lab_col, tscale, row_scale, inv_batch, nnz, nullptr, rows_dt, lab_ent, lab_row,
       nullptr, 0.f);
   KGEB_LAUNCH_CHECK("label_entry_rows");
-  return lab_perm ? kgeb_scatter_add_rows_perm(lab_ent, 1, lab_perm, rows_dt, nnz, d, dense_out, n_ent, wp, scatter_bytes, st)
-                  : kgeb_scatter_add_rows(lab_ent, 1, rows_dt, nnz, d, dense_out, n_ent, wp, scatter_bytes, st);
+  // out_rows: the rows go to dense_out[out_rows[i]] ([n_out, d]) instead of dense_out[entity - e_lo]; entries of other
+  // shards carry zero rows either way.  lab_perm must then sort out_rows as well (equal keys contiguous).
+  const int64_t* keys = out_rows ? out_rows : lab_ent;
+  const int64_t vocab = out_rows ? n_out : n_ent;
+  return lab_perm ? kgeb_scatter_add_rows_perm(keys, 1, lab_perm, rows_dt, nnz, d, dense_out, vocab, wp, scatter_bytes, st)
+                  : kgeb_scatter_add_rows(keys, 1, rows_dt, nnz, d, dense_out, vocab, wp, scatter_bytes, st);
 }
 
 int tc_wait_tiles(cudaStream_t st) {

@@ -24,12 +24,13 @@ int tc_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);  // tc_
 int tc_wait_tiles(cudaStream_t st);  // tc_bwd.cu
 int tc_label_rows(const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t n_ent, const int64_t* lab_off,
                   const int64_t* lab_col, int64_t nnz, const int32_t* lab_perm, const float* tscale, const float* row_scale,
-                  float inv_batch, float* dense_out, void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
+                  float inv_batch, float* dense_out, void* ws, int64_t ws_bytes, cudaStream_t st,
+                  const int64_t* out_rows = nullptr, int64_t n_out = 0);  // tc_bwd.cu
 int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb,
                  int64_t e_lo, int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz,
                  const int32_t* lab_perm, const float* tscale, float ls_add, float offset, const float* lse,
                  float inv_batch, const float* row_scale, float* dQ, float* dTable, float* rowstat_out, int flags,
-                 void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
+                 void* ws, int64_t ws_bytes, cudaStream_t st, const TableUpdate* upd = nullptr);  // tc_bwd.cu
 int tc_flash_fwd(const float* Q, const void* Qb, int64_t B, int d, const float* table, const void* tableb, int64_t e_lo,
                  int64_t n_ent, const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, float* rowstat, float* o_sum,
                  int* status, void* ws, int64_t ws_bytes, cudaStream_t st);  // tc_bwd.cu
@@ -860,6 +861,55 @@ int kgeb_fused_label_rows(int loss, const float* Q, int64_t B, int d, const floa
   KGEB_LAUNCH_CHECK("label_weight");
   return tc_label_rows(Q, B, d, table, e_lo, e_hi - e_lo, lab_off, lab_col, nnz, lab_perm, tscale, grad_scale, inv_batch,
                        dTable_out, reinterpret_cast<char*>(workspace) + head, workspace_bytes - head, st);
+}
+
+// kgeb_fused_label_rows with the rows routed to dense_out[out_rows[i]] ([n_out, d]): the sparse half of the fused update
+int kgeb_fused_label_rows_to(int loss, const float* Q, int64_t B, int d, const float* table, int64_t e_lo, int64_t e_hi,
+                             const int64_t* lab_off, const int64_t* lab_col, int64_t nnz, const int32_t* lab_perm,
+                             float label_smoothing, float inv_batch, const float* grad_scale, const int64_t* out_rows,
+                             int64_t n_out, float* dense_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
+  if (rc) return rc;
+  KGEB_REQUIRE(lab_off && lab_col && dense_out && workspace && out_rows && n_out > 0, "fused_label_rows_to: bad arguments");
+  KGEB_REQUIRE(d % 4 == 0, "fused_label_rows_to: entity dim must be a multiple of 4 (got %d)", d);
+  if (B == 0 || nnz == 0) return KGEB_OK;
+  cudaStream_t st = as_stream(stream);
+  const int64_t head = ((B * 4 + 255) / 256) * 256;
+  KGEB_REQUIRE(workspace_bytes > head, "fused_label_rows_to: workspace too small");
+  float* tscale = reinterpret_cast<float*>(workspace);
+  label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, 1.f - label_smoothing, tscale);
+  KGEB_LAUNCH_CHECK("label_weight");
+  return tc_label_rows(Q, B, d, table, e_lo, e_hi - e_lo, lab_off, lab_col, nnz, lab_perm, tscale, grad_scale, inv_batch,
+                       dense_out, reinterpret_cast<char*>(workspace) + head, workspace_bytes - head, st, out_rows, n_out);
+}
+
+// The dense table gradient of kgeb_fused_bwd (bf16 tiles, no label part) with torch.optim.Adagrad.step applied by the
+// tile kernel's flush: rows with slot_of[row] < 0 are updated in place (W, state, bf16 mirror), the others are parked in
+// gbuf[slot] for kgeb_touched_update.  Replaces, for an [E, d] table, a stored gradient buffer and an update pass over it
+// (2 x E*d*4 bytes of HBM traffic and one launch); reference: train.py:375 optimizer.step() after :323 backward().
+int kgeb_fused_bwd_update(int loss, const float* Q, int64_t B, int d, float* table, int64_t e_lo, int64_t e_hi,
+                          int64_t num_entities, const int64_t* lab_off, float label_smoothing, float offset,
+                          const float* lse, float inv_batch, const float* grad_scale, void* table_bf16, float* state,
+                          float clr, float eps, const int32_t* slot_of, float* gbuf, const int32_t* skip_flag,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = check_fused(loss, d, label_smoothing, Q, table, e_lo, e_hi);
+  if (rc) return rc;
+  KGEB_REQUIRE(tc_bwd_supported(KGEB_MATH_BF16, d), "fused_bwd_update: entity dim must be a multiple of 16 and <= 256 (got %d)", d);
+  KGEB_REQUIRE(loss != KGEB_LOSS_KL || lse, "fused_bwd_update: KL needs the per-row log-sum-exp");
+  KGEB_REQUIRE(table_bf16 && state && slot_of && gbuf && lab_off, "fused_bwd_update: NULL buffer");
+  const int64_t n_ent = e_hi - e_lo;
+  if (B == 0 || n_ent == 0) return KGEB_OK;      // zero gradient: Adagrad leaves W and the state as they are
+  cudaStream_t st = as_stream(stream);
+  KGEB_REQUIRE(workspace && workspace_bytes >= kgeb_fused_workspace_bytes(B, d, n_ent, 0), "fused_bwd_update: workspace too small");
+  LossParams lp{loss, 1.f - label_smoothing, label_smoothing > 0.f ? 1.f / (float)num_entities : 0.f, offset, inv_batch};
+  TailWs tail = carve_tail(workspace, workspace_bytes, B, d);
+  label_weight_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(loss, lab_off, B, lp.ls_keep, tail.tscale);
+  KGEB_LAUNCH_CHECK("label_weight");
+  if ((rc = tc_to_bf16(Q, tail.qb, B * (int64_t)d, st))) return rc;
+  TableUpdate upd{table, state, table_bf16, slot_of, gbuf, skip_flag, clr, eps};
+  return tc_fused_bwd(loss, Q, tail.qb, B, d, table, table_bf16, e_lo, n_ent, lab_off, lab_off, 0, nullptr, tail.tscale,
+                      lp.ls_add, offset, lse, inv_batch, grad_scale, nullptr, nullptr, nullptr, 0, workspace, tail.usable, st,
+                      &upd);
 }
 
 int kgeb_fused_bwd(int loss, int math, const float* Q, int64_t B, int d, const float* table, int64_t e_lo,

@@ -500,6 +500,112 @@ static int sort_and_segment(const void* idx, int idx64, int64_t n, int64_t vocab
 }
 
 // ------------------------------------------------------------------------------------------
+// rows touched by the sparse gradient parts of an all-entity step (kgeb_touched_build / kgeb_touched_update)
+// ------------------------------------------------------------------------------------------
+constexpr int kTouchedThreads = 1024, kTouchedItems = 8, kTouchedMax = kTouchedThreads * kTouchedItems;
+
+// One block: sort the <= 8192 ids, number the distinct in-shard ones 0.. in ascending order, publish slot_of[local id] and
+// the slot of every input position (ids of other shards -> the dummy slot `dummy`).
+__global__ void __launch_bounds__(kTouchedThreads, 1)
+touched_build_kernel(const int64_t* __restrict__ ids_a, int n_a, const int64_t* __restrict__ ids_b, int n_b,
+                     const int64_t* __restrict__ n_b_real, int64_t e_lo, int64_t e_hi, int32_t* __restrict__ slot_of,
+                     int64_t* __restrict__ uniq, int64_t* __restrict__ num_uniq, int64_t* __restrict__ slot_a,
+                     int64_t* __restrict__ slot_b, int64_t dummy) {
+  using Sort = cub::BlockRadixSort<unsigned, kTouchedThreads, kTouchedItems>;
+  using Scan = cub::BlockScan<int, kTouchedThreads>;
+  __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
+  __shared__ unsigned last_of[kTouchedThreads];
+  const int t = threadIdx.x, n = n_a + n_b;
+  // positions of ids_b past *n_b_real are padding: not touched; their slot is 0 (a sorted scatter whose permutation
+  // places the padding first, as entity 0, still sees non-decreasing keys; padding entries carry zero rows)
+  const int n_live = n_a + (n_b_real ? (int)min((int64_t)n_b, max((int64_t)0, *n_b_real)) : n_b);
+  unsigned key[kTouchedItems];
+#pragma unroll
+  for (int j = 0; j < kTouchedItems; ++j) {
+    const int i = t * kTouchedItems + j;
+    unsigned k = 0xffffffffu;
+    if (i < n_live) {
+      const int64_t e = (i < n_a ? ids_a[i] : ids_b[i - n_a]);
+      if (e >= e_lo && e < e_hi) k = (unsigned)(e - e_lo);
+    }
+    key[j] = k;
+  }
+  Sort(tmp.sort).Sort(key);        // blocked arrangement: thread t holds the sorted items [8 t, 8 t + 8)
+  last_of[t] = key[kTouchedItems - 1];
+  __syncthreads();
+  const unsigned prev = t == 0 ? 0xffffffffu : last_of[t - 1];
+  int heads = 0;
+  bool head[kTouchedItems];
+#pragma unroll
+  for (int j = 0; j < kTouchedItems; ++j) {
+    const unsigned before = j == 0 ? prev : key[j - 1];
+    head[j] = key[j] != 0xffffffffu && (t * kTouchedItems + j == 0 || key[j] != before);
+    heads += head[j];
+  }
+  int base, total;
+  Scan(tmp.scan).ExclusiveSum(heads, base, total);
+#pragma unroll
+  for (int j = 0; j < kTouchedItems; ++j)
+    if (head[j]) {
+      slot_of[key[j]] = base;
+      uniq[base] = (int64_t)key[j];
+      ++base;
+    }
+  if (t == 0) *num_uniq = total;
+  __threadfence_block();
+  __syncthreads();
+  for (int i = t; i < n; i += kTouchedThreads) {
+    const int64_t e = (i < n_a ? ids_a[i] : ids_b[i - n_a]);
+    const int64_t s = i >= n_live ? 0 : (e >= e_lo && e < e_hi) ? (int64_t)slot_of[e - e_lo] : dummy;
+    if (i < n_a) slot_a[i] = s; else slot_b[i - n_a] = s;
+  }
+}
+
+// Adagrad on the touched rows: gradient = dense part parked by the tile kernel + the summed sparse rows; clears the
+// sparse buffer and the rows' slot_of entries for the next step.  skip != 0: clear only.
+__global__ void touched_update_kernel(float* __restrict__ W, float* __restrict__ state, __nv_bfloat16* __restrict__ mirror,
+                                      int32_t* __restrict__ slot_of, const int64_t* __restrict__ uniq,
+                                      const int64_t* __restrict__ num_uniq, const float* __restrict__ g_dense,
+                                      float* __restrict__ g_sparse, int64_t dummy, int d, float clr, float eps,
+                                      const int* __restrict__ skip) {
+  const int64_t n = *num_uniq;
+  const bool live = skip == nullptr || *skip == 0;
+  const int d4 = d / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n + 1) * d4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t slot = i / d4;
+    const int c = (int)(i - slot * d4) * 4;
+    if (slot == n) {      // the dummy row collects the rows of other shards
+      *reinterpret_cast<float4*>(g_sparse + dummy * d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const int64_t row = uniq[slot];
+    float4* gs = reinterpret_cast<float4*>(g_sparse + slot * d + c);
+    if (live) {
+      float4 g = *reinterpret_cast<const float4*>(g_dense + slot * d + c);
+      const float4 h = *gs;
+      g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+      float4 w = *reinterpret_cast<float4*>(W + row * d + c), s = *reinterpret_cast<float4*>(state + row * d + c);
+      s.x = fmaf(g.x, g.x, s.x); s.y = fmaf(g.y, g.y, s.y); s.z = fmaf(g.z, g.z, s.z); s.w = fmaf(g.w, g.w, s.w);
+      w.x -= clr * g.x / (sqrtf(s.x) + eps);
+      w.y -= clr * g.y / (sqrtf(s.y) + eps);
+      w.z -= clr * g.z / (sqrtf(s.z) + eps);
+      w.w -= clr * g.w / (sqrtf(s.w) + eps);
+      *reinterpret_cast<float4*>(W + row * d + c) = w;
+      *reinterpret_cast<float4*>(state + row * d + c) = s;
+      if (mirror) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(w.x, w.y), b = __floats2bfloat162_rn(w.z, w.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&a);
+        o.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(mirror + row * d + c) = o;
+      }
+    }
+    *gs = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c == 0) slot_of[row] = -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // optimizers
 // ------------------------------------------------------------------------------------------
 __global__ void adagrad_dense_kernel(float* __restrict__ W, float* __restrict__ state, const float* __restrict__ grad,
@@ -662,6 +768,37 @@ int kgeb_segment_reduce_rows(const void* idx, int idx64, const float* rows, int6
   int rc = sort_and_segment(idx, idx64, n, 0, w, num_uniq, st);
   if (rc) return rc;
   return segment_sums<false>(w, n, d, rows, nullptr, 0, uniq_ids, uniq_rows, st);
+}
+
+int kgeb_touched_capacity(void) { return kgeb::kTouchedMax; }
+
+int kgeb_touched_build(const int64_t* ids_a, int64_t n_a, const int64_t* ids_b, int64_t n_b, const int64_t* n_b_real,
+                       int64_t e_lo, int64_t e_hi, int32_t* slot_of, int64_t* uniq_rows, int64_t* num_uniq, int64_t* slot_a,
+                       int64_t* slot_b, void* stream) {
+  KGEB_REQUIRE(n_a >= 0 && n_b >= 0 && n_a + n_b <= kgeb::kTouchedMax, "touched_build: at most %d ids per step (got %lld)",
+               kgeb::kTouchedMax, (long long)(n_a + n_b));
+  KGEB_REQUIRE((n_a == 0 || (ids_a && slot_a)) && (n_b == 0 || (ids_b && slot_b)) && slot_of && uniq_rows && num_uniq &&
+                   e_hi >= e_lo && e_hi - e_lo < ((int64_t)1 << 32) - 1,
+               "touched_build: bad arguments");
+  kgeb::touched_build_kernel<<<1, kgeb::kTouchedThreads, 0, as_stream(stream)>>>(
+      ids_a, (int)n_a, ids_b, (int)n_b, n_b_real, e_lo, e_hi, slot_of, uniq_rows, num_uniq, slot_a, slot_b, n_a + n_b);
+  KGEB_LAUNCH_CHECK("touched_build");
+  return KGEB_OK;
+}
+
+int kgeb_touched_update(float* W, float* state, void* bf16_mirror, int32_t* slot_of, const int64_t* uniq_rows,
+                        const int64_t* num_uniq, int64_t capacity, const float* g_dense, float* g_sparse, int d, float clr,
+                        float eps, const int32_t* skip_flag, void* stream) {
+  KGEB_REQUIRE(W && state && slot_of && uniq_rows && num_uniq && g_dense && g_sparse && capacity > 0 && d > 0 && d % 4 == 0,
+               "touched_update: bad arguments");
+  const int64_t work = (capacity + 1) * (d / 4);
+  int64_t blocks = (work + 255) / 256;
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  kgeb::touched_update_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      W, state, reinterpret_cast<__nv_bfloat16*>(bf16_mirror), slot_of, uniq_rows, num_uniq, g_dense, g_sparse, capacity, d,
+      clr, eps, skip_flag);
+  KGEB_LAUNCH_CHECK("touched_update");
+  return KGEB_OK;
 }
 
 int kgeb_adagrad_dense(float* W, float* state, const float* grad, const float* grad2, int64_t numel, float clr,

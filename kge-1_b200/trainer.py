@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import os
+
 import torch
 
 from . import fused, lib, ops
@@ -103,6 +105,33 @@ class PeerExchange:
             raise RuntimeError("a peer did not arrive at a peer-memory barrier")
 
 
+class _TouchedRows:
+    """Device state of the fused table update (include/kgeb200.h, kgeb_touched_build / kgeb_fused_bwd_update /
+    kgeb_touched_update) for one table shard of `n_rows` rows: the rows that receive sparse gradient rows in a step are
+    numbered (slots), their dense gradient is parked in g_dense, their sparse rows are summed in g_sparse."""
+
+    def __init__(self, n_rows: int, cap: int, d: int, n_a: int, n_b: int, dev):
+        self.cap, self.d = cap, d
+        self.slot_of = torch.full((max(n_rows, 1),), -1, dtype=torch.int32, device=dev)
+        self.uniq = torch.zeros(cap, dtype=torch.int64, device=dev)
+        self.num = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.slot_a = torch.zeros(n_a, dtype=torch.int64, device=dev)
+        self.slot_b = torch.zeros(n_b, dtype=torch.int64, device=dev)
+        self.g_dense = torch.zeros(cap, d, dtype=torch.float32, device=dev)
+        self.g_sparse = torch.zeros(cap + 1, d, dtype=torch.float32, device=dev)      # last row: rows of other shards
+
+    def build(self, ids_a, ids_b, n_b_real, e_lo: int, e_hi: int, stream):
+        assert ids_a.numel() + ids_b.numel() == self.cap
+        lib.call("kgeb_touched_build", ids_a.data_ptr(), ids_a.numel(), ids_b.data_ptr(), ids_b.numel(),
+                 None if n_b_real is None else n_b_real.data_ptr(), e_lo, e_hi, self.slot_of.data_ptr(), self.uniq.data_ptr(),
+                 self.num.data_ptr(), self.slot_a.data_ptr(), self.slot_b.data_ptr(), stream)
+
+    def update(self, w, state, mirror, lr: float, eps: float, skip, stream):
+        lib.call("kgeb_touched_update", w.data_ptr(), state.data_ptr(), None if mirror is None else mirror.data_ptr(),
+                 self.slot_of.data_ptr(), self.uniq.data_ptr(), self.num.data_ptr(), self.cap, self.g_dense.data_ptr(),
+                 self.g_sparse.data_ptr(), self.d, lr, eps, None if skip is None else skip.data_ptr(), stream)
+
+
 class FusedAllEntityStepper:
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
@@ -168,18 +197,32 @@ class FusedAllEntityStepper:
         self.seq = (math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256 and dp_group is None
                     and not (shard is not None and shard.distributed) and self.pen is None and nnz_max > 0
                     and n_e * 4 >= (64 << 20))
+        # ... and NO gradient buffer at all when the step's sparse rows fit the touched-row machinery: Adagrad runs in the
+        # flush of the dTable tile kernel (kgeb_fused_bwd_update), the <= 8192 rows that also get label / query-side rows
+        # are parked and updated by a row kernel.  Saves the store and the read-back of an [E, d] gradient per step.
+        self.fuse_update = (self.seq and rows + max(nnz_max, 1) <= lib.load().kgeb_touched_capacity()
+                            and os.environ.get("KGEB_NO_FUSED_UPDATE", "0") in ("", "0"))
         if dp_group is not None and dp_p2p:
             self._setup_p2p(dp_group, n_e, n_r, dev)      # gradients live in peer-mapped (symmetric) memory
+        elif self.fuse_update:
+            self.gflat = torch.zeros(n_r + 1, **f32)
         elif self.seq:
             self.gflat = torch.zeros(n_e + n_r + 1, **f32)
         else:
             self.gflat = torch.zeros(2 * n_e + n_r + 1, **f32)
-        g0 = 0 if self.seq else n_e
-        self.g_q = self.gflat[:n_e].view(self.E, self.d)              # query-side rows (da scattered by entity id)
-        self.g_ent = self.gflat[g0:g0 + n_e].view(self.E, self.d)     # dense part (G^T Q) + label rows (side stream)
-        self.g_rel = self.gflat[g0 + n_e:g0 + n_e + n_r].view(self.rel.shape[0], self.dr)
-        self.loss = self.gflat[g0 + n_e + n_r:].view(())
-        self.dp_flat = self.gflat[n_e:]                               # what the replicas exchange
+        if self.fuse_update:
+            cap = rows + max(nnz_max, 1)
+            self.touched = _TouchedRows(self.E, cap, self.d, rows, max(nnz_max, 1), dev)
+            self.g_q = self.g_ent = None
+            self.g_rel = self.gflat[:n_r].view(self.rel.shape[0], self.dr)
+            self.loss = self.gflat[n_r:].view(())
+        else:
+            g0 = 0 if self.seq else n_e
+            self.g_q = self.gflat[:n_e].view(self.E, self.d)              # query-side rows (da scattered by entity id)
+            self.g_ent = self.gflat[g0:g0 + n_e].view(self.E, self.d)     # dense part (G^T Q) + label rows (side stream)
+            self.g_rel = self.gflat[g0 + n_e:g0 + n_e + n_r].view(self.rel.shape[0], self.dr)
+            self.loss = self.gflat[g0 + n_e + n_r:].view(())
+            self.dp_flat = self.gflat[n_e:]                               # what the replicas exchange
         self.rowstat = torch.empty(rows, 4, **f32)
         # KL on the bf16 tiles: forward statistics and dQ from ONE table pass (kgeb_fused_flash_fwd / _dq)
         # (single GPU, no folded penalty: a failed flash pass is undone by clearing the gradients -- Adagrad is then a no-op --
@@ -251,7 +294,10 @@ class FusedAllEntityStepper:
         cur = torch.cuda.current_stream()
         self.side2.wait_stream(cur)
         with torch.cuda.stream(self.side2):
-            if self.seq:
+            if self.fuse_update:
+                self.gflat.zero_()                        # relation gradient + loss
+                self.touched.build(self.a_idx, self.lab_col, self.lab_off[self.rows:], 0, self.E, lib.stream_ptr(self.ent))
+            elif self.seq:
                 self.gflat[self.E * self.d:].zero_()      # relation gradient + loss only
             else:
                 self.gflat.zero_()
@@ -316,7 +362,9 @@ class FusedAllEntityStepper:
             split = self._split_label_rows()
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.ev_q)
-                if split:
+                if split and self.fuse_update:
+                    self._dense_update(lse)
+                elif split:
                     dense = list(common)
                     dense[11], dense[12] = 0, None          # nnz, lab_perm: label rows are scattered separately
                     if not self.seq:
@@ -344,11 +392,14 @@ class FusedAllEntityStepper:
             dense[11], dense[12] = 0, None          # nnz, lab_perm
             with torch.cuda.stream(self.side):
                 lib.call("kgeb_fused_bwd_wait_tiles", lib.stream_ptr(self.ent))   # the dQ tile kernel, not its reductions
-                if not self.seq:
-                    self.side.wait_event(self.ev_clear)
-                lib.call("kgeb_fused_bwd", *dense, None, self.g_ent.data_ptr(), None,
-                         lib.BWD_OVERWRITE_TABLE if self.seq else 0, self.ws3.data_ptr(), self.ws3.numel(),
-                         lib.stream_ptr(self.ent))
+                if self.fuse_update:
+                    self._dense_update(lse)
+                else:
+                    if not self.seq:
+                        self.side.wait_event(self.ev_clear)
+                    lib.call("kgeb_fused_bwd", *dense, None, self.g_ent.data_ptr(), None,
+                             lib.BWD_OVERWRITE_TABLE if self.seq else 0, self.ws3.data_ptr(), self.ws3.numel(),
+                             lib.stream_ptr(self.ent))
             return
         self.side.wait_stream(cur)
         if not sh.distributed:
@@ -360,6 +411,18 @@ class FusedAllEntityStepper:
                  0, self.ws.data_ptr(), self.ws.numel(), st)
         if sh.distributed:
             self._join_side()     # the collectives that follow need the complete dense gradient
+
+    def _dense_update(self, lse):
+        """(current stream = the dTable stream) Dense table gradient + Adagrad in the tile kernel's flush.  Reads of the fp32
+        table that run beside it -- query backward, label rows of dQ -- touch only rows of the touched set, which this kernel
+        leaves alone."""
+        self.side.wait_event(self.ev_clear)           # slot_of is built on the third stream
+        t = self.touched
+        lib.call("kgeb_fused_bwd_update", self.loss_kind, self.Q.data_ptr(), self.rows, self.d, self.ent.detach().data_ptr(), 0,
+                 self.E, self.E, self.lab_off.data_ptr(), self.ls, self.offset, lse, 1.0 / self.global_batch, None,
+                 self.mirror.data_ptr(), self.opt.state[self.ent]["sum"].data_ptr(), self.lr, self.eps, t.slot_of.data_ptr(),
+                 t.g_dense.data_ptr(), self.flash_status.data_ptr() if self._use_flash else None, self.ws3.data_ptr(),
+                 self.ws3.numel(), lib.stream_ptr(self.ent))
 
     def _join_side(self):
         torch.cuda.current_stream().wait_stream(self.side)
@@ -403,6 +466,22 @@ class FusedAllEntityStepper:
                     self._guard_flash(self.g_rel)
                     lib.call("kgeb_adagrad_dense", rel.data_ptr(), s_rel.data_ptr(), self.g_rel.data_ptr(), None,
                              rel.numel(), self.lr, self.eps, 0.0, None, st2)
+        if self.fuse_update:
+            # the sparse rows (label rows, then query-side rows) are summed per touched row underneath the dTable kernel;
+            # the row kernel adds the dense part that kernel parked and applies Adagrad to the touched rows
+            t = self.touched
+            cur.wait_event(self.ev_clear)
+            lib.call("kgeb_fused_label_rows_to", self.loss_kind, self.Q.data_ptr(), self.rows, self.d, ent.data_ptr(), 0,
+                     self.E, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max, self.lab_perm.data_ptr(),
+                     self.ls, 1.0 / self.global_batch, None, t.slot_b.data_ptr(), t.cap + 1, t.g_sparse.data_ptr(),
+                     self.ws2.data_ptr(), self.ws2.numel(), st)
+            lib.call("kgeb_scatter_add_rows_perm", t.slot_a.data_ptr(), 1, self.a_perm.data_ptr(), self.da.data_ptr(),
+                     self.rows, self.d, t.g_sparse.data_ptr(), t.cap + 1, self.sws.data_ptr(), self.sws.numel(), st)
+            self._join_side()
+            t.update(ent, self.opt.state[self.ent]["sum"], self.mirror, self.lr, self.eps,
+                     self.flash_status if self._use_flash else None, st)
+            cur.wait_stream(self.side2)
+            return
         if self.seq:
             # the dense part has been STORED into the one gradient buffer: label rows and query-side rows go on top
             self._join_side()
@@ -737,9 +816,16 @@ class RowShardedAllEntityStepper:
         # (KGEB_BWD_OVERWRITE_TABLE), label rows and query-side rows are scattered on top; row n_loc collects the
         # query-side rows of other owners ("not mine") and is the only row zeroed per step.  fp32 tiles: two cleared buffers.
         self.one_buffer = math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256
-        self.g_all = torch.zeros(self.n_loc + 1, self.d, **f32)
-        self.g_ent = self.g_all[:max(self.n_loc, 1)]                      # dense part + label rows, local rows only
-        self.g_q = self.g_all if self.one_buffer else torch.zeros(self.n_loc + 1, self.d, **f32)   # last row = "not mine"
+        # ... or none: Adagrad in the flush of the tile kernel, touched rows by a row kernel (see FusedAllEntityStepper)
+        self.fuse_update = (self.one_buffer and self.n_loc > 0 and rows + nz <= lib.load().kgeb_touched_capacity()
+                            and os.environ.get("KGEB_NO_FUSED_UPDATE", "0") in ("", "0"))
+        if self.fuse_update:
+            self.touched = _TouchedRows(self.n_loc, rows + nz, self.d, rows, nz, dev)
+            self.g_all = self.g_ent = self.g_q = None
+        else:
+            self.g_all = torch.zeros(self.n_loc + 1, self.d, **f32)
+            self.g_ent = self.g_all[:max(self.n_loc, 1)]                      # dense part + label rows, local rows only
+            self.g_q = self.g_all if self.one_buffer else torch.zeros(self.n_loc + 1, self.d, **f32)   # last row = "not mine"
         self.g_rel = torch.zeros(self.rel.shape[0], self.dr, **f32)
         self.loss = torch.zeros((), **f32)
         self.rowstat = torch.empty(rows, 4, **f32)
@@ -798,7 +884,9 @@ class RowShardedAllEntityStepper:
     # -- compute stages (each one CUDA graph) and the collectives between them ----------------------------------
     def _stage_gather(self):
         st = lib.stream_ptr(self.ent)
-        if self.one_buffer:
+        if self.fuse_update:
+            self.touched.build(self.a_idx, self.lab_col, self.lab_off[self.rows:], self.e_lo, self.e_hi, st)
+        elif self.one_buffer:
             self.g_all[self.n_loc:].zero_()
         else:
             self.g_ent.zero_(); self.g_q.zero_()
@@ -841,10 +929,20 @@ class RowShardedAllEntityStepper:
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
-            # the dense part is stored (no cleared buffer), the label rows of this shard are scattered on top by the call
-            lib.call("kgeb_fused_bwd", *common, None, self.g_ent.data_ptr(), None,
-                     lib.BWD_OVERWRITE_TABLE if self.mirror is not None else 0, self.ws2.data_ptr(), self.ws2.numel(),
-                     lib.stream_ptr(self.ent))
+            if self.fuse_update:
+                # dense part + Adagrad in the tile kernel's flush; rows of the touched set are parked for _stage_update
+                lib.call("kgeb_fused_bwd_update", self.loss_kind, self.Q.data_ptr(), self.rows, self.d,
+                         self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.E, self.lab_off.data_ptr(), self.ls, self.offset,
+                         lse, 1.0 / self.batch_size, None, self.mirror.data_ptr(),
+                         self.opt.state[self.ent]["sum"][self.e_lo:self.e_hi].data_ptr(), self.lr, self.eps,
+                         self.touched.slot_of.data_ptr(), self.touched.g_dense.data_ptr(),
+                         self.flash_status.data_ptr() if self._use_flash else None, self.ws2.data_ptr(), self.ws2.numel(),
+                         lib.stream_ptr(self.ent))
+            else:
+                # the dense part is stored (no cleared buffer), the label rows of this shard are scattered on top by the call
+                lib.call("kgeb_fused_bwd", *common, None, self.g_ent.data_ptr(), None,
+                         lib.BWD_OVERWRITE_TABLE if self.mirror is not None else 0, self.ws2.data_ptr(), self.ws2.numel(),
+                         lib.stream_ptr(self.ent))
         if self._use_flash:      # dQ partial of this shard from o_sum and the GLOBAL log-sum-exp: no second table pass
             lib.call("kgeb_fused_flash_dq", self.Q.data_ptr(), self.rows, self.d, self._ent_loc().data_ptr(), self.e_lo,
                      self.e_hi, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
@@ -870,6 +968,21 @@ class RowShardedAllEntityStepper:
         self._guard_flash(self.g_rel)
         lib.call("kgeb_adagrad_dense", rel.data_ptr(), self.opt.state[self.rel]["sum"].data_ptr(), self.g_rel.data_ptr(),
                  None, rel.numel(), self.lr, self.eps, 0.0, None, st)
+        if self.fuse_update:
+            # label rows of this shard and the query-side rows it owns, summed per touched row (rows of other owners go to the
+            # dummy slot) -- still underneath the dTable kernel; then the row kernel finishes the touched rows
+            t = self.touched
+            lib.call("kgeb_fused_label_rows_to", self.loss_kind, self.Q.data_ptr(), self.rows, self.d,
+                     self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.lab_off.data_ptr(), self.lab_col.data_ptr(),
+                     self.nnz_max, None, self.ls, 1.0 / self.batch_size, None, t.slot_b.data_ptr(), t.cap + 1,
+                     t.g_sparse.data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
+            lib.call("kgeb_scatter_add_rows", t.slot_a.data_ptr(), 1, self.da.data_ptr(), self.rows, self.d,
+                     t.g_sparse.data_ptr(), t.cap + 1, self.sws.data_ptr(), self.sws.numel(), st)
+            if self.px is not None:
+                torch.cuda.current_stream().wait_stream(self.side)
+            t.update(self._ent_loc(), self.opt.state[self.ent]["sum"][self.e_lo:self.e_hi], self.mirror, self.lr, self.eps,
+                     self.flash_status if self._use_flash else None, st)
+            return
         if self.px is not None:
             # one graph for the whole step: the dense table gradient (second stream) is joined only here -- the dQ exchange,
             # the query-transform backward and the relation chain ran underneath the dTable tile kernel.  The query-side

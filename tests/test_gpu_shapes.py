@@ -237,9 +237,9 @@ def test_wikidata5m_shape_rank_counts_bit_exact_on_dyadic_tables(kb, model, math
 
 @pytest.mark.parametrize("loss", ["kl", "bce"])
 def test_large_table_captured_step_one_gradient_buffer(kb, loss):
-    """Tables of >= 64 MB take the one-buffer flow of FusedAllEntityStepper (dense gradient STORED by the tile kernel,
-    KGEB_BWD_OVERWRITE_TABLE; label and query-side rows scattered on top; nothing cleared): three 1vsAll steps must equal
-    the autograd flow on the same bf16 tiles (same arithmetic, different buffer handling) to fp32 rounding."""
+    """Tables of >= 64 MB take the no-gradient-buffer flow of FusedAllEntityStepper (Adagrad applied by the flush of the dense
+    table-gradient kernel, kgeb_fused_bwd_update; label and query-side rows summed per touched row and finished by a row
+    kernel): three 1vsAll steps must equal the autograd flow on the same bf16 tiles to fp32 rounding."""
     e, r, d, b = 140_000, 50, 128, 256
     torch.manual_seed(0)
     ref = kb.KgeModel("distmult", e, r, d).cuda()
@@ -249,7 +249,7 @@ def test_large_table_captured_step_one_gradient_buffer(kb, loss):
     jr = kb.TrainingJob1vsAll(ref, mk(ref), kb.KgeLoss.create(loss), math_mode=kb.lib.MATH_BF16)
     kind = kb.lib.LOSS_KL if loss == "kl" else kb.lib.LOSS_BCE
     st = kb.trainer.FusedAllEntityStepper(new, mk(new), 2 * b, 2 * b, kind, b, math_mode=kb.lib.MATH_BF16)
-    assert st.seq, "the one-buffer flow was not selected"
+    assert st.seq and st.fuse_update, "the no-gradient-buffer flow (Adagrad in the tile kernel) was not selected"
     gen = torch.Generator().manual_seed(1)
     for step in range(3):
         t = torch.stack((torch.randint(0, e, (b,), generator=gen), torch.randint(0, r, (b,), generator=gen),
@@ -263,6 +263,96 @@ def test_large_table_captured_step_one_gradient_buffer(kb, loss):
         assert got == pytest.approx(a.avg_loss, rel=2e-5), (loss, step)
         for x, y in ((new.get_s_embedder().weight, ref.get_s_embedder().weight), (new.get_p_embedder().weight, ref.get_p_embedder().weight)):
             assert (x - y).abs().max().item() <= 0.2 * 1e-3, (loss, step, (x - y).abs().max().item())
+
+
+def test_touched_rows_numbering(kb):
+    """kgeb_touched_build against numpy: distinct in-shard ids numbered in ascending order, ids of other shards on the dummy
+    slot, padding of the second list on slot 0 and not touched."""
+    rng = np.random.default_rng(5)
+    e_lo, e_hi, n_a, n_b, real = 1000, 9000, 700, 900, 640
+    a = rng.integers(0, 12000, n_a)
+    b = rng.integers(0, 12000, n_b)
+    b[real:] = 1234                                        # stale padding
+    t = kb.trainer._TouchedRows(e_hi - e_lo, n_a + n_b, 16, n_a, n_b, torch.device("cuda"))
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    t.build(ta, tb, torch.tensor([real], device="cuda"), e_lo, e_hi, kb.lib.stream_ptr(ta))
+    live = np.concatenate((a, b[:real]))
+    uniq = np.unique(live[(live >= e_lo) & (live < e_hi)])
+    assert int(t.num.item()) == len(uniq)
+    assert np.array_equal(t.uniq[:len(uniq)].cpu().numpy(), uniq - e_lo)
+    slot_of = np.full(e_hi - e_lo, -1, np.int32)
+    slot_of[uniq - e_lo] = np.arange(len(uniq))
+    assert np.array_equal(t.slot_of.cpu().numpy(), slot_of)
+    want = lambda ids: np.where((ids >= e_lo) & (ids < e_hi), slot_of[np.clip(ids - e_lo, 0, e_hi - e_lo - 1)], n_a + n_b)  # noqa: E731
+    assert np.array_equal(t.slot_a.cpu().numpy(), want(a))
+    wb = want(b)
+    wb[real:] = 0
+    assert np.array_equal(t.slot_b.cpu().numpy(), wb)
+
+
+@pytest.mark.parametrize("loss", ["kl", "bce"])
+def test_adagrad_in_the_table_gradient_kernel_equals_the_separate_pass(kb, loss, monkeypatch):
+    """kgeb_fused_bwd_update + kgeb_touched_update (Adagrad applied by the flush of the dense table-gradient kernel; rows
+    that also get label / query-side rows finished by a row kernel) against the same step with a stored gradient buffer
+    and kgeb_adagrad_dense: rows outside the touched set get the same gradient bits and an update term within a few ulp
+    (MUFU sqrt / rcp in the tile kernel), touched rows agree to rounding (dense + (labels + query side) instead of
+    (dense + labels) + query side; IEEE arithmetic in the row kernel)."""
+    e, r, d, b = 140_000, 50, 128, 256
+    torch.manual_seed(0)
+    base = kb.KgeModel("distmult", e, r, d).cuda()
+    mk = lambda m: kb.optim.create("Adagrad", m.parameters(), lr=0.2, initial_accumulator_value=0.1)   # noqa: E731
+    kind = kb.lib.LOSS_KL if loss == "kl" else kb.lib.LOSS_BCE
+    steppers = []
+    for fused_update in (False, True):
+        m = kb.KgeModel("distmult", e, r, d).cuda()
+        m.load_state_dict(base.state_dict())
+        monkeypatch.setenv("KGEB_NO_FUSED_UPDATE", "0" if fused_update else "1")
+        st = kb.trainer.FusedAllEntityStepper(m, mk(m), 2 * b, 2 * b, kind, b, math_mode=kb.lib.MATH_BF16)
+        assert st.seq and st.fuse_update == fused_update
+        steppers.append((m, st))
+    gen = torch.Generator().manual_seed(1)
+    touched = torch.zeros(e, dtype=torch.bool, device="cuda")
+    for step in range(3):
+        t = torch.stack((torch.randint(0, e, (b,), generator=gen), torch.randint(0, r, (b,), generator=gen),
+                         torch.randint(0, e, (b,), generator=gen)), 1).cuda()
+        t[:8, 2] = t[0, 2]
+        touched[t[:, 0]] = True
+        touched[t[:, 2]] = True
+        z = torch.zeros(b, dtype=torch.int32, device="cuda")
+        losses = []
+        for m, st in steppers:
+            st.set_inputs(torch.cat((t[:, 0], t[:, 2])), torch.cat((t[:, 1], t[:, 1])), torch.cat((z, z + 1)),
+                          torch.arange(2 * b + 1, device="cuda"), torch.cat((t[:, 2], t[:, 0])))
+            losses.append(st.step().item())
+            assert st.flash_fallbacks == 0
+        assert losses[0] == pytest.approx(losses[1], rel=1e-6), (loss, step)
+    (m0, s0), (m1, s1) = steppers
+    torch.cuda.synchronize()
+    w0, w1 = m0.get_s_embedder().weight.detach(), m1.get_s_embedder().weight.detach()
+    a0, a1 = s0.opt.state[s0.ent]["sum"], s1.opt.state[s1.ent]["sum"]
+    assert not torch.equal(w0, base.get_s_embedder().weight.detach()), "nothing was trained"
+    # rows outside the touched set: the same gradient arithmetic; the update term uses the MUFU square root and reciprocal in
+    # the tile kernel (within a few ulp of the IEEE one), and a weight that differs in its last bits can round to another
+    # bf16 operand in the next step: everything agrees to rounding, nothing bit for bit after the first step
+    wb = base.get_s_embedder().weight.detach()
+    d0, d1 = (w0 - wb)[~touched], (w1 - wb)[~touched]
+    # (2e-6: one element of G = sigmoid / batch ~ 2e-3 rounded the other way in bf16, times |Q| ~ 0.05, times lr / sqrt(state):
+    # measured on 5 of 140,000 rows, ~6 columns each -- a weight that differs in its last bit moves a score across a tie)
+    bad = (d0 - d1).abs() > 1e-4 * d0.abs() + 2e-6
+    if bool(bad.any()):
+        i = int((d0 - d1).abs().argmax())
+        r_, c_ = divmod(i, d)
+        rows_idx = torch.nonzero(~touched).flatten()
+        raise AssertionError(f"{int(bad.sum())} elements off; worst: row {int(rows_idx[r_])} col {c_} d0 {float(d0.flatten()[i]):.6e} "
+                             f"d1 {float(d1.flatten()[i]):.6e} state {float(a0[~touched].flatten()[i]):.6e} / "
+                             f"{float(a1[~touched].flatten()[i]):.6e}; rows with a bad element: "
+                             f"{rows_idx[bad.any(1)][:8].tolist()} of {int(bad.any(1).sum())}")
+    assert ((a0 - a1).abs() <= 1e-4 * a0.abs()).all()
+    assert (w0 - w1).abs().max().item() <= 1e-5 and (a0 - a1).abs().max().item() <= 1e-6 * a0.abs().max().item()
+    assert torch.equal(s1.mirror, w1.bfloat16()), "bf16 mirror out of step with the table"
+    # (an entity used again in a later step carries its rounding difference into that step's queries)
+    assert (m0.get_p_embedder().weight - m1.get_p_embedder().weight).abs().max().item() <= 1e-5
+    assert int((s1.touched.slot_of != -1).sum().item()) == 0 and float(s1.touched.g_sparse.abs().max().item()) == 0.0
 
 
 @pytest.mark.parametrize("e,b,scale", [(14541, 4096, 8.0), (14541, 512, 1500.0), (4_600_000, 256, 8.0), (1000, 130, 8.0)])
