@@ -928,7 +928,15 @@ class RowShardedAllEntityStepper:
                   self.offset, lse, 1.0 / self.batch_size, None, None if self.mirror is None else self.mirror.data_ptr())
         cur = torch.cuda.current_stream()
         self.side.wait_stream(cur)
+        dq_first = self.fuse_update and not self._use_flash
+        if dq_first:
+            # the fused update rewrites the bf16 mirror, which the dQ tile kernel reads: dQ first, the update kernel behind
+            # its TILE kernel (kgeb_fused_bwd_wait_tiles), beside its small reduction kernels
+            lib.call("kgeb_fused_bwd", *common, self._dst("dQ").data_ptr(), None,
+                     self._dst("stat").data_ptr() if late else None, 0, self.ws.data_ptr(), self.ws.numel(), st)
         with torch.cuda.stream(self.side):
+            if dq_first:
+                lib.call("kgeb_fused_bwd_wait_tiles", lib.stream_ptr(self.ent))
             if self.fuse_update:
                 # dense part + Adagrad in the tile kernel's flush; rows of the touched set are parked for _stage_update
                 lib.call("kgeb_fused_bwd_update", self.loss_kind, self.Q.data_ptr(), self.rows, self.d,
@@ -948,7 +956,7 @@ class RowShardedAllEntityStepper:
                      self.e_hi, self.lab_off.data_ptr(), self.lab_col.data_ptr(), self.nnz_max,
                      self.rowstat_local.data_ptr(), self.lse.data_ptr(), 1.0 / self.batch_size, None, self.o_sum.data_ptr(),
                      self._dst("dQ").data_ptr(), self.ws.data_ptr(), self.ws.numel(), st)
-        else:
+        elif not dq_first:
             lib.call("kgeb_fused_bwd", *common, self._dst("dQ").data_ptr(), None,
                      self._dst("stat").data_ptr() if late else None, 0, self.ws.data_ptr(), self.ws.numel(), st)
         if self.px is None:      # separately captured stage graphs: nothing may stay forked at the end of one
