@@ -140,6 +140,37 @@ def run_cpu_reference(batches, steps, warmup, job=None):
             "loss_step0": losses[0], "job": job}
 
 
+def reference_cuda(batches, local_rank, steps=5, warmup=2):
+    """SURVEY.md 8(d), last paragraph: the reference's own CUDA path -- the UNMODIFIED reference with its stock model and
+    torch.optim.Adagrad, job.device cuda -- on the same GPU, same config and batches: 'same API, stock kernels'.  Timed like
+    the e2e figure (pinned host triples in, loss read back by the job) with CUDA events around the steps."""
+    try:
+        job = reference_job(f"cuda:{local_rank}")
+        torch.cuda.synchronize()
+        with quiet():
+            for i in range(warmup):
+                reference_step(job, i, batches[i % len(batches)])
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for i in range(steps):
+                loss = reference_step(job, warmup + i, batches[(warmup + i) % len(batches)])
+            b.record()
+            torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        peak = torch.cuda.max_memory_allocated() / 2 ** 30
+        del job
+        torch.cuda.empty_cache()
+        return {"value": B / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "last_loss": float(loss), "peak_memory_gib": round(peak, 1),
+                "what": ("kge.job.train.TrainingJob1vsAll from baseline/_ref, model distmult (stock scorer / LookupEmbedder), "
+                         "torch.optim.Adagrad, job.device cuda: zero_grad + _process_batch + optimizer.step() per step; fp32 "
+                         "(torch's default matmul precision), [batch, E] score matrices materialised")}
+    except Exception as exc:      # e.g. out of memory next to this arm's own allocations
+        torch.cuda.empty_cache()
+        return {"value": None, "unavailable": f"{type(exc).__name__}: {str(exc)[:200]}"}
+
+
 def reference_arm(args):
     from baseline import ref_env
     rank = int(os.environ.get("RANK", "0"))
@@ -422,6 +453,8 @@ def our_arm(args):
         fb_args = bench_fb237.parser().parse_args(["--steps", str(max(steps, 20)), "--warmup", "5", "--cpu-steps", "3"])
         with quiet():
             extra = {"fb15k237": bench_fb237.run(fb_args)}
+        if use_ref and not args.skip_reference_cuda:
+            extra["reference_cuda"] = reference_cuda(batches, local_rank)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -467,6 +500,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=1, help="timed steps of the bounded CPU-baseline sample (N = 1)")
+    ap.add_argument("--skip-reference-cuda", action="store_true", help="do not time the reference's stock CUDA path (N = 1)")
     ap.add_argument("--skip-e2e", action="store_true", help="tuning runs: device-resident value + kernel roofline only")
     ap.add_argument("--skip-extra", action="store_true", help="do not run the FB15k-237 workload (extra key)")
     ap.add_argument("--no-reference-job", action="store_true", help="e2e through this repo's stepper instead of the reference's job object")
