@@ -410,3 +410,45 @@ def test_flash_reports_scores_outside_its_window_and_autograd_falls_back(kb):
     # (scores of +-500 carry +-2 nats of bf16 operand rounding: the row losses agree to that, and a softmax peaked on
     # one of three near-tied hot entities makes dQ incomparable between roundings -- finiteness was asserted above)
     close(res["bf16"][0], res["fp32"][0], 1e-2, "fallback row losses")
+
+
+def test_failed_flash_pass_in_the_captured_step_is_a_no_op_and_the_two_pass_graph_repeats_it(kb):
+    """The captured large-table step (flash forward, Adagrad inside the table-gradient kernel) on a table where three
+    entities score hundreds of nats above the flash reference: the flash graph must change NOTHING (status word -> the tile
+    kernel's update warps and the row kernel skip, the relation gradient is cleared), step() must replay the two-pass graph,
+    and the result must equal the autograd flow on the same bf16 tiles."""
+    e, r, d, b = 140_000, 20, 128, 128
+    torch.manual_seed(0)
+    ref = kb.KgeModel("distmult", e, r, d).cuda()
+    hot = torch.tensor([11, 70_001, 139_001], device="cuda")
+    with torch.no_grad():
+        ref.get_s_embedder().weight[hot] *= 3.0e4       # scores of +-300 nats against queries of ~0.01 per dimension
+    new = kb.KgeModel("distmult", e, r, d).cuda()
+    new.load_state_dict(ref.state_dict())
+    mk = lambda m: kb.optim.create("Adagrad", m.parameters(), lr=0.2, initial_accumulator_value=0.1)   # noqa: E731
+    jr = kb.TrainingJob1vsAll(ref, mk(ref), kb.KgeLoss.create("kl"), math_mode=kb.lib.MATH_BF16)
+    st = kb.trainer.FusedAllEntityStepper(new, mk(new), 2 * b, 2 * b, kb.lib.LOSS_KL, b, math_mode=kb.lib.MATH_BF16)
+    assert st.seq and st.fuse_update and st.flash
+    gen = torch.Generator().manual_seed(2)
+    t = torch.stack((torch.randint(0, e, (b,), generator=gen), torch.randint(0, r, (b,), generator=gen),
+                     torch.randint(0, e, (b,), generator=gen)), 1).cuda()
+    assert not torch.isin(hot, t[:, [0, 2]].flatten()).any()
+    z = torch.zeros(b, dtype=torch.int32, device="cuda")
+    st.set_inputs(torch.cat((t[:, 0], t[:, 2])), torch.cat((t[:, 1], t[:, 1])), torch.cat((z, z + 1)),
+                  torch.arange(2 * b + 1, device="cuda"), torch.cat((t[:, 2], t[:, 0])))
+    # (1) the flash graph alone: a failed pass leaves tables, optimizer state and mirror untouched
+    before = [x.detach().clone() for x in (st.ent, st.rel, st.opt.state[st.ent]["sum"], st.opt.state[st.rel]["sum"], st.mirror)]
+    st.graph.replay()
+    torch.cuda.synchronize()
+    assert int(st.flash_status[0].item()) != 0, "the flash pass did not report the overflow"
+    after = (st.ent, st.rel, st.opt.state[st.ent]["sum"], st.opt.state[st.rel]["sum"], st.mirror)
+    assert all(torch.equal(x, y.detach()) for x, y in zip(before, after)), "a failed flash pass changed the model"
+    assert int((st.touched.slot_of != -1).sum().item()) == 0 and float(st.touched.g_sparse.abs().max().item()) == 0.0
+    # (2) the public step: falls back, and equals the autograd flow
+    got = st.step().item()
+    assert st.flash_fallbacks == 1
+    a = jr.step(0, {"triples": t})
+    assert got == pytest.approx(a.avg_loss, rel=2e-5)
+    for x, y in ((new.get_s_embedder().weight, ref.get_s_embedder().weight), (new.get_p_embedder().weight, ref.get_p_embedder().weight)):
+        assert torch.isfinite(x).all()
+        assert bool(((x - y).abs() <= 0.2 * 1e-3 + 1e-6 * y.abs()).all()), (x - y).abs().max().item()
