@@ -1343,7 +1343,9 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __r
 // batch and carry the largest norms.  This is a heuristic: the kernel reports rows it failed on (Params::status) and the
 // caller repeats the step with the two-pass kernels, so a wrong guess costs time, never a wrong result.
 // One warp per row, four candidate rows in flight per iteration (the loop is pure L2 latency otherwise).
-constexpr int kFlashSamples = 64, kFlashLabelSamples = 192, kFlashWarps = 4, kFlashRows = 8;
+// (16 warps: the candidate loop is a chain of dependent L2 loads and shuffle reductions, ~1 us per candidate and warp; with 4
+// warps per block the kernel took 65 us whatever the shard size -- 5 % of a step at 8 GPUs)
+constexpr int kFlashSamples = 64, kFlashLabelSamples = 192, kFlashWarps = 16, kFlashRows = 8;
 __global__ void __launch_bounds__(kFlashWarps * 32)
 sample_max_kernel(const float* __restrict__ Q, const float* __restrict__ table, int64_t B, int d, int64_t e_lo, int64_t n_ent,
                   const int64_t* __restrict__ lab_off, const int64_t* __restrict__ lab_col, const float* __restrict__ entry_dot,

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import weakref
+
 import torch
 
 from . import lib
@@ -30,17 +32,22 @@ _mirror_cache = {}
 
 def bf16_mirror(table: torch.Tensor) -> torch.Tensor:
     """bf16 copy of an fp32 table for KGEB_MATH_BF16, refreshed when the tensor's version counter moves
-    (optimizer steps, renormalisation hooks and checkpoint loads all bump it)."""
+    (optimizer steps, renormalisation hooks and checkpoint loads all bump it).  An entry belongs to a STORAGE (weak
+    reference: PyTorch keeps one Python object per live storage), not to an address: the caching allocator hands the
+    address of a freed table to the next one of the same shape, and version counters of fresh tensors coincide."""
     t = table.detach()
+    storage = t.untyped_storage()
     key = (t.data_ptr(), tuple(t.shape))
     hit = _mirror_cache.get(key)
+    if hit is not None and hit[2]() is not storage:
+        hit = None
     if hit is not None and hit[0] == table._version:
         return hit[1]
     buf = hit[1] if hit is not None else torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
     lib.call("kgeb_to_bf16", lib.f32(t.contiguous(), "table"), buf.data_ptr(), t.numel(), lib.stream_ptr(t))
     if len(_mirror_cache) > 16:
         _mirror_cache.clear()
-    _mirror_cache[key] = (table._version, buf)
+    _mirror_cache[key] = (table._version, buf, weakref.ref(storage))
     return buf
 
 

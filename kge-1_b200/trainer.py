@@ -844,6 +844,7 @@ class RowShardedAllEntityStepper:
         self.sws = torch.empty(L.kgeb_scatter_workspace_bytes(rows, max(self.d, self.dr)), dtype=torch.uint8, device=dev)
         self.sws2 = torch.empty_like(self.sws)
         self.side = torch.cuda.Stream(device=dev)
+        self.ev_touched = torch.cuda.Event()
         self.mirror = None
         if math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256:
             self.mirror = torch.empty(max(self.n_loc, 1), self.d, dtype=torch.bfloat16, device=dev)
@@ -885,7 +886,16 @@ class RowShardedAllEntityStepper:
     def _stage_gather(self):
         st = lib.stream_ptr(self.ent)
         if self.fuse_update:
-            self.touched.build(self.a_idx, self.lab_col, self.lab_off[self.rows:], self.e_lo, self.e_hi, st)
+            # numbering of the touched rows: needed by the dTable kernel (second stream) and by the sparse scatters of the
+            # update stage only -- off the critical path (a one-block sort: 27 us)
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                self.touched.build(self.a_idx, self.lab_col, self.lab_off[self.rows:], self.e_lo, self.e_hi,
+                                   lib.stream_ptr(self.ent))
+                self.ev_touched.record()
+            if self.px is None:
+                cur.wait_stream(self.side)         # separately captured stage graphs: nothing may stay forked
         elif self.one_buffer:
             self.g_all[self.n_loc:].zero_()
         else:
@@ -980,6 +990,8 @@ class RowShardedAllEntityStepper:
             # label rows of this shard and the query-side rows it owns, summed per touched row (rows of other owners go to the
             # dummy slot) -- still underneath the dTable kernel; then the row kernel finishes the touched rows
             t = self.touched
+            if self.px is not None:
+                torch.cuda.current_stream().wait_event(self.ev_touched)
             lib.call("kgeb_fused_label_rows_to", self.loss_kind, self.Q.data_ptr(), self.rows, self.d,
                      self._ent_loc().data_ptr(), self.e_lo, self.e_hi, self.lab_off.data_ptr(), self.lab_col.data_ptr(),
                      self.nnz_max, None, self.ls, 1.0 / self.batch_size, None, t.slot_b.data_ptr(), t.cap + 1,

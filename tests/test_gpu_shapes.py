@@ -452,3 +452,18 @@ def test_failed_flash_pass_in_the_captured_step_is_a_no_op_and_the_two_pass_grap
     for x, y in ((new.get_s_embedder().weight, ref.get_s_embedder().weight), (new.get_p_embedder().weight, ref.get_p_embedder().weight)):
         assert torch.isfinite(x).all()
         assert bool(((x - y).abs() <= 0.2 * 1e-3 + 1e-6 * y.abs()).all()), (x - y).abs().max().item()
+
+
+def test_bf16_mirror_cache_belongs_to_a_storage_not_to_an_address(kb):
+    """The caching allocator hands the address of a freed table to the next tensor of the same shape, and both have version
+    counter 0: the cached bf16 mirror of the first must not be served for the second."""
+    a = torch.full((4096, 128), 1.0, device="cuda")
+    ptr = a.data_ptr()
+    assert float(kb.ops.bf16_mirror(a).float().max()) == 1.0
+    del a
+    b = torch.full((4096, 128), 2.0, device="cuda")
+    if b.data_ptr() != ptr:
+        pytest.skip("the allocator did not reuse the address")
+    assert float(kb.ops.bf16_mirror(b).float().min()) == 2.0
+    b.mul_(2.0)                                   # in-place change: version counter
+    assert float(kb.ops.bf16_mirror(b).float().min()) == 4.0
