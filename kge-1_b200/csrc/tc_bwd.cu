@@ -697,10 +697,8 @@ tc_bwd4_kernel(const __grid_constant__ CUtensorMap tm_res, const __grid_constant
       int slot = 0;
       uint32_t phase = 0, rphase = 0;
       if (UPD && p.stagger_clk > 0) {
-        // Fused update: all CTAs run jobs of the same length, so without this their flushes -- 288 KB of HBM traffic each at
-        // d = 128 -- coincide: 43 MB bursts that take 7 us while HBM idles for the rest of the ~16 us job (measured: the
-        // kernel 2.3 ms longer than without the update).  Spreading the CTAs' phases over one job period keeps the update
-        // traffic continuous; the data-dependent pipeline behind this warp inherits the delay.
+        // (tuning, KGEB_UPD_STAGGER: the hypothesis was that CTAs running jobs of equal length flush in lockstep -- 43 MB
+        // bursts of update traffic; spreading their phases over one job period changed nothing)
         const long long t0 = clock64(), wait = (long long)blockIdx.x * p.stagger_clk;
         while (clock64() - t0 < wait) __nanosleep(100);
       }
@@ -1612,8 +1610,10 @@ int tc_fused_bwd(int loss, const float* Q, const void* Qb, int64_t B, int d, con
         pl.p.upd_slot = upd->slot_of; pl.p.upd_gbuf = upd->gbuf; pl.p.upd_skip = upd->skip;
         pl.p.upd_clr = upd->clr; pl.p.upd_eps = upd->eps;
         pl.p.upd_debug = getenv("KGEB_UPD_DEBUG") ? atoi(getenv("KGEB_UPD_DEBUG")) : 0;
-        // one job = n_str_tiles tiles of ~1000 clk (measured: 975 at d = 128) + the flush; phases spread over one period
-        static const int stagger_tile_clk = getenv("KGEB_UPD_STAGGER") ? atoi(getenv("KGEB_UPD_STAGGER")) : 1100;
+        // tuning knob, off by default: spread the CTAs' phases over one job period (KGEB_UPD_STAGGER = clocks per tile, e.g.
+        // 1100).  Measured with 0 / 1100 / 2200: no difference -- the CTAs do not run in lockstep -- and the last CTA's
+        // start delay of one job period is 3 % of the kernel on an eighth of the table.
+        static const int stagger_tile_clk = getenv("KGEB_UPD_STAGGER") ? atoi(getenv("KGEB_UPD_STAGGER")) : 0;
         const int64_t grid = pl.p.n_res_blocks < kNumSMs ? pl.p.n_res_blocks : kNumSMs;
         pl.p.stagger_clk = pl.p.n_res_blocks > 2 * grid ? (int)(pl.p.n_str_tiles * stagger_tile_clk / grid) : 0;
       }

@@ -1201,12 +1201,12 @@ class FusedNegSamplingStepper:
                  offset: float = 0.0, use_graph: bool = True, dp_group=None, segment_bwd: bool = False,
                  fused_slot: bool = True, deterministic: bool = True):
         """`segment_bwd`: candidate gradients without materialised rows (csrc/ns_segment.cu: pairs sorted by candidate, one
-        warp per distinct candidate) instead of pairs_bwd's dC rows + the sorted scatter; tuning path, not yet run on
-        hardware.
+        warp per distinct candidate) instead of pairs_bwd's dC rows + the sorted scatter; measured slower than the sort it
+        replaces (0.509 vs 0.414 ms per C3 step): kept as a tuning path.
         `dp_group`: data-parallel replicas (every rank its own batch of `batch_size` triples; SURVEY.md 8e, second row):
         gradients of both tables are exchanged and applied by the peer-memory kernels of csrc/p2p.cu inside the same CUDA
-        graph; loss terms are scaled by the global batch so that all replicas apply the identical update.  (Not yet
-        run on hardware -- tests/p2p_ns_check.py.)"""
+        graph; loss terms are scaled by the global batch so that all replicas apply the identical update
+        (tests/p2p_ns_check.py; profiles/r2/p2p_ns_check_2.log)."""
         _require_plain_model(model, "FusedNegSamplingStepper")
         # fused_slot: scores, loss, dQ and the candidate gradient of a slot in ONE kernel (kgeb_ns_fused) instead of
         # kgeb_pairs_score + kgeb_ns_loss + kgeb_pairs_bwd -- same sums in the same order, bit-identical results.

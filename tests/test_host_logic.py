@@ -464,3 +464,28 @@ def test_row_exchange_routes_requests_and_gradients_over_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_captured_steppers_refuse_what_they_would_silently_drop():
+    """a captured step reads the raw tables without autograd; reciprocal-relations models, embedder dropout,
+    per-batch renormalisation and (outside the all-entity stepper's folded Lp term) penalties must raise, not be ignored.
+    The refusal comes before anything touches a device, so it is checked here on CPU models."""
+    import kgeb200 as kb
+    e, r, d = 50, 5, 16
+    mk = lambda m: kb.optim.create("Adagrad", m.parameters(), lr=0.1)   # noqa: E731
+    cases = {
+        "reciprocal": kb.model.ReciprocalRelationsModel("distmult", e, r, d),
+        "dropout": kb.KgeModel("distmult", e, r, d, entity_embedder={"dropout": 0.2}),
+        "normalize": kb.KgeModel("distmult", e, r, d, relation_embedder={"normalize_p": 2.0}),
+    }
+    for name, m in cases.items():
+        with pytest.raises(NotImplementedError):
+            kb.trainer.FusedAllEntityStepper(m, mk(m), 8, 8, kb.lib.LOSS_KL, 4, use_graph=False)
+        with pytest.raises(NotImplementedError):
+            kb.trainer.FusedNegSamplingStepper(m, mk(m), 4, 2, 2, kb.lib.LOSS_KL, use_graph=False)
+    pen = kb.KgeModel("distmult", e, r, d, entity_embedder={"regularize_weight": 1e-3})
+    with pytest.raises(NotImplementedError):
+        kb.trainer.FusedNegSamplingStepper(pen, mk(pen), 4, 2, 2, kb.lib.LOSS_KL, use_graph=False)
+    weighted = kb.KgeModel("distmult", e, r, d, entity_embedder={"regularize_weight": 1e-3, "regularize_weighted": True})
+    with pytest.raises(NotImplementedError):
+        kb.trainer.FusedAllEntityStepper(weighted, mk(weighted), 8, 8, kb.lib.LOSS_KL, 4, use_graph=False)
