@@ -397,16 +397,24 @@ def our_arm(args):
         n_ent = sh.e_hi - sh.e_lo
 
     # ---------------- value: batches resident in HBM, CUDA events ---------------------------------------------------
-    dev_inputs = [device_batch(b, dev) for b in batches]
+    if getattr(st, "triples", None) is not None:
+        # the stepper builds its batch from the triples inside the captured step (kgeb_onevsall_batch_build): the resident
+        # inputs are the triples themselves
+        dev_triples = [b.to(dev) for b in batches]
+        set_batch = lambda i: st.set_triples(dev_triples[i])       # noqa: E731
+        dev_inputs = None
+    else:
+        dev_inputs = [device_batch(b, dev) for b in batches]
+        set_batch = lambda i: st.set_inputs(*dev_inputs[i])        # noqa: E731
     for i in range(warm):
-        st.set_inputs(*dev_inputs[i])
+        set_batch(i)
         st.step()
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     with bench_fb237.ClockSampler(local_rank) as clocks:
         barrier()
         for i in range(steps):
-            st.set_inputs(*dev_inputs[warm + i])
+            set_batch(warm + i)
             evs[i][0].record()
             st.step()
             evs[i][1].record()
@@ -444,7 +452,7 @@ def our_arm(args):
         e2e_s = t.item()
     e2e_value = None if args.skip_e2e else B * steps / e2e_s
 
-    launches = count_library_launches(lambda: (st.set_inputs(*dev_inputs[0]), st.step()))
+    launches = count_library_launches(lambda: (set_batch(0), st.step()))
     roof = kernel_roofline(kb, st, 2 * B, n_ent, total_ms / steps, world)
 
     extra = None

@@ -333,6 +333,14 @@ int kgeb_kvsall_batch_build(const kgeb_index_t* sp_index, const kgeb_index_t* po
                             int32_t* p_perm, int32_t* lab_perm, int32_t* overflow, void* workspace,
                             int64_t workspace_bytes, void* stream);
 
+/* The 1vsAll batch (train.py:1032-1062: an sp_ pass with label o and a _po pass with label s over the same triples) from
+ * the [B, 3] int64 triples: the same eight arrays as kgeb_kvsall_batch_build, 2 B rows (sp_ rows first), one label per
+ * row, 2 B <= 8192.  One block; meant as the first node of the captured step's graph, so that a training step of the
+ * reference's TrainingJob1vsAll costs the host one H2D copy of the triples and one graph launch. */
+int kgeb_onevsall_batch_build(const int64_t* triples, int64_t B, int64_t num_entities, int64_t num_relations, int64_t* a_idx,
+                              int64_t* p_idx, int32_t* row_combine, int64_t* lab_off, int64_t* lab_col, int32_t* a_perm,
+                              int32_t* p_perm, int32_t* lab_perm, void* stream);
+
 /* ---- 8f-2: on-device negative sampling (kge/util/sampler.py).  Philox4x32-10, counter-based: results depend only on
  * state = {seed, offset} (device memory, so CUDA-graph replays draw fresh numbers; kgeb_philox_advance bumps the offset
  * on the stream), never on launch shape.  The reference's torch / numpy / `random` streams cannot be reproduced on a

@@ -136,6 +136,57 @@ static size_t build_cub_bytes(int64_t n) {
   return a > b ? a : b;
 }
 
+// ------------------------------------------------------------------------------------------
+// 1vsAll batch (train.py:1032-1062) straight from the [B, 3] triples: the static inputs of the captured step and the
+// three stable argsorts, one block, no host work.  Rows 0..B-1 are the sp_ queries (label = o), rows B..2B-1 the _po
+// queries (label = s); every row has exactly one label.
+// ------------------------------------------------------------------------------------------
+constexpr int kOvaThreads = 1024, kOvaItems = 8, kOvaMax = kOvaThreads * kOvaItems;   // 2 B <= 8192
+
+__global__ void __launch_bounds__(kOvaThreads, 1)
+onevsall_build_kernel(const int64_t* __restrict__ triples, int B, int64_t* __restrict__ a_idx, int64_t* __restrict__ p_idx,
+                      int32_t* __restrict__ row_combine, int64_t* __restrict__ lab_off, int64_t* __restrict__ lab_col,
+                      int32_t* __restrict__ a_perm, int32_t* __restrict__ p_perm, int32_t* __restrict__ lab_perm) {
+  using Sort = cub::BlockRadixSort<unsigned, kOvaThreads, kOvaItems, int>;
+  __shared__ typename Sort::TempStorage tmp;
+  const int t = threadIdx.x, n = 2 * B;
+  for (int i = t; i < n; i += kOvaThreads) {
+    const int r = i < B ? i : i - B;
+    const int64_t s = triples[3 * r], p = triples[3 * r + 1], o = triples[3 * r + 2];
+    a_idx[i] = i < B ? s : o;
+    p_idx[i] = p;
+    lab_col[i] = i < B ? o : s;
+    row_combine[i] = i < B ? 0 : 1;
+    lab_off[i] = i;
+  }
+  if (t == 0) lab_off[n] = n;
+  // stable argsort of each id list (LSD radix sort keeps the order of equal keys; padding keys sort last)
+  for (int which = 0; which < 3; ++which) {
+    unsigned key[kOvaItems];
+    int val[kOvaItems];
+#pragma unroll
+    for (int j = 0; j < kOvaItems; ++j) {
+      const int i = t * kOvaItems + j;
+      unsigned k = 0xffffffffu;
+      if (i < n) {
+        const int r = i < B ? i : i - B;
+        const int col = which == 1 ? 1 : ((which == 0) == (i < B) ? 0 : 2);   // a: s | o ;  p: p | p ;  labels: o | s
+        k = (unsigned)triples[3 * r + col];
+      }
+      key[j] = k;
+      val[j] = i;
+    }
+    __syncthreads();
+    Sort(tmp).Sort(key, val);
+    int32_t* out = which == 0 ? a_perm : (which == 1 ? p_perm : lab_perm);
+#pragma unroll
+    for (int j = 0; j < kOvaItems; ++j) {
+      const int i = t * kOvaItems + j;
+      if (i < n) out[i] = val[j];
+    }
+  }
+}
+
 static bool index_ok(const kgeb_index_t& ix) { return ix.num_keys >= 0 && (ix.num_keys == 0 || (ix.keys && ix.offsets && ix.values)); }
 
 }  // namespace kgeb
@@ -257,6 +308,21 @@ int kgeb_kvsall_batch_build(const kgeb_index_t* sp_index, const kgeb_index_t* po
     e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, (const int64_t*)lab_col, w.keys_tmp, (const int32_t*)w.iota,
                                         lab_perm, (int)capacity, 0, eb, st);
   if (e != cudaSuccess) return cuda_status(e, "kvsall_batch_build sort");
+  return KGEB_OK;
+}
+
+int kgeb_onevsall_batch_build(const int64_t* triples, int64_t B, int64_t num_entities, int64_t num_relations, int64_t* a_idx,
+                              int64_t* p_idx, int32_t* row_combine, int64_t* lab_off, int64_t* lab_col, int32_t* a_perm,
+                              int32_t* p_perm, int32_t* lab_perm, void* stream) {
+  KGEB_REQUIRE(triples && a_idx && p_idx && row_combine && lab_off && lab_col && a_perm && p_perm && lab_perm,
+               "onevsall_batch_build: NULL buffer");
+  KGEB_REQUIRE(B >= 1 && 2 * B <= kgeb::kOvaMax, "onevsall_batch_build: 1 <= batch <= %d (got %lld)", kgeb::kOvaMax / 2,
+               (long long)B);
+  KGEB_REQUIRE(num_entities < ((int64_t)1 << 32) - 1 && num_relations < ((int64_t)1 << 32) - 1,
+               "onevsall_batch_build: ids must fit 32 bits");
+  kgeb::onevsall_build_kernel<<<1, kgeb::kOvaThreads, 0, as_stream(stream)>>>(triples, (int)B, a_idx, p_idx, row_combine,
+                                                                             lab_off, lab_col, a_perm, p_perm, lab_perm);
+  KGEB_LAUNCH_CHECK("onevsall_batch_build");
   return KGEB_OK;
 }
 

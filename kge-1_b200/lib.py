@@ -50,6 +50,7 @@ SIGNATURES = {
     "kgeb_touched_build": [_p, _l, _p, _l, _p, _l, _l, _p, _p, _p, _p, _p, _p],
     "kgeb_fused_bwd_update": [_i, _p, _l, _i, _p, _l, _l, _l, _p, _f, _f, _p, _f, _p, _p, _p, _f, _f, _p, _p, _p, _p, _l, _p],
     "kgeb_touched_update": [_p, _p, _p, _p, _p, _p, _l, _p, _p, _i, _f, _f, _p, _p],
+    "kgeb_onevsall_batch_build": [_p, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "kgeb_fused_bwd_wait_tiles": [_p],
     "kgeb_to_bf16": [_p, _p, _l, _p],
     "kgeb_loss_from_rowstat": [_i, _p, _p, _l, _f, _l, _f, _p, _p, _p, _p],

@@ -170,7 +170,8 @@ def _install_captured_step(job, model, base: str, loss_kind: int, offset: float,
         st = state["stepper"]
         if st is None:
             st = FusedAllEntityStepper(view, job.optimizer, rows, nnz_max, loss_kind, job.batch_size if not is_1vsall else rows // 2,
-                                       offset, label_smoothing, math_mode, use_graph=True)
+                                       offset, label_smoothing, math_mode, use_graph=True,
+                                       onevsall_triples=is_1vsall and rows <= 8192)
             state["stepper"] = st
             model._b200_stepper = st
         return st
@@ -184,11 +185,15 @@ def _install_captured_step(job, model, base: str, loss_kind: int, offset: float,
                 model._b200_captured_batch = False
                 return ref_body(self, batch_index, batch)
             st = stepper_for(2 * b, 2 * b)
-            t = triples.to(dev, non_blocking=True)
-            s, p, o = t[:, 0], t[:, 1], t[:, 2]
-            zeros = torch.zeros(b, dtype=torch.int32, device=dev)
-            st.set_inputs(torch.cat((s, o)), torch.cat((p, p)), torch.cat((zeros, zeros + 1)),
-                          torch.arange(2 * b + 1, dtype=torch.int64, device=dev), torch.cat((o, s)))
+            if st.triples is not None:
+                # the batch (queries, labels, scatter permutations) is built by the first kernel of the captured step
+                st.set_triples(triples if triples.dtype == torch.int64 else triples.long())
+            else:
+                t = triples.to(dev, non_blocking=True)
+                s, p, o = t[:, 0], t[:, 1], t[:, 2]
+                zeros = torch.zeros(b, dtype=torch.int32, device=dev)
+                st.set_inputs(torch.cat((s, o)), torch.cat((p, p)), torch.cat((zeros, zeros + 1)),
+                              torch.arange(2 * b + 1, dtype=torch.int64, device=dev), torch.cat((o, s)))
             size = b
         else:
             q = batch["queries"]

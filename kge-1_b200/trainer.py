@@ -135,7 +135,11 @@ class _TouchedRows:
 class FusedAllEntityStepper:
     def __init__(self, model: KgeModel, optimizer, rows: int, nnz_max: int, loss_kind: int, batch_size: int,
                  offset: float = 0.0, label_smoothing: float = 0.0, math_mode: int = lib.MATH_BF16,
-                 use_graph: bool = True, shard: Optional[fused.Shard] = None, dp_group=None, dp_p2p: bool = False):
+                 use_graph: bool = True, shard: Optional[fused.Shard] = None, dp_group=None, dp_p2p: bool = False,
+                 onevsall_triples: bool = False):
+        """`onevsall_triples`: the step starts from a static [rows / 2, 3] int64 buffer of TRIPLES (`set_triples`): its first
+        kernel builds the 1vsAll batch -- queries, one label per row, the three scatter permutations -- on the device
+        (kgeb_onevsall_batch_build), so a step costs the host one copy and one graph launch."""
         if model.get_scorer().kind != lib.DOT:
             raise NotImplementedError("the fused all-entity step serves the DOT scorers")
         _require_plain_model(model, "FusedAllEntityStepper", allow_penalty=True)
@@ -266,9 +270,18 @@ class FusedAllEntityStepper:
             self.mirror = torch.empty(self.E, self.d, dtype=torch.bfloat16, device=dev)
             lib.call("kgeb_to_bf16", lib.f32(self.ent.detach(), "table"), self.mirror.data_ptr(), self.ent.numel(),
                      lib.stream_ptr(self.ent))
+        self.triples = None
+        if onevsall_triples:
+            if rows % 2 != 0 or nnz_max != rows or rows > 8192:
+                raise ValueError("onevsall_triples: rows = nnz_max = 2 * batch <= 8192")
+            self.triples = torch.zeros(rows // 2, 3, **i64)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         if use_graph:
             self._capture()
+
+    def set_triples(self, triples: torch.Tensor):
+        """One copy (host pinned or device, non-blocking) of the batch's [batch, 3] int64 triples; see onevsall_triples."""
+        self.triples.copy_(triples, non_blocking=True)
 
     def input_views(self, buf: torch.Tensor) -> dict:
         """Typed views into a byte buffer with the layout of the static inputs (see __init__)."""
@@ -290,6 +303,10 @@ class FusedAllEntityStepper:
         model_id = lib.MODELS[self.model.model]
         ent, rel = self.ent.detach(), self.rel.detach()
         sh = self.shard
+        if self.triples is not None:
+            lib.call("kgeb_onevsall_batch_build", self.triples.data_ptr(), self.rows // 2, self.E, self.rel.shape[0],
+                     self.a_idx.data_ptr(), self.p_idx.data_ptr(), self.row_combine.data_ptr(), self.lab_off.data_ptr(),
+                     self.lab_col.data_ptr(), self.a_perm.data_ptr(), self.p_perm.data_ptr(), self.lab_perm.data_ptr(), st)
         # the gradient buffers are cleared on the third stream, beside the query build (joined where they are first used)
         cur = torch.cuda.current_stream()
         self.side2.wait_stream(cur)
@@ -684,6 +701,8 @@ class FusedAllEntityStepper:
 
     def set_inputs(self, a_idx, p_idx, row_combine, lab_off, lab_col, perms=None):
         """Copies one batch into the static input buffers (host pinned or device tensors; non-blocking)."""
+        if self.triples is not None:
+            raise RuntimeError("this stepper builds its batch from triples inside the captured step: use set_triples()")
         if perms is None:
             perms = self.batch_perms(a_idx, p_idx, lab_col)
         self.a_perm.copy_(perms[0], non_blocking=True)
@@ -718,6 +737,8 @@ class FusedAllEntityStepper:
 
     def set_packed(self, packed: torch.Tensor):
         """One H2D copy of a packed (pinned) host batch into the static inputs."""
+        if self.triples is not None:
+            raise RuntimeError("this stepper builds its batch from triples inside the captured step: use set_triples()")
         self.input_bytes.copy_(packed, non_blocking=True)
 
     def step(self) -> torch.Tensor:

@@ -467,3 +467,27 @@ def test_bf16_mirror_cache_belongs_to_a_storage_not_to_an_address(kb):
     assert float(kb.ops.bf16_mirror(b).float().min()) == 2.0
     b.mul_(2.0)                                   # in-place change: version counter
     assert float(kb.ops.bf16_mirror(b).float().min()) == 4.0
+
+
+@pytest.mark.parametrize("b", [1, 37, 1024, 4096])
+def test_onevsall_batch_build_equals_the_host_side_construction(kb, b):
+    """kgeb_onevsall_batch_build (first kernel of the captured 1vsAll step) against the torch construction it replaces:
+    queries, label CSR, row types and the three STABLE argsorts, bit for bit (hub entities / few relations: many ties)."""
+    e, r = 4_600_000, 7
+    gen = torch.Generator().manual_seed(b)
+    t = torch.stack((torch.randint(0, e, (b,), generator=gen), torch.randint(0, r, (b,), generator=gen),
+                     torch.randint(0, e, (b,), generator=gen)), 1).cuda()
+    t[: b // 3, 2] = t[0, 2]
+    n = 2 * b
+    i64 = lambda k: torch.full((k,), -7, dtype=torch.int64, device="cuda")     # noqa: E731
+    i32 = lambda k: torch.full((k,), -7, dtype=torch.int32, device="cuda")     # noqa: E731
+    a, p, lo, lc, rc, ap, pp, lp = i64(n), i64(n), i64(n + 1), i64(n), i32(n), i32(n), i32(n), i32(n)
+    kb.lib.call("kgeb_onevsall_batch_build", t.data_ptr(), b, e, r, a.data_ptr(), p.data_ptr(), rc.data_ptr(), lo.data_ptr(),
+                lc.data_ptr(), ap.data_ptr(), pp.data_ptr(), lp.data_ptr(), kb.lib.stream_ptr(t))
+    s_, p_, o_ = t[:, 0], t[:, 1], t[:, 2]
+    want_a, want_p, want_l = torch.cat((s_, o_)), torch.cat((p_, p_)), torch.cat((o_, s_))
+    z = torch.zeros(b, dtype=torch.int32, device="cuda")
+    sp = kb.trainer.FusedAllEntityStepper.sort_perm
+    assert torch.equal(a, want_a) and torch.equal(p, want_p) and torch.equal(lc, want_l)
+    assert torch.equal(rc, torch.cat((z, z + 1))) and torch.equal(lo, torch.arange(n + 1, device="cuda"))
+    assert torch.equal(ap, sp(want_a)) and torch.equal(pp, sp(want_p)) and torch.equal(lp, sp(want_l, n))
