@@ -204,7 +204,8 @@ class FusedAllEntityStepper:
         # ... and NO gradient buffer at all when the step's sparse rows fit the touched-row machinery: Adagrad runs in the
         # flush of the dTable tile kernel (kgeb_fused_bwd_update), the <= 8192 rows that also get label / query-side rows
         # are parked and updated by a row kernel.  Saves the store and the read-back of an [E, d] gradient per step.
-        self.fuse_update = (self.seq and rows + max(nnz_max, 1) <= lib.load().kgeb_touched_capacity()
+        # (d % 32 == 0: whole 32-column boxes only -- the dimensions this flow has been run at: 64, 128, 256)
+        self.fuse_update = (self.seq and self.d % 32 == 0 and rows + max(nnz_max, 1) <= lib.load().kgeb_touched_capacity()
                             and os.environ.get("KGEB_NO_FUSED_UPDATE", "0") in ("", "0"))
         if dp_group is not None and dp_p2p:
             self._setup_p2p(dp_group, n_e, n_r, dev)      # gradients live in peer-mapped (symmetric) memory
@@ -838,7 +839,8 @@ class RowShardedAllEntityStepper:
         # query-side rows of other owners ("not mine") and is the only row zeroed per step.  fp32 tiles: two cleared buffers.
         self.one_buffer = math_mode == lib.MATH_BF16 and self.d % 16 == 0 and self.d <= 256
         # ... or none: Adagrad in the flush of the tile kernel, touched rows by a row kernel (see FusedAllEntityStepper)
-        self.fuse_update = (self.one_buffer and self.n_loc > 0 and rows + nz <= lib.load().kgeb_touched_capacity()
+        self.fuse_update = (self.one_buffer and self.d % 32 == 0 and self.n_loc > 0
+                            and rows + nz <= lib.load().kgeb_touched_capacity()
                             and os.environ.get("KGEB_NO_FUSED_UPDATE", "0") in ("", "0"))
         if self.fuse_update:
             self.touched = _TouchedRows(self.n_loc, rows + nz, self.d, rows, nz, dev)

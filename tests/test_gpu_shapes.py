@@ -290,14 +290,15 @@ def test_touched_rows_numbering(kb):
     assert np.array_equal(t.slot_b.cpu().numpy(), wb)
 
 
-@pytest.mark.parametrize("loss", ["kl", "bce"])
-def test_adagrad_in_the_table_gradient_kernel_equals_the_separate_pass(kb, loss, monkeypatch):
+@pytest.mark.parametrize("loss,d", [("kl", 128), ("bce", 128), ("kl", 64), ("bce", 256)])
+def test_adagrad_in_the_table_gradient_kernel_equals_the_separate_pass(kb, loss, d, monkeypatch):
     """kgeb_fused_bwd_update + kgeb_touched_update (Adagrad applied by the flush of the dense table-gradient kernel; rows
     that also get label / query-side rows finished by a row kernel) against the same step with a stored gradient buffer
     and kgeb_adagrad_dense: rows outside the touched set get the same gradient bits and an update term within a few ulp
     (MUFU sqrt / rcp in the tile kernel), touched rows agree to rounding (dense + (labels + query side) instead of
-    (dense + labels) + query side; IEEE arithmetic in the row kernel)."""
-    e, r, d, b = 140_000, 50, 128, 256
+    (dense + labels) + query side; IEEE arithmetic in the row kernel).  d = 64: two of the four column parts have no box;
+    d = 256: two boxes per part and no A operand in tensor memory."""
+    e, r, b = 140_000 * 128 // d, 50, 256
     torch.manual_seed(0)
     base = kb.KgeModel("distmult", e, r, d).cuda()
     mk = lambda m: kb.optim.create("Adagrad", m.parameters(), lr=0.2, initial_accumulator_value=0.1)   # noqa: E731
